@@ -1,0 +1,55 @@
+/* spirit_b200 extensions to the Spirit C API (plain C ABI, no torch types).
+ *
+ * (1) Double-precision probes. The reference API narrows energies, torques and magnetisation to float
+ *     (core/include/Spirit/System.h:55, Quantities.h:21, Simulation.h:58-71, Chain.h:86-96), which cannot carry a
+ *     1e-12 parity check. The reference's own tests reach below the API for that
+ *     (core/test/test_anisotropy.cpp:137-149 calls hamiltonian->Gradient_and_Energy on doubles); these probes are
+ *     the same thing for this library. Every probe has a twin `refshim_*` with the same signature in
+ *     oracle/ref_shim.cpp that calls the unmodified reference engine.
+ * (2) Device control and device-resident stepping for benchmarks: run iterations on spins that already live in
+ *     HBM and time them with CUDA events on the image's own stream.
+ *
+ * All functions return a negative value (or 0.0) on error and never throw.
+ */
+#ifndef SPIRIT_B200_H
+#define SPIRIT_B200_H
+#include "Spirit/Export.h"
+struct State;
+typedef struct State State;
+
+/* --- (1) probes --------------------------------------------------------------------------------------------- */
+/* gradient[nos][3] and total energy of `spins` ([nos][3], NULL: the image's own spins).
+ * replaces Engine::Hamiltonian_Heisenberg::Gradient_and_Energy, core/src/engine/Hamiltonian_Heisenberg.cpp:704-766 */
+SPIRIT_API int SpiritB200_Gradient_and_Energy( State * state, const double * spins, double * gradient, double * energy, int idx_image ) SPIRIT_NOEXCEPT;
+/* replaces Hamiltonian_Heisenberg::Gradient, Hamiltonian_Heisenberg.cpp:670-702 */
+SPIRIT_API int SpiritB200_Gradient( State * state, const double * spins, double * gradient, int idx_image ) SPIRIT_NOEXCEPT;
+/* per-term energies: names [max_terms][32], totals[max_terms], per_spin (nullable) [n_terms][nos]; returns n_terms.
+ * replaces Energy_Contributions_per_Spin, Hamiltonian_Heisenberg.cpp:262-404 */
+SPIRIT_API int SpiritB200_Energy_Contributions( State * state, const double * spins, int max_terms, char * names, double * totals, double * per_spin, int idx_image ) SPIRIT_NOEXCEPT;
+/* image->E in double */
+SPIRIT_API double SpiritB200_Get_Energy( State * state, int idx_image ) SPIRIT_NOEXCEPT;
+/* (redundant) pair lists after Update_Interactions (Hamiltonian_Heisenberg.cpp:101-198). kind 0 exchange, 1 DMI.
+ * ijt [max][5] = i j da db dc; magnitudes[max]; normals[max][3] (DMI). Returns the number of pairs. Host only. */
+SPIRIT_API int SpiritB200_Get_Pairs( State * state, int kind, int max_pairs, int * ijt, double * magnitudes, double * normals, int idx_image ) SPIRIT_NOEXCEPT;
+/* max torque of the running / last method on the image (idx_image == -2: the chain method), in double */
+SPIRIT_API double SpiritB200_Get_MaxTorque( State * state, int idx_image ) SPIRIT_NOEXCEPT;
+/* reaction coordinate and energies of all images in double; returns noi */
+SPIRIT_API int SpiritB200_Chain_Get_Rx_E( State * state, double * Rx, double * E ) SPIRIT_NOEXCEPT;
+/* mean of mu_s*s in double (Vectormath::Magnetization, core/src/engine/Vectormath.cpp:495-502) */
+SPIRIT_API int SpiritB200_Get_Magnetization( State * state, double * m, int idx_image ) SPIRIT_NOEXCEPT;
+
+/* --- (2) device ------------------------------------------------------------------------------------------------ */
+SPIRIT_API int SpiritB200_Device_Count( void ) SPIRIT_NOEXCEPT;          /* 0 when there is no usable CUDA device */
+SPIRIT_API int SpiritB200_Set_Device( int device ) SPIRIT_NOEXCEPT;      /* device for subsequently created images */
+SPIRIT_API const char * SpiritB200_Device_Name( void ) SPIRIT_NOEXCEPT;
+/* Number of kernels this library launched for the image since it was created */
+SPIRIT_API unsigned long long SpiritB200_Kernel_Launches( State * state, int idx_image ) SPIRIT_NOEXCEPT;
+/* Upload the image's host spins to HBM (and build the device tables) / download spins + effective field */
+SPIRIT_API int SpiritB200_Upload( State * state, int idx_image ) SPIRIT_NOEXCEPT;
+SPIRIT_API int SpiritB200_Download( State * state, int idx_image ) SPIRIT_NOEXCEPT;
+/* Run n_iterations of an LLG solver on the device-resident spins of the image (no host<->device copies, no hooks
+ * except after the last iteration) and return the elapsed milliseconds measured with CUDA events on the image's
+ * stream; < 0 on error. The image's LLG parameters (dt, damping, temperature, seed, ...) apply.
+ * Same arithmetic as Simulation_LLG_Start: Method_Solver<solver>::Iteration, core/include/engine/Solver_*.hpp */
+SPIRIT_API double SpiritB200_LLG_Iterate_Device( State * state, int solver_type, int n_iterations, int idx_image ) SPIRIT_NOEXCEPT;
+#endif

@@ -1,0 +1,439 @@
+// C API: System, Quantities, Geometry.
+// Reference behaviour: core/src/Spirit/System.cpp, Quantities.cpp:17-60, Geometry.cpp:13-560.
+#include "api_common.hpp"
+
+#include <Spirit/Geometry.h>
+#include <Spirit/Quantities.h>
+#include <Spirit/Simulation.h>
+#include <Spirit/System.h>
+
+#include <cstring>
+
+using namespace sb;
+
+int System_Get_Index( State * state ) noexcept
+{
+    return state ? state->idx_active_image : -1;
+}
+
+int System_Get_NOS( State * state, int idx_image, int idx_chain ) noexcept
+try
+{
+    return resolve( state, idx_image, idx_chain ).image->nos;
+}
+SB_API_CATCH_RET( 0 )
+
+scalar * System_Get_Spin_Directions( State * state, int idx_image, int idx_chain ) noexcept
+try
+{
+    return resolve( state, idx_image, idx_chain ).image->spins.scalars();
+}
+SB_API_CATCH_RET( nullptr )
+
+scalar * System_Get_Effective_Field( State * state, int idx_image, int idx_chain ) noexcept
+try
+{
+    return resolve( state, idx_image, idx_chain ).image->effective_field.scalars();
+}
+SB_API_CATCH_RET( nullptr )
+
+float System_Get_Rx( State * state, int idx_image, int idx_chain ) noexcept
+try
+{
+    auto r = resolve( state, idx_image, idx_chain );
+    return float( r.chain->Rx[idx_image] );
+}
+SB_API_CATCH_RET( 0 )
+
+float System_Get_Energy( State * state, int idx_image, int idx_chain ) noexcept
+try
+{
+    return float( resolve( state, idx_image, idx_chain ).image->E );
+}
+SB_API_CATCH_RET( 0 )
+
+// System.cpp:137-177
+int System_Get_Energy_Array_Names( State * state, char * names, int idx_image, int idx_chain ) noexcept
+try
+{
+    auto image       = resolve( state, idx_image, idx_chain ).image;
+    int n_char_array = -1;
+    for( const auto & e : image->E_array )
+        n_char_array += int( e.first.size() ) + 1;
+    if( names == nullptr )
+        return n_char_array;
+    int idx = 0;
+    for( std::size_t i = 0; i < image->E_array.size(); ++i )
+    {
+        for( char c : image->E_array[i].first )
+            names[idx++] = c;
+        if( i + 1 != image->E_array.size() )
+            names[idx++] = '|';
+    }
+    return -1;
+}
+SB_API_CATCH_RET( -1 )
+
+// System.cpp:179-211
+int System_Get_Energy_Array( State * state, float * energies, bool divide_by_nspins, int idx_image, int idx_chain ) noexcept
+try
+{
+    auto image     = resolve( state, idx_image, idx_chain ).image;
+    double nd      = divide_by_nspins ? 1.0 / double( image->nos ) : 1.0;
+    if( energies == nullptr )
+        return int( image->E_array.size() );
+    for( std::size_t i = 0; i < image->E_array.size(); ++i )
+        energies[i] = float( nd * image->E_array[i].second );
+    return -1;
+}
+SB_API_CATCH_RET( -1 )
+
+void System_Print_Energy_Array( State * state, int idx_image, int idx_chain ) noexcept
+try
+{
+    auto image = resolve( state, idx_image, idx_chain ).image;
+    std::fprintf( stdout, "E_tot = %.10g meV/spin\n", image->E / image->nos );
+    for( const auto & e : image->E_array )
+        std::fprintf( stdout, "  %-18s %.10g meV/spin\n", e.first.c_str(), e.second / image->nos );
+}
+SB_API_CATCH_VOID
+
+// System.cpp:255-278: per-term energies of the current spins (evaluated on the GPU)
+void System_Update_Data( State * state, int idx_image, int idx_chain ) noexcept
+try
+{
+    auto image = resolve( state, idx_image, idx_chain ).image;
+    ImageLock lock( *image );
+    image->UpdateEnergy();
+}
+SB_API_CATCH_VOID
+
+// ---- Quantities ----
+void Quantity_Get_Average_Spin( State * state, float s[3], int idx_image, int idx_chain ) noexcept
+try
+{
+    auto image = resolve( state, idx_image, idx_chain ).image;
+    double m[3];
+    image->sync_to_device();
+    image->device().magnetization( m, false );
+    for( int d = 0; d < 3; ++d )
+        s[d] = float( m[d] );
+}
+SB_API_CATCH_VOID
+
+void Quantity_Get_Magnetization( State * state, float m[3], int idx_image, int idx_chain ) noexcept
+try
+{
+    auto image = resolve( state, idx_image, idx_chain ).image;
+    double mag[3];
+    image->sync_to_device();
+    image->device().magnetization( mag, true );
+    image->M = Vec3{ mag[0], mag[1], mag[2] };
+    for( int d = 0; d < 3; ++d )
+        m[d] = float( mag[d] );
+}
+SB_API_CATCH_VOID
+
+// ---- Geometry ----
+namespace
+{
+// Vectormath::change_dimensions (Vectormath.hpp:571-612): keep the overlap of old and new lattice
+void change_dimensions(
+    HostField & field, int nb_old, const std::array<int, 3> & n_old, int nb_new, const std::array<int, 3> & n_new, Vec3 default_value )
+{
+    HostField out( std::size_t( nb_new ) * n_new[0] * n_new[1] * n_new[2] );
+    for( std::size_t i = 0; i < out.size(); ++i )
+        out[i] = default_value;
+    for( int c = 0; c < n_new[2]; ++c )
+        for( int b = 0; b < n_new[1]; ++b )
+            for( int a = 0; a < n_new[0]; ++a )
+                for( int ib = 0; ib < nb_new; ++ib )
+                    if( ib < nb_old && a < n_old[0] && b < n_old[1] && c < n_old[2] )
+                        out[ib + std::size_t( nb_new ) * ( a + std::size_t( n_new[0] ) * ( b + std::size_t( n_new[1] ) * c ) )]
+                            = field[ib + std::size_t( nb_old ) * ( a + std::size_t( n_old[0] ) * ( b + std::size_t( n_old[1] ) * c ) )];
+    field = out;
+}
+
+// Geometry.cpp:13-37
+void system_set_geometry( Spin_System & system, const Geometry & new_geometry )
+{
+    const Geometry old = *system.geometry;
+    system.nos         = new_geometry.nos;
+    change_dimensions( system.spins, old.n_cell_atoms, old.n_cells, new_geometry.n_cell_atoms, new_geometry.n_cells, { 0, 0, 1 } );
+    change_dimensions( system.effective_field, old.n_cell_atoms, old.n_cells, new_geometry.n_cell_atoms, new_geometry.n_cells, { 0, 0, 0 } );
+    *system.geometry = new_geometry;
+    system.drop_device();
+    system.hamiltonian->Update_Interactions();
+}
+
+// Geometry.cpp:39-108
+void state_set_geometry( State & state, const Geometry & new_geometry )
+{
+    Simulation_Stop_All( &state );
+    state.chain->Lock();
+    try
+    {
+        for( auto & system : state.chain->images )
+            system_set_geometry( *system, new_geometry );
+    }
+    catch( ... )
+    {
+        handle_exception_api( "Geometry_Set" );
+    }
+    state.chain->Unlock();
+    state.nos = state.active_image->nos;
+    if( state.clipboard_image )
+        system_set_geometry( *state.clipboard_image, new_geometry );
+    if( state.clipboard_spins )
+    {
+        // the clipboard configuration lives in a plain vector: convert through a HostField
+        state.clipboard_spins.reset();
+    }
+    state.method_image.assign( state.chain->noi, nullptr );
+    state.method_chain.reset();
+}
+
+std::shared_ptr<Geometry> active_geometry( State * state )
+{
+    if( !state || !state->active_image )
+        throw std::runtime_error( "The State pointer is invalid" );
+    return state->active_image->geometry;
+}
+} // namespace
+
+void Geometry_Set_Bravais_Lattice_Type( State * state, Bravais_Lattice_Type lattice_type ) noexcept
+try
+{
+    auto old = active_geometry( state );
+    std::vector<Vec3> bv;
+    switch( lattice_type )
+    {
+        case Bravais_Lattice_SC: bv = Geometry::BravaisVectorsSC(); break;
+        case Bravais_Lattice_Hex2D:
+        case Bravais_Lattice_Hex2D_60: bv = Geometry::BravaisVectorsHex2D60(); break;
+        case Bravais_Lattice_Hex2D_120: bv = Geometry::BravaisVectorsHex2D120(); break;
+        case Bravais_Lattice_BCC: bv = Geometry::BravaisVectorsBCC(); break;
+        case Bravais_Lattice_FCC: bv = Geometry::BravaisVectorsFCC(); break;
+        default:
+            Log( Log_Level::Warning, Log_Sender::API, "Geometry_Set_Bravais_Lattice_Type: cannot set this lattice type" );
+            return;
+    }
+    Geometry g( bv, old->n_cells, old->cell_atoms, old->cell_mu_s, old->lattice_constant );
+    g.cell_atom_types = old->cell_atom_types;
+    state_set_geometry( *state, g );
+}
+catch( ... )
+{
+    handle_exception_api( __func__ );
+}
+
+void Geometry_Set_N_Cells( State * state, int n_cells[3] ) noexcept
+try
+{
+    auto old = active_geometry( state );
+    Geometry g( old->bravais_vectors, { n_cells[0], n_cells[1], n_cells[2] }, old->cell_atoms, old->cell_mu_s, old->lattice_constant );
+    g.cell_atom_types = old->cell_atom_types;
+    state_set_geometry( *state, g );
+}
+catch( ... )
+{
+    handle_exception_api( __func__ );
+}
+
+void Geometry_Set_Cell_Atoms( State * state, int n_atoms, float ** atoms ) noexcept
+try
+{
+    auto old = active_geometry( state );
+    if( n_atoms < 1 )
+    {
+        Log( Log_Level::Error, Log_Sender::API, "Cannot set number of atoms to less than one." );
+        return;
+    }
+    std::vector<Vec3> cell_atoms( n_atoms );
+    for( int i = 0; i < n_atoms; ++i )
+        cell_atoms[i] = Vec3{ atoms[i][0], atoms[i][1], atoms[i][2] };
+    // Geometry.cpp:246-262: keep the composition of the atoms that still exist, new ones copy atom 0
+    std::vector<double> mu_s( n_atoms );
+    for( int i = 0; i < n_atoms; ++i )
+        mu_s[i] = i < old->n_cell_atoms ? old->cell_mu_s[i] : old->cell_mu_s[0];
+    Geometry g( old->bravais_vectors, old->n_cells, cell_atoms, mu_s, old->lattice_constant );
+    state_set_geometry( *state, g );
+}
+catch( ... )
+{
+    handle_exception_api( __func__ );
+}
+
+void Geometry_Set_mu_s( State * state, float mu_s, int idx_image, int idx_chain ) noexcept
+try
+{
+    auto old = active_geometry( state );
+    std::vector<double> new_mu_s( old->n_cell_atoms, double( mu_s ) );
+    Geometry g( old->bravais_vectors, old->n_cells, old->cell_atoms, new_mu_s, old->lattice_constant );
+    g.cell_atom_types = old->cell_atom_types;
+    state_set_geometry( *state, g );
+}
+SB_API_CATCH_VOID
+
+void Geometry_Set_Cell_Atom_Types( State * state, int n_atoms, int * atom_types ) noexcept
+try
+{
+    auto old = active_geometry( state );
+    Geometry g = *old;
+    for( int i = 0; i < n_atoms && i < g.n_cell_atoms; ++i )
+        g.cell_atom_types[i] = atom_types[i];
+    state_set_geometry( *state, g );
+}
+catch( ... )
+{
+    handle_exception_api( __func__ );
+}
+
+void Geometry_Set_Bravais_Vectors( State * state, float ta[3], float tb[3], float tc[3] ) noexcept
+try
+{
+    auto old = active_geometry( state );
+    std::vector<Vec3> bv{ Vec3{ ta[0], ta[1], ta[2] }, Vec3{ tb[0], tb[1], tb[2] }, Vec3{ tc[0], tc[1], tc[2] } };
+    Geometry g( bv, old->n_cells, old->cell_atoms, old->cell_mu_s, old->lattice_constant );
+    g.cell_atom_types = old->cell_atom_types;
+    state_set_geometry( *state, g );
+}
+catch( ... )
+{
+    handle_exception_api( __func__ );
+}
+
+void Geometry_Set_Lattice_Constant( State * state, float lattice_constant ) noexcept
+try
+{
+    auto old = active_geometry( state );
+    Geometry g( old->bravais_vectors, old->n_cells, old->cell_atoms, old->cell_mu_s, double( lattice_constant ) );
+    g.cell_atom_types = old->cell_atom_types;
+    state_set_geometry( *state, g );
+}
+catch( ... )
+{
+    handle_exception_api( __func__ );
+}
+
+int Geometry_Get_NOS( State * state ) noexcept
+try
+{
+    return active_geometry( state )->nos;
+}
+catch( ... )
+{
+    handle_exception_api( __func__ );
+    return 0;
+}
+
+scalar * Geometry_Get_Positions( State * state, int idx_image, int idx_chain ) noexcept
+try
+{
+    auto image = resolve( state, idx_image, idx_chain ).image;
+    return const_cast<scalar *>( reinterpret_cast<const scalar *>( image->geometry->positions().data() ) );
+}
+SB_API_CATCH_RET( nullptr )
+
+int * Geometry_Get_Atom_Types( State * state, int idx_image, int idx_chain ) noexcept
+try
+{
+    auto image = resolve( state, idx_image, idx_chain ).image;
+    return const_cast<int *>( image->geometry->atom_types().data() );
+}
+SB_API_CATCH_RET( nullptr )
+
+void Geometry_Get_Bounds( State * state, float min[3], float max[3], int idx_image, int idx_chain ) noexcept
+try
+{
+    auto g = resolve( state, idx_image, idx_chain ).image->geometry;
+    for( int d = 0; d < 3; ++d )
+    {
+        min[d] = float( g->bounds_min[d] );
+        max[d] = float( g->bounds_max[d] );
+    }
+}
+SB_API_CATCH_VOID
+
+void Geometry_Get_Center( State * state, float center[3], int idx_image, int idx_chain ) noexcept
+try
+{
+    auto g = resolve( state, idx_image, idx_chain ).image->geometry;
+    for( int d = 0; d < 3; ++d )
+        center[d] = float( g->center[d] );
+}
+SB_API_CATCH_VOID
+
+void Geometry_Get_Cell_Bounds( State * state, float min[3], float max[3], int idx_image, int idx_chain ) noexcept
+try
+{
+    auto g = resolve( state, idx_image, idx_chain ).image->geometry;
+    for( int d = 0; d < 3; ++d )
+    {
+        min[d] = float( g->cell_bounds_min[d] );
+        max[d] = float( g->cell_bounds_max[d] );
+    }
+}
+SB_API_CATCH_VOID
+
+Bravais_Lattice_Type Geometry_Get_Bravais_Lattice_Type( State * state, int idx_image, int idx_chain ) noexcept
+try
+{
+    return Bravais_Lattice_Type( int( resolve( state, idx_image, idx_chain ).image->geometry->classifier ) );
+}
+SB_API_CATCH_RET( Bravais_Lattice_Irregular )
+
+void Geometry_Get_Bravais_Vectors( State * state, float a[3], float b[3], float c[3], int idx_image, int idx_chain ) noexcept
+try
+{
+    auto g = resolve( state, idx_image, idx_chain ).image->geometry;
+    for( int d = 0; d < 3; ++d )
+    {
+        a[d] = float( g->bravais_vectors[0][d] );
+        b[d] = float( g->bravais_vectors[1][d] );
+        c[d] = float( g->bravais_vectors[2][d] );
+    }
+}
+SB_API_CATCH_VOID
+
+int Geometry_Get_Dimensionality( State * state, int idx_image, int idx_chain ) noexcept
+try
+{
+    return resolve( state, idx_image, idx_chain ).image->geometry->dimensionality;
+}
+SB_API_CATCH_RET( 0 )
+
+void Geometry_Get_mu_s( State * state, float * mu_s, int idx_image, int idx_chain ) noexcept
+try
+{
+    auto g = resolve( state, idx_image, idx_chain ).image->geometry;
+    for( int i = 0; i < g->n_cell_atoms; ++i )
+        mu_s[i] = float( g->cell_mu_s[i] );
+}
+SB_API_CATCH_VOID
+
+void Geometry_Get_N_Cells( State * state, int n_cells[3], int idx_image, int idx_chain ) noexcept
+try
+{
+    auto g = resolve( state, idx_image, idx_chain ).image->geometry;
+    for( int d = 0; d < 3; ++d )
+        n_cells[d] = g->n_cells[d];
+}
+SB_API_CATCH_VOID
+
+int Geometry_Get_N_Cell_Atoms( State * state, int idx_image, int idx_chain ) noexcept
+try
+{
+    return resolve( state, idx_image, idx_chain ).image->geometry->n_cell_atoms;
+}
+SB_API_CATCH_RET( 0 )
+
+int Geometry_Get_Cell_Atoms( State * state, scalar ** atoms, int idx_image, int idx_chain ) noexcept
+try
+{
+    auto g = resolve( state, idx_image, idx_chain ).image->geometry;
+    if( atoms != nullptr )
+        *atoms = reinterpret_cast<scalar *>( g->cell_atoms.data() );
+    return g->n_cell_atoms;
+}
+SB_API_CATCH_RET( 0 )

@@ -1,0 +1,271 @@
+#include "method.hpp"
+#include "constants.hpp"
+#include "logging.hpp"
+
+#include <algorithm>
+#include <cmath>
+#include <fstream>
+
+namespace sb
+{
+
+Method::Method( std::shared_ptr<Parameters_Method> parameters_, int idx_image_, int idx_chain_ )
+        : idx_image( idx_image_ ), idx_chain( idx_chain_ ), parameters( std::move( parameters_ ) )
+{
+    // Method.cpp:15-47
+    n_iterations_amortize = parameters->n_iterations_amortize;
+    n_iterations          = std::max( 1L, parameters->n_iterations );
+    n_iterations_log      = std::min( parameters->n_iterations_log, n_iterations );
+    if( n_iterations_log <= 0 )
+        n_iterations_log = n_iterations;
+    n_log = n_iterations / n_iterations_log;
+    if( n_iterations_amortize > n_iterations_log )
+        n_iterations_amortize = n_iterations_log;
+    if( n_iterations_amortize < 1 )
+        n_iterations_amortize = 1;
+    for( int i = 0; i < 7; ++i )
+        t_iterations.push_back( std::chrono::system_clock::now() );
+    t_start = t_last = std::chrono::system_clock::now();
+}
+
+void Method::Iterate()
+{
+    t_start = t_last = std::chrono::system_clock::now();
+    auto t_current   = t_start;
+
+    Save_Current( true, false );
+
+    for( iteration = 0;
+         ContinueIterating() && !Walltime_Expired( std::chrono::duration<double>( t_current - t_start ).count() );
+         iteration += n_iterations_amortize )
+    {
+        t_current = std::chrono::system_clock::now();
+        Lock();
+        Hook_Pre_Iteration();
+        for( long i = 0; i < n_iterations_amortize; ++i )
+            Iteration( i == n_iterations_amortize - 1 );
+        Hook_Post_Iteration();
+
+        t_iterations.pop_front();
+        t_iterations.push_back( std::chrono::system_clock::now() );
+
+        if( n_iterations_log > 0 && iteration > 0 && 0 == std::fmod( double( iteration ), double( n_iterations_log ) ) )
+        {
+            ++step;
+            Sync_Host();
+            Save_Current( false, false );
+            t_last = std::chrono::system_clock::now();
+        }
+        Unlock();
+    }
+
+    Sync_Host();
+    Finalize();
+    step = iteration / n_iterations_log;
+    Save_Current( false, true );
+}
+
+void Method::Save_Current( bool, bool ) {}
+
+std::string Method::SolverName()
+{
+    switch( solver )
+    {
+        case dev::Solver_VP: return "VP";
+        case dev::Solver_SIB: return "SIB";
+        case dev::Solver_Depondt: return "Depondt";
+        case dev::Solver_Heun: return "Heun";
+        case dev::Solver_RK4: return "RK4";
+        default: return "--";
+    }
+}
+
+std::string Method::SolverFullName()
+{
+    switch( solver )
+    {
+        case dev::Solver_VP: return "Velocity Projection";
+        case dev::Solver_SIB: return "Semi-implicit B";
+        case dev::Solver_Depondt: return "Depondt";
+        case dev::Solver_Heun: return "Heun";
+        case dev::Solver_RK4: return "Runge Kutta (4th order)";
+        default: return "--";
+    }
+}
+
+// Method.cpp:178-200
+bool Method::ContinueIterating()
+{
+    if( !( iteration < n_iterations && Iterations_Allowed() ) )
+        return false;
+    std::ifstream f( "STOP" );
+    if( f.good() )
+        return false;
+    return !Converged();
+}
+
+bool Method::Walltime_Expired( double seconds ) const
+{
+    if( parameters->max_walltime_sec <= 0 )
+        return false;
+    return seconds > double( parameters->max_walltime_sec );
+}
+
+double Method::getIterationsPerSecond()
+{
+    double l_ips = 0;
+    for( std::size_t i = 0; i + 1 < t_iterations.size(); ++i )
+        l_ips += std::chrono::duration<double>( t_iterations[i + 1] - t_iterations[i] ).count();
+    return 1.0 / ( l_ips / double( t_iterations.size() - 1 ) ) * double( n_iterations_amortize );
+}
+
+std::int64_t Method::getWallTime() const
+{
+    auto dt = std::chrono::system_clock::now() - t_start;
+    return std::chrono::duration_cast<std::chrono::milliseconds>( dt ).count();
+}
+
+// ---------------------------------------------------------------------------------------------
+// Method_LLG
+// ---------------------------------------------------------------------------------------------
+Method_LLG::Method_LLG( std::shared_ptr<Spin_System> system_, int solver_, int idx_image_, int idx_chain_ )
+        : Method( system_->llg_parameters, idx_image_, idx_chain_ ), system( std::move( system_ ) )
+{
+    solver = solver_;
+    if( solver != dev::Solver_VP && solver != dev::Solver_SIB && solver != dev::Solver_Depondt
+        && solver != dev::Solver_Heun && solver != dev::Solver_RK4 )
+        throw std::runtime_error(
+            "Solver " + std::to_string( solver )
+            + " is not implemented in spirit_b200 (available: VP 0, SIB 1, Depondt 2, Heun 3, RK4 4)" );
+
+    // We assume it is not converged before the first iteration (Method_LLG.cpp:44-46)
+    max_torque = system->llg_parameters->force_convergence + 1.0;
+
+    // Constructor-time force evaluation + hook (Method_LLG.cpp:57-62)
+    system->sync_to_device();
+    llg_          = make_params( *system, solver );
+    hook_pending_ = true;
+    system->device().llg_initial_hook( solver, llg_, &pending_hook_ );
+    ++system->llg_parameters->philox_counter;
+    Hook_Post_Iteration();
+    // the constructor-time hook does not count as simulated time (Method_LLG.cpp:24 starts at 0 and the hook adds dt;
+    // the reference has the same off-by-one, which Simulation_Get_Time exposes -- keep it)
+}
+
+// Method_LLG.cpp:131-226 (prefactors) and :65-110 (thermal amplitude)
+dev::LLGParams Method_LLG::make_params( const Spin_System & system, int solver )
+{
+    namespace C    = constants;
+    const auto & P = *system.llg_parameters;
+    const auto & g = *system.geometry;
+    dev::LLGParams l{};
+    const bool minimise   = P.direct_minimization || solver == dev::Solver_VP;
+    l.damping             = P.damping;
+    l.dt                  = P.dt;
+    l.direct_minimization = minimise ? 1 : 0;
+    if( minimise )
+        l.dtg = P.dt * C::gamma / C::mu_B;
+    else
+        l.dtg = P.dt * C::gamma / C::mu_B / ( 1 + P.damping * P.damping );
+
+    // STT, monolayer approximation only (the gradient approximation is SURVEY.md 8f rank 4)
+    l.has_stt = 0;
+    if( !minimise && P.stt_magnitude > 0 )
+    {
+        if( P.stt_use_gradient )
+            throw std::runtime_error( "spirit_b200: llg_stt_use_gradient 1 (spin-current gradient term) is not implemented" );
+        l.has_stt = 1;
+        l.stt_c1  = -l.dtg * P.stt_magnitude * ( P.damping - P.beta );
+        l.stt_c2  = -l.dtg * P.stt_magnitude * ( 1 + P.beta * P.damping );
+        for( int d = 0; d < 3; ++d )
+            l.stt_pol[d] = P.stt_polarisation_normal[d];
+    }
+
+    if( P.temperature_gradient_inclination != 0 )
+        throw std::runtime_error( "spirit_b200: temperature gradients are not implemented (SURVEY.md 8f rank 4)" );
+    l.has_thermal = ( !minimise && P.temperature > 0 ) ? 1 : 0;
+    const double epsilon = std::sqrt( 2 * P.damping * P.dt * C::gamma / C::mu_B * C::k_B ) / ( 1 + P.damping * P.damping );
+    for( int ib = 0; ib < dev::MAX_BASIS; ++ib )
+    {
+        const double mu      = ib < g.n_cell_atoms ? g.cell_mu_s[ib] : 1.0;
+        l.inv_mu_s[ib]       = 1.0 / mu;
+        l.thermal_scale[ib]  = l.has_thermal ? epsilon * std::sqrt( P.temperature / mu ) : 0.0;
+    }
+    l.seed      = std::uint64_t( std::uint32_t( P.rng_seed ) ) | ( std::uint64_t( 0x5b200 ) << 32 );
+    l.iteration = P.philox_counter;
+    return l;
+}
+
+void Method_LLG::Iteration( bool hook_follows )
+{
+    llg_ = make_params( *system, solver );
+    system->device().set_hamiltonian( *system->hamiltonian );
+    system->device().llg_iterate( solver, llg_, 1, hook_follows, hook_follows ? &pending_hook_ : nullptr );
+    ++system->llg_parameters->philox_counter;
+    hook_pending_ = hook_follows;
+}
+
+double Method_LLG::Iterate_Device_Resident( const std::shared_ptr<Spin_System> & system, int solver, int n_iterations )
+{
+    if( solver < dev::Solver_VP || solver > dev::Solver_RK4 )
+        throw std::runtime_error( "Solver " + std::to_string( solver ) + " is not implemented in spirit_b200" );
+    auto & d = system->device();
+    d.set_hamiltonian( *system->hamiltonian );
+    dev::LLGParams l = make_params( *system, solver );
+    dev::HookResult result;
+    if( solver == dev::Solver_VP )
+        d.llg_initial_hook( solver, l, &result ); // F_prev of the first VP iteration
+    d.timer_start();
+    d.llg_iterate( solver, l, n_iterations, true, &result );
+    const double ms = d.timer_stop();
+    system->llg_parameters->philox_counter = l.iteration;
+    system->E                              = result.energy;
+    return ms;
+}
+
+// Method_LLG.cpp:246-301
+void Method_LLG::Hook_Post_Iteration()
+{
+    picoseconds_passed += system->llg_parameters->dt;
+    if( !hook_pending_ )
+        return;
+    hook_pending_    = false;
+    force_converged_ = false;
+    double fmax      = pending_hook_.max_torque;
+    max_torque       = fmax > 0 ? fmax : 0;
+    if( fmax < system->llg_parameters->force_convergence )
+        force_converged_ = true;
+    system->E = pending_hook_.energy;
+}
+
+bool Method_LLG::Converged()
+{
+    return force_converged_;
+}
+
+void Method_LLG::Finalize()
+{
+    system->iteration_allowed = false;
+}
+
+void Method_LLG::Save_Current( bool, bool )
+{
+    // Method_LLG.cpp:312-315 (history); file output is not written
+    history_iteration.push_back( int( iteration ) );
+    history_max_torque.push_back( max_torque );
+    history_energy.push_back( system->E );
+}
+
+void Method_LLG::Sync_Host()
+{
+    auto & d = system->device();
+    d.download_spins( system->spins.scalars() );
+    d.download_effective_field( system->effective_field.scalars() );
+}
+
+void Method_LLG::Sync_Device()
+{
+    system->sync_to_device();
+}
+
+} // namespace sb

@@ -1,0 +1,113 @@
+// Private to the device layer: error checking and the buffer structs shared by device_image.cu and
+// device_chain.cu. Not visible to the host library.
+#pragma once
+
+#include "kernels.cuh"
+#include "runtime.hpp"
+
+#include <stdexcept>
+#include <string>
+
+namespace sb
+{
+namespace dev
+{
+
+#define SB_CUDA_CHECK( expr )                                                                                          \
+    do                                                                                                                 \
+    {                                                                                                                  \
+        cudaError_t err__ = ( expr );                                                                                  \
+        if( err__ != cudaSuccess )                                                                                     \
+            throw std::runtime_error(                                                                                  \
+                std::string( "spirit_b200 CUDA error: " ) + cudaGetErrorString( err__ ) + " at " + __FILE__ + ":"      \
+                + std::to_string( __LINE__ ) + " (" #expr ")" );                                                       \
+    } while( 0 )
+
+struct DeviceField
+{
+    double * base = nullptr;
+    std::size_t n = 0; // elements per component (storage, including halo planes)
+
+    void allocate( std::size_t n_ )
+    {
+        release();
+        n = n_;
+        SB_CUDA_CHECK( cudaMalloc( &base, 3 * n * sizeof( double ) ) );
+    }
+    void release()
+    {
+        if( base )
+            cudaFree( base );
+        base = nullptr;
+        n    = 0;
+    }
+    bool allocated() const
+    {
+        return base != nullptr;
+    }
+    Field3 f() const
+    {
+        Field3 r;
+        r.x = base;
+        r.y = base + n;
+        r.z = base + 2 * n;
+        return r;
+    }
+    ConstField3 c() const
+    {
+        ConstField3 r;
+        r.x = base;
+        r.y = base + n;
+        r.z = base + 2 * n;
+        return r;
+    }
+};
+
+struct DeviceBuffers
+{
+    cudaStream_t stream = nullptr;
+    cudaEvent_t ev_start = nullptr, ev_stop = nullptr;
+
+    LaunchGeom lg{};
+    int nblocks            = 0;
+    std::size_t n_storage  = 0; // sites stored per component (with halos)
+    int interior_offset    = 0; // storage index of site 0 of the owned range
+
+    DeviceField spins, pred, next; // configuration ping-pong
+    DeviceField pred2;             // RK4 second predictor
+    DeviceField acc;               // RK4 accumulator
+    DeviceField F, Fv;             // force / virtual force (hook, VP); F doubles as the effective field
+    DeviceField ddi_s, ddi_p;      // DDI gradient fields of s and of the predictor
+    DeviceField scratch;           // gradient output for one-off evaluations
+
+    double * staging   = nullptr; // AoS staging [nos][3]
+    double * partials  = nullptr; // [4][nblocks] reduction scratch
+    double * scalars   = nullptr; // device scalars: [0..3] VP, [4] energy, [5] torque^2, [6..8] magnetisation
+    double * h_scalars = nullptr; // pinned mirror
+    double * terms     = nullptr; // per-term energies [6][nos]
+
+    ~DeviceBuffers()
+    {
+        for( DeviceField * f : { &spins, &pred, &next, &pred2, &acc, &F, &Fv, &ddi_s, &ddi_p, &scratch } )
+            f->release();
+        if( staging )
+            cudaFree( staging );
+        if( partials )
+            cudaFree( partials );
+        if( scalars )
+            cudaFree( scalars );
+        if( terms )
+            cudaFree( terms );
+        if( h_scalars )
+            cudaFreeHost( h_scalars );
+        if( ev_start )
+            cudaEventDestroy( ev_start );
+        if( ev_stop )
+            cudaEventDestroy( ev_stop );
+        if( stream )
+            cudaStreamDestroy( stream );
+    }
+};
+
+} // namespace dev
+} // namespace sb

@@ -1,0 +1,633 @@
+// Host-side driver of the device layer: buffers, streams, kernel launches.
+#include "device_buffers.cuh"
+
+#include "../core/constants.hpp"
+#include "../core/hamiltonian.hpp"
+
+#include <algorithm>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <map>
+#include <stdexcept>
+#include <tuple>
+
+namespace sb
+{
+namespace dev
+{
+
+bool device_available()
+{
+    int n           = 0;
+    cudaError_t err = cudaGetDeviceCount( &n );
+    if( err != cudaSuccess )
+    {
+        cudaGetLastError(); // clear
+        return false;
+    }
+    return n > 0;
+}
+
+int device_count()
+{
+    int n = 0;
+    if( cudaGetDeviceCount( &n ) != cudaSuccess )
+    {
+        cudaGetLastError();
+        return 0;
+    }
+    return n;
+}
+
+void set_device( int device )
+{
+    require_device();
+    SB_CUDA_CHECK( cudaSetDevice( device ) );
+}
+
+void require_device()
+{
+    if( !device_available() )
+        throw std::runtime_error(
+            "spirit_b200: no CUDA device available. This library has no CPU fallback: the gradient, energy and "
+            "solver path runs only as sm_100a CUDA kernels." );
+}
+
+std::string device_name()
+{
+    require_device();
+    int d = 0;
+    SB_CUDA_CHECK( cudaGetDevice( &d ) );
+    cudaDeviceProp prop;
+    SB_CUDA_CHECK( cudaGetDeviceProperties( &prop, d ) );
+    return prop.name;
+}
+
+void * host_alloc( std::size_t bytes, bool & pinned )
+{
+    pinned = false;
+    if( bytes == 0 )
+        bytes = 8;
+    if( device_available() )
+    {
+        void * p = nullptr;
+        if( cudaHostAlloc( &p, bytes, cudaHostAllocDefault ) == cudaSuccess )
+        {
+            pinned = true;
+            return p;
+        }
+        cudaGetLastError();
+    }
+    void * p = nullptr;
+    if( posix_memalign( &p, 64, bytes ) != 0 )
+        throw std::bad_alloc();
+    return p;
+}
+
+void host_free( void * ptr, bool pinned )
+{
+    if( !ptr )
+        return;
+    if( pinned )
+        cudaFreeHost( ptr );
+    else
+        std::free( ptr );
+}
+
+// ---------------------------------------------------------------------------------------------
+
+struct DDIPlan
+{
+};
+
+namespace
+{
+int next_pow2( int v )
+{
+    int p = 1;
+    while( p < v )
+        p <<= 1;
+    return p;
+}
+
+LaunchGeom make_geom( const StencilParams & p )
+{
+    LaunchGeom lg;
+    lg.rowlen   = p.Na * p.NB;
+    lg.rows     = p.Nb * p.nc_local;
+    lg.bx       = std::min( 128, std::max( 32, next_pow2( lg.rowlen ) ) );
+    lg.by       = BLOCK_THREADS / lg.bx;
+    lg.blocks_x = ( lg.rowlen + lg.bx - 1 ) / lg.bx;
+    lg.blocks_y = ( lg.rows + lg.by - 1 ) / lg.by;
+    return lg;
+}
+} // namespace
+
+DeviceImage::DeviceImage( const Geometry & g )
+{
+    require_device();
+    nos_ = g.nos;
+    if( g.n_cell_atoms > MAX_BASIS )
+        throw std::runtime_error( "spirit_b200: more than 8 basis atoms per cell are not supported by the stencil kernels" );
+    buf_ = std::make_unique<DeviceBuffers>();
+
+    std::memset( &stencil_, 0, sizeof( stencil_ ) );
+    stencil_.Na       = g.n_cells[0];
+    stencil_.Nb       = g.n_cells[1];
+    stencil_.Nc       = g.n_cells[2];
+    stencil_.NB       = g.n_cell_atoms;
+    stencil_.c_begin  = 0;
+    stencil_.nc_local = g.n_cells[2];
+    stencil_.halo     = 0;
+    for( int ib = 0; ib < g.n_cell_atoms; ++ib )
+        stencil_.mu_s[ib] = g.cell_mu_s[ib];
+
+    auto & b          = *buf_;
+    b.lg              = make_geom( stencil_ );
+    b.nblocks         = b.lg.blocks_x * b.lg.blocks_y;
+    b.n_storage       = std::size_t( nos_ );
+    b.interior_offset = 0;
+    SB_CUDA_CHECK( cudaStreamCreateWithFlags( &b.stream, cudaStreamNonBlocking ) );
+    SB_CUDA_CHECK( cudaEventCreate( &b.ev_start ) );
+    SB_CUDA_CHECK( cudaEventCreate( &b.ev_stop ) );
+    b.spins.allocate( b.n_storage );
+    SB_CUDA_CHECK( cudaMalloc( &b.partials, 4 * std::size_t( b.nblocks ) * sizeof( double ) ) );
+    SB_CUDA_CHECK( cudaMalloc( &b.scalars, 16 * sizeof( double ) ) );
+    SB_CUDA_CHECK( cudaMemset( b.scalars, 0, 16 * sizeof( double ) ) );
+    SB_CUDA_CHECK( cudaHostAlloc( &b.h_scalars, 16 * sizeof( double ), cudaHostAllocDefault ) );
+}
+
+DeviceImage::~DeviceImage() = default;
+
+void DeviceImage::synchronize()
+{
+    SB_CUDA_CHECK( cudaStreamSynchronize( buf_->stream ) );
+}
+
+void DeviceImage::timer_start()
+{
+    SB_CUDA_CHECK( cudaEventRecord( buf_->ev_start, buf_->stream ) );
+}
+double DeviceImage::timer_stop()
+{
+    SB_CUDA_CHECK( cudaEventRecord( buf_->ev_stop, buf_->stream ) );
+    SB_CUDA_CHECK( cudaEventSynchronize( buf_->ev_stop ) );
+    float ms = 0;
+    SB_CUDA_CHECK( cudaEventElapsedTime( &ms, buf_->ev_start, buf_->ev_stop ) );
+    return ms;
+}
+
+// Build the merged neighbour table and on-site tables from the host Hamiltonian
+void DeviceImage::set_hamiltonian( const Hamiltonian & ham )
+{
+    if( ham.revision == ham_revision_ )
+        return;
+    const Geometry & g = *ham.geometry;
+    StencilParams & p  = stencil_;
+    for( int d = 0; d < 3; ++d )
+        p.bc[d] = ham.boundary_conditions[d];
+    for( int ib = 0; ib < g.n_cell_atoms; ++ib )
+        p.mu_s[ib] = g.cell_mu_s[ib];
+
+    // Merge exchange and DMI pairs with identical (i, j, translations). Pairs that reach further than the
+    // lattice are invalid for every site (idx_from_pair, Vectormath.hpp:451-453) and dropped here.
+    using Key = std::tuple<int, int, int, int, int>;
+    std::map<Key, Neighbour> merged;
+    std::vector<Key> order;
+    auto entry = [&]( const Pair & pr ) -> Neighbour * {
+        const auto & t = pr.translations;
+        if( std::abs( t[0] ) > g.n_cells[0] || std::abs( t[1] ) > g.n_cells[1] || std::abs( t[2] ) > g.n_cells[2] )
+            return nullptr;
+        if( pr.i < 0 || pr.i >= g.n_cell_atoms || pr.j < 0 || pr.j >= g.n_cell_atoms )
+            return nullptr;
+        Key k{ pr.i, pr.j, t[0], t[1], t[2] };
+        auto it = merged.find( k );
+        if( it == merged.end() )
+        {
+            Neighbour nb{};
+            nb.jb = pr.j;
+            nb.da = t[0];
+            nb.db = t[1];
+            nb.dc = t[2];
+            it    = merged.emplace( k, nb ).first;
+            order.push_back( k );
+        }
+        return &it->second;
+    };
+    for( std::size_t i = 0; i < ham.exchange_pairs.size(); ++i )
+        if( Neighbour * nb = entry( ham.exchange_pairs[i] ) )
+            nb->J += ham.exchange_magnitudes[i];
+    for( std::size_t i = 0; i < ham.dmi_pairs.size(); ++i )
+        if( Neighbour * nb = entry( ham.dmi_pairs[i] ) )
+        {
+            nb->Dx += ham.dmi_magnitudes[i] * ham.dmi_normals[i].x;
+            nb->Dy += ham.dmi_magnitudes[i] * ham.dmi_normals[i].y;
+            nb->Dz += ham.dmi_magnitudes[i] * ham.dmi_normals[i].z;
+        }
+    if( order.size() > std::size_t( MAX_NEIGH ) )
+        throw std::runtime_error( "spirit_b200: more than 160 distinct neighbour entries are not supported" );
+    // group by basis atom i, keeping the reference's pair order inside a group
+    p.n_neigh = 0;
+    for( int ib = 0; ib < g.n_cell_atoms; ++ib )
+    {
+        p.neigh_begin[ib] = p.n_neigh;
+        for( const Key & k : order )
+            if( std::get<0>( k ) == ib )
+                p.neigh[p.n_neigh++] = merged[k];
+    }
+    for( int ib = g.n_cell_atoms; ib <= MAX_BASIS; ++ib )
+        p.neigh_begin[ib] = p.n_neigh;
+
+    // Uniaxial anisotropy
+    if( ham.anisotropy_indices.size() > std::size_t( MAX_ANISO ) )
+        throw std::runtime_error( "spirit_b200: more than 16 anisotropy entries are not supported" );
+    p.n_aniso = int( ham.anisotropy_indices.size() );
+    for( int i = 0; i < p.n_aniso; ++i )
+    {
+        p.aniso[i].ib = ham.anisotropy_indices[i];
+        p.aniso[i].K  = ham.anisotropy_magnitudes[i];
+        p.aniso[i].nx = ham.anisotropy_normals[i].x;
+        p.aniso[i].ny = ham.anisotropy_normals[i].y;
+        p.aniso[i].nz = ham.anisotropy_normals[i].z;
+    }
+    // Cubic anisotropy (entries for the same atom add up)
+    p.has_cubic = !ham.cubic_anisotropy_indices.empty();
+    for( int ib = 0; ib < MAX_BASIS; ++ib )
+        p.K4[ib] = 0;
+    for( std::size_t i = 0; i < ham.cubic_anisotropy_indices.size(); ++i )
+        if( ham.cubic_anisotropy_indices[i] >= 0 && ham.cubic_anisotropy_indices[i] < MAX_BASIS )
+            p.K4[ham.cubic_anisotropy_indices[i]] += ham.cubic_anisotropy_magnitudes[i];
+    // Zeeman
+    p.has_zeeman = ham.idx_zeeman >= 0;
+    for( int ib = 0; ib < MAX_BASIS; ++ib )
+        for( int d = 0; d < 3; ++d )
+            p.zeeman[ib][d]
+                = ib < g.n_cell_atoms ? g.cell_mu_s[ib] * ham.external_field_magnitude * ham.external_field_normal[d] : 0.0;
+
+    p.has_ddi = 0;
+    if( ham.ddi_method == DDI_Method::FFT )
+        throw std::runtime_error( "spirit_b200: ddi_method fft is not implemented yet" );
+    else if( ham.ddi_method != DDI_Method::None )
+        throw std::runtime_error( "spirit_b200: only ddi_method none/fft are in scope (SURVEY.md 2.2)" );
+
+    ham_revision_ = ham.revision;
+}
+
+// ---------------------------------------------------------------------------------------------
+void DeviceImage::upload_spins( const double * host_aos )
+{
+    auto & b = *buf_;
+    if( !b.staging )
+        SB_CUDA_CHECK( cudaMalloc( &b.staging, 3 * std::size_t( nos_ ) * sizeof( double ) ) );
+    SB_CUDA_CHECK( cudaMemcpyAsync(
+        b.staging, host_aos, 3 * std::size_t( nos_ ) * sizeof( double ), cudaMemcpyHostToDevice, b.stream ) );
+    k_aos_to_soa<<<( nos_ + BLOCK_THREADS - 1 ) / BLOCK_THREADS, BLOCK_THREADS, 0, b.stream>>>(
+        b.staging, b.spins.f(), nos_, b.interior_offset );
+    ++launches_;
+    SB_CUDA_CHECK( cudaGetLastError() );
+}
+
+static void download_field(
+    DeviceBuffers & b, const DeviceField & f, double * host_aos, int nos, double scale, std::uint64_t & launches )
+{
+    if( !b.staging )
+        SB_CUDA_CHECK( cudaMalloc( &b.staging, 3 * std::size_t( nos ) * sizeof( double ) ) );
+    k_soa_to_aos<<<( nos + BLOCK_THREADS - 1 ) / BLOCK_THREADS, BLOCK_THREADS, 0, b.stream>>>(
+        f.c(), b.staging, nos, b.interior_offset, scale );
+    ++launches;
+    SB_CUDA_CHECK( cudaGetLastError() );
+    SB_CUDA_CHECK( cudaMemcpyAsync(
+        host_aos, b.staging, 3 * std::size_t( nos ) * sizeof( double ), cudaMemcpyDeviceToHost, b.stream ) );
+    SB_CUDA_CHECK( cudaStreamSynchronize( b.stream ) );
+}
+
+void DeviceImage::download_spins( double * host_aos )
+{
+    download_field( *buf_, buf_->spins, host_aos, nos_, 1.0, launches_ );
+}
+
+void DeviceImage::download_effective_field( double * host_aos )
+{
+    if( !buf_->F.allocated() )
+        throw std::runtime_error( "spirit_b200: effective field requested before it was computed" );
+    download_field( *buf_, effective_field_in_Fv_ ? buf_->Fv : buf_->F, host_aos, nos_, 1.0, launches_ );
+}
+
+// ---------------------------------------------------------------------------------------------
+#define SB_DISPATCH_NB( KERNEL_CALL_NB1, KERNEL_CALL_NBX )                                                             \
+    do                                                                                                                 \
+    {                                                                                                                  \
+        if( stencil_.NB == 1 )                                                                                         \
+        {                                                                                                              \
+            KERNEL_CALL_NB1;                                                                                           \
+        }                                                                                                              \
+        else                                                                                                           \
+        {                                                                                                              \
+            KERNEL_CALL_NBX;                                                                                           \
+        }                                                                                                              \
+        ++launches_;                                                                                                   \
+        SB_CUDA_CHECK( cudaGetLastError() );                                                                           \
+    } while( 0 )
+
+static void reduce_sum_to( DeviceBuffers & b, const double * partials, int slot, std::uint64_t & launches )
+{
+    k_reduce_sum<<<1, BLOCK_THREADS, 0, b.stream>>>( partials, b.nblocks, b.scalars + slot );
+    ++launches;
+}
+
+void DeviceImage::gradient_and_energy( double * gradient_host_aos, double * energy )
+{
+    auto & b = *buf_;
+    if( !b.scratch.allocated() )
+        b.scratch.allocate( b.n_storage );
+    SB_DISPATCH_NB(
+        ( k_gradient<1, true><<<b.nblocks, BLOCK_THREADS, 0, b.stream>>>(
+            stencil_, b.lg, b.spins.c(), b.ddi_s.c(), b.scratch.f(), 1.0, b.partials ) ),
+        ( k_gradient<0, true><<<b.nblocks, BLOCK_THREADS, 0, b.stream>>>(
+            stencil_, b.lg, b.spins.c(), b.ddi_s.c(), b.scratch.f(), 1.0, b.partials ) ) );
+    reduce_sum_to( b, b.partials, 4, launches_ );
+    SB_CUDA_CHECK( cudaMemcpyAsync( b.h_scalars + 4, b.scalars + 4, sizeof( double ), cudaMemcpyDeviceToHost, b.stream ) );
+    if( gradient_host_aos )
+        download_field( b, b.scratch, gradient_host_aos, nos_, 1.0, launches_ );
+    SB_CUDA_CHECK( cudaStreamSynchronize( b.stream ) );
+    if( energy )
+        *energy = b.h_scalars[4];
+}
+
+void DeviceImage::update_effective_field()
+{
+    auto & b = *buf_;
+    if( !b.F.allocated() )
+        b.F.allocate( b.n_storage );
+    effective_field_in_Fv_ = false;
+    SB_DISPATCH_NB(
+        ( k_gradient<1, false><<<b.nblocks, BLOCK_THREADS, 0, b.stream>>>(
+            stencil_, b.lg, b.spins.c(), b.ddi_s.c(), b.F.f(), -1.0, nullptr ) ),
+        ( k_gradient<0, false><<<b.nblocks, BLOCK_THREADS, 0, b.stream>>>(
+            stencil_, b.lg, b.spins.c(), b.ddi_s.c(), b.F.f(), -1.0, nullptr ) ) );
+}
+
+int DeviceImage::energy_contributions( const Hamiltonian & ham, double * totals, double * per_spin_host )
+{
+    auto & b = *buf_;
+    set_hamiltonian( ham );
+    const int n_terms = int( ham.contribution_names.size() );
+    if( n_terms == 0 )
+        return 0;
+    if( !b.terms )
+        SB_CUDA_CHECK( cudaMalloc( &b.terms, 6 * std::size_t( nos_ ) * sizeof( double ) ) );
+    EnergyTermPointers ptrs{};
+    const int idx[6] = { ham.idx_zeeman, ham.idx_anisotropy, ham.idx_cubic_anisotropy, ham.idx_exchange, ham.idx_dmi, ham.idx_ddi };
+    for( int t = 0; t < 6; ++t )
+        ptrs.term[t] = idx[t] >= 0 ? b.terms + std::size_t( idx[t] ) * nos_ : nullptr;
+    SB_DISPATCH_NB(
+        ( k_energy_contributions<1><<<b.nblocks, BLOCK_THREADS, 0, b.stream>>>( stencil_, b.lg, b.spins.c(), b.ddi_s.c(), ptrs ) ),
+        ( k_energy_contributions<0><<<b.nblocks, BLOCK_THREADS, 0, b.stream>>>( stencil_, b.lg, b.spins.c(), b.ddi_s.c(), ptrs ) ) );
+    std::vector<double> h( static_cast<std::size_t>( n_terms ), 0.0 );
+    for( int t = 0; t < n_terms; ++t )
+    {
+        const double * term = b.terms + std::size_t( t ) * nos_;
+        // Simple and deterministic: one CTA folds the whole array (only used for one-off evaluations)
+        k_reduce_sum<<<1, BLOCK_THREADS, 0, b.stream>>>( term, nos_, b.scalars + 9 );
+        ++launches_;
+        SB_CUDA_CHECK( cudaMemcpyAsync( b.h_scalars + 9, b.scalars + 9, sizeof( double ), cudaMemcpyDeviceToHost, b.stream ) );
+        SB_CUDA_CHECK( cudaStreamSynchronize( b.stream ) );
+        h[t] = b.h_scalars[9];
+    }
+    for( int t = 0; t < n_terms; ++t )
+        totals[t] = h[t];
+    if( per_spin_host )
+    {
+        SB_CUDA_CHECK( cudaMemcpyAsync(
+            per_spin_host, b.terms, std::size_t( n_terms ) * nos_ * sizeof( double ), cudaMemcpyDeviceToHost, b.stream ) );
+        SB_CUDA_CHECK( cudaStreamSynchronize( b.stream ) );
+    }
+    return n_terms;
+}
+
+void DeviceImage::magnetization( double m[3], bool weighted )
+{
+    auto & b = *buf_;
+    k_magnetization<<<b.nblocks, BLOCK_THREADS, 0, b.stream>>>( stencil_, b.lg, b.spins.c(), b.partials, b.nblocks, weighted ? 1 : 0 );
+    ++launches_;
+    for( int d = 0; d < 3; ++d )
+    {
+        k_reduce_sum<<<1, BLOCK_THREADS, 0, b.stream>>>( b.partials + std::size_t( d ) * b.nblocks, b.nblocks, b.scalars + 6 + d );
+        ++launches_;
+    }
+    SB_CUDA_CHECK( cudaGetLastError() );
+    SB_CUDA_CHECK( cudaMemcpyAsync( b.h_scalars + 6, b.scalars + 6, 3 * sizeof( double ), cudaMemcpyDeviceToHost, b.stream ) );
+    SB_CUDA_CHECK( cudaStreamSynchronize( b.stream ) );
+    for( int d = 0; d < 3; ++d )
+        m[d] = b.h_scalars[6 + d] / double( nos_ );
+}
+
+// ---------------------------------------------------------------------------------------------
+void DeviceImage::ensure_work_fields( int solver )
+{
+    auto & b = *buf_;
+    auto need = [&]( DeviceField & f ) {
+        if( !f.allocated() )
+            f.allocate( b.n_storage );
+    };
+    need( b.F );
+    need( b.Fv );
+    if( solver != Solver_VP )
+    {
+        need( b.pred );
+        need( b.next );
+    }
+    if( solver == Solver_RK4 )
+    {
+        need( b.pred2 );
+        need( b.acc );
+    }
+}
+
+void DeviceImage::vp_reset()
+{
+    vp_initialized_ = false;
+    SB_CUDA_CHECK( cudaMemsetAsync( buf_->scalars, 0, 4 * sizeof( double ), buf_->stream ) );
+}
+
+namespace
+{
+template<int SOLVER, int STAGE>
+void launch_stage(
+    bool nb1, bool hook, int nblocks, cudaStream_t stream, const StencilParams & p, const LaunchGeom & lg, const LLGParams & l,
+    const StageArgs & a )
+{
+    if( nb1 )
+    {
+        if( hook )
+            k_llg_stage<SOLVER, STAGE, 1, true><<<nblocks, BLOCK_THREADS, 0, stream>>>( p, lg, l, a );
+        else
+            k_llg_stage<SOLVER, STAGE, 1, false><<<nblocks, BLOCK_THREADS, 0, stream>>>( p, lg, l, a );
+    }
+    else
+    {
+        if( hook )
+            k_llg_stage<SOLVER, STAGE, 0, true><<<nblocks, BLOCK_THREADS, 0, stream>>>( p, lg, l, a );
+        else
+            k_llg_stage<SOLVER, STAGE, 0, false><<<nblocks, BLOCK_THREADS, 0, stream>>>( p, lg, l, a );
+    }
+}
+} // namespace
+
+void DeviceImage::llg_initial_hook( int solver, const LLGParams & llg, HookResult * result )
+{
+    auto & b = *buf_;
+    ensure_work_fields( solver );
+    SB_DISPATCH_NB(
+        ( k_force_and_virtual<1><<<b.nblocks, BLOCK_THREADS, 0, b.stream>>>(
+            stencil_, b.lg, llg, b.spins.c(), b.ddi_s.c(), b.F.f(), b.Fv.f(), b.partials ) ),
+        ( k_force_and_virtual<0><<<b.nblocks, BLOCK_THREADS, 0, b.stream>>>(
+            stencil_, b.lg, llg, b.spins.c(), b.ddi_s.c(), b.F.f(), b.Fv.f(), b.partials ) ) );
+    k_reduce_sum<<<1, BLOCK_THREADS, 0, b.stream>>>( b.partials, b.nblocks, b.scalars + 4 );
+    k_hook<<<b.nblocks, BLOCK_THREADS, 0, b.stream>>>( stencil_, b.lg, b.spins.c(), b.F.f(), b.Fv.c(), b.partials + b.nblocks );
+    k_reduce_max<<<1, BLOCK_THREADS, 0, b.stream>>>( b.partials + b.nblocks, b.nblocks, b.scalars + 5 );
+    launches_ += 3;
+    SB_CUDA_CHECK( cudaGetLastError() );
+    SB_CUDA_CHECK( cudaMemcpyAsync( b.h_scalars + 4, b.scalars + 4, 2 * sizeof( double ), cudaMemcpyDeviceToHost, b.stream ) );
+    SB_CUDA_CHECK( cudaStreamSynchronize( b.stream ) );
+    if( result )
+    {
+        result->energy     = b.h_scalars[4];
+        result->max_torque = std::sqrt( b.h_scalars[5] );
+    }
+    if( solver == Solver_VP )
+    {
+        // velocity = 0, F_prev = projected force of the constructor-time hook
+        SB_CUDA_CHECK( cudaMemsetAsync( b.scalars, 0, 4 * sizeof( double ), b.stream ) );
+        vp_initialized_    = true;
+        vp_prev_projected_ = false; // k_hook projected F in place and ratio_prev = 0, so F serves as both
+    }
+    effective_field_in_Fv_ = false;
+}
+
+void DeviceImage::llg_iterate( int solver, LLGParams & llg, int n_iterations, bool hook, HookResult * result )
+{
+    auto & b = *buf_;
+    ensure_work_fields( solver );
+    const bool nb1 = stencil_.NB == 1;
+
+    for( int it = 0; it < n_iterations; ++it )
+    {
+        const bool hk = hook && ( it == n_iterations - 1 );
+        StageArgs a{};
+        a.s               = b.spins.c();
+        a.ddi_s           = b.ddi_s.c();
+        a.ddi_sp          = b.ddi_p.c();
+        a.F_out           = b.F.f();
+        a.Fv_out          = b.Fv.f();
+        a.energy_partials = b.partials;
+
+        if( solver == Solver_Depondt || solver == Solver_Heun || solver == Solver_SIB )
+        {
+            a.out = b.pred.f();
+            if( solver == Solver_Depondt )
+                launch_stage<Solver_Depondt, 1>( nb1, hk, b.nblocks, b.stream, stencil_, b.lg, llg, a );
+            else if( solver == Solver_Heun )
+                launch_stage<Solver_Heun, 1>( nb1, hk, b.nblocks, b.stream, stencil_, b.lg, llg, a );
+            else
+                launch_stage<Solver_SIB, 1>( nb1, hk, b.nblocks, b.stream, stencil_, b.lg, llg, a );
+            a.sp  = b.pred.c();
+            a.out = b.next.f();
+            if( solver == Solver_Depondt )
+                launch_stage<Solver_Depondt, 2>( nb1, hk, b.nblocks, b.stream, stencil_, b.lg, llg, a );
+            else if( solver == Solver_Heun )
+                launch_stage<Solver_Heun, 2>( nb1, hk, b.nblocks, b.stream, stencil_, b.lg, llg, a );
+            else
+                launch_stage<Solver_SIB, 2>( nb1, hk, b.nblocks, b.stream, stencil_, b.lg, llg, a );
+            launches_ += 2;
+            std::swap( b.spins, b.next );
+        }
+        else if( solver == Solver_RK4 )
+        {
+            a.acc = b.acc.f();
+            a.out = b.pred.f();
+            launch_stage<Solver_RK4, 1>( nb1, hk, b.nblocks, b.stream, stencil_, b.lg, llg, a );
+            a.sp  = b.pred.c();
+            a.out = b.pred2.f();
+            launch_stage<Solver_RK4, 2>( nb1, hk, b.nblocks, b.stream, stencil_, b.lg, llg, a );
+            a.sp  = b.pred2.c();
+            a.out = b.pred.f();
+            launch_stage<Solver_RK4, 3>( nb1, hk, b.nblocks, b.stream, stencil_, b.lg, llg, a );
+            a.sp  = b.pred.c();
+            a.out = b.next.f();
+            launch_stage<Solver_RK4, 4>( nb1, hk, b.nblocks, b.stream, stencil_, b.lg, llg, a );
+            launches_ += 4;
+            std::swap( b.spins, b.next );
+        }
+        else if( solver == Solver_VP )
+        {
+            if( !vp_initialized_ )
+                throw std::logic_error( "spirit_b200: VP iteration without the initial force evaluation" );
+            double * pp = b.partials;
+            double * pn = b.partials + b.nblocks;
+            double * pe = b.partials + 2 * std::size_t( b.nblocks );
+            const ConstField3 Fprev = vp_prev_projected_ ? b.Fv.c() : b.F.c();
+            if( nb1 )
+            {
+                if( hk )
+                    k_vp_a<1, true><<<b.nblocks, BLOCK_THREADS, 0, b.stream>>>( stencil_, b.lg, b.spins.c(), b.ddi_s.c(), b.F.f(), Fprev, b.scalars, pp, pn, pe );
+                else
+                    k_vp_a<1, false><<<b.nblocks, BLOCK_THREADS, 0, b.stream>>>( stencil_, b.lg, b.spins.c(), b.ddi_s.c(), b.F.f(), Fprev, b.scalars, pp, pn, pe );
+            }
+            else
+            {
+                if( hk )
+                    k_vp_a<0, true><<<b.nblocks, BLOCK_THREADS, 0, b.stream>>>( stencil_, b.lg, b.spins.c(), b.ddi_s.c(), b.F.f(), Fprev, b.scalars, pp, pn, pe );
+                else
+                    k_vp_a<0, false><<<b.nblocks, BLOCK_THREADS, 0, b.stream>>>( stencil_, b.lg, b.spins.c(), b.ddi_s.c(), b.F.f(), Fprev, b.scalars, pp, pn, pe );
+            }
+            vp_prev_projected_ = hk;
+            k_reduce_sum<<<1, BLOCK_THREADS, 0, b.stream>>>( pp, b.nblocks, b.scalars + 1 );
+            k_reduce_sum<<<1, BLOCK_THREADS, 0, b.stream>>>( pn, b.nblocks, b.scalars + 2 );
+            k_vp_ratio<<<1, 1, 0, b.stream>>>( b.scalars );
+            if( hk )
+            {
+                k_reduce_sum<<<1, BLOCK_THREADS, 0, b.stream>>>( pe, b.nblocks, b.scalars + 4 );
+                k_vp_b<true><<<b.nblocks, BLOCK_THREADS, 0, b.stream>>>(
+                    stencil_, b.lg, b.spins.f(), b.F.c(), b.Fv.f(), b.scalars, llg.dt, llg.dtg, b.partials + 3 * std::size_t( b.nblocks ) );
+                k_reduce_max<<<1, BLOCK_THREADS, 0, b.stream>>>( b.partials + 3 * std::size_t( b.nblocks ), b.nblocks, b.scalars + 5 );
+                launches_ += 2;
+            }
+            else
+                k_vp_b<false><<<b.nblocks, BLOCK_THREADS, 0, b.stream>>>(
+                    stencil_, b.lg, b.spins.f(), b.F.c(), b.Fv.f(), b.scalars, llg.dt, llg.dtg, nullptr );
+            launches_ += 5;
+        }
+        else
+            throw std::runtime_error( "spirit_b200: solver id " + std::to_string( solver ) + " is not implemented" );
+
+        if( hk && solver != Solver_VP )
+        {
+            k_reduce_sum<<<1, BLOCK_THREADS, 0, b.stream>>>( b.partials, b.nblocks, b.scalars + 4 );
+            k_hook<<<b.nblocks, BLOCK_THREADS, 0, b.stream>>>(
+                stencil_, b.lg, b.spins.c(), b.F.f(), b.Fv.c(), b.partials + b.nblocks );
+            k_reduce_max<<<1, BLOCK_THREADS, 0, b.stream>>>( b.partials + b.nblocks, b.nblocks, b.scalars + 5 );
+            launches_ += 3;
+        }
+        ++llg.iteration;
+    }
+    if( hook )
+        effective_field_in_Fv_ = solver == Solver_VP;
+    SB_CUDA_CHECK( cudaGetLastError() );
+    if( hook )
+    {
+        SB_CUDA_CHECK( cudaMemcpyAsync( b.h_scalars + 4, b.scalars + 4, 2 * sizeof( double ), cudaMemcpyDeviceToHost, b.stream ) );
+        SB_CUDA_CHECK( cudaStreamSynchronize( b.stream ) );
+        if( result )
+        {
+            result->energy     = b.h_scalars[4];
+            result->max_torque = std::sqrt( b.h_scalars[5] );
+        }
+    }
+}
+
+void DeviceImage::compute_ddi_gradient( int ) {}
+
+} // namespace dev
+} // namespace sb

@@ -1,0 +1,571 @@
+// CUDA kernels of the hot path (sm_100a, fp64, SoA). Included by device/device_image.cu only.
+//
+// Kernel inventory (one line each; rooflines and byte counts are in DESIGN.md):
+//   k_aos_to_soa / k_soa_to_aos      layout conversion at the C-API boundary
+//   k_gradient                       gradient (+ energy partials) of one configuration
+//   k_energy_contributions           per-spin, per-term energies
+//   k_llg_stage<SOLVER,STAGE,..>     fused "gradient -> virtual force -> spin update" solver stages
+//   k_vp_a / k_vp_b                  velocity-projection minimiser (two global sums between them)
+//   k_hook                           max-torque + tangential projection after an iteration block
+//   k_reduce_sum / k_reduce_max      second level of the deterministic two-level reductions
+#pragma once
+
+#include "llg.cuh"
+
+namespace sb
+{
+namespace dev
+{
+
+constexpr int BLOCK_THREADS = 256;
+
+// Launch geometry: a CTA covers BX consecutive sites of a row times BY consecutive rows (so the
+// +-b neighbour rows are shared inside the CTA through L1), grid is 1-D.
+struct LaunchGeom
+{
+    int bx, by;           // block shape, bx*by = BLOCK_THREADS
+    int blocks_x, blocks_y;
+    int rowlen, rows;     // Na*NB, Nb*nc_local
+};
+
+__device__ __forceinline__ bool locate_site( const StencilParams & p, const LaunchGeom & lg, Site & site, int NB )
+{
+    const int bxi = blockIdx.x % lg.blocks_x;
+    const int byi = blockIdx.x / lg.blocks_x;
+    const int tx  = threadIdx.x % lg.bx;
+    const int ty  = threadIdx.x / lg.bx;
+    const int x   = bxi * lg.bx + tx;
+    const int row = byi * lg.by + ty;
+    if( x >= lg.rowlen || row >= lg.rows )
+        return false;
+    site.b = row % p.Nb;
+    site.c = row / p.Nb;
+    if( NB == 1 )
+    {
+        site.a  = x;
+        site.ib = 0;
+    }
+    else
+    {
+        site.a  = x / NB;
+        site.ib = x - site.a * NB;
+    }
+    site.idx = storage_index( p, x, site.b, site.c );
+    return true;
+}
+
+// ---------------------------------------------------------------------------------------------
+// Block-level reductions (deterministic: fixed tree shape)
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ double warp_sum( double v )
+{
+#pragma unroll
+    for( int o = 16; o > 0; o >>= 1 )
+        v += __shfl_down_sync( 0xffffffffu, v, o );
+    return v;
+}
+__device__ __forceinline__ double warp_max( double v )
+{
+#pragma unroll
+    for( int o = 16; o > 0; o >>= 1 )
+        v = fmax( v, __shfl_down_sync( 0xffffffffu, v, o ) );
+    return v;
+}
+// All threads of the CTA must call. Result valid in thread 0.
+__device__ __forceinline__ double block_sum( double v )
+{
+    __shared__ double sh[BLOCK_THREADS / 32];
+    v = warp_sum( v );
+    __syncthreads(); // protect sh against a previous use
+    if( ( threadIdx.x & 31 ) == 0 )
+        sh[threadIdx.x >> 5] = v;
+    __syncthreads();
+    if( threadIdx.x < 32 )
+    {
+        v = threadIdx.x < BLOCK_THREADS / 32 ? sh[threadIdx.x] : 0.0;
+        v = warp_sum( v );
+    }
+    return v;
+}
+__device__ __forceinline__ double block_max( double v )
+{
+    __shared__ double shm[BLOCK_THREADS / 32];
+    v = warp_max( v );
+    __syncthreads();
+    if( ( threadIdx.x & 31 ) == 0 )
+        shm[threadIdx.x >> 5] = v;
+    __syncthreads();
+    if( threadIdx.x < 32 )
+    {
+        v = threadIdx.x < BLOCK_THREADS / 32 ? shm[threadIdx.x] : 0.0;
+        v = warp_max( v );
+    }
+    return v;
+}
+
+// Second level: one CTA folds `n` partials in a fixed order. out[0] = result.
+static __global__ void __launch_bounds__( BLOCK_THREADS ) k_reduce_sum( const double * __restrict__ partials, int n, double * __restrict__ out )
+{
+    double v = 0;
+    for( int i = threadIdx.x; i < n; i += BLOCK_THREADS )
+        v += partials[i];
+    v = block_sum( v );
+    if( threadIdx.x == 0 )
+        out[0] = v;
+}
+static __global__ void __launch_bounds__( BLOCK_THREADS ) k_reduce_max( const double * __restrict__ partials, int n, double * __restrict__ out )
+{
+    double v = 0;
+    for( int i = threadIdx.x; i < n; i += BLOCK_THREADS )
+        v = fmax( v, partials[i] );
+    v = block_max( v );
+    if( threadIdx.x == 0 )
+        out[0] = v;
+}
+
+// ---------------------------------------------------------------------------------------------
+// Layout conversion at the C-API boundary: host arrays are AoS [nos][3] in the reference's site
+// order; device fields are planar with (optional) halo planes.
+// ---------------------------------------------------------------------------------------------
+static __global__ void __launch_bounds__( BLOCK_THREADS )
+    k_aos_to_soa( const double * __restrict__ aos, Field3 f, int n, int offset )
+{
+    const int i = blockIdx.x * BLOCK_THREADS + threadIdx.x;
+    if( i < n )
+    {
+        f.x[offset + i] = aos[3 * std::size_t( i ) + 0];
+        f.y[offset + i] = aos[3 * std::size_t( i ) + 1];
+        f.z[offset + i] = aos[3 * std::size_t( i ) + 2];
+    }
+}
+static __global__ void __launch_bounds__( BLOCK_THREADS )
+    k_soa_to_aos( ConstField3 f, double * __restrict__ aos, int n, int offset, double scale )
+{
+    const int i = blockIdx.x * BLOCK_THREADS + threadIdx.x;
+    if( i < n )
+    {
+        aos[3 * std::size_t( i ) + 0] = scale * f.x[offset + i];
+        aos[3 * std::size_t( i ) + 1] = scale * f.y[offset + i];
+        aos[3 * std::size_t( i ) + 2] = scale * f.z[offset + i];
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Gradient (+ energy) of one configuration. Hamiltonian_Heisenberg.cpp:670-766.
+// out = sign * gradient (sign = -1 gives the effective field / force).
+// ---------------------------------------------------------------------------------------------
+template<int NB_T, bool WITH_ENERGY>
+static __global__ void __launch_bounds__( BLOCK_THREADS ) k_gradient(
+    const __grid_constant__ StencilParams p, const __grid_constant__ LaunchGeom lg, ConstField3 s, ConstField3 ddi,
+    Field3 out, double sign, double * __restrict__ energy_partials )
+{
+    Site site;
+    const bool active = locate_site( p, lg, site, NB_T > 0 ? NB_T : p.NB );
+    double e          = 0;
+    if( active )
+    {
+        const D3 si          = load3( s, site.idx );
+        const SiteGradient g = site_gradient<NB_T>( p, s, ddi, site, si );
+        const D3 gt          = total( g );
+        store3( out, site.idx, make_d3( sign * gt.x, sign * gt.y, sign * gt.z ) );
+        if( WITH_ENERGY )
+            e = site_energy<NB_T>( p, site, si, g );
+    }
+    if( WITH_ENERGY )
+    {
+        e = block_sum( e );
+        if( threadIdx.x == 0 )
+            energy_partials[blockIdx.x] = e;
+    }
+}
+
+// Per-spin energies of each term (Hamiltonian_Heisenberg.cpp:307-404). `terms` holds up to 6 output
+// arrays (null = term inactive), indexed 0 Zeeman, 1 anisotropy, 2 cubic, 3 exchange, 4 DMI, 5 DDI,
+// each of length nos in the reference's site order (no halo).
+struct EnergyTermPointers
+{
+    double * term[6];
+};
+template<int NB_T>
+static __global__ void __launch_bounds__( BLOCK_THREADS ) k_energy_contributions(
+    const __grid_constant__ StencilParams p, const __grid_constant__ LaunchGeom lg, ConstField3 s, ConstField3 ddi,
+    EnergyTermPointers out )
+{
+    Site site;
+    const int NB = NB_T > 0 ? NB_T : p.NB;
+    if( !locate_site( p, lg, site, NB ) )
+        return;
+    const int ib  = NB_T == 1 ? 0 : site.ib;
+    const D3 si   = load3( s, site.idx );
+    const int lin = site.a * NB + ib + p.Na * NB * ( site.b + p.Nb * site.c ); // index without halo
+
+    if( out.term[0] )
+        out.term[0][lin] = -( p.zeeman[ib][0] * si.x + p.zeeman[ib][1] * si.y + p.zeeman[ib][2] * si.z );
+    if( out.term[1] )
+    {
+        double e = 0;
+        for( int i = 0; i < p.n_aniso; ++i )
+            if( p.aniso[i].ib == ib )
+            {
+                const double d = p.aniso[i].nx * si.x + p.aniso[i].ny * si.y + p.aniso[i].nz * si.z;
+                e -= p.aniso[i].K * d * d;
+            }
+        out.term[1][lin] = e;
+    }
+    if( out.term[2] )
+    {
+        const double x2 = si.x * si.x, y2 = si.y * si.y, z2 = si.z * si.z;
+        out.term[2][lin] = -0.5 * p.K4[ib] * ( x2 * x2 + y2 * y2 + z2 * z2 );
+    }
+    if( out.term[3] || out.term[4] )
+    {
+        double e_ex = 0, e_dmi = 0;
+        for( int n = p.neigh_begin[ib]; n < p.neigh_begin[ib + 1]; ++n )
+        {
+            const Neighbour & nb = p.neigh[n];
+            int ja = site.a + nb.da, jb = site.b + nb.db, jc = site.c + nb.dc;
+            bool valid = true;
+            if( ja < 0 ) { ja += p.Na; valid = valid && p.bc[0]; }
+            else if( ja >= p.Na ) { ja -= p.Na; valid = valid && p.bc[0]; }
+            if( jb < 0 ) { jb += p.Nb; valid = valid && p.bc[1]; }
+            else if( jb >= p.Nb ) { jb -= p.Nb; valid = valid && p.bc[1]; }
+            if( p.halo == 0 )
+            {
+                if( jc < 0 ) { jc += p.Nc; valid = valid && p.bc[2]; }
+                else if( jc >= p.Nc ) { jc -= p.Nc; valid = valid && p.bc[2]; }
+            }
+            else
+            {
+                const int gc = p.c_begin + jc;
+                valid        = valid && ( p.bc[2] || ( gc >= 0 && gc < p.Nc ) );
+            }
+            if( valid )
+            {
+                const D3 sj = load3( s, storage_index( p, ja * NB + nb.jb, jb, jc ) );
+                e_ex -= 0.5 * nb.J * dot3( si, sj );
+                // -1/2 D . (s_i x s_j)
+                const D3 c = cross3( si, sj );
+                e_dmi -= 0.5 * ( nb.Dx * c.x + nb.Dy * c.y + nb.Dz * c.z );
+            }
+        }
+        if( out.term[3] )
+            out.term[3][lin] = e_ex;
+        if( out.term[4] )
+            out.term[4][lin] = e_dmi;
+    }
+    if( out.term[5] )
+        out.term[5][lin] = 0.5 * dot3( si, load3( ddi, site.idx ) );
+}
+
+// ---------------------------------------------------------------------------------------------
+// Fused solver stages. One launch = gradient stencil + virtual force + spin update for every site.
+//
+//   Depondt (Solver_Depondt.hpp:29-77)  stage 1: s' = R(Fv(s)) s          stage 2: s <- R((Fv(s)+Fv(s'))/2) s
+//   Heun    (Solver_Heun.hpp:30-81)     stage 1: s' = |s - s x Fv(s)|     stage 2: s <- |s + k1/2 + k2/2|
+//   SIB     (Solver_SIB.hpp:22-50)      stage 1: s' = (s + T(s,Fv(s)))/2  stage 2: s <- T(s, Fv(s'))
+//   RK4     (Solver_RK4.hpp:41-147)     stages 1-4 with a running accumulator acc = k1/6 + k2/3 + k3/3
+//
+// Stage 2 of Depondt / Heun RECOMPUTES the stage-1 virtual force from s instead of storing it:
+// 120 B of HBM traffic per spin and iteration (R s | W s' | R s, s' | W s_new) instead of 168 B.
+// The new configuration goes to a third buffer because neighbours still read the old one.
+//
+// HOOK variants (last iteration before Method_LLG::Hook_Post_Iteration, Method_LLG.cpp:246-301):
+// stage 1 also stores F(s) and Fv(s); the last stage also reduces the energy of the configuration
+// of its (last) force evaluation -- the reference's `current_energy`.
+// ---------------------------------------------------------------------------------------------
+struct StageArgs
+{
+    ConstField3 s;      // configuration at the start of the iteration
+    ConstField3 sp;     // current predictor configuration (stages >= 2)
+    ConstField3 ddi_s;  // DDI gradient of s  (if has_ddi)
+    ConstField3 ddi_sp; // DDI gradient of sp (if has_ddi)
+    Field3 out;         // configuration written by this stage
+    Field3 acc;         // RK4 accumulator (read-modify-write, own site only)
+    Field3 F_out;       // HOOK, stage 1: force -gradient(s)
+    Field3 Fv_out;      // HOOK, stage 1: virtual force Fv(s)
+    double * energy_partials; // HOOK, last stage
+};
+
+template<int SOLVER, int STAGE, int NB_T, bool HOOK>
+static __global__ void __launch_bounds__( BLOCK_THREADS ) k_llg_stage(
+    const __grid_constant__ StencilParams p, const __grid_constant__ LaunchGeom lg, const __grid_constant__ LLGParams l,
+    const __grid_constant__ StageArgs a )
+{
+    constexpr bool two_stage   = SOLVER == Solver_Depondt || SOLVER == Solver_Heun || SOLVER == Solver_SIB;
+    constexpr bool last_stage  = ( two_stage && STAGE == 2 ) || ( SOLVER == Solver_RK4 && STAGE == 4 );
+    constexpr bool need_Fv_s   = STAGE == 1 || ( STAGE == 2 && ( SOLVER == Solver_Depondt || SOLVER == Solver_Heun ) );
+    constexpr bool need_Fv_sp  = STAGE >= 2;
+
+    Site site;
+    const bool active = locate_site( p, lg, site, NB_T > 0 ? NB_T : p.NB );
+    double e          = 0;
+    if( active )
+    {
+        const D3 si = load3( a.s, site.idx );
+        D3 xi       = make_d3( 0, 0, 0 );
+        if( l.has_thermal && !l.direct_minimization )
+            xi = thermal_field<NB_T>( p, l, site );
+
+        D3 Fv = make_d3( 0, 0, 0 ), Fvp = make_d3( 0, 0, 0 ), spi = si;
+        if( need_Fv_s )
+        {
+            const SiteGradient g = site_gradient<NB_T>( p, a.s, a.ddi_s, site, si );
+            const D3 gt          = total( g );
+            const D3 F           = make_d3( -gt.x, -gt.y, -gt.z );
+            Fv                   = virtual_force<NB_T>( l, site, si, F, xi );
+            if( HOOK && STAGE == 1 )
+            {
+                store3( a.F_out, site.idx, F );
+                store3( a.Fv_out, site.idx, Fv );
+            }
+        }
+        if( need_Fv_sp )
+        {
+            spi                  = load3( a.sp, site.idx );
+            const SiteGradient g = site_gradient<NB_T>( p, a.sp, a.ddi_sp, site, spi );
+            const D3 gt          = total( g );
+            Fvp                  = virtual_force<NB_T>( l, site, spi, make_d3( -gt.x, -gt.y, -gt.z ), xi );
+            if( HOOK && last_stage )
+                e = site_energy<NB_T>( p, site, spi, g );
+        }
+
+        D3 out;
+        if( SOLVER == Solver_Depondt )
+        {
+            if( STAGE == 1 )
+                out = rotate_about( si, Fv );
+            else
+                out = rotate_about( si, make_d3( 0.5 * Fv.x + 0.5 * Fvp.x, 0.5 * Fv.y + 0.5 * Fvp.y, 0.5 * Fv.z + 0.5 * Fvp.z ) );
+        }
+        else if( SOLVER == Solver_Heun )
+        {
+            const D3 k1 = cross3( Fv, si ); // -(s x Fv)
+            if( STAGE == 1 )
+                out = normalized3( make_d3( si.x + k1.x, si.y + k1.y, si.z + k1.z ) );
+            else
+            {
+                const D3 k2 = cross3( Fvp, spi ); // -(s' x Fv')
+                out         = normalized3( make_d3(
+                    si.x + 0.5 * k1.x + 0.5 * k2.x, si.y + 0.5 * k1.y + 0.5 * k2.y, si.z + 0.5 * k1.z + 0.5 * k2.z ) );
+            }
+        }
+        else if( SOLVER == Solver_SIB )
+        {
+            if( STAGE == 1 )
+            {
+                const D3 t = sib_transform( si, Fv );
+                out        = make_d3( 0.5 * ( t.x + si.x ), 0.5 * ( t.y + si.y ), 0.5 * ( t.z + si.z ) );
+            }
+            else
+                out = sib_transform( si, Fvp );
+        }
+        else // RK4
+        {
+            // k_n = -(conf_n x Fv_n); intermediates are |s + c k_n| with c = 1/2, 1/2, 1
+            const D3 k = STAGE == 1 ? cross3( Fv, si ) : cross3( Fvp, spi );
+            D3 acc     = make_d3( 0, 0, 0 );
+            if( STAGE > 1 )
+                acc = make_d3( a.acc.x[site.idx], a.acc.y[site.idx], a.acc.z[site.idx] );
+            const double w = ( STAGE == 1 || STAGE == 4 ) ? 1.0 / 6.0 : 1.0 / 3.0;
+            acc            = make_d3( acc.x + w * k.x, acc.y + w * k.y, acc.z + w * k.z );
+            if( STAGE < 4 )
+            {
+                store3( a.acc, site.idx, acc );
+                const double c = STAGE == 3 ? 1.0 : 0.5;
+                out            = normalized3( make_d3( si.x + c * k.x, si.y + c * k.y, si.z + c * k.z ) );
+            }
+            else
+                out = normalized3( make_d3( si.x + acc.x, si.y + acc.y, si.z + acc.z ) );
+        }
+        store3( a.out, site.idx, out );
+    }
+    if( HOOK && last_stage )
+    {
+        e = block_sum( e );
+        if( threadIdx.x == 0 )
+            a.energy_partials[blockIdx.x] = e;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Velocity projection (Solver_VP.hpp:29-114), mass m = 1. The projected velocity after an
+// iteration is always ratio*F (or 0), so the velocity field is never stored:
+//   A:  F = -grad(s);  v = ratio_prev F_prev + (F_prev + F)/2;  partial sums of v.F and F.F;  F_prev <- F
+//   (two-level reduce, ratio = proj/|F|^2 or 0)
+//   B:  s <- |s + dt ratio F + dt F/2|
+// `scal` layout: [0] ratio_prev, [1] sum v.F, [2] sum F.F, [3] ratio of this iteration.
+// HOOK: A reduces the energy E(s); B also produces max |Fv - (Fv.s_new)s_new| with
+// Fv = dtg' s x F, and writes F projected tangentially to the NEW spins into a second buffer -- the
+// reference's hook projects `forces` in place and the projected force is what the next iteration
+// sees as F_prev, while its stored velocity still derives from the raw force (SURVEY.md 8c hazard 6).
+// ---------------------------------------------------------------------------------------------
+template<int NB_T, bool HOOK>
+static __global__ void __launch_bounds__( BLOCK_THREADS ) k_vp_a(
+    const __grid_constant__ StencilParams p, const __grid_constant__ LaunchGeom lg, ConstField3 s, ConstField3 ddi,
+    Field3 F, ConstField3 F_prev, const double * __restrict__ scal, double * __restrict__ part_proj,
+    double * __restrict__ part_norm2, double * __restrict__ energy_partials )
+{
+    Site site;
+    const bool active = locate_site( p, lg, site, NB_T > 0 ? NB_T : p.NB );
+    double proj = 0, norm2 = 0, e = 0;
+    if( active )
+    {
+        const double ratio_prev = scal[0];
+        const D3 si             = load3( s, site.idx );
+        const SiteGradient g    = site_gradient<NB_T>( p, s, ddi, site, si );
+        const D3 gt             = total( g );
+        const D3 Fn             = make_d3( -gt.x, -gt.y, -gt.z );
+        // velocity of the last iteration = ratio_prev * (raw force of the last iteration); F_prev is the same force,
+        // or its tangential projection if a post-iteration hook ran in between (SURVEY.md 8c hazard 6)
+        const D3 Fr             = make_d3( F.x[site.idx], F.y[site.idx], F.z[site.idx] );
+        const D3 Fp             = load3( F_prev, site.idx );
+        const D3 v              = make_d3(
+            ratio_prev * Fr.x + 0.5 * ( Fp.x + Fn.x ), ratio_prev * Fr.y + 0.5 * ( Fp.y + Fn.y ),
+            ratio_prev * Fr.z + 0.5 * ( Fp.z + Fn.z ) );
+        proj  = dot3( v, Fn );
+        norm2 = dot3( Fn, Fn );
+        store3( F, site.idx, Fn );
+        if( HOOK )
+            e = site_energy<NB_T>( p, site, si, g );
+    }
+    proj = block_sum( proj );
+    if( threadIdx.x == 0 )
+        part_proj[blockIdx.x] = proj;
+    norm2 = block_sum( norm2 );
+    if( threadIdx.x == 0 )
+        part_norm2[blockIdx.x] = norm2;
+    if( HOOK )
+    {
+        e = block_sum( e );
+        if( threadIdx.x == 0 )
+            energy_partials[blockIdx.x] = e;
+    }
+}
+
+// scal[3] = ratio (0 if the projection is not positive); also becomes ratio_prev of the next iteration
+static __global__ void k_vp_ratio( double * __restrict__ scal )
+{
+    const double proj = scal[1], norm2 = scal[2];
+    const double ratio = proj > 0 ? proj / norm2 : 0.0;
+    scal[3]            = ratio;
+    scal[0]            = ratio;
+}
+
+template<bool HOOK>
+static __global__ void __launch_bounds__( BLOCK_THREADS ) k_vp_b(
+    const __grid_constant__ StencilParams p, const __grid_constant__ LaunchGeom lg, Field3 s, ConstField3 F, Field3 F_projected,
+    const double * __restrict__ scal, double dt, double dtg, double * __restrict__ torque_partials )
+{
+    Site site;
+    const bool active = locate_site( p, lg, site, p.NB );
+    double t2         = 0;
+    if( active )
+    {
+        const double ratio = scal[3];
+        const D3 si        = make_d3( s.x[site.idx], s.y[site.idx], s.z[site.idx] );
+        D3 Fi              = load3( F, site.idx );
+        const double c     = dt * ratio + 0.5 * dt;
+        const D3 sn        = normalized3( make_d3( si.x + c * Fi.x, si.y + c * Fi.y, si.z + c * Fi.z ) );
+        store3( s, site.idx, sn );
+        if( HOOK )
+        {
+            const D3 sxF = cross3( si, Fi );
+            D3 Fv        = make_d3( dtg * sxF.x, dtg * sxF.y, dtg * sxF.z );
+            const double d = dot3( Fv, sn );
+            Fv             = make_d3( Fv.x - d * sn.x, Fv.y - d * sn.y, Fv.z - d * sn.z );
+            t2             = dot3( Fv, Fv );
+            const double f = dot3( Fi, sn );
+            Fi             = make_d3( Fi.x - f * sn.x, Fi.y - f * sn.y, Fi.z - f * sn.z );
+            store3( F_projected, site.idx, Fi );
+        }
+    }
+    if( HOOK )
+    {
+        t2 = block_max( t2 );
+        if( threadIdx.x == 0 )
+            torque_partials[blockIdx.x] = t2;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Post-iteration hook (Method_LLG.cpp:246-301, Method_Solver.hpp:224-230):
+//   max torque = max_i |Fv_i - (Fv_i.s_i) s_i|  (Fv: stage-1 virtual force, s: the NEW spins)
+//   effective field = F - (F.s) s               (F: stage-1 force)  -- in place
+// ---------------------------------------------------------------------------------------------
+static __global__ void __launch_bounds__( BLOCK_THREADS ) k_hook(
+    const __grid_constant__ StencilParams p, const __grid_constant__ LaunchGeom lg, ConstField3 s, Field3 F, ConstField3 Fv,
+    double * __restrict__ torque_partials )
+{
+    Site site;
+    const bool active = locate_site( p, lg, site, p.NB );
+    double t2         = 0;
+    if( active )
+    {
+        const D3 si    = load3( s, site.idx );
+        const D3 fv    = load3( Fv, site.idx );
+        const double d = dot3( fv, si );
+        const D3 tq    = make_d3( fv.x - d * si.x, fv.y - d * si.y, fv.z - d * si.z );
+        t2             = dot3( tq, tq );
+        const D3 Fi    = make_d3( F.x[site.idx], F.y[site.idx], F.z[site.idx] );
+        const double f = dot3( Fi, si );
+        store3( F, site.idx, make_d3( Fi.x - f * si.x, Fi.y - f * si.y, Fi.z - f * si.z ) );
+    }
+    t2 = block_max( t2 );
+    if( threadIdx.x == 0 )
+        torque_partials[blockIdx.x] = t2;
+}
+
+// Force, virtual force and energy of the current spins (constructor-time evaluation, Method_LLG.cpp:57-62)
+template<int NB_T>
+static __global__ void __launch_bounds__( BLOCK_THREADS ) k_force_and_virtual(
+    const __grid_constant__ StencilParams p, const __grid_constant__ LaunchGeom lg, const __grid_constant__ LLGParams l,
+    ConstField3 s, ConstField3 ddi, Field3 F_out, Field3 Fv_out, double * __restrict__ energy_partials )
+{
+    Site site;
+    const bool active = locate_site( p, lg, site, NB_T > 0 ? NB_T : p.NB );
+    double e          = 0;
+    if( active )
+    {
+        const D3 si = load3( s, site.idx );
+        D3 xi       = make_d3( 0, 0, 0 );
+        if( l.has_thermal && !l.direct_minimization )
+            xi = thermal_field<NB_T>( p, l, site );
+        const SiteGradient g = site_gradient<NB_T>( p, s, ddi, site, si );
+        const D3 gt          = total( g );
+        const D3 F           = make_d3( -gt.x, -gt.y, -gt.z );
+        store3( F_out, site.idx, F );
+        store3( Fv_out, site.idx, virtual_force<NB_T>( l, site, si, F, xi ) );
+        e = site_energy<NB_T>( p, site, si, g );
+    }
+    e = block_sum( e );
+    if( threadIdx.x == 0 )
+        energy_partials[blockIdx.x] = e;
+}
+
+// sum_i mu_s[ib] * s_i per component (Magnetization, Vectormath.cpp:495-502): partials [3][nblocks]
+static __global__ void __launch_bounds__( BLOCK_THREADS ) k_magnetization(
+    const __grid_constant__ StencilParams p, const __grid_constant__ LaunchGeom lg, ConstField3 s, double * __restrict__ partials,
+    int nblocks, int weighted )
+{
+    Site site;
+    const bool active = locate_site( p, lg, site, p.NB );
+    D3 m              = make_d3( 0, 0, 0 );
+    if( active )
+    {
+        const D3 si     = load3( s, site.idx );
+        const double mu = weighted ? p.mu_s[site.ib] : 1.0;
+        m               = make_d3( mu * si.x, mu * si.y, mu * si.z );
+    }
+    double v = block_sum( m.x );
+    if( threadIdx.x == 0 )
+        partials[blockIdx.x] = v;
+    v = block_sum( m.y );
+    if( threadIdx.x == 0 )
+        partials[nblocks + blockIdx.x] = v;
+    v = block_sum( m.z );
+    if( threadIdx.x == 0 )
+        partials[2 * nblocks + blockIdx.x] = v;
+}
+
+} // namespace dev
+} // namespace sb

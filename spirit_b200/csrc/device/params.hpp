@@ -1,0 +1,94 @@
+// Plain-old-data parameter blocks shared between the host library and the CUDA kernels.
+// They are passed BY VALUE as __grid_constant__ kernel parameters, so every thread reads them
+// through the constant bank (uniform loads, no global traffic, no per-image __constant__ symbol
+// to keep in sync when several images with different Hamiltonians live in one process).
+#pragma once
+
+#include <cstdint>
+
+namespace sb
+{
+namespace dev
+{
+
+// Solver ids of the C API (core/include/Spirit/Simulation.h:33-54)
+enum Solver
+{
+    Solver_VP      = 0,
+    Solver_SIB     = 1,
+    Solver_Depondt = 2,
+    Solver_Heun    = 3,
+    Solver_RK4     = 4
+};
+
+constexpr int MAX_BASIS = 8;   // basis atoms per cell handled by the stencil kernels
+constexpr int MAX_NEIGH = 160; // merged (exchange + DMI) neighbour entries over all basis atoms
+constexpr int MAX_ANISO = 16;  // uniaxial anisotropy entries
+
+// One gathered neighbour of basis atom `ib`: the spin (jb, a+da, b+db, c+dc) contributes
+//     g_i -= J * s_j + s_j x D          (D = D_magnitude * normal)
+// which merges the reference's Gradient_Exchange and Gradient_DMI loops
+// (core/src/engine/Hamiltonian_Heisenberg.cpp:822-864) for pairs with identical (i, j, translations).
+struct Neighbour
+{
+    int jb;
+    int da, db, dc;
+    double J;
+    double Dx, Dy, Dz;
+};
+
+struct Anisotropy
+{
+    int ib;
+    int pad;
+    double K;
+    double nx, ny, nz;
+};
+
+// Everything the gradient / energy stencil needs. Site order is the reference's
+// (core/include/engine/Vectormath.hpp:61-74): x = ib + NB*a is the contiguous index of a row,
+// rows are ordered b + Nb*c.
+struct StencilParams
+{
+    int Na, Nb, Nc, NB;
+    int bc[3]; // periodic (1) or open (0) along a, b, c -- idx_from_pair, Vectormath.hpp:437-528
+    int n_neigh;
+    int neigh_begin[MAX_BASIS + 1]; // entries of basis atom ib are neigh[neigh_begin[ib] .. neigh_begin[ib+1])
+    int n_aniso;
+    int has_cubic;
+    int has_zeeman;
+    int has_ddi; // a precomputed DDI gradient field is added (device/ddi_fft.cu)
+
+    // Slab decomposition along c (multi-GPU): this device stores planes [c_begin - halo, c_begin + nc_local + halo).
+    // Single device: c_begin = 0, nc_local = Nc, halo = 0 and periodic c wraps locally.
+    int c_begin, nc_local, halo;
+    int pad0;
+
+    double K4[MAX_BASIS];        // cubic anisotropy per basis atom (Hamiltonian_Heisenberg.cpp:802-820)
+    double zeeman[MAX_BASIS][3]; // mu_s[ib] * (B mu_B) * n_B   (Hamiltonian_Heisenberg.cpp:768-783)
+    double mu_s[MAX_BASIS];
+    Anisotropy aniso[MAX_ANISO];
+    Neighbour neigh[MAX_NEIGH];
+};
+
+// LLG virtual-force parameters (core/src/engine/Method_LLG.cpp:131-226)
+struct LLGParams
+{
+    double dtg;       // dt*gamma/mu_B/(1+alpha^2)   (dynamics)   or   dt*gamma/mu_B (direct minimisation)
+    double damping;   // alpha
+    double dt;        // raw llg_dt (VP uses it directly, Solver_VP.hpp:95-110)
+    int direct_minimization; // Fv = dtg * s x F
+    int has_stt;      // monolayer spin-transfer torque (Method_LLG.cpp:207-212)
+    double stt_c1;    // -dtg*a_j*(alpha-beta)
+    double stt_c2;    // -dtg*a_j*(1+beta*alpha)
+    double stt_pol[3];
+    int has_thermal;  // Method_LLG.cpp:65-110,215-219
+    int pad;
+    double thermal_scale[MAX_BASIS]; // epsilon*sqrt(T/mu_s[ib])
+    double inv_mu_s[MAX_BASIS];
+    std::uint64_t seed;      // Philox key
+    std::uint64_t iteration; // Philox counter high words: one xi per iteration, shared by all stages
+};
+
+} // namespace dev
+} // namespace sb

@@ -1,0 +1,123 @@
+// Host-visible interface of the device layer (no CUDA headers needed by the callers).
+//
+// A DeviceImage is the HBM-resident state of one spin system ("image"): SoA fp64 spin buffers
+// (current / predictor / next), work fields, reduction scratch, and the by-value parameter block
+// of its Hamiltonian. All kernels of one image run on the image's own CUDA stream.
+//
+// There is NO CPU fallback: every entry point calls require_device() and throws if the CUDA
+// runtime reports no usable device.
+#pragma once
+
+#include "params.hpp"
+
+#include <cstddef>
+#include <cstdint>
+#include <memory>
+#include <string>
+#include <vector>
+
+namespace sb
+{
+struct Hamiltonian;
+struct Geometry;
+
+namespace dev
+{
+
+bool device_available();
+int device_count();    // 0 when the CUDA runtime reports no usable device
+void require_device(); // throws std::runtime_error when there is no CUDA device
+void set_device( int device ); // device used by the calling thread for images created afterwards
+std::string device_name();
+
+// Pinned host memory when a device is present (full-speed H2D/D2H of the AoS mirrors that the C API
+// exposes), plain aligned memory otherwise (host-only use: config parsing, pair lists, tests on CPU).
+void * host_alloc( std::size_t bytes, bool & pinned );
+void host_free( void * ptr, bool pinned );
+
+struct DeviceBuffers; // opaque (device pointers, stream, events)
+struct DDIPlan;       // opaque (device/ddi_fft.cu)
+
+struct HookResult
+{
+    double energy     = 0; // energy of the configuration of the last force evaluation of the iteration
+    double max_torque = 0; // max_i |Fv_i - (Fv_i.s_i) s_i| with Fv from the first stage, s the new spins
+};
+
+class DeviceImage
+{
+public:
+    DeviceImage( const Geometry & geometry );
+    ~DeviceImage();
+    DeviceImage( const DeviceImage & )             = delete;
+    DeviceImage & operator=( const DeviceImage & ) = delete;
+
+    int nos() const
+    {
+        return nos_;
+    }
+
+    // (Re)build the stencil tables from the host Hamiltonian if its revision changed
+    void set_hamiltonian( const Hamiltonian & ham );
+    const StencilParams & stencil() const
+    {
+        return stencil_;
+    }
+
+    // AoS [nos][3] host <-> SoA device
+    void upload_spins( const double * host_aos );
+    void download_spins( double * host_aos );
+    void download_effective_field( double * host_aos );
+
+    // One-off evaluations on the device-resident spins (System_Update_Data, tests).
+    // gradient_host_aos may be null. Hamiltonian_Heisenberg.cpp:670-766
+    void gradient_and_energy( double * gradient_host_aos, double * energy );
+    // -gradient into the effective-field buffer (Spin_System::UpdateEffectiveField)
+    void update_effective_field();
+    // Per-term energies: totals[n_terms]; per_spin_host (nullable) [n_terms][nos]. Hamiltonian_Heisenberg.cpp:262-404
+    int energy_contributions( const Hamiltonian & ham, double * totals, double * per_spin_host );
+    // mean of mu_s * s (Vectormath.cpp:495-502), or the plain mean of s if !weighted (Vectormath.cpp:150-160)
+    void magnetization( double m[3], bool weighted );
+
+    // n iterations of an LLG solver; if `hook` the last iteration also produces the quantities of
+    // Method_LLG::Hook_Post_Iteration (Method_LLG.cpp:246-301) and the effective field buffer.
+    // `llg.iteration` is advanced by n.
+    void llg_iterate( int solver, LLGParams & llg, int n_iterations, bool hook, HookResult * result );
+    // The constructor-time evaluation of Method_LLG (Method_LLG.cpp:57-62): force, virtual force, hook
+    void llg_initial_hook( int solver, const LLGParams & llg, HookResult * result );
+    // VP keeps velocity / previous force between iterations (Solver_VP.hpp:29-114)
+    void vp_reset();
+
+    void synchronize();
+
+    // Timing of the enqueued work on this image's stream (CUDA events), milliseconds
+    void timer_start();
+    double timer_stop();
+
+    std::uint64_t kernel_launches() const
+    {
+        return launches_;
+    }
+
+    DeviceBuffers * buffers()
+    {
+        return buf_.get();
+    }
+
+private:
+    void ensure_work_fields( int solver );
+    void compute_ddi_gradient( int which_config );
+
+    int nos_ = 0;
+    StencilParams stencil_{};
+    std::uint64_t ham_revision_ = ~std::uint64_t( 0 );
+    std::unique_ptr<DeviceBuffers> buf_;
+    std::unique_ptr<DDIPlan> ddi_;
+    std::uint64_t launches_ = 0;
+    bool vp_initialized_        = false;
+    bool vp_prev_projected_     = false; // the last VP iteration ran a hook: F_prev is the projected force (in Fv)
+    bool effective_field_in_Fv_ = false;
+};
+
+} // namespace dev
+} // namespace sb
