@@ -52,4 +52,7 @@ SPIRIT_API int SpiritB200_Download( State * state, int idx_image ) SPIRIT_NOEXCE
  * stream; < 0 on error. The image's LLG parameters (dt, damping, temperature, seed, ...) apply.
  * Same arithmetic as Simulation_LLG_Start: Method_Solver<solver>::Iteration, core/include/engine/Solver_*.hpp */
 SPIRIT_API double SpiritB200_LLG_Iterate_Device( State * state, int solver_type, int n_iterations, int idx_image ) SPIRIT_NOEXCEPT;
+/* The same iterations with a CUDA event between the stage kernels: stage_ms[k] = mean milliseconds of stage k+1
+ * (Depondt/Heun/SIB: 2 stages, RK4: 4). Returns the number of stages, < 0 on error. For per-kernel rooflines. */
+SPIRIT_API int SpiritB200_LLG_Profile_Stages( State * state, int solver_type, int n_iterations, double * stage_ms, int max_stages, int idx_image ) SPIRIT_NOEXCEPT;
 #endif

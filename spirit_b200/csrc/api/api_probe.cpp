@@ -258,3 +258,22 @@ catch( ... )
     handle_exception_api( __func__, idx_image );
     return -1;
 }
+
+int SpiritB200_LLG_Profile_Stages( State * state, int solver_type, int n_iterations, double * stage_ms, int max_stages, int idx_image ) noexcept
+try
+{
+    int idx_chain = -1;
+    auto image    = resolve( state, idx_image, idx_chain ).image;
+    ImageLock lock( *image );
+    auto & d = image->device();
+    d.set_hamiltonian( *image->hamiltonian );
+    dev::LLGParams l = Method_LLG::make_params( *image, solver_type );
+    const int n      = d.llg_profile_stages( solver_type, l, n_iterations, stage_ms, max_stages );
+    image->llg_parameters->philox_counter = l.iteration;
+    return n;
+}
+catch( ... )
+{
+    handle_exception_api( __func__, idx_image );
+    return -1;
+}

@@ -512,9 +512,20 @@ void DeviceImage::llg_iterate( int solver, LLGParams & llg, int n_iterations, bo
     ensure_work_fields( solver );
     const bool nb1 = stencil_.NB == 1;
 
+    auto mark = [&]() {
+        if( stage_events_ )
+        {
+            cudaEvent_t ev;
+            SB_CUDA_CHECK( cudaEventCreate( &ev ) );
+            SB_CUDA_CHECK( cudaEventRecord( ev, b.stream ) );
+            stage_events_->push_back( ev );
+        }
+    };
+
     for( int it = 0; it < n_iterations; ++it )
     {
         const bool hk = hook && ( it == n_iterations - 1 );
+        mark();
         StageArgs a{};
         a.s               = b.spins.c();
         a.ddi_s           = b.ddi_s.c();
@@ -532,6 +543,7 @@ void DeviceImage::llg_iterate( int solver, LLGParams & llg, int n_iterations, bo
                 launch_stage<Solver_Heun, 1>( nb1, hk, b.nblocks, b.stream, stencil_, b.lg, llg, a );
             else
                 launch_stage<Solver_SIB, 1>( nb1, hk, b.nblocks, b.stream, stencil_, b.lg, llg, a );
+            mark();
             a.sp  = b.pred.c();
             a.out = b.next.f();
             if( solver == Solver_Depondt )
@@ -540,6 +552,7 @@ void DeviceImage::llg_iterate( int solver, LLGParams & llg, int n_iterations, bo
                 launch_stage<Solver_Heun, 2>( nb1, hk, b.nblocks, b.stream, stencil_, b.lg, llg, a );
             else
                 launch_stage<Solver_SIB, 2>( nb1, hk, b.nblocks, b.stream, stencil_, b.lg, llg, a );
+            mark();
             launches_ += 2;
             std::swap( b.spins, b.next );
         }
@@ -548,15 +561,19 @@ void DeviceImage::llg_iterate( int solver, LLGParams & llg, int n_iterations, bo
             a.acc = b.acc.f();
             a.out = b.pred.f();
             launch_stage<Solver_RK4, 1>( nb1, hk, b.nblocks, b.stream, stencil_, b.lg, llg, a );
+            mark();
             a.sp  = b.pred.c();
             a.out = b.pred2.f();
             launch_stage<Solver_RK4, 2>( nb1, hk, b.nblocks, b.stream, stencil_, b.lg, llg, a );
+            mark();
             a.sp  = b.pred2.c();
             a.out = b.pred.f();
             launch_stage<Solver_RK4, 3>( nb1, hk, b.nblocks, b.stream, stencil_, b.lg, llg, a );
+            mark();
             a.sp  = b.pred.c();
             a.out = b.next.f();
             launch_stage<Solver_RK4, 4>( nb1, hk, b.nblocks, b.stream, stencil_, b.lg, llg, a );
+            mark();
             launches_ += 4;
             std::swap( b.spins, b.next );
         }
@@ -625,6 +642,40 @@ void DeviceImage::llg_iterate( int solver, LLGParams & llg, int n_iterations, bo
             result->max_torque = std::sqrt( b.h_scalars[5] );
         }
     }
+}
+
+int DeviceImage::llg_profile_stages( int solver, LLGParams & llg, int n_iterations, double * stage_ms, int max_stages )
+{
+    const int n_stages = solver == Solver_RK4 ? 4 : ( solver == Solver_VP ? 0 : 2 );
+    if( n_stages == 0 || n_stages > max_stages )
+        throw std::runtime_error( "spirit_b200: stage profiling is available for Depondt, Heun, SIB and RK4" );
+    std::vector<void *> events;
+    stage_events_ = &events;
+    try
+    {
+        llg_iterate( solver, llg, n_iterations, false, nullptr );
+    }
+    catch( ... )
+    {
+        stage_events_ = nullptr;
+        throw;
+    }
+    stage_events_ = nullptr;
+    SB_CUDA_CHECK( cudaStreamSynchronize( buf_->stream ) );
+    for( int k = 0; k < n_stages; ++k )
+        stage_ms[k] = 0;
+    const int per_it = n_stages + 1; // one event before stage 1 and one after every stage
+    for( int it = 0; it < n_iterations; ++it )
+        for( int k = 0; k < n_stages; ++k )
+        {
+            float ms = 0;
+            SB_CUDA_CHECK( cudaEventElapsedTime(
+                &ms, cudaEvent_t( events[it * per_it + k] ), cudaEvent_t( events[it * per_it + k + 1] ) ) );
+            stage_ms[k] += ms / n_iterations;
+        }
+    for( void * ev : events )
+        cudaEventDestroy( cudaEvent_t( ev ) );
+    return n_stages;
 }
 
 void DeviceImage::compute_ddi_gradient( int ) {}

@@ -83,6 +83,9 @@ public:
     // Method_LLG::Hook_Post_Iteration (Method_LLG.cpp:246-301) and the effective field buffer.
     // `llg.iteration` is advanced by n.
     void llg_iterate( int solver, LLGParams & llg, int n_iterations, bool hook, HookResult * result );
+    // Same iterations with a CUDA event recorded between the stage kernels: stage_ms[k] receives the mean duration
+    // (milliseconds) of stage k+1 over the n iterations (bench.py's per-kernel roofline). Returns the number of stages.
+    int llg_profile_stages( int solver, LLGParams & llg, int n_iterations, double * stage_ms, int max_stages );
     // The constructor-time evaluation of Method_LLG (Method_LLG.cpp:57-62): force, virtual force, hook
     void llg_initial_hook( int solver, const LLGParams & llg, HookResult * result );
     // VP keeps velocity / previous force between iterations (Solver_VP.hpp:29-114)
@@ -117,6 +120,7 @@ private:
     bool vp_initialized_        = false;
     bool vp_prev_projected_     = false; // the last VP iteration ran a hook: F_prev is the projected force (in Fv)
     bool effective_field_in_Fv_ = false;
+    std::vector<void *> * stage_events_ = nullptr; // when set, llg_iterate records an event after every stage kernel
 };
 
 } // namespace dev
