@@ -189,6 +189,8 @@ dev::LLGParams Method_LLG::make_params( const Spin_System & system, int solver )
     {
         const double mu      = ib < g.n_cell_atoms ? g.cell_mu_s[ib] : 1.0;
         l.inv_mu_s[ib]       = 1.0 / mu;
+        l.c1[ib]             = l.dtg / mu;
+        l.c2[ib]             = l.damping * l.dtg / mu;
         l.thermal_scale[ib]  = l.has_thermal ? epsilon * std::sqrt( P.temperature / mu ) : 0.0;
     }
     l.seed      = std::uint64_t( std::uint32_t( P.rng_seed ) ) | ( std::uint64_t( 0x5b200 ) << 32 );

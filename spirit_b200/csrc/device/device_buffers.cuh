@@ -3,6 +3,7 @@
 #pragma once
 
 #include "kernels.cuh"
+#include "sc6.cuh"
 #include "runtime.hpp"
 
 #include <stdexcept>
@@ -63,8 +64,15 @@ struct DeviceField
     }
 };
 
+struct SC6Launch
+{
+    dim3 grid, block;
+    int lc = 1; // planes per CTA (march length)
+};
+
 struct DeviceBuffers
 {
+    SC6Launch sc6;
     cudaStream_t stream = nullptr;
     cudaEvent_t ev_start = nullptr, ev_stop = nullptr;
 

@@ -7,6 +7,7 @@
 #include <algorithm>
 #include <cstdio>
 #include <cstdlib>
+#include <cmath>
 #include <cstring>
 #include <map>
 #include <stdexcept>
@@ -111,6 +112,48 @@ int next_pow2( int v )
     return p;
 }
 
+int env_int( const char * name, int fallback )
+{
+    const char * v = std::getenv( name );
+    return ( v && *v ) ? std::atoi( v ) : fallback;
+}
+
+// Block shape and march length of the sc6 kernels. BX x BY threads own BX sites of BY rows; the grid's z dimension
+// splits c into segments of lc planes. lc trades the two extra planes read per segment against the tail of the last
+// wave of CTAs. (SPIRIT_B200_SC6_BX / _BY / _LC override for tuning runs.)
+SC6Launch make_sc6_launch( const StencilParams & p )
+{
+    SC6Launch L;
+    int bx = std::min( 128, ( ( p.Na + 31 ) / 32 ) * 32 );
+    bx     = env_int( "SPIRIT_B200_SC6_BX", bx );
+    int by = std::max( 1, std::min( SC6_MAX_THREADS / bx, p.Nb ) );
+    by     = env_int( "SPIRIT_B200_SC6_BY", std::min( by, 4 ) );
+    L.block = dim3( bx, by, 1 );
+    const int gx = ( p.Na + bx - 1 ) / bx, gy = ( p.Nb + by - 1 ) / by;
+    int n_sm = 148, dev = 0;
+    if( cudaGetDevice( &dev ) == cudaSuccess )
+        cudaDeviceGetAttribute( &n_sm, cudaDevAttrMultiProcessorCount, dev );
+    const double slots = double( n_sm ) * std::max( 1, 1024 / ( bx * by ) ); // resident CTAs, assuming <= 64 registers/thread
+    int best_lc = p.nc_local;
+    double best = 1e300;
+    for( int lc : { 4, 6, 8, 12, 16, 24, 32, 48, 64, 96, 128 } )
+    {
+        if( lc > p.nc_local )
+            lc = p.nc_local;
+        const int nseg     = ( p.nc_local + lc - 1 ) / lc;
+        const double waves = double( gx ) * gy * nseg / slots;
+        const double cost  = ( 1.0 + 2.0 / lc ) * std::ceil( waves ) / waves;
+        if( cost < best - 1e-12 )
+        {
+            best    = cost;
+            best_lc = lc;
+        }
+    }
+    L.lc   = std::max( 1, env_int( "SPIRIT_B200_SC6_LC", best_lc ) );
+    L.grid = dim3( gx, gy, ( p.nc_local + L.lc - 1 ) / L.lc );
+    return L;
+}
+
 LaunchGeom make_geom( const StencilParams & p )
 {
     LaunchGeom lg;
@@ -147,6 +190,7 @@ DeviceImage::DeviceImage( const Geometry & g )
     b.lg              = make_geom( stencil_ );
     b.nblocks         = b.lg.blocks_x * b.lg.blocks_y;
     b.n_storage       = std::size_t( nos_ );
+    b.sc6             = make_sc6_launch( stencil_ );
     b.interior_offset = 0;
     SB_CUDA_CHECK( cudaStreamCreateWithFlags( &b.stream, cudaStreamNonBlocking ) );
     SB_CUDA_CHECK( cudaEventCreate( &b.ev_start ) );
@@ -239,6 +283,57 @@ void DeviceImage::set_hamiltonian( const Hamiltonian & ham )
     for( int ib = g.n_cell_atoms; ib <= MAX_BASIS; ++ib )
         p.neigh_begin[ib] = p.n_neigh;
 
+    // Nearest-neighbour structure (sc6.cuh): one basis atom, neighbours only at +-a, +-b, +-c, symmetric J, antisymmetric D
+    p.sc6 = 0;
+    for( int d = 0; d < 3; ++d )
+    {
+        p.sc6_axis[d] = p.sc6_dflags[d] = 0;
+        p.sc6_J[d]                      = 0;
+        for( int k = 0; k < 3; ++k )
+            p.sc6_D[d][k] = 0;
+    }
+    if( g.n_cell_atoms == 1 )
+    {
+        bool ok = true;
+        const Neighbour * plus[3]  = { nullptr, nullptr, nullptr };
+        const Neighbour * minus[3] = { nullptr, nullptr, nullptr };
+        for( int n = 0; n < p.n_neigh && ok; ++n )
+        {
+            const Neighbour & nb = p.neigh[n];
+            const int t[3]       = { nb.da, nb.db, nb.dc };
+            int axis = -1, nonzero = 0;
+            for( int d = 0; d < 3; ++d )
+                if( t[d] != 0 )
+                {
+                    ++nonzero;
+                    axis = d;
+                }
+            if( nonzero != 1 || std::abs( t[axis] ) != 1 )
+                ok = false;
+            else
+                ( t[axis] > 0 ? plus : minus )[axis] = &nb;
+        }
+        for( int d = 0; d < 3 && ok; ++d )
+        {
+            if( !plus[d] && !minus[d] )
+                continue;
+            if( !plus[d] || !minus[d] || plus[d]->J != minus[d]->J || plus[d]->Dx != -minus[d]->Dx
+                || plus[d]->Dy != -minus[d]->Dy || plus[d]->Dz != -minus[d]->Dz )
+            {
+                ok = false;
+                break;
+            }
+            p.sc6_axis[d]   = 1;
+            p.sc6_J[d]      = plus[d]->J;
+            p.sc6_D[d][0]   = plus[d]->Dx;
+            p.sc6_D[d][1]   = plus[d]->Dy;
+            p.sc6_D[d][2]   = plus[d]->Dz;
+            p.sc6_dflags[d] = ( plus[d]->Dx != 0 ? 1 : 0 ) | ( plus[d]->Dy != 0 ? 2 : 0 ) | ( plus[d]->Dz != 0 ? 4 : 0 );
+        }
+        const char * off = std::getenv( "SPIRIT_B200_GENERIC_STENCIL" ); // tests: force the generic gather kernels
+        p.sc6            = ( ok && !( off && off[0] == '1' ) ) ? 1 : 0;
+    }
+
     // Uniaxial anisotropy
     if( ham.anisotropy_indices.size() > std::size_t( MAX_ANISO ) )
         throw std::runtime_error( "spirit_b200: more than 16 anisotropy entries are not supported" );
@@ -250,6 +345,7 @@ void DeviceImage::set_hamiltonian( const Hamiltonian & ham )
         p.aniso[i].nx = ham.anisotropy_normals[i].x;
         p.aniso[i].ny = ham.anisotropy_normals[i].y;
         p.aniso[i].nz = ham.anisotropy_normals[i].z;
+        p.aniso[i].flags = ( p.aniso[i].nx != 0 ? 1 : 0 ) | ( p.aniso[i].ny != 0 ? 2 : 0 ) | ( p.aniso[i].nz != 0 ? 4 : 0 );
     }
     // Cubic anisotropy (entries for the same atom add up)
     p.has_cubic = !ham.cubic_anisotropy_indices.empty();
@@ -456,8 +552,15 @@ namespace
 template<int SOLVER, int STAGE>
 void launch_stage(
     bool nb1, bool hook, int nblocks, cudaStream_t stream, const StencilParams & p, const LaunchGeom & lg, const LLGParams & l,
-    const StageArgs & a )
+    const StageArgs & a, const SC6Launch & sc6 )
 {
+    if( p.sc6 && !hook )
+    {
+        // nearest-neighbour structure: marching kernel (the hook iteration, which also stores F, Fv and reduces the
+        // energy, goes through the generic kernel)
+        k_sc6_stage<SOLVER, STAGE><<<sc6.grid, sc6.block, 0, stream>>>( p, sc6.lc, l, a );
+        return;
+    }
     if( nb1 )
     {
         if( hook )
@@ -538,20 +641,20 @@ void DeviceImage::llg_iterate( int solver, LLGParams & llg, int n_iterations, bo
         {
             a.out = b.pred.f();
             if( solver == Solver_Depondt )
-                launch_stage<Solver_Depondt, 1>( nb1, hk, b.nblocks, b.stream, stencil_, b.lg, llg, a );
+                launch_stage<Solver_Depondt, 1>( nb1, hk, b.nblocks, b.stream, stencil_, b.lg, llg, a, b.sc6 );
             else if( solver == Solver_Heun )
-                launch_stage<Solver_Heun, 1>( nb1, hk, b.nblocks, b.stream, stencil_, b.lg, llg, a );
+                launch_stage<Solver_Heun, 1>( nb1, hk, b.nblocks, b.stream, stencil_, b.lg, llg, a, b.sc6 );
             else
-                launch_stage<Solver_SIB, 1>( nb1, hk, b.nblocks, b.stream, stencil_, b.lg, llg, a );
+                launch_stage<Solver_SIB, 1>( nb1, hk, b.nblocks, b.stream, stencil_, b.lg, llg, a, b.sc6 );
             mark();
             a.sp  = b.pred.c();
             a.out = b.next.f();
             if( solver == Solver_Depondt )
-                launch_stage<Solver_Depondt, 2>( nb1, hk, b.nblocks, b.stream, stencil_, b.lg, llg, a );
+                launch_stage<Solver_Depondt, 2>( nb1, hk, b.nblocks, b.stream, stencil_, b.lg, llg, a, b.sc6 );
             else if( solver == Solver_Heun )
-                launch_stage<Solver_Heun, 2>( nb1, hk, b.nblocks, b.stream, stencil_, b.lg, llg, a );
+                launch_stage<Solver_Heun, 2>( nb1, hk, b.nblocks, b.stream, stencil_, b.lg, llg, a, b.sc6 );
             else
-                launch_stage<Solver_SIB, 2>( nb1, hk, b.nblocks, b.stream, stencil_, b.lg, llg, a );
+                launch_stage<Solver_SIB, 2>( nb1, hk, b.nblocks, b.stream, stencil_, b.lg, llg, a, b.sc6 );
             mark();
             launches_ += 2;
             std::swap( b.spins, b.next );
@@ -560,19 +663,19 @@ void DeviceImage::llg_iterate( int solver, LLGParams & llg, int n_iterations, bo
         {
             a.acc = b.acc.f();
             a.out = b.pred.f();
-            launch_stage<Solver_RK4, 1>( nb1, hk, b.nblocks, b.stream, stencil_, b.lg, llg, a );
+            launch_stage<Solver_RK4, 1>( nb1, hk, b.nblocks, b.stream, stencil_, b.lg, llg, a, b.sc6 );
             mark();
             a.sp  = b.pred.c();
             a.out = b.pred2.f();
-            launch_stage<Solver_RK4, 2>( nb1, hk, b.nblocks, b.stream, stencil_, b.lg, llg, a );
+            launch_stage<Solver_RK4, 2>( nb1, hk, b.nblocks, b.stream, stencil_, b.lg, llg, a, b.sc6 );
             mark();
             a.sp  = b.pred2.c();
             a.out = b.pred.f();
-            launch_stage<Solver_RK4, 3>( nb1, hk, b.nblocks, b.stream, stencil_, b.lg, llg, a );
+            launch_stage<Solver_RK4, 3>( nb1, hk, b.nblocks, b.stream, stencil_, b.lg, llg, a, b.sc6 );
             mark();
             a.sp  = b.pred.c();
             a.out = b.next.f();
-            launch_stage<Solver_RK4, 4>( nb1, hk, b.nblocks, b.stream, stencil_, b.lg, llg, a );
+            launch_stage<Solver_RK4, 4>( nb1, hk, b.nblocks, b.stream, stencil_, b.lg, llg, a, b.sc6 );
             mark();
             launches_ += 4;
             std::swap( b.spins, b.next );

@@ -291,10 +291,8 @@ static __global__ void __launch_bounds__( BLOCK_THREADS ) k_llg_stage(
     const __grid_constant__ StencilParams p, const __grid_constant__ LaunchGeom lg, const __grid_constant__ LLGParams l,
     const __grid_constant__ StageArgs a )
 {
-    constexpr bool two_stage   = SOLVER == Solver_Depondt || SOLVER == Solver_Heun || SOLVER == Solver_SIB;
-    constexpr bool last_stage  = ( two_stage && STAGE == 2 ) || ( SOLVER == Solver_RK4 && STAGE == 4 );
-    constexpr bool need_Fv_s   = STAGE == 1 || ( STAGE == 2 && ( SOLVER == Solver_Depondt || SOLVER == Solver_Heun ) );
-    constexpr bool need_Fv_sp  = STAGE >= 2;
+    using Needs               = StageNeeds<SOLVER, STAGE>;
+    constexpr bool last_stage = Needs::last;
 
     Site site;
     const bool active = locate_site( p, lg, site, NB_T > 0 ? NB_T : p.NB );
@@ -307,7 +305,7 @@ static __global__ void __launch_bounds__( BLOCK_THREADS ) k_llg_stage(
             xi = thermal_field<NB_T>( p, l, site );
 
         D3 Fv = make_d3( 0, 0, 0 ), Fvp = make_d3( 0, 0, 0 ), spi = si;
-        if( need_Fv_s )
+        if( Needs::Fv_s )
         {
             const SiteGradient g = site_gradient<NB_T>( p, a.s, a.ddi_s, site, si );
             const D3 gt          = total( g );
@@ -319,7 +317,7 @@ static __global__ void __launch_bounds__( BLOCK_THREADS ) k_llg_stage(
                 store3( a.Fv_out, site.idx, Fv );
             }
         }
-        if( need_Fv_sp )
+        if( Needs::Fv_sp )
         {
             spi                  = load3( a.sp, site.idx );
             const SiteGradient g = site_gradient<NB_T>( p, a.sp, a.ddi_sp, site, spi );
@@ -329,54 +327,12 @@ static __global__ void __launch_bounds__( BLOCK_THREADS ) k_llg_stage(
                 e = site_energy<NB_T>( p, site, spi, g );
         }
 
-        D3 out;
-        if( SOLVER == Solver_Depondt )
-        {
-            if( STAGE == 1 )
-                out = rotate_about( si, Fv );
-            else
-                out = rotate_about( si, make_d3( 0.5 * Fv.x + 0.5 * Fvp.x, 0.5 * Fv.y + 0.5 * Fvp.y, 0.5 * Fv.z + 0.5 * Fvp.z ) );
-        }
-        else if( SOLVER == Solver_Heun )
-        {
-            const D3 k1 = cross3( Fv, si ); // -(s x Fv)
-            if( STAGE == 1 )
-                out = normalized3( make_d3( si.x + k1.x, si.y + k1.y, si.z + k1.z ) );
-            else
-            {
-                const D3 k2 = cross3( Fvp, spi ); // -(s' x Fv')
-                out         = normalized3( make_d3(
-                    si.x + 0.5 * k1.x + 0.5 * k2.x, si.y + 0.5 * k1.y + 0.5 * k2.y, si.z + 0.5 * k1.z + 0.5 * k2.z ) );
-            }
-        }
-        else if( SOLVER == Solver_SIB )
-        {
-            if( STAGE == 1 )
-            {
-                const D3 t = sib_transform( si, Fv );
-                out        = make_d3( 0.5 * ( t.x + si.x ), 0.5 * ( t.y + si.y ), 0.5 * ( t.z + si.z ) );
-            }
-            else
-                out = sib_transform( si, Fvp );
-        }
-        else // RK4
-        {
-            // k_n = -(conf_n x Fv_n); intermediates are |s + c k_n| with c = 1/2, 1/2, 1
-            const D3 k = STAGE == 1 ? cross3( Fv, si ) : cross3( Fvp, spi );
-            D3 acc     = make_d3( 0, 0, 0 );
-            if( STAGE > 1 )
-                acc = make_d3( a.acc.x[site.idx], a.acc.y[site.idx], a.acc.z[site.idx] );
-            const double w = ( STAGE == 1 || STAGE == 4 ) ? 1.0 / 6.0 : 1.0 / 3.0;
-            acc            = make_d3( acc.x + w * k.x, acc.y + w * k.y, acc.z + w * k.z );
-            if( STAGE < 4 )
-            {
-                store3( a.acc, site.idx, acc );
-                const double c = STAGE == 3 ? 1.0 : 0.5;
-                out            = normalized3( make_d3( si.x + c * k.x, si.y + c * k.y, si.z + c * k.z ) );
-            }
-            else
-                out = normalized3( make_d3( si.x + acc.x, si.y + acc.y, si.z + acc.z ) );
-        }
+        D3 acc = make_d3( 0, 0, 0 );
+        if( SOLVER == Solver_RK4 && STAGE > 1 )
+            acc = make_d3( a.acc.x[site.idx], a.acc.y[site.idx], a.acc.z[site.idx] );
+        const D3 out = solver_update<SOLVER, STAGE>( si, Fv, spi, Fvp, acc );
+        if( SOLVER == Solver_RK4 && STAGE < 4 )
+            store3( a.acc, site.idx, acc );
         store3( a.out, site.idx, out );
     }
     if( HOOK && last_stage )

@@ -1,7 +1,10 @@
 // Device-side LLG building blocks: virtual force, counter-based thermal field, and the
 // per-spin update rules of the solvers. Everything is evaluated in registers inside the fused
-// stage kernels (device/kernels.cu) -- the reference runs one full-field sweep per primitive
-// (~75 sweeps per Depondt iteration).
+// stage kernels (device/kernels.cuh, device/sc6.cuh) -- the reference runs one full-field sweep per
+// primitive (~75 sweeps per Depondt iteration).
+//
+// The step is close to the fp64-pipe / HBM balance point of B200, so the arithmetic here is
+// written for a minimal number of fp64 instructions: no divisions, polynomial coefficients as literals.
 #pragma once
 
 #include "stencil.cuh"
@@ -41,22 +44,62 @@ __device__ __forceinline__ void philox4x32_10( unsigned c0, unsigned c1, unsigne
     out[3] = c3;
 }
 
-// Three standard normal variates for (seed, iteration, global site): Box-Muller in fp64 on
-// uniforms of 32-bit resolution, u in (0,1).
+// MUFU-based fp32 primitives (approx, flush-to-zero): one SFU instruction each instead of the ~100-instruction fp64
+// library routines. They are used ONLY to shape the random variates of the thermal field.
+__device__ __forceinline__ float sfu_lg2( float x )
+{
+    float y;
+    asm( "lg2.approx.ftz.f32 %0, %1;" : "=f"( y ) : "f"( x ) );
+    return y;
+}
+__device__ __forceinline__ float sfu_sqrt( float x )
+{
+    float y;
+    asm( "sqrt.approx.ftz.f32 %0, %1;" : "=f"( y ) : "f"( x ) );
+    return y;
+}
+__device__ __forceinline__ float sfu_sin( float x )
+{
+    float y;
+    asm( "sin.approx.ftz.f32 %0, %1;" : "=f"( y ) : "f"( x ) );
+    return y;
+}
+__device__ __forceinline__ float sfu_cos( float x )
+{
+    float y;
+    asm( "cos.approx.ftz.f32 %0, %1;" : "=f"( y ) : "f"( x ) );
+    return y;
+}
+// 23 random bits -> float in (2^-24, 1)
+__device__ __forceinline__ float unit_open( unsigned r )
+{
+    return __uint_as_float( ( r >> 9 ) | 0x3f800000u ) - 0.99999994f;
+}
+
+// Three standard normal variates for (seed, iteration, global site): Philox4x32-10 -> Box-Muller. The variates are
+// shaped in fp32 with SFU instructions (23-bit uniforms, |error| of sin/cos/lg2 ~ 1e-6): they are random numbers
+// whose distribution, not whose digits, matters (T > 0 parity is statistical), and an fp64 Box-Muller
+// (log, sqrt, sincospi in software) costs more instructions than the whole rest of a solver stage, which would make
+// the step compute-bound instead of HBM-bound. Everything downstream of the variates is fp64.
 __device__ __forceinline__ D3 gaussian3( std::uint64_t seed, std::uint64_t iteration, std::uint64_t site )
 {
     unsigned r[4];
     philox4x32_10(
         unsigned( site ), unsigned( site >> 32 ), unsigned( iteration ), unsigned( iteration >> 32 ), unsigned( seed ),
         unsigned( seed >> 32 ), r );
-    const double scale = 2.3283064365386963e-10; // 2^-32
-    const double u0 = ( double( r[0] ) + 0.5 ) * scale, u1 = ( double( r[1] ) + 0.5 ) * scale;
-    const double u2 = ( double( r[2] ) + 0.5 ) * scale, u3 = ( double( r[3] ) + 0.5 ) * scale;
-    const double rad0 = sqrt( -2.0 * log( u0 ) ), rad1 = sqrt( -2.0 * log( u2 ) );
-    double s0, c0, s1;
-    sincospi( 2.0 * u1, &s0, &c0 );
-    s1 = sinpi( 2.0 * u3 );
-    return make_d3( rad0 * c0, rad0 * s0, rad1 * s1 );
+    const float rad0 = sfu_sqrt( -1.3862943611198906f * sfu_lg2( unit_open( r[0] ) ) ); // sqrt(-2 ln u)
+    const float rad1 = sfu_sqrt( -1.3862943611198906f * sfu_lg2( unit_open( r[2] ) ) );
+    const float ang0 = 6.2831853071795865f * unit_open( r[1] ) - 3.1415926535897932f;
+    const float ang1 = 6.2831853071795865f * unit_open( r[3] ) - 3.1415926535897932f;
+    return make_d3( double( rad0 * sfu_cos( ang0 ) ), double( rad0 * sfu_sin( ang0 ) ), double( rad1 * sfu_sin( ang1 ) ) );
+}
+
+// xi for the site with GLOBAL index gsite (reference site order) of basis atom ib
+__device__ __forceinline__ D3 thermal_field_at( const LLGParams & l, std::uint64_t gsite, int ib )
+{
+    const D3 n      = gaussian3( l.seed, l.iteration, gsite );
+    const double sc = l.thermal_scale[ib];
+    return make_d3( sc * n.x, sc * n.y, sc * n.z );
 }
 
 template<int NB_T>
@@ -66,28 +109,30 @@ __device__ __forceinline__ D3 thermal_field( const StencilParams & p, const LLGP
     const std::uint64_t gsite
         = std::uint64_t( site.a ) * p.NB + site.ib
           + std::uint64_t( p.Na ) * p.NB * ( std::uint64_t( site.b ) + std::uint64_t( p.Nb ) * ( p.c_begin + site.c ) );
-    const D3 n      = gaussian3( l.seed, l.iteration, gsite );
-    const double sc = l.thermal_scale[NB_T == 1 ? 0 : site.ib];
-    return make_d3( sc * n.x, sc * n.y, sc * n.z );
+    return thermal_field_at( l, gsite, NB_T == 1 ? 0 : site.ib );
 }
 
 // Virtual force (Method_LLG.cpp:131-226): F = -gradient.
 //   dynamics:      Fv = dtg/mu_s (F + alpha s x F) [+ STT monolayer] [+ xi + alpha s x xi]
 //   minimisation:  Fv = dtg' s x F
-template<int NB_T>
-__device__ __forceinline__ D3
-virtual_force( const LLGParams & l, const Site & site, const D3 & s, const D3 & F, const D3 & xi )
+// evaluated as Fv = c1 F + xi + s x (c2 F + alpha xi), c1 = dtg/mu_s, c2 = alpha c1: one cross product instead of two.
+__device__ __forceinline__ D3 virtual_force_ib( const LLGParams & l, int ib, const D3 & s, const D3 & F, const D3 & xi )
 {
     if( l.direct_minimization )
     {
         const D3 c = cross3( s, F );
         return make_d3( l.dtg * c.x, l.dtg * c.y, l.dtg * c.z );
     }
-    const D3 sxF     = cross3( s, F );
-    const double da  = l.dtg * l.damping;
-    const double ims = l.inv_mu_s[NB_T == 1 ? 0 : site.ib];
-    D3 fv            = make_d3(
-        ( l.dtg * F.x + da * sxF.x ) * ims, ( l.dtg * F.y + da * sxF.y ) * ims, ( l.dtg * F.z + da * sxF.z ) * ims );
+    const double c1 = l.c1[ib], c2 = l.c2[ib];
+    D3 w            = make_d3( c2 * F.x, c2 * F.y, c2 * F.z );
+    D3 fv           = make_d3( c1 * F.x, c1 * F.y, c1 * F.z );
+    if( l.has_thermal )
+    {
+        w  = make_d3( fma( l.damping, xi.x, w.x ), fma( l.damping, xi.y, w.y ), fma( l.damping, xi.z, w.z ) );
+        fv = make_d3( fv.x + xi.x, fv.y + xi.y, fv.z + xi.z );
+    }
+    const D3 sxw = cross3( s, w );
+    fv           = make_d3( fv.x + sxw.x, fv.y + sxw.y, fv.z + sxw.z );
     if( l.has_stt )
     {
         // monolayer approximation: Fv += c1 * pol + c2 * (pol x s)   (Method_LLG.cpp:207-212)
@@ -97,66 +142,57 @@ virtual_force( const LLGParams & l, const Site & site, const D3 & s, const D3 & 
         fv.y += l.stt_c1 * pol.y + l.stt_c2 * pxs.y;
         fv.z += l.stt_c1 * pol.z + l.stt_c2 * pxs.z;
     }
-    if( l.has_thermal )
-    {
-        const D3 sxxi = cross3( s, xi );
-        fv.x += xi.x + l.damping * sxxi.x;
-        fv.y += xi.y + l.damping * sxxi.y;
-        fv.z += xi.z + l.damping * sxxi.z;
-    }
     return fv;
 }
 
+template<int NB_T>
+__device__ __forceinline__ D3
+virtual_force( const LLGParams & l, const Site & site, const D3 & s, const D3 & F, const D3 & xi )
+{
+    return virtual_force_ib( l, NB_T == 1 ? 0 : site.ib, s, F, xi );
+}
+
 // Rodrigues rotation of v about H by the angle |H| (Depondt; Vectormath.cpp:474-485 with
-// axis = H/|H|, angle = |H|, Solver_Depondt.hpp:43-52). Written in terms of theta^2 = |H|^2:
+// axis = H/|H|, angle = |H|, Solver_Depondt.hpp:43-52). Written in terms of x = |H|^2:
 //   R v = v cos(t) + (H x v) sin(t)/t + H (H.v) (1-cos(t))/t^2
 // so that no normalisation of the axis (and no division by zero for H = 0) is needed.
-// For t^2 < 0.25 the three even functions are evaluated as polynomials in t^2 (truncation < 1e-17);
-// otherwise through sincos.
+// For x < 1/16 the even functions sin(t)/t and (1-cos t)/t^2 are degree-6 polynomials in x (truncation
+// < 1.1e-17 relative); otherwise through sincos. dt-sized steps always take the polynomial branch.
 __device__ __forceinline__ D3 rotate_about( const D3 & v, const D3 & H )
 {
-    const double t2 = dot3( H, H );
+    const double x = dot3( H, H );
     double c, sinc, omc; // cos t, sin t / t, (1 - cos t)/t^2
-    if( t2 < 0.25 )
+    if( x < 0.0625 )
     {
-        // Horner in x = t^2: sinc = sum (-x)^k/(2k+1)!, omc = sum (-x)^k/(2k+2)!
-        const double x = t2;
-        sinc = 1.0
-               - x / 6.0
-                     * ( 1.0
-                         - x / 20.0
-                               * ( 1.0
-                                   - x / 42.0
-                                         * ( 1.0
-                                             - x / 72.0
-                                                   * ( 1.0
-                                                       - x / 110.0
-                                                             * ( 1.0 - x / 156.0 * ( 1.0 - x / 210.0 * ( 1.0 - x / 272.0 ) ) ) ) ) ) );
-        omc = 0.5
-              * ( 1.0
-                  - x / 12.0
-                        * ( 1.0
-                            - x / 30.0
-                                  * ( 1.0
-                                      - x / 56.0
-                                            * ( 1.0
-                                                - x / 90.0
-                                                      * ( 1.0
-                                                          - x / 132.0
-                                                                * ( 1.0 - x / 182.0 * ( 1.0 - x / 240.0 * ( 1.0 - x / 306.0 ) ) ) ) ) ) ) );
-        c = 1.0 - x * omc;
+        sinc = 1.6059043836821613e-10;                  // 1/13!
+        sinc = fma( sinc, x, -2.5052108385441720e-08 ); // -1/11!
+        sinc = fma( sinc, x, 2.7557319223985893e-06 );  // 1/9!
+        sinc = fma( sinc, x, -1.9841269841269841e-04 ); // -1/7!
+        sinc = fma( sinc, x, 8.3333333333333332e-03 );  // 1/5!
+        sinc = fma( sinc, x, -1.6666666666666666e-01 ); // -1/3!
+        sinc = fma( sinc, x, 1.0 );
+        omc  = 1.1470745597729725e-11;                  // 1/14!
+        omc  = fma( omc, x, -2.0876756987868100e-09 );  // -1/12!
+        omc  = fma( omc, x, 2.7557319223985888e-07 );   // 1/10!
+        omc  = fma( omc, x, -2.4801587301587302e-05 );  // -1/8!
+        omc  = fma( omc, x, 1.3888888888888889e-03 );   // 1/6!
+        omc  = fma( omc, x, -4.1666666666666664e-02 );  // -1/4!
+        omc  = fma( omc, x, 0.5 );
+        c    = fma( -x, omc, 1.0 );
     }
     else
     {
-        const double t = sqrt( t2 );
+        const double t = sqrt( x );
         double sn;
         sincos( t, &sn, &c );
         sinc = sn / t;
-        omc  = ( 1.0 - c ) / t2;
+        omc  = ( 1.0 - c ) / x;
     }
     const D3 Hxv    = cross3( H, v );
     const double hv = dot3( H, v ) * omc;
-    return make_d3( v.x * c + Hxv.x * sinc + H.x * hv, v.y * c + Hxv.y * sinc + H.y * hv, v.z * c + Hxv.z * sinc + H.z * hv );
+    return make_d3(
+        fma( v.x, c, fma( Hxv.x, sinc, H.x * hv ) ), fma( v.y, c, fma( Hxv.y, sinc, H.y * hv ) ),
+        fma( v.z, c, fma( Hxv.z, sinc, H.z * hv ) ) );
 }
 
 // Eigen's normalize(): leaves the zero vector untouched
@@ -165,7 +201,7 @@ __device__ __forceinline__ D3 normalized3( const D3 & v )
     const double n2 = dot3( v, v );
     if( n2 > 0 )
     {
-        const double inv = 1.0 / sqrt( n2 );
+        const double inv = rsqrt( n2 );
         return make_d3( v.x * inv, v.y * inv, v.z * inv );
     }
     return v;
@@ -184,6 +220,67 @@ __device__ __forceinline__ D3 sib_transform( const D3 & s, const D3 & force )
     o.z = ( a2.x * ( A.z * A.x - A.y ) + a2.y * ( A.z * A.y + A.x ) + a2.z * ( A.z * A.z + 1 ) ) * detAi;
     return o;
 }
+
+// ---------------------------------------------------------------------------------------------
+// Per-site update rules of the explicit solvers, shared by the generic and the specialised stage kernels.
+//   Depondt (Solver_Depondt.hpp:29-77)  stage 1: s' = R(Fv(s)) s          stage 2: s <- R((Fv(s)+Fv(s'))/2) s
+//   Heun    (Solver_Heun.hpp:30-81)     stage 1: s' = |s - s x Fv(s)|     stage 2: s <- |s + k1/2 + k2/2|
+//   SIB     (Solver_SIB.hpp:22-50)      stage 1: s' = (s + T(s,Fv(s)))/2  stage 2: s <- T(s, Fv(s'))
+//   RK4     (Solver_RK4.hpp:41-147)     stages 1-4 with a running accumulator acc = k1/6 + k2/3 + k3/3
+// si / Fv: configuration at the start of the iteration and its virtual force (where the stage needs it);
+// spi / Fvp: the current predictor and its virtual force (stages >= 2). acc: RK4 accumulator, updated in place.
+// ---------------------------------------------------------------------------------------------
+template<int SOLVER, int STAGE>
+__device__ __forceinline__ D3 solver_update( const D3 & si, const D3 & Fv, const D3 & spi, const D3 & Fvp, D3 & acc )
+{
+    if( SOLVER == Solver_Depondt )
+    {
+        if( STAGE == 1 )
+            return rotate_about( si, Fv );
+        return rotate_about( si, make_d3( 0.5 * ( Fv.x + Fvp.x ), 0.5 * ( Fv.y + Fvp.y ), 0.5 * ( Fv.z + Fvp.z ) ) );
+    }
+    else if( SOLVER == Solver_Heun )
+    {
+        const D3 k1 = cross3( Fv, si ); // -(s x Fv)
+        if( STAGE == 1 )
+            return normalized3( make_d3( si.x + k1.x, si.y + k1.y, si.z + k1.z ) );
+        const D3 k2 = cross3( Fvp, spi ); // -(s' x Fv')
+        return normalized3( make_d3(
+            si.x + 0.5 * k1.x + 0.5 * k2.x, si.y + 0.5 * k1.y + 0.5 * k2.y, si.z + 0.5 * k1.z + 0.5 * k2.z ) );
+    }
+    else if( SOLVER == Solver_SIB )
+    {
+        if( STAGE == 1 )
+        {
+            const D3 t = sib_transform( si, Fv );
+            return make_d3( 0.5 * ( t.x + si.x ), 0.5 * ( t.y + si.y ), 0.5 * ( t.z + si.z ) );
+        }
+        return sib_transform( si, Fvp );
+    }
+    else // RK4
+    {
+        // k_n = -(conf_n x Fv_n); intermediates are |s + c k_n| with c = 1/2, 1/2, 1
+        const D3 k     = STAGE == 1 ? cross3( Fv, si ) : cross3( Fvp, spi );
+        const double w = ( STAGE == 1 || STAGE == 4 ) ? 1.0 / 6.0 : 1.0 / 3.0;
+        acc            = make_d3( acc.x + w * k.x, acc.y + w * k.y, acc.z + w * k.z );
+        if( STAGE < 4 )
+        {
+            const double c = STAGE == 3 ? 1.0 : 0.5;
+            return normalized3( make_d3( si.x + c * k.x, si.y + c * k.y, si.z + c * k.z ) );
+        }
+        return normalized3( make_d3( si.x + acc.x, si.y + acc.y, si.z + acc.z ) );
+    }
+}
+
+// Which virtual forces a stage needs
+template<int SOLVER, int STAGE>
+struct StageNeeds
+{
+    static constexpr bool two_stage = SOLVER == Solver_Depondt || SOLVER == Solver_Heun || SOLVER == Solver_SIB;
+    static constexpr bool last      = ( two_stage && STAGE == 2 ) || ( SOLVER == Solver_RK4 && STAGE == 4 );
+    static constexpr bool Fv_s      = STAGE == 1 || ( STAGE == 2 && ( SOLVER == Solver_Depondt || SOLVER == Solver_Heun ) );
+    static constexpr bool Fv_sp     = STAGE >= 2;
+};
 
 } // namespace dev
 } // namespace sb

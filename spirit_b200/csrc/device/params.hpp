@@ -40,7 +40,7 @@ struct Neighbour
 struct Anisotropy
 {
     int ib;
-    int pad;
+    int flags; // bit k set: component k of the normal is non-zero (lets the kernels skip the zero terms)
     double K;
     double nx, ny, nz;
 };
@@ -64,6 +64,14 @@ struct StencilParams
     int c_begin, nc_local, halo;
     int pad0;
 
+    // Nearest-neighbour ("7-point") structure, detected on the host: one basis atom and the merged neighbour list is
+    // a subset of {+-a, +-b, +-c} with J(+) == J(-) and D(+) == -D(-). Served by the marching kernels of sc6.cuh.
+    int sc6;
+    int sc6_axis[3];   // neighbours along a / b / c present
+    int sc6_dflags[3]; // bit k set: component k of sc6_D[axis] is non-zero
+    double sc6_J[3];
+    double sc6_D[3][3]; // D_magnitude * normal of the +direction neighbour of each axis
+
     double K4[MAX_BASIS];        // cubic anisotropy per basis atom (Hamiltonian_Heisenberg.cpp:802-820)
     double zeeman[MAX_BASIS][3]; // mu_s[ib] * (B mu_B) * n_B   (Hamiltonian_Heisenberg.cpp:768-783)
     double mu_s[MAX_BASIS];
@@ -86,6 +94,8 @@ struct LLGParams
     int pad;
     double thermal_scale[MAX_BASIS]; // epsilon*sqrt(T/mu_s[ib])
     double inv_mu_s[MAX_BASIS];
+    double c1[MAX_BASIS];    // dtg / mu_s[ib]
+    double c2[MAX_BASIS];    // alpha * dtg / mu_s[ib]
     std::uint64_t seed;      // Philox key
     std::uint64_t iteration; // Philox counter high words: one xi per iteration, shared by all stages
 };
