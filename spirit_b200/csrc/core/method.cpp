@@ -191,10 +191,17 @@ dev::LLGParams Method_LLG::make_params( const Spin_System & system, int solver )
         l.inv_mu_s[ib]       = 1.0 / mu;
         l.c1[ib]             = l.dtg / mu;
         l.c2[ib]             = l.damping * l.dtg / mu;
+        l.nc1[ib]            = -l.c1[ib];
+        l.nc2[ib]            = -l.c2[ib];
         l.thermal_scale[ib]  = l.has_thermal ? epsilon * std::sqrt( P.temperature / mu ) : 0.0;
     }
     l.seed      = std::uint64_t( std::uint32_t( P.rng_seed ) ) | ( std::uint64_t( 0x5b200 ) << 32 );
     l.iteration = P.philox_counter;
+    for( unsigned r = 0; r < 10; ++r )
+    {
+        l.philox_key[r][0] = unsigned( l.seed ) + r * 0x9E3779B9u;
+        l.philox_key[r][1] = unsigned( l.seed >> 32 ) + r * 0xBB67AE85u;
+    }
     return l;
 }
 

@@ -27,7 +27,7 @@ namespace dev
 struct DeviceField
 {
     double * base = nullptr;
-    std::size_t n = 0; // elements per component (storage, including halo planes)
+    std::size_t n = 0; // storage sites (padded planes, including halo planes); a multiple of 32
 
     void allocate( std::size_t n_ )
     {
@@ -49,25 +49,15 @@ struct DeviceField
     Field3 f() const
     {
         Field3 r;
-        r.x = base;
-        r.y = base + n;
-        r.z = base + 2 * n;
+        r.base = base;
         return r;
     }
     ConstField3 c() const
     {
         ConstField3 r;
-        r.x = base;
-        r.y = base + n;
-        r.z = base + 2 * n;
+        r.base = base;
         return r;
     }
-};
-
-struct SC6Launch
-{
-    dim3 grid, block;
-    int lc = 1; // planes per CTA (march length)
 };
 
 struct DeviceBuffers
@@ -78,8 +68,8 @@ struct DeviceBuffers
 
     LaunchGeom lg{};
     int nblocks            = 0;
-    std::size_t n_storage  = 0; // sites stored per component (with halos)
-    int interior_offset    = 0; // storage index of site 0 of the owned range
+    std::size_t n_storage  = 0; // storage sites per field (padded planes, with halo planes)
+    int plane_sites        = 0; // real sites per plane: Na*NB*Nb
 
     DeviceField spins, pred, next; // configuration ping-pong
     DeviceField pred2;             // RK4 second predictor

@@ -189,9 +189,10 @@ DeviceImage::DeviceImage( const Geometry & g )
     auto & b          = *buf_;
     b.lg              = make_geom( stencil_ );
     b.nblocks         = b.lg.blocks_x * b.lg.blocks_y;
-    b.n_storage       = std::size_t( nos_ );
+    stencil_.plane_stride = ( ( stencil_.Na * stencil_.NB * stencil_.Nb + FIELD_BLOCK - 1 ) / FIELD_BLOCK ) * FIELD_BLOCK;
+    b.plane_sites         = stencil_.Na * stencil_.NB * stencil_.Nb;
+    b.n_storage           = std::size_t( stencil_.plane_stride ) * ( stencil_.nc_local + 2 * stencil_.halo );
     b.sc6             = make_sc6_launch( stencil_ );
-    b.interior_offset = 0;
     SB_CUDA_CHECK( cudaStreamCreateWithFlags( &b.stream, cudaStreamNonBlocking ) );
     SB_CUDA_CHECK( cudaEventCreate( &b.ev_start ) );
     SB_CUDA_CHECK( cudaEventCreate( &b.ev_stop ) );
@@ -288,7 +289,7 @@ void DeviceImage::set_hamiltonian( const Hamiltonian & ham )
     for( int d = 0; d < 3; ++d )
     {
         p.sc6_axis[d] = p.sc6_dflags[d] = 0;
-        p.sc6_J[d]                      = 0;
+        p.sc6_J[d] = p.sc6_nJ[d] = 0;
         for( int k = 0; k < 3; ++k )
             p.sc6_D[d][k] = 0;
     }
@@ -325,6 +326,7 @@ void DeviceImage::set_hamiltonian( const Hamiltonian & ham )
             }
             p.sc6_axis[d]   = 1;
             p.sc6_J[d]      = plus[d]->J;
+            p.sc6_nJ[d]     = -plus[d]->J;
             p.sc6_D[d][0]   = plus[d]->Dx;
             p.sc6_D[d][1]   = plus[d]->Dy;
             p.sc6_D[d][2]   = plus[d]->Dz;
@@ -361,12 +363,42 @@ void DeviceImage::set_hamiltonian( const Hamiltonian & ham )
             p.zeeman[ib][d]
                 = ib < g.n_cell_atoms ? g.cell_mu_s[ib] * ham.external_field_magnitude * ham.external_field_normal[d] : 0.0;
 
+    // sc6: on-site quadratic form, start value, and the template SPEC of the marching kernels
+    for( int k = 0; k < 6; ++k )
+        p.sc6_A[k] = 0;
+    for( int i = 0; i < p.n_aniso; ++i )
+        if( p.aniso[i].ib == 0 )
+        {
+            const double n[3] = { p.aniso[i].nx, p.aniso[i].ny, p.aniso[i].nz };
+            const double f    = -2.0 * p.aniso[i].K;
+            p.sc6_A[0] += f * n[0] * n[0];
+            p.sc6_A[1] += f * n[1] * n[1];
+            p.sc6_A[2] += f * n[2] * n[2];
+            p.sc6_A[3] += f * n[0] * n[1];
+            p.sc6_A[4] += f * n[0] * n[2];
+            p.sc6_A[5] += f * n[1] * n[2];
+        }
+    for( int d = 0; d < 3; ++d )
+        p.sc6_g0[d] = p.has_zeeman ? -p.zeeman[0][d] : 0.0;
+    {
+        int spec = 0;
+        if( p.sc6_axis[2] )
+            spec |= SC6_HAS_C;
+        for( int d = 0; d < 3; ++d )
+            if( p.sc6_dflags[d] & ~( 1 << d ) )
+                spec |= SC6_DMI_GENERAL;
+        if( p.sc6_A[3] != 0 || p.sc6_A[4] != 0 || p.sc6_A[5] != 0 )
+            spec |= SC6_ANISO_FULL;
+        buf_->sc6.spec = spec;
+    }
+
     p.has_ddi = 0;
     if( ham.ddi_method == DDI_Method::FFT )
         throw std::runtime_error( "spirit_b200: ddi_method fft is not implemented yet" );
     else if( ham.ddi_method != DDI_Method::None )
         throw std::runtime_error( "spirit_b200: only ddi_method none/fft are in scope (SURVEY.md 2.2)" );
 
+    p.sc6_extras  = ( p.has_cubic || p.has_ddi ) ? 1 : 0;
     ham_revision_ = ham.revision;
 }
 
@@ -379,18 +411,19 @@ void DeviceImage::upload_spins( const double * host_aos )
     SB_CUDA_CHECK( cudaMemcpyAsync(
         b.staging, host_aos, 3 * std::size_t( nos_ ) * sizeof( double ), cudaMemcpyHostToDevice, b.stream ) );
     k_aos_to_soa<<<( nos_ + BLOCK_THREADS - 1 ) / BLOCK_THREADS, BLOCK_THREADS, 0, b.stream>>>(
-        b.staging, b.spins.f(), nos_, b.interior_offset );
+        b.staging, b.spins.f(), nos_, b.plane_sites, stencil_.plane_stride, stencil_.halo );
     ++launches_;
     SB_CUDA_CHECK( cudaGetLastError() );
 }
 
 static void download_field(
-    DeviceBuffers & b, const DeviceField & f, double * host_aos, int nos, double scale, std::uint64_t & launches )
+    DeviceBuffers & b, const StencilParams & p, const DeviceField & f, double * host_aos, int nos, double scale,
+    std::uint64_t & launches )
 {
     if( !b.staging )
         SB_CUDA_CHECK( cudaMalloc( &b.staging, 3 * std::size_t( nos ) * sizeof( double ) ) );
     k_soa_to_aos<<<( nos + BLOCK_THREADS - 1 ) / BLOCK_THREADS, BLOCK_THREADS, 0, b.stream>>>(
-        f.c(), b.staging, nos, b.interior_offset, scale );
+        f.c(), b.staging, nos, b.plane_sites, p.plane_stride, p.halo, scale );
     ++launches;
     SB_CUDA_CHECK( cudaGetLastError() );
     SB_CUDA_CHECK( cudaMemcpyAsync(
@@ -400,14 +433,14 @@ static void download_field(
 
 void DeviceImage::download_spins( double * host_aos )
 {
-    download_field( *buf_, buf_->spins, host_aos, nos_, 1.0, launches_ );
+    download_field( *buf_, stencil_, buf_->spins, host_aos, nos_, 1.0, launches_ );
 }
 
 void DeviceImage::download_effective_field( double * host_aos )
 {
     if( !buf_->F.allocated() )
         throw std::runtime_error( "spirit_b200: effective field requested before it was computed" );
-    download_field( *buf_, effective_field_in_Fv_ ? buf_->Fv : buf_->F, host_aos, nos_, 1.0, launches_ );
+    download_field( *buf_, stencil_, effective_field_in_Fv_ ? buf_->Fv : buf_->F, host_aos, nos_, 1.0, launches_ );
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -445,7 +478,7 @@ void DeviceImage::gradient_and_energy( double * gradient_host_aos, double * ener
     reduce_sum_to( b, b.partials, 4, launches_ );
     SB_CUDA_CHECK( cudaMemcpyAsync( b.h_scalars + 4, b.scalars + 4, sizeof( double ), cudaMemcpyDeviceToHost, b.stream ) );
     if( gradient_host_aos )
-        download_field( b, b.scratch, gradient_host_aos, nos_, 1.0, launches_ );
+        download_field( b, stencil_, b.scratch, gradient_host_aos, nos_, 1.0, launches_ );
     SB_CUDA_CHECK( cudaStreamSynchronize( b.stream ) );
     if( energy )
         *energy = b.h_scalars[4];
@@ -558,7 +591,14 @@ void launch_stage(
     {
         // nearest-neighbour structure: marching kernel (the hook iteration, which also stores F, Fv and reduces the
         // energy, goes through the generic kernel)
-        k_sc6_stage<SOLVER, STAGE><<<sc6.grid, sc6.block, 0, stream>>>( p, sc6.lc, l, a );
+        if( SOLVER == Solver_Depondt )
+            sc6_launch_depondt( STAGE, sc6, stream, p, l, a );
+        else if( SOLVER == Solver_Heun )
+            sc6_launch_heun( STAGE, sc6, stream, p, l, a );
+        else if( SOLVER == Solver_SIB )
+            sc6_launch_sib( STAGE, sc6, stream, p, l, a );
+        else
+            sc6_launch_rk4( STAGE, sc6, stream, p, l, a );
         return;
     }
     if( nb1 )

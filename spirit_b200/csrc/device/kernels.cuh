@@ -127,26 +127,31 @@ static __global__ void __launch_bounds__( BLOCK_THREADS ) k_reduce_max( const do
 // Layout conversion at the C-API boundary: host arrays are AoS [nos][3] in the reference's site
 // order; device fields are planar with (optional) halo planes.
 // ---------------------------------------------------------------------------------------------
-static __global__ void __launch_bounds__( BLOCK_THREADS )
-    k_aos_to_soa( const double * __restrict__ aos, Field3 f, int n, int offset )
+// i: index in the reference's site order (no padding, no halo) -> storage index
+__device__ __forceinline__ std::size_t storage_of_linear( int i, int plane_sites, int plane_stride, int halo )
 {
-    const int i = blockIdx.x * BLOCK_THREADS + threadIdx.x;
-    if( i < n )
-    {
-        f.x[offset + i] = aos[3 * std::size_t( i ) + 0];
-        f.y[offset + i] = aos[3 * std::size_t( i ) + 1];
-        f.z[offset + i] = aos[3 * std::size_t( i ) + 2];
-    }
+    const int c = i / plane_sites;
+    return std::size_t( i - c * plane_sites ) + std::size_t( plane_stride ) * ( c + halo );
 }
 static __global__ void __launch_bounds__( BLOCK_THREADS )
-    k_soa_to_aos( ConstField3 f, double * __restrict__ aos, int n, int offset, double scale )
+    k_aos_to_soa( const double * __restrict__ aos, Field3 f, int n, int plane_sites, int plane_stride, int halo )
+{
+    const int i = blockIdx.x * BLOCK_THREADS + threadIdx.x;
+    if( i < n )
+        store3(
+            f, storage_of_linear( i, plane_sites, plane_stride, halo ),
+            make_d3( aos[3 * std::size_t( i ) + 0], aos[3 * std::size_t( i ) + 1], aos[3 * std::size_t( i ) + 2] ) );
+}
+static __global__ void __launch_bounds__( BLOCK_THREADS )
+    k_soa_to_aos( ConstField3 f, double * __restrict__ aos, int n, int plane_sites, int plane_stride, int halo, double scale )
 {
     const int i = blockIdx.x * BLOCK_THREADS + threadIdx.x;
     if( i < n )
     {
-        aos[3 * std::size_t( i ) + 0] = scale * f.x[offset + i];
-        aos[3 * std::size_t( i ) + 1] = scale * f.y[offset + i];
-        aos[3 * std::size_t( i ) + 2] = scale * f.z[offset + i];
+        const D3 v                    = load3( f, storage_of_linear( i, plane_sites, plane_stride, halo ) );
+        aos[3 * std::size_t( i ) + 0] = scale * v.x;
+        aos[3 * std::size_t( i ) + 1] = scale * v.y;
+        aos[3 * std::size_t( i ) + 2] = scale * v.z;
     }
 }
 
@@ -329,7 +334,7 @@ static __global__ void __launch_bounds__( BLOCK_THREADS ) k_llg_stage(
 
         D3 acc = make_d3( 0, 0, 0 );
         if( SOLVER == Solver_RK4 && STAGE > 1 )
-            acc = make_d3( a.acc.x[site.idx], a.acc.y[site.idx], a.acc.z[site.idx] );
+            acc = load3( a.acc, site.idx );
         const D3 out = solver_update<SOLVER, STAGE>( si, Fv, spi, Fvp, acc );
         if( SOLVER == Solver_RK4 && STAGE < 4 )
             store3( a.acc, site.idx, acc );
@@ -373,7 +378,7 @@ static __global__ void __launch_bounds__( BLOCK_THREADS ) k_vp_a(
         const D3 Fn             = make_d3( -gt.x, -gt.y, -gt.z );
         // velocity of the last iteration = ratio_prev * (raw force of the last iteration); F_prev is the same force,
         // or its tangential projection if a post-iteration hook ran in between (SURVEY.md 8c hazard 6)
-        const D3 Fr             = make_d3( F.x[site.idx], F.y[site.idx], F.z[site.idx] );
+        const D3 Fr             = load3( F, site.idx );
         const D3 Fp             = load3( F_prev, site.idx );
         const D3 v              = make_d3(
             ratio_prev * Fr.x + 0.5 * ( Fp.x + Fn.x ), ratio_prev * Fr.y + 0.5 * ( Fp.y + Fn.y ),
@@ -418,7 +423,7 @@ static __global__ void __launch_bounds__( BLOCK_THREADS ) k_vp_b(
     if( active )
     {
         const double ratio = scal[3];
-        const D3 si        = make_d3( s.x[site.idx], s.y[site.idx], s.z[site.idx] );
+        const D3 si        = load3( s, site.idx );
         D3 Fi              = load3( F, site.idx );
         const double c     = dt * ratio + 0.5 * dt;
         const D3 sn        = normalized3( make_d3( si.x + c * Fi.x, si.y + c * Fi.y, si.z + c * Fi.z ) );
@@ -462,7 +467,7 @@ static __global__ void __launch_bounds__( BLOCK_THREADS ) k_hook(
         const double d = dot3( fv, si );
         const D3 tq    = make_d3( fv.x - d * si.x, fv.y - d * si.y, fv.z - d * si.z );
         t2             = dot3( tq, tq );
-        const D3 Fi    = make_d3( F.x[site.idx], F.y[site.idx], F.z[site.idx] );
+        const D3 Fi    = load3( F, site.idx );
         const double f = dot3( Fi, si );
         store3( F, site.idx, make_d3( Fi.x - f * si.x, Fi.y - f * si.y, Fi.z - f * si.z ) );
     }

@@ -62,15 +62,20 @@ struct StencilParams
     // Slab decomposition along c (multi-GPU): this device stores planes [c_begin - halo, c_begin + nc_local + halo).
     // Single device: c_begin = 0, nc_local = Nc, halo = 0 and periodic c wraps locally.
     int c_begin, nc_local, halo;
-    int pad0;
+    int plane_stride; // storage sites per plane: Na*NB*Nb rounded up to a multiple of 32
 
     // Nearest-neighbour ("7-point") structure, detected on the host: one basis atom and the merged neighbour list is
     // a subset of {+-a, +-b, +-c} with J(+) == J(-) and D(+) == -D(-). Served by the marching kernels of sc6.cuh.
     int sc6;
     int sc6_axis[3];   // neighbours along a / b / c present
     int sc6_dflags[3]; // bit k set: component k of sc6_D[axis] is non-zero
+    int sc6_extras;    // has_cubic || has_ddi: rare terms behind one flag
+    int sc6_pad;
     double sc6_J[3];
+    double sc6_nJ[3];   // -J
     double sc6_D[3][3]; // D_magnitude * normal of the +direction neighbour of each axis
+    double sc6_A[6];    // on-site quadratic form -2 sum_k K_k n_k n_k^T of basis atom 0: xx, yy, zz, xy, xz, yz
+    double sc6_g0[3];   // -mu_s B n: start value of the gradient accumulation
 
     double K4[MAX_BASIS];        // cubic anisotropy per basis atom (Hamiltonian_Heisenberg.cpp:802-820)
     double zeeman[MAX_BASIS][3]; // mu_s[ib] * (B mu_B) * n_B   (Hamiltonian_Heisenberg.cpp:768-783)
@@ -96,6 +101,9 @@ struct LLGParams
     double inv_mu_s[MAX_BASIS];
     double c1[MAX_BASIS];    // dtg / mu_s[ib]
     double c2[MAX_BASIS];    // alpha * dtg / mu_s[ib]
+    double nc1[MAX_BASIS];   // -c1
+    double nc2[MAX_BASIS];   // -c2
+    unsigned philox_key[10][2]; // round keys of Philox4x32-10: (seed_lo + r W0, seed_hi + r W1)
     std::uint64_t seed;      // Philox key
     std::uint64_t iteration; // Philox counter high words: one xi per iteration, shared by all stages
 };

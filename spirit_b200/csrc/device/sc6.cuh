@@ -7,14 +7,21 @@
 // planes. Each thread keeps its own column (c-1, c, c+1) in registers, so per plane it reads one new own-column
 // value (the only access that has to come from HBM) and the four in-plane neighbours, which are the own-column
 // values of neighbouring threads of the same plane step and hit L1 (+-a, +-b inside the CTA) or L2 (the two
-// halo rows above / below the CTA's rows). All index arithmetic, boundary handling and the Philox round keys
-// are hoisted out of the plane loop. L2->SM traffic per field is (BY+2)/BY x 24 B per site instead of 5-7 x.
+// halo rows above / below the CTA's rows). L2->SM traffic per field is (BY+2)/BY x 24 B per site instead of 5-7 x.
+//
+// The step sits near the balance point of B200's fp64 pipe (16 lanes per SM sub-partition: one DFMA warp
+// instruction per 2 cycles) and HBM, so the plane loop is written for a minimal instruction count:
+//   * all index arithmetic and boundary handling is hoisted out of the loop; inside it a neighbour costs one
+//     64-bit address (plane pointer + 32-bit element offset) and three loads at immediate offsets (AoSoA-32);
+//   * the Hamiltonian's structure is a template parameter (SPEC): no flag tests or constant reloads per plane;
+//   * CTAs that touch no open boundary run a loop without predicated loads or zero-selects (BOUNDARY = false);
+//   * signs and prefactors are folded into host-computed constants, the Philox round keys come from the host.
 //
 // HBM traffic per site: stage 1 reads s (24 B) and writes s' (24 B); stage 2 of Depondt/Heun reads s and s'
 // and writes the new configuration (72 B), recomputing the stage-1 virtual force instead of storing it.
 #pragma once
 
-#include "llg.cuh"
+#include "kernels.cuh"
 
 namespace sb
 {
@@ -23,156 +30,175 @@ namespace dev
 
 constexpr int SC6_MAX_THREADS = 512;
 
-// load or zero: open boundaries / absent axes contribute a zero spin
-__device__ __forceinline__ D3 ld3v( const ConstField3 & f, std::size_t idx, bool valid )
+// SPEC bits
+constexpr int SC6_HAS_C       = 1; // neighbours along c exist (3-D system)
+constexpr int SC6_DMI_GENERAL = 2; // DMI vectors are not parallel to their bonds (else: axis a -> Dx, b -> Dy, c -> Dz only)
+constexpr int SC6_ANISO_FULL  = 4; // the on-site quadratic form has off-diagonal elements
+constexpr int SC6_N_SPECS     = 8;
+
+struct SC6Launch
+{
+    dim3 grid, block;
+    int lc   = 1; // planes per CTA (march length)
+    int spec = 0;
+};
+
+__device__ __forceinline__ D3 ld3p( const double * __restrict__ plane, unsigned e )
+{
+    const double * q = plane + e;
+    return make_d3( __ldg( q ), __ldg( q + FIELD_BLOCK ), __ldg( q + 2 * FIELD_BLOCK ) );
+}
+// load or zero: open boundaries contribute a zero spin
+__device__ __forceinline__ D3 ld3pv( const double * __restrict__ plane, unsigned e, bool valid )
 {
     D3 r = make_d3( 0.0, 0.0, 0.0 );
     if( valid )
-        r = make_d3( __ldg( f.x + idx ), __ldg( f.y + idx ), __ldg( f.z + idx ) );
+        r = ld3p( plane, e );
     return r;
 }
 
 // Contribution of the neighbour pair (minus, plus) along one axis:
 //   g -= J (s+ + s-) + (s+ - s-) x D        [ D(+) = D, D(-) = -D ]
 // which is Gradient_Exchange + Gradient_DMI (Hamiltonian_Heisenberg.cpp:822-864) for the two redundant pairs.
-template<int AXIS>
+template<int AXIS, bool DMI_GENERAL>
 __device__ __forceinline__ void sc6_axis_gradient( const StencilParams & p, const D3 & m, const D3 & pl, D3 & g )
 {
-    if( !p.sc6_axis[AXIS] )
-        return;
-    const double J = p.sc6_J[AXIS];
-    g.x            = fma( -J, m.x + pl.x, g.x );
-    g.y            = fma( -J, m.y + pl.y, g.y );
-    g.z            = fma( -J, m.z + pl.z, g.z );
-    const int fl   = p.sc6_dflags[AXIS];
-    if( fl )
+    const double nJ = p.sc6_nJ[AXIS]; // -J
+    g.x             = fma( nJ, m.x + pl.x, g.x );
+    g.y             = fma( nJ, m.y + pl.y, g.y );
+    g.z             = fma( nJ, m.z + pl.z, g.z );
+    const D3 d      = make_d3( pl.x - m.x, pl.y - m.y, pl.z - m.z );
+    // g -= d x D,  d x D = (d.y Dz - d.z Dy, d.z Dx - d.x Dz, d.x Dy - d.y Dx)
+    if( DMI_GENERAL || AXIS == 0 )
     {
-        const D3 d = make_d3( pl.x - m.x, pl.y - m.y, pl.z - m.z );
-        // d x D = (d.y Dz - d.z Dy, d.z Dx - d.x Dz, d.x Dy - d.y Dx), zero components of D skipped
-        if( fl & 1 )
-        {
-            const double D = p.sc6_D[AXIS][0];
-            g.y            = fma( -D, d.z, g.y );
-            g.z            = fma( D, d.y, g.z );
-        }
-        if( fl & 2 )
-        {
-            const double D = p.sc6_D[AXIS][1];
-            g.x            = fma( D, d.z, g.x );
-            g.z            = fma( -D, d.x, g.z );
-        }
-        if( fl & 4 )
-        {
-            const double D = p.sc6_D[AXIS][2];
-            g.x            = fma( -D, d.y, g.x );
-            g.y            = fma( D, d.x, g.y );
-        }
+        const double D = p.sc6_D[AXIS][0];
+        g.y            = fma( -D, d.z, g.y );
+        g.z            = fma( D, d.y, g.z );
+    }
+    if( DMI_GENERAL || AXIS == 1 )
+    {
+        const double D = p.sc6_D[AXIS][1];
+        g.x            = fma( D, d.z, g.x );
+        g.z            = fma( -D, d.x, g.z );
+    }
+    if( DMI_GENERAL || AXIS == 2 )
+    {
+        const double D = p.sc6_D[AXIS][2];
+        g.x            = fma( -D, d.y, g.x );
+        g.y            = fma( D, d.x, g.y );
     }
 }
 
-// Full site gradient from the six neighbour spins (same split as site_gradient of stencil.cuh)
-__device__ __forceinline__ SiteGradient sc6_site_gradient(
+// Gradient of all terms at one site from its six neighbour spins.
+//   start value: -mu_s B n (Zeeman, Hamiltonian_Heisenberg.cpp:768-783; zero without a field)
+//   on-site quadratic form: g += A s with A = -2 sum_k K_k n_k n_k^T (uniaxial anisotropies, :785-800)
+//   rare terms behind one uniform flag: cubic anisotropy (:802-820), precomputed dipolar field
+template<int SPEC>
+__device__ __forceinline__ D3 sc6_gradient(
     const StencilParams & p, const D3 & si, const D3 & xm, const D3 & xp, const D3 & bm, const D3 & bp, const D3 & cm,
-    const D3 & cp, const ConstField3 & ddi, std::size_t idx )
+    const D3 & cp, const double * __restrict__ ddi_plane, unsigned e )
 {
-    SiteGradient out;
-    D3 g = make_d3( 0.0, 0.0, 0.0 );
-    sc6_axis_gradient<0>( p, xm, xp, g );
-    sc6_axis_gradient<1>( p, bm, bp, g );
-    sc6_axis_gradient<2>( p, cm, cp, g );
-    // Uniaxial anisotropy: g -= 2 K (n.s) n   (Hamiltonian_Heisenberg.cpp:785-800)
-    for( int i = 0; i < p.n_aniso; ++i )
+    D3 g = make_d3( p.sc6_g0[0], p.sc6_g0[1], p.sc6_g0[2] );
+    sc6_axis_gradient<0, ( SPEC & SC6_DMI_GENERAL ) != 0>( p, xm, xp, g );
+    sc6_axis_gradient<1, ( SPEC & SC6_DMI_GENERAL ) != 0>( p, bm, bp, g );
+    if( SPEC & SC6_HAS_C )
+        sc6_axis_gradient<2, ( SPEC & SC6_DMI_GENERAL ) != 0>( p, cm, cp, g );
+    g.x = fma( p.sc6_A[0], si.x, g.x );
+    g.y = fma( p.sc6_A[1], si.y, g.y );
+    g.z = fma( p.sc6_A[2], si.z, g.z );
+    if( SPEC & SC6_ANISO_FULL )
     {
-        const Anisotropy & an = p.aniso[i];
-        if( an.ib != 0 )
-            continue;
-        double d = 0.0;
-        if( an.flags & 1 )
-            d = an.nx * si.x;
-        if( an.flags & 2 )
-            d = fma( an.ny, si.y, d );
-        if( an.flags & 4 )
-            d = fma( an.nz, si.z, d );
-        d *= -2.0 * an.K;
-        if( an.flags & 1 )
-            g.x = fma( d, an.nx, g.x );
-        if( an.flags & 2 )
-            g.y = fma( d, an.ny, g.y );
-        if( an.flags & 4 )
-            g.z = fma( d, an.nz, g.z );
+        g.x = fma( p.sc6_A[3], si.y, fma( p.sc6_A[4], si.z, g.x ) );
+        g.y = fma( p.sc6_A[3], si.x, fma( p.sc6_A[5], si.z, g.y ) );
+        g.z = fma( p.sc6_A[4], si.x, fma( p.sc6_A[5], si.y, g.z ) );
     }
-    if( p.has_ddi )
+    if( p.sc6_extras )
     {
-        g.x += __ldg( ddi.x + idx );
-        g.y += __ldg( ddi.y + idx );
-        g.z += __ldg( ddi.z + idx );
+        if( p.has_cubic )
+        {
+            const double k = -2.0 * p.K4[0];
+            g.x            = fma( k * si.x, si.x * si.x, g.x );
+            g.y            = fma( k * si.y, si.y * si.y, g.y );
+            g.z            = fma( k * si.z, si.z * si.z, g.z );
+        }
+        if( p.has_ddi )
+        {
+            const D3 gd = ld3p( ddi_plane, e );
+            g.x += gd.x;
+            g.y += gd.y;
+            g.z += gd.z;
+        }
     }
-    out.bilinear = g;
-    D3 r         = make_d3( 0.0, 0.0, 0.0 );
-    if( p.has_cubic )
-    {
-        const double k = 2.0 * p.K4[0];
-        r.x -= k * si.x * si.x * si.x;
-        r.y -= k * si.y * si.y * si.y;
-        r.z -= k * si.z * si.z * si.z;
-    }
-    if( p.has_zeeman )
-    {
-        r.x -= p.zeeman[0][0];
-        r.y -= p.zeeman[0][1];
-        r.z -= p.zeeman[0][2];
-    }
-    out.rest = r;
-    return out;
+    return g;
 }
 
-// In-plane neighbour offsets of a thread's column and the plane bookkeeping of the march
-struct SC6Column
+// Virtual force from the gradient g = -F (Method_LLG.cpp:131-226), signs folded into nc1 = -dtg/mu_s, nc2 = alpha nc1:
+//   dynamics:      Fv = nc1 g + xi + s x (nc2 g + alpha xi)
+//   minimisation:  Fv = -dtg' s x g
+__device__ __forceinline__ D3 sc6_virtual_force( const LLGParams & l, bool thermal, const D3 & s, const D3 & g, const D3 & xi )
 {
-    int oc, oxm, oxp, obm, obp; // offsets inside a plane
-    bool vxm, vxp, vbm, vbp;
-    std::size_t plane_stride;
-};
-
-__device__ __forceinline__ SC6Column sc6_column( const StencilParams & p, int x, int b )
-{
-    SC6Column col;
-    int xm = x - 1, xp = x + 1, bm = b - 1, bp = b + 1;
-    col.vxm = col.vxp = p.sc6_axis[0] != 0;
-    col.vbm = col.vbp = p.sc6_axis[1] != 0;
-    if( xm < 0 )
+    D3 w, fv;
+    if( l.direct_minimization )
     {
-        xm += p.Na;
-        col.vxm = col.vxm && p.bc[0];
+        w  = make_d3( -l.dtg * g.x, -l.dtg * g.y, -l.dtg * g.z );
+        fv = make_d3( 0.0, 0.0, 0.0 );
     }
-    if( xp >= p.Na )
+    else
     {
-        xp -= p.Na;
-        col.vxp = col.vxp && p.bc[0];
+        const double nc1 = l.nc1[0], nc2 = l.nc2[0];
+        if( thermal )
+        {
+            w  = make_d3( fma( nc2, g.x, l.damping * xi.x ), fma( nc2, g.y, l.damping * xi.y ), fma( nc2, g.z, l.damping * xi.z ) );
+            fv = make_d3( fma( nc1, g.x, xi.x ), fma( nc1, g.y, xi.y ), fma( nc1, g.z, xi.z ) );
+        }
+        else
+        {
+            w  = make_d3( nc2 * g.x, nc2 * g.y, nc2 * g.z );
+            fv = make_d3( nc1 * g.x, nc1 * g.y, nc1 * g.z );
+        }
     }
-    if( bm < 0 )
+    fv.x = fma( s.y, w.z, fma( -s.z, w.y, fv.x ) );
+    fv.y = fma( s.z, w.x, fma( -s.x, w.z, fv.y ) );
+    fv.z = fma( s.x, w.y, fma( -s.y, w.x, fv.z ) );
+    if( l.has_stt && !l.direct_minimization )
     {
-        bm += p.Nb;
-        col.vbm = col.vbm && p.bc[1];
+        const D3 pol = make_d3( l.stt_pol[0], l.stt_pol[1], l.stt_pol[2] );
+        const D3 pxs = cross3( pol, s );
+        fv.x += l.stt_c1 * pol.x + l.stt_c2 * pxs.x;
+        fv.y += l.stt_c1 * pol.y + l.stt_c2 * pxs.y;
+        fv.z += l.stt_c1 * pol.z + l.stt_c2 * pxs.z;
     }
-    if( bp >= p.Nb )
-    {
-        bp -= p.Nb;
-        col.vbp = col.vbp && p.bc[1];
-    }
-    const int row    = p.Na * b;
-    col.oc           = row + x;
-    col.oxm          = row + xm;
-    col.oxp          = row + xp;
-    col.obm          = p.Na * bm + x;
-    col.obp          = p.Na * bp + x;
-    col.plane_stride = std::size_t( p.Na ) * p.Nb;
-    return col;
+    return fv;
 }
 
-// Storage offset of the plane that holds the c-neighbour `cc` (= c-1 or c+1, local index). The plane always exists in
-// storage (periodic wrap on one device, halo planes on a slab); whether it CONTRIBUTES is sc6_c_valid.
-__device__ __forceinline__ std::size_t sc6_c_plane( const StencilParams & p, const SC6Column & col, int cc )
+// xi of one site: Philox4x32-10 with the host-expanded round keys (LLGParams::philox_key)
+__device__ __forceinline__ D3 sc6_thermal_field( const LLGParams & l, std::uint64_t gsite )
+{
+    unsigned c0 = unsigned( gsite ), c1 = unsigned( gsite >> 32 ), c2 = unsigned( l.iteration ), c3 = unsigned( l.iteration >> 32 );
+#pragma unroll
+    for( int r = 0; r < 10; ++r )
+    {
+        const std::uint64_t p0 = std::uint64_t( 0xD2511F53u ) * c0;
+        const std::uint64_t p1 = std::uint64_t( 0xCD9E8D57u ) * c2;
+        const unsigned n0 = unsigned( p1 >> 32 ) ^ c1 ^ l.philox_key[r][0];
+        const unsigned n2 = unsigned( p0 >> 32 ) ^ c3 ^ l.philox_key[r][1];
+        c1                = unsigned( p1 );
+        c3                = unsigned( p0 );
+        c0                = n0;
+        c2                = n2;
+    }
+    const float rad0 = sfu_sqrt( -1.3862943611198906f * sfu_lg2( unit_open( c0 ) ) );
+    const float rad1 = sfu_sqrt( -1.3862943611198906f * sfu_lg2( unit_open( c2 ) ) );
+    const float ang0 = 6.2831853071795865f * unit_open( c1 ) - 3.1415926535897932f;
+    const float ang1 = 6.2831853071795865f * unit_open( c3 ) - 3.1415926535897932f;
+    const double sc  = l.thermal_scale[0];
+    return make_d3( sc * double( rad0 * sfu_cos( ang0 ) ), sc * double( rad0 * sfu_sin( ang0 ) ), sc * double( rad1 * sfu_sin( ang1 ) ) );
+}
+
+// Element offset (inside the plane pointer of a field) of the plane that holds the c-neighbour `cc` (= c-1 or c+1,
+// local index). The plane always exists in storage (periodic wrap on one device, halo planes on a slab); whether it
+// CONTRIBUTES is sc6_c_valid.
+__device__ __forceinline__ std::size_t sc6_c_plane( const StencilParams & p, int cc )
 {
     if( p.halo == 0 )
     {
@@ -180,41 +206,179 @@ __device__ __forceinline__ std::size_t sc6_c_plane( const StencilParams & p, con
             cc += p.Nc;
         else if( cc >= p.Nc )
             cc -= p.Nc;
-        return std::size_t( cc ) * col.plane_stride;
+        return std::size_t( cc ) * ( 3 * std::size_t( p.plane_stride ) );
     }
-    return std::size_t( cc + p.halo ) * col.plane_stride;
+    return std::size_t( cc + p.halo ) * ( 3 * std::size_t( p.plane_stride ) );
 }
 __device__ __forceinline__ bool sc6_c_valid( const StencilParams & p, int cc )
 {
     const int gc = p.c_begin + cc;
-    return p.sc6_axis[2] != 0 && ( p.bc[2] || ( gc >= 0 && gc < p.Nc ) );
+    return p.bc[2] || ( gc >= 0 && gc < p.Nc );
 }
 
-// Virtual force of the configuration `f` at the thread's site of the current plane. (below, center, above) is the
-// thread's column of `f`; the in-plane neighbours are gathered here.
-__device__ __forceinline__ D3 sc6_virtual_force(
-    const StencilParams & p, const LLGParams & l, const SC6Column & col, const ConstField3 & f, const ConstField3 & ddi,
-    std::size_t base, const D3 & below_raw, bool vb, const D3 & center, const D3 & above_raw, bool va, const D3 & xi )
+// The march of one thread over the planes [c0, c1) of its column (x, b).
+template<int SOLVER, int STAGE, int SPEC, bool BOUNDARY>
+__device__ __forceinline__ void sc6_march(
+    const StencilParams & p, const LLGParams & l, const StageArgs & a, const int x, const int b, const int c0, const int c1 )
 {
-    const D3 zero        = make_d3( 0.0, 0.0, 0.0 );
-    const D3 below       = vb ? below_raw : zero;
-    const D3 above       = va ? above_raw : zero;
-    const D3 xm          = ld3v( f, base + col.oxm, col.vxm );
-    const D3 xp          = ld3v( f, base + col.oxp, col.vxp );
-    const D3 bm          = ld3v( f, base + col.obm, col.vbm );
-    const D3 bp          = ld3v( f, base + col.obp, col.vbp );
-    const SiteGradient g = sc6_site_gradient( p, center, xm, xp, bm, bp, below, above, ddi, base + col.oc );
-    const D3 gt          = total( g );
-    return virtual_force_ib( l, 0, center, make_d3( -gt.x, -gt.y, -gt.z ), xi );
+    using Needs          = StageNeeds<SOLVER, STAGE>;
+    constexpr bool HAS_C = ( SPEC & SC6_HAS_C ) != 0;
+
+    // in-plane neighbours: site offsets -> element offsets (AoSoA-32)
+    int xm = x - 1, xp = x + 1, bm = b - 1, bp = b + 1;
+    bool vxm = true, vxp = true, vbm = true, vbp = true;
+    if( xm < 0 )
+    {
+        xm += p.Na;
+        vxm = p.bc[0];
+    }
+    if( xp >= p.Na )
+    {
+        xp -= p.Na;
+        vxp = p.bc[0];
+    }
+    if( bm < 0 )
+    {
+        bm += p.Nb;
+        vbm = p.bc[1];
+    }
+    if( bp >= p.Nb )
+    {
+        bp -= p.Nb;
+        vbp = p.bc[1];
+    }
+    const int row      = p.Na * b;
+    const unsigned ec  = unsigned( elem_offset( row + x ) );
+    const unsigned exm = unsigned( elem_offset( row + xm ) ), exp_ = unsigned( elem_offset( row + xp ) );
+    const unsigned ebm = unsigned( elem_offset( p.Na * bm + x ) ), ebp = unsigned( elem_offset( p.Na * bp + x ) );
+    const std::size_t plane_elems = 3 * std::size_t( p.plane_stride );
+
+    const bool thermal = l.has_thermal && !l.direct_minimization;
+    // global index of the site (x, b, c_begin + c0) in the reference's order: Philox counter
+    std::uint64_t gsite = std::uint64_t( row + x ) + std::uint64_t( p.Na ) * p.Nb * std::uint64_t( p.c_begin + c0 );
+
+    // the thread's columns: s (needed with neighbours only if this stage evaluates Fv(s)) and the predictor
+    const D3 zero = make_d3( 0.0, 0.0, 0.0 );
+    D3 s_below = zero, s_center, s_above = zero;
+    D3 p_below = zero, p_center = zero, p_above = zero;
+    {
+        const std::size_t base = std::size_t( c0 + p.halo ) * plane_elems;
+        s_center               = ld3p( a.s.base + base, ec );
+        if( Needs::Fv_sp )
+            p_center = ld3p( a.sp.base + base, ec );
+        if( HAS_C )
+        {
+            const std::size_t pb = sc6_c_plane( p, c0 - 1 );
+            if( Needs::Fv_s )
+                s_below = ld3p( a.s.base + pb, ec );
+            if( Needs::Fv_sp )
+                p_below = ld3p( a.sp.base + pb, ec );
+        }
+    }
+
+    for( int c = c0; c < c1; ++c )
+    {
+        const std::size_t base = std::size_t( c + p.halo ) * plane_elems;
+        const std::size_t pa   = HAS_C ? sc6_c_plane( p, c + 1 ) : base + plane_elems;
+        // own column, next plane. Without neighbours of s (SIB stage 2, RK4 stages 2-4) only the centre is needed.
+        if( ( HAS_C && Needs::Fv_s ) || c + 1 < c1 )
+            s_above = ld3p( a.s.base + pa, ec );
+        if( Needs::Fv_sp && ( HAS_C || c + 1 < c1 ) )
+            p_above = ld3p( a.sp.base + pa, ec );
+        bool vb = true, va = true;
+        if( BOUNDARY && HAS_C )
+        {
+            vb = sc6_c_valid( p, c - 1 );
+            va = sc6_c_valid( p, c + 1 );
+        }
+
+        D3 xi = zero;
+        if( thermal )
+            xi = sc6_thermal_field( l, gsite );
+
+        D3 Fv = zero, Fvp = zero;
+        if( Needs::Fv_s )
+        {
+            const double * pl = a.s.base + base;
+            D3 nxm, nxp, nbm, nbp, ncm = s_below, ncp = s_above;
+            if( BOUNDARY )
+            {
+                nxm = ld3pv( pl, exm, vxm );
+                nxp = ld3pv( pl, exp_, vxp );
+                nbm = ld3pv( pl, ebm, vbm );
+                nbp = ld3pv( pl, ebp, vbp );
+                ncm = vb ? s_below : zero;
+                ncp = va ? s_above : zero;
+            }
+            else
+            {
+                nxm = ld3p( pl, exm );
+                nxp = ld3p( pl, exp_ );
+                nbm = ld3p( pl, ebm );
+                nbp = ld3p( pl, ebp );
+            }
+            const D3 g = sc6_gradient<SPEC>( p, s_center, nxm, nxp, nbm, nbp, ncm, ncp, a.ddi_s.base + base, ec );
+            Fv         = sc6_virtual_force( l, thermal, s_center, g, xi );
+        }
+        if( Needs::Fv_sp )
+        {
+            const double * pl = a.sp.base + base;
+            D3 nxm, nxp, nbm, nbp, ncm = p_below, ncp = p_above;
+            if( BOUNDARY )
+            {
+                nxm = ld3pv( pl, exm, vxm );
+                nxp = ld3pv( pl, exp_, vxp );
+                nbm = ld3pv( pl, ebm, vbm );
+                nbp = ld3pv( pl, ebp, vbp );
+                ncm = vb ? p_below : zero;
+                ncp = va ? p_above : zero;
+            }
+            else
+            {
+                nxm = ld3p( pl, exm );
+                nxp = ld3p( pl, exp_ );
+                nbm = ld3p( pl, ebm );
+                nbp = ld3p( pl, ebp );
+            }
+            const D3 g = sc6_gradient<SPEC>( p, p_center, nxm, nxp, nbm, nbp, ncm, ncp, a.ddi_sp.base + base, ec );
+            Fvp        = sc6_virtual_force( l, thermal, p_center, g, xi );
+        }
+
+        D3 acc = zero;
+        if( SOLVER == Solver_RK4 && STAGE > 1 )
+        {
+            const double * q = a.acc.base + base + ec;
+            acc              = make_d3( q[0], q[FIELD_BLOCK], q[2 * FIELD_BLOCK] );
+        }
+        const D3 out = solver_update<SOLVER, STAGE>( s_center, Fv, p_center, Fvp, acc );
+        if( SOLVER == Solver_RK4 && STAGE < 4 )
+        {
+            double * q         = a.acc.base + base + ec;
+            q[0]               = acc.x;
+            q[FIELD_BLOCK]     = acc.y;
+            q[2 * FIELD_BLOCK] = acc.z;
+        }
+        {
+            double * q         = a.out.base + base + ec;
+            q[0]               = out.x;
+            q[FIELD_BLOCK]     = out.y;
+            q[2 * FIELD_BLOCK] = out.z;
+        }
+
+        // march
+        s_below  = s_center;
+        s_center = s_above;
+        p_below  = p_center;
+        p_center = p_above;
+        gsite += std::uint64_t( p.Na ) * p.Nb;
+    }
 }
 
-template<int SOLVER, int STAGE>
+template<int SOLVER, int STAGE, int SPEC>
 static __global__ void __launch_bounds__( SC6_MAX_THREADS ) k_sc6_stage(
     const __grid_constant__ StencilParams p, const int lc, const __grid_constant__ LLGParams l,
     const __grid_constant__ StageArgs a )
 {
-    using Needs = StageNeeds<SOLVER, STAGE>;
-
     const int x = blockIdx.x * blockDim.x + threadIdx.x;
     const int b = blockIdx.y * blockDim.y + threadIdx.y;
     if( x >= p.Na || b >= p.Nb )
@@ -222,70 +386,45 @@ static __global__ void __launch_bounds__( SC6_MAX_THREADS ) k_sc6_stage(
     const int c0 = blockIdx.z * lc;
     const int c1 = min( c0 + lc, p.nc_local );
 
-    const SC6Column col = sc6_column( p, x, b );
-    const bool thermal  = l.has_thermal && !l.direct_minimization;
-    // global index of the site (x, b, c_begin + c0) in the reference's order: Philox counter
-    std::uint64_t gsite = std::uint64_t( col.oc ) + col.plane_stride * std::uint64_t( p.c_begin + c0 );
-
-    // the thread's columns: s (needed with neighbours only if this stage evaluates Fv(s)) and the predictor
-    D3 s_below = make_d3( 0, 0, 0 ), s_center, s_above = make_d3( 0, 0, 0 );
-    D3 p_below = make_d3( 0, 0, 0 ), p_center = make_d3( 0, 0, 0 ), p_above = make_d3( 0, 0, 0 );
-    {
-        const std::size_t pb   = sc6_c_plane( p, col, c0 - 1 );
-        const std::size_t base = std::size_t( c0 + p.halo ) * col.plane_stride;
-        s_center               = ld3v( a.s, base + col.oc, true );
-        if( Needs::Fv_s )
-            s_below = ld3v( a.s, pb + col.oc, true );
-        if( Needs::Fv_sp )
-        {
-            p_center = ld3v( a.sp, base + col.oc, true );
-            p_below  = ld3v( a.sp, pb + col.oc, true );
-        }
-    }
-
-    for( int c = c0; c < c1; ++c )
-    {
-        const std::size_t base = std::size_t( c + p.halo ) * col.plane_stride;
-        const std::size_t pa   = sc6_c_plane( p, col, c + 1 );
-        const bool vb = sc6_c_valid( p, c - 1 ), va = sc6_c_valid( p, c + 1 );
-        // own column, next plane. Without neighbours of s (SIB stage 2, RK4 stages 2-4) only the centre is needed.
-        if( Needs::Fv_s || c + 1 < c1 )
-            s_above = ld3v( a.s, pa + col.oc, true );
-        if( Needs::Fv_sp )
-            p_above = ld3v( a.sp, pa + col.oc, true );
-
-        D3 xi = make_d3( 0, 0, 0 );
-        if( thermal )
-            xi = thermal_field_at( l, gsite, 0 );
-
-        D3 Fv = make_d3( 0, 0, 0 ), Fvp = make_d3( 0, 0, 0 );
-        if( Needs::Fv_s )
-            Fv = sc6_virtual_force( p, l, col, a.s, a.ddi_s, base, s_below, vb, s_center, s_above, va, xi );
-        if( Needs::Fv_sp )
-            Fvp = sc6_virtual_force( p, l, col, a.sp, a.ddi_sp, base, p_below, vb, p_center, p_above, va, xi );
-
-        D3 acc = make_d3( 0, 0, 0 );
-        if( SOLVER == Solver_RK4 && STAGE > 1 )
-            acc = make_d3( a.acc.x[base + col.oc], a.acc.y[base + col.oc], a.acc.z[base + col.oc] );
-        const D3 out = solver_update<SOLVER, STAGE>( s_center, Fv, p_center, Fvp, acc );
-        if( SOLVER == Solver_RK4 && STAGE < 4 )
-        {
-            a.acc.x[base + col.oc] = acc.x;
-            a.acc.y[base + col.oc] = acc.y;
-            a.acc.z[base + col.oc] = acc.z;
-        }
-        a.out.x[base + col.oc] = out.x;
-        a.out.y[base + col.oc] = out.y;
-        a.out.z[base + col.oc] = out.z;
-
-        // march
-        s_below  = s_center;
-        s_center = s_above;
-        p_below  = p_center;
-        p_center = p_above;
-        gsite += col.plane_stride;
-    }
+    // Does this CTA touch an open boundary? (uniform) Interior CTAs run the loop without predicates.
+    const int x0 = blockIdx.x * blockDim.x, x1 = min( x0 + int( blockDim.x ), p.Na ) - 1;
+    const int b0 = blockIdx.y * blockDim.y, b1 = min( b0 + int( blockDim.y ), p.Nb ) - 1;
+    bool boundary = ( !p.bc[0] && ( x0 == 0 || x1 == p.Na - 1 ) ) || ( !p.bc[1] && ( b0 == 0 || b1 == p.Nb - 1 ) );
+    if( ( SPEC & SC6_HAS_C ) && !p.bc[2] )
+        boundary = boundary || ( p.c_begin + c0 == 0 ) || ( p.c_begin + c1 == p.Nc );
+    if( boundary )
+        sc6_march<SOLVER, STAGE, SPEC, true>( p, l, a, x, b, c0, c1 );
+    else
+        sc6_march<SOLVER, STAGE, SPEC, false>( p, l, a, x, b, c0, c1 );
 }
+
+// One launcher per solver, each in its own translation unit (sc6_<solver>.cu) so that the 8 SPEC x stage
+// instantiations compile in parallel.
+template<int SOLVER, int STAGE>
+void sc6_launch_stage(
+    const SC6Launch & L, cudaStream_t stream, const StencilParams & p, const LLGParams & l, const StageArgs & a )
+{
+#define SB_SC6_CASE( S )                                                                                               \
+    case S: k_sc6_stage<SOLVER, STAGE, S><<<L.grid, L.block, 0, stream>>>( p, L.lc, l, a ); break;
+    switch( L.spec )
+    {
+        SB_SC6_CASE( 0 )
+        SB_SC6_CASE( 1 )
+        SB_SC6_CASE( 2 )
+        SB_SC6_CASE( 3 )
+        SB_SC6_CASE( 4 )
+        SB_SC6_CASE( 5 )
+        SB_SC6_CASE( 6 )
+        SB_SC6_CASE( 7 )
+    }
+#undef SB_SC6_CASE
+}
+
+// defined in sc6_depondt.cu, sc6_heun.cu, sc6_sib.cu, sc6_rk4.cu
+void sc6_launch_depondt( int stage, const SC6Launch & L, cudaStream_t stream, const StencilParams & p, const LLGParams & l, const StageArgs & a );
+void sc6_launch_heun( int stage, const SC6Launch & L, cudaStream_t stream, const StencilParams & p, const LLGParams & l, const StageArgs & a );
+void sc6_launch_sib( int stage, const SC6Launch & L, cudaStream_t stream, const StencilParams & p, const LLGParams & l, const StageArgs & a );
+void sc6_launch_rk4( int stage, const SC6Launch & L, cudaStream_t stream, const StencilParams & p, const LLGParams & l, const StageArgs & a );
 
 } // namespace dev
 } // namespace sb

@@ -4,16 +4,17 @@
 // construction -- the same convention as the reference's OpenMP/CUDA builds, which double every
 // pair, Hamiltonian_Heisenberg.cpp:103-109,130-139,165-175).
 //
-// Data layout in HBM: three planar arrays x[], y[], z[] per field. The contiguous index of a row
-// is x = ib + NB*a, rows are b + Nb*(c_local + halo). A warp therefore reads 32 consecutive
-// doubles per component and neighbour: fully coalesced 256-B requests; the +-a neighbours hit
-// the same lines (L1), the +-b rows are re-used inside the CTA (several rows per CTA), the +-c
-// planes are re-used out of L2.
+// Data layout in HBM: AoSoA-32 (below). The contiguous index of a row is x = ib + NB*a, rows are ordered by b,
+// planes by c_local + halo. A warp reads 32 consecutive doubles per component and neighbour: fully coalesced
+// 256-B requests; the +-a neighbours hit the same lines (L1), the +-b rows are re-used inside the CTA, the
+// +-c planes are re-used out of L2 (generic kernels) or kept in registers (marching kernels, sc6.cuh).
 #pragma once
 
 #include "params.hpp"
 
 #include <cuda_runtime.h>
+
+#include <cstddef>
 
 namespace sb
 {
@@ -42,28 +43,44 @@ __device__ __forceinline__ D3 cross3( const D3 & a, const D3 & b )
     return make_d3( a.y * b.z - a.z * b.y, a.z * b.x - a.x * b.z, a.x * b.y - a.y * b.x );
 }
 
+// Field layout in HBM: "AoSoA-32". Sites are grouped in blocks of 32 consecutive storage indices; a block stores
+// its 32 x components, then its 32 y, then its 32 z (768 B). A warp reading one component of 32 consecutive sites
+// reads 256 contiguous bytes (two full lines), and the three components of a site sit at fixed byte offsets
+// +0 / +256 / +512 from one address, so a neighbour costs ONE address computation and three loads with immediate
+// offsets (planar x[], y[], z[] arrays cost three 64-bit address computations per neighbour).
+constexpr int FIELD_BLOCK = 32;
+
+__device__ __host__ __forceinline__ std::size_t elem_offset( std::size_t idx )
+{
+    return ( idx >> 5 ) * ( 3 * FIELD_BLOCK ) + ( idx & ( FIELD_BLOCK - 1 ) );
+}
+
 struct ConstField3
 {
-    const double * __restrict__ x;
-    const double * __restrict__ y;
-    const double * __restrict__ z;
+    const double * __restrict__ base;
 };
 struct Field3
 {
-    double * __restrict__ x;
-    double * __restrict__ y;
-    double * __restrict__ z;
+    double * __restrict__ base;
 };
 
-__device__ __forceinline__ D3 load3( const ConstField3 & f, int idx )
+__device__ __forceinline__ D3 load3( const ConstField3 & f, std::size_t idx )
 {
-    return make_d3( __ldg( f.x + idx ), __ldg( f.y + idx ), __ldg( f.z + idx ) );
+    const double * q = f.base + elem_offset( idx );
+    return make_d3( __ldg( q ), __ldg( q + FIELD_BLOCK ), __ldg( q + 2 * FIELD_BLOCK ) );
 }
-__device__ __forceinline__ void store3( const Field3 & f, int idx, const D3 & v )
+// plain (coherent) load from a buffer that other kernels of the same stream write
+__device__ __forceinline__ D3 load3( const Field3 & f, std::size_t idx )
 {
-    f.x[idx] = v.x;
-    f.y[idx] = v.y;
-    f.z[idx] = v.z;
+    const double * q = f.base + elem_offset( idx );
+    return make_d3( q[0], q[FIELD_BLOCK], q[2 * FIELD_BLOCK] );
+}
+__device__ __forceinline__ void store3( const Field3 & f, std::size_t idx, const D3 & v )
+{
+    double * q          = f.base + elem_offset( idx );
+    q[0]               = v.x;
+    q[FIELD_BLOCK]     = v.y;
+    q[2 * FIELD_BLOCK] = v.z;
 }
 
 // Coordinates of the site a thread owns
@@ -74,9 +91,11 @@ struct Site
     int idx;     // storage index into the planar arrays
 };
 
+// Storage index of (x, b, c_local): planes are padded to a multiple of 32 sites (p.plane_stride) so that a step in
+// c moves every site by the same number of field elements.
 __device__ __forceinline__ int storage_index( const StencilParams & p, int x, int b, int c_local )
 {
-    return x + p.Na * p.NB * ( b + p.Nb * ( c_local + p.halo ) );
+    return x + p.Na * p.NB * b + p.plane_stride * ( c_local + p.halo );
 }
 
 // Gradient of the pair terms + uniaxial anisotropy ("bilinear" terms: E = 1/2 g.s), and of the
