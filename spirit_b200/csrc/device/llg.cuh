@@ -152,6 +152,13 @@ virtual_force( const LLGParams & l, const Site & site, const D3 & s, const D3 & 
     return virtual_force_ib( l, NB_T == 1 ? 0 : site.ib, s, F, xi );
 }
 
+// Taylor coefficients of sin(t)/t and (1-cos t)/t^2 in x = t^2: (-1)^k/(2k+1)! and (-1)^k/(2k+2)!. In constant
+// memory so that the DFMAs take them as constant-bank operands (64-bit literals would each cost two UMOVs per use).
+static __constant__ double ROT_SINC[7] = { 1.0, -1.6666666666666666e-01, 8.3333333333333332e-03, -1.9841269841269841e-04,
+                                           2.7557319223985893e-06, -2.5052108385441720e-08, 1.6059043836821613e-10 };
+static __constant__ double ROT_OMC[7]  = { 0.5, -4.1666666666666664e-02, 1.3888888888888889e-03, -2.4801587301587302e-05,
+                                          2.7557319223985888e-07, -2.0876756987868100e-09, 1.1470745597729725e-11 };
+
 // Rodrigues rotation of v about H by the angle |H| (Depondt; Vectormath.cpp:474-485 with
 // axis = H/|H|, angle = |H|, Solver_Depondt.hpp:43-52). Written in terms of x = |H|^2:
 //   R v = v cos(t) + (H x v) sin(t)/t + H (H.v) (1-cos(t))/t^2
@@ -164,19 +171,19 @@ __device__ __forceinline__ D3 rotate_about( const D3 & v, const D3 & H )
     double c, sinc, omc; // cos t, sin t / t, (1 - cos t)/t^2
     if( x < 0.0625 )
     {
-        sinc = 1.6059043836821613e-10;                  // 1/13!
-        sinc = fma( sinc, x, -2.5052108385441720e-08 ); // -1/11!
-        sinc = fma( sinc, x, 2.7557319223985893e-06 );  // 1/9!
-        sinc = fma( sinc, x, -1.9841269841269841e-04 ); // -1/7!
-        sinc = fma( sinc, x, 8.3333333333333332e-03 );  // 1/5!
-        sinc = fma( sinc, x, -1.6666666666666666e-01 ); // -1/3!
+        sinc = ROT_SINC[6];
+        sinc = fma( sinc, x, ROT_SINC[5] );
+        sinc = fma( sinc, x, ROT_SINC[4] );
+        sinc = fma( sinc, x, ROT_SINC[3] );
+        sinc = fma( sinc, x, ROT_SINC[2] );
+        sinc = fma( sinc, x, ROT_SINC[1] );
         sinc = fma( sinc, x, 1.0 );
-        omc  = 1.1470745597729725e-11;                  // 1/14!
-        omc  = fma( omc, x, -2.0876756987868100e-09 );  // -1/12!
-        omc  = fma( omc, x, 2.7557319223985888e-07 );   // 1/10!
-        omc  = fma( omc, x, -2.4801587301587302e-05 );  // -1/8!
-        omc  = fma( omc, x, 1.3888888888888889e-03 );   // 1/6!
-        omc  = fma( omc, x, -4.1666666666666664e-02 );  // -1/4!
+        omc  = ROT_OMC[6];
+        omc  = fma( omc, x, ROT_OMC[5] );
+        omc  = fma( omc, x, ROT_OMC[4] );
+        omc  = fma( omc, x, ROT_OMC[3] );
+        omc  = fma( omc, x, ROT_OMC[2] );
+        omc  = fma( omc, x, ROT_OMC[1] );
         omc  = fma( omc, x, 0.5 );
         c    = fma( -x, omc, 1.0 );
     }

@@ -216,75 +216,119 @@ __device__ __forceinline__ bool sc6_c_valid( const StencilParams & p, int cc )
     return p.bc[2] || ( gc >= 0 && gc < p.Nc );
 }
 
-// The march of one thread over the planes [c0, c1) of its column (x, b).
+// What a thread holds of one configuration while it marches: its own column and the in-plane neighbours of the
+// current plane.
+struct SC6Window
+{
+    D3 below, center, above; // own column at c-1, c, c+1
+    D3 xm, xp, bm, bp;       // in-plane neighbours at c
+};
+
+struct SC6Offsets
+{
+    unsigned ec, exm, exp_, ebm, ebp; // element offsets inside a plane
+    bool vxm, vxp, vbm, vbp;          // neighbour contributes (open boundaries)
+};
+
+template<bool BOUNDARY>
+__device__ __forceinline__ void sc6_load_inplane( SC6Window & w, const double * __restrict__ plane, const SC6Offsets & o )
+{
+    if( BOUNDARY )
+    {
+        w.xm = ld3pv( plane, o.exm, o.vxm );
+        w.xp = ld3pv( plane, o.exp_, o.vxp );
+        w.bm = ld3pv( plane, o.ebm, o.vbm );
+        w.bp = ld3pv( plane, o.ebp, o.vbp );
+    }
+    else
+    {
+        w.xm = ld3p( plane, o.exm );
+        w.xp = ld3p( plane, o.exp_ );
+        w.bm = ld3p( plane, o.ebm );
+        w.bp = ld3p( plane, o.ebp );
+    }
+}
+
+// The march of one thread over the planes [c0, c1) of its column (x, b). Software-pipelined by hand: right after
+// the gradients of plane c have consumed the neighbour registers, the loads of plane c+1 are issued into them and
+// travel while the thread does the remaining ~250 instructions of plane c (noise, virtual force, rotation, store).
 template<int SOLVER, int STAGE, int SPEC, bool BOUNDARY>
 __device__ __forceinline__ void sc6_march(
     const StencilParams & p, const LLGParams & l, const StageArgs & a, const int x, const int b, const int c0, const int c1 )
 {
     using Needs          = StageNeeds<SOLVER, STAGE>;
     constexpr bool HAS_C = ( SPEC & SC6_HAS_C ) != 0;
+    constexpr bool COL_S = HAS_C && Needs::Fv_s;  // s needs its c-neighbours
+    constexpr bool COL_P = HAS_C && Needs::Fv_sp; // s' needs its c-neighbours
 
     // in-plane neighbours: site offsets -> element offsets (AoSoA-32)
-    int xm = x - 1, xp = x + 1, bm = b - 1, bp = b + 1;
-    bool vxm = true, vxp = true, vbm = true, vbp = true;
-    if( xm < 0 )
+    SC6Offsets o;
     {
-        xm += p.Na;
-        vxm = p.bc[0];
+        int xm = x - 1, xp = x + 1, bm = b - 1, bp = b + 1;
+        o.vxm = o.vxp = o.vbm = o.vbp = true;
+        if( xm < 0 )
+        {
+            xm += p.Na;
+            o.vxm = p.bc[0];
+        }
+        if( xp >= p.Na )
+        {
+            xp -= p.Na;
+            o.vxp = p.bc[0];
+        }
+        if( bm < 0 )
+        {
+            bm += p.Nb;
+            o.vbm = p.bc[1];
+        }
+        if( bp >= p.Nb )
+        {
+            bp -= p.Nb;
+            o.vbp = p.bc[1];
+        }
+        const int row = p.Na * b;
+        o.ec          = unsigned( elem_offset( row + x ) );
+        o.exm         = unsigned( elem_offset( row + xm ) );
+        o.exp_        = unsigned( elem_offset( row + xp ) );
+        o.ebm         = unsigned( elem_offset( p.Na * bm + x ) );
+        o.ebp         = unsigned( elem_offset( p.Na * bp + x ) );
     }
-    if( xp >= p.Na )
-    {
-        xp -= p.Na;
-        vxp = p.bc[0];
-    }
-    if( bm < 0 )
-    {
-        bm += p.Nb;
-        vbm = p.bc[1];
-    }
-    if( bp >= p.Nb )
-    {
-        bp -= p.Nb;
-        vbp = p.bc[1];
-    }
-    const int row      = p.Na * b;
-    const unsigned ec  = unsigned( elem_offset( row + x ) );
-    const unsigned exm = unsigned( elem_offset( row + xm ) ), exp_ = unsigned( elem_offset( row + xp ) );
-    const unsigned ebm = unsigned( elem_offset( p.Na * bm + x ) ), ebp = unsigned( elem_offset( p.Na * bp + x ) );
     const std::size_t plane_elems = 3 * std::size_t( p.plane_stride );
 
     const bool thermal = l.has_thermal && !l.direct_minimization;
     // global index of the site (x, b, c_begin + c0) in the reference's order: Philox counter
-    std::uint64_t gsite = std::uint64_t( row + x ) + std::uint64_t( p.Na ) * p.Nb * std::uint64_t( p.c_begin + c0 );
+    std::uint64_t gsite = std::uint64_t( p.Na * b + x ) + std::uint64_t( p.Na ) * p.Nb * std::uint64_t( p.c_begin + c0 );
 
-    // the thread's columns: s (needed with neighbours only if this stage evaluates Fv(s)) and the predictor
     const D3 zero = make_d3( 0.0, 0.0, 0.0 );
-    D3 s_below = zero, s_center, s_above = zero;
-    D3 p_below = zero, p_center = zero, p_above = zero;
+    SC6Window ws, wp; // windows of s and of the predictor s'
+    ws.below = ws.above = wp.below = wp.center = wp.above = zero;
+    ws.xm = ws.xp = ws.bm = ws.bp = wp.xm = wp.xp = wp.bm = wp.bp = zero;
+
+    // prologue: plane c0 and the own-column value of plane c0 + 1
     {
         const std::size_t base = std::size_t( c0 + p.halo ) * plane_elems;
-        s_center               = ld3p( a.s.base + base, ec );
+        const std::size_t pa   = HAS_C ? sc6_c_plane( p, c0 + 1 ) : base + plane_elems;
+        ws.center              = ld3p( a.s.base + base, o.ec );
+        if( COL_S || c0 + 1 < c1 )
+            ws.above = ld3p( a.s.base + pa, o.ec );
+        if( COL_S )
+            ws.below = ld3p( a.s.base + sc6_c_plane( p, c0 - 1 ), o.ec );
+        if( Needs::Fv_s )
+            sc6_load_inplane<BOUNDARY>( ws, a.s.base + base, o );
         if( Needs::Fv_sp )
-            p_center = ld3p( a.sp.base + base, ec );
-        if( HAS_C )
         {
-            const std::size_t pb = sc6_c_plane( p, c0 - 1 );
-            if( Needs::Fv_s )
-                s_below = ld3p( a.s.base + pb, ec );
-            if( Needs::Fv_sp )
-                p_below = ld3p( a.sp.base + pb, ec );
+            wp.center = ld3p( a.sp.base + base, o.ec );
+            if( COL_P || c0 + 1 < c1 )
+                wp.above = ld3p( a.sp.base + pa, o.ec );
+            if( COL_P )
+                wp.below = ld3p( a.sp.base + sc6_c_plane( p, c0 - 1 ), o.ec );
+            sc6_load_inplane<BOUNDARY>( wp, a.sp.base + base, o );
         }
     }
 
     for( int c = c0; c < c1; ++c )
     {
         const std::size_t base = std::size_t( c + p.halo ) * plane_elems;
-        const std::size_t pa   = HAS_C ? sc6_c_plane( p, c + 1 ) : base + plane_elems;
-        // own column, next plane. Without neighbours of s (SIB stage 2, RK4 stages 2-4) only the centre is needed.
-        if( ( HAS_C && Needs::Fv_s ) || c + 1 < c1 )
-            s_above = ld3p( a.s.base + pa, ec );
-        if( Needs::Fv_sp && ( HAS_C || c + 1 < c1 ) )
-            p_above = ld3p( a.sp.base + pa, ec );
         bool vb = true, va = true;
         if( BOUNDARY && HAS_C )
         {
@@ -292,84 +336,73 @@ __device__ __forceinline__ void sc6_march(
             va = sc6_c_valid( p, c + 1 );
         }
 
+        // 1. gradients of plane c (consume the neighbour registers)
+        D3 gs = zero, gp = zero;
+        if( Needs::Fv_s )
+            gs = sc6_gradient<SPEC>(
+                p, ws.center, ws.xm, ws.xp, ws.bm, ws.bp, ( BOUNDARY && !vb ) ? zero : ws.below,
+                ( BOUNDARY && !va ) ? zero : ws.above, a.ddi_s.base + base, o.ec );
+        if( Needs::Fv_sp )
+            gp = sc6_gradient<SPEC>(
+                p, wp.center, wp.xm, wp.xp, wp.bm, wp.bp, ( BOUNDARY && !vb ) ? zero : wp.below,
+                ( BOUNDARY && !va ) ? zero : wp.above, a.ddi_sp.base + base, o.ec );
+
+        // 2. issue the loads of plane c + 1: in-plane neighbours and the own-column value of plane c + 2
+        D3 s_next2 = zero, p_next2 = zero;
+        if( c + 1 < c1 )
+        {
+            const std::size_t base1 = base + plane_elems;
+            const std::size_t pa2   = HAS_C ? sc6_c_plane( p, c + 2 ) : base1 + plane_elems;
+            if( COL_S || c + 2 < c1 )
+                s_next2 = ld3p( a.s.base + pa2, o.ec );
+            if( Needs::Fv_s )
+                sc6_load_inplane<BOUNDARY>( ws, a.s.base + base1, o );
+            if( Needs::Fv_sp )
+            {
+                if( COL_P || c + 2 < c1 )
+                    p_next2 = ld3p( a.sp.base + pa2, o.ec );
+                sc6_load_inplane<BOUNDARY>( wp, a.sp.base + base1, o );
+            }
+        }
+
+        // 3. the rest of plane c
         D3 xi = zero;
         if( thermal )
             xi = sc6_thermal_field( l, gsite );
-
         D3 Fv = zero, Fvp = zero;
         if( Needs::Fv_s )
-        {
-            const double * pl = a.s.base + base;
-            D3 nxm, nxp, nbm, nbp, ncm = s_below, ncp = s_above;
-            if( BOUNDARY )
-            {
-                nxm = ld3pv( pl, exm, vxm );
-                nxp = ld3pv( pl, exp_, vxp );
-                nbm = ld3pv( pl, ebm, vbm );
-                nbp = ld3pv( pl, ebp, vbp );
-                ncm = vb ? s_below : zero;
-                ncp = va ? s_above : zero;
-            }
-            else
-            {
-                nxm = ld3p( pl, exm );
-                nxp = ld3p( pl, exp_ );
-                nbm = ld3p( pl, ebm );
-                nbp = ld3p( pl, ebp );
-            }
-            const D3 g = sc6_gradient<SPEC>( p, s_center, nxm, nxp, nbm, nbp, ncm, ncp, a.ddi_s.base + base, ec );
-            Fv         = sc6_virtual_force( l, thermal, s_center, g, xi );
-        }
+            Fv = sc6_virtual_force( l, thermal, ws.center, gs, xi );
         if( Needs::Fv_sp )
-        {
-            const double * pl = a.sp.base + base;
-            D3 nxm, nxp, nbm, nbp, ncm = p_below, ncp = p_above;
-            if( BOUNDARY )
-            {
-                nxm = ld3pv( pl, exm, vxm );
-                nxp = ld3pv( pl, exp_, vxp );
-                nbm = ld3pv( pl, ebm, vbm );
-                nbp = ld3pv( pl, ebp, vbp );
-                ncm = vb ? p_below : zero;
-                ncp = va ? p_above : zero;
-            }
-            else
-            {
-                nxm = ld3p( pl, exm );
-                nxp = ld3p( pl, exp_ );
-                nbm = ld3p( pl, ebm );
-                nbp = ld3p( pl, ebp );
-            }
-            const D3 g = sc6_gradient<SPEC>( p, p_center, nxm, nxp, nbm, nbp, ncm, ncp, a.ddi_sp.base + base, ec );
-            Fvp        = sc6_virtual_force( l, thermal, p_center, g, xi );
-        }
+            Fvp = sc6_virtual_force( l, thermal, wp.center, gp, xi );
 
         D3 acc = zero;
         if( SOLVER == Solver_RK4 && STAGE > 1 )
         {
-            const double * q = a.acc.base + base + ec;
+            const double * q = a.acc.base + base + o.ec;
             acc              = make_d3( q[0], q[FIELD_BLOCK], q[2 * FIELD_BLOCK] );
         }
-        const D3 out = solver_update<SOLVER, STAGE>( s_center, Fv, p_center, Fvp, acc );
+        const D3 out = solver_update<SOLVER, STAGE>( ws.center, Fv, wp.center, Fvp, acc );
         if( SOLVER == Solver_RK4 && STAGE < 4 )
         {
-            double * q         = a.acc.base + base + ec;
+            double * q         = a.acc.base + base + o.ec;
             q[0]               = acc.x;
             q[FIELD_BLOCK]     = acc.y;
             q[2 * FIELD_BLOCK] = acc.z;
         }
         {
-            double * q         = a.out.base + base + ec;
+            double * q         = a.out.base + base + o.ec;
             q[0]               = out.x;
             q[FIELD_BLOCK]     = out.y;
             q[2 * FIELD_BLOCK] = out.z;
         }
 
-        // march
-        s_below  = s_center;
-        s_center = s_above;
-        p_below  = p_center;
-        p_center = p_above;
+        // 4. march
+        ws.below  = ws.center;
+        ws.center = ws.above;
+        ws.above  = s_next2;
+        wp.below  = wp.center;
+        wp.center = wp.above;
+        wp.above  = p_next2;
         gsite += std::uint64_t( p.Na ) * p.Nb;
     }
 }
