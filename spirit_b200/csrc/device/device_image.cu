@@ -387,8 +387,7 @@ void DeviceImage::set_hamiltonian( const Hamiltonian & ham )
         for( int d = 0; d < 3; ++d )
             if( p.sc6_dflags[d] & ~( 1 << d ) )
                 spec |= SC6_DMI_GENERAL;
-        if( p.sc6_A[3] != 0 || p.sc6_A[4] != 0 || p.sc6_A[5] != 0 )
-            spec |= SC6_ANISO_FULL;
+        p.sc6_aniso_full = ( p.sc6_A[3] != 0 || p.sc6_A[4] != 0 || p.sc6_A[5] != 0 ) ? 1 : 0;
         buf_->sc6.spec = spec;
     }
 

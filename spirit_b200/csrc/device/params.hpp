@@ -70,7 +70,7 @@ struct StencilParams
     int sc6_axis[3];   // neighbours along a / b / c present
     int sc6_dflags[3]; // bit k set: component k of sc6_D[axis] is non-zero
     int sc6_extras;    // has_cubic || has_ddi: rare terms behind one flag
-    int sc6_pad;
+    int sc6_aniso_full; // sc6_A has off-diagonal elements
     double sc6_J[3];
     double sc6_nJ[3];   // -J
     double sc6_D[3][3]; // D_magnitude * normal of the +direction neighbour of each axis

@@ -33,14 +33,18 @@ constexpr int SC6_MAX_THREADS = 512;
 // SPEC bits
 constexpr int SC6_HAS_C       = 1; // neighbours along c exist (3-D system)
 constexpr int SC6_DMI_GENERAL = 2; // DMI vectors are not parallel to their bonds (else: axis a -> Dx, b -> Dy, c -> Dz only)
-constexpr int SC6_ANISO_FULL  = 4; // the on-site quadratic form has off-diagonal elements
-constexpr int SC6_N_SPECS     = 8;
+constexpr int SC6_N_SPECS     = 4;
+// MODE: what the virtual force is made of (Method_LLG.cpp:131-226)
+constexpr int SC6_DYNAMICS = 0; // Fv = dtg/mu_s (F + alpha s x F) [+ STT]
+constexpr int SC6_THERMAL  = 1; // ... + xi + alpha s x xi
+constexpr int SC6_MINIMISE = 2; // Fv = dtg' s x F (direct minimisation)
+constexpr int SC6_N_MODES  = 3;
 
 struct SC6Launch
 {
     dim3 grid, block;
     int lc   = 1; // planes per CTA (march length)
-    int spec = 0;
+    int spec = 0; // SC6_HAS_C | SC6_DMI_GENERAL
 };
 
 __device__ __forceinline__ D3 ld3p( const double * __restrict__ plane, unsigned e )
@@ -106,7 +110,7 @@ __device__ __forceinline__ D3 sc6_gradient(
     g.x = fma( p.sc6_A[0], si.x, g.x );
     g.y = fma( p.sc6_A[1], si.y, g.y );
     g.z = fma( p.sc6_A[2], si.z, g.z );
-    if( SPEC & SC6_ANISO_FULL )
+    if( p.sc6_aniso_full ) // off-diagonal elements: anisotropy axes that are not lattice axes
     {
         g.x = fma( p.sc6_A[3], si.y, fma( p.sc6_A[4], si.z, g.x ) );
         g.y = fma( p.sc6_A[3], si.x, fma( p.sc6_A[5], si.z, g.y ) );
@@ -135,10 +139,11 @@ __device__ __forceinline__ D3 sc6_gradient(
 // Virtual force from the gradient g = -F (Method_LLG.cpp:131-226), signs folded into nc1 = -dtg/mu_s, nc2 = alpha nc1:
 //   dynamics:      Fv = nc1 g + xi + s x (nc2 g + alpha xi)
 //   minimisation:  Fv = -dtg' s x g
-__device__ __forceinline__ D3 sc6_virtual_force( const LLGParams & l, bool thermal, const D3 & s, const D3 & g, const D3 & xi )
+template<int MODE>
+__device__ __forceinline__ D3 sc6_virtual_force( const LLGParams & l, const D3 & s, const D3 & g, const D3 & xi )
 {
     D3 w, fv;
-    if( l.direct_minimization )
+    if( MODE == SC6_MINIMISE )
     {
         w  = make_d3( -l.dtg * g.x, -l.dtg * g.y, -l.dtg * g.z );
         fv = make_d3( 0.0, 0.0, 0.0 );
@@ -146,7 +151,7 @@ __device__ __forceinline__ D3 sc6_virtual_force( const LLGParams & l, bool therm
     else
     {
         const double nc1 = l.nc1[0], nc2 = l.nc2[0];
-        if( thermal )
+        if( MODE == SC6_THERMAL )
         {
             w  = make_d3( fma( nc2, g.x, l.damping * xi.x ), fma( nc2, g.y, l.damping * xi.y ), fma( nc2, g.z, l.damping * xi.z ) );
             fv = make_d3( fma( nc1, g.x, xi.x ), fma( nc1, g.y, xi.y ), fma( nc1, g.z, xi.z ) );
@@ -160,7 +165,7 @@ __device__ __forceinline__ D3 sc6_virtual_force( const LLGParams & l, bool therm
     fv.x = fma( s.y, w.z, fma( -s.z, w.y, fv.x ) );
     fv.y = fma( s.z, w.x, fma( -s.x, w.z, fv.y ) );
     fv.z = fma( s.x, w.y, fma( -s.y, w.x, fv.z ) );
-    if( l.has_stt && !l.direct_minimization )
+    if( MODE != SC6_MINIMISE && l.has_stt )
     {
         const D3 pol = make_d3( l.stt_pol[0], l.stt_pol[1], l.stt_pol[2] );
         const D3 pxs = cross3( pol, s );
@@ -249,17 +254,99 @@ __device__ __forceinline__ void sc6_load_inplane( SC6Window & w, const double * 
     }
 }
 
-// The march of one thread over the planes [c0, c1) of its column (x, b). Software-pipelined by hand: right after
-// the gradients of plane c have consumed the neighbour registers, the loads of plane c+1 are issued into them and
-// travel while the thread does the remaining ~250 instructions of plane c (noise, virtual force, rotation, store).
-template<int SOLVER, int STAGE, int SPEC, bool BOUNDARY>
-__device__ __forceinline__ void sc6_march(
-    const StencilParams & p, const LLGParams & l, const StageArgs & a, const int x, const int b, const int c0, const int c1 )
+// One plane step of a thread. (below, center, above) are its own-column registers for plane c; `below` is dead once
+// the gradient has consumed it and receives the own-column value of plane c + 2, so that three calls with cyclically
+// rotated arguments advance the march without a single register move.
+// Software-pipelined by hand: right after the gradients of plane c have consumed the neighbour registers, the loads
+// of plane c+1 are issued into them and travel while the thread does the remaining ~200 instructions of plane c
+// (noise, virtual force, rotation, store).
+template<int SOLVER, int STAGE, int SPEC, int MODE, bool BOUNDARY>
+__device__ __forceinline__ void sc6_plane_step(
+    const StencilParams & p, const LLGParams & l, const StageArgs & a, const SC6Offsets & o, const int c, const int c1,
+    const std::size_t plane_elems, const std::uint64_t gsite, D3 & s_below, const D3 & s_center, const D3 & s_above,
+    D3 & p_below, const D3 & p_center, const D3 & p_above, SC6Window & ws, SC6Window & wp )
 {
     using Needs          = StageNeeds<SOLVER, STAGE>;
     constexpr bool HAS_C = ( SPEC & SC6_HAS_C ) != 0;
     constexpr bool COL_S = HAS_C && Needs::Fv_s;  // s needs its c-neighbours
     constexpr bool COL_P = HAS_C && Needs::Fv_sp; // s' needs its c-neighbours
+    const D3 zero        = make_d3( 0.0, 0.0, 0.0 );
+
+    const std::size_t base = std::size_t( c + p.halo ) * plane_elems;
+    bool vb = true, va = true;
+    if( BOUNDARY && HAS_C )
+    {
+        vb = sc6_c_valid( p, c - 1 );
+        va = sc6_c_valid( p, c + 1 );
+    }
+
+    // 1. gradients of plane c (consume the neighbour registers)
+    D3 gs = zero, gp = zero;
+    if( Needs::Fv_s )
+        gs = sc6_gradient<SPEC>(
+            p, s_center, ws.xm, ws.xp, ws.bm, ws.bp, ( BOUNDARY && !vb ) ? zero : s_below, ( BOUNDARY && !va ) ? zero : s_above,
+            a.ddi_s.base + base, o.ec );
+    if( Needs::Fv_sp )
+        gp = sc6_gradient<SPEC>(
+            p, p_center, wp.xm, wp.xp, wp.bm, wp.bp, ( BOUNDARY && !vb ) ? zero : p_below, ( BOUNDARY && !va ) ? zero : p_above,
+            a.ddi_sp.base + base, o.ec );
+
+    // 2. issue the loads of plane c + 1: in-plane neighbours, and the own-column value of plane c + 2 into `below`
+    if( c + 1 < c1 )
+    {
+        const std::size_t base1 = base + plane_elems;
+        const std::size_t pa2   = HAS_C ? sc6_c_plane( p, c + 2 ) : base1 + plane_elems;
+        if( COL_S || c + 2 < c1 )
+            s_below = ld3p( a.s.base + pa2, o.ec );
+        if( Needs::Fv_s )
+            sc6_load_inplane<BOUNDARY>( ws, a.s.base + base1, o );
+        if( Needs::Fv_sp )
+        {
+            if( COL_P || c + 2 < c1 )
+                p_below = ld3p( a.sp.base + pa2, o.ec );
+            sc6_load_inplane<BOUNDARY>( wp, a.sp.base + base1, o );
+        }
+    }
+
+    // 3. the rest of plane c
+    D3 xi = zero;
+    if( MODE == SC6_THERMAL )
+        xi = sc6_thermal_field( l, gsite );
+    D3 Fv = zero, Fvp = zero;
+    if( Needs::Fv_s )
+        Fv = sc6_virtual_force<MODE>( l, s_center, gs, xi );
+    if( Needs::Fv_sp )
+        Fvp = sc6_virtual_force<MODE>( l, p_center, gp, xi );
+
+    D3 acc = zero;
+    if( SOLVER == Solver_RK4 && STAGE > 1 )
+    {
+        const double * q = a.acc.base + base + o.ec;
+        acc              = make_d3( q[0], q[FIELD_BLOCK], q[2 * FIELD_BLOCK] );
+    }
+    const D3 out = solver_update<SOLVER, STAGE>( s_center, Fv, p_center, Fvp, acc );
+    if( SOLVER == Solver_RK4 && STAGE < 4 )
+    {
+        double * q         = a.acc.base + base + o.ec;
+        q[0]               = acc.x;
+        q[FIELD_BLOCK]     = acc.y;
+        q[2 * FIELD_BLOCK] = acc.z;
+    }
+    double * q         = a.out.base + base + o.ec;
+    q[0]               = out.x;
+    q[FIELD_BLOCK]     = out.y;
+    q[2 * FIELD_BLOCK] = out.z;
+}
+
+// The march of one thread over the planes [c0, c1) of its column (x, b).
+template<int SOLVER, int STAGE, int SPEC, int MODE, bool BOUNDARY>
+__device__ __forceinline__ void sc6_march(
+    const StencilParams & p, const LLGParams & l, const StageArgs & a, const int x, const int b, const int c0, const int c1 )
+{
+    using Needs          = StageNeeds<SOLVER, STAGE>;
+    constexpr bool HAS_C = ( SPEC & SC6_HAS_C ) != 0;
+    constexpr bool COL_S = HAS_C && Needs::Fv_s;
+    constexpr bool COL_P = HAS_C && Needs::Fv_sp;
 
     // in-plane neighbours: site offsets -> element offsets (AoSoA-32)
     SC6Offsets o;
@@ -294,120 +381,55 @@ __device__ __forceinline__ void sc6_march(
         o.ebp         = unsigned( elem_offset( p.Na * bp + x ) );
     }
     const std::size_t plane_elems = 3 * std::size_t( p.plane_stride );
-
-    const bool thermal = l.has_thermal && !l.direct_minimization;
+    const std::uint64_t plane_api = std::uint64_t( p.Na ) * p.Nb;
     // global index of the site (x, b, c_begin + c0) in the reference's order: Philox counter
-    std::uint64_t gsite = std::uint64_t( p.Na * b + x ) + std::uint64_t( p.Na ) * p.Nb * std::uint64_t( p.c_begin + c0 );
+    std::uint64_t gsite = std::uint64_t( p.Na * b + x ) + plane_api * std::uint64_t( p.c_begin + c0 );
 
     const D3 zero = make_d3( 0.0, 0.0, 0.0 );
-    SC6Window ws, wp; // windows of s and of the predictor s'
-    ws.below = ws.above = wp.below = wp.center = wp.above = zero;
+    SC6Window ws, wp; // in-plane neighbours of s and of the predictor s'
     ws.xm = ws.xp = ws.bm = ws.bp = wp.xm = wp.xp = wp.bm = wp.bp = zero;
+    // own-column rings: at plane c0 + k the roles (below, center, above) are ring[k % 3], ring[(k+1) % 3], ring[(k+2) % 3]
+    D3 rs[3] = { zero, zero, zero }, rp[3] = { zero, zero, zero };
 
     // prologue: plane c0 and the own-column value of plane c0 + 1
     {
         const std::size_t base = std::size_t( c0 + p.halo ) * plane_elems;
         const std::size_t pa   = HAS_C ? sc6_c_plane( p, c0 + 1 ) : base + plane_elems;
-        ws.center              = ld3p( a.s.base + base, o.ec );
+        rs[1]                  = ld3p( a.s.base + base, o.ec );
         if( COL_S || c0 + 1 < c1 )
-            ws.above = ld3p( a.s.base + pa, o.ec );
+            rs[2] = ld3p( a.s.base + pa, o.ec );
         if( COL_S )
-            ws.below = ld3p( a.s.base + sc6_c_plane( p, c0 - 1 ), o.ec );
+            rs[0] = ld3p( a.s.base + sc6_c_plane( p, c0 - 1 ), o.ec );
         if( Needs::Fv_s )
             sc6_load_inplane<BOUNDARY>( ws, a.s.base + base, o );
         if( Needs::Fv_sp )
         {
-            wp.center = ld3p( a.sp.base + base, o.ec );
+            rp[1] = ld3p( a.sp.base + base, o.ec );
             if( COL_P || c0 + 1 < c1 )
-                wp.above = ld3p( a.sp.base + pa, o.ec );
+                rp[2] = ld3p( a.sp.base + pa, o.ec );
             if( COL_P )
-                wp.below = ld3p( a.sp.base + sc6_c_plane( p, c0 - 1 ), o.ec );
+                rp[0] = ld3p( a.sp.base + sc6_c_plane( p, c0 - 1 ), o.ec );
             sc6_load_inplane<BOUNDARY>( wp, a.sp.base + base, o );
         }
     }
 
-    for( int c = c0; c < c1; ++c )
+    for( int cb = c0; cb < c1; cb += 3 )
     {
-        const std::size_t base = std::size_t( c + p.halo ) * plane_elems;
-        bool vb = true, va = true;
-        if( BOUNDARY && HAS_C )
+#pragma unroll
+        for( int k = 0; k < 3; ++k )
         {
-            vb = sc6_c_valid( p, c - 1 );
-            va = sc6_c_valid( p, c + 1 );
+            const int c = cb + k;
+            if( k > 0 && c >= c1 )
+                break;
+            sc6_plane_step<SOLVER, STAGE, SPEC, MODE, BOUNDARY>(
+                p, l, a, o, c, c1, plane_elems, gsite, rs[k], rs[( k + 1 ) % 3], rs[( k + 2 ) % 3], rp[k], rp[( k + 1 ) % 3],
+                rp[( k + 2 ) % 3], ws, wp );
+            gsite += plane_api;
         }
-
-        // 1. gradients of plane c (consume the neighbour registers)
-        D3 gs = zero, gp = zero;
-        if( Needs::Fv_s )
-            gs = sc6_gradient<SPEC>(
-                p, ws.center, ws.xm, ws.xp, ws.bm, ws.bp, ( BOUNDARY && !vb ) ? zero : ws.below,
-                ( BOUNDARY && !va ) ? zero : ws.above, a.ddi_s.base + base, o.ec );
-        if( Needs::Fv_sp )
-            gp = sc6_gradient<SPEC>(
-                p, wp.center, wp.xm, wp.xp, wp.bm, wp.bp, ( BOUNDARY && !vb ) ? zero : wp.below,
-                ( BOUNDARY && !va ) ? zero : wp.above, a.ddi_sp.base + base, o.ec );
-
-        // 2. issue the loads of plane c + 1: in-plane neighbours and the own-column value of plane c + 2
-        D3 s_next2 = zero, p_next2 = zero;
-        if( c + 1 < c1 )
-        {
-            const std::size_t base1 = base + plane_elems;
-            const std::size_t pa2   = HAS_C ? sc6_c_plane( p, c + 2 ) : base1 + plane_elems;
-            if( COL_S || c + 2 < c1 )
-                s_next2 = ld3p( a.s.base + pa2, o.ec );
-            if( Needs::Fv_s )
-                sc6_load_inplane<BOUNDARY>( ws, a.s.base + base1, o );
-            if( Needs::Fv_sp )
-            {
-                if( COL_P || c + 2 < c1 )
-                    p_next2 = ld3p( a.sp.base + pa2, o.ec );
-                sc6_load_inplane<BOUNDARY>( wp, a.sp.base + base1, o );
-            }
-        }
-
-        // 3. the rest of plane c
-        D3 xi = zero;
-        if( thermal )
-            xi = sc6_thermal_field( l, gsite );
-        D3 Fv = zero, Fvp = zero;
-        if( Needs::Fv_s )
-            Fv = sc6_virtual_force( l, thermal, ws.center, gs, xi );
-        if( Needs::Fv_sp )
-            Fvp = sc6_virtual_force( l, thermal, wp.center, gp, xi );
-
-        D3 acc = zero;
-        if( SOLVER == Solver_RK4 && STAGE > 1 )
-        {
-            const double * q = a.acc.base + base + o.ec;
-            acc              = make_d3( q[0], q[FIELD_BLOCK], q[2 * FIELD_BLOCK] );
-        }
-        const D3 out = solver_update<SOLVER, STAGE>( ws.center, Fv, wp.center, Fvp, acc );
-        if( SOLVER == Solver_RK4 && STAGE < 4 )
-        {
-            double * q         = a.acc.base + base + o.ec;
-            q[0]               = acc.x;
-            q[FIELD_BLOCK]     = acc.y;
-            q[2 * FIELD_BLOCK] = acc.z;
-        }
-        {
-            double * q         = a.out.base + base + o.ec;
-            q[0]               = out.x;
-            q[FIELD_BLOCK]     = out.y;
-            q[2 * FIELD_BLOCK] = out.z;
-        }
-
-        // 4. march
-        ws.below  = ws.center;
-        ws.center = ws.above;
-        ws.above  = s_next2;
-        wp.below  = wp.center;
-        wp.center = wp.above;
-        wp.above  = p_next2;
-        gsite += std::uint64_t( p.Na ) * p.Nb;
     }
 }
 
-template<int SOLVER, int STAGE, int SPEC>
+template<int SOLVER, int STAGE, int SPEC, int MODE>
 static __global__ void __launch_bounds__( SC6_MAX_THREADS ) k_sc6_stage(
     const __grid_constant__ StencilParams p, const int lc, const __grid_constant__ LLGParams l,
     const __grid_constant__ StageArgs a )
@@ -426,9 +448,9 @@ static __global__ void __launch_bounds__( SC6_MAX_THREADS ) k_sc6_stage(
     if( ( SPEC & SC6_HAS_C ) && !p.bc[2] )
         boundary = boundary || ( p.c_begin + c0 == 0 ) || ( p.c_begin + c1 == p.Nc );
     if( boundary )
-        sc6_march<SOLVER, STAGE, SPEC, true>( p, l, a, x, b, c0, c1 );
+        sc6_march<SOLVER, STAGE, SPEC, MODE, true>( p, l, a, x, b, c0, c1 );
     else
-        sc6_march<SOLVER, STAGE, SPEC, false>( p, l, a, x, b, c0, c1 );
+        sc6_march<SOLVER, STAGE, SPEC, MODE, false>( p, l, a, x, b, c0, c1 );
 }
 
 // One launcher per solver, each in its own translation unit (sc6_<solver>.cu) so that the 8 SPEC x stage
@@ -437,18 +459,23 @@ template<int SOLVER, int STAGE>
 void sc6_launch_stage(
     const SC6Launch & L, cudaStream_t stream, const StencilParams & p, const LLGParams & l, const StageArgs & a )
 {
-#define SB_SC6_CASE( S )                                                                                               \
-    case S: k_sc6_stage<SOLVER, STAGE, S><<<L.grid, L.block, 0, stream>>>( p, L.lc, l, a ); break;
-    switch( L.spec )
+    const int mode = l.direct_minimization ? SC6_MINIMISE : ( l.has_thermal ? SC6_THERMAL : SC6_DYNAMICS );
+#define SB_SC6_CASE( S, M )                                                                                            \
+    case S * SC6_N_MODES + M: k_sc6_stage<SOLVER, STAGE, S, M><<<L.grid, L.block, 0, stream>>>( p, L.lc, l, a ); break;
+    switch( L.spec * SC6_N_MODES + mode )
     {
-        SB_SC6_CASE( 0 )
-        SB_SC6_CASE( 1 )
-        SB_SC6_CASE( 2 )
-        SB_SC6_CASE( 3 )
-        SB_SC6_CASE( 4 )
-        SB_SC6_CASE( 5 )
-        SB_SC6_CASE( 6 )
-        SB_SC6_CASE( 7 )
+        SB_SC6_CASE( 0, 0 )
+        SB_SC6_CASE( 0, 1 )
+        SB_SC6_CASE( 0, 2 )
+        SB_SC6_CASE( 1, 0 )
+        SB_SC6_CASE( 1, 1 )
+        SB_SC6_CASE( 1, 2 )
+        SB_SC6_CASE( 2, 0 )
+        SB_SC6_CASE( 2, 1 )
+        SB_SC6_CASE( 2, 2 )
+        SB_SC6_CASE( 3, 0 )
+        SB_SC6_CASE( 3, 1 )
+        SB_SC6_CASE( 3, 2 )
     }
 #undef SB_SC6_CASE
 }
