@@ -1,0 +1,27 @@
+#!/usr/bin/env python
+"""Tuning sweep (GPU box): bench.py device-resident leg under different block shapes / march lengths / build variants.
+usage: python profiles/sweep.py "LIB=libSpirit.so BX=128 BY=4 LC=16" "LIB=... BX=.." ...   (any subset of keys)"""
+import json
+import os
+import subprocess
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+for spec in sys.argv[1:]:
+    env = dict(os.environ)
+    for kv in spec.split():
+        k, v = kv.split("=")
+        if k == "LIB":
+            env["SPIRIT_B200_LIB"] = v
+        elif k == "ARGS":
+            pass
+        else:
+            env["SPIRIT_B200_SC6_" + k] = v
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--steps", "100", "--warmup", "10", "--no-e2e", "--no-cpu-baseline"],
+                       env=env, capture_output=True, text=True)
+    try:
+        d = json.loads([l for l in r.stdout.splitlines() if l.startswith("{")][-1])
+        print("%-50s %.4e spin-steps/s  %.4f ms/step  stages %s  frac %.3f" % (
+            spec, d["value"], d["ms_per_step"], ["%.4f" % x for x in d["roofline"]["stage_ms"]], d["roofline"]["step"]["frac"]), flush=True)
+    except Exception as e:  # noqa: BLE001
+        print(spec, "FAILED", e, r.stderr[-500:], flush=True)

@@ -15,6 +15,13 @@ CSRC = os.path.join(HERE, "csrc")
 BUILD = os.path.join(HERE, "build")
 LIB = os.path.join(HERE, "libSpirit.so")
 
+# experiments: SPIRIT_B200_VARIANT=name SPIRIT_B200_DEFINES="-DX=1 -DY=2" builds libSpirit_<name>.so with extra defines
+VARIANT = os.environ.get("SPIRIT_B200_VARIANT", "")
+EXTRA_DEFINES = os.environ.get("SPIRIT_B200_DEFINES", "").split()
+if VARIANT:
+    BUILD = os.path.join(HERE, "build_" + VARIANT)
+    LIB = os.path.join(HERE, "libSpirit_%s.so" % VARIANT)
+
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 CXX = os.environ.get("SPIRIT_B200_CXX", "/usr/bin/g++")
 ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
@@ -46,7 +53,7 @@ def _headers_mtime():
 
 def _compile(src, obj, verbose):
     if src.endswith(".cu"):
-        cmd = [NVCC] + NVCCFLAGS + INCLUDES + ["-c", src, "-o", obj]
+        cmd = [NVCC] + NVCCFLAGS + EXTRA_DEFINES + INCLUDES + ["-c", src, "-o", obj]
     else:
         cmd = [CXX] + CXXFLAGS + INCLUDES + ["-c", src, "-o", obj]
     if verbose:

@@ -17,7 +17,8 @@ import re
 HERE = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(HERE)
 INCLUDE = os.path.join(ROOT, "include")
-PRODUCT_LIB = os.path.join(HERE, "libSpirit.so")
+# SPIRIT_B200_LIB selects an experimental build variant (spirit_b200/build.py); the default is the product library
+PRODUCT_LIB = os.path.join(HERE, os.environ.get("SPIRIT_B200_LIB", "libSpirit.so"))
 ORACLE_LIB = os.path.join(ROOT, "oracle", "_ref", "libSpirit_ref.so")
 
 

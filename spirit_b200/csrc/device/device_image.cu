@@ -119,38 +119,47 @@ int env_int( const char * name, int fallback )
 }
 
 // Block shape and march length of the sc6 kernels. BX x BY threads own BX sites of BY rows; the grid's z dimension
-// splits c into segments of lc planes. lc trades the two extra planes read per segment against the tail of the last
-// wave of CTAs. (SPIRIT_B200_SC6_BX / _BY / _LC override for tuning runs.)
-SC6Launch make_sc6_launch( const StencilParams & p )
+// splits c into segments of lc planes. lc trades the two extra planes read per segment (and the pipeline fill of
+// the march) against the tail of the last wave of CTAs. (SPIRIT_B200_SC6_BX / _BY / _LC override for tuning runs.)
+SC6Geometry make_sc6_geometry( const StencilParams & p, int threads, int ctas_per_sm )
 {
-    SC6Launch L;
+    SC6Geometry G;
     int bx = std::min( 128, ( ( p.Na + 31 ) / 32 ) * 32 );
-    bx     = env_int( "SPIRIT_B200_SC6_BX", bx );
-    int by = std::max( 1, std::min( SC6_MAX_THREADS / bx, p.Nb ) );
-    by     = env_int( "SPIRIT_B200_SC6_BY", std::min( by, 4 ) );
-    L.block = dim3( bx, by, 1 );
+    bx     = std::min( threads, env_int( "SPIRIT_B200_SC6_BX", bx ) );
+    int by = std::max( 1, std::min( threads / bx, p.Nb ) );
+    by     = std::max( 1, std::min( threads / bx, env_int( "SPIRIT_B200_SC6_BY", by ) ) );
+    G.block = dim3( bx, by, 1 );
     const int gx = ( p.Na + bx - 1 ) / bx, gy = ( p.Nb + by - 1 ) / by;
     int n_sm = 148, dev = 0;
     if( cudaGetDevice( &dev ) == cudaSuccess )
         cudaDeviceGetAttribute( &n_sm, cudaDevAttrMultiProcessorCount, dev );
-    const double slots = double( n_sm ) * std::max( 1, 1024 / ( bx * by ) ); // resident CTAs, assuming <= 64 registers/thread
+    const double slots = double( n_sm ) * ctas_per_sm;
     int best_lc = p.nc_local;
     double best = 1e300;
-    for( int lc : { 4, 6, 8, 12, 16, 24, 32, 48, 64, 96, 128 } )
+    for( int lc : { 4, 8, 16, 32, 64, 128 } )
     {
         if( lc > p.nc_local )
             lc = p.nc_local;
         const int nseg     = ( p.nc_local + lc - 1 ) / lc;
         const double waves = double( gx ) * gy * nseg / slots;
-        const double cost  = ( 1.0 + 2.0 / lc ) * std::ceil( waves ) / waves;
+        // 3 plane-steps of fill / extra reads per segment (measured: lc 32 beats 16 beats 8 at 256^3)
+        const double cost = ( 1.0 + 3.0 / lc ) * std::ceil( waves ) / waves;
         if( cost < best - 1e-12 )
         {
             best    = cost;
             best_lc = lc;
         }
     }
-    L.lc   = std::max( 1, env_int( "SPIRIT_B200_SC6_LC", best_lc ) );
-    L.grid = dim3( gx, gy, ( p.nc_local + L.lc - 1 ) / L.lc );
+    G.lc   = std::max( 1, env_int( "SPIRIT_B200_SC6_LC", best_lc ) );
+    G.grid = dim3( gx, gy, ( p.nc_local + G.lc - 1 ) / G.lc );
+    return G;
+}
+
+SC6Launch make_sc6_launch( const StencilParams & p )
+{
+    SC6Launch L;
+    L.one_window  = make_sc6_geometry( p, SC6_THREADS_1W, SC6_MINB_1W );
+    L.two_windows = make_sc6_geometry( p, SC6_THREADS_2W, SC6_MINB_2W );
     return L;
 }
 

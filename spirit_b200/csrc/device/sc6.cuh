@@ -28,7 +28,20 @@ namespace sb
 namespace dev
 {
 
+// Launch shapes. A stage that evaluates the gradient of ONE configuration (every stage 1, SIB stage 2, RK4) holds one
+// register window and compiles to <= 80 registers: 256-thread CTAs, three per SM (24 warps). Stage 2 of Depondt and
+// Heun holds two windows (s and s'), needs ~128 registers and runs as one 512-thread CTA per SM (16 warps).
+// Measured on B200 (256^3, profiles/): stage 1 0.228 ms at 16 warps/SM -> 0.203 ms at 24 warps/SM.
+constexpr int SC6_THREADS_1W = 256, SC6_MINB_1W = 3;
+constexpr int SC6_THREADS_2W = 512, SC6_MINB_2W = 1;
 constexpr int SC6_MAX_THREADS = 512;
+template<int SOLVER, int STAGE>
+struct SC6Shape
+{
+    static constexpr bool two_windows = StageNeeds<SOLVER, STAGE>::Fv_s && StageNeeds<SOLVER, STAGE>::Fv_sp;
+    static constexpr int threads      = two_windows ? SC6_THREADS_2W : SC6_THREADS_1W;
+    static constexpr int min_blocks   = two_windows ? SC6_MINB_2W : SC6_MINB_1W;
+};
 
 // SPEC bits
 constexpr int SC6_HAS_C       = 1; // neighbours along c exist (3-D system)
@@ -40,11 +53,15 @@ constexpr int SC6_THERMAL  = 1; // ... + xi + alpha s x xi
 constexpr int SC6_MINIMISE = 2; // Fv = dtg' s x F (direct minimisation)
 constexpr int SC6_N_MODES  = 3;
 
-struct SC6Launch
+struct SC6Geometry
 {
     dim3 grid, block;
-    int lc   = 1; // planes per CTA (march length)
-    int spec = 0; // SC6_HAS_C | SC6_DMI_GENERAL
+    int lc = 1; // planes per CTA (march length)
+};
+struct SC6Launch
+{
+    SC6Geometry one_window, two_windows; // see SC6Shape
+    int spec = 0;                        // SC6_HAS_C | SC6_DMI_GENERAL
 };
 
 __device__ __forceinline__ D3 ld3p( const double * __restrict__ plane, unsigned e )
@@ -430,7 +447,7 @@ __device__ __forceinline__ void sc6_march(
 }
 
 template<int SOLVER, int STAGE, int SPEC, int MODE>
-static __global__ void __launch_bounds__( SC6_MAX_THREADS ) k_sc6_stage(
+static __global__ void __launch_bounds__( SC6Shape<SOLVER, STAGE>::threads, SC6Shape<SOLVER, STAGE>::min_blocks ) k_sc6_stage(
     const __grid_constant__ StencilParams p, const int lc, const __grid_constant__ LLGParams l,
     const __grid_constant__ StageArgs a )
 {
@@ -461,7 +478,8 @@ void sc6_launch_stage(
 {
     const int mode = l.direct_minimization ? SC6_MINIMISE : ( l.has_thermal ? SC6_THERMAL : SC6_DYNAMICS );
 #define SB_SC6_CASE( S, M )                                                                                            \
-    case S * SC6_N_MODES + M: k_sc6_stage<SOLVER, STAGE, S, M><<<L.grid, L.block, 0, stream>>>( p, L.lc, l, a ); break;
+    case S * SC6_N_MODES + M: k_sc6_stage<SOLVER, STAGE, S, M><<<G.grid, G.block, 0, stream>>>( p, G.lc, l, a ); break;
+    const SC6Geometry & G = SC6Shape<SOLVER, STAGE>::two_windows ? L.two_windows : L.one_window;
     switch( L.spec * SC6_N_MODES + mode )
     {
         SB_SC6_CASE( 0, 0 )
