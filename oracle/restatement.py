@@ -1,0 +1,217 @@
+"""oracle/restatement.py -- TEST INFRASTRUCTURE, not product code.
+
+A NumPy restatement of the reference's hot-path arithmetic for the nearest-neighbour simple-cubic Heisenberg
+Hamiltonian (exchange + bond-parallel DMI + uniaxial / cubic anisotropy + Zeeman), the LLG virtual force and the
+Depondt / Heun / SIB / RK4 / VP solver updates, and the GNEB force. It is an independent third opinion beside the
+compiled reference (oracle/_ref/libSpirit_ref.so) and documents the mathematics the CUDA kernels implement.
+
+Pinned: tests/test_oracle.py checks every function here against the compiled reference and against the committed
+golden vectors (tests/golden/*.npz, produced by tests/golden/make_golden.py from the reference itself).
+Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline leg may import this module.
+
+Reference locations (relative to /root/reference/core):
+  gradient terms            src/engine/Hamiltonian_Heisenberg.cpp:768-864
+  energy                    src/engine/Hamiltonian_Heisenberg.cpp:704-766 (1/2 g.s for bilinear terms)
+  idx_from_pair / BC        include/engine/Vectormath.hpp:437-528
+  virtual force             src/engine/Method_LLG.cpp:131-226
+  Depondt / Heun / SIB      include/engine/Solver_Depondt.hpp:29-77, Solver_Heun.hpp:30-81, Solver_SIB.hpp:22-50,
+                            src/engine/Solver_Kernels.cpp:15-48 (sib_transform)
+  RK4 / VP                  include/engine/Solver_RK4.hpp:41-147, Solver_VP.hpp:29-114
+  rotate                    src/engine/Vectormath.cpp:474-485
+  GNEB force, tangents      src/engine/Method_GNEB.cpp:87-258, src/engine/Manifoldmath.cpp:115-213
+  constants                 include/utility/Constants.hpp:18-46
+"""
+import numpy as np
+
+mu_B = 0.057883817555
+gamma = 0.1760859644
+k_B = 0.08617330350
+
+
+class Model:
+    """sc lattice n = (Na, Nb, Nc), periodic flags bc, first-shell J, Bloch DMI D (d parallel to the bond),
+    uniaxial K along Kn, cubic K4, field B (Tesla) along Bn, mu_s (mu_B)."""
+
+    def __init__(self, n, bc, J=10.0, D=6.0, B=25.0, Bn=(0, 0, 1), mu_s=2.0, K=0.0, Kn=(0, 0, 1), K4=0.0,
+                 dt=1e-3, alpha=0.3):
+        self.n, self.bc = tuple(n), tuple(bc)
+        self.J, self.D, self.B, self.Bn = J, D, B, np.asarray(Bn, float)
+        self.mu_s, self.K, self.Kn, self.K4 = mu_s, K, np.asarray(Kn, float), K4
+        self.dt, self.alpha = dt, alpha
+
+    # ---- Hamiltonian ----------------------------------------------------------------------------------------------
+    def pair_gradient(self, S):
+        """exchange + DMI, S shaped (Nc, Nb, Na, 3): g_i -= J s_j + D s_j x d_ij over the (redundant) neighbours"""
+        g = np.zeros_like(S)
+        for axis, (N, per) in zip((2, 1, 0), zip(self.n, self.bc)):
+            d = np.zeros(3)
+            d[2 - axis] = 1.0
+            for sign in (+1, -1):
+                if N == 1 and not per:
+                    continue
+                Sj = np.roll(S, -sign, axis=axis)
+                mask = np.ones(S.shape[:3], bool)
+                if not per:
+                    idx = [slice(None)] * 3
+                    idx[axis] = (N - 1) if sign > 0 else 0
+                    mask[tuple(idx)] = False
+                g -= (self.J * Sj + self.D * np.cross(Sj, sign * d)) * mask[..., None]
+        return g
+
+    def gradient_and_energy(self, s):
+        Na, Nb, Nc = self.n
+        S = s.reshape(Nc, Nb, Na, 3)
+        gp = self.pair_gradient(S)
+        ga = -2 * self.K * (S @ self.Kn)[..., None] * self.Kn
+        gc = -2 * self.K4 * S ** 3
+        gz = -self.mu_s * mu_B * self.B * self.Bn * np.ones_like(S)
+        E = 0.5 * np.sum((gp + ga) * S) - 0.5 * self.K4 * np.sum(S ** 4) + np.sum(gz * S)
+        return (gp + ga + gc + gz).reshape(-1, 3), E
+
+    def gradient(self, s):
+        return self.gradient_and_energy(s)[0]
+
+    # ---- LLG ------------------------------------------------------------------------------------------------------------
+    def virtual_force(self, s, xi=None):
+        dtg = self.dt * gamma / mu_B / (1 + self.alpha ** 2)
+        F = -self.gradient(s)
+        fv = (dtg * F + dtg * self.alpha * np.cross(s, F)) / self.mu_s
+        if xi is not None:
+            fv = fv + xi + self.alpha * np.cross(s, xi)
+        return fv
+
+    def thermal_amplitude(self, T):
+        """epsilon * sqrt(T / mu_s), Method_LLG.cpp:74-75,105"""
+        return np.sqrt(2 * self.alpha * self.dt * gamma / mu_B * k_B) / (1 + self.alpha ** 2) * np.sqrt(T / self.mu_s)
+
+    def depondt(self, s, xi=None):
+        H1 = self.virtual_force(s, xi)
+        sp = rotate(s, H1)
+        return rotate(s, 0.5 * (H1 + self.virtual_force(sp, xi)))
+
+    def heun(self, s):
+        k1 = -np.cross(s, self.virtual_force(s))
+        sp = normalize(s + k1)
+        return normalize(s + 0.5 * k1 - 0.5 * np.cross(sp, self.virtual_force(sp)))
+
+    def sib(self, s):
+        sp = 0.5 * (s + sib_transform(s, self.virtual_force(s)))
+        return sib_transform(s, self.virtual_force(sp))
+
+    def rk4(self, s):
+        fv = self.virtual_force
+        k1 = -np.cross(s, fv(s))
+        s1 = normalize(s + 0.5 * k1)
+        k2 = -np.cross(s1, fv(s1))
+        s2 = normalize(s + 0.5 * k2)
+        k3 = -np.cross(s2, fv(s2))
+        s3 = normalize(s + k3)
+        k4 = -np.cross(s3, fv(s3))
+        return normalize(s + k1 / 6 + k2 / 3 + k3 / 3 + k4 / 6)
+
+    def vp_single_shots(self, s, n_steps):
+        """VP with the post-iteration hook after every iteration (Simulation_SingleShot): the hook projects the force
+        in place, and the projected force is next iteration's F_prev (SURVEY.md 8c hazard 6)"""
+        F = project_tangential(-self.gradient(s), s)
+        v = np.zeros_like(s)
+        for _ in range(n_steps):
+            Fp, F = F, -self.gradient(s)
+            v = v + 0.5 * (Fp + F)
+            p_, f2 = np.sum(v * F), np.sum(F * F)
+            v = F * (p_ / f2) if p_ > 0 else np.zeros_like(s)
+            s = normalize(s + self.dt * v + 0.5 * self.dt * F)
+            F = project_tangential(F, s)
+        return s
+
+
+def normalize(x):
+    return x / np.linalg.norm(x, axis=1, keepdims=True)
+
+
+def project_tangential(F, s):
+    return F - np.sum(F * s, axis=1, keepdims=True) * s
+
+
+def rotate(v, H):
+    """Rodrigues rotation of v about H/|H| by |H| (zero force: identity)"""
+    th = np.linalg.norm(H, axis=1, keepdims=True)
+    k = np.divide(H, th, out=np.zeros_like(H), where=th > 0)
+    return v * np.cos(th) + np.cross(k, v) * np.sin(th) + k * np.sum(k * v, axis=1, keepdims=True) * (1 - np.cos(th))
+
+
+def sib_transform(s, H):
+    A = 0.5 * H
+    a = s - np.cross(s, A)
+    Ax, Ay, Az = A.T
+    x, y, z = a.T
+    o = np.stack([x * (Ax * Ax + 1) + y * (Ax * Ay - Az) + z * (Ax * Az + Ay),
+                  x * (Ay * Ax + Az) + y * (Ay * Ay + 1) + z * (Ay * Az - Ax),
+                  x * (Az * Ax - Ay) + y * (Az * Ay + Ax) + z * (Az * Az + 1)], axis=1)
+    return o / (1 + np.sum(A * A, axis=1))[:, None]
+
+
+# ---- GNEB -------------------------------------------------------------------------------------------------------------------
+NORMAL, CLIMBING, FALLING, STATIONARY = 0, 1, 2, 3
+
+
+def geodesic_distance(a, b):
+    return np.sqrt(np.sum(np.arccos(np.clip(np.sum(a * b, axis=1), -1, 1)) ** 2))
+
+
+def tangents(imgs, E):
+    """energy-weighted tangents of the interior images, projected and normalised in 3N space (Manifoldmath.cpp:143-211)"""
+    T = [None] * len(imgs)
+    for i in range(1, len(imgs) - 1):
+        tp, tm = imgs[i + 1] - imgs[i], imgs[i] - imgs[i - 1]
+        Em, Ep, Emi = E[i], E[i + 1], E[i - 1]
+        if (Ep < Em and Em > Emi) or (Ep > Em and Em < Emi):
+            Emax, Emin = max(abs(Ep - Em), abs(Emi - Em)), min(abs(Ep - Em), abs(Emi - Em))
+            t = Emax * tp + Emin * tm if Ep > Emi else Emin * tp + Emax * tm
+        elif Ep > Em > Emi:
+            t = tp
+        elif Ep < Em < Emi:
+            t = tm
+        else:
+            t = tp + tm
+        t = project_tangential(t, imgs[i])
+        T[i] = t / np.sqrt(np.sum(t * t))
+    return T
+
+
+def gneb_force(model, imgs, types, k_spring):
+    gE = [model.gradient_and_energy(s) for s in imgs]
+    E = [e for _, e in gE]
+    Rx = [0.0]
+    for i in range(1, len(imgs)):
+        Rx.append(Rx[-1] + geodesic_distance(imgs[i], imgs[i - 1]))
+    T = tangents(imgs, E)
+    F = [np.zeros_like(imgs[0]) for _ in imgs]
+    for i in range(1, len(imgs) - 1):
+        Fg = project_tangential(-gE[i][0], imgs[i])
+        if types[i] == CLIMBING:
+            F[i] = Fg - 2 * np.sum(Fg * T[i]) * T[i]
+        elif types[i] == FALLING:
+            F[i] = Fg
+        elif types[i] == NORMAL:
+            F[i] = Fg - np.sum(Fg * T[i]) * T[i] + k_spring * (Rx[i + 1] - 2 * Rx[i] + Rx[i - 1]) * T[i]
+    return F, E, Rx
+
+
+def gneb_vp_single_shots(model, imgs, types, k_spring, n_steps):
+    """GNEB + VP coupled over all images, hook (in-place projection of the forces) after every iteration"""
+    noi = len(imgs)
+    imgs = [x.copy() for x in imgs]
+    F = [np.zeros_like(imgs[0]) for _ in imgs]
+    v = [np.zeros_like(imgs[0]) for _ in imgs]
+    E = Rx = None
+    for _ in range(n_steps):
+        Fp = F
+        F, E, Rx = gneb_force(model, imgs, types, k_spring)
+        v = [v[i] + 0.5 * (Fp[i] + F[i]) for i in range(noi)]
+        pf = sum(np.sum(v[i] * F[i]) for i in range(noi))
+        f2 = sum(np.sum(F[i] * F[i]) for i in range(noi))
+        for i in range(noi):
+            v[i] = F[i] * (pf / f2) if pf > 0 else np.zeros_like(F[i])
+            imgs[i] = normalize(imgs[i] + model.dt * v[i] + 0.5 * model.dt * F[i])
+        F = [project_tangential(F[i], imgs[i]) for i in range(noi)]
+    return imgs, E, Rx

@@ -1,0 +1,100 @@
+"""Host-side logic of the library against the reference (CPU, no GPU): input.cfg parsing, pair lists, configurations,
+chain operations. These produce the inputs of the hot path and must be identical bit for bit."""
+import numpy as np
+import pytest
+
+from spirit_b200 import session as S
+
+CASES = [
+    ("solvers", {}),
+    ("default", {"n_basis_cells": "12 10 3"}),
+    ("fd_pairs", {}),
+    ("cubic256", {"n_basis_cells": "6 5 4"}),
+    ("cubic256", {"n_basis_cells": "6 5 4", "n_shells_exchange": "4", "jij": "10 5 2.5 1.25", "n_shells_dmi": "3", "dij": "6 3 1", "dm_chirality": "-2"}),
+    ("cubic256", {"n_basis_cells": "5 5 5", "bravais_lattice": "fcc", "n_shells_exchange": "2", "jij": "10 5", "dm_chirality": "-1"}),
+    ("cubic256", {"n_basis_cells": "5 5 2", "bravais_lattice": "bcc", "n_shells_exchange": "2", "jij": "10 5"}),
+    ("cubic256", {"n_basis_cells": "7 7 1", "bravais_lattice": "hex2d", "boundary_conditions": "1 1 0", "n_shells_exchange": "3", "jij": "10 5 1", "n_shells_dmi": "2", "dij": "6 1", "dm_chirality": "2"}),
+    ("ddi", {"ddi_method": "none"}),
+]
+
+
+@pytest.mark.parametrize("preset,overrides", CASES)
+def test_pair_lists_match_reference(cfg, product, oracle, preset, overrides):
+    """Hamiltonian_Heisenberg::Update_Interactions + Neighbours::Get_Neighbours_in_Shells + DMI_Normal_from_Pair"""
+    path = cfg(preset, **overrides)
+    p, o = S.Session(product, path), S.Session(oracle, path)
+    assert p.nos == o.nos
+    for kind in (0, 1):
+        a, b = p.pairs(kind), o.pairs(kind)
+        assert np.array_equal(a[0], b[0]), "pair indices/translations, kind %d" % kind
+        assert np.array_equal(a[1], b[1]), "magnitudes"
+        assert np.abs(a[2] - b[2]).max(initial=0) <= 1e-15, "DMI normals"
+    p.close()
+    o.close()
+
+
+@pytest.mark.parametrize("preset,overrides", [CASES[0], CASES[1], CASES[5], CASES[8]])
+def test_configurations_match_reference(cfg, product, oracle, preset, overrides):
+    """Utility::Configurations: Random (same mt19937 stream), PlusZ, Domain, Skyrmion"""
+    path = cfg(preset, **overrides)
+    p, o = S.Session(product, path), S.Session(oracle, path)
+    assert np.array_equal(p.spins(), o.spins())  # State_Setup ends with Configuration_Random
+    for x in (p, o):
+        x.random()
+    assert np.array_equal(p.spins(), o.spins())
+    for x in (p, o):
+        x.domain((0.3, -0.2, 0.9))
+    assert np.abs(p.spins() - o.spins()).max() < 1e-15
+    for x in (p, o):
+        x.plus_z()
+        x.skyrmion(4.0, order=1, phase=-90.0, pos=(1.0, -1.0, 0.0))
+    assert np.abs(p.spins() - o.spins()).max() < 1e-14
+    for x in (p, o):
+        x.minus_z()
+        x.skyrmion(3.0, order=2, phase=30.0, up_down=True, achiral=True, rl=True)
+    assert np.abs(p.spins() - o.spins()).max() < 1e-14
+    p.close()
+    o.close()
+
+
+def test_chain_operations_match_reference(cfg, product, oracle):
+    """Chain_Image_to_Clipboard / Chain_Set_Length / Chain_Jump_To_Image / Transition_Homogeneous"""
+    path = cfg("solvers", n_basis_cells="10 10 1")
+    out = []
+    for lib in (product, oracle):
+        x = S.Session(lib, path)
+        x.plus_z()
+        x.skyrmion(3.0, phase=-90.0)
+        x.chain_set_length(7)
+        assert x.noi == 7
+        x.jump_to_image(6)
+        x.plus_z()
+        x.jump_to_image(0)
+        x.transition_homogeneous(0, 6)
+        out.append(np.stack([x.spins(i).copy() for i in range(7)]))
+        x.close()
+    assert np.abs(out[0] - out[1]).max() < 1e-14
+
+
+def test_setters_and_getters_round_trip(cfg, product, oracle):
+    """Hamiltonian_Set_* / Get_* and Parameters_LLG_Set_* / Get_*: float narrowing as in the reference"""
+    import ctypes
+    path = cfg("solvers")
+    vals = []
+    for lib in (product, oracle):
+        x = S.Session(lib, path)
+        x.set_field(12.5, (0.0, 1.0, 1.0))
+        x.set_anisotropy(0.7, (1.0, 1.0, 0.0))
+        x.set_exchange([9.0, 1.5])
+        x.set_dmi([5.0], S.CHIRALITY_NEEL)
+        x.llg_set(dt=2e-3, damping=0.25, temperature=3.0, convergence=1e-7)
+        mag, nrm = ctypes.c_float(), (ctypes.c_float * 3)()
+        lib.Hamiltonian_Get_Field(x.state, ctypes.byref(mag), nrm, -1, -1)
+        k, kn = ctypes.c_float(), (ctypes.c_float * 3)()
+        lib.Hamiltonian_Get_Anisotropy(x.state, ctypes.byref(k), kn, -1, -1)
+        vals.append((mag.value, list(nrm), k.value, list(kn), lib.Hamiltonian_Get_Exchange_N_Pairs(x.state, -1, -1),
+                     lib.Hamiltonian_Get_DMI_N_Pairs(x.state, -1, -1), lib.Parameters_LLG_Get_Time_Step(x.state, -1, -1),
+                     lib.Parameters_LLG_Get_Damping(x.state, -1, -1), lib.Parameters_LLG_Get_Temperature(x.state, -1, -1),
+                     lib.Parameters_LLG_Get_Convergence(x.state, -1, -1), x.pairs(0)[1].tolist(), x.pairs(1)[2].tolist()))
+        x.close()
+    assert vals[0] == vals[1]
