@@ -215,3 +215,40 @@ def gneb_vp_single_shots(model, imgs, types, k_spring, n_steps):
             imgs[i] = normalize(imgs[i] + model.dt * v[i] + 0.5 * model.dt * F[i])
         F = [project_tangential(F[i], imgs[i]) for i in range(noi)]
     return imgs, E, Rx
+
+
+def gneb_two_stage_single_shots(model, imgs, types, k_spring, n_steps, solver):
+    """GNEB with Depondt / Heun / SIB over all images (Solver_*.hpp with noi images). Virtual force dt gamma/mu_B s x F,
+    ZERO for the two end images (Method_GNEB.cpp:359-391 skips them).
+    Note: the compiled reference leaves forces_virtual of the end images UNINITIALISED for SIB
+    (Solver_SIB.hpp:4-5 allocates without a fill value), so its GNEB + SIB results are not reproducible; this function
+    states the intended semantics and is the oracle for that combination."""
+    imgs = [x.copy() for x in imgs]
+    dtg = model.dt * gamma / mu_B
+
+    def fv(conf):
+        F, E, Rx = gneb_force(model, conf, types, k_spring)
+        out = [dtg * np.cross(s, f) for s, f in zip(conf, F)]
+        out[0] = np.zeros_like(out[0])
+        out[-1] = np.zeros_like(out[-1])
+        return out, E, Rx
+
+    E = Rx = None
+    for _ in range(n_steps):
+        Fv, _, _ = fv(imgs)
+        if solver == "SIB":
+            pred = [0.5 * (s + sib_transform(s, f)) for s, f in zip(imgs, Fv)]
+            Fvp, E, Rx = fv(pred)
+            imgs = [sib_transform(s, f) for s, f in zip(imgs, Fvp)]
+        elif solver == "Depondt":
+            pred = [rotate(s, f) for s, f in zip(imgs, Fv)]
+            Fvp, E, Rx = fv(pred)
+            imgs = [rotate(s, 0.5 * (f + fp)) for s, f, fp in zip(imgs, Fv, Fvp)]
+        elif solver == "Heun":
+            k1 = [-np.cross(s, f) for s, f in zip(imgs, Fv)]
+            pred = [normalize(s + k) for s, k in zip(imgs, k1)]
+            Fvp, E, Rx = fv(pred)
+            imgs = [normalize(s + 0.5 * k - 0.5 * np.cross(sp, fp)) for s, k, sp, fp in zip(imgs, k1, pred, Fvp)]
+        else:
+            raise ValueError(solver)
+    return imgs, E, Rx

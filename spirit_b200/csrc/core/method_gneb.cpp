@@ -1,5 +1,8 @@
 #include "method_gneb.hpp"
+#include "constants.hpp"
 #include "logging.hpp"
+
+#include <algorithm>
 
 #include <cmath>
 #include <stdexcept>
@@ -32,30 +35,114 @@ std::vector<std::vector<double>> cubic_hermite_interpolate(
 }
 
 
-// ---- temporary: the image-batched device chain is not built yet ----
-namespace dev
-{
-class DeviceChain
-{
-};
-} // namespace dev
-
+// ---------------------------------------------------------------------------------------------
+// Method_GNEB (core/src/engine/Method_GNEB.cpp:23-456)
+// ---------------------------------------------------------------------------------------------
 Method_GNEB::Method_GNEB( std::shared_ptr<Chain> chain_, int solver_, int idx_chain_ )
         : Method( chain_->gneb_parameters, -1, idx_chain_ ), chain( std::move( chain_ ) )
 {
-    solver = solver_;
-    throw std::runtime_error( "spirit_b200: GNEB is not implemented yet" );
+    solver          = solver_;
+    const auto & P  = *chain->gneb_parameters;
+    // Not implemented (none of them is on the BASELINE configurations): refuse loudly instead of computing something else
+    if( P.spring_force_ratio > 0 )
+        throw std::runtime_error( "spirit_b200: gneb_spring_force_ratio > 0 (energy-weighted springs) is not implemented" );
+    if( P.path_shortening_constant > 0 )
+        throw std::runtime_error( "spirit_b200: gneb_path_shortening_constant > 0 is not implemented" );
+    if( P.moving_endpoints || P.translating_endpoints )
+        throw std::runtime_error( "spirit_b200: GNEB moving / translating endpoints are not implemented" );
+
+    // We assume that the chain is not converged before the first iteration (Method_GNEB.cpp:53-55)
+    max_torque     = P.force_convergence + 1.0;
+    max_torque_all = std::vector<double>( chain->noi, 0.0 );
+
+    device_ = std::make_unique<dev::DeviceChain>( *chain->images[0]->geometry, chain->noi );
+    device_->set_hamiltonian( *chain->images[0]->hamiltonian );
+    Sync_Device();
+    device_->vp_reset();
+
+    // Data of the border images, which are not updated (Method_GNEB.cpp:68-72)
+    chain->images.front()->UpdateEffectiveField();
+    chain->images.back()->UpdateEffectiveField();
 }
+
 Method_GNEB::~Method_GNEB() = default;
-void Method_GNEB::Iteration( bool ) {}
-void Method_GNEB::Hook_Post_Iteration() {}
-void Method_GNEB::Finalize() {}
-void Method_GNEB::Save_Current( bool, bool ) {}
+
+static dev::GNEBParams gneb_params( const Chain & chain )
+{
+    dev::GNEBParams g;
+    g.spring_constant = chain.gneb_parameters->spring_constant;
+    g.dt              = chain.images[0]->llg_parameters->dt;
+    g.dtg             = g.dt * constants::gamma / constants::mu_B;
+    for( int i = 0; i < chain.noi; ++i )
+        g.image_type.push_back( int( chain.image_type[i] ) );
+    return g;
+}
+
+void Method_GNEB::Iteration( bool hook_follows )
+{
+    device_->set_hamiltonian( *chain->images[0]->hamiltonian );
+    device_->iterate( solver, gneb_params( *chain ), 1, hook_follows, hook_follows ? &pending_ : nullptr );
+    hook_pending_ = hook_follows;
+    evaluated_    = true;
+}
+
+// Method_GNEB.cpp:410-456
+void Method_GNEB::Hook_Post_Iteration()
+{
+    if( !hook_pending_ )
+        return;
+    hook_pending_ = false;
+    if( pending_.degenerate )
+    {
+        Log( Log_Level::Error, Log_Sender::GNEB, "The geodesic distance between two images is zero! Stopping...", -1, idx_chain );
+        chain->iteration_allowed = false;
+        return;
+    }
+    max_torque = 0;
+    for( int img = 0; img < chain->noi; ++img )
+    {
+        max_torque_all[img] = pending_.max_torque[img];
+        max_torque          = std::max( max_torque, pending_.max_torque[img] );
+    }
+    auto interp = cubic_hermite_interpolate( pending_.Rx, pending_.energy, pending_.dE_dRx, chain->gneb_parameters->n_E_interpolations );
+    chain->Rx   = pending_.Rx;
+    for( int img = 0; img < chain->noi; ++img )
+        chain->images[img]->E = pending_.energy[img];
+    chain->Rx_interpolated = interp[0];
+    chain->E_interpolated  = interp[1];
+}
+
 bool Method_GNEB::Converged()
 {
-    return true;
+    return max_torque < chain->gneb_parameters->force_convergence;
 }
-void Method_GNEB::Sync_Host() {}
-void Method_GNEB::Sync_Device() {}
+
+void Method_GNEB::Finalize()
+{
+    chain->iteration_allowed = false;
+}
+
+void Method_GNEB::Save_Current( bool, bool )
+{
+    history_iteration.push_back( int( iteration ) );
+    history_max_torque.push_back( max_torque );
+    history_energy.push_back( chain->images[chain->idx_active_image]->E );
+}
+
+void Method_GNEB::Sync_Host()
+{
+    for( int img = 0; img < chain->noi; ++img )
+    {
+        device_->download_image( img, chain->images[img]->spins.scalars() );
+        if( evaluated_ )
+            device_->download_effective_field( img, chain->images[img]->effective_field.scalars() );
+    }
+}
+
+void Method_GNEB::Sync_Device()
+{
+    for( int img = 0; img < chain->noi; ++img )
+        device_->upload_image( img, chain->images[img]->spins.scalars() );
+}
 
 } // namespace sb

@@ -9,10 +9,6 @@
 
 namespace sb
 {
-namespace dev
-{
-class DeviceChain;
-}
 
 class Method_GNEB : public Method
 {
@@ -53,7 +49,9 @@ public:
 
 private:
     std::unique_ptr<dev::DeviceChain> device_;
+    dev::ChainHookResult pending_;
     bool hook_pending_ = false;
+    bool evaluated_    = false; // at least one force evaluation ran (the effective fields on the device are meaningful)
 };
 
 // Cubic Hermite interpolation of p(x) with slopes m (core/src/utility/Cubic_Hermite_Spline.cpp:11-48)

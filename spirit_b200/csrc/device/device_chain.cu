@@ -1,0 +1,674 @@
+// GNEB on the device: the whole chain of images lives in HBM as [noi][field] allocations and every kernel is batched
+// over images (blockIdx.y = image). Reference: Method_GNEB::Calculate_Force / Calculate_Force_Virtual /
+// Hook_Post_Iteration (core/src/engine/Method_GNEB.cpp:87-456), Manifoldmath::Tangents / Geodesic_Tangent /
+// dist_geodesic / project_* (core/src/engine/Manifoldmath.cpp:23-213), the solver templates over `noi` images
+// (core/include/engine/Solver_VP.hpp:29-114, Solver_Depondt.hpp:29-77, Solver_Heun.hpp:30-81, Solver_SIB.hpp:22-50).
+//
+// One force evaluation of a configuration set {s_img}:
+//   k_chain_gradient   F_g = -grad E(s_img) for every image, partial sums of E and of the squared geodesic
+//                      distance to the previous image
+//   k_reduce_rows      E[img], D2[img]                                   (deterministic two-level reductions)
+//   k_chain_rx         Rx[img] = Rx[img-1] + sqrt(D2[img])
+//   k_chain_tangent    t_img (energy-weighted secants, projected to the tangent planes; geodesic tangent at the two
+//                      end images), partial sums of t.t and of P(F_g).t
+//   k_reduce_rows      TT[img], FT[img]
+//   k_chain_coeffs     per image: F = P(F_g) + c_t t   with c_t from the image type (normal: -FT/TT + spring; climbing:
+//                      -2 FT/TT; falling: 0), F = 0 for the end images and stationary images
+// and the total force is assembled inside the solver kernel that consumes it (VP velocity update, or the stage of
+// Depondt / Heun / SIB), so F is written once and the projected gradient force, the spring force and the tangent
+// normalisation never exist as separate fields (the reference keeps F_gradient, F_spring, F_total, tangents and two
+// secant temporaries per image and sweeps each of them several times).
+#include "device_buffers.cuh"
+
+#include "../core/hamiltonian.hpp"
+
+#include <cmath>
+#include <cstring>
+#include <stdexcept>
+
+namespace sb
+{
+namespace dev
+{
+
+namespace
+{
+
+// Scalar slots on the device, each an array [noi]
+enum Slot
+{
+    S_E = 0,  // energy of the last evaluated configuration
+    S_D2,     // squared geodesic distance to the previous image
+    S_RX,     // reaction coordinate
+    S_TT,     // t.t
+    S_FT,     // P(F_g).t = F_g.t
+    S_CT,     // coefficient of t in the total force
+    S_ZERO,   // 1: the total force of this image is zero (end image / stationary)
+    S_TQ,     // max torque^2 (hook)
+    S_VP,     // partial v.F per image
+    S_VP2,    // partial F.F per image
+    S_N_SLOTS
+};
+// global scalars behind the per-image slots: [0] ratio_prev, [1] ratio, [2] degenerate flag
+constexpr int G_RATIO_PREV = 0, G_RATIO = 1, G_DEGENERATE = 2, G_N = 4;
+
+struct ChainView
+{
+    double * S;   // configurations
+    double * P;   // predictor configurations
+    double * Fg;  // effective field -grad E (unprojected) of the last evaluation
+    double * T;   // tangents (not normalised)
+    double * F;   // total force of the first evaluation of the iteration ("forces")
+    double * F2;  // total force of the predictor evaluation / new force of VP
+    double * Fpr; // VP: force projected by the hook (F_prev of the next iteration)
+    std::size_t stride; // doubles per image and field
+    double * scal;      // [S_N_SLOTS][noi] + G_N
+    int noi;
+};
+
+__device__ __forceinline__ ConstField3 cfield( const double * base, std::size_t stride, int img )
+{
+    ConstField3 f;
+    f.base = base + stride * img;
+    return f;
+}
+__device__ __forceinline__ Field3 field( double * base, std::size_t stride, int img )
+{
+    Field3 f;
+    f.base = base + stride * img;
+    return f;
+}
+__device__ __forceinline__ double * slot( const ChainView & v, int s )
+{
+    return v.scal + std::size_t( s ) * v.noi;
+}
+__device__ __forceinline__ double * globals( const ChainView & v )
+{
+    return v.scal + std::size_t( S_N_SLOTS ) * v.noi;
+}
+
+// row r of `partials` ([rows][n]) -> out[r]
+static __global__ void __launch_bounds__( BLOCK_THREADS ) k_reduce_rows( const double * __restrict__ partials, int n, double * __restrict__ out )
+{
+    const double * row = partials + std::size_t( blockIdx.x ) * n;
+    double v           = 0;
+    for( int i = threadIdx.x; i < n; i += BLOCK_THREADS )
+        v += row[i];
+    v = block_sum( v );
+    if( threadIdx.x == 0 )
+        out[blockIdx.x] = v;
+}
+static __global__ void __launch_bounds__( BLOCK_THREADS ) k_reduce_rows_max( const double * __restrict__ partials, int n, double * __restrict__ out )
+{
+    const double * row = partials + std::size_t( blockIdx.x ) * n;
+    double v           = 0;
+    for( int i = threadIdx.x; i < n; i += BLOCK_THREADS )
+        v = fmax( v, row[i] );
+    v = block_max( v );
+    if( threadIdx.x == 0 )
+        out[blockIdx.x] = v;
+}
+
+// Gradient and energy of every image + squared geodesic distance to the previous image (Method_GNEB.cpp:95-128)
+template<int NB_T>
+static __global__ void __launch_bounds__( BLOCK_THREADS ) k_chain_gradient(
+    const __grid_constant__ StencilParams p, const __grid_constant__ LaunchGeom lg, const __grid_constant__ ChainView v,
+    const double * __restrict__ conf, double * __restrict__ partials, int nblocks )
+{
+    const int img = blockIdx.y;
+    Site site;
+    const bool active = locate_site( p, lg, site, NB_T > 0 ? NB_T : p.NB );
+    double e = 0, d2 = 0;
+    if( active )
+    {
+        const ConstField3 s  = cfield( conf, v.stride, img );
+        const ConstField3 no = cfield( conf, v.stride, img ); // no DDI field in the chain path
+        const D3 si          = load3( s, site.idx );
+        const SiteGradient g = site_gradient<NB_T>( p, s, no, site, si );
+        const D3 gt          = total( g );
+        store3( field( v.Fg, v.stride, img ), site.idx, make_d3( -gt.x, -gt.y, -gt.z ) );
+        e = site_energy<NB_T>( p, site, si, g );
+        if( img > 0 )
+        {
+            const D3 sp = load3( cfield( conf, v.stride, img - 1 ), site.idx );
+            double r    = dot3( si, sp );
+            r           = fmax( -1.0, fmin( 1.0, r ) ); // Vectormath::angle, Vectormath.cpp:434-441
+            const double a = acos( r );
+            d2             = a * a;
+        }
+    }
+    e = block_sum( e );
+    if( threadIdx.x == 0 )
+        partials[( std::size_t( 0 ) * v.noi + img ) * nblocks + blockIdx.x] = e;
+    d2 = block_sum( d2 );
+    if( threadIdx.x == 0 )
+        partials[( std::size_t( 1 ) * v.noi + img ) * nblocks + blockIdx.x] = d2;
+}
+
+// Rx and the degenerate-chain check (Method_GNEB.cpp:116-126)
+static __global__ void k_chain_rx( const __grid_constant__ ChainView v )
+{
+    double * Rx       = slot( v, S_RX );
+    const double * D2 = slot( v, S_D2 );
+    Rx[0]             = 0;
+    for( int i = 1; i < v.noi; ++i )
+    {
+        const double d = sqrt( D2[i] );
+        Rx[i]          = Rx[i - 1] + d;
+        if( d < 1e-10 )
+            globals( v )[G_DEGENERATE] = 1.0;
+    }
+}
+
+// Tangents (Manifoldmath.cpp:77-213)
+static __global__ void __launch_bounds__( BLOCK_THREADS ) k_chain_tangent(
+    const __grid_constant__ StencilParams p, const __grid_constant__ LaunchGeom lg, const __grid_constant__ ChainView v,
+    const double * __restrict__ conf, double * __restrict__ partials, int nblocks )
+{
+    const int img = blockIdx.y;
+    Site site;
+    const bool active = locate_site( p, lg, site, p.NB );
+    double tt = 0, ft = 0;
+    if( active )
+    {
+        const D3 s = load3( cfield( conf, v.stride, img ), site.idx );
+        D3 t;
+        if( img == 0 || img == v.noi - 1 )
+        {
+            // Geodesic_Tangent at the end images: t = mid x (plus x minus)
+            const D3 minus = img == 0 ? s : load3( cfield( conf, v.stride, img - 1 ), site.idx );
+            const D3 plus  = img == 0 ? load3( cfield( conf, v.stride, 1 ), site.idx ) : s;
+            D3 axis        = cross3( plus, minus );
+            if( fabs( dot3( minus, plus ) + 1.0 ) < 1e-15 )
+                axis = fabs( s.x - 1.0 ) > 1e-15 ? make_d3( 1, 0, 0 ) : make_d3( 0, 1, 0 );
+            t = cross3( s, axis );
+        }
+        else
+        {
+            const D3 sp      = load3( cfield( conf, v.stride, img + 1 ), site.idx );
+            const D3 sm      = load3( cfield( conf, v.stride, img - 1 ), site.idx );
+            const D3 tp      = make_d3( sp.x - s.x, sp.y - s.y, sp.z - s.z );
+            const D3 tm      = make_d3( s.x - sm.x, s.y - sm.y, s.z - sm.z );
+            const double * E = slot( v, S_E );
+            const double Em = E[img], Ep = E[img + 1], Emi = E[img - 1];
+            double wp, wm;
+            if( ( Ep < Em && Em > Emi ) || ( Ep > Em && Em < Emi ) )
+            {
+                const double Emax = fmax( fabs( Ep - Em ), fabs( Emi - Em ) );
+                const double Emin = fmin( fabs( Ep - Em ), fabs( Emi - Em ) );
+                wp                = Ep > Emi ? Emax : Emin;
+                wm                = Ep > Emi ? Emin : Emax;
+            }
+            else if( Ep > Em && Em > Emi )
+            {
+                wp = 1;
+                wm = 0;
+            }
+            else if( Ep < Em && Em < Emi )
+            {
+                wp = 0;
+                wm = 1;
+            }
+            else
+            {
+                wp = 1;
+                wm = 1;
+            }
+            t = make_d3( wp * tp.x + wm * tm.x, wp * tp.y + wm * tm.y, wp * tp.z + wm * tm.z );
+            // project into the tangent plane of the spin
+            const double d = dot3( t, s );
+            t              = make_d3( t.x - d * s.x, t.y - d * s.y, t.z - d * s.z );
+        }
+        store3( field( v.T, v.stride, img ), site.idx, t );
+        tt          = dot3( t, t );
+        const D3 Fg = load3( cfield( v.Fg, v.stride, img ), site.idx );
+        // projected gradient force . tangent (for interior images t is perpendicular to s, so this is also F_g.t)
+        const double d = dot3( Fg, s );
+        ft             = ( Fg.x - d * s.x ) * t.x + ( Fg.y - d * s.y ) * t.y + ( Fg.z - d * s.z ) * t.z;
+        if( img == 0 || img == v.noi - 1 )
+            ft = dot3( Fg, t ); // dE/dRx at the end images uses the unprojected effective field (Method_GNEB.cpp:433-437)
+    }
+    tt = block_sum( tt );
+    if( threadIdx.x == 0 )
+        partials[( std::size_t( 0 ) * v.noi + img ) * nblocks + blockIdx.x] = tt;
+    ft = block_sum( ft );
+    if( threadIdx.x == 0 )
+        partials[( std::size_t( 1 ) * v.noi + img ) * nblocks + blockIdx.x] = ft;
+}
+
+struct ChainTypes
+{
+    int type[256];
+};
+
+// Per-image coefficients of the total force (Method_GNEB.cpp:175-258), one thread per image
+static __global__ void k_chain_coeffs( const __grid_constant__ ChainView v, const __grid_constant__ ChainTypes types, double spring_constant )
+{
+    const int img = blockIdx.x * blockDim.x + threadIdx.x;
+    if( img >= v.noi )
+        return;
+    double ct = 0, zero = 0;
+    if( img == 0 || img == v.noi - 1 || types.type[img] == 3 )
+        zero = 1;
+    else
+    {
+        const double tt = slot( v, S_TT )[img], ft = slot( v, S_FT )[img];
+        const double * Rx = slot( v, S_RX );
+        if( types.type[img] == 1 ) // climbing: invert the component along the tangent
+            ct = -2.0 * ft / tt;
+        else if( types.type[img] == 2 ) // falling: gradient force only
+            ct = 0;
+        else // normal: orthogonal to the tangent + spring force along it
+            ct = -ft / tt + spring_constant * ( Rx[img + 1] - 2 * Rx[img] + Rx[img - 1] ) / sqrt( tt );
+    }
+    slot( v, S_CT )[img]   = ct;
+    slot( v, S_ZERO )[img] = zero;
+}
+
+// Total force of a site from the effective field, the tangent and the image coefficients
+__device__ __forceinline__ D3 chain_total_force( const ChainView & v, int img, std::size_t idx, const D3 & s )
+{
+    if( slot( v, S_ZERO )[img] != 0.0 )
+        return make_d3( 0, 0, 0 );
+    const D3 Fg     = load3( cfield( v.Fg, v.stride, img ), idx );
+    const D3 t      = load3( cfield( v.T, v.stride, img ), idx );
+    const double d  = dot3( Fg, s );
+    const double ct = slot( v, S_CT )[img];
+    return make_d3( Fg.x - d * s.x + ct * t.x, Fg.y - d * s.y + ct * t.y, Fg.z - d * s.z + ct * t.z );
+}
+
+// VP, part A (Solver_VP.hpp:29-79): F_new, v = ratio_prev F_old + (F_prev + F_new)/2, partial sums of v.F_new, F_new.F_new
+static __global__ void __launch_bounds__( BLOCK_THREADS ) k_chain_vp_a(
+    const __grid_constant__ StencilParams p, const __grid_constant__ LaunchGeom lg, const __grid_constant__ ChainView v,
+    const double * __restrict__ F_prev, double * __restrict__ partials, int nblocks )
+{
+    const int img = blockIdx.y;
+    Site site;
+    const bool active = locate_site( p, lg, site, p.NB );
+    double proj = 0, norm2 = 0;
+    if( active )
+    {
+        const double ratio_prev = globals( v )[G_RATIO_PREV];
+        const D3 s              = load3( cfield( v.S, v.stride, img ), site.idx );
+        const D3 Fn             = chain_total_force( v, img, site.idx, s );
+        const D3 Fo             = load3( cfield( v.F, v.stride, img ), site.idx );    // raw force of the last iteration
+        const D3 Fp             = load3( cfield( F_prev, v.stride, img ), site.idx ); // the same, or projected by the hook
+        const D3 vel            = make_d3(
+            ratio_prev * Fo.x + 0.5 * ( Fp.x + Fn.x ), ratio_prev * Fo.y + 0.5 * ( Fp.y + Fn.y ),
+            ratio_prev * Fo.z + 0.5 * ( Fp.z + Fn.z ) );
+        proj  = dot3( vel, Fn );
+        norm2 = dot3( Fn, Fn );
+        store3( field( v.F2, v.stride, img ), site.idx, Fn );
+    }
+    proj = block_sum( proj );
+    if( threadIdx.x == 0 )
+        partials[( std::size_t( 0 ) * v.noi + img ) * nblocks + blockIdx.x] = proj;
+    norm2 = block_sum( norm2 );
+    if( threadIdx.x == 0 )
+        partials[( std::size_t( 1 ) * v.noi + img ) * nblocks + blockIdx.x] = norm2;
+}
+
+// sums over images -> ratio (Solver_VP.hpp:75-103)
+static __global__ void k_chain_vp_ratio( const __grid_constant__ ChainView v )
+{
+    double proj = 0, norm2 = 0;
+    for( int i = 0; i < v.noi; ++i )
+    {
+        proj += slot( v, S_VP )[i];
+        norm2 += slot( v, S_VP2 )[i];
+    }
+    const double ratio        = proj > 0 ? proj / norm2 : 0.0;
+    globals( v )[G_RATIO]      = ratio;
+    globals( v )[G_RATIO_PREV] = ratio;
+}
+
+// VP, part B: s <- |s + dt ratio F + dt F / 2| for every image; HOOK: max torque and the in-place projection of the
+// forces (Method_GNEB.cpp:416-428)
+template<bool HOOK>
+static __global__ void __launch_bounds__( BLOCK_THREADS ) k_chain_vp_b(
+    const __grid_constant__ StencilParams p, const __grid_constant__ LaunchGeom lg, const __grid_constant__ ChainView v, double dt,
+    double * __restrict__ partials, int nblocks )
+{
+    const int img = blockIdx.y;
+    Site site;
+    const bool active = locate_site( p, lg, site, p.NB );
+    double t2         = 0;
+    if( active )
+    {
+        const double ratio = globals( v )[G_RATIO];
+        const Field3 S     = field( v.S, v.stride, img );
+        const D3 s         = load3( S, site.idx );
+        D3 F               = load3( cfield( v.F2, v.stride, img ), site.idx );
+        const double c     = dt * ratio + 0.5 * dt;
+        const D3 sn        = normalized3( make_d3( s.x + c * F.x, s.y + c * F.y, s.z + c * F.z ) );
+        store3( S, site.idx, sn );
+        if( HOOK )
+        {
+            const double f = dot3( F, sn );
+            F              = make_d3( F.x - f * sn.x, F.y - f * sn.y, F.z - f * sn.z );
+            t2             = dot3( F, F );
+            store3( field( v.Fpr, v.stride, img ), site.idx, F );
+        }
+    }
+    if( HOOK )
+    {
+        t2 = block_max( t2 );
+        if( threadIdx.x == 0 )
+            partials[std::size_t( img ) * nblocks + blockIdx.x] = t2;
+    }
+}
+
+// Stages of the two-stage solvers over all images. Virtual force: Fv = dtg s x F, zero for the end images
+// (Method_GNEB.cpp:359-391). Stage 1 assembles F(s) and writes the predictor; stage 2 assembles F(s') and updates s.
+template<int SOLVER, int STAGE>
+static __global__ void __launch_bounds__( BLOCK_THREADS ) k_chain_stage(
+    const __grid_constant__ StencilParams p, const __grid_constant__ LaunchGeom lg, const __grid_constant__ ChainView v, double dtg )
+{
+    const int img = blockIdx.y;
+    Site site;
+    if( !locate_site( p, lg, site, p.NB ) )
+        return;
+    const bool end = img == 0 || img == v.noi - 1;
+    const D3 s     = load3( cfield( v.S, v.stride, img ), site.idx );
+    D3 acc         = make_d3( 0, 0, 0 );
+    if( STAGE == 1 )
+    {
+        const D3 F = chain_total_force( v, img, site.idx, s );
+        store3( field( v.F, v.stride, img ), site.idx, F );
+        D3 Fv = make_d3( 0, 0, 0 );
+        if( !end )
+        {
+            const D3 c = cross3( s, F );
+            Fv         = make_d3( dtg * c.x, dtg * c.y, dtg * c.z );
+        }
+        store3( field( v.P, v.stride, img ), site.idx, solver_update<SOLVER, 1>( s, Fv, s, Fv, acc ) );
+    }
+    else
+    {
+        const D3 sp = load3( cfield( v.P, v.stride, img ), site.idx );
+        const D3 F2 = chain_total_force( v, img, site.idx, sp );
+        store3( field( v.F2, v.stride, img ), site.idx, F2 );
+        D3 Fv = make_d3( 0, 0, 0 ), Fvp = make_d3( 0, 0, 0 );
+        if( !end )
+        {
+            const D3 F1 = load3( cfield( v.F, v.stride, img ), site.idx );
+            const D3 c1 = cross3( s, F1 );
+            Fv          = make_d3( dtg * c1.x, dtg * c1.y, dtg * c1.z );
+            const D3 c2 = cross3( sp, F2 );
+            Fvp         = make_d3( dtg * c2.x, dtg * c2.y, dtg * c2.z );
+        }
+        store3( field( v.S, v.stride, img ), site.idx, solver_update<SOLVER, 2>( s, Fv, sp, Fvp, acc ) );
+    }
+}
+
+// Hook of the two-stage solvers: max_i |F_total - (F_total.s)s| per image with the NEW spins, F_total = force of the last
+// (predictor) evaluation (Method_GNEB.cpp:416-424)
+static __global__ void __launch_bounds__( BLOCK_THREADS ) k_chain_hook(
+    const __grid_constant__ StencilParams p, const __grid_constant__ LaunchGeom lg, const __grid_constant__ ChainView v,
+    double * __restrict__ partials, int nblocks )
+{
+    const int img = blockIdx.y;
+    Site site;
+    const bool active = locate_site( p, lg, site, p.NB );
+    double t2         = 0;
+    if( active )
+    {
+        const D3 s     = load3( cfield( v.S, v.stride, img ), site.idx );
+        const D3 F     = load3( cfield( v.F2, v.stride, img ), site.idx );
+        const double f = dot3( F, s );
+        const D3 q     = make_d3( F.x - f * s.x, F.y - f * s.y, F.z - f * s.z );
+        t2             = dot3( q, q );
+    }
+    t2 = block_max( t2 );
+    if( threadIdx.x == 0 )
+        partials[std::size_t( img ) * nblocks + blockIdx.x] = t2;
+}
+
+} // namespace
+
+// ---------------------------------------------------------------------------------------------
+struct DeviceChainBuffers
+{
+    cudaStream_t stream = nullptr;
+    double * fields     = nullptr; // 7 x [noi][stride]
+    double * partials   = nullptr; // [2][noi][nblocks]
+    double * scal       = nullptr;
+    double * h_scal     = nullptr; // pinned mirror
+    double * staging    = nullptr; // AoS [nos][3]
+    std::size_t stride  = 0;
+    std::size_t n_scal  = 0;
+    ChainView view{};
+
+    ~DeviceChainBuffers()
+    {
+        if( fields )
+            cudaFree( fields );
+        if( partials )
+            cudaFree( partials );
+        if( scal )
+            cudaFree( scal );
+        if( staging )
+            cudaFree( staging );
+        if( h_scal )
+            cudaFreeHost( h_scal );
+        if( stream )
+            cudaStreamDestroy( stream );
+    }
+};
+
+DeviceChain::DeviceChain( const Geometry & geometry, int noi ) : noi_( noi )
+{
+    require_device();
+    if( noi > 256 )
+        throw std::runtime_error( "spirit_b200: chains of more than 256 images are not supported" );
+    table_ = std::make_unique<DeviceImage>( geometry );
+    nos_   = table_->nos();
+    buf_   = std::make_unique<DeviceChainBuffers>();
+    auto & b       = *buf_;
+    const auto & T = *table_->buffers();
+    b.stride       = 3 * T.n_storage;
+    b.n_scal       = std::size_t( S_N_SLOTS ) * noi + G_N;
+    SB_CUDA_CHECK( cudaStreamCreateWithFlags( &b.stream, cudaStreamNonBlocking ) );
+    SB_CUDA_CHECK( cudaMalloc( &b.fields, 7 * std::size_t( noi ) * b.stride * sizeof( double ) ) );
+    SB_CUDA_CHECK( cudaMemset( b.fields, 0, 7 * std::size_t( noi ) * b.stride * sizeof( double ) ) );
+    SB_CUDA_CHECK( cudaMalloc( &b.partials, 2 * std::size_t( noi ) * T.nblocks * sizeof( double ) ) );
+    SB_CUDA_CHECK( cudaMalloc( &b.scal, b.n_scal * sizeof( double ) ) );
+    SB_CUDA_CHECK( cudaMemset( b.scal, 0, b.n_scal * sizeof( double ) ) );
+    SB_CUDA_CHECK( cudaHostAlloc( &b.h_scal, b.n_scal * sizeof( double ), cudaHostAllocDefault ) );
+    SB_CUDA_CHECK( cudaMalloc( &b.staging, 3 * std::size_t( nos_ ) * sizeof( double ) ) );
+    const std::size_t fs = std::size_t( noi ) * b.stride;
+    b.view.S             = b.fields + 0 * fs;
+    b.view.P             = b.fields + 1 * fs;
+    b.view.Fg            = b.fields + 2 * fs;
+    b.view.T             = b.fields + 3 * fs;
+    b.view.F             = b.fields + 4 * fs;
+    b.view.F2            = b.fields + 5 * fs;
+    b.view.Fpr           = b.fields + 6 * fs;
+    b.view.stride        = b.stride;
+    b.view.scal          = b.scal;
+    b.view.noi           = noi;
+}
+
+DeviceChain::~DeviceChain() = default;
+
+void DeviceChain::set_hamiltonian( const Hamiltonian & ham )
+{
+    table_->set_hamiltonian( ham );
+    if( table_->stencil().has_ddi )
+        throw std::runtime_error( "spirit_b200: GNEB with dipole-dipole interaction is not implemented" );
+}
+
+void DeviceChain::synchronize()
+{
+    SB_CUDA_CHECK( cudaStreamSynchronize( buf_->stream ) );
+}
+
+void DeviceChain::upload_image( int img, const double * host_aos )
+{
+    auto & b       = *buf_;
+    const auto & p = table_->stencil();
+    SB_CUDA_CHECK( cudaMemcpyAsync( b.staging, host_aos, 3 * std::size_t( nos_ ) * sizeof( double ), cudaMemcpyHostToDevice, b.stream ) );
+    Field3 f;
+    f.base = b.view.S + b.stride * img;
+    k_aos_to_soa<<<( nos_ + BLOCK_THREADS - 1 ) / BLOCK_THREADS, BLOCK_THREADS, 0, b.stream>>>(
+        b.staging, f, nos_, table_->buffers()->plane_sites, p.plane_stride, p.halo );
+    ++launches_;
+    SB_CUDA_CHECK( cudaGetLastError() );
+    SB_CUDA_CHECK( cudaStreamSynchronize( b.stream ) ); // the staging buffer is reused by the next image
+}
+
+static void chain_download( DeviceChainBuffers & b, const DeviceImage & table, const double * base, int img, double * host_aos, int nos )
+{
+    const auto & p = table.stencil();
+    ConstField3 f;
+    f.base = base + b.stride * img;
+    k_soa_to_aos<<<( nos + BLOCK_THREADS - 1 ) / BLOCK_THREADS, BLOCK_THREADS, 0, b.stream>>>(
+        f, b.staging, nos, const_cast<DeviceImage &>( table ).buffers()->plane_sites, p.plane_stride, p.halo, 1.0 );
+    SB_CUDA_CHECK( cudaGetLastError() );
+    SB_CUDA_CHECK( cudaMemcpyAsync( host_aos, b.staging, 3 * std::size_t( nos ) * sizeof( double ), cudaMemcpyDeviceToHost, b.stream ) );
+    SB_CUDA_CHECK( cudaStreamSynchronize( b.stream ) );
+}
+
+void DeviceChain::download_image( int img, double * host_aos )
+{
+    chain_download( *buf_, *table_, buf_->view.S, img, host_aos, nos_ );
+    ++launches_;
+}
+
+void DeviceChain::download_effective_field( int img, double * host_aos )
+{
+    chain_download( *buf_, *table_, buf_->view.Fg, img, host_aos, nos_ );
+    ++launches_;
+}
+
+void DeviceChain::vp_reset()
+{
+    auto & b = *buf_;
+    // velocity = 0, F = F_prev = 0 (Method_GNEB's constructor evaluates no force, Method_GNEB.cpp:23-73)
+    const std::size_t fs = std::size_t( noi_ ) * b.stride * sizeof( double );
+    SB_CUDA_CHECK( cudaMemsetAsync( b.view.F, 0, fs, b.stream ) );
+    SB_CUDA_CHECK( cudaMemsetAsync( b.view.F2, 0, fs, b.stream ) );
+    SB_CUDA_CHECK( cudaMemsetAsync( b.view.Fpr, 0, fs, b.stream ) );
+    SB_CUDA_CHECK( cudaMemsetAsync( b.scal + std::size_t( S_N_SLOTS ) * noi_, 0, G_N * sizeof( double ), b.stream ) );
+    vp_prev_projected_ = false;
+}
+
+// which_configuration: 0 = S, 1 = P. Leaves F_g, T and the per-image coefficients on the device.
+void DeviceChain::evaluate_force( const GNEBParams & params, int which_configuration, int )
+{
+    auto & b          = *buf_;
+    const auto & T    = *table_->buffers();
+    const auto & p    = table_->stencil();
+    const double * cf = which_configuration == 0 ? b.view.S : b.view.P;
+    const dim3 grid( T.nblocks, noi_ );
+    if( p.NB == 1 )
+        k_chain_gradient<1><<<grid, BLOCK_THREADS, 0, b.stream>>>( p, T.lg, b.view, cf, b.partials, T.nblocks );
+    else
+        k_chain_gradient<0><<<grid, BLOCK_THREADS, 0, b.stream>>>( p, T.lg, b.view, cf, b.partials, T.nblocks );
+    // rows [0, noi) -> E, rows [noi, 2 noi) -> D2 (adjacent slots)
+    k_reduce_rows<<<2 * noi_, BLOCK_THREADS, 0, b.stream>>>( b.partials, T.nblocks, b.scal + std::size_t( S_E ) * noi_ );
+    k_chain_rx<<<1, 1, 0, b.stream>>>( b.view );
+    k_chain_tangent<<<grid, BLOCK_THREADS, 0, b.stream>>>( p, T.lg, b.view, cf, b.partials, T.nblocks );
+    k_reduce_rows<<<2 * noi_, BLOCK_THREADS, 0, b.stream>>>( b.partials, T.nblocks, b.scal + std::size_t( S_TT ) * noi_ );
+    ChainTypes types{};
+    for( int i = 0; i < noi_; ++i )
+        types.type[i] = i < int( params.image_type.size() ) ? params.image_type[i] : 0;
+    k_chain_coeffs<<<( noi_ + 63 ) / 64, 64, 0, b.stream>>>( b.view, types, params.spring_constant );
+    launches_ += 6;
+    SB_CUDA_CHECK( cudaGetLastError() );
+}
+
+namespace
+{
+template<int SOLVER>
+void launch_chain_stages(
+    DeviceChain & chain, DeviceChainBuffers & b, const DeviceBuffers & T, const StencilParams & p, int noi, double dtg, int stage )
+{
+    const dim3 grid( T.nblocks, noi );
+    if( stage == 1 )
+        k_chain_stage<SOLVER, 1><<<grid, BLOCK_THREADS, 0, b.stream>>>( p, T.lg, b.view, dtg );
+    else
+        k_chain_stage<SOLVER, 2><<<grid, BLOCK_THREADS, 0, b.stream>>>( p, T.lg, b.view, dtg );
+}
+} // namespace
+
+void DeviceChain::iterate( int solver, const GNEBParams & params, int n_iterations, bool hook, ChainHookResult * result )
+{
+    auto & b       = *buf_;
+    const auto & T = *table_->buffers();
+    const auto & p = table_->stencil();
+    const dim3 grid( T.nblocks, noi_ );
+    if( solver != Solver_VP && solver != Solver_Depondt && solver != Solver_Heun && solver != Solver_SIB )
+        throw std::runtime_error( "spirit_b200: GNEB solver id " + std::to_string( solver ) + " is not implemented" );
+
+    for( int it = 0; it < n_iterations; ++it )
+    {
+        const bool hk = hook && it == n_iterations - 1;
+        if( solver == Solver_VP )
+        {
+            evaluate_force( params, 0, 0 );
+            const double * F_prev = vp_prev_projected_ ? b.view.Fpr : b.view.F;
+            k_chain_vp_a<<<grid, BLOCK_THREADS, 0, b.stream>>>( p, T.lg, b.view, F_prev, b.partials, T.nblocks );
+            k_reduce_rows<<<2 * noi_, BLOCK_THREADS, 0, b.stream>>>( b.partials, T.nblocks, b.scal + std::size_t( S_VP ) * noi_ );
+            k_chain_vp_ratio<<<1, 1, 0, b.stream>>>( b.view );
+            if( hk )
+            {
+                k_chain_vp_b<true><<<grid, BLOCK_THREADS, 0, b.stream>>>( p, T.lg, b.view, params.dt, b.partials, T.nblocks );
+                k_reduce_rows_max<<<noi_, BLOCK_THREADS, 0, b.stream>>>( b.partials, T.nblocks, b.scal + std::size_t( S_TQ ) * noi_ );
+                ++launches_;
+            }
+            else
+                k_chain_vp_b<false><<<grid, BLOCK_THREADS, 0, b.stream>>>( p, T.lg, b.view, params.dt, b.partials, T.nblocks );
+            launches_ += 4;
+            // the new force becomes "the force of the last iteration"
+            std::swap( b.view.F, b.view.F2 );
+            vp_prev_projected_ = hk;
+        }
+        else
+        {
+            for( int stage = 1; stage <= 2; ++stage )
+            {
+                evaluate_force( params, stage - 1, 0 );
+                if( solver == Solver_Depondt )
+                    launch_chain_stages<Solver_Depondt>( *this, b, T, p, noi_, params.dtg, stage );
+                else if( solver == Solver_Heun )
+                    launch_chain_stages<Solver_Heun>( *this, b, T, p, noi_, params.dtg, stage );
+                else
+                    launch_chain_stages<Solver_SIB>( *this, b, T, p, noi_, params.dtg, stage );
+                ++launches_;
+            }
+            if( hk )
+            {
+                k_chain_hook<<<grid, BLOCK_THREADS, 0, b.stream>>>( p, T.lg, b.view, b.partials, T.nblocks );
+                k_reduce_rows_max<<<noi_, BLOCK_THREADS, 0, b.stream>>>( b.partials, T.nblocks, b.scal + std::size_t( S_TQ ) * noi_ );
+                launches_ += 2;
+            }
+        }
+    }
+    SB_CUDA_CHECK( cudaGetLastError() );
+    if( hook )
+    {
+        SB_CUDA_CHECK( cudaMemcpyAsync( b.h_scal, b.scal, b.n_scal * sizeof( double ), cudaMemcpyDeviceToHost, b.stream ) );
+        SB_CUDA_CHECK( cudaStreamSynchronize( b.stream ) );
+        if( result )
+        {
+            auto get = [&]( int s, int i ) { return b.h_scal[std::size_t( s ) * noi_ + i]; };
+            result->energy.assign( noi_, 0.0 );
+            result->Rx.assign( noi_, 0.0 );
+            result->max_torque.assign( noi_, 0.0 );
+            result->dE_dRx.assign( noi_, 0.0 );
+            for( int i = 0; i < noi_; ++i )
+            {
+                result->energy[i]     = get( S_E, i );
+                result->Rx[i]         = get( S_RX, i );
+                result->max_torque[i] = std::sqrt( get( S_TQ, i ) );
+                const double tt       = get( S_TT, i );
+                result->dE_dRx[i]     = tt > 0 ? get( S_FT, i ) / std::sqrt( tt ) : 0.0;
+            }
+            result->degenerate = b.h_scal[std::size_t( S_N_SLOTS ) * noi_ + G_DEGENERATE] != 0.0;
+        }
+    }
+}
+
+} // namespace dev
+} // namespace sb

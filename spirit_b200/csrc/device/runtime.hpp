@@ -123,5 +123,61 @@ private:
     std::vector<void *> * stage_events_ = nullptr; // when set, llg_iterate records an event after every stage kernel
 };
 
+// GNEB parameters the device needs per force evaluation (Method_GNEB.cpp:87-258)
+struct GNEBParams
+{
+    double spring_constant = 1;
+    double dt              = 1e-3; // llg_dt of the images (VP uses it raw, Solver_VP.hpp:95-110)
+    double dtg             = 0;    // dt * gamma / mu_B: Fv = dtg s x F (Method_GNEB.cpp:359-391)
+    std::vector<int> image_type;   // 0 normal, 1 climbing, 2 falling, 3 stationary
+};
+
+struct ChainHookResult
+{
+    bool degenerate = false; // two neighbouring images coincide (Method_GNEB.cpp:119-126)
+    std::vector<double> energy, Rx, max_torque, dE_dRx;
+};
+
+// HBM-resident state of a whole chain of images (GNEB): every field is one contiguous allocation [noi][field] and the
+// kernels are batched over images (blockIdx.y = image). All images share one Hamiltonian.
+struct DeviceChainBuffers;
+class DeviceChain
+{
+public:
+    DeviceChain( const Geometry & geometry, int noi );
+    ~DeviceChain();
+    DeviceChain( const DeviceChain & )             = delete;
+    DeviceChain & operator=( const DeviceChain & ) = delete;
+
+    int noi() const
+    {
+        return noi_;
+    }
+    void set_hamiltonian( const Hamiltonian & ham );
+    void upload_image( int img, const double * host_aos );
+    void download_image( int img, double * host_aos );
+    // effective field (-gradient, unprojected) of image img from the last force evaluation
+    void download_effective_field( int img, double * host_aos );
+
+    // n iterations of solver VP / SIB / Depondt / Heun over all images; with `hook` the last iteration also produces
+    // the quantities of Method_GNEB::Hook_Post_Iteration (Method_GNEB.cpp:410-456)
+    void iterate( int solver, const GNEBParams & params, int n_iterations, bool hook, ChainHookResult * result );
+    void vp_reset();
+    void synchronize();
+    std::uint64_t kernel_launches() const
+    {
+        return launches_;
+    }
+
+private:
+    void evaluate_force( const GNEBParams & params, int which_configuration, int which_force );
+
+    int noi_ = 0, nos_ = 0;
+    std::unique_ptr<DeviceImage> table_; // owns the stencil tables (shared Hamiltonian)
+    std::unique_ptr<DeviceChainBuffers> buf_;
+    std::uint64_t launches_  = 0;
+    bool vp_prev_projected_ = false;
+};
+
 } // namespace dev
 } // namespace sb
