@@ -1,0 +1,655 @@
+// Dipole-dipole interaction as a zero-padded FFT convolution, with hand-written batched FFT passes.
+// Reference: Hamiltonian_Heisenberg::Prepare_DDI / FFT_Dipole_Matrices / FFT_Spins / Gradient_DDI_FFT
+// (core/src/engine/Hamiltonian_Heisenberg.cpp:1373-1601, 920-1014), FFT::FFT_Plan (core/include/engine/FFT.hpp:171-265).
+//
+//   g_i -= mu_i * sum_j D(r_i - r_j) mu_j s_j,   D_ab(r) = C (3 r_a r_b / r^5 - delta_ab / r^3),  C = mu_0 mu_B^2 / (4 pi 1e-30)
+// summed over `ddi_n_periodic_images` along periodic directions, evaluated as a circular convolution on the padded
+// lattice P_d = 2 N_d (open or zero-padded periodic directions with N_d > 1), else N_d.
+//
+// The reference scatters mu s into a padded real buffer, runs a library 3-D R2C (FFTW / kissFFT / cuFFT), multiplies,
+// runs a library C2R and un-pads in a serial loop: ~3 kB of memory traffic per spin. Here the 3-D transform is split
+// into its three 1-D passes and each pass only touches data that is not known to be zero (pruning):
+//   1 k_ddi_fwd_a      reads the spin field directly (x mu_s), length-Pa transforms of the Nb*Nc non-zero rows,
+//                      writes the half spectrum  A[q][c<Nc][b<Nb][ka<=Pa/2]
+//   2 k_fft_pass (b)   A -> B[q][c<Nc][kb<Pb][ka]                 (inputs b >= Nb are zero and never read)
+//   3 k_ddi_c_mult     per (kb, ka): forward c-transform of the 3 NB components (inputs c >= Nc zero), multiply with
+//                      the precomputed tensor spectrum D^(kc, kb, ka) (3x3 symmetric per sublattice pair), inverse
+//                      c-transform, keep c < Nc:  B -> B (in place)
+//   4 k_fft_pass (b)   inverse, keep b < Nb:  B -> A
+//   5 k_ddi_inv_a      Hermitian extension, inverse a-transform, keep a < Na, g_ddi = -mu_s * result / P written as
+//                      a field (AoSoA-32) that the stencil kernels add to the gradient
+// Every pass is a batch of shared-memory Stockham FFTs (mixed radix 4 / 2 / generic prime, fp64, twiddles from a
+// precomputed table), `ncol` adjacent transforms per CTA so that strided passes still move contiguous segments.
+// cuFFT is not used by the product; the tests compare against the reference's FFT and direct-sum paths.
+#include "device_buffers.cuh"
+
+#include "../core/constants.hpp"
+#include "../core/hamiltonian.hpp"
+
+#include <cmath>
+#include <cstring>
+#include <stdexcept>
+#include <vector>
+
+namespace sb
+{
+namespace dev
+{
+
+namespace
+{
+
+constexpr int FFT_THREADS  = 256;
+constexpr int MAX_RADICES  = 16;
+constexpr int MAX_SMEM_FFT = 200 * 1024;
+
+struct FFTPlan1D
+{
+    int n       = 1;
+    int n_radix = 0;
+    int radix[MAX_RADICES];
+    const double2 * twiddle = nullptr; // exp(-2 pi i k / n), k < n
+};
+
+__device__ __forceinline__ double2 cmul( const double2 & a, const double2 & b )
+{
+    return make_double2( a.x * b.x - a.y * b.y, a.x * b.y + a.y * b.x );
+}
+__device__ __forceinline__ double2 cadd( const double2 & a, const double2 & b )
+{
+    return make_double2( a.x + b.x, a.y + b.y );
+}
+__device__ __forceinline__ double2 csub( const double2 & a, const double2 & b )
+{
+    return make_double2( a.x - b.x, a.y - b.y );
+}
+// twiddle exp(-+2 pi i k/n): the table holds the forward sign
+template<bool INVERSE>
+__device__ __forceinline__ double2 tw( const FFTPlan1D & plan, int k )
+{
+    const double2 w = __ldg( plan.twiddle + k );
+    return INVERSE ? make_double2( w.x, -w.y ) : w;
+}
+
+// In-shared-memory Stockham autosort FFT of `ncol` independent sequences of length plan.n stored as x[j * ncol + col].
+// Returns the buffer (x or y) that holds the result. All threads of the CTA must call.
+template<bool INVERSE>
+__device__ double2 * block_fft( const FFTPlan1D & plan, double2 * x, double2 * y, int ncol )
+{
+    const int n = plan.n;
+    int s       = 1; // stride = product of the radices already processed
+    for( int stage = 0; stage < plan.n_radix; ++stage )
+    {
+        const int r = plan.radix[stage];
+        const int m = n / ( s * r ); // remaining sub-transform length / r
+        // one work item = (butterfly (p, q), column)
+        const int items = m * s * ncol;
+        for( int item = threadIdx.x; item < items; item += blockDim.x )
+        {
+            const int col = item % ncol;
+            const int t   = item / ncol;
+            const int q   = t % s;
+            const int p   = t / s;
+            // inputs a_i = x[q + s (p + m i)], outputs y[q + s (r p + i)] = (sum_k a_k w_r^{ik}) w_{n/s}^{p i}
+            const int tw_step = p * s; // w_{n/s}^{p} = W_n^{p s}
+            if( r == 2 )
+            {
+                const double2 a0 = x[( q + s * p ) * ncol + col];
+                const double2 a1 = x[( q + s * ( p + m ) ) * ncol + col];
+                y[( q + s * ( 2 * p ) ) * ncol + col]     = cadd( a0, a1 );
+                y[( q + s * ( 2 * p + 1 ) ) * ncol + col] = cmul( csub( a0, a1 ), tw<INVERSE>( plan, tw_step ) );
+            }
+            else if( r == 4 )
+            {
+                const double2 a0 = x[( q + s * p ) * ncol + col];
+                const double2 a1 = x[( q + s * ( p + m ) ) * ncol + col];
+                const double2 a2 = x[( q + s * ( p + 2 * m ) ) * ncol + col];
+                const double2 a3 = x[( q + s * ( p + 3 * m ) ) * ncol + col];
+                const double2 b0 = cadd( a0, a2 ), b1 = csub( a0, a2 ), b2 = cadd( a1, a3 ), b3 = csub( a1, a3 );
+                // -i b3 (forward) or +i b3 (inverse)
+                const double2 jb3 = INVERSE ? make_double2( -b3.y, b3.x ) : make_double2( b3.y, -b3.x );
+                y[( q + s * ( 4 * p ) ) * ncol + col]     = cadd( b0, b2 );
+                y[( q + s * ( 4 * p + 1 ) ) * ncol + col] = cmul( cadd( b1, jb3 ), tw<INVERSE>( plan, tw_step ) );
+                y[( q + s * ( 4 * p + 2 ) ) * ncol + col] = cmul( csub( b0, b2 ), tw<INVERSE>( plan, ( 2 * tw_step ) % n ) );
+                y[( q + s * ( 4 * p + 3 ) ) * ncol + col] = cmul( csub( b1, jb3 ), tw<INVERSE>( plan, ( 3 * tw_step ) % n ) );
+            }
+            else
+            {
+                // generic prime radix: O(r^2) butterfly, w_r^{ik} = W_n^{(i k mod r) n / r}
+                const int nr = n / r;
+                for( int i = 0; i < r; ++i )
+                {
+                    double2 acc = make_double2( 0.0, 0.0 );
+                    for( int k = 0; k < r; ++k )
+                    {
+                        const double2 a = x[( q + s * ( p + m * k ) ) * ncol + col];
+                        acc             = cadd( acc, cmul( a, tw<INVERSE>( plan, ( ( i * k ) % r ) * nr ) ) );
+                    }
+                    y[( q + s * ( r * p + i ) ) * ncol + col] = cmul( acc, tw<INVERSE>( plan, int( ( std::int64_t( i ) * tw_step ) % n ) ) );
+                }
+            }
+        }
+        __syncthreads();
+        double2 * t = x;
+        x           = y;
+        y           = t;
+        s *= r;
+    }
+    return x;
+}
+
+// ---------------------------------------------------------------------------------------------
+// Generic strided pass: transforms along j of  in[o * in_os + j * in_js + u]  for u < n_u (contiguous), o < n_o.
+// Inputs j >= n_in are zero (not read), outputs j >= n_out are dropped. A CTA handles `ncol` consecutive u of one o.
+// ---------------------------------------------------------------------------------------------
+struct PassArgs
+{
+    const double2 * in;
+    double2 * out;
+    std::size_t in_os, in_js, out_os, out_js;
+    int n_u, n_o, n_in, n_out, ncol;
+    double scale;
+};
+
+template<bool INVERSE>
+static __global__ void __launch_bounds__( FFT_THREADS ) k_fft_pass( const __grid_constant__ FFTPlan1D plan, const __grid_constant__ PassArgs a )
+{
+    extern __shared__ double2 smem[];
+    const int n    = plan.n;
+    double2 * x    = smem;
+    double2 * y    = smem + std::size_t( n ) * a.ncol;
+    const int tile = blockIdx.x, o = blockIdx.y;
+    const int u0   = tile * a.ncol;
+    const int nc   = min( a.ncol, a.n_u - u0 );
+    for( int item = threadIdx.x; item < n * a.ncol; item += blockDim.x )
+    {
+        const int col = item % a.ncol, j = item / a.ncol;
+        double2 v     = make_double2( 0.0, 0.0 );
+        if( j < a.n_in && col < nc )
+            v = a.in[std::size_t( o ) * a.in_os + std::size_t( j ) * a.in_js + u0 + col];
+        x[item] = v;
+    }
+    __syncthreads();
+    const double2 * r = block_fft<INVERSE>( plan, x, y, a.ncol );
+    for( int item = threadIdx.x; item < a.n_out * a.ncol; item += blockDim.x )
+    {
+        const int col = item % a.ncol, j = item / a.ncol;
+        if( col < nc )
+        {
+            const double2 v = r[item];
+            a.out[std::size_t( o ) * a.out_os + std::size_t( j ) * a.out_js + u0 + col] = make_double2( a.scale * v.x, a.scale * v.y );
+        }
+    }
+}
+
+// Pass a for a dense REAL input (setup of the tensor spectrum): real row of length n -> half spectrum
+static __global__ void __launch_bounds__( FFT_THREADS ) k_fft_real_rows(
+    const __grid_constant__ FFTPlan1D plan, const double * __restrict__ in, double2 * __restrict__ out, int Ha )
+{
+    extern __shared__ double2 smem[];
+    const int n       = plan.n;
+    double2 * x       = smem;
+    double2 * y       = smem + n;
+    const size_t row  = blockIdx.x;
+    for( int j = threadIdx.x; j < n; j += blockDim.x )
+        x[j] = make_double2( in[row * n + j], 0.0 );
+    __syncthreads();
+    const double2 * r = block_fft<false>( plan, x, y, 1 );
+    for( int j = threadIdx.x; j < Ha; j += blockDim.x )
+        out[row * Ha + j] = r[j];
+}
+
+// ---------------------------------------------------------------------------------------------
+// DDI plan (device side)
+// ---------------------------------------------------------------------------------------------
+struct DDIDims
+{
+    int Na, Nb, Nc, NB;
+    int Pa, Pb, Pc, Ha; // padded sizes, Ha = Pa/2 + 1
+    int n_inter;
+    int lookup[MAX_BASIS * MAX_BASIS]; // inter-sublattice index of (b1, b2)  (Hamiltonian_Heisenberg.cpp:1418-1428)
+    int plane_stride, halo;
+    double mu_s[MAX_BASIS];
+};
+
+// 1: forward a-pass straight from the spin field. One CTA per (row = b + Nb c, component q = comp + 3 ib).
+static __global__ void __launch_bounds__( FFT_THREADS ) k_ddi_fwd_a(
+    const __grid_constant__ FFTPlan1D plan, const __grid_constant__ DDIDims d, ConstField3 spins, double2 * __restrict__ A )
+{
+    extern __shared__ double2 smem[];
+    const int n   = plan.n;
+    double2 * x   = smem;
+    double2 * y   = smem + n;
+    const int row = blockIdx.x; // b + Nb * c
+    const int ib  = blockIdx.y;
+    const int b = row % d.Nb, c = row / d.Nb;
+    // the three components of basis atom ib: three transforms per CTA, one after the other (same row of the field)
+    for( int comp = 0; comp < 3; ++comp )
+    {
+        for( int j = threadIdx.x; j < n; j += blockDim.x )
+        {
+            double v = 0.0;
+            if( j < d.Na )
+            {
+                const std::size_t idx = std::size_t( ib + d.NB * j ) + std::size_t( d.Na ) * d.NB * b + std::size_t( d.plane_stride ) * ( c + d.halo );
+                v                     = __ldg( spins.base + elem_offset( idx ) + comp * FIELD_BLOCK ) * d.mu_s[ib];
+            }
+            x[j] = make_double2( v, 0.0 );
+        }
+        __syncthreads();
+        const double2 * r = block_fft<false>( plan, x, y, 1 );
+        const int q       = comp + 3 * ib;
+        double2 * out     = A + ( ( std::size_t( q ) * d.Nc + c ) * d.Nb + b ) * d.Ha;
+        for( int j = threadIdx.x; j < d.Ha; j += blockDim.x )
+            out[j] = r[j];
+        __syncthreads();
+    }
+}
+
+// 3: per (kb, ka-tile): forward c-transforms of all 3 NB components, tensor multiply, inverse c-transforms.
+// B layout [q][c][kb][ka]; D^ layout [t][kc][kb][ka], t = comp6 + 6 * inter.
+static __global__ void __launch_bounds__( FFT_THREADS ) k_ddi_c_mult(
+    const __grid_constant__ FFTPlan1D plan, const __grid_constant__ DDIDims d, double2 * __restrict__ B,
+    const double2 * __restrict__ Dhat, int ncol )
+{
+    extern __shared__ double2 smem[];
+    const int n  = plan.n; // Pc
+    const int nq = 3 * d.NB;
+    // per component: two buffers of n * ncol
+    const std::size_t buf = std::size_t( n ) * ncol;
+    const int kb = blockIdx.y, u0 = blockIdx.x * ncol;
+    const int nc = min( ncol, d.Ha - u0 );
+    const std::size_t c_stride = std::size_t( d.Pb ) * d.Ha;
+    // load + forward transform every component
+    __shared__ int result_in_y; // all transforms have the same number of stages: same final buffer
+    for( int q = 0; q < nq; ++q )
+    {
+        double2 * x = smem + ( 2 * q ) * buf;
+        for( int item = threadIdx.x; item < n * ncol; item += blockDim.x )
+        {
+            const int col = item % ncol, j = item / ncol;
+            double2 v     = make_double2( 0.0, 0.0 );
+            if( j < d.Nc && col < nc )
+                v = B[( std::size_t( q ) * d.Nc + j ) * c_stride + std::size_t( kb ) * d.Ha + u0 + col];
+            x[item] = v;
+        }
+    }
+    __syncthreads();
+    for( int q = 0; q < nq; ++q )
+    {
+        double2 * x       = smem + ( 2 * q ) * buf;
+        double2 * y       = x + buf;
+        const double2 * r = block_fft<false>( plan, x, y, ncol );
+        if( threadIdx.x == 0 && q == 0 )
+            result_in_y = ( r == y ) ? 1 : 0;
+    }
+    __syncthreads();
+    const int in_y = result_in_y;
+    // multiply: F_{b1} = sum_{b2} D^(b1,b2) S_{b2}; results go to the OTHER buffer of each component
+    for( int item = threadIdx.x; item < n * ncol; item += blockDim.x )
+    {
+        const int col = item % ncol, kc = item / ncol;
+        if( col >= nc )
+            continue;
+        const std::size_t dk = ( std::size_t( kc ) * d.Pb + kb ) * d.Ha + u0 + col;
+        const std::size_t dcomp = std::size_t( d.Pc ) * d.Pb * d.Ha;
+        for( int b1 = 0; b1 < d.NB; ++b1 )
+        {
+            double2 fx = make_double2( 0, 0 ), fy = fx, fz = fx;
+            for( int b2 = 0; b2 < d.NB; ++b2 )
+            {
+                const int inter    = d.lookup[b1 + b2 * d.NB];
+                const double2 * Dp = Dhat + std::size_t( 6 * inter ) * dcomp + dk;
+                const double2 Dxx = __ldg( Dp ), Dxy = __ldg( Dp + dcomp ), Dxz = __ldg( Dp + 2 * dcomp );
+                const double2 Dyy = __ldg( Dp + 3 * dcomp ), Dyz = __ldg( Dp + 4 * dcomp ), Dzz = __ldg( Dp + 5 * dcomp );
+                const double2 sx = smem[( 2 * ( 0 + 3 * b2 ) + in_y ) * buf + item];
+                const double2 sy = smem[( 2 * ( 1 + 3 * b2 ) + in_y ) * buf + item];
+                const double2 sz = smem[( 2 * ( 2 + 3 * b2 ) + in_y ) * buf + item];
+                fx = cadd( fx, cadd( cmul( Dxx, sx ), cadd( cmul( Dxy, sy ), cmul( Dxz, sz ) ) ) );
+                fy = cadd( fy, cadd( cmul( Dxy, sx ), cadd( cmul( Dyy, sy ), cmul( Dyz, sz ) ) ) );
+                fz = cadd( fz, cadd( cmul( Dxz, sx ), cadd( cmul( Dyz, sy ), cmul( Dzz, sz ) ) ) );
+            }
+            smem[( 2 * ( 0 + 3 * b1 ) + 1 - in_y ) * buf + item] = fx;
+            smem[( 2 * ( 1 + 3 * b1 ) + 1 - in_y ) * buf + item] = fy;
+            smem[( 2 * ( 2 + 3 * b1 ) + 1 - in_y ) * buf + item] = fz;
+        }
+    }
+    __syncthreads();
+    // inverse transforms and store c < Nc
+    for( int q = 0; q < nq; ++q )
+    {
+        double2 * x       = smem + ( 2 * q + 1 - in_y ) * buf;
+        double2 * y       = smem + ( 2 * q + in_y ) * buf;
+        const double2 * r = block_fft<true>( plan, x, y, ncol );
+        for( int item = threadIdx.x; item < d.Nc * ncol; item += blockDim.x )
+        {
+            const int col = item % ncol, j = item / ncol;
+            if( col < nc )
+                B[( std::size_t( q ) * d.Nc + j ) * c_stride + std::size_t( kb ) * d.Ha + u0 + col] = r[item];
+        }
+        __syncthreads();
+    }
+}
+
+// 5: inverse a-pass (C2R through a complex transform of the Hermitian-extended row) fused with
+//    g_ddi = -mu_s res / P  (Hamiltonian_Heisenberg.cpp:995-1013), written as a field
+static __global__ void __launch_bounds__( FFT_THREADS ) k_ddi_inv_a(
+    const __grid_constant__ FFTPlan1D plan, const __grid_constant__ DDIDims d, const double2 * __restrict__ A, Field3 g, double inv_P )
+{
+    extern __shared__ double2 smem[];
+    const int n   = plan.n;
+    double2 * x   = smem;
+    double2 * y   = smem + n;
+    const int row = blockIdx.x;
+    const int ib  = blockIdx.y;
+    const int b = row % d.Nb, c = row / d.Nb;
+    for( int comp = 0; comp < 3; ++comp )
+    {
+        const int q        = comp + 3 * ib;
+        const double2 * in = A + ( ( std::size_t( q ) * d.Nc + c ) * d.Nb + b ) * d.Ha;
+        for( int j = threadIdx.x; j < n; j += blockDim.x )
+        {
+            double2 v;
+            if( j < d.Ha )
+                v = in[j];
+            else
+            {
+                v   = in[n - j];
+                v.y = -v.y;
+            }
+            x[j] = v;
+        }
+        __syncthreads();
+        const double2 * r = block_fft<true>( plan, x, y, 1 );
+        const double f    = -d.mu_s[ib] * inv_P;
+        for( int j = threadIdx.x; j < d.Na; j += blockDim.x )
+        {
+            const std::size_t idx = std::size_t( ib + d.NB * j ) + std::size_t( d.Na ) * d.NB * b + std::size_t( d.plane_stride ) * ( c + d.halo );
+            g.base[elem_offset( idx ) + comp * FIELD_BLOCK] = f * r[j].x;
+        }
+        __syncthreads();
+    }
+}
+
+// Dipole tensor component `comp6` of sublattice pair (b1, b2) on the padded lattice, with periodic images
+// (FFT_Dipole_Matrices, Hamiltonian_Heisenberg.cpp:1406-1499)
+struct TensorGeom
+{
+    double ta[3], tb[3], tc[3]; // lattice_constant * bravais vectors
+    double da, db, dc;          // cell_atoms[b1] - cell_atoms[b2] in lattice coordinates
+    int img[3];
+    double mult;
+};
+static __global__ void k_ddi_tensor( const __grid_constant__ DDIDims d, const __grid_constant__ TensorGeom t, int comp6, double * __restrict__ out )
+{
+    const std::size_t i = blockIdx.x * std::size_t( blockDim.x ) + threadIdx.x;
+    const std::size_t P = std::size_t( d.Pa ) * d.Pb * d.Pc;
+    if( i >= P )
+        return;
+    const int a = int( i % d.Pa ), b = int( ( i / d.Pa ) % d.Pb ), c = int( i / ( std::size_t( d.Pa ) * d.Pb ) );
+    const int ai = a < d.Na ? a : a - d.Pa, bi = b < d.Nb ? b : b - d.Pb, ci = c < d.Nc ? c : c - d.Pc;
+    double D = 0.0;
+    for( int pa = -t.img[0]; pa <= t.img[0]; ++pa )
+        for( int pb = -t.img[1]; pb <= t.img[1]; ++pb )
+            for( int pc = -t.img[2]; pc <= t.img[2]; ++pc )
+            {
+                const double fa = ai + pa * d.Na + t.da, fb = bi + pb * d.Nb + t.db, fc = ci + pc * d.Nc + t.dc;
+                const double rx = fa * t.ta[0] + fb * t.tb[0] + fc * t.tc[0];
+                const double ry = fa * t.ta[1] + fb * t.tb[1] + fc * t.tc[1];
+                const double rz = fa * t.ta[2] + fb * t.tb[2] + fc * t.tc[2];
+                const double r  = sqrt( rx * rx + ry * ry + rz * rz );
+                if( r > 1e-10 )
+                {
+                    const double r3 = r * r * r, r5 = r * r * r * r * r;
+                    double v;
+                    switch( comp6 )
+                    {
+                        case 0: v = 3 * rx * rx / r5 - 1 / r3; break;
+                        case 1: v = 3 * rx * ry / r5; break;
+                        case 2: v = 3 * rx * rz / r5; break;
+                        case 3: v = 3 * ry * ry / r5 - 1 / r3; break;
+                        case 4: v = 3 * ry * rz / r5; break;
+                        default: v = 3 * rz * rz / r5 - 1 / r3; break;
+                    }
+                    D += t.mult * v;
+                }
+            }
+    out[i] = D;
+}
+
+std::vector<int> factorize( int n )
+{
+    std::vector<int> r;
+    while( n % 4 == 0 )
+    {
+        r.push_back( 4 );
+        n /= 4;
+    }
+    for( int p = 2; p * p <= n; ++p )
+        while( n % p == 0 )
+        {
+            r.push_back( p );
+            n /= p;
+        }
+    if( n > 1 )
+        r.push_back( n );
+    return r;
+}
+
+} // namespace
+
+// ---------------------------------------------------------------------------------------------
+struct DDIPlan
+{
+    DDIDims dims{};
+    FFTPlan1D plan[3]; // a, b, c
+    double2 * twiddle[3] = { nullptr, nullptr, nullptr };
+    double2 * Dhat       = nullptr;
+    double2 * A          = nullptr;
+    double2 * B          = nullptr;
+    int ncol_b = 1, ncol_c = 1;
+    std::size_t smem_a = 0, smem_b = 0, smem_c = 0;
+    std::uint64_t launches_setup = 0;
+
+    ~DDIPlan()
+    {
+        for( auto * t : twiddle )
+            if( t )
+                cudaFree( t );
+        if( Dhat )
+            cudaFree( Dhat );
+        if( A )
+            cudaFree( A );
+        if( B )
+            cudaFree( B );
+    }
+};
+
+namespace
+{
+void make_plan_1d( FFTPlan1D & plan, double2 *& table, int n )
+{
+    plan.n         = n;
+    const auto fac = factorize( n );
+    if( fac.size() > std::size_t( MAX_RADICES ) )
+        throw std::runtime_error( "spirit_b200: FFT length with too many factors" );
+    plan.n_radix = int( fac.size() );
+    for( int i = 0; i < plan.n_radix; ++i )
+        plan.radix[i] = fac[i];
+    std::vector<double2> w( n );
+    for( int k = 0; k < n; ++k )
+    {
+        const long double ang = -2.0L * 3.14159265358979323846264338327950288L * k / n;
+        w[k]                  = make_double2( double( cosl( ang ) ), double( sinl( ang ) ) );
+    }
+    SB_CUDA_CHECK( cudaMalloc( &table, std::size_t( n ) * sizeof( double2 ) ) );
+    SB_CUDA_CHECK( cudaMemcpy( table, w.data(), std::size_t( n ) * sizeof( double2 ), cudaMemcpyHostToDevice ) );
+    plan.twiddle = table;
+}
+
+int choose_ncol( int n, int n_components, int n_u )
+{
+    const std::size_t per_col = std::size_t( n ) * 2 * sizeof( double2 ) * n_components;
+    int ncol                  = int( std::min<std::size_t>( 16, std::max<std::size_t>( 1, MAX_SMEM_FFT / per_col ) ) );
+    ncol                      = std::min( ncol, std::max( 1, n_u ) );
+    if( per_col > std::size_t( MAX_SMEM_FFT ) )
+        throw std::runtime_error( "spirit_b200: padded lattice dimension too long for the shared-memory FFT passes" );
+    return ncol;
+}
+
+template<typename K>
+void allow_smem( K kernel, std::size_t bytes )
+{
+    SB_CUDA_CHECK( cudaFuncSetAttribute( kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int( bytes ) ) );
+}
+} // namespace
+
+void ddi_plan_destroy( DDIPlan * p )
+{
+    delete p;
+}
+
+// Prepare_DDI (Hamiltonian_Heisenberg.cpp:1501-1595): padded sizes, plans, tensor spectrum
+DDIPlan * ddi_plan_create( const Hamiltonian & ham, const StencilParams & sp, cudaStream_t stream )
+{
+    const Geometry & g = *ham.geometry;
+    auto plan          = std::unique_ptr<DDIPlan>( new DDIPlan );
+    DDIDims & d        = plan->dims;
+    d.Na = g.n_cells[0], d.Nb = g.n_cells[1], d.Nc = g.n_cells[2], d.NB = g.n_cell_atoms;
+    int P[3];
+    for( int i = 0; i < 3; ++i )
+    {
+        P[i] = g.n_cells[i];
+        if( g.n_cells[i] > 1 && ( ham.boundary_conditions[i] == 0 || ham.ddi_pb_zero_padding ) )
+            P[i] *= 2;
+    }
+    d.Pa = P[0], d.Pb = P[1], d.Pc = P[2];
+    d.Ha           = d.Pa / 2 + 1;
+    d.plane_stride = sp.plane_stride;
+    d.halo         = sp.halo;
+    for( int ib = 0; ib < d.NB; ++ib )
+        d.mu_s[ib] = g.cell_mu_s[ib];
+    // inter-sublattice lookup (same enumeration as the reference)
+    d.n_inter = 0;
+    for( int b1 = 0; b1 < d.NB; ++b1 )
+        for( int b2 = 0; b2 < d.NB; ++b2 )
+        {
+            if( b1 == b2 && b1 != 0 )
+            {
+                d.lookup[b1 + b2 * d.NB] = 0;
+                continue;
+            }
+            d.lookup[b1 + b2 * d.NB] = d.n_inter++;
+        }
+
+    make_plan_1d( plan->plan[0], plan->twiddle[0], d.Pa );
+    make_plan_1d( plan->plan[1], plan->twiddle[1], d.Pb );
+    make_plan_1d( plan->plan[2], plan->twiddle[2], d.Pc );
+    plan->ncol_b = choose_ncol( d.Pb, 1, d.Ha );
+    plan->ncol_c = choose_ncol( d.Pc, 3 * d.NB, d.Ha );
+    plan->smem_a = std::size_t( d.Pa ) * 2 * sizeof( double2 );
+    plan->smem_b = std::size_t( d.Pb ) * 2 * sizeof( double2 ) * plan->ncol_b;
+    plan->smem_c = std::size_t( d.Pc ) * 2 * sizeof( double2 ) * plan->ncol_c * 3 * d.NB;
+    if( plan->smem_a > std::size_t( MAX_SMEM_FFT ) )
+        throw std::runtime_error( "spirit_b200: padded lattice dimension a too long for the shared-memory FFT passes" );
+    allow_smem( k_ddi_fwd_a, plan->smem_a );
+    allow_smem( k_ddi_inv_a, plan->smem_a );
+    allow_smem( k_fft_real_rows, plan->smem_a );
+    allow_smem( k_fft_pass<false>, std::max( plan->smem_b, std::size_t( d.Pc ) * 2 * sizeof( double2 ) * plan->ncol_b ) );
+    allow_smem( k_fft_pass<true>, plan->smem_b );
+    allow_smem( k_ddi_c_mult, plan->smem_c );
+
+    const std::size_t half = std::size_t( d.Pc ) * d.Pb * d.Ha;
+    const std::size_t full = std::size_t( d.Pc ) * d.Pb * d.Pa;
+    SB_CUDA_CHECK( cudaMalloc( &plan->Dhat, std::size_t( 6 * d.n_inter ) * half * sizeof( double2 ) ) );
+    SB_CUDA_CHECK( cudaMalloc( &plan->A, std::size_t( 3 * d.NB ) * d.Nc * d.Nb * d.Ha * sizeof( double2 ) ) );
+    SB_CUDA_CHECK( cudaMalloc( &plan->B, std::size_t( 3 * d.NB ) * d.Nc * d.Pb * d.Ha * sizeof( double2 ) ) );
+
+    // tensor spectrum, one component at a time: real D -> rows (a) -> b -> c
+    double * Dreal  = nullptr;
+    double2 * tmp1  = nullptr;
+    SB_CUDA_CHECK( cudaMalloc( &Dreal, full * sizeof( double ) ) );
+    SB_CUDA_CHECK( cudaMalloc( &tmp1, half * sizeof( double2 ) ) );
+    TensorGeom tg{};
+    for( int k = 0; k < 3; ++k )
+    {
+        tg.ta[k] = g.lattice_constant * g.bravais_vectors[0][k];
+        tg.tb[k] = g.lattice_constant * g.bravais_vectors[1][k];
+        tg.tc[k] = g.lattice_constant * g.bravais_vectors[2][k];
+        tg.img[k] = ham.boundary_conditions[k] == 0 ? 0 : ham.ddi_n_periodic_images[k];
+    }
+    tg.mult = constants::mu_0 * constants::mu_B * constants::mu_B / ( 4 * constants::Pi * 1e-30 );
+    const int ncol_setup = plan->ncol_b;
+    for( int b1 = 0; b1 < d.NB; ++b1 )
+        for( int b2 = 0; b2 < d.NB; ++b2 )
+        {
+            if( b1 == b2 && b1 != 0 )
+                continue;
+            const int inter = d.lookup[b1 + b2 * d.NB];
+            tg.da           = g.cell_atoms[b1][0] - g.cell_atoms[b2][0];
+            tg.db           = g.cell_atoms[b1][1] - g.cell_atoms[b2][1];
+            tg.dc           = g.cell_atoms[b1][2] - g.cell_atoms[b2][2];
+            for( int comp6 = 0; comp6 < 6; ++comp6 )
+            {
+                double2 * Dout = plan->Dhat + std::size_t( 6 * inter + comp6 ) * half;
+                k_ddi_tensor<<<unsigned( ( full + 255 ) / 256 ), 256, 0, stream>>>( d, tg, comp6, Dreal );
+                k_fft_real_rows<<<unsigned( std::size_t( d.Pb ) * d.Pc ), FFT_THREADS, plan->smem_a, stream>>>( plan->plan[0], Dreal, tmp1, d.Ha );
+                // b: tmp1[c][b][ka] -> Dout[c][kb][ka]
+                PassArgs pb{};
+                pb.in = tmp1, pb.out = Dout;
+                pb.in_os = pb.out_os = std::size_t( d.Pb ) * d.Ha;
+                pb.in_js = pb.out_js = d.Ha;
+                pb.n_u = d.Ha, pb.n_o = d.Pc, pb.n_in = d.Pb, pb.n_out = d.Pb, pb.ncol = ncol_setup, pb.scale = 1.0;
+                k_fft_pass<false><<<dim3( ( d.Ha + ncol_setup - 1 ) / ncol_setup, d.Pc ), FFT_THREADS, plan->smem_b, stream>>>( plan->plan[1], pb );
+                // c: Dout[c][kb][ka] -> tmp1[kc][kb][ka]; (kb, ka) is one contiguous index of length Pb*Ha
+                PassArgs pc{};
+                pc.in = Dout, pc.out = tmp1;
+                pc.in_os = pc.out_os = 0;
+                pc.in_js = pc.out_js = std::size_t( d.Pb ) * d.Ha;
+                pc.n_u = d.Pb * d.Ha, pc.n_o = 1, pc.n_in = d.Pc, pc.n_out = d.Pc, pc.scale = 1.0;
+                pc.ncol = choose_ncol( d.Pc, 1, pc.n_u );
+                const std::size_t smem_c1 = std::size_t( d.Pc ) * 2 * sizeof( double2 ) * pc.ncol;
+                allow_smem( k_fft_pass<false>, std::max( plan->smem_b, smem_c1 ) );
+                k_fft_pass<false><<<dim3( ( pc.n_u + pc.ncol - 1 ) / pc.ncol, 1 ), FFT_THREADS, smem_c1, stream>>>( plan->plan[2], pc );
+                SB_CUDA_CHECK( cudaMemcpyAsync( Dout, tmp1, half * sizeof( double2 ), cudaMemcpyDeviceToDevice, stream ) );
+                plan->launches_setup += 4;
+            }
+        }
+    SB_CUDA_CHECK( cudaGetLastError() );
+    SB_CUDA_CHECK( cudaStreamSynchronize( stream ) );
+    cudaFree( Dreal );
+    cudaFree( tmp1 );
+    return plan.release();
+}
+
+// One DDI gradient evaluation: spins -> g_ddi field. Returns the number of kernels launched.
+int ddi_gradient( DDIPlan & plan, ConstField3 spins, Field3 g_ddi, cudaStream_t stream )
+{
+    const DDIDims & d = plan.dims;
+    const int rows    = d.Nb * d.Nc;
+    k_ddi_fwd_a<<<dim3( rows, d.NB ), FFT_THREADS, plan.smem_a, stream>>>( plan.plan[0], d, spins, plan.A );
+    // forward b: A[q][c][b][ka] -> B[q][c][kb][ka]; outer index o = q * Nc + c
+    PassArgs pb{};
+    pb.in = plan.A, pb.out = plan.B;
+    pb.in_os = std::size_t( d.Nb ) * d.Ha, pb.out_os = std::size_t( d.Pb ) * d.Ha;
+    pb.in_js = pb.out_js = d.Ha;
+    pb.n_u = d.Ha, pb.n_o = 3 * d.NB * d.Nc, pb.n_in = d.Nb, pb.n_out = d.Pb, pb.ncol = plan.ncol_b, pb.scale = 1.0;
+    const dim3 grid_b( ( d.Ha + plan.ncol_b - 1 ) / plan.ncol_b, pb.n_o );
+    k_fft_pass<false><<<grid_b, FFT_THREADS, plan.smem_b, stream>>>( plan.plan[1], pb );
+    k_ddi_c_mult<<<dim3( ( d.Ha + plan.ncol_c - 1 ) / plan.ncol_c, d.Pb ), FFT_THREADS, plan.smem_c, stream>>>(
+        plan.plan[2], d, plan.B, plan.Dhat, plan.ncol_c );
+    // inverse b: B -> A, keep b < Nb
+    PassArgs ib{};
+    ib.in = plan.B, ib.out = plan.A;
+    ib.in_os = std::size_t( d.Pb ) * d.Ha, ib.out_os = std::size_t( d.Nb ) * d.Ha;
+    ib.in_js = ib.out_js = d.Ha;
+    ib.n_u = d.Ha, ib.n_o = 3 * d.NB * d.Nc, ib.n_in = d.Pb, ib.n_out = d.Nb, ib.ncol = plan.ncol_b, ib.scale = 1.0;
+    k_fft_pass<true><<<grid_b, FFT_THREADS, plan.smem_b, stream>>>( plan.plan[1], ib );
+    const double inv_P = 1.0 / ( double( d.Pa ) * d.Pb * d.Pc );
+    k_ddi_inv_a<<<dim3( rows, d.NB ), FFT_THREADS, plan.smem_a, stream>>>( plan.plan[0], d, plan.A, g_ddi, inv_P );
+    SB_CUDA_CHECK( cudaGetLastError() );
+    return 5;
+}
+
+} // namespace dev
+} // namespace sb

@@ -60,6 +60,12 @@ struct DeviceField
     }
 };
 
+// device/ddi_fft.cu
+struct DDIPlan;
+DDIPlan * ddi_plan_create( const Hamiltonian & ham, const StencilParams & sp, cudaStream_t stream );
+void ddi_plan_destroy( DDIPlan * plan );
+int ddi_gradient( DDIPlan & plan, ConstField3 spins, Field3 g_ddi, cudaStream_t stream );
+
 struct DeviceBuffers
 {
     SC6Launch sc6;

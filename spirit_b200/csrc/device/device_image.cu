@@ -98,10 +98,6 @@ void host_free( void * ptr, bool pinned )
 
 // ---------------------------------------------------------------------------------------------
 
-struct DDIPlan
-{
-};
-
 namespace
 {
 int next_pow2( int v )
@@ -212,7 +208,11 @@ DeviceImage::DeviceImage( const Geometry & g )
     SB_CUDA_CHECK( cudaHostAlloc( &b.h_scalars, 16 * sizeof( double ), cudaHostAllocDefault ) );
 }
 
-DeviceImage::~DeviceImage() = default;
+DeviceImage::~DeviceImage()
+{
+    if( ddi_ )
+        ddi_plan_destroy( ddi_ );
+}
 
 void DeviceImage::synchronize()
 {
@@ -401,10 +401,25 @@ void DeviceImage::set_hamiltonian( const Hamiltonian & ham )
     }
 
     p.has_ddi = 0;
+    if( ddi_ )
+    {
+        ddi_plan_destroy( ddi_ );
+        ddi_ = nullptr;
+    }
     if( ham.ddi_method == DDI_Method::FFT )
-        throw std::runtime_error( "spirit_b200: ddi_method fft is not implemented yet" );
+    {
+        if( p.halo != 0 )
+            throw std::runtime_error( "spirit_b200: the FFT dipole convolution is not slab-decomposed yet" );
+        ddi_      = ddi_plan_create( ham, p, buf_->stream );
+        p.has_ddi = 1;
+        if( !buf_->ddi_s.allocated() )
+        {
+            buf_->ddi_s.allocate( buf_->n_storage );
+            buf_->ddi_p.allocate( buf_->n_storage );
+        }
+    }
     else if( ham.ddi_method != DDI_Method::None )
-        throw std::runtime_error( "spirit_b200: only ddi_method none/fft are in scope (SURVEY.md 2.2)" );
+        throw std::runtime_error( "spirit_b200: only ddi_method none/fft are in scope (SURVEY.md 2.2): the reference's cutoff / direct sums are oracle-side ground truth" );
 
     p.sc6_extras  = ( p.has_cubic || p.has_ddi ) ? 1 : 0;
     ham_revision_ = ham.revision;
@@ -476,6 +491,7 @@ static void reduce_sum_to( DeviceBuffers & b, const double * partials, int slot,
 void DeviceImage::gradient_and_energy( double * gradient_host_aos, double * energy )
 {
     auto & b = *buf_;
+    compute_ddi_gradient( 0 );
     if( !b.scratch.allocated() )
         b.scratch.allocate( b.n_storage );
     SB_DISPATCH_NB(
@@ -498,6 +514,7 @@ void DeviceImage::update_effective_field()
     if( !b.F.allocated() )
         b.F.allocate( b.n_storage );
     effective_field_in_Fv_ = false;
+    compute_ddi_gradient( 0 );
     SB_DISPATCH_NB(
         ( k_gradient<1, false><<<b.nblocks, BLOCK_THREADS, 0, b.stream>>>(
             stencil_, b.lg, b.spins.c(), b.ddi_s.c(), b.F.f(), -1.0, nullptr ) ),
@@ -514,6 +531,7 @@ int DeviceImage::energy_contributions( const Hamiltonian & ham, double * totals,
         return 0;
     if( !b.terms )
         SB_CUDA_CHECK( cudaMalloc( &b.terms, 6 * std::size_t( nos_ ) * sizeof( double ) ) );
+    compute_ddi_gradient( 0 );
     EnergyTermPointers ptrs{};
     const int idx[6] = { ham.idx_zeeman, ham.idx_anisotropy, ham.idx_cubic_anisotropy, ham.idx_exchange, ham.idx_dmi, ham.idx_ddi };
     for( int t = 0; t < 6; ++t )
@@ -630,6 +648,7 @@ void DeviceImage::llg_initial_hook( int solver, const LLGParams & llg, HookResul
 {
     auto & b = *buf_;
     ensure_work_fields( solver );
+    compute_ddi_gradient( 0 );
     SB_DISPATCH_NB(
         ( k_force_and_virtual<1><<<b.nblocks, BLOCK_THREADS, 0, b.stream>>>(
             stencil_, b.lg, llg, b.spins.c(), b.ddi_s.c(), b.F.f(), b.Fv.f(), b.partials ) ),
@@ -685,6 +704,7 @@ void DeviceImage::llg_iterate( int solver, LLGParams & llg, int n_iterations, bo
         a.Fv_out          = b.Fv.f();
         a.energy_partials = b.partials;
 
+        compute_ddi_gradient( 0 );
         if( solver == Solver_Depondt || solver == Solver_Heun || solver == Solver_SIB )
         {
             a.out = b.pred.f();
@@ -695,6 +715,7 @@ void DeviceImage::llg_iterate( int solver, LLGParams & llg, int n_iterations, bo
             else
                 launch_stage<Solver_SIB, 1>( nb1, hk, b.nblocks, b.stream, stencil_, b.lg, llg, a, b.sc6 );
             mark();
+            compute_ddi_gradient( 1 );
             a.sp  = b.pred.c();
             a.out = b.next.f();
             if( solver == Solver_Depondt )
@@ -713,14 +734,17 @@ void DeviceImage::llg_iterate( int solver, LLGParams & llg, int n_iterations, bo
             a.out = b.pred.f();
             launch_stage<Solver_RK4, 1>( nb1, hk, b.nblocks, b.stream, stencil_, b.lg, llg, a, b.sc6 );
             mark();
+            compute_ddi_gradient( 1 );
             a.sp  = b.pred.c();
             a.out = b.pred2.f();
             launch_stage<Solver_RK4, 2>( nb1, hk, b.nblocks, b.stream, stencil_, b.lg, llg, a, b.sc6 );
             mark();
+            compute_ddi_gradient( 2 );
             a.sp  = b.pred2.c();
             a.out = b.pred.f();
             launch_stage<Solver_RK4, 3>( nb1, hk, b.nblocks, b.stream, stencil_, b.lg, llg, a, b.sc6 );
             mark();
+            compute_ddi_gradient( 1 );
             a.sp  = b.pred.c();
             a.out = b.next.f();
             launch_stage<Solver_RK4, 4>( nb1, hk, b.nblocks, b.stream, stencil_, b.lg, llg, a, b.sc6 );
@@ -829,7 +853,15 @@ int DeviceImage::llg_profile_stages( int solver, LLGParams & llg, int n_iteratio
     return n_stages;
 }
 
-void DeviceImage::compute_ddi_gradient( int ) {}
+void DeviceImage::compute_ddi_gradient( int which )
+{
+    if( !stencil_.has_ddi || !ddi_ )
+        return;
+    auto & b = *buf_;
+    const DeviceField & conf = which == 0 ? b.spins : ( which == 1 ? b.pred : b.pred2 );
+    DeviceField & out        = which == 0 ? b.ddi_s : b.ddi_p;
+    launches_ += ddi_gradient( *ddi_, conf.c(), out.f(), b.stream );
+}
 
 } // namespace dev
 } // namespace sb

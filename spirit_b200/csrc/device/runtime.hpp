@@ -109,13 +109,14 @@ public:
 
 private:
     void ensure_work_fields( int solver );
+    // DDI gradient field of a configuration (0: spins -> ddi_s, 1: pred -> ddi_p, 2: pred2 -> ddi_p); no-op without DDI
     void compute_ddi_gradient( int which_config );
 
     int nos_ = 0;
     StencilParams stencil_{};
     std::uint64_t ham_revision_ = ~std::uint64_t( 0 );
     std::unique_ptr<DeviceBuffers> buf_;
-    std::unique_ptr<DDIPlan> ddi_;
+    DDIPlan * ddi_ = nullptr; // owned; created by set_hamiltonian when ddi_method == fft
     std::uint64_t launches_ = 0;
     bool vp_initialized_        = false;
     bool vp_prev_projected_     = false; // the last VP iteration ran a hook: F_prev is the projected force (in Fv)
