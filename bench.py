@@ -26,7 +26,7 @@ sys.path.insert(0, ROOT)
 
 import numpy as np  # noqa: E402
 
-from spirit_b200 import capi, session as S  # noqa: E402
+from spirit_b200 import capi, session as S, slab  # noqa: E402
 from tests import cfgs  # noqa: E402
 
 METRIC = "spin-steps/s (LLG Depondt fp64)"
@@ -171,7 +171,9 @@ def workload_config(args, cells, note=None):
                     "periodic, LLG Depondt dt=1e-3 alpha=0.3 T=10 K, fp64" % tuple(cells),
         "lattice": list(cells), "solver": "Depondt", "temperature_K": 10.0,
         "l2": "inputs larger than L2 (3 x %.0f MB spin buffers per step vs 126 MB L2)" % (np.prod(cells) * 24 / 1e6),
-        "parallelism": "1 GPU" if args.gpus == 1 else "%d GPUs, one %dx%dx%d lattice per GPU (replicas; slab halo exchange not in this round's bench)" % ((args.gpus,) + tuple(cells)),
+        "parallelism": "1 GPU" if args.gpus == 1 else (
+            "%d GPUs: ONE %dx%dx%d lattice (periodic), slab-decomposed along c, one %dx%dx%d slab per GPU, one-plane halo "
+            "exchange per solver stage over NCCL inside the library" % (args.gpus, cells[0], cells[1], cells[2] * args.gpus, cells[0], cells[1], cells[2])),
         "e2e_call": "Simulation_LLG_Start(Solver_Depondt, n_iterations=%d) per call, spins + effective field in host memory between calls" % E2E_BLOCK,
     }
     if note:
@@ -190,12 +192,17 @@ def run_b200(args):
         import torch
         import torch.distributed as dist
         torch.cuda.set_device(local_rank)
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+        dist.init_process_group("cpu:gloo,cuda:nccl", device_id=torch.device("cuda", local_rank))
+        slab.init_comm(product, dist, rank, world)
 
     cells = tuple(args.lattice)
     tmp = tempfile.mkdtemp()
-    p = S.Session(product, write_cfg(tmp, cells))
+    p = S.Session(product, write_cfg(tmp, cells, "bench_%d.cfg" % rank))
     nos = p.nos
+    if world > 1:
+        # weak scaling: the global lattice has world * Nc planes, this rank owns planes [rank * Nc, (rank + 1) * Nc)
+        if product.SpiritB200_Slab_Setup(p.state, rank * cells[2], world * cells[2], -1) != 0:
+            raise SystemExit("bench.py: SpiritB200_Slab_Setup failed")
     fill_random(p, seed=20006 + rank)
     p.upload()
     launches0 = p.kernel_launches()

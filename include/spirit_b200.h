@@ -52,6 +52,18 @@ SPIRIT_API int SpiritB200_Download( State * state, int idx_image ) SPIRIT_NOEXCE
  * stream; < 0 on error. The image's LLG parameters (dt, damping, temperature, seed, ...) apply.
  * Same arithmetic as Simulation_LLG_Start: Method_Solver<solver>::Iteration, core/include/engine/Solver_*.hpp */
 SPIRIT_API double SpiritB200_LLG_Iterate_Device( State * state, int solver_type, int n_iterations, int idx_image ) SPIRIT_NOEXCEPT;
+/* --- (3) slab decomposition over several GPUs, one process per GPU ------------------------------------------------------
+ * The pair stencils shard along c: rank r holds the planes [c_begin, c_begin + nc_local) of a lattice with Nc_global
+ * planes; its State is set up with the LOCAL slab (n_basis_cells a b nc_local). After every kernel that writes a
+ * configuration the first / last plane travels to the neighbouring ranks over NCCL (NVLink); energies, torques and the
+ * VP projections are all-reduced. The thermal noise is keyed by the GLOBAL site index, so results do not depend on the
+ * decomposition. The reference has no multi-GPU path; these entry points have no counterpart there. */
+/* 128-byte NCCL unique id, to be created on rank 0 and distributed by the launcher */
+SPIRIT_API int SpiritB200_Comm_Unique_Id( char * id128 ) SPIRIT_NOEXCEPT;
+SPIRIT_API int SpiritB200_Comm_Init( int rank, int world, const char * id128 ) SPIRIT_NOEXCEPT;
+/* Declare the image to be the slab starting at plane c_begin of a lattice with Nc_global planes. Call before any compute. */
+SPIRIT_API int SpiritB200_Slab_Setup( State * state, int c_begin, int Nc_global, int idx_image ) SPIRIT_NOEXCEPT;
+
 /* The same iterations with a CUDA event between the stage kernels: stage_ms[k] = mean milliseconds of stage k+1
  * (Depondt/Heun/SIB: 2 stages, RK4: 4). Returns the number of stages, < 0 on error. For per-kernel rooflines. */
 SPIRIT_API int SpiritB200_LLG_Profile_Stages( State * state, int solver_type, int n_iterations, double * stage_ms, int max_stages, int idx_image ) SPIRIT_NOEXCEPT;

@@ -277,3 +277,44 @@ catch( ... )
     handle_exception_api( __func__, idx_image );
     return -1;
 }
+
+// ---------------------------------------------------------------------------------------------
+int SpiritB200_Comm_Unique_Id( char * id128 ) noexcept
+try
+{
+    dev::comm_unique_id( id128 );
+    return 0;
+}
+catch( ... )
+{
+    handle_exception_api( __func__ );
+    return -1;
+}
+
+int SpiritB200_Comm_Init( int rank, int world, const char * id128 ) noexcept
+try
+{
+    dev::comm_init( rank, world, id128 );
+    return 0;
+}
+catch( ... )
+{
+    handle_exception_api( __func__ );
+    return -1;
+}
+
+int SpiritB200_Slab_Setup( State * state, int c_begin, int Nc_global, int idx_image ) noexcept
+try
+{
+    int idx_chain = -1;
+    auto image    = resolve( state, idx_image, idx_chain ).image;
+    ImageLock lock( *image );
+    image->drop_device();
+    image->device().set_slab( c_begin, Nc_global );
+    return 0;
+}
+catch( ... )
+{
+    handle_exception_api( __func__, idx_image );
+    return -1;
+}

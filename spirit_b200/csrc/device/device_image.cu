@@ -9,6 +9,7 @@
 #include <cstdlib>
 #include <cmath>
 #include <cstring>
+#include <dlfcn.h>
 #include <map>
 #include <stdexcept>
 #include <tuple>
@@ -97,6 +98,104 @@ void host_free( void * ptr, bool pinned )
 }
 
 // ---------------------------------------------------------------------------------------------
+// NCCL, bound at run time (dlopen) so that the library has no link-time dependency on it: single-GPU use never
+// touches it. Prototypes as in nccl.h (2.x ABI).
+// ---------------------------------------------------------------------------------------------
+namespace
+{
+struct NcclId
+{
+    char internal[128];
+};
+using ncclComm_t = void *;
+struct NcclApi
+{
+    void * lib                                                                                   = nullptr;
+    int ( *GetUniqueId )( NcclId * )                                                             = nullptr;
+    int ( *CommInitRank )( ncclComm_t *, int, NcclId, int )                                      = nullptr;
+    int ( *CommDestroy )( ncclComm_t )                                                           = nullptr;
+    int ( *Send )( const void *, std::size_t, int, int, ncclComm_t, cudaStream_t )               = nullptr;
+    int ( *Recv )( void *, std::size_t, int, int, ncclComm_t, cudaStream_t )                     = nullptr;
+    int ( *AllReduce )( const void *, void *, std::size_t, int, int, ncclComm_t, cudaStream_t ) = nullptr;
+    int ( *GroupStart )()                                                                        = nullptr;
+    int ( *GroupEnd )()                                                                          = nullptr;
+    const char * ( *GetErrorString )( int )                                                      = nullptr;
+    ncclComm_t comm                                                                              = nullptr;
+    int rank = 0, world = 1;
+};
+NcclApi g_nccl;
+constexpr int NCCL_FLOAT64 = 8, NCCL_SUM = 0, NCCL_MAX = 2;
+
+void nccl_load()
+{
+    if( g_nccl.lib )
+        return;
+    const char * env          = std::getenv( "SPIRIT_B200_NCCL" );
+    const char * candidates[] = { env, "libnccl.so.2", "libnccl.so" };
+    for( const char * c : candidates )
+    {
+        if( !c || !*c )
+            continue;
+        g_nccl.lib = dlopen( c, RTLD_NOW | RTLD_GLOBAL );
+        if( g_nccl.lib )
+            break;
+    }
+    if( !g_nccl.lib )
+        throw std::runtime_error( "spirit_b200: cannot load libnccl.so.2 (set SPIRIT_B200_NCCL to its path)" );
+    auto sym = [&]( const char * name ) {
+        void * f = dlsym( g_nccl.lib, name );
+        if( !f )
+            throw std::runtime_error( std::string( "spirit_b200: libnccl has no symbol " ) + name );
+        return f;
+    };
+    g_nccl.GetUniqueId    = reinterpret_cast<decltype( g_nccl.GetUniqueId )>( sym( "ncclGetUniqueId" ) );
+    g_nccl.CommInitRank   = reinterpret_cast<decltype( g_nccl.CommInitRank )>( sym( "ncclCommInitRank" ) );
+    g_nccl.CommDestroy    = reinterpret_cast<decltype( g_nccl.CommDestroy )>( sym( "ncclCommDestroy" ) );
+    g_nccl.Send           = reinterpret_cast<decltype( g_nccl.Send )>( sym( "ncclSend" ) );
+    g_nccl.Recv           = reinterpret_cast<decltype( g_nccl.Recv )>( sym( "ncclRecv" ) );
+    g_nccl.AllReduce      = reinterpret_cast<decltype( g_nccl.AllReduce )>( sym( "ncclAllReduce" ) );
+    g_nccl.GroupStart     = reinterpret_cast<decltype( g_nccl.GroupStart )>( sym( "ncclGroupStart" ) );
+    g_nccl.GroupEnd       = reinterpret_cast<decltype( g_nccl.GroupEnd )>( sym( "ncclGroupEnd" ) );
+    g_nccl.GetErrorString = reinterpret_cast<decltype( g_nccl.GetErrorString )>( sym( "ncclGetErrorString" ) );
+}
+void nccl_check( int result, const char * what )
+{
+    if( result != 0 )
+        throw std::runtime_error( std::string( "spirit_b200 NCCL error in " ) + what + ": " + ( g_nccl.GetErrorString ? g_nccl.GetErrorString( result ) : "?" ) );
+}
+} // namespace
+
+void comm_unique_id( char id[128] )
+{
+    nccl_load();
+    NcclId nid;
+    nccl_check( g_nccl.GetUniqueId( &nid ), "ncclGetUniqueId" );
+    std::memcpy( id, nid.internal, 128 );
+}
+void comm_init( int rank, int world, const char id[128] )
+{
+    require_device();
+    nccl_load();
+    if( g_nccl.comm )
+        throw std::runtime_error( "spirit_b200: the communicator is already initialised" );
+    NcclId nid;
+    std::memcpy( nid.internal, id, 128 );
+    nccl_check( g_nccl.CommInitRank( &g_nccl.comm, world, nid, rank ), "ncclCommInitRank" );
+    g_nccl.rank  = rank;
+    g_nccl.world = world;
+}
+bool comm_active()
+{
+    return g_nccl.comm != nullptr;
+}
+int comm_rank()
+{
+    return g_nccl.rank;
+}
+int comm_world()
+{
+    return g_nccl.world;
+}
 
 namespace
 {
@@ -214,6 +313,78 @@ DeviceImage::~DeviceImage()
         ddi_plan_destroy( ddi_ );
 }
 
+void DeviceImage::set_slab( int c_begin, int Nc_global )
+{
+    if( !comm_active() )
+        throw std::runtime_error( "spirit_b200: set_slab needs an initialised communicator (SpiritB200_Comm_Init)" );
+    auto & b = *buf_;
+    if( b.F.allocated() || b.pred.allocated() || ddi_ )
+        throw std::runtime_error( "spirit_b200: set_slab must be called before the image is used" );
+    if( c_begin < 0 || c_begin + stencil_.nc_local > Nc_global )
+        throw std::runtime_error( "spirit_b200: slab outside of the global lattice" );
+    stencil_.Nc      = Nc_global;
+    stencil_.c_begin = c_begin;
+    stencil_.halo    = 1; // grown by set_hamiltonian if the pair list reaches further in c
+    slab_            = true;
+    ham_revision_    = ~std::uint64_t( 0 );
+    b.n_storage      = std::size_t( stencil_.plane_stride ) * ( stencil_.nc_local + 2 * stencil_.halo );
+    b.spins.allocate( b.n_storage );
+    SB_CUDA_CHECK( cudaMemset( b.spins.base, 0, 3 * b.n_storage * sizeof( double ) ) );
+}
+
+// Send the first / last `halo` owned planes of `field` to the lower / upper neighbour slab and receive their planes into
+// the halo planes. Planes are contiguous (3 * plane_stride doubles). Open c: the chain ends have no neighbour.
+void DeviceImage::exchange_halo( void * device_field )
+{
+    if( !slab_ )
+        return;
+    auto & b          = *buf_;
+    DeviceField & f   = *static_cast<DeviceField *>( device_field );
+    const auto & p    = stencil_;
+    const int world = g_nccl.world, rank = g_nccl.rank;
+    const std::size_t plane = 3 * std::size_t( p.plane_stride );
+    const std::size_t count = plane * p.halo;
+    const bool periodic     = p.bc[2] != 0;
+    const int lower = rank > 0 ? rank - 1 : ( periodic ? world - 1 : -1 );
+    const int upper = rank < world - 1 ? rank + 1 : ( periodic ? 0 : -1 );
+    double * first_owned = f.base + plane * p.halo;
+    double * last_owned  = f.base + plane * p.nc_local; // = halo + nc_local - halo
+    double * low_halo    = f.base;
+    double * high_halo   = f.base + plane * ( p.halo + p.nc_local );
+    if( world == 1 )
+    {
+        // a single slab that is periodic in c: its own planes wrap around
+        if( periodic )
+        {
+            SB_CUDA_CHECK( cudaMemcpyAsync( low_halo, last_owned, count * sizeof( double ), cudaMemcpyDeviceToDevice, b.stream ) );
+            SB_CUDA_CHECK( cudaMemcpyAsync( high_halo, first_owned, count * sizeof( double ), cudaMemcpyDeviceToDevice, b.stream ) );
+        }
+        return;
+    }
+    nccl_check( g_nccl.GroupStart(), "ncclGroupStart" );
+    if( lower >= 0 )
+        nccl_check( g_nccl.Send( first_owned, count, NCCL_FLOAT64, lower, g_nccl.comm, b.stream ), "ncclSend" );
+    if( upper >= 0 )
+        nccl_check( g_nccl.Send( last_owned, count, NCCL_FLOAT64, upper, g_nccl.comm, b.stream ), "ncclSend" );
+    // receive order matters when lower == upper (two slabs, periodic): the peer sends its FIRST planes first, and those
+    // are my upper neighbours
+    if( upper >= 0 )
+        nccl_check( g_nccl.Recv( high_halo, count, NCCL_FLOAT64, upper, g_nccl.comm, b.stream ), "ncclRecv" );
+    if( lower >= 0 )
+        nccl_check( g_nccl.Recv( low_halo, count, NCCL_FLOAT64, lower, g_nccl.comm, b.stream ), "ncclRecv" );
+    nccl_check( g_nccl.GroupEnd(), "ncclGroupEnd" );
+}
+
+void DeviceImage::allreduce_scalars( int first, int count, bool max )
+{
+    if( !slab_ || g_nccl.world == 1 )
+        return;
+    auto & b = *buf_;
+    nccl_check(
+        g_nccl.AllReduce( b.scalars + first, b.scalars + first, count, NCCL_FLOAT64, max ? NCCL_MAX : NCCL_SUM, g_nccl.comm, b.stream ),
+        "ncclAllReduce" );
+}
+
 void DeviceImage::synchronize()
 {
     SB_CUDA_CHECK( cudaStreamSynchronize( buf_->stream ) );
@@ -251,8 +422,10 @@ void DeviceImage::set_hamiltonian( const Hamiltonian & ham )
     std::vector<Key> order;
     auto entry = [&]( const Pair & pr ) -> Neighbour * {
         const auto & t = pr.translations;
-        if( std::abs( t[0] ) > g.n_cells[0] || std::abs( t[1] ) > g.n_cells[1] || std::abs( t[2] ) > g.n_cells[2] )
+        if( std::abs( t[0] ) > g.n_cells[0] || std::abs( t[1] ) > g.n_cells[1] || std::abs( t[2] ) > p.Nc )
             return nullptr;
+        if( slab_ && std::abs( t[2] ) > p.halo )
+            throw std::runtime_error( "spirit_b200: pairs reaching further than one plane in c are not supported on a slab decomposition yet" );
         if( pr.i < 0 || pr.i >= g.n_cell_atoms || pr.j < 0 || pr.j >= g.n_cell_atoms )
             return nullptr;
         Key k{ pr.i, pr.j, t[0], t[1], t[2] };
@@ -437,6 +610,7 @@ void DeviceImage::upload_spins( const double * host_aos )
         b.staging, b.spins.f(), nos_, b.plane_sites, stencil_.plane_stride, stencil_.halo );
     ++launches_;
     SB_CUDA_CHECK( cudaGetLastError() );
+    exchange_halo( &b.spins );
 }
 
 static void download_field(
@@ -500,6 +674,7 @@ void DeviceImage::gradient_and_energy( double * gradient_host_aos, double * ener
         ( k_gradient<0, true><<<b.nblocks, BLOCK_THREADS, 0, b.stream>>>(
             stencil_, b.lg, b.spins.c(), b.ddi_s.c(), b.scratch.f(), 1.0, b.partials ) ) );
     reduce_sum_to( b, b.partials, 4, launches_ );
+    allreduce_scalars( 4, 1, false );
     SB_CUDA_CHECK( cudaMemcpyAsync( b.h_scalars + 4, b.scalars + 4, sizeof( double ), cudaMemcpyDeviceToHost, b.stream ) );
     if( gradient_host_aos )
         download_field( b, stencil_, b.scratch, gradient_host_aos, nos_, 1.0, launches_ );
@@ -659,6 +834,8 @@ void DeviceImage::llg_initial_hook( int solver, const LLGParams & llg, HookResul
     k_reduce_max<<<1, BLOCK_THREADS, 0, b.stream>>>( b.partials + b.nblocks, b.nblocks, b.scalars + 5 );
     launches_ += 3;
     SB_CUDA_CHECK( cudaGetLastError() );
+    allreduce_scalars( 4, 1, false );
+    allreduce_scalars( 5, 1, true );
     SB_CUDA_CHECK( cudaMemcpyAsync( b.h_scalars + 4, b.scalars + 4, 2 * sizeof( double ), cudaMemcpyDeviceToHost, b.stream ) );
     SB_CUDA_CHECK( cudaStreamSynchronize( b.stream ) );
     if( result )
@@ -715,6 +892,7 @@ void DeviceImage::llg_iterate( int solver, LLGParams & llg, int n_iterations, bo
             else
                 launch_stage<Solver_SIB, 1>( nb1, hk, b.nblocks, b.stream, stencil_, b.lg, llg, a, b.sc6 );
             mark();
+            exchange_halo( &b.pred );
             compute_ddi_gradient( 1 );
             a.sp  = b.pred.c();
             a.out = b.next.f();
@@ -725,6 +903,7 @@ void DeviceImage::llg_iterate( int solver, LLGParams & llg, int n_iterations, bo
             else
                 launch_stage<Solver_SIB, 2>( nb1, hk, b.nblocks, b.stream, stencil_, b.lg, llg, a, b.sc6 );
             mark();
+            exchange_halo( &b.next );
             launches_ += 2;
             std::swap( b.spins, b.next );
         }
@@ -734,21 +913,25 @@ void DeviceImage::llg_iterate( int solver, LLGParams & llg, int n_iterations, bo
             a.out = b.pred.f();
             launch_stage<Solver_RK4, 1>( nb1, hk, b.nblocks, b.stream, stencil_, b.lg, llg, a, b.sc6 );
             mark();
+            exchange_halo( &b.pred );
             compute_ddi_gradient( 1 );
             a.sp  = b.pred.c();
             a.out = b.pred2.f();
             launch_stage<Solver_RK4, 2>( nb1, hk, b.nblocks, b.stream, stencil_, b.lg, llg, a, b.sc6 );
             mark();
+            exchange_halo( &b.pred2 );
             compute_ddi_gradient( 2 );
             a.sp  = b.pred2.c();
             a.out = b.pred.f();
             launch_stage<Solver_RK4, 3>( nb1, hk, b.nblocks, b.stream, stencil_, b.lg, llg, a, b.sc6 );
             mark();
+            exchange_halo( &b.pred );
             compute_ddi_gradient( 1 );
             a.sp  = b.pred.c();
             a.out = b.next.f();
             launch_stage<Solver_RK4, 4>( nb1, hk, b.nblocks, b.stream, stencil_, b.lg, llg, a, b.sc6 );
             mark();
+            exchange_halo( &b.next );
             launches_ += 4;
             std::swap( b.spins, b.next );
         }
@@ -777,6 +960,7 @@ void DeviceImage::llg_iterate( int solver, LLGParams & llg, int n_iterations, bo
             vp_prev_projected_ = hk;
             k_reduce_sum<<<1, BLOCK_THREADS, 0, b.stream>>>( pp, b.nblocks, b.scalars + 1 );
             k_reduce_sum<<<1, BLOCK_THREADS, 0, b.stream>>>( pn, b.nblocks, b.scalars + 2 );
+            allreduce_scalars( 1, 2, false ); // projections are sums over ALL slabs
             k_vp_ratio<<<1, 1, 0, b.stream>>>( b.scalars );
             if( hk )
             {
@@ -789,6 +973,7 @@ void DeviceImage::llg_iterate( int solver, LLGParams & llg, int n_iterations, bo
             else
                 k_vp_b<false><<<b.nblocks, BLOCK_THREADS, 0, b.stream>>>(
                     stencil_, b.lg, b.spins.f(), b.F.c(), b.Fv.f(), b.scalars, llg.dt, llg.dtg, nullptr );
+            exchange_halo( &b.spins );
             launches_ += 5;
         }
         else
@@ -803,6 +988,11 @@ void DeviceImage::llg_iterate( int solver, LLGParams & llg, int n_iterations, bo
             launches_ += 3;
         }
         ++llg.iteration;
+    }
+    if( hook )
+    {
+        allreduce_scalars( 4, 1, false ); // energy
+        allreduce_scalars( 5, 1, true );  // max torque^2
     }
     if( hook )
         effective_field_in_Fv_ = solver == Solver_VP;

@@ -35,6 +35,14 @@ std::string device_name();
 void * host_alloc( std::size_t bytes, bool & pinned );
 void host_free( void * ptr, bool pinned );
 
+// Process-wide NCCL communicator for the slab decomposition (one process per GPU). The 128-byte unique id is created
+// on rank 0 (comm_unique_id) and distributed by the launcher (bench.py / tests: torch.distributed broadcast).
+void comm_unique_id( char id[128] );
+void comm_init( int rank, int world, const char id[128] );
+bool comm_active();
+int comm_rank();
+int comm_world();
+
 struct DeviceBuffers; // opaque (device pointers, stream, events)
 struct DDIPlan;       // opaque (device/ddi_fft.cu)
 
@@ -56,6 +64,12 @@ public:
     {
         return nos_;
     }
+
+    // Slab decomposition along c: this image holds the planes [c_begin, c_begin + nc_local) of a lattice with Nc_global
+    // planes (nc_local = the geometry's n_cells[2]). Neighbouring slabs live on ranks rank-1 / rank+1 of the process-wide
+    // communicator; `halo` planes are exchanged after every kernel that writes a configuration. Must be called before
+    // the spins are uploaded.
+    void set_slab( int c_begin, int Nc_global );
 
     // (Re)build the stencil tables from the host Hamiltonian if its revision changed
     void set_hamiltonian( const Hamiltonian & ham );
@@ -109,6 +123,8 @@ public:
 
 private:
     void ensure_work_fields( int solver );
+    void exchange_halo( void * device_field ); // DeviceField *
+    void allreduce_scalars( int first, int count, bool max );
     // DDI gradient field of a configuration (0: spins -> ddi_s, 1: pred -> ddi_p, 2: pred2 -> ddi_p); no-op without DDI
     void compute_ddi_gradient( int which_config );
 
@@ -118,6 +134,7 @@ private:
     std::unique_ptr<DeviceBuffers> buf_;
     DDIPlan * ddi_ = nullptr; // owned; created by set_hamiltonian when ddi_method == fft
     std::uint64_t launches_ = 0;
+    bool slab_                  = false;
     bool vp_initialized_        = false;
     bool vp_prev_projected_     = false; // the last VP iteration ran a hook: F_prev is the projected force (in Fv)
     bool effective_field_in_Fv_ = false;
