@@ -54,7 +54,9 @@ def main():
                 ref = g.spins().copy()
                 dev = np.abs(np.concatenate(parts) - ref).max()
                 moved = np.abs(ref - s_global).max()
-                ok = dev == 0.0 and moved > 1e-4 and abs(e_slab - g.energy()) <= 1e-12 * abs(g.energy())
+                # VP couples all sites through two global sums whose summation order depends on the decomposition
+                tol = 1e-12 if solver == "VP" else 0.0
+                ok = dev <= tol and moved > 1e-4 and abs(e_slab - g.energy()) <= 1e-12 * abs(g.energy())
                 print("bc_c=%d %-8s T=%g: max deviation %.3e, moved %.2e, E slab %.12e global %.12e %s" % (
                     bc_c, solver, temperature, dev, moved, e_slab, g.energy(), "OK" if ok else "FAIL"), flush=True)
                 if not ok:
