@@ -27,6 +27,8 @@
 #include "../core/hamiltonian.hpp"
 
 #include <cmath>
+#include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <stdexcept>
 #include <vector>
@@ -39,7 +41,7 @@ namespace dev
 namespace
 {
 
-constexpr int FFT_THREADS  = 256;
+constexpr int FFT_THREADS  = 1024; // upper bound; launches use fft_threads( work items )
 constexpr int MAX_RADICES  = 16;
 constexpr int MAX_SMEM_FFT = 200 * 1024;
 
@@ -47,6 +49,7 @@ struct FFTPlan1D
 {
     int n       = 1;
     int n_radix = 0;
+    int pow2    = 0; // n is a power of two (all strides are powers of two: shifts instead of divisions)
     int radix[MAX_RADICES];
     const double2 * twiddle = nullptr; // exp(-2 pi i k / n), k < n
 };
@@ -84,12 +87,26 @@ __device__ double2 * block_fft( const FFTPlan1D & plan, double2 * x, double2 * y
         const int m = n / ( s * r ); // remaining sub-transform length / r
         // one work item = (butterfly (p, q), column)
         const int items = m * s * ncol;
+        // ncol and (for power-of-two lengths) s are powers of two: shifts and masks instead of integer divisions
+        const int lg_ncol = 31 - __clz( ncol ), lg_s = 31 - __clz( s );
+        const bool fast   = plan.pow2 && ( ncol & ( ncol - 1 ) ) == 0;
         for( int item = threadIdx.x; item < items; item += blockDim.x )
         {
-            const int col = item % ncol;
-            const int t   = item / ncol;
-            const int q   = t % s;
-            const int p   = t / s;
+            int col, q, p;
+            if( fast )
+            {
+                col         = item & ( ncol - 1 );
+                const int t = item >> lg_ncol;
+                q           = t & ( s - 1 );
+                p           = t >> lg_s;
+            }
+            else
+            {
+                col         = item % ncol;
+                const int t = item / ncol;
+                q           = t % s;
+                p           = t / s;
+            }
             // inputs a_i = x[q + s (p + m i)], outputs y[q + s (r p + i)] = (sum_k a_k w_r^{ik}) w_{n/s}^{p i}
             const int tw_step = p * s; // w_{n/s}^{p} = W_n^{p s}
             if( r == 2 )
@@ -110,8 +127,8 @@ __device__ double2 * block_fft( const FFTPlan1D & plan, double2 * x, double2 * y
                 const double2 jb3 = INVERSE ? make_double2( -b3.y, b3.x ) : make_double2( b3.y, -b3.x );
                 y[( q + s * ( 4 * p ) ) * ncol + col]     = cadd( b0, b2 );
                 y[( q + s * ( 4 * p + 1 ) ) * ncol + col] = cmul( cadd( b1, jb3 ), tw<INVERSE>( plan, tw_step ) );
-                y[( q + s * ( 4 * p + 2 ) ) * ncol + col] = cmul( csub( b0, b2 ), tw<INVERSE>( plan, ( 2 * tw_step ) % n ) );
-                y[( q + s * ( 4 * p + 3 ) ) * ncol + col] = cmul( csub( b1, jb3 ), tw<INVERSE>( plan, ( 3 * tw_step ) % n ) );
+                y[( q + s * ( 4 * p + 2 ) ) * ncol + col] = cmul( csub( b0, b2 ), tw<INVERSE>( plan, 2 * tw_step ) );
+                y[( q + s * ( 4 * p + 3 ) ) * ncol + col] = cmul( csub( b1, jb3 ), tw<INVERSE>( plan, 3 * tw_step ) );
             }
             else
             {
@@ -331,6 +348,170 @@ static __global__ void __launch_bounds__( FFT_THREADS ) k_ddi_c_mult(
     }
 }
 
+
+// exp(-2 pi i k / 32), k < 32: twiddles of the in-register transforms (lengths up to 32)
+static __constant__ double2 TW32[32] = {
+    { 1, 0 },
+    { 0.98078528040323043, -0.19509032201612825 },
+    { 0.92387953251128674, -0.38268343236508978 },
+    { 0.83146961230254524, -0.55557023301960218 },
+    { 0.70710678118654757, -0.70710678118654746 },
+    { 0.55557023301960229, -0.83146961230254524 },
+    { 0.38268343236508984, -0.92387953251128674 },
+    { 0.19509032201612833, -0.98078528040323043 },
+    { 0, -1 },
+    { -0.19509032201612819, -0.98078528040323043 },
+    { -0.38268343236508973, -0.92387953251128674 },
+    { -0.55557023301960196, -0.83146961230254546 },
+    { -0.70710678118654746, -0.70710678118654757 },
+    { -0.83146961230254535, -0.55557023301960218 },
+    { -0.92387953251128674, -0.38268343236508989 },
+    { -0.98078528040323043, -0.19509032201612861 },
+    { -1, 0 },
+    { -0.98078528040323043, 0.19509032201612836 },
+    { -0.92387953251128685, 0.38268343236508967 },
+    { -0.83146961230254546, 0.55557023301960196 },
+    { -0.70710678118654768, 0.70710678118654746 },
+    { -0.55557023301960218, 0.83146961230254524 },
+    { -0.38268343236509034, 0.92387953251128652 },
+    { -0.19509032201612866, 0.98078528040323032 },
+    { 0, 1 },
+    { 0.1950903220161283, 0.98078528040323043 },
+    { 0.38268343236509, 0.92387953251128663 },
+    { 0.55557023301960184, 0.83146961230254546 },
+    { 0.70710678118654735, 0.70710678118654768 },
+    { 0.83146961230254524, 0.55557023301960218 },
+    { 0.92387953251128652, 0.38268343236509039 },
+    { 0.98078528040323032, 0.19509032201612872 } };
+
+// 3': the same for small power-of-two Pc (thin films): ONE THREAD per (kb, ka) column does the length-PC transforms of
+// all three components in registers -- no shared memory, no barriers, fully coalesced along ka. REAL_D: the tensor
+// spectrum is real (single sublattice: D(-r) = D(r)) and stored as doubles, halving the dominant read stream.
+template<int PC, bool INVERSE>
+__device__ __forceinline__ void reg_fft( double2 ( &v )[PC] )
+{
+    // iterative radix-2 decimation in frequency, output in bit-reversed order -> reorder at the end
+#pragma unroll
+    for( int half = PC / 2; half >= 1; half /= 2 )
+    {
+#pragma unroll
+        for( int base = 0; base < PC; base += 2 * half )
+        {
+#pragma unroll
+            for( int j = 0; j < half; ++j )
+            {
+                const double2 a = v[base + j], b = v[base + j + half];
+                v[base + j]     = cadd( a, b );
+                const double2 d = csub( a, b );
+                // twiddle exp(-+ 2 pi i j / (2 half)) (constant-bank operand after unrolling)
+                const double2 t    = TW32[j * ( 16 / half )];
+                v[base + j + half] = cmul( d, make_double2( t.x, INVERSE ? -t.y : t.y ) );
+            }
+        }
+    }
+    // bit reversal
+    double2 w[PC];
+#pragma unroll
+    for( int i = 0; i < PC; ++i )
+    {
+        int r = 0;
+#pragma unroll
+        for( int bit = 1, rb = PC / 2; bit < PC; bit *= 2, rb /= 2 )
+            if( i & bit )
+                r |= rb;
+        w[r] = v[i];
+    }
+#pragma unroll
+    for( int i = 0; i < PC; ++i )
+        v[i] = w[i];
+}
+
+template<int PC, bool REAL_D>
+static __global__ void __launch_bounds__( 128 ) k_ddi_c_mult_small(
+    const __grid_constant__ DDIDims d, double2 * __restrict__ B, const void * __restrict__ Dhat_v )
+{
+    const int ka = blockIdx.x * blockDim.x + threadIdx.x;
+    const int kb = blockIdx.y;
+    if( ka >= d.Ha )
+        return;
+    const std::size_t c_stride = std::size_t( d.Pb ) * d.Ha;
+    const std::size_t col      = std::size_t( kb ) * d.Ha + ka;
+    const std::size_t dcomp    = std::size_t( PC ) * d.Pb * d.Ha;
+    double2 sx[PC], sy[PC], sz[PC];
+#pragma unroll
+    for( int j = 0; j < PC; ++j )
+    {
+        const double2 zero = make_double2( 0.0, 0.0 );
+        sx[j] = j < d.Nc ? B[( std::size_t( 0 ) * d.Nc + j ) * c_stride + col] : zero;
+        sy[j] = j < d.Nc ? B[( std::size_t( 1 ) * d.Nc + j ) * c_stride + col] : zero;
+        sz[j] = j < d.Nc ? B[( std::size_t( 2 ) * d.Nc + j ) * c_stride + col] : zero;
+    }
+    reg_fft<PC, false>( sx );
+    reg_fft<PC, false>( sy );
+    reg_fft<PC, false>( sz );
+#pragma unroll
+    for( int kc = 0; kc < PC; ++kc )
+    {
+        const std::size_t dk = std::size_t( kc ) * c_stride + col;
+        double2 fx, fy, fz;
+        if( REAL_D )
+        {
+            const double * Dp = static_cast<const double *>( Dhat_v ) + dk;
+            const double Dxx = __ldg( Dp ), Dxy = __ldg( Dp + dcomp ), Dxz = __ldg( Dp + 2 * dcomp );
+            const double Dyy = __ldg( Dp + 3 * dcomp ), Dyz = __ldg( Dp + 4 * dcomp ), Dzz = __ldg( Dp + 5 * dcomp );
+            fx = make_double2( Dxx * sx[kc].x + Dxy * sy[kc].x + Dxz * sz[kc].x, Dxx * sx[kc].y + Dxy * sy[kc].y + Dxz * sz[kc].y );
+            fy = make_double2( Dxy * sx[kc].x + Dyy * sy[kc].x + Dyz * sz[kc].x, Dxy * sx[kc].y + Dyy * sy[kc].y + Dyz * sz[kc].y );
+            fz = make_double2( Dxz * sx[kc].x + Dyz * sy[kc].x + Dzz * sz[kc].x, Dxz * sx[kc].y + Dyz * sy[kc].y + Dzz * sz[kc].y );
+        }
+        else
+        {
+            const double2 * Dp = static_cast<const double2 *>( Dhat_v ) + dk;
+            const double2 Dxx = __ldg( Dp ), Dxy = __ldg( Dp + dcomp ), Dxz = __ldg( Dp + 2 * dcomp );
+            const double2 Dyy = __ldg( Dp + 3 * dcomp ), Dyz = __ldg( Dp + 4 * dcomp ), Dzz = __ldg( Dp + 5 * dcomp );
+            fx = cadd( cmul( Dxx, sx[kc] ), cadd( cmul( Dxy, sy[kc] ), cmul( Dxz, sz[kc] ) ) );
+            fy = cadd( cmul( Dxy, sx[kc] ), cadd( cmul( Dyy, sy[kc] ), cmul( Dyz, sz[kc] ) ) );
+            fz = cadd( cmul( Dxz, sx[kc] ), cadd( cmul( Dyz, sy[kc] ), cmul( Dzz, sz[kc] ) ) );
+        }
+        sx[kc] = fx;
+        sy[kc] = fy;
+        sz[kc] = fz;
+    }
+    reg_fft<PC, true>( sx );
+    reg_fft<PC, true>( sy );
+    reg_fft<PC, true>( sz );
+#pragma unroll
+    for( int j = 0; j < PC; ++j )
+        if( j < d.Nc )
+        {
+            B[( std::size_t( 0 ) * d.Nc + j ) * c_stride + col] = sx[j];
+            B[( std::size_t( 1 ) * d.Nc + j ) * c_stride + col] = sy[j];
+            B[( std::size_t( 2 ) * d.Nc + j ) * c_stride + col] = sz[j];
+        }
+}
+
+// max |Im D^| and max |D^| (is the tensor spectrum real?) -- partial maxima per block
+static __global__ void k_ddi_imag_check( const double2 * __restrict__ D, std::size_t n, double * __restrict__ out )
+{
+    double mi = 0, ma = 0;
+    for( std::size_t i = blockIdx.x * std::size_t( blockDim.x ) + threadIdx.x; i < n; i += std::size_t( gridDim.x ) * blockDim.x )
+    {
+        mi = fmax( mi, fabs( D[i].y ) );
+        ma = fmax( ma, fmax( fabs( D[i].x ), fabs( D[i].y ) ) );
+    }
+    mi = block_max( mi );
+    if( threadIdx.x == 0 )
+        out[2 * blockIdx.x] = mi;
+    ma = block_max( ma );
+    if( threadIdx.x == 0 )
+        out[2 * blockIdx.x + 1] = ma;
+}
+static __global__ void k_ddi_take_real( const double2 * __restrict__ in, double * __restrict__ out, std::size_t n )
+{
+    const std::size_t i = blockIdx.x * std::size_t( blockDim.x ) + threadIdx.x;
+    if( i < n )
+        out[i] = in[i].x;
+}
+
 // 5: inverse a-pass (C2R through a complex transform of the Hermitian-extended row) fused with
 //    g_ddi = -mu_s res / P  (Hamiltonian_Heisenberg.cpp:995-1013), written as a field
 static __global__ void __launch_bounds__( FFT_THREADS ) k_ddi_inv_a(
@@ -388,6 +569,15 @@ static __global__ void k_ddi_tensor( const __grid_constant__ DDIDims d, const __
         return;
     const int a = int( i % d.Pa ), b = int( ( i / d.Pa ) % d.Pb ), c = int( i / ( std::size_t( d.Pa ) * d.Pb ) );
     const int ai = a < d.Na ? a : a - d.Pa, bi = b < d.Nb ? b : b - d.Pb, ci = c < d.Nc ? c : c - d.Pc;
+    // Offsets of -N along a padded direction never occur between two real sites (|difference| <= N - 1). The reference
+    // fills them (with the value for -N, there is no slot for +N), which breaks the inversion symmetry of the padded
+    // tensor; zeroed here, D(-r) = D(r) holds on the whole padded lattice and the spectrum of a single sublattice is
+    // real. The convolution result at the real sites is identical.
+    if( ( d.Pa > d.Na && ai == -d.Na ) || ( d.Pb > d.Nb && bi == -d.Nb ) || ( d.Pc > d.Nc && ci == -d.Nc ) )
+    {
+        out[i] = 0.0;
+        return;
+    }
     double D = 0.0;
     for( int pa = -t.img[0]; pa <= t.img[0]; ++pa )
         for( int pb = -t.img[1]; pb <= t.img[1]; ++pb )
@@ -444,7 +634,8 @@ struct DDIPlan
     DDIDims dims{};
     FFTPlan1D plan[3]; // a, b, c
     double2 * twiddle[3] = { nullptr, nullptr, nullptr };
-    double2 * Dhat       = nullptr;
+    double2 * Dhat       = nullptr; // complex tensor spectrum, or
+    double * Dhat_real   = nullptr; // its real part when the imaginary part vanishes (single sublattice)
     double2 * A          = nullptr;
     double2 * B          = nullptr;
     int ncol_b = 1, ncol_c = 1;
@@ -458,6 +649,8 @@ struct DDIPlan
                 cudaFree( t );
         if( Dhat )
             cudaFree( Dhat );
+        if( Dhat_real )
+            cudaFree( Dhat_real );
         if( A )
             cudaFree( A );
         if( B )
@@ -474,6 +667,7 @@ void make_plan_1d( FFTPlan1D & plan, double2 *& table, int n )
     if( fac.size() > std::size_t( MAX_RADICES ) )
         throw std::runtime_error( "spirit_b200: FFT length with too many factors" );
     plan.n_radix = int( fac.size() );
+    plan.pow2    = ( n & ( n - 1 ) ) == 0 ? 1 : 0;
     for( int i = 0; i < plan.n_radix; ++i )
         plan.radix[i] = fac[i];
     std::vector<double2> w( n );
@@ -485,6 +679,12 @@ void make_plan_1d( FFTPlan1D & plan, double2 *& table, int n )
     SB_CUDA_CHECK( cudaMalloc( &table, std::size_t( n ) * sizeof( double2 ) ) );
     SB_CUDA_CHECK( cudaMemcpy( table, w.data(), std::size_t( n ) * sizeof( double2 ), cudaMemcpyHostToDevice ) );
     plan.twiddle = table;
+}
+
+// CTA size for a pass with `items` radix-4 work items per stage
+int fft_threads( int items )
+{
+    return std::max( 64, std::min( FFT_THREADS, ( ( items + 31 ) / 32 ) * 32 ) );
 }
 
 int choose_ncol( int n, int n_components, int n_u )
@@ -593,14 +793,14 @@ DDIPlan * ddi_plan_create( const Hamiltonian & ham, const StencilParams & sp, cu
             {
                 double2 * Dout = plan->Dhat + std::size_t( 6 * inter + comp6 ) * half;
                 k_ddi_tensor<<<unsigned( ( full + 255 ) / 256 ), 256, 0, stream>>>( d, tg, comp6, Dreal );
-                k_fft_real_rows<<<unsigned( std::size_t( d.Pb ) * d.Pc ), FFT_THREADS, plan->smem_a, stream>>>( plan->plan[0], Dreal, tmp1, d.Ha );
+                k_fft_real_rows<<<unsigned( std::size_t( d.Pb ) * d.Pc ), fft_threads( d.Pa / 4 ), plan->smem_a, stream>>>( plan->plan[0], Dreal, tmp1, d.Ha );
                 // b: tmp1[c][b][ka] -> Dout[c][kb][ka]
                 PassArgs pb{};
                 pb.in = tmp1, pb.out = Dout;
                 pb.in_os = pb.out_os = std::size_t( d.Pb ) * d.Ha;
                 pb.in_js = pb.out_js = d.Ha;
                 pb.n_u = d.Ha, pb.n_o = d.Pc, pb.n_in = d.Pb, pb.n_out = d.Pb, pb.ncol = ncol_setup, pb.scale = 1.0;
-                k_fft_pass<false><<<dim3( ( d.Ha + ncol_setup - 1 ) / ncol_setup, d.Pc ), FFT_THREADS, plan->smem_b, stream>>>( plan->plan[1], pb );
+                k_fft_pass<false><<<dim3( ( d.Ha + ncol_setup - 1 ) / ncol_setup, d.Pc ), fft_threads( d.Pb / 4 * ncol_setup ), plan->smem_b, stream>>>( plan->plan[1], pb );
                 // c: Dout[c][kb][ka] -> tmp1[kc][kb][ka]; (kb, ka) is one contiguous index of length Pb*Ha
                 PassArgs pc{};
                 pc.in = Dout, pc.out = tmp1;
@@ -610,7 +810,7 @@ DDIPlan * ddi_plan_create( const Hamiltonian & ham, const StencilParams & sp, cu
                 pc.ncol = choose_ncol( d.Pc, 1, pc.n_u );
                 const std::size_t smem_c1 = std::size_t( d.Pc ) * 2 * sizeof( double2 ) * pc.ncol;
                 allow_smem( k_fft_pass<false>, std::max( plan->smem_b, smem_c1 ) );
-                k_fft_pass<false><<<dim3( ( pc.n_u + pc.ncol - 1 ) / pc.ncol, 1 ), FFT_THREADS, smem_c1, stream>>>( plan->plan[2], pc );
+                k_fft_pass<false><<<dim3( ( pc.n_u + pc.ncol - 1 ) / pc.ncol, 1 ), fft_threads( std::max( 1, d.Pc / 4 ) * pc.ncol ), smem_c1, stream>>>( plan->plan[2], pc );
                 SB_CUDA_CHECK( cudaMemcpyAsync( Dout, tmp1, half * sizeof( double2 ), cudaMemcpyDeviceToDevice, stream ) );
                 plan->launches_setup += 4;
             }
@@ -619,6 +819,38 @@ DDIPlan * ddi_plan_create( const Hamiltonian & ham, const StencilParams & sp, cu
     SB_CUDA_CHECK( cudaStreamSynchronize( stream ) );
     cudaFree( Dreal );
     cudaFree( tmp1 );
+
+    // Single sublattice: D(-r) = D(r), the spectrum is real. Verify numerically, then keep only the real parts.
+    if( d.NB == 1 && ( d.Pc & ( d.Pc - 1 ) ) == 0 && d.Pc <= 32 )
+    {
+        const std::size_t n_all = std::size_t( 6 * d.n_inter ) * half;
+        const int blocks        = 1024;
+        double * part           = nullptr;
+        SB_CUDA_CHECK( cudaMalloc( &part, 2 * blocks * sizeof( double ) ) );
+        k_ddi_imag_check<<<blocks, BLOCK_THREADS, 0, stream>>>( plan->Dhat, n_all, part );
+        std::vector<double> h( 2 * blocks );
+        SB_CUDA_CHECK( cudaMemcpyAsync( h.data(), part, h.size() * sizeof( double ), cudaMemcpyDeviceToHost, stream ) );
+        SB_CUDA_CHECK( cudaStreamSynchronize( stream ) );
+        cudaFree( part );
+        double max_imag = 0, max_abs = 0;
+        for( int i = 0; i < blocks; ++i )
+        {
+            max_imag = std::max( max_imag, h[2 * i] );
+            max_abs  = std::max( max_abs, h[2 * i + 1] );
+        }
+        if( std::getenv( "SPIRIT_B200_DDI_VERBOSE" ) )
+            std::fprintf( stderr, "spirit_b200 ddi: max |Im D^| = %.3e, max |D^| = %.3e\n", max_imag, max_abs );
+        // The imaginary parts are pure round-off of the forward transforms (a few ulp of the largest element times
+        // log2 P): mathematically zero. 1e-12 relative is 4 orders above what is observed and far below any signal.
+        if( max_imag <= 1e-12 * max_abs )
+        {
+            SB_CUDA_CHECK( cudaMalloc( &plan->Dhat_real, n_all * sizeof( double ) ) );
+            k_ddi_take_real<<<unsigned( ( n_all + 255 ) / 256 ), 256, 0, stream>>>( plan->Dhat, plan->Dhat_real, n_all );
+            SB_CUDA_CHECK( cudaStreamSynchronize( stream ) );
+            cudaFree( plan->Dhat );
+            plan->Dhat = nullptr;
+        }
+    }
     return plan.release();
 }
 
@@ -627,7 +859,7 @@ int ddi_gradient( DDIPlan & plan, ConstField3 spins, Field3 g_ddi, cudaStream_t 
 {
     const DDIDims & d = plan.dims;
     const int rows    = d.Nb * d.Nc;
-    k_ddi_fwd_a<<<dim3( rows, d.NB ), FFT_THREADS, plan.smem_a, stream>>>( plan.plan[0], d, spins, plan.A );
+    k_ddi_fwd_a<<<dim3( rows, d.NB ), fft_threads( d.Pa / 4 ), plan.smem_a, stream>>>( plan.plan[0], d, spins, plan.A );
     // forward b: A[q][c][b][ka] -> B[q][c][kb][ka]; outer index o = q * Nc + c
     PassArgs pb{};
     pb.in = plan.A, pb.out = plan.B;
@@ -635,18 +867,46 @@ int ddi_gradient( DDIPlan & plan, ConstField3 spins, Field3 g_ddi, cudaStream_t 
     pb.in_js = pb.out_js = d.Ha;
     pb.n_u = d.Ha, pb.n_o = 3 * d.NB * d.Nc, pb.n_in = d.Nb, pb.n_out = d.Pb, pb.ncol = plan.ncol_b, pb.scale = 1.0;
     const dim3 grid_b( ( d.Ha + plan.ncol_b - 1 ) / plan.ncol_b, pb.n_o );
-    k_fft_pass<false><<<grid_b, FFT_THREADS, plan.smem_b, stream>>>( plan.plan[1], pb );
-    k_ddi_c_mult<<<dim3( ( d.Ha + plan.ncol_c - 1 ) / plan.ncol_c, d.Pb ), FFT_THREADS, plan.smem_c, stream>>>(
-        plan.plan[2], d, plan.B, plan.Dhat, plan.ncol_c );
+    k_fft_pass<false><<<grid_b, fft_threads( d.Pb / 4 * plan.ncol_b ), plan.smem_b, stream>>>( plan.plan[1], pb );
+    const bool small_c = d.NB == 1 && ( d.Pc & ( d.Pc - 1 ) ) == 0 && d.Pc <= 32;
+    if( small_c )
+    {
+        const dim3 grid( ( d.Ha + 127 ) / 128, d.Pb );
+        const void * D = plan.Dhat_real ? static_cast<const void *>( plan.Dhat_real ) : static_cast<const void *>( plan.Dhat );
+#define SB_DDI_SMALL( PC )                                                                                             \
+    case PC:                                                                                                           \
+        if( plan.Dhat_real )                                                                                           \
+            k_ddi_c_mult_small<PC, true><<<grid, 128, 0, stream>>>( d, plan.B, D );                                    \
+        else                                                                                                           \
+            k_ddi_c_mult_small<PC, false><<<grid, 128, 0, stream>>>( d, plan.B, D );                                   \
+        break;
+        switch( d.Pc )
+        {
+            SB_DDI_SMALL( 1 )
+            SB_DDI_SMALL( 2 )
+            SB_DDI_SMALL( 4 )
+            SB_DDI_SMALL( 8 )
+            SB_DDI_SMALL( 16 )
+            SB_DDI_SMALL( 32 )
+        }
+#undef SB_DDI_SMALL
+    }
+    else
+    {
+        if( !plan.Dhat )
+            throw std::logic_error( "spirit_b200: real tensor spectrum with the shared-memory multiply kernel" );
+        k_ddi_c_mult<<<dim3( ( d.Ha + plan.ncol_c - 1 ) / plan.ncol_c, d.Pb ), fft_threads( d.Pc / 4 * plan.ncol_c * 3 * d.NB ), plan.smem_c, stream>>>(
+            plan.plan[2], d, plan.B, plan.Dhat, plan.ncol_c );
+    }
     // inverse b: B -> A, keep b < Nb
     PassArgs ib{};
     ib.in = plan.B, ib.out = plan.A;
     ib.in_os = std::size_t( d.Pb ) * d.Ha, ib.out_os = std::size_t( d.Nb ) * d.Ha;
     ib.in_js = ib.out_js = d.Ha;
     ib.n_u = d.Ha, ib.n_o = 3 * d.NB * d.Nc, ib.n_in = d.Pb, ib.n_out = d.Nb, ib.ncol = plan.ncol_b, ib.scale = 1.0;
-    k_fft_pass<true><<<grid_b, FFT_THREADS, plan.smem_b, stream>>>( plan.plan[1], ib );
+    k_fft_pass<true><<<grid_b, fft_threads( d.Pb / 4 * plan.ncol_b ), plan.smem_b, stream>>>( plan.plan[1], ib );
     const double inv_P = 1.0 / ( double( d.Pa ) * d.Pb * d.Pc );
-    k_ddi_inv_a<<<dim3( rows, d.NB ), FFT_THREADS, plan.smem_a, stream>>>( plan.plan[0], d, plan.A, g_ddi, inv_P );
+    k_ddi_inv_a<<<dim3( rows, d.NB ), fft_threads( d.Pa / 4 ), plan.smem_a, stream>>>( plan.plan[0], d, plan.A, g_ddi, inv_P );
     SB_CUDA_CHECK( cudaGetLastError() );
     return 5;
 }
