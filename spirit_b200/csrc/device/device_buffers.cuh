@@ -71,6 +71,10 @@ struct DeviceBuffers
     SC6Launch sc6;
     cudaStream_t stream = nullptr;
     cudaEvent_t ev_start = nullptr, ev_stop = nullptr;
+    // slab decomposition: halo exchanges run on their own stream so that they overlap the interior of a stage
+    cudaStream_t comm_stream = nullptr; // NCCL halo exchange (high priority)
+    cudaStream_t bnd_stream  = nullptr; // the boundary segments of a stage (high priority), concurrent with the interior
+    cudaEvent_t ev_boundary = nullptr, ev_comm = nullptr, ev_ready = nullptr;
 
     LaunchGeom lg{};
     int nblocks            = 0;
@@ -108,6 +112,16 @@ struct DeviceBuffers
             cudaEventDestroy( ev_start );
         if( ev_stop )
             cudaEventDestroy( ev_stop );
+        if( ev_boundary )
+            cudaEventDestroy( ev_boundary );
+        if( ev_comm )
+            cudaEventDestroy( ev_comm );
+        if( ev_ready )
+            cudaEventDestroy( ev_ready );
+        if( comm_stream )
+            cudaStreamDestroy( comm_stream );
+        if( bnd_stream )
+            cudaStreamDestroy( bnd_stream );
         if( stream )
             cudaStreamDestroy( stream );
     }

@@ -330,11 +330,35 @@ void DeviceImage::set_slab( int c_begin, int Nc_global )
     b.n_storage      = std::size_t( stencil_.plane_stride ) * ( stencil_.nc_local + 2 * stencil_.halo );
     b.spins.allocate( b.n_storage );
     SB_CUDA_CHECK( cudaMemset( b.spins.base, 0, 3 * b.n_storage * sizeof( double ) ) );
+    if( !b.comm_stream )
+    {
+        int prio_low = 0, prio_high = 0;
+        SB_CUDA_CHECK( cudaDeviceGetStreamPriorityRange( &prio_low, &prio_high ) );
+        SB_CUDA_CHECK( cudaStreamCreateWithPriority( &b.comm_stream, cudaStreamNonBlocking, prio_high ) );
+        SB_CUDA_CHECK( cudaStreamCreateWithPriority( &b.bnd_stream, cudaStreamNonBlocking, prio_high ) );
+        SB_CUDA_CHECK( cudaEventCreateWithFlags( &b.ev_boundary, cudaEventDisableTiming ) );
+        SB_CUDA_CHECK( cudaEventCreateWithFlags( &b.ev_comm, cudaEventDisableTiming ) );
+        SB_CUDA_CHECK( cudaEventCreateWithFlags( &b.ev_ready, cudaEventDisableTiming ) );
+    }
 }
 
 // Send the first / last `halo` owned planes of `field` to the lower / upper neighbour slab and receive their planes into
 // the halo planes. Planes are contiguous (3 * plane_stride doubles). Open c: the chain ends have no neighbour.
 void DeviceImage::exchange_halo( void * device_field )
+{
+    exchange_halo_begin( device_field );
+    exchange_halo_end();
+}
+
+void * DeviceImage::boundary_stream()
+{
+    auto & b = *buf_;
+    SB_CUDA_CHECK( cudaEventRecord( b.ev_ready, b.stream ) );
+    SB_CUDA_CHECK( cudaStreamWaitEvent( b.bnd_stream, b.ev_ready, 0 ) );
+    return b.bnd_stream;
+}
+
+void DeviceImage::exchange_halo_begin( void * device_field, bool from_boundary_stream )
 {
     if( !slab_ )
         return;
@@ -351,28 +375,41 @@ void DeviceImage::exchange_halo( void * device_field )
     double * last_owned  = f.base + plane * p.nc_local; // = halo + nc_local - halo
     double * low_halo    = f.base;
     double * high_halo   = f.base + plane * ( p.halo + p.nc_local );
+    // the exchange starts when the work enqueued so far on the image's stream is done
+    SB_CUDA_CHECK( cudaEventRecord( b.ev_boundary, from_boundary_stream ? b.bnd_stream : b.stream ) );
+    SB_CUDA_CHECK( cudaStreamWaitEvent( b.comm_stream, b.ev_boundary, 0 ) );
     if( world == 1 )
     {
         // a single slab that is periodic in c: its own planes wrap around
         if( periodic )
         {
-            SB_CUDA_CHECK( cudaMemcpyAsync( low_halo, last_owned, count * sizeof( double ), cudaMemcpyDeviceToDevice, b.stream ) );
-            SB_CUDA_CHECK( cudaMemcpyAsync( high_halo, first_owned, count * sizeof( double ), cudaMemcpyDeviceToDevice, b.stream ) );
+            SB_CUDA_CHECK( cudaMemcpyAsync( low_halo, last_owned, count * sizeof( double ), cudaMemcpyDeviceToDevice, b.comm_stream ) );
+            SB_CUDA_CHECK( cudaMemcpyAsync( high_halo, first_owned, count * sizeof( double ), cudaMemcpyDeviceToDevice, b.comm_stream ) );
         }
-        return;
     }
-    nccl_check( g_nccl.GroupStart(), "ncclGroupStart" );
-    if( lower >= 0 )
-        nccl_check( g_nccl.Send( first_owned, count, NCCL_FLOAT64, lower, g_nccl.comm, b.stream ), "ncclSend" );
-    if( upper >= 0 )
-        nccl_check( g_nccl.Send( last_owned, count, NCCL_FLOAT64, upper, g_nccl.comm, b.stream ), "ncclSend" );
-    // receive order matters when lower == upper (two slabs, periodic): the peer sends its FIRST planes first, and those
-    // are my upper neighbours
-    if( upper >= 0 )
-        nccl_check( g_nccl.Recv( high_halo, count, NCCL_FLOAT64, upper, g_nccl.comm, b.stream ), "ncclRecv" );
-    if( lower >= 0 )
-        nccl_check( g_nccl.Recv( low_halo, count, NCCL_FLOAT64, lower, g_nccl.comm, b.stream ), "ncclRecv" );
-    nccl_check( g_nccl.GroupEnd(), "ncclGroupEnd" );
+    else
+    {
+        nccl_check( g_nccl.GroupStart(), "ncclGroupStart" );
+        if( lower >= 0 )
+            nccl_check( g_nccl.Send( first_owned, count, NCCL_FLOAT64, lower, g_nccl.comm, b.comm_stream ), "ncclSend" );
+        if( upper >= 0 )
+            nccl_check( g_nccl.Send( last_owned, count, NCCL_FLOAT64, upper, g_nccl.comm, b.comm_stream ), "ncclSend" );
+        // receive order matters when lower == upper (two slabs, periodic): the peer sends its FIRST planes first, and
+        // those are my upper neighbours
+        if( upper >= 0 )
+            nccl_check( g_nccl.Recv( high_halo, count, NCCL_FLOAT64, upper, g_nccl.comm, b.comm_stream ), "ncclRecv" );
+        if( lower >= 0 )
+            nccl_check( g_nccl.Recv( low_halo, count, NCCL_FLOAT64, lower, g_nccl.comm, b.comm_stream ), "ncclRecv" );
+        nccl_check( g_nccl.GroupEnd(), "ncclGroupEnd" );
+    }
+    SB_CUDA_CHECK( cudaEventRecord( b.ev_comm, b.comm_stream ) );
+}
+
+void DeviceImage::exchange_halo_end()
+{
+    if( !slab_ )
+        return;
+    SB_CUDA_CHECK( cudaStreamWaitEvent( buf_->stream, buf_->ev_comm, 0 ) );
 }
 
 void DeviceImage::allreduce_scalars( int first, int count, bool max )
@@ -784,22 +821,52 @@ void DeviceImage::vp_reset()
 namespace
 {
 template<int SOLVER, int STAGE>
+void sc6_dispatch( const SC6Launch & sc6, cudaStream_t stream, const StencilParams & p, const LLGParams & l, const StageArgs & a )
+{
+    if( SOLVER == Solver_Depondt )
+        sc6_launch_depondt( STAGE, sc6, stream, p, l, a );
+    else if( SOLVER == Solver_Heun )
+        sc6_launch_heun( STAGE, sc6, stream, p, l, a );
+    else if( SOLVER == Solver_SIB )
+        sc6_launch_sib( STAGE, sc6, stream, p, l, a );
+    else
+        sc6_launch_rk4( STAGE, sc6, stream, p, l, a );
+}
+
+// Launches one solver stage that writes the configuration `out` and brings the halo planes of `out` up to date (slab
+// decomposition). With the marching kernels the stage is split in two launches: the c-segments at the two slab ends
+// first, then -- while their first / last plane travels to the neighbouring ranks on the communication stream -- the
+// interior segments.
+template<int SOLVER, int STAGE>
 void launch_stage(
     bool nb1, bool hook, int nblocks, cudaStream_t stream, const StencilParams & p, const LaunchGeom & lg, const LLGParams & l,
-    const StageArgs & a, const SC6Launch & sc6 )
+    const StageArgs & a, const SC6Launch & sc6, DeviceImage & image, void * out )
 {
     if( p.sc6 && !hook )
     {
         // nearest-neighbour structure: marching kernel (the hook iteration, which also stores F, Fv and reduces the
         // energy, goes through the generic kernel)
-        if( SOLVER == Solver_Depondt )
-            sc6_launch_depondt( STAGE, sc6, stream, p, l, a );
-        else if( SOLVER == Solver_Heun )
-            sc6_launch_heun( STAGE, sc6, stream, p, l, a );
-        else if( SOLVER == Solver_SIB )
-            sc6_launch_sib( STAGE, sc6, stream, p, l, a );
-        else
-            sc6_launch_rk4( STAGE, sc6, stream, p, l, a );
+        const SC6Geometry & G = SC6Shape<SOLVER, STAGE>::two_windows ? sc6.two_windows : sc6.one_window;
+        const int nseg        = int( G.grid.z );
+        if( image.is_slab() && nseg >= 3 )
+        {
+            SC6Launch part         = sc6;
+            SC6Geometry & Gp       = SC6Shape<SOLVER, STAGE>::two_windows ? part.two_windows : part.one_window;
+            Gp.grid.z              = 2;
+            Gp.seg_first           = 0;
+            Gp.seg_stride          = nseg - 1;
+            // the two end segments on the high-priority boundary stream, concurrently with the interior segments
+            sc6_dispatch<SOLVER, STAGE>( part, cudaStream_t( image.boundary_stream() ), p, l, a );
+            image.exchange_halo_begin( out, true );
+            Gp.grid.z     = nseg - 2;
+            Gp.seg_first  = 1;
+            Gp.seg_stride = 1;
+            sc6_dispatch<SOLVER, STAGE>( part, stream, p, l, a );
+            image.exchange_halo_end();
+            return;
+        }
+        sc6_dispatch<SOLVER, STAGE>( sc6, stream, p, l, a );
+        image.exchange_halo( out );
         return;
     }
     if( nb1 )
@@ -816,6 +883,7 @@ void launch_stage(
         else
             k_llg_stage<SOLVER, STAGE, 0, false><<<nblocks, BLOCK_THREADS, 0, stream>>>( p, lg, l, a );
     }
+    image.exchange_halo( out );
 }
 } // namespace
 
@@ -886,24 +954,22 @@ void DeviceImage::llg_iterate( int solver, LLGParams & llg, int n_iterations, bo
         {
             a.out = b.pred.f();
             if( solver == Solver_Depondt )
-                launch_stage<Solver_Depondt, 1>( nb1, hk, b.nblocks, b.stream, stencil_, b.lg, llg, a, b.sc6 );
+                launch_stage<Solver_Depondt, 1>( nb1, hk, b.nblocks, b.stream, stencil_, b.lg, llg, a, b.sc6, *this, &b.pred );
             else if( solver == Solver_Heun )
-                launch_stage<Solver_Heun, 1>( nb1, hk, b.nblocks, b.stream, stencil_, b.lg, llg, a, b.sc6 );
+                launch_stage<Solver_Heun, 1>( nb1, hk, b.nblocks, b.stream, stencil_, b.lg, llg, a, b.sc6, *this, &b.pred );
             else
-                launch_stage<Solver_SIB, 1>( nb1, hk, b.nblocks, b.stream, stencil_, b.lg, llg, a, b.sc6 );
+                launch_stage<Solver_SIB, 1>( nb1, hk, b.nblocks, b.stream, stencil_, b.lg, llg, a, b.sc6, *this, &b.pred );
             mark();
-            exchange_halo( &b.pred );
             compute_ddi_gradient( 1 );
             a.sp  = b.pred.c();
             a.out = b.next.f();
             if( solver == Solver_Depondt )
-                launch_stage<Solver_Depondt, 2>( nb1, hk, b.nblocks, b.stream, stencil_, b.lg, llg, a, b.sc6 );
+                launch_stage<Solver_Depondt, 2>( nb1, hk, b.nblocks, b.stream, stencil_, b.lg, llg, a, b.sc6, *this, &b.next );
             else if( solver == Solver_Heun )
-                launch_stage<Solver_Heun, 2>( nb1, hk, b.nblocks, b.stream, stencil_, b.lg, llg, a, b.sc6 );
+                launch_stage<Solver_Heun, 2>( nb1, hk, b.nblocks, b.stream, stencil_, b.lg, llg, a, b.sc6, *this, &b.next );
             else
-                launch_stage<Solver_SIB, 2>( nb1, hk, b.nblocks, b.stream, stencil_, b.lg, llg, a, b.sc6 );
+                launch_stage<Solver_SIB, 2>( nb1, hk, b.nblocks, b.stream, stencil_, b.lg, llg, a, b.sc6, *this, &b.next );
             mark();
-            exchange_halo( &b.next );
             launches_ += 2;
             std::swap( b.spins, b.next );
         }
@@ -911,27 +977,23 @@ void DeviceImage::llg_iterate( int solver, LLGParams & llg, int n_iterations, bo
         {
             a.acc = b.acc.f();
             a.out = b.pred.f();
-            launch_stage<Solver_RK4, 1>( nb1, hk, b.nblocks, b.stream, stencil_, b.lg, llg, a, b.sc6 );
+            launch_stage<Solver_RK4, 1>( nb1, hk, b.nblocks, b.stream, stencil_, b.lg, llg, a, b.sc6, *this, &b.pred );
             mark();
-            exchange_halo( &b.pred );
             compute_ddi_gradient( 1 );
             a.sp  = b.pred.c();
             a.out = b.pred2.f();
-            launch_stage<Solver_RK4, 2>( nb1, hk, b.nblocks, b.stream, stencil_, b.lg, llg, a, b.sc6 );
+            launch_stage<Solver_RK4, 2>( nb1, hk, b.nblocks, b.stream, stencil_, b.lg, llg, a, b.sc6, *this, &b.pred2 );
             mark();
-            exchange_halo( &b.pred2 );
             compute_ddi_gradient( 2 );
             a.sp  = b.pred2.c();
             a.out = b.pred.f();
-            launch_stage<Solver_RK4, 3>( nb1, hk, b.nblocks, b.stream, stencil_, b.lg, llg, a, b.sc6 );
+            launch_stage<Solver_RK4, 3>( nb1, hk, b.nblocks, b.stream, stencil_, b.lg, llg, a, b.sc6, *this, &b.pred );
             mark();
-            exchange_halo( &b.pred );
             compute_ddi_gradient( 1 );
             a.sp  = b.pred.c();
             a.out = b.next.f();
-            launch_stage<Solver_RK4, 4>( nb1, hk, b.nblocks, b.stream, stencil_, b.lg, llg, a, b.sc6 );
+            launch_stage<Solver_RK4, 4>( nb1, hk, b.nblocks, b.stream, stencil_, b.lg, llg, a, b.sc6, *this, &b.next );
             mark();
-            exchange_halo( &b.next );
             launches_ += 4;
             std::swap( b.spins, b.next );
         }

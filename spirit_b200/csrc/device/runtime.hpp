@@ -121,9 +121,20 @@ public:
         return buf_.get();
     }
 
+    bool is_slab() const
+    {
+        return slab_;
+    }
+    void exchange_halo( void * device_field ); // DeviceField *; ordered after everything enqueued on the image's stream
+    // the two halves of an overlapped exchange: start after the work enqueued so far (the boundary segments of a stage),
+    // and make the image's stream wait for its completion
+    void exchange_halo_begin( void * device_field, bool from_boundary_stream = false );
+    void exchange_halo_end();
+    // stream for the boundary segments of a stage; on return it waits for everything enqueued so far on the image's stream
+    void * boundary_stream();
+
 private:
     void ensure_work_fields( int solver );
-    void exchange_halo( void * device_field ); // DeviceField *
     void allreduce_scalars( int first, int count, bool max );
     // DDI gradient field of a configuration (0: spins -> ddi_s, 1: pred -> ddi_p, 2: pred2 -> ddi_p); no-op without DDI
     void compute_ddi_gradient( int which_config );

@@ -56,7 +56,9 @@ constexpr int SC6_N_MODES  = 3;
 struct SC6Geometry
 {
     dim3 grid, block;
-    int lc = 1; // planes per CTA (march length)
+    int lc          = 1; // planes per CTA (march length)
+    int seg_first   = 0; // CTA z index -> c-segment: seg_first + blockIdx.z * seg_stride (lets a launch cover only the
+    int seg_stride  = 1; // two segments at the slab ends, or only the interior ones: halo-exchange overlap)
 };
 struct SC6Launch
 {
@@ -448,14 +450,14 @@ __device__ __forceinline__ void sc6_march(
 
 template<int SOLVER, int STAGE, int SPEC, int MODE>
 static __global__ void __launch_bounds__( SC6Shape<SOLVER, STAGE>::threads, SC6Shape<SOLVER, STAGE>::min_blocks ) k_sc6_stage(
-    const __grid_constant__ StencilParams p, const int lc, const __grid_constant__ LLGParams l,
-    const __grid_constant__ StageArgs a )
+    const __grid_constant__ StencilParams p, const int lc, const int seg_first, const int seg_stride,
+    const __grid_constant__ LLGParams l, const __grid_constant__ StageArgs a )
 {
     const int x = blockIdx.x * blockDim.x + threadIdx.x;
     const int b = blockIdx.y * blockDim.y + threadIdx.y;
     if( x >= p.Na || b >= p.Nb )
         return;
-    const int c0 = blockIdx.z * lc;
+    const int c0 = ( seg_first + int( blockIdx.z ) * seg_stride ) * lc;
     const int c1 = min( c0 + lc, p.nc_local );
 
     // Does this CTA touch an open boundary? (uniform) Interior CTAs run the loop without predicates.
@@ -478,7 +480,7 @@ void sc6_launch_stage(
 {
     const int mode = l.direct_minimization ? SC6_MINIMISE : ( l.has_thermal ? SC6_THERMAL : SC6_DYNAMICS );
 #define SB_SC6_CASE( S, M )                                                                                            \
-    case S * SC6_N_MODES + M: k_sc6_stage<SOLVER, STAGE, S, M><<<G.grid, G.block, 0, stream>>>( p, G.lc, l, a ); break;
+    case S * SC6_N_MODES + M: k_sc6_stage<SOLVER, STAGE, S, M><<<G.grid, G.block, 0, stream>>>( p, G.lc, G.seg_first, G.seg_stride, l, a ); break;
     const SC6Geometry & G = SC6Shape<SOLVER, STAGE>::two_windows ? L.two_windows : L.one_window;
     switch( L.spec * SC6_N_MODES + mode )
     {
