@@ -64,6 +64,11 @@ SPIRIT_API int SpiritB200_Comm_Init( int rank, int world, const char * id128 ) S
 /* Declare the image to be the slab starting at plane c_begin of a lattice with Nc_global planes. Call before any compute. */
 SPIRIT_API int SpiritB200_Slab_Setup( State * state, int c_begin, int Nc_global, int idx_image ) SPIRIT_NOEXCEPT;
 
+/* GNEB: whole images per GPU. This process's chain holds the images [i_begin, i_begin + noi) of a chain of noi_global
+ * images; per force evaluation the first / last local image travels to the neighbouring rank (tangents, geodesic
+ * distances), per-image scalars (E, Rx, projections) are all-reduced, VP's projections are summed over all images. */
+SPIRIT_API int SpiritB200_Chain_Shard_Setup( State * state, int i_begin, int noi_global ) SPIRIT_NOEXCEPT;
+
 /* The same iterations with a CUDA event between the stage kernels: stage_ms[k] = mean milliseconds of stage k+1
  * (Depondt/Heun/SIB: 2 stages, RK4: 4). Returns the number of stages, < 0 on error. For per-kernel rooflines. */
 SPIRIT_API int SpiritB200_LLG_Profile_Stages( State * state, int solver_type, int n_iterations, double * stage_ms, int max_stages, int idx_image ) SPIRIT_NOEXCEPT;

@@ -318,3 +318,20 @@ catch( ... )
     handle_exception_api( __func__, idx_image );
     return -1;
 }
+
+int SpiritB200_Chain_Shard_Setup( State * state, int i_begin, int noi_global ) noexcept
+try
+{
+    int idx_image = -1, idx_chain = -1;
+    auto chain = resolve( state, idx_image, idx_chain ).chain;
+    if( i_begin < 0 || i_begin + chain->noi > noi_global )
+        throw std::runtime_error( "SpiritB200_Chain_Shard_Setup: shard outside of the global chain" );
+    chain->shard_begin      = i_begin;
+    chain->shard_noi_global = noi_global;
+    return 0;
+}
+catch( ... )
+{
+    handle_exception_api( __func__ );
+    return -1;
+}

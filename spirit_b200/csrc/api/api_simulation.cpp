@@ -159,7 +159,7 @@ try
             Log( Log_Level::Warning, Log_Sender::API, "A simulation is running on an image of this chain. No action taken.", -1, idx_chain );
             return;
         }
-    if( r.chain->noi < 3 )
+    if( ( r.chain->shard_noi_global < 0 ? r.chain->noi : r.chain->shard_noi_global ) < 3 )
     {
         Log( Log_Level::Error, Log_Sender::API, "There are less than 3 images in the chain. GNEB cannot be started.", -1, idx_chain );
         return;

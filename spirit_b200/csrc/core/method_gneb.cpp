@@ -55,14 +55,17 @@ Method_GNEB::Method_GNEB( std::shared_ptr<Chain> chain_, int solver_, int idx_ch
     max_torque     = P.force_convergence + 1.0;
     max_torque_all = std::vector<double>( chain->noi, 0.0 );
 
-    device_ = std::make_unique<dev::DeviceChain>( *chain->images[0]->geometry, chain->noi );
+    device_ = std::make_unique<dev::DeviceChain>( *chain->images[0]->geometry, chain->noi, chain->shard_begin, chain->shard_noi_global );
     device_->set_hamiltonian( *chain->images[0]->hamiltonian );
     Sync_Device();
     device_->vp_reset();
 
     // Data of the border images, which are not updated (Method_GNEB.cpp:68-72)
-    chain->images.front()->UpdateEffectiveField();
-    chain->images.back()->UpdateEffectiveField();
+    if( chain->shard_noi_global < 0 )
+    {
+        chain->images.front()->UpdateEffectiveField();
+        chain->images.back()->UpdateEffectiveField();
+    }
 }
 
 Method_GNEB::~Method_GNEB() = default;
@@ -98,12 +101,9 @@ void Method_GNEB::Hook_Post_Iteration()
         chain->iteration_allowed = false;
         return;
     }
-    max_torque = 0;
     for( int img = 0; img < chain->noi; ++img )
-    {
         max_torque_all[img] = pending_.max_torque[img];
-        max_torque          = std::max( max_torque, pending_.max_torque[img] );
-    }
+    max_torque = pending_.max_torque_chain; // over all images, also those held by other ranks
     auto interp = cubic_hermite_interpolate( pending_.Rx, pending_.energy, pending_.dE_dRx, chain->gneb_parameters->n_E_interpolations );
     chain->Rx   = pending_.Rx;
     for( int img = 0; img < chain->noi; ++img )

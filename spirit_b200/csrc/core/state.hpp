@@ -202,6 +202,11 @@ struct Chain
     bool iteration_allowed  = false;
     bool singleshot_allowed = false;
 
+    // Images sharded over several GPUs, one process each (include/spirit_b200.h (3)): this process holds the images
+    // [shard_begin, shard_begin + noi) of a chain of shard_noi_global images (-1: not sharded)
+    int shard_begin      = 0;
+    int shard_noi_global = -1;
+
     std::vector<double> Rx, Rx_interpolated, E_interpolated;
     std::vector<std::vector<double>> E_array_interpolated;
 

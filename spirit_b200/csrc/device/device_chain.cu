@@ -22,7 +22,9 @@
 
 #include "../core/hamiltonian.hpp"
 
+#include <algorithm>
 #include <cmath>
+#include <cstddef>
 #include <cstring>
 #include <stdexcept>
 
@@ -62,9 +64,13 @@ struct ChainView
     double * F2;  // total force of the predictor evaluation / new force of VP
     double * Fpr; // VP: force projected by the hook (F_prev of the next iteration)
     std::size_t stride; // doubles per image and field
-    double * scal;      // [S_N_SLOTS][noi] + G_N
-    int noi;
+    double * scal;      // [S_N_SLOTS][noi] + G_N   (noi = GLOBAL number of images)
+    int noi;            // global number of images of the chain
+    int n_local;        // images held by this rank: global indices [i_begin, i_begin + n_local)
+    int i_begin;
 };
+// Field pointers are offset by one image, so that local index -1 / n_local address the halo images received from the
+// neighbouring ranks (images sharded over GPUs); unsharded chains have no halo and i_begin = 0.
 
 __device__ __forceinline__ ConstField3 cfield( const double * base, std::size_t stride, int img )
 {
@@ -115,7 +121,8 @@ static __global__ void __launch_bounds__( BLOCK_THREADS ) k_chain_gradient(
     const __grid_constant__ StencilParams p, const __grid_constant__ LaunchGeom lg, const __grid_constant__ ChainView v,
     const double * __restrict__ conf, double * __restrict__ partials, int nblocks )
 {
-    const int img = blockIdx.y;
+    const int img = blockIdx.y;      // local image
+    const int gi  = v.i_begin + img; // global image
     Site site;
     const bool active = locate_site( p, lg, site, NB_T > 0 ? NB_T : p.NB );
     double e = 0, d2 = 0;
@@ -128,7 +135,7 @@ static __global__ void __launch_bounds__( BLOCK_THREADS ) k_chain_gradient(
         const D3 gt          = total( g );
         store3( field( v.Fg, v.stride, img ), site.idx, make_d3( -gt.x, -gt.y, -gt.z ) );
         e = site_energy<NB_T>( p, site, si, g );
-        if( img > 0 )
+        if( gi > 0 )
         {
             const D3 sp = load3( cfield( conf, v.stride, img - 1 ), site.idx );
             double r    = dot3( si, sp );
@@ -139,10 +146,10 @@ static __global__ void __launch_bounds__( BLOCK_THREADS ) k_chain_gradient(
     }
     e = block_sum( e );
     if( threadIdx.x == 0 )
-        partials[( std::size_t( 0 ) * v.noi + img ) * nblocks + blockIdx.x] = e;
+        partials[( std::size_t( 0 ) * v.n_local + img ) * nblocks + blockIdx.x] = e;
     d2 = block_sum( d2 );
     if( threadIdx.x == 0 )
-        partials[( std::size_t( 1 ) * v.noi + img ) * nblocks + blockIdx.x] = d2;
+        partials[( std::size_t( 1 ) * v.n_local + img ) * nblocks + blockIdx.x] = d2;
 }
 
 // Rx and the degenerate-chain check (Method_GNEB.cpp:116-126)
@@ -166,6 +173,7 @@ static __global__ void __launch_bounds__( BLOCK_THREADS ) k_chain_tangent(
     const double * __restrict__ conf, double * __restrict__ partials, int nblocks )
 {
     const int img = blockIdx.y;
+    const int g   = v.i_begin + img;
     Site site;
     const bool active = locate_site( p, lg, site, p.NB );
     double tt = 0, ft = 0;
@@ -173,11 +181,11 @@ static __global__ void __launch_bounds__( BLOCK_THREADS ) k_chain_tangent(
     {
         const D3 s = load3( cfield( conf, v.stride, img ), site.idx );
         D3 t;
-        if( img == 0 || img == v.noi - 1 )
+        if( g == 0 || g == v.noi - 1 )
         {
             // Geodesic_Tangent at the end images: t = mid x (plus x minus)
-            const D3 minus = img == 0 ? s : load3( cfield( conf, v.stride, img - 1 ), site.idx );
-            const D3 plus  = img == 0 ? load3( cfield( conf, v.stride, 1 ), site.idx ) : s;
+            const D3 minus = g == 0 ? s : load3( cfield( conf, v.stride, img - 1 ), site.idx );
+            const D3 plus  = g == 0 ? load3( cfield( conf, v.stride, img + 1 ), site.idx ) : s;
             D3 axis        = cross3( plus, minus );
             if( fabs( dot3( minus, plus ) + 1.0 ) < 1e-15 )
                 axis = fabs( s.x - 1.0 ) > 1e-15 ? make_d3( 1, 0, 0 ) : make_d3( 0, 1, 0 );
@@ -190,7 +198,7 @@ static __global__ void __launch_bounds__( BLOCK_THREADS ) k_chain_tangent(
             const D3 tp      = make_d3( sp.x - s.x, sp.y - s.y, sp.z - s.z );
             const D3 tm      = make_d3( s.x - sm.x, s.y - sm.y, s.z - sm.z );
             const double * E = slot( v, S_E );
-            const double Em = E[img], Ep = E[img + 1], Emi = E[img - 1];
+            const double Em = E[g], Ep = E[g + 1], Emi = E[g - 1];
             double wp, wm;
             if( ( Ep < Em && Em > Emi ) || ( Ep > Em && Em < Emi ) )
             {
@@ -225,15 +233,15 @@ static __global__ void __launch_bounds__( BLOCK_THREADS ) k_chain_tangent(
         // projected gradient force . tangent (for interior images t is perpendicular to s, so this is also F_g.t)
         const double d = dot3( Fg, s );
         ft             = ( Fg.x - d * s.x ) * t.x + ( Fg.y - d * s.y ) * t.y + ( Fg.z - d * s.z ) * t.z;
-        if( img == 0 || img == v.noi - 1 )
+        if( g == 0 || g == v.noi - 1 )
             ft = dot3( Fg, t ); // dE/dRx at the end images uses the unprojected effective field (Method_GNEB.cpp:433-437)
     }
     tt = block_sum( tt );
     if( threadIdx.x == 0 )
-        partials[( std::size_t( 0 ) * v.noi + img ) * nblocks + blockIdx.x] = tt;
+        partials[( std::size_t( 0 ) * v.n_local + img ) * nblocks + blockIdx.x] = tt;
     ft = block_sum( ft );
     if( threadIdx.x == 0 )
-        partials[( std::size_t( 1 ) * v.noi + img ) * nblocks + blockIdx.x] = ft;
+        partials[( std::size_t( 1 ) * v.n_local + img ) * nblocks + blockIdx.x] = ft;
 }
 
 struct ChainTypes
@@ -244,36 +252,38 @@ struct ChainTypes
 // Per-image coefficients of the total force (Method_GNEB.cpp:175-258), one thread per image
 static __global__ void k_chain_coeffs( const __grid_constant__ ChainView v, const __grid_constant__ ChainTypes types, double spring_constant )
 {
-    const int img = blockIdx.x * blockDim.x + threadIdx.x;
-    if( img >= v.noi )
+    const int img = blockIdx.x * blockDim.x + threadIdx.x; // local image; types are indexed locally
+    if( img >= v.n_local )
         return;
+    const int g = v.i_begin + img;
     double ct = 0, zero = 0;
-    if( img == 0 || img == v.noi - 1 || types.type[img] == 3 )
+    if( g == 0 || g == v.noi - 1 || types.type[img] == 3 )
         zero = 1;
     else
     {
-        const double tt = slot( v, S_TT )[img], ft = slot( v, S_FT )[img];
+        const double tt = slot( v, S_TT )[g], ft = slot( v, S_FT )[g];
         const double * Rx = slot( v, S_RX );
         if( types.type[img] == 1 ) // climbing: invert the component along the tangent
             ct = -2.0 * ft / tt;
         else if( types.type[img] == 2 ) // falling: gradient force only
             ct = 0;
         else // normal: orthogonal to the tangent + spring force along it
-            ct = -ft / tt + spring_constant * ( Rx[img + 1] - 2 * Rx[img] + Rx[img - 1] ) / sqrt( tt );
+            ct = -ft / tt + spring_constant * ( Rx[g + 1] - 2 * Rx[g] + Rx[g - 1] ) / sqrt( tt );
     }
-    slot( v, S_CT )[img]   = ct;
-    slot( v, S_ZERO )[img] = zero;
+    slot( v, S_CT )[g]   = ct;
+    slot( v, S_ZERO )[g] = zero;
 }
 
 // Total force of a site from the effective field, the tangent and the image coefficients
 __device__ __forceinline__ D3 chain_total_force( const ChainView & v, int img, std::size_t idx, const D3 & s )
 {
-    if( slot( v, S_ZERO )[img] != 0.0 )
+    const int g = v.i_begin + img;
+    if( slot( v, S_ZERO )[g] != 0.0 )
         return make_d3( 0, 0, 0 );
     const D3 Fg     = load3( cfield( v.Fg, v.stride, img ), idx );
     const D3 t      = load3( cfield( v.T, v.stride, img ), idx );
     const double d  = dot3( Fg, s );
-    const double ct = slot( v, S_CT )[img];
+    const double ct = slot( v, S_CT )[g];
     return make_d3( Fg.x - d * s.x + ct * t.x, Fg.y - d * s.y + ct * t.y, Fg.z - d * s.z + ct * t.z );
 }
 
@@ -302,10 +312,10 @@ static __global__ void __launch_bounds__( BLOCK_THREADS ) k_chain_vp_a(
     }
     proj = block_sum( proj );
     if( threadIdx.x == 0 )
-        partials[( std::size_t( 0 ) * v.noi + img ) * nblocks + blockIdx.x] = proj;
+        partials[( std::size_t( 0 ) * v.n_local + img ) * nblocks + blockIdx.x] = proj;
     norm2 = block_sum( norm2 );
     if( threadIdx.x == 0 )
-        partials[( std::size_t( 1 ) * v.noi + img ) * nblocks + blockIdx.x] = norm2;
+        partials[( std::size_t( 1 ) * v.n_local + img ) * nblocks + blockIdx.x] = norm2;
 }
 
 // sums over images -> ratio (Solver_VP.hpp:75-103)
@@ -368,7 +378,8 @@ static __global__ void __launch_bounds__( BLOCK_THREADS ) k_chain_stage(
     Site site;
     if( !locate_site( p, lg, site, p.NB ) )
         return;
-    const bool end = img == 0 || img == v.noi - 1;
+    const int g    = v.i_begin + img;
+    const bool end = g == 0 || g == v.noi - 1;
     const D3 s     = load3( cfield( v.S, v.stride, img ), site.idx );
     D3 acc         = make_d3( 0, 0, 0 );
     if( STAGE == 1 )
@@ -456,37 +467,46 @@ struct DeviceChainBuffers
     }
 };
 
-DeviceChain::DeviceChain( const Geometry & geometry, int noi ) : noi_( noi )
+DeviceChain::DeviceChain( const Geometry & geometry, int noi, int i_begin, int noi_global )
+        : noi_( noi ), i_begin_( i_begin ), noi_global_( noi_global < 0 ? noi : noi_global )
 {
     require_device();
-    if( noi > 256 )
+    if( noi_global_ > 256 )
         throw std::runtime_error( "spirit_b200: chains of more than 256 images are not supported" );
+    sharded_ = noi_global_ != noi_;
+    if( sharded_ && !comm_active() )
+        throw std::runtime_error( "spirit_b200: a sharded chain needs an initialised communicator (SpiritB200_Comm_Init)" );
+    if( i_begin_ < 0 || i_begin_ + noi_ > noi_global_ )
+        throw std::runtime_error( "spirit_b200: chain shard outside of the global chain" );
     table_ = std::make_unique<DeviceImage>( geometry );
     nos_   = table_->nos();
     buf_   = std::make_unique<DeviceChainBuffers>();
     auto & b       = *buf_;
     const auto & T = *table_->buffers();
     b.stride       = 3 * T.n_storage;
-    b.n_scal       = std::size_t( S_N_SLOTS ) * noi + G_N;
+    b.n_scal       = std::size_t( S_N_SLOTS ) * noi_global_ + G_N;
+    // every field holds the local images plus one halo image on each side (neighbour images of the adjacent ranks)
+    const std::size_t fs = std::size_t( noi + 2 ) * b.stride;
     SB_CUDA_CHECK( cudaStreamCreateWithFlags( &b.stream, cudaStreamNonBlocking ) );
-    SB_CUDA_CHECK( cudaMalloc( &b.fields, 7 * std::size_t( noi ) * b.stride * sizeof( double ) ) );
-    SB_CUDA_CHECK( cudaMemset( b.fields, 0, 7 * std::size_t( noi ) * b.stride * sizeof( double ) ) );
+    SB_CUDA_CHECK( cudaMalloc( &b.fields, 7 * fs * sizeof( double ) ) );
+    SB_CUDA_CHECK( cudaMemset( b.fields, 0, 7 * fs * sizeof( double ) ) );
     SB_CUDA_CHECK( cudaMalloc( &b.partials, 2 * std::size_t( noi ) * T.nblocks * sizeof( double ) ) );
     SB_CUDA_CHECK( cudaMalloc( &b.scal, b.n_scal * sizeof( double ) ) );
     SB_CUDA_CHECK( cudaMemset( b.scal, 0, b.n_scal * sizeof( double ) ) );
     SB_CUDA_CHECK( cudaHostAlloc( &b.h_scal, b.n_scal * sizeof( double ), cudaHostAllocDefault ) );
     SB_CUDA_CHECK( cudaMalloc( &b.staging, 3 * std::size_t( nos_ ) * sizeof( double ) ) );
-    const std::size_t fs = std::size_t( noi ) * b.stride;
-    b.view.S             = b.fields + 0 * fs;
-    b.view.P             = b.fields + 1 * fs;
-    b.view.Fg            = b.fields + 2 * fs;
-    b.view.T             = b.fields + 3 * fs;
-    b.view.F             = b.fields + 4 * fs;
-    b.view.F2            = b.fields + 5 * fs;
-    b.view.Fpr           = b.fields + 6 * fs;
-    b.view.stride        = b.stride;
-    b.view.scal          = b.scal;
-    b.view.noi           = noi;
+    b.view.S       = b.fields + 0 * fs + b.stride; // + stride: local image 0 (index -1 is the lower halo image)
+    b.view.P       = b.fields + 1 * fs + b.stride;
+    b.view.Fg      = b.fields + 2 * fs + b.stride;
+    b.view.T       = b.fields + 3 * fs + b.stride;
+    b.view.F       = b.fields + 4 * fs + b.stride;
+    b.view.F2      = b.fields + 5 * fs + b.stride;
+    b.view.Fpr     = b.fields + 6 * fs + b.stride;
+    b.view.stride  = b.stride;
+    b.view.scal    = b.scal;
+    b.view.noi     = noi_global_;
+    b.view.n_local = noi_;
+    b.view.i_begin = i_begin_;
 }
 
 DeviceChain::~DeviceChain() = default;
@@ -549,8 +569,31 @@ void DeviceChain::vp_reset()
     SB_CUDA_CHECK( cudaMemsetAsync( b.view.F, 0, fs, b.stream ) );
     SB_CUDA_CHECK( cudaMemsetAsync( b.view.F2, 0, fs, b.stream ) );
     SB_CUDA_CHECK( cudaMemsetAsync( b.view.Fpr, 0, fs, b.stream ) );
-    SB_CUDA_CHECK( cudaMemsetAsync( b.scal + std::size_t( S_N_SLOTS ) * noi_, 0, G_N * sizeof( double ), b.stream ) );
+    SB_CUDA_CHECK( cudaMemsetAsync( b.scal + std::size_t( S_N_SLOTS ) * noi_global_, 0, G_N * sizeof( double ), b.stream ) );
     vp_prev_projected_ = false;
+}
+
+// Sharded chain: the first / last local image of `field` goes to the lower / upper rank, whose last / first image arrives
+// in the halo slots (local index -1 / n_local). A chain is open: the end ranks have one neighbour only.
+void DeviceChain::exchange_halo_images( double * field_base )
+{
+    if( !sharded_ )
+        return;
+    auto & b          = *buf_;
+    const int rank = comm_rank(), world = comm_world();
+    const int lower = rank > 0 ? rank - 1 : -1, upper = rank < world - 1 ? rank + 1 : -1;
+    comm_sendrecv(
+        field_base, field_base + b.stride * ( noi_ - 1 ), field_base - std::ptrdiff_t( b.stride ), field_base + b.stride * noi_, b.stride,
+        lower, upper, b.stream );
+}
+
+// rows [slot][local image] written by a reduction -> every rank gets the values of ALL images
+void DeviceChain::share_slots( int first_slot, int n_slots, bool max )
+{
+    if( !sharded_ )
+        return;
+    auto & b = *buf_;
+    comm_allreduce( b.scal + std::size_t( first_slot ) * noi_global_, std::size_t( n_slots ) * noi_global_, max, b.stream );
 }
 
 // which_configuration: 0 = S, 1 = P. Leaves F_g, T and the per-image coefficients on the device.
@@ -559,23 +602,44 @@ void DeviceChain::evaluate_force( const GNEBParams & params, int which_configura
     auto & b          = *buf_;
     const auto & T    = *table_->buffers();
     const auto & p    = table_->stencil();
-    const double * cf = which_configuration == 0 ? b.view.S : b.view.P;
+    double * cf       = which_configuration == 0 ? b.view.S : b.view.P;
     const dim3 grid( T.nblocks, noi_ );
+    exchange_halo_images( cf );
     if( p.NB == 1 )
         k_chain_gradient<1><<<grid, BLOCK_THREADS, 0, b.stream>>>( p, T.lg, b.view, cf, b.partials, T.nblocks );
     else
         k_chain_gradient<0><<<grid, BLOCK_THREADS, 0, b.stream>>>( p, T.lg, b.view, cf, b.partials, T.nblocks );
-    // rows [0, noi) -> E, rows [noi, 2 noi) -> D2 (adjacent slots)
-    k_reduce_rows<<<2 * noi_, BLOCK_THREADS, 0, b.stream>>>( b.partials, T.nblocks, b.scal + std::size_t( S_E ) * noi_ );
+    // two adjacent slots (E, D2): rows [slot][local image] -> scal[slot][i_begin + image]
+    reduce_to_slots( S_E, 2, false );
     k_chain_rx<<<1, 1, 0, b.stream>>>( b.view );
     k_chain_tangent<<<grid, BLOCK_THREADS, 0, b.stream>>>( p, T.lg, b.view, cf, b.partials, T.nblocks );
-    k_reduce_rows<<<2 * noi_, BLOCK_THREADS, 0, b.stream>>>( b.partials, T.nblocks, b.scal + std::size_t( S_TT ) * noi_ );
+    reduce_to_slots( S_TT, 2, false );
     ChainTypes types{};
     for( int i = 0; i < noi_; ++i )
         types.type[i] = i < int( params.image_type.size() ) ? params.image_type[i] : 0;
     k_chain_coeffs<<<( noi_ + 63 ) / 64, 64, 0, b.stream>>>( b.view, types, params.spring_constant );
     launches_ += 6;
     SB_CUDA_CHECK( cudaGetLastError() );
+}
+
+// partial rows [n_slots][n_local][nblocks] -> slots first_slot .. first_slot + n_slots - 1, entries of the local images;
+// sharded: zero the rest and all-reduce so that every rank holds all images' values
+void DeviceChain::reduce_to_slots( int first_slot, int n_slots, bool max )
+{
+    auto & b       = *buf_;
+    const auto & T = *table_->buffers();
+    if( sharded_ )
+        SB_CUDA_CHECK( cudaMemsetAsync( b.scal + std::size_t( first_slot ) * noi_global_, 0, std::size_t( n_slots ) * noi_global_ * sizeof( double ), b.stream ) );
+    for( int k = 0; k < n_slots; ++k )
+    {
+        double * out          = b.scal + std::size_t( first_slot + k ) * noi_global_ + i_begin_;
+        const double * rows   = b.partials + std::size_t( k ) * noi_ * T.nblocks;
+        if( max )
+            k_reduce_rows_max<<<noi_, BLOCK_THREADS, 0, b.stream>>>( rows, T.nblocks, out );
+        else
+            k_reduce_rows<<<noi_, BLOCK_THREADS, 0, b.stream>>>( rows, T.nblocks, out );
+    }
+    share_slots( first_slot, n_slots, max );
 }
 
 namespace
@@ -609,12 +673,12 @@ void DeviceChain::iterate( int solver, const GNEBParams & params, int n_iteratio
             evaluate_force( params, 0, 0 );
             const double * F_prev = vp_prev_projected_ ? b.view.Fpr : b.view.F;
             k_chain_vp_a<<<grid, BLOCK_THREADS, 0, b.stream>>>( p, T.lg, b.view, F_prev, b.partials, T.nblocks );
-            k_reduce_rows<<<2 * noi_, BLOCK_THREADS, 0, b.stream>>>( b.partials, T.nblocks, b.scal + std::size_t( S_VP ) * noi_ );
+            reduce_to_slots( S_VP, 2, false );
             k_chain_vp_ratio<<<1, 1, 0, b.stream>>>( b.view );
             if( hk )
             {
                 k_chain_vp_b<true><<<grid, BLOCK_THREADS, 0, b.stream>>>( p, T.lg, b.view, params.dt, b.partials, T.nblocks );
-                k_reduce_rows_max<<<noi_, BLOCK_THREADS, 0, b.stream>>>( b.partials, T.nblocks, b.scal + std::size_t( S_TQ ) * noi_ );
+                reduce_to_slots( S_TQ, 1, true );
                 ++launches_;
             }
             else
@@ -640,7 +704,7 @@ void DeviceChain::iterate( int solver, const GNEBParams & params, int n_iteratio
             if( hk )
             {
                 k_chain_hook<<<grid, BLOCK_THREADS, 0, b.stream>>>( p, T.lg, b.view, b.partials, T.nblocks );
-                k_reduce_rows_max<<<noi_, BLOCK_THREADS, 0, b.stream>>>( b.partials, T.nblocks, b.scal + std::size_t( S_TQ ) * noi_ );
+                reduce_to_slots( S_TQ, 1, true );
                 launches_ += 2;
             }
         }
@@ -652,7 +716,7 @@ void DeviceChain::iterate( int solver, const GNEBParams & params, int n_iteratio
         SB_CUDA_CHECK( cudaStreamSynchronize( b.stream ) );
         if( result )
         {
-            auto get = [&]( int s, int i ) { return b.h_scal[std::size_t( s ) * noi_ + i]; };
+            auto get = [&]( int s, int i ) { return b.h_scal[std::size_t( s ) * noi_global_ + i_begin_ + i]; };
             result->energy.assign( noi_, 0.0 );
             result->Rx.assign( noi_, 0.0 );
             result->max_torque.assign( noi_, 0.0 );
@@ -665,7 +729,11 @@ void DeviceChain::iterate( int solver, const GNEBParams & params, int n_iteratio
                 const double tt       = get( S_TT, i );
                 result->dE_dRx[i]     = tt > 0 ? get( S_FT, i ) / std::sqrt( tt ) : 0.0;
             }
-            result->degenerate = b.h_scal[std::size_t( S_N_SLOTS ) * noi_ + G_DEGENERATE] != 0.0;
+            result->degenerate = b.h_scal[std::size_t( S_N_SLOTS ) * noi_global_ + G_DEGENERATE] != 0.0;
+            // convergence is decided on the whole chain, identically on every rank
+            result->max_torque_chain = 0;
+            for( int i = 0; i < noi_global_; ++i )
+                result->max_torque_chain = std::max( result->max_torque_chain, std::sqrt( b.h_scal[std::size_t( S_TQ ) * noi_global_ + i] ) );
         }
     }
 }

@@ -188,6 +188,30 @@ bool comm_active()
 {
     return g_nccl.comm != nullptr;
 }
+void comm_sendrecv(
+    const double * send_low, const double * send_high, double * recv_low, double * recv_high, std::size_t count, int lower, int upper,
+    void * stream )
+{
+    if( !g_nccl.comm )
+        throw std::runtime_error( "spirit_b200: communicator not initialised" );
+    cudaStream_t st = cudaStream_t( stream );
+    nccl_check( g_nccl.GroupStart(), "ncclGroupStart" );
+    if( lower >= 0 )
+        nccl_check( g_nccl.Send( send_low, count, NCCL_FLOAT64, lower, g_nccl.comm, st ), "ncclSend" );
+    if( upper >= 0 )
+        nccl_check( g_nccl.Send( send_high, count, NCCL_FLOAT64, upper, g_nccl.comm, st ), "ncclSend" );
+    if( upper >= 0 )
+        nccl_check( g_nccl.Recv( recv_high, count, NCCL_FLOAT64, upper, g_nccl.comm, st ), "ncclRecv" );
+    if( lower >= 0 )
+        nccl_check( g_nccl.Recv( recv_low, count, NCCL_FLOAT64, lower, g_nccl.comm, st ), "ncclRecv" );
+    nccl_check( g_nccl.GroupEnd(), "ncclGroupEnd" );
+}
+void comm_allreduce( double * data, std::size_t count, bool max, void * stream )
+{
+    if( !g_nccl.comm )
+        throw std::runtime_error( "spirit_b200: communicator not initialised" );
+    nccl_check( g_nccl.AllReduce( data, data, count, NCCL_FLOAT64, max ? NCCL_MAX : NCCL_SUM, g_nccl.comm, cudaStream_t( stream ) ), "ncclAllReduce" );
+}
 int comm_rank()
 {
     return g_nccl.rank;

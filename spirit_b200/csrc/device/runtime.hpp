@@ -40,6 +40,11 @@ void host_free( void * ptr, bool pinned );
 void comm_unique_id( char id[128] );
 void comm_init( int rank, int world, const char id[128] );
 bool comm_active();
+// low-level helpers on the process-wide communicator (stream = cudaStream_t): neighbour exchange of `count` doubles
+// (send_low -> rank `lower`, send_high -> rank `upper`, receive into recv_low / recv_high; a negative rank = no
+// neighbour) and an in-place all-reduce (sum or max) of `count` doubles
+void comm_sendrecv( const double * send_low, const double * send_high, double * recv_low, double * recv_high, std::size_t count, int lower, int upper, void * stream );
+void comm_allreduce( double * data, std::size_t count, bool max, void * stream );
 int comm_rank();
 int comm_world();
 
@@ -164,7 +169,8 @@ struct GNEBParams
 struct ChainHookResult
 {
     bool degenerate = false; // two neighbouring images coincide (Method_GNEB.cpp:119-126)
-    std::vector<double> energy, Rx, max_torque, dE_dRx;
+    std::vector<double> energy, Rx, max_torque, dE_dRx; // of the local images
+    double max_torque_chain = 0;                         // over ALL images of the (possibly sharded) chain
 };
 
 // HBM-resident state of a whole chain of images (GNEB): every field is one contiguous allocation [noi][field] and the
@@ -173,7 +179,9 @@ struct DeviceChainBuffers;
 class DeviceChain
 {
 public:
-    DeviceChain( const Geometry & geometry, int noi );
+    // noi: images held by this process. Sharded over several GPUs (one process each): they are the images
+    // [i_begin, i_begin + noi) of a chain of noi_global images; neighbouring ranks hold the neighbouring images.
+    DeviceChain( const Geometry & geometry, int noi, int i_begin = 0, int noi_global = -1 );
     ~DeviceChain();
     DeviceChain( const DeviceChain & )             = delete;
     DeviceChain & operator=( const DeviceChain & ) = delete;
@@ -200,8 +208,12 @@ public:
 
 private:
     void evaluate_force( const GNEBParams & params, int which_configuration, int which_force );
+    void exchange_halo_images( double * field_base );
+    void share_slots( int first_slot, int n_slots, bool max );
+    void reduce_to_slots( int first_slot, int n_slots, bool max );
 
-    int noi_ = 0, nos_ = 0;
+    int noi_ = 0, nos_ = 0, i_begin_ = 0, noi_global_ = 0;
+    bool sharded_ = false;
     std::unique_ptr<DeviceImage> table_; // owns the stencil tables (shared Hamiltonian)
     std::unique_ptr<DeviceChainBuffers> buf_;
     std::uint64_t launches_  = 0;

@@ -62,11 +62,67 @@ def main():
                 if not ok:
                     failures.append((bc_c, solver, temperature))
                 g.close()
+    failures += gneb_sharded(lib, rank, world, tmp)
     dist.barrier()
     if rank == 0:
         print("MGPU_FAILURES %d" % len(failures), flush=True)
     dist.destroy_process_group()
     sys.exit(1 if failures else 0)
+
+
+def gneb_sharded(lib, rank, world, tmp):
+    """whole GNEB images per GPU: 8 images over `world` ranks vs the same chain on one GPU"""
+    from tests.test_gneb_gpu import make_chain
+    failures = []
+    noi = 8
+    path = os.path.join(tmp, "gneb_%d.cfg" % rank)
+    open(path, "w").write(cfgs.render("solvers", n_basis_cells="12 10 1", boundary_conditions="1 0 0"))
+    # every rank builds the full initial chain on the host (cheap) and keeps its shard
+    full = S.Session(lib, path)
+    make_chain(full, noi=noi)
+    images0 = [full.spins(i).copy() for i in range(noi)]
+    full.close()
+    i_begin, n_local = slab.partition(noi, world)[rank]
+    for solver, n, types in (("VP", 30, {3: S.GNEB_CLIMBING}), ("Depondt", 8, {2: S.GNEB_FALLING, 5: S.GNEB_CLIMBING}), ("Heun", 8, {})):
+        p = S.Session(lib, path)
+        p.set_anisotropy(0.25, (0, 0, 1))
+        p.chain_set_length(n_local)
+        for i in range(n_local):
+            p.set_spins(images0[i_begin + i], idx_image=i)
+        for g, t in types.items():
+            if i_begin <= g < i_begin + n_local:
+                p.gneb_set_image_type(t, g - i_begin)
+        assert lib.SpiritB200_Chain_Shard_Setup(p.state, i_begin, noi) == 0
+        p.gneb_start(S.SOLVERS[solver], single_shot=True)
+        p.n_shot(n)
+        mine = np.stack([p.spins(i).copy() for i in range(n_local)])
+        rx, e = p.chain_rx_e()
+        tq = p.chain_max_torque()
+        p.stop()
+        p.close()
+        parts = [None] * world
+        dist.all_gather_object(parts, (mine, rx, e, tq))
+        if rank == 0:
+            g = S.Session(lib, path)
+            make_chain(g, noi=noi)
+            for gi, t in types.items():
+                g.gneb_set_image_type(t, gi)
+            g.gneb_start(S.SOLVERS[solver], single_shot=True)
+            g.n_shot(n)
+            ref = np.stack([g.spins(i).copy() for i in range(noi)])
+            rx_ref, e_ref = g.chain_rx_e()
+            tq_ref = g.chain_max_torque()
+            g.stop()
+            g.close()
+            dev = np.abs(np.concatenate([x[0] for x in parts]) - ref).max()
+            drx = np.abs(np.concatenate([x[1] for x in parts]) - rx_ref).max()
+            de = np.abs(np.concatenate([x[2] for x in parts]) - e_ref).max()
+            dtq = max(abs(x[3] - tq_ref) for x in parts)
+            ok = dev <= 1e-13 and drx <= 1e-12 and de <= 1e-10 and dtq <= 1e-12 * tq_ref
+            print("GNEB sharded %-8s: spins %.3e Rx %.3e E %.3e torque %.3e %s" % (solver, dev, drx, de, dtq, "OK" if ok else "FAIL"), flush=True)
+            if not ok:
+                failures.append(("gneb", solver))
+    return failures
 
 
 if __name__ == "__main__":
