@@ -655,7 +655,7 @@ void DeviceImage::set_hamiltonian( const Hamiltonian & ham )
     else if( ham.ddi_method != DDI_Method::None )
         throw std::runtime_error( "spirit_b200: only ddi_method none/fft are in scope (SURVEY.md 2.2): the reference's cutoff / direct sums are oracle-side ground truth" );
 
-    p.sc6_extras  = ( p.has_cubic || p.has_ddi ) ? 1 : 0;
+    p.sc6_extras  = ( p.has_cubic || p.has_ddi || p.sc6_aniso_full ) ? 1 : 0;
     ham_revision_ = ham.revision;
 }
 
@@ -866,7 +866,7 @@ void launch_stage(
     bool nb1, bool hook, int nblocks, cudaStream_t stream, const StencilParams & p, const LaunchGeom & lg, const LLGParams & l,
     const StageArgs & a, const SC6Launch & sc6, DeviceImage & image, void * out )
 {
-    if( p.sc6 && !hook )
+    if( p.sc6 && !hook && !l.has_stt )
     {
         // nearest-neighbour structure: marching kernel (the hook iteration, which also stores F, Fv and reduces the
         // energy, goes through the generic kernel)

@@ -236,3 +236,29 @@ def test_thermal_langevin_known_answer(cfg, product):
         err = means.std(ddof=1) / np.sqrt(len(means))
         assert abs(means.mean() - expected) < max(4 * err, 0.01), (solver, means.mean(), expected, err)
         p.close()
+
+
+@pytest.mark.parametrize("solver", ["Depondt", "SIB", "Heun"])
+def test_thermal_averages_match_reference_within_error_bars(cfg, product, oracle, solver):
+    """BASELINE.json: at T > 0, time-averaged magnetisation and energy must agree within statistical error bars.
+    Interacting system (J, D, K, B, T = 40 K on 16x16x8), independent noise streams (reference: serial mt19937; here:
+    Philox), 3000 equilibration steps, then 30 block averages of 300 steps each. Error bars from the scatter of the
+    blocks; the two means must agree within 4 combined standard errors."""
+    path = cfg("cubic256", n_basis_cells="16 16 8", llg_temperature=40, llg_n_iterations_amortize=50, external_field_magnitude=5)
+    stats = []
+    for lib in (product, oracle):
+        x = S.Session(lib, path)
+        x.plus_z()
+        x.llg_start(S.SOLVERS[solver], n_iterations=3000, n_iterations_log=3000)
+        m, e = [], []
+        for _ in range(30):
+            x.llg_start(S.SOLVERS[solver], n_iterations=300, n_iterations_log=300)
+            m.append(x.spins()[:, 2].mean())
+            x.update_data()
+            e.append(x.energy() / x.nos)
+        stats.append((np.mean(m), np.std(m, ddof=1) / np.sqrt(len(m)), np.mean(e), np.std(e, ddof=1) / np.sqrt(len(e))))
+        x.close()
+    (mp, dmp, ep, dep), (mo, dmo, eo, deo) = stats
+    assert 0.5 < mo < 0.99  # thermally disordered but not paramagnetic: the comparison is meaningful
+    assert abs(mp - mo) < 4 * np.hypot(dmp, dmo), (solver, mp, dmp, mo, dmo)
+    assert abs(ep - eo) < 4 * np.hypot(dep, deo), (solver, ep, dep, eo, deo)
