@@ -166,7 +166,16 @@ struct PassArgs
     std::size_t in_os, in_js, out_os, out_js;
     int n_u, n_o, n_in, n_out, ncol;
     double scale;
+    // optional blocked layout of the transform index j on the input / output side: element j lives at
+    // (j / split) * split_stride + (j % split) * js. Used by the distributed convolution, where the kb axis is cut into
+    // per-rank blocks so that the all-to-all moves one contiguous block per peer.
+    int in_split, out_split;
+    std::size_t in_split_stride, out_split_stride;
 };
+__device__ __forceinline__ std::size_t pass_offset( int j, std::size_t js, int split, std::size_t split_stride )
+{
+    return split ? std::size_t( j / split ) * split_stride + std::size_t( j % split ) * js : std::size_t( j ) * js;
+}
 
 template<bool INVERSE>
 static __global__ void __launch_bounds__( FFT_THREADS ) k_fft_pass( const __grid_constant__ FFTPlan1D plan, const __grid_constant__ PassArgs a )
@@ -183,7 +192,7 @@ static __global__ void __launch_bounds__( FFT_THREADS ) k_fft_pass( const __grid
         const int col = item % a.ncol, j = item / a.ncol;
         double2 v     = make_double2( 0.0, 0.0 );
         if( j < a.n_in && col < nc )
-            v = a.in[std::size_t( o ) * a.in_os + std::size_t( j ) * a.in_js + u0 + col];
+            v = a.in[std::size_t( o ) * a.in_os + pass_offset( j, a.in_js, a.in_split, a.in_split_stride ) + u0 + col];
         x[item] = v;
     }
     __syncthreads();
@@ -194,7 +203,8 @@ static __global__ void __launch_bounds__( FFT_THREADS ) k_fft_pass( const __grid
         if( col < nc )
         {
             const double2 v = r[item];
-            a.out[std::size_t( o ) * a.out_os + std::size_t( j ) * a.out_js + u0 + col] = make_double2( a.scale * v.x, a.scale * v.y );
+            a.out[std::size_t( o ) * a.out_os + pass_offset( j, a.out_js, a.out_split, a.out_split_stride ) + u0 + col]
+                = make_double2( a.scale * v.x, a.scale * v.y );
         }
     }
 }
@@ -227,7 +237,16 @@ struct DDIDims
     int lookup[MAX_BASIS * MAX_BASIS]; // inter-sublattice index of (b1, b2)  (Hamiltonian_Heisenberg.cpp:1418-1428)
     int plane_stride, halo;
     double mu_s[MAX_BASIS];
+    // layout of the c-pass operand: element (q, c, kb, ka) at
+    //   (c / c_block) * block_stride + q * q_stride + (c % c_block) * Pb * Ha + kb * Ha + ka
+    // single device: c_block = Nc, q_stride = Nc Pb Ha (plain [q][c][kb][ka]); distributed: one block per source rank
+    int c_block;
+    std::size_t block_stride, q_stride;
 };
+__device__ __forceinline__ std::size_t c_operand( const DDIDims & d, int q, int c )
+{
+    return std::size_t( c / d.c_block ) * d.block_stride + std::size_t( q ) * d.q_stride + std::size_t( c % d.c_block ) * ( std::size_t( d.Pb ) * d.Ha );
+}
 
 // 1: forward a-pass straight from the spin field. One CTA per (row = b + Nb c, component q = comp + 3 ib).
 static __global__ void __launch_bounds__( FFT_THREADS ) k_ddi_fwd_a(
@@ -287,7 +306,7 @@ static __global__ void __launch_bounds__( FFT_THREADS ) k_ddi_c_mult(
             const int col = item % ncol, j = item / ncol;
             double2 v     = make_double2( 0.0, 0.0 );
             if( j < d.Nc && col < nc )
-                v = B[( std::size_t( q ) * d.Nc + j ) * c_stride + std::size_t( kb ) * d.Ha + u0 + col];
+                v = B[c_operand( d, q, j ) + std::size_t( kb ) * d.Ha + u0 + col];
             x[item] = v;
         }
     }
@@ -342,7 +361,7 @@ static __global__ void __launch_bounds__( FFT_THREADS ) k_ddi_c_mult(
         {
             const int col = item % ncol, j = item / ncol;
             if( col < nc )
-                B[( std::size_t( q ) * d.Nc + j ) * c_stride + std::size_t( kb ) * d.Ha + u0 + col] = r[item];
+                B[c_operand( d, q, j ) + std::size_t( kb ) * d.Ha + u0 + col] = r[item];
         }
         __syncthreads();
     }
@@ -442,9 +461,9 @@ static __global__ void __launch_bounds__( 128 ) k_ddi_c_mult_small(
     for( int j = 0; j < PC; ++j )
     {
         const double2 zero = make_double2( 0.0, 0.0 );
-        sx[j] = j < d.Nc ? B[( std::size_t( 0 ) * d.Nc + j ) * c_stride + col] : zero;
-        sy[j] = j < d.Nc ? B[( std::size_t( 1 ) * d.Nc + j ) * c_stride + col] : zero;
-        sz[j] = j < d.Nc ? B[( std::size_t( 2 ) * d.Nc + j ) * c_stride + col] : zero;
+        sx[j] = j < d.Nc ? B[c_operand( d, 0, j ) + col] : zero;
+        sy[j] = j < d.Nc ? B[c_operand( d, 1, j ) + col] : zero;
+        sz[j] = j < d.Nc ? B[c_operand( d, 2, j ) + col] : zero;
     }
     reg_fft<PC, false>( sx );
     reg_fft<PC, false>( sy );
@@ -483,9 +502,9 @@ static __global__ void __launch_bounds__( 128 ) k_ddi_c_mult_small(
     for( int j = 0; j < PC; ++j )
         if( j < d.Nc )
         {
-            B[( std::size_t( 0 ) * d.Nc + j ) * c_stride + col] = sx[j];
-            B[( std::size_t( 1 ) * d.Nc + j ) * c_stride + col] = sy[j];
-            B[( std::size_t( 2 ) * d.Nc + j ) * c_stride + col] = sz[j];
+            B[c_operand( d, 0, j ) + col] = sx[j];
+            B[c_operand( d, 1, j ) + col] = sy[j];
+            B[c_operand( d, 2, j ) + col] = sz[j];
         }
 }
 
@@ -631,7 +650,11 @@ std::vector<int> factorize( int n )
 // ---------------------------------------------------------------------------------------------
 struct DDIPlan
 {
-    DDIDims dims{};
+    DDIDims dims{};   // local planes: a- and b-passes
+    DDIDims dims_g{}; // global lattice: tensor setup
+    DDIDims dims_c{}; // c-pass operand: all planes, local kb range
+    int world = 1, rank = 0;
+    double2 * C = nullptr; // distributed: the c-pass operand after the all-to-all
     FFTPlan1D plan[3]; // a, b, c
     double2 * twiddle[3] = { nullptr, nullptr, nullptr };
     double2 * Dhat       = nullptr; // complex tensor spectrum, or
@@ -655,6 +678,8 @@ struct DDIPlan
             cudaFree( A );
         if( B )
             cudaFree( B );
+        if( C )
+            cudaFree( C );
     }
 };
 
@@ -692,6 +717,8 @@ int choose_ncol( int n, int n_components, int n_u )
     const std::size_t per_col = std::size_t( n ) * 2 * sizeof( double2 ) * n_components;
     int ncol                  = int( std::min<std::size_t>( 16, std::max<std::size_t>( 1, MAX_SMEM_FFT / per_col ) ) );
     ncol                      = std::min( ncol, std::max( 1, n_u ) );
+    while( ncol & ( ncol - 1 ) ) // power of two: shift-based index arithmetic in block_fft
+        ncol &= ncol - 1;
     if( per_col > std::size_t( MAX_SMEM_FFT ) )
         throw std::runtime_error( "spirit_b200: padded lattice dimension too long for the shared-memory FFT passes" );
     return ncol;
@@ -714,13 +741,26 @@ DDIPlan * ddi_plan_create( const Hamiltonian & ham, const StencilParams & sp, cu
 {
     const Geometry & g = *ham.geometry;
     auto plan          = std::unique_ptr<DDIPlan>( new DDIPlan );
-    DDIDims & d        = plan->dims;
-    d.Na = g.n_cells[0], d.Nb = g.n_cells[1], d.Nc = g.n_cells[2], d.NB = g.n_cell_atoms;
+    // Slab decomposition (one process per GPU): this rank holds ncl = n_cells[2] planes of a lattice with Nc_global
+    // planes. The a- and b-passes run on the local planes; an all-to-all turns "my planes, all kb" into "all planes, my kb
+    // range" for the c-pass + tensor multiply, and back. The tensor spectrum is stored for the local kb range only.
+    const bool slab     = sp.halo > 0;
+    const int world     = slab ? comm_world() : 1;
+    const int rank      = slab ? comm_rank() : 0;
+    const int ncl       = g.n_cells[2];
+    const int Nc_global = slab ? sp.Nc : ncl;
+    plan->world = world, plan->rank = rank;
+    if( slab && ( Nc_global != ncl * world || sp.c_begin != rank * ncl ) )
+        throw std::runtime_error( "spirit_b200: the distributed dipole convolution needs equal slabs in rank order" );
+
+    DDIDims & d = plan->dims; // local passes (a, b)
+    d.Na = g.n_cells[0], d.Nb = g.n_cells[1], d.Nc = ncl, d.NB = g.n_cell_atoms;
+    const int N[3] = { g.n_cells[0], g.n_cells[1], Nc_global };
     int P[3];
     for( int i = 0; i < 3; ++i )
     {
-        P[i] = g.n_cells[i];
-        if( g.n_cells[i] > 1 && ( ham.boundary_conditions[i] == 0 || ham.ddi_pb_zero_padding ) )
+        P[i] = N[i];
+        if( N[i] > 1 && ( ham.boundary_conditions[i] == 0 || ham.ddi_pb_zero_padding ) )
             P[i] *= 2;
     }
     d.Pa = P[0], d.Pb = P[1], d.Pc = P[2];
@@ -741,15 +781,40 @@ DDIPlan * ddi_plan_create( const Hamiltonian & ham, const StencilParams & sp, cu
             }
             d.lookup[b1 + b2 * d.NB] = d.n_inter++;
         }
+    if( d.Pb % world != 0 )
+        throw std::runtime_error( "spirit_b200: the padded b dimension must be divisible by the number of ranks" );
+    const int kbl = d.Pb / world;
+    const int nq  = 3 * d.NB;
+    d.c_block      = d.Nc;
+    d.q_stride     = std::size_t( d.Nc ) * d.Pb * d.Ha;
+    d.block_stride = 0;
+
+    DDIDims & dg = plan->dims_g; // global lattice: the tensor
+    dg           = d;
+    dg.Nc        = Nc_global;
+    DDIDims & dc = plan->dims_c; // c-pass operand: all planes, local kb range
+    dc           = dg;
+    dc.Pb        = kbl;
+    if( world > 1 )
+    {
+        dc.c_block      = ncl;
+        dc.q_stride     = std::size_t( ncl ) * kbl * d.Ha;
+        dc.block_stride = std::size_t( nq ) * ncl * kbl * d.Ha;
+    }
+    else
+    {
+        dc.c_block  = Nc_global;
+        dc.q_stride = std::size_t( Nc_global ) * kbl * d.Ha;
+    }
 
     make_plan_1d( plan->plan[0], plan->twiddle[0], d.Pa );
     make_plan_1d( plan->plan[1], plan->twiddle[1], d.Pb );
     make_plan_1d( plan->plan[2], plan->twiddle[2], d.Pc );
     plan->ncol_b = choose_ncol( d.Pb, 1, d.Ha );
-    plan->ncol_c = choose_ncol( d.Pc, 3 * d.NB, d.Ha );
+    plan->ncol_c = choose_ncol( d.Pc, nq, d.Ha );
     plan->smem_a = std::size_t( d.Pa ) * 2 * sizeof( double2 );
     plan->smem_b = std::size_t( d.Pb ) * 2 * sizeof( double2 ) * plan->ncol_b;
-    plan->smem_c = std::size_t( d.Pc ) * 2 * sizeof( double2 ) * plan->ncol_c * 3 * d.NB;
+    plan->smem_c = std::size_t( d.Pc ) * 2 * sizeof( double2 ) * plan->ncol_c * nq;
     if( plan->smem_a > std::size_t( MAX_SMEM_FFT ) )
         throw std::runtime_error( "spirit_b200: padded lattice dimension a too long for the shared-memory FFT passes" );
     allow_smem( k_ddi_fwd_a, plan->smem_a );
@@ -759,17 +824,23 @@ DDIPlan * ddi_plan_create( const Hamiltonian & ham, const StencilParams & sp, cu
     allow_smem( k_fft_pass<true>, plan->smem_b );
     allow_smem( k_ddi_c_mult, plan->smem_c );
 
-    const std::size_t half = std::size_t( d.Pc ) * d.Pb * d.Ha;
-    const std::size_t full = std::size_t( d.Pc ) * d.Pb * d.Pa;
-    SB_CUDA_CHECK( cudaMalloc( &plan->Dhat, std::size_t( 6 * d.n_inter ) * half * sizeof( double2 ) ) );
-    SB_CUDA_CHECK( cudaMalloc( &plan->A, std::size_t( 3 * d.NB ) * d.Nc * d.Nb * d.Ha * sizeof( double2 ) ) );
-    SB_CUDA_CHECK( cudaMalloc( &plan->B, std::size_t( 3 * d.NB ) * d.Nc * d.Pb * d.Ha * sizeof( double2 ) ) );
+    const std::size_t half       = std::size_t( d.Pc ) * d.Pb * d.Ha; // full half-spectrum of one tensor component
+    const std::size_t half_local = std::size_t( d.Pc ) * kbl * d.Ha;  // the local kb range of it
+    const std::size_t full       = std::size_t( d.Pc ) * d.Pb * d.Pa;
+    const std::size_t n_B        = std::size_t( nq ) * ncl * d.Pb * d.Ha;
+    SB_CUDA_CHECK( cudaMalloc( &plan->Dhat, std::size_t( 6 * d.n_inter ) * half_local * sizeof( double2 ) ) );
+    SB_CUDA_CHECK( cudaMalloc( &plan->A, std::size_t( nq ) * ncl * d.Nb * d.Ha * sizeof( double2 ) ) );
+    SB_CUDA_CHECK( cudaMalloc( &plan->B, n_B * sizeof( double2 ) ) );
+    if( world > 1 )
+        SB_CUDA_CHECK( cudaMalloc( &plan->C, n_B * sizeof( double2 ) ) );
 
-    // tensor spectrum, one component at a time: real D -> rows (a) -> b -> c
-    double * Dreal  = nullptr;
-    double2 * tmp1  = nullptr;
+    // tensor spectrum, one component at a time: real D -> rows (a) -> b -> c on the WHOLE padded lattice (every rank
+    // computes it redundantly: the tensor is analytic, no communication), then the local kb range is kept
+    double * Dreal = nullptr;
+    double2 *tmp1 = nullptr, *tmp2 = nullptr;
     SB_CUDA_CHECK( cudaMalloc( &Dreal, full * sizeof( double ) ) );
     SB_CUDA_CHECK( cudaMalloc( &tmp1, half * sizeof( double2 ) ) );
+    SB_CUDA_CHECK( cudaMalloc( &tmp2, half * sizeof( double2 ) ) );
     TensorGeom tg{};
     for( int k = 0; k < 3; ++k )
     {
@@ -791,19 +862,19 @@ DDIPlan * ddi_plan_create( const Hamiltonian & ham, const StencilParams & sp, cu
             tg.dc           = g.cell_atoms[b1][2] - g.cell_atoms[b2][2];
             for( int comp6 = 0; comp6 < 6; ++comp6 )
             {
-                double2 * Dout = plan->Dhat + std::size_t( 6 * inter + comp6 ) * half;
-                k_ddi_tensor<<<unsigned( ( full + 255 ) / 256 ), 256, 0, stream>>>( d, tg, comp6, Dreal );
+                double2 * Dout = plan->Dhat + std::size_t( 6 * inter + comp6 ) * half_local;
+                k_ddi_tensor<<<unsigned( ( full + 255 ) / 256 ), 256, 0, stream>>>( dg, tg, comp6, Dreal );
                 k_fft_real_rows<<<unsigned( std::size_t( d.Pb ) * d.Pc ), fft_threads( d.Pa / 4 ), plan->smem_a, stream>>>( plan->plan[0], Dreal, tmp1, d.Ha );
-                // b: tmp1[c][b][ka] -> Dout[c][kb][ka]
+                // b: tmp1[c][b][ka] -> tmp2[c][kb][ka]
                 PassArgs pb{};
-                pb.in = tmp1, pb.out = Dout;
+                pb.in = tmp1, pb.out = tmp2;
                 pb.in_os = pb.out_os = std::size_t( d.Pb ) * d.Ha;
                 pb.in_js = pb.out_js = d.Ha;
                 pb.n_u = d.Ha, pb.n_o = d.Pc, pb.n_in = d.Pb, pb.n_out = d.Pb, pb.ncol = ncol_setup, pb.scale = 1.0;
                 k_fft_pass<false><<<dim3( ( d.Ha + ncol_setup - 1 ) / ncol_setup, d.Pc ), fft_threads( d.Pb / 4 * ncol_setup ), plan->smem_b, stream>>>( plan->plan[1], pb );
-                // c: Dout[c][kb][ka] -> tmp1[kc][kb][ka]; (kb, ka) is one contiguous index of length Pb*Ha
+                // c: tmp2[c][kb][ka] -> tmp1[kc][kb][ka]; (kb, ka) is one contiguous index of length Pb*Ha
                 PassArgs pc{};
-                pc.in = Dout, pc.out = tmp1;
+                pc.in = tmp2, pc.out = tmp1;
                 pc.in_os = pc.out_os = 0;
                 pc.in_js = pc.out_js = std::size_t( d.Pb ) * d.Ha;
                 pc.n_u = d.Pb * d.Ha, pc.n_o = 1, pc.n_in = d.Pc, pc.n_out = d.Pc, pc.scale = 1.0;
@@ -811,7 +882,11 @@ DDIPlan * ddi_plan_create( const Hamiltonian & ham, const StencilParams & sp, cu
                 const std::size_t smem_c1 = std::size_t( d.Pc ) * 2 * sizeof( double2 ) * pc.ncol;
                 allow_smem( k_fft_pass<false>, std::max( plan->smem_b, smem_c1 ) );
                 k_fft_pass<false><<<dim3( ( pc.n_u + pc.ncol - 1 ) / pc.ncol, 1 ), fft_threads( std::max( 1, d.Pc / 4 ) * pc.ncol ), smem_c1, stream>>>( plan->plan[2], pc );
-                SB_CUDA_CHECK( cudaMemcpyAsync( Dout, tmp1, half * sizeof( double2 ), cudaMemcpyDeviceToDevice, stream ) );
+                // keep the local kb range: [kc][kb in range][ka]
+                SB_CUDA_CHECK( cudaMemcpy2DAsync(
+                    Dout, std::size_t( kbl ) * d.Ha * sizeof( double2 ), tmp1 + std::size_t( rank ) * kbl * d.Ha,
+                    std::size_t( d.Pb ) * d.Ha * sizeof( double2 ), std::size_t( kbl ) * d.Ha * sizeof( double2 ), d.Pc,
+                    cudaMemcpyDeviceToDevice, stream ) );
                 plan->launches_setup += 4;
             }
         }
@@ -819,11 +894,12 @@ DDIPlan * ddi_plan_create( const Hamiltonian & ham, const StencilParams & sp, cu
     SB_CUDA_CHECK( cudaStreamSynchronize( stream ) );
     cudaFree( Dreal );
     cudaFree( tmp1 );
+    cudaFree( tmp2 );
 
     // Single sublattice: D(-r) = D(r), the spectrum is real. Verify numerically, then keep only the real parts.
     if( d.NB == 1 && ( d.Pc & ( d.Pc - 1 ) ) == 0 && d.Pc <= 32 )
     {
-        const std::size_t n_all = std::size_t( 6 * d.n_inter ) * half;
+        const std::size_t n_all = std::size_t( 6 * d.n_inter ) * half_local;
         const int blocks        = 1024;
         double * part           = nullptr;
         SB_CUDA_CHECK( cudaMalloc( &part, 2 * blocks * sizeof( double ) ) );
@@ -842,7 +918,8 @@ DDIPlan * ddi_plan_create( const Hamiltonian & ham, const StencilParams & sp, cu
             std::fprintf( stderr, "spirit_b200 ddi: max |Im D^| = %.3e, max |D^| = %.3e\n", max_imag, max_abs );
         // The imaginary parts are pure round-off of the forward transforms (a few ulp of the largest element times
         // log2 P): mathematically zero. 1e-12 relative is 4 orders above what is observed and far below any signal.
-        if( max_imag <= 1e-12 * max_abs )
+        // (world > 1: every rank must take the same decision -> only for the undistributed plan.)
+        if( world == 1 && max_imag <= 1e-12 * max_abs )
         {
             SB_CUDA_CHECK( cudaMalloc( &plan->Dhat_real, n_all * sizeof( double ) ) );
             k_ddi_take_real<<<unsigned( ( n_all + 255 ) / 256 ), 256, 0, stream>>>( plan->Dhat, plan->Dhat_real, n_all );
@@ -857,30 +934,58 @@ DDIPlan * ddi_plan_create( const Hamiltonian & ham, const StencilParams & sp, cu
 // One DDI gradient evaluation: spins -> g_ddi field. Returns the number of kernels launched.
 int ddi_gradient( DDIPlan & plan, ConstField3 spins, Field3 g_ddi, cudaStream_t stream )
 {
-    const DDIDims & d = plan.dims;
-    const int rows    = d.Nb * d.Nc;
+    const DDIDims & d  = plan.dims;
+    const DDIDims & dc = plan.dims_c;
+    const int world    = plan.world;
+    const int nq       = 3 * d.NB;
+    const int kbl      = dc.Pb;
+    const int rows     = d.Nb * d.Nc;
     k_ddi_fwd_a<<<dim3( rows, d.NB ), fft_threads( d.Pa / 4 ), plan.smem_a, stream>>>( plan.plan[0], d, spins, plan.A );
-    // forward b: A[q][c][b][ka] -> B[q][c][kb][ka]; outer index o = q * Nc + c
+    // forward b: A[q][c][b][ka] -> B; outer index o = q * ncl + c. Single device: B[o][kb][ka]; distributed: the kb axis
+    // is cut into per-rank blocks, B[r][o][kb % kbl][ka], so that block r is what rank r needs
     PassArgs pb{};
     pb.in = plan.A, pb.out = plan.B;
-    pb.in_os = std::size_t( d.Nb ) * d.Ha, pb.out_os = std::size_t( d.Pb ) * d.Ha;
-    pb.in_js = pb.out_js = d.Ha;
-    pb.n_u = d.Ha, pb.n_o = 3 * d.NB * d.Nc, pb.n_in = d.Nb, pb.n_out = d.Pb, pb.ncol = plan.ncol_b, pb.scale = 1.0;
+    pb.in_os = std::size_t( d.Nb ) * d.Ha, pb.in_js = pb.out_js = d.Ha;
+    pb.out_os = std::size_t( kbl ) * d.Ha * ( world > 1 ? 1 : world );
+    if( world > 1 )
+    {
+        pb.out_split        = kbl;
+        pb.out_split_stride = dc.block_stride;
+    }
+    else
+        pb.out_os = std::size_t( d.Pb ) * d.Ha;
+    pb.n_u = d.Ha, pb.n_o = nq * d.Nc, pb.n_in = d.Nb, pb.n_out = d.Pb, pb.ncol = plan.ncol_b, pb.scale = 1.0;
     const dim3 grid_b( ( d.Ha + plan.ncol_b - 1 ) / plan.ncol_b, pb.n_o );
     k_fft_pass<false><<<grid_b, fft_threads( d.Pb / 4 * plan.ncol_b ), plan.smem_b, stream>>>( plan.plan[1], pb );
-    const bool small_c = d.NB == 1 && ( d.Pc & ( d.Pc - 1 ) ) == 0 && d.Pc <= 32;
+
+    double2 * operand = plan.B;
+    const std::size_t block_doubles = 2 * dc.block_stride; // one per-rank block, in doubles
+    if( world > 1 )
+    {
+        // all-to-all: my block r -> rank r's block (my rank): "my planes, kb range of r" becomes "planes of r, my kb range"
+        comm_group_begin();
+        for( int r = 0; r < world; ++r )
+        {
+            comm_send( reinterpret_cast<const double *>( plan.B + std::size_t( r ) * dc.block_stride ), block_doubles, r, stream );
+            comm_recv( reinterpret_cast<double *>( plan.C + std::size_t( r ) * dc.block_stride ), block_doubles, r, stream );
+        }
+        comm_group_end();
+        operand = plan.C;
+    }
+
+    const bool small_c = d.NB == 1 && ( dc.Pc & ( dc.Pc - 1 ) ) == 0 && dc.Pc <= 32;
     if( small_c )
     {
-        const dim3 grid( ( d.Ha + 127 ) / 128, d.Pb );
+        const dim3 grid( ( d.Ha + 127 ) / 128, kbl );
         const void * D = plan.Dhat_real ? static_cast<const void *>( plan.Dhat_real ) : static_cast<const void *>( plan.Dhat );
 #define SB_DDI_SMALL( PC )                                                                                             \
     case PC:                                                                                                           \
         if( plan.Dhat_real )                                                                                           \
-            k_ddi_c_mult_small<PC, true><<<grid, 128, 0, stream>>>( d, plan.B, D );                                    \
+            k_ddi_c_mult_small<PC, true><<<grid, 128, 0, stream>>>( dc, operand, D );                                  \
         else                                                                                                           \
-            k_ddi_c_mult_small<PC, false><<<grid, 128, 0, stream>>>( d, plan.B, D );                                   \
+            k_ddi_c_mult_small<PC, false><<<grid, 128, 0, stream>>>( dc, operand, D );                                 \
         break;
-        switch( d.Pc )
+        switch( dc.Pc )
         {
             SB_DDI_SMALL( 1 )
             SB_DDI_SMALL( 2 )
@@ -895,15 +1000,34 @@ int ddi_gradient( DDIPlan & plan, ConstField3 spins, Field3 g_ddi, cudaStream_t 
     {
         if( !plan.Dhat )
             throw std::logic_error( "spirit_b200: real tensor spectrum with the shared-memory multiply kernel" );
-        k_ddi_c_mult<<<dim3( ( d.Ha + plan.ncol_c - 1 ) / plan.ncol_c, d.Pb ), fft_threads( d.Pc / 4 * plan.ncol_c * 3 * d.NB ), plan.smem_c, stream>>>(
-            plan.plan[2], d, plan.B, plan.Dhat, plan.ncol_c );
+        k_ddi_c_mult<<<dim3( ( d.Ha + plan.ncol_c - 1 ) / plan.ncol_c, kbl ), fft_threads( std::max( 1, dc.Pc / 4 ) * plan.ncol_c * nq ), plan.smem_c, stream>>>(
+            plan.plan[2], dc, operand, plan.Dhat, plan.ncol_c );
     }
+
+    if( world > 1 )
+    {
+        comm_group_begin();
+        for( int r = 0; r < world; ++r )
+        {
+            comm_send( reinterpret_cast<const double *>( plan.C + std::size_t( r ) * dc.block_stride ), block_doubles, r, stream );
+            comm_recv( reinterpret_cast<double *>( plan.B + std::size_t( r ) * dc.block_stride ), block_doubles, r, stream );
+        }
+        comm_group_end();
+    }
+
     // inverse b: B -> A, keep b < Nb
     PassArgs ib{};
     ib.in = plan.B, ib.out = plan.A;
-    ib.in_os = std::size_t( d.Pb ) * d.Ha, ib.out_os = std::size_t( d.Nb ) * d.Ha;
-    ib.in_js = ib.out_js = d.Ha;
-    ib.n_u = d.Ha, ib.n_o = 3 * d.NB * d.Nc, ib.n_in = d.Pb, ib.n_out = d.Nb, ib.ncol = plan.ncol_b, ib.scale = 1.0;
+    ib.out_os = std::size_t( d.Nb ) * d.Ha, ib.in_js = ib.out_js = d.Ha;
+    if( world > 1 )
+    {
+        ib.in_os           = std::size_t( kbl ) * d.Ha;
+        ib.in_split        = kbl;
+        ib.in_split_stride = dc.block_stride;
+    }
+    else
+        ib.in_os = std::size_t( d.Pb ) * d.Ha;
+    ib.n_u = d.Ha, ib.n_o = nq * d.Nc, ib.n_in = d.Pb, ib.n_out = d.Nb, ib.ncol = plan.ncol_b, ib.scale = 1.0;
     k_fft_pass<true><<<grid_b, fft_threads( d.Pb / 4 * plan.ncol_b ), plan.smem_b, stream>>>( plan.plan[1], ib );
     const double inv_P = 1.0 / ( double( d.Pa ) * d.Pb * d.Pc );
     k_ddi_inv_a<<<dim3( rows, d.NB ), fft_threads( d.Pa / 4 ), plan.smem_a, stream>>>( plan.plan[0], d, plan.A, g_ddi, inv_P );

@@ -206,6 +206,24 @@ void comm_sendrecv(
         nccl_check( g_nccl.Recv( recv_low, count, NCCL_FLOAT64, lower, g_nccl.comm, st ), "ncclRecv" );
     nccl_check( g_nccl.GroupEnd(), "ncclGroupEnd" );
 }
+void comm_group_begin()
+{
+    if( !g_nccl.comm )
+        throw std::runtime_error( "spirit_b200: communicator not initialised" );
+    nccl_check( g_nccl.GroupStart(), "ncclGroupStart" );
+}
+void comm_group_end()
+{
+    nccl_check( g_nccl.GroupEnd(), "ncclGroupEnd" );
+}
+void comm_send( const double * data, std::size_t count, int peer, void * stream )
+{
+    nccl_check( g_nccl.Send( data, count, NCCL_FLOAT64, peer, g_nccl.comm, cudaStream_t( stream ) ), "ncclSend" );
+}
+void comm_recv( double * data, std::size_t count, int peer, void * stream )
+{
+    nccl_check( g_nccl.Recv( data, count, NCCL_FLOAT64, peer, g_nccl.comm, cudaStream_t( stream ) ), "ncclRecv" );
+}
 void comm_allreduce( double * data, std::size_t count, bool max, void * stream )
 {
     if( !g_nccl.comm )
@@ -342,7 +360,7 @@ void DeviceImage::set_slab( int c_begin, int Nc_global )
     if( !comm_active() )
         throw std::runtime_error( "spirit_b200: set_slab needs an initialised communicator (SpiritB200_Comm_Init)" );
     auto & b = *buf_;
-    if( b.F.allocated() || b.pred.allocated() || ddi_ )
+    if( b.F.allocated() || b.pred.allocated() )
         throw std::runtime_error( "spirit_b200: set_slab must be called before the image is used" );
     if( c_begin < 0 || c_begin + stencil_.nc_local > Nc_global )
         throw std::runtime_error( "spirit_b200: slab outside of the global lattice" );
@@ -642,8 +660,6 @@ void DeviceImage::set_hamiltonian( const Hamiltonian & ham )
     }
     if( ham.ddi_method == DDI_Method::FFT )
     {
-        if( p.halo != 0 )
-            throw std::runtime_error( "spirit_b200: the FFT dipole convolution is not slab-decomposed yet" );
         ddi_      = ddi_plan_create( ham, p, buf_->stream );
         p.has_ddi = 1;
         if( !buf_->ddi_s.allocated() )

@@ -45,6 +45,10 @@ bool comm_active();
 // neighbour) and an in-place all-reduce (sum or max) of `count` doubles
 void comm_sendrecv( const double * send_low, const double * send_high, double * recv_low, double * recv_high, std::size_t count, int lower, int upper, void * stream );
 void comm_allreduce( double * data, std::size_t count, bool max, void * stream );
+void comm_group_begin();
+void comm_group_end();
+void comm_send( const double * data, std::size_t count, int peer, void * stream );
+void comm_recv( double * data, std::size_t count, int peer, void * stream );
 int comm_rank();
 int comm_world();
 
