@@ -44,6 +44,9 @@ SPIRIT_API int SpiritB200_Set_Device( int device ) SPIRIT_NOEXCEPT;      /* devi
 SPIRIT_API const char * SpiritB200_Device_Name( void ) SPIRIT_NOEXCEPT;
 /* Number of kernels this library launched for the image since it was created */
 SPIRIT_API unsigned long long SpiritB200_Kernel_Launches( State * state, int idx_image ) SPIRIT_NOEXCEPT;
+/* Which stage kernels serve the image's Hamiltonian: 1 the nearest-neighbour marching kernels, 0 the generic gather
+ * kernels; < 0 on error. No counterpart in the reference (its CUDA backend has one kernel per term). */
+SPIRIT_API int SpiritB200_Stencil_Variant( State * state, int idx_image ) SPIRIT_NOEXCEPT;
 /* Upload the image's host spins to HBM (and build the device tables) / download spins + effective field */
 SPIRIT_API int SpiritB200_Upload( State * state, int idx_image ) SPIRIT_NOEXCEPT;
 SPIRIT_API int SpiritB200_Download( State * state, int idx_image ) SPIRIT_NOEXCEPT;
@@ -56,7 +59,7 @@ SPIRIT_API double SpiritB200_LLG_Iterate_Device( State * state, int solver_type,
  * The pair stencils shard along c: rank r holds the planes [c_begin, c_begin + nc_local) of a lattice with Nc_global
  * planes; its State is set up with the LOCAL slab (n_basis_cells a b nc_local). After every kernel that writes a
  * configuration the first / last plane travels to the neighbouring ranks over NCCL (NVLink); energies, torques and the
- * VP projections are all-reduced. The thermal noise is keyed by the GLOBAL site index, so results do not depend on the
+ * VP projections are all-reduced. The thermal noise is keyed by (site in plane, GLOBAL plane), so results do not depend on the
  * decomposition. The reference has no multi-GPU path; these entry points have no counterpart there. */
 /* 128-byte NCCL unique id, to be created on rank 0 and distributed by the launcher */
 SPIRIT_API int SpiritB200_Comm_Unique_Id( char * id128 ) SPIRIT_NOEXCEPT;

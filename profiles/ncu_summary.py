@@ -29,6 +29,15 @@ def main():
         for k in KEYS:
             if k in hdr:
                 print("   %-75s %s %s" % (k, r[hdr.index(k)], units[hdr.index(k)]))
+        # warp-state breakdown: stalled warps per issued instruction, by reason (largest first)
+        stalls = []
+        for i, h in enumerate(hdr):
+            if h.startswith("smsp__average_warps_issue_stalled_") and h.endswith("_per_issue_active.ratio"):
+                try:
+                    stalls.append((float(r[i].replace(",", "")), h[len("smsp__average_warps_issue_stalled_"):-len("_per_issue_active.ratio")]))
+                except ValueError:
+                    pass
+        print("   stalls per issue: " + "  ".join("%s %.2f" % (n, v) for v, n in sorted(stalls, reverse=True)[:9]))
     src = list(csv.reader(io.StringIO(run([rep, "--page", "source", "--csv"]))))
     kern, data = None, {}
     for r in src:

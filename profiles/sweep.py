@@ -15,6 +15,8 @@ for spec in sys.argv[1:]:
             env["SPIRIT_B200_LIB"] = v
         elif k == "ARGS":
             pass
+        elif k.startswith("SPIRIT_"):
+            env[k] = v
         else:
             env["SPIRIT_B200_SC6_" + k] = v
     r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--steps", "100", "--warmup", "10", "--no-e2e", "--no-cpu-baseline"],

@@ -213,6 +213,22 @@ catch( ... )
     return 0;
 }
 
+int SpiritB200_Stencil_Variant( State * state, int idx_image ) noexcept
+try
+{
+    int idx_chain = -1;
+    auto image    = resolve( state, idx_image, idx_chain ).image;
+    ImageLock lock( *image );
+    auto & d = image->device(); // creates the device image if there is none yet; throws without a CUDA device
+    d.set_hamiltonian( *image->hamiltonian );
+    return d.stencil_variant();
+}
+catch( ... )
+{
+    handle_exception_api( __func__, idx_image );
+    return -1;
+}
+
 int SpiritB200_Upload( State * state, int idx_image ) noexcept
 try
 {

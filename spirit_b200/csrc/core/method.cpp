@@ -194,7 +194,12 @@ dev::LLGParams Method_LLG::make_params( const Spin_System & system, int solver )
         l.nc1[ib]            = -l.c1[ib];
         l.nc2[ib]            = -l.c2[ib];
         l.thermal_scale[ib]  = l.has_thermal ? epsilon * std::sqrt( P.temperature / mu ) : 0.0;
+        l.half_nc1[ib]       = 0.5 * l.nc1[ib];
+        l.half_nc2[ib]       = 0.5 * l.nc2[ib];
+        l.thermal_k[ib]      = float( -2.0 * 0.69314718055994531 * l.thermal_scale[ib] * l.thermal_scale[ib] );
     }
+    l.half_damping = 0.5 * l.damping;
+    l.half_ndtg    = -0.5 * l.dtg;
     l.seed      = std::uint64_t( std::uint32_t( P.rng_seed ) ) | ( std::uint64_t( 0x5b200 ) << 32 );
     l.iteration = P.philox_counter;
     for( unsigned r = 0; r < 10; ++r )

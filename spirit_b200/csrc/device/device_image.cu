@@ -858,6 +858,13 @@ void DeviceImage::vp_reset()
     SB_CUDA_CHECK( cudaMemsetAsync( buf_->scalars, 0, 4 * sizeof( double ), buf_->stream ) );
 }
 
+int DeviceImage::stencil_variant() const
+{
+    if( !stencil_.sc6 )
+        return 0;
+    return 1;
+}
+
 namespace
 {
 template<int SOLVER, int STAGE>

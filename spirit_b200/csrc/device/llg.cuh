@@ -76,40 +76,38 @@ __device__ __forceinline__ float unit_open( unsigned r )
     return __uint_as_float( ( r >> 9 ) | 0x3f800000u ) - 0.99999994f;
 }
 
-// Three standard normal variates for (seed, iteration, global site): Philox4x32-10 -> Box-Muller. The variates are
-// shaped in fp32 with SFU instructions (23-bit uniforms, |error| of sin/cos/lg2 ~ 1e-6): they are random numbers
-// whose distribution, not whose digits, matters (T > 0 parity is statistical), and an fp64 Box-Muller
-// (log, sqrt, sincospi in software) costs more instructions than the whole rest of a solver stage, which would make
-// the step compute-bound instead of HBM-bound. Everything downstream of the variates is fp64.
-__device__ __forceinline__ D3 gaussian3( std::uint64_t seed, std::uint64_t iteration, std::uint64_t site )
+// Three normal variates of standard deviation sigma from four Philox words: Box-Muller shaped in fp32 with SFU
+// instructions (23-bit uniforms, |error| of sin/cos/lg2 ~ 1e-6): they are random numbers whose distribution, not whose
+// digits, matters (T > 0 parity is statistical), and an fp64 Box-Muller (log, sqrt, sincospi in software)
+// costs more instructions than the whole rest of a solver stage, which would make the step compute-bound instead of
+// HBM-bound. Everything downstream of the variates is fp64.
+//   radius  sigma sqrt(-2 ln u) = sqrt(k lg2 u),  k = -2 ln2 sigma^2 (host constant, LLGParams::thermal_k)
+//   angle   2 pi v with v = 1.mantissa in [1, 2): the same point of the circle as v - 1, no subtraction needed
+__device__ __forceinline__ D3 scaled_gaussian3( unsigned r0, unsigned r1, unsigned r2, unsigned r3, float k )
 {
-    unsigned r[4];
-    philox4x32_10(
-        unsigned( site ), unsigned( site >> 32 ), unsigned( iteration ), unsigned( iteration >> 32 ), unsigned( seed ),
-        unsigned( seed >> 32 ), r );
-    const float rad0 = sfu_sqrt( -1.3862943611198906f * sfu_lg2( unit_open( r[0] ) ) ); // sqrt(-2 ln u)
-    const float rad1 = sfu_sqrt( -1.3862943611198906f * sfu_lg2( unit_open( r[2] ) ) );
-    const float ang0 = 6.2831853071795865f * unit_open( r[1] ) - 3.1415926535897932f;
-    const float ang1 = 6.2831853071795865f * unit_open( r[3] ) - 3.1415926535897932f;
+    const float rad0 = sfu_sqrt( k * sfu_lg2( unit_open( r0 ) ) );
+    const float rad1 = sfu_sqrt( k * sfu_lg2( unit_open( r2 ) ) );
+    const float ang0 = 6.2831853071795865f * __uint_as_float( ( r1 >> 9 ) | 0x3f800000u );
+    const float ang1 = 6.2831853071795865f * __uint_as_float( ( r3 >> 9 ) | 0x3f800000u );
     return make_d3( double( rad0 * sfu_cos( ang0 ) ), double( rad0 * sfu_sin( ang0 ) ), double( rad1 * sfu_sin( ang1 ) ) );
 }
 
-// xi for the site with GLOBAL index gsite (reference site order) of basis atom ib
-__device__ __forceinline__ D3 thermal_field_at( const LLGParams & l, std::uint64_t gsite, int ib )
+// xi of the site `plane_site` (index inside its plane, reference order: ib + NB (a + Na b)) of the GLOBAL plane `gplane`
+// for basis atom ib. Philox counter = (plane_site, gplane, iteration lo, iteration hi): independent of the
+// decomposition over GPUs and of the kernel that evaluates it.
+__device__ __forceinline__ D3 thermal_field_at( const LLGParams & l, unsigned plane_site, unsigned gplane, int ib )
 {
-    const D3 n      = gaussian3( l.seed, l.iteration, gsite );
-    const double sc = l.thermal_scale[ib];
-    return make_d3( sc * n.x, sc * n.y, sc * n.z );
+    unsigned r[4];
+    philox4x32_10(
+        plane_site, gplane, unsigned( l.iteration ), unsigned( l.iteration >> 32 ), unsigned( l.seed ), unsigned( l.seed >> 32 ), r );
+    return scaled_gaussian3( r[0], r[1], r[2], r[3], l.thermal_k[ib] );
 }
 
 template<int NB_T>
 __device__ __forceinline__ D3 thermal_field( const StencilParams & p, const LLGParams & l, const Site & site )
 {
-    // global site index in the reference's order
-    const std::uint64_t gsite
-        = std::uint64_t( site.a ) * p.NB + site.ib
-          + std::uint64_t( p.Na ) * p.NB * ( std::uint64_t( site.b ) + std::uint64_t( p.Nb ) * ( p.c_begin + site.c ) );
-    return thermal_field_at( l, gsite, NB_T == 1 ? 0 : site.ib );
+    const unsigned plane_site = unsigned( site.a * p.NB + site.ib + p.Na * p.NB * site.b );
+    return thermal_field_at( l, plane_site, unsigned( p.c_begin + site.c ), NB_T == 1 ? 0 : site.ib );
 }
 
 // Virtual force (Method_LLG.cpp:131-226): F = -gradient.

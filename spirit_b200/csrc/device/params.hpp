@@ -103,6 +103,11 @@ struct LLGParams
     double c2[MAX_BASIS];    // alpha * dtg / mu_s[ib]
     double nc1[MAX_BASIS];   // -c1
     double nc2[MAX_BASIS];   // -c2
+    double half_nc1[MAX_BASIS]; // -c1/2, -c2/2, alpha/2, -dtg/2: Depondt's corrector averages two virtual forces
+    double half_nc2[MAX_BASIS];
+    double half_damping;
+    double half_ndtg;
+    float thermal_k[MAX_BASIS]; // -2 ln2 thermal_scale^2: Box-Muller radius sqrt(k lg2 u) already carries the amplitude
     unsigned philox_key[10][2]; // round keys of Philox4x32-10: (seed_lo + r W0, seed_hi + r W1)
     std::uint64_t seed;      // Philox key
     std::uint64_t iteration; // Philox counter high words: one xi per iteration, shared by all stages

@@ -125,6 +125,10 @@ public:
         return launches_;
     }
 
+    // Which stage kernels serve this image: 1 nearest-neighbour marching kernels (sc6.cuh), 0 generic gather kernels.
+    // Valid after the device tables are built.
+    int stencil_variant() const;
+
     DeviceBuffers * buffers()
     {
         return buf_.get();

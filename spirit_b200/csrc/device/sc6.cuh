@@ -32,9 +32,17 @@ namespace dev
 // register window and compiles to <= 80 registers: 256-thread CTAs, three per SM (24 warps). Stage 2 of Depondt and
 // Heun holds two windows (s and s'), needs ~128 registers and runs as one 512-thread CTA per SM (16 warps).
 // Measured on B200 (256^3, profiles/): stage 1 0.228 ms at 16 warps/SM -> 0.203 ms at 24 warps/SM.
-constexpr int SC6_THREADS_1W = 256, SC6_MINB_1W = 3;
-constexpr int SC6_THREADS_2W = 512, SC6_MINB_2W = 1;
-constexpr int SC6_MAX_THREADS = 512;
+// (SB_SC6_* macros: tuning builds, spirit_b200/build.py SPIRIT_B200_DEFINES)
+#ifndef SB_SC6_THREADS_1W
+#define SB_SC6_THREADS_1W 256
+#define SB_SC6_MINB_1W 3
+#endif
+#ifndef SB_SC6_THREADS_2W
+#define SB_SC6_THREADS_2W 512
+#define SB_SC6_MINB_2W 1
+#endif
+constexpr int SC6_THREADS_1W = SB_SC6_THREADS_1W, SC6_MINB_1W = SB_SC6_MINB_1W;
+constexpr int SC6_THREADS_2W = SB_SC6_THREADS_2W, SC6_MINB_2W = SB_SC6_MINB_2W;
 template<int SOLVER, int STAGE>
 struct SC6Shape
 {
@@ -195,10 +203,13 @@ __device__ __forceinline__ D3 sc6_virtual_force( const LLGParams & l, const D3 &
     return fv;
 }
 
-// xi of one site: Philox4x32-10 with the host-expanded round keys (LLGParams::philox_key)
-__device__ __forceinline__ D3 sc6_thermal_field( const LLGParams & l, std::uint64_t gsite )
+// xi of one site: Philox4x32-10 with the host-expanded round keys (LLGParams::philox_key) -> Box-Muller shaped in fp32
+// (llg.cuh, gaussian3). The amplitude epsilon sqrt(T/mu_s) is folded into the radius: sqrt(k lg2 u) with the host
+// constant k = -2 ln2 scale^2, and the angle uniforms stay in [1, 2) turns (sin / cos are periodic): 7 MUFU + 9 fp32
+// instructions + 3 conversions per site.
+__device__ __forceinline__ D3 sc6_thermal_field( const LLGParams & l, unsigned plane_site, unsigned gplane )
 {
-    unsigned c0 = unsigned( gsite ), c1 = unsigned( gsite >> 32 ), c2 = unsigned( l.iteration ), c3 = unsigned( l.iteration >> 32 );
+    unsigned c0 = plane_site, c1 = gplane, c2 = unsigned( l.iteration ), c3 = unsigned( l.iteration >> 32 );
 #pragma unroll
     for( int r = 0; r < 10; ++r )
     {
@@ -211,12 +222,7 @@ __device__ __forceinline__ D3 sc6_thermal_field( const LLGParams & l, std::uint6
         c0                = n0;
         c2                = n2;
     }
-    const float rad0 = sfu_sqrt( -1.3862943611198906f * sfu_lg2( unit_open( c0 ) ) );
-    const float rad1 = sfu_sqrt( -1.3862943611198906f * sfu_lg2( unit_open( c2 ) ) );
-    const float ang0 = 6.2831853071795865f * unit_open( c1 ) - 3.1415926535897932f;
-    const float ang1 = 6.2831853071795865f * unit_open( c3 ) - 3.1415926535897932f;
-    const double sc  = l.thermal_scale[0];
-    return make_d3( sc * double( rad0 * sfu_cos( ang0 ) ), sc * double( rad0 * sfu_sin( ang0 ) ), sc * double( rad1 * sfu_sin( ang1 ) ) );
+    return scaled_gaussian3( c0, c1, c2, c3, l.thermal_k[0] );
 }
 
 // Element offset (inside the plane pointer of a field) of the plane that holds the c-neighbour `cc` (= c-1 or c+1,
@@ -282,7 +288,7 @@ __device__ __forceinline__ void sc6_load_inplane( SC6Window & w, const double * 
 template<int SOLVER, int STAGE, int SPEC, int MODE, bool BOUNDARY>
 __device__ __forceinline__ void sc6_plane_step(
     const StencilParams & p, const LLGParams & l, const StageArgs & a, const SC6Offsets & o, const int c, const int c1,
-    const std::size_t plane_elems, const std::uint64_t gsite, D3 & s_below, const D3 & s_center, const D3 & s_above,
+    const std::size_t plane_elems, const unsigned plane_site, const unsigned gplane, D3 & s_below, const D3 & s_center, const D3 & s_above,
     D3 & p_below, const D3 & p_center, const D3 & p_above, SC6Window & ws, SC6Window & wp )
 {
     using Needs          = StageNeeds<SOLVER, STAGE>;
@@ -330,7 +336,7 @@ __device__ __forceinline__ void sc6_plane_step(
     // 3. the rest of plane c
     D3 xi = zero;
     if( MODE == SC6_THERMAL )
-        xi = sc6_thermal_field( l, gsite );
+        xi = sc6_thermal_field( l, plane_site, gplane );
     D3 Fv = zero, Fvp = zero;
     if( Needs::Fv_s )
         Fv = sc6_virtual_force<MODE>( l, s_center, gs, xi );
@@ -400,9 +406,9 @@ __device__ __forceinline__ void sc6_march(
         o.ebp         = unsigned( elem_offset( p.Na * bp + x ) );
     }
     const std::size_t plane_elems = 3 * std::size_t( p.plane_stride );
-    const std::uint64_t plane_api = std::uint64_t( p.Na ) * p.Nb;
-    // global index of the site (x, b, c_begin + c0) in the reference's order: Philox counter
-    std::uint64_t gsite = std::uint64_t( p.Na * b + x ) + plane_api * std::uint64_t( p.c_begin + c0 );
+    // Philox counter: (site inside the plane, global plane)
+    const unsigned plane_site = unsigned( p.Na * b + x );
+    unsigned gplane           = unsigned( p.c_begin + c0 );
 
     const D3 zero = make_d3( 0.0, 0.0, 0.0 );
     SC6Window ws, wp; // in-plane neighbours of s and of the predictor s'
@@ -441,9 +447,9 @@ __device__ __forceinline__ void sc6_march(
             if( k > 0 && c >= c1 )
                 break;
             sc6_plane_step<SOLVER, STAGE, SPEC, MODE, BOUNDARY>(
-                p, l, a, o, c, c1, plane_elems, gsite, rs[k], rs[( k + 1 ) % 3], rs[( k + 2 ) % 3], rp[k], rp[( k + 1 ) % 3],
+                p, l, a, o, c, c1, plane_elems, plane_site, gplane, rs[k], rs[( k + 1 ) % 3], rs[( k + 2 ) % 3], rp[k], rp[( k + 1 ) % 3],
                 rp[( k + 2 ) % 3], ws, wp );
-            gsite += plane_api;
+            ++gplane;
         }
     }
 }

@@ -266,5 +266,9 @@ class Session:
             raise RuntimeError("SpiritB200_LLG_Iterate_Device failed")
         return ms
 
+    def stencil_variant(self, idx_image=-1):
+        """1: nearest-neighbour marching kernels, 0: generic gather kernels (include/spirit_b200.h)"""
+        return self.lib.SpiritB200_Stencil_Variant(self.state, idx_image)
+
     def kernel_launches(self, idx_image=-1):
         return self.lib.SpiritB200_Kernel_Launches(self.state, idx_image)

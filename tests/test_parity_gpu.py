@@ -262,3 +262,20 @@ def test_thermal_averages_match_reference_within_error_bars(cfg, product, oracle
     assert 0.5 < mo < 0.99  # thermally disordered but not paramagnetic: the comparison is meaningful
     assert abs(mp - mo) < 4 * np.hypot(dmp, dmo), (solver, mp, dmp, mo, dmo)
     assert abs(ep - eo) < 4 * np.hypot(dep, deo), (solver, ep, dep, eo, deo)
+
+
+def test_stencil_variant_probe(cfg, product, monkeypatch):
+    """The nearest-neighbour Hamiltonians of the BASELINE configs are served by the marching kernels (and the tests
+    parametrised over `stencil_path` do exercise both code paths); a general pair list by the gather kernels."""
+    monkeypatch.setenv("SPIRIT_B200_GENERIC_STENCIL", "0")
+    p = S.Session(product, cfg("cubic256", n_basis_cells="16 12 10"))
+    assert p.stencil_variant() == 1
+    p.close()
+    monkeypatch.setenv("SPIRIT_B200_GENERIC_STENCIL", "1")
+    p = S.Session(product, cfg("cubic256", n_basis_cells="16 12 10"))
+    assert p.stencil_variant() == 0
+    p.close()
+    monkeypatch.setenv("SPIRIT_B200_GENERIC_STENCIL", "0")
+    p = S.Session(product, cfg("cubic256", n_basis_cells="16 12 10", n_shells_exchange="2", jij="10.0 -2.5"))
+    assert p.stencil_variant() == 0
+    p.close()
