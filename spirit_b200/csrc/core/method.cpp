@@ -76,6 +76,8 @@ std::string Method::SolverName()
         case dev::Solver_Depondt: return "Depondt";
         case dev::Solver_Heun: return "Heun";
         case dev::Solver_RK4: return "RK4";
+        case dev::Solver_LBFGS_OSO: return "LBFGS_OSO";
+        case dev::Solver_VP_OSO: return "VP_OSO";
         default: return "--";
     }
 }
@@ -89,6 +91,8 @@ std::string Method::SolverFullName()
         case dev::Solver_Depondt: return "Depondt";
         case dev::Solver_Heun: return "Heun";
         case dev::Solver_RK4: return "Runge Kutta (4th order)";
+        case dev::Solver_LBFGS_OSO: return "Limited memory Broyden-Fletcher-Goldfarb-Shanno using exponential transforms";
+        case dev::Solver_VP_OSO: return "Velocity Projection using exponential transforms";
         default: return "--";
     }
 }
@@ -133,16 +137,18 @@ Method_LLG::Method_LLG( std::shared_ptr<Spin_System> system_, int solver_, int i
 {
     solver = solver_;
     if( solver != dev::Solver_VP && solver != dev::Solver_SIB && solver != dev::Solver_Depondt
-        && solver != dev::Solver_Heun && solver != dev::Solver_RK4 )
+        && solver != dev::Solver_Heun && solver != dev::Solver_RK4 && solver != dev::Solver_LBFGS_OSO
+        && solver != dev::Solver_VP_OSO )
         throw std::runtime_error(
             "Solver " + std::to_string( solver )
-            + " is not implemented in spirit_b200 (available: VP 0, SIB 1, Depondt 2, Heun 3, RK4 4)" );
+            + " is not implemented in spirit_b200 (available: VP 0, SIB 1, Depondt 2, Heun 3, RK4 4, LBFGS_OSO 5, VP_OSO 7)" );
 
     // We assume it is not converged before the first iteration (Method_LLG.cpp:44-46)
     max_torque = system->llg_parameters->force_convergence + 1.0;
 
     // Constructor-time force evaluation + hook (Method_LLG.cpp:57-62)
     system->sync_to_device();
+    system->device().oso_reset(); // Method_Solver<...OSO>::Initialize: zero velocity / empty L-BFGS memory
     llg_          = make_params( *system, solver );
     hook_pending_ = true;
     system->device().llg_initial_hook( solver, llg_, &pending_hook_ );
@@ -159,11 +165,14 @@ dev::LLGParams Method_LLG::make_params( const Spin_System & system, int solver )
     const auto & P = *system.llg_parameters;
     const auto & g = *system.geometry;
     dev::LLGParams l{};
-    const bool minimise   = P.direct_minimization || solver == dev::Solver_VP;
+    const bool lbfgs      = solver == dev::Solver_LBFGS_OSO || solver == dev::Solver_LBFGS_Atlas;
+    const bool minimise   = P.direct_minimization || solver == dev::Solver_VP || solver == dev::Solver_VP_OSO || lbfgs;
     l.damping             = P.damping;
     l.dt                  = P.dt;
     l.direct_minimization = minimise ? 1 : 0;
-    if( minimise )
+    if( lbfgs )
+        l.dtg = 1.0; // Fv = s x F (Method_LLG.cpp:163-166)
+    else if( minimise )
         l.dtg = P.dt * C::gamma / C::mu_B;
     else
         l.dtg = P.dt * C::gamma / C::mu_B / ( 1 + P.damping * P.damping );
@@ -214,7 +223,10 @@ void Method_LLG::Iteration( bool hook_follows )
 {
     llg_ = make_params( *system, solver );
     system->device().set_hamiltonian( *system->hamiltonian );
-    system->device().llg_iterate( solver, llg_, 1, hook_follows, hook_follows ? &pending_hook_ : nullptr );
+    if( solver == dev::Solver_LBFGS_OSO || solver == dev::Solver_VP_OSO )
+        system->device().oso_iterate( solver, llg_, 1, hook_follows, hook_follows ? &pending_hook_ : nullptr );
+    else
+        system->device().llg_iterate( solver, llg_, 1, hook_follows, hook_follows ? &pending_hook_ : nullptr );
     ++system->llg_parameters->philox_counter;
     hook_pending_ = hook_follows;
 }

@@ -24,6 +24,22 @@ namespace dev
                 + std::to_string( __LINE__ ) + " (" #expr ")" );                                                       \
     } while( 0 )
 
+// one kernel per number of basis atoms known at compile time (1) or not (0); counts the launch
+#define SB_DISPATCH_NB( KERNEL_CALL_NB1, KERNEL_CALL_NBX )                                                             \
+    do                                                                                                                 \
+    {                                                                                                                  \
+        if( stencil_.NB == 1 )                                                                                         \
+        {                                                                                                              \
+            KERNEL_CALL_NB1;                                                                                           \
+        }                                                                                                              \
+        else                                                                                                           \
+        {                                                                                                              \
+            KERNEL_CALL_NBX;                                                                                           \
+        }                                                                                                              \
+        ++launches_;                                                                                                   \
+        SB_CUDA_CHECK( cudaGetLastError() );                                                                           \
+    } while( 0 )
+
 struct DeviceField
 {
     double * base = nullptr;

@@ -718,21 +718,6 @@ void DeviceImage::download_effective_field( double * host_aos )
 }
 
 // ---------------------------------------------------------------------------------------------
-#define SB_DISPATCH_NB( KERNEL_CALL_NB1, KERNEL_CALL_NBX )                                                             \
-    do                                                                                                                 \
-    {                                                                                                                  \
-        if( stencil_.NB == 1 )                                                                                         \
-        {                                                                                                              \
-            KERNEL_CALL_NB1;                                                                                           \
-        }                                                                                                              \
-        else                                                                                                           \
-        {                                                                                                              \
-            KERNEL_CALL_NBX;                                                                                           \
-        }                                                                                                              \
-        ++launches_;                                                                                                   \
-        SB_CUDA_CHECK( cudaGetLastError() );                                                                           \
-    } while( 0 )
-
 static void reduce_sum_to( DeviceBuffers & b, const double * partials, int slot, std::uint64_t & launches )
 {
     k_reduce_sum<<<1, BLOCK_THREADS, 0, b.stream>>>( partials, b.nblocks, b.scalars + slot );

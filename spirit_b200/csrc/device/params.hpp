@@ -18,7 +18,10 @@ enum Solver
     Solver_SIB     = 1,
     Solver_Depondt = 2,
     Solver_Heun    = 3,
-    Solver_RK4     = 4
+    Solver_RK4     = 4,
+    Solver_LBFGS_OSO   = 5,
+    Solver_LBFGS_Atlas = 6,
+    Solver_VP_OSO      = 7
 };
 
 constexpr int MAX_BASIS = 8;   // basis atoms per cell handled by the stencil kernels

@@ -61,6 +61,12 @@ struct HookResult
     double max_torque = 0; // max_i |Fv_i - (Fv_i.s_i) s_i| with Fv from the first stage, s the new spins
 };
 
+struct OsoState;
+struct OsoStateDeleter
+{
+    void operator()( OsoState * p ) const;
+};
+
 class DeviceImage
 {
 public:
@@ -113,6 +119,10 @@ public:
     void llg_initial_hook( int solver, const LLGParams & llg, HookResult * result );
     // VP keeps velocity / previous force between iterations (Solver_VP.hpp:29-114)
     void vp_reset();
+    // n iterations of VP_OSO / LBFGS_OSO (device_oso.cu; Solver_VP_OSO.hpp:34-115, Solver_LBFGS_OSO.hpp:39-77). `llg` must
+    // carry the prefactor of the solver's virtual force (Method_LLG.cpp:163-171). oso_reset drops velocity / memory.
+    void oso_iterate( int solver, LLGParams & llg, int n_iterations, bool hook, HookResult * result );
+    void oso_reset();
 
     void synchronize();
 
@@ -163,6 +173,7 @@ private:
     bool vp_prev_projected_     = false; // the last VP iteration ran a hook: F_prev is the projected force (in Fv)
     bool effective_field_in_Fv_ = false;
     std::vector<void *> * stage_events_ = nullptr; // when set, llg_iterate records an event after every stage kernel
+    std::unique_ptr<OsoState, OsoStateDeleter> oso_; // fields and scalars of the OSO minimisers (device_oso.cu)
 };
 
 // GNEB parameters the device needs per force evaluation (Method_GNEB.cpp:87-258)

@@ -14,7 +14,8 @@ from . import capi
 
 # core/include/Spirit/Simulation.h:33-54
 SOLVER_VP, SOLVER_SIB, SOLVER_DEPONDT, SOLVER_HEUN, SOLVER_RK4 = 0, 1, 2, 3, 4
-SOLVERS = {"VP": 0, "SIB": 1, "Depondt": 2, "Heun": 3, "RK4": 4}
+SOLVER_LBFGS_OSO, SOLVER_LBFGS_ATLAS, SOLVER_VP_OSO = 5, 6, 7  # core/include/Spirit/Simulation.h:33-54
+SOLVERS = {"VP": 0, "SIB": 1, "Depondt": 2, "Heun": 3, "RK4": 4, "LBFGS_OSO": 5, "LBFGS_Atlas": 6, "VP_OSO": 7}
 # core/include/Spirit/Hamiltonian.h:31-57
 CHIRALITY_BLOCH, CHIRALITY_NEEL = 1, 2
 DDI_NONE, DDI_FFT, DDI_FMM, DDI_CUTOFF = 0, 1, 2, 3

@@ -1,6 +1,6 @@
 """Slab decomposition across GPUs (needs >= 2 GPUs: `gpurun --gpus 2 -- python -m pytest tests/test_multigpu.py -m gpu`).
 A lattice cut into slabs with NCCL halo exchange must evolve BIT-IDENTICALLY to the same lattice on one GPU, also at T > 0
-(Philox is keyed by the global site index); energies agree to summation order."""
+(Philox is keyed by the site inside its plane and the GLOBAL plane index); energies agree to summation order."""
 import os
 import subprocess
 import sys

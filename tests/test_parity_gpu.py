@@ -279,3 +279,60 @@ def test_stencil_variant_probe(cfg, product, monkeypatch):
     p = S.Session(product, cfg("cubic256", n_basis_cells="16 12 10", n_shells_exchange="2", jij="10.0 -2.5"))
     assert p.stencil_variant() == 0
     p.close()
+
+
+OSO_CASES = [CASES[0], CASES[2], CASES[3], CASES[5], CASES[6], CASES[9]]
+
+
+@pytest.mark.parametrize("solver", ["VP_OSO", "LBFGS_OSO"])
+@pytest.mark.parametrize("preset,overrides,extra", OSO_CASES)
+def test_oso_minimisers_match_reference(cfg, product, oracle, solver, preset, overrides, extra):
+    """Solver_VP_OSO.hpp:34-115 / Solver_LBFGS_OSO.hpp:39-77 + lbfgs_get_searchdir (Solver_Kernels.hpp:44-190):
+    25 iterations in amortised blocks of 5 from the same random state (the L-BFGS memory wraps around several times and
+    the step limiter is active at first). The scalars of the recursion are sums over all sites, folded in a different
+    order than the reference's OpenMP reduction, so parity is to 1e-9 in the spins rather than bit-level."""
+    kw = dict(overrides, llg_n_iterations_amortize=5)
+    p, o = make_case(cfg, product, oracle, preset, kw, extra)
+    s0 = unit_random(p.nos, 13)
+    for x in (p, o):
+        x.llg_set(temperature=0.0, damping=0.3, dt=1e-3)
+        x.set_spins(s0)
+        x.llg_start(S.SOLVERS[solver], n_iterations=25, n_iterations_log=25)
+    assert np.abs(o.spins() - s0).max() > 1e-4
+    assert np.abs(p.spins() - o.spins()).max() < 1e-9
+    assert abs(p.energy() - o.energy()) <= 1e-10 * max(1.0, abs(o.energy()))
+    assert abs(p.max_torque() - o.max_torque()) <= 1e-7 * max(1e-30, o.max_torque())
+    p.close()
+    o.close()
+
+
+@pytest.mark.parametrize("solver", ["VP_OSO", "LBFGS_OSO"])
+def test_oso_single_shots_match_reference(cfg, product, oracle, solver):
+    """Simulation_SingleShot x 12 (a hook after every iteration)"""
+    p, o = make_case(cfg, product, oracle, "solvers", {}, None)
+    for x in (p, o):
+        x.plus_z()
+        x.skyrmion(5.0, phase=-90.0)
+        x.llg_start(S.SOLVERS[solver], single_shot=True)
+        for _ in range(12):
+            x.single_shot()
+    assert np.abs(p.spins() - o.spins()).max() < 1e-9
+    assert abs(p.energy() - o.energy()) <= 1e-10 * abs(o.energy())
+    for x in (p, o):
+        x.stop()
+        x.close()
+
+
+def test_oso_skyrmion_relaxation_golden(cfg, product):
+    """core/test/test_solvers.cpp:39-72: LBFGS_OSO and VP_OSO relax the 16x16 skyrmion to E = -5849.69140625, Mz = 2*0.79977"""
+    for solver in ("LBFGS_OSO", "VP_OSO"):
+        p = S.Session(product, cfg("solvers"))
+        p.plus_z()
+        p.skyrmion(5.0, phase=-90.0)
+        p.llg_set(direct_minimization=True)
+        p.llg_start(S.SOLVERS[solver])
+        p.update_data()
+        assert abs(p.energy() - (-5849.69140625)) < 1e-5 * 5849.0, solver
+        m = p.magnetization()
+        assert abs(m[2] - 2 * 0.79977) < 1e-4, solver
+        p.close()
