@@ -106,11 +106,11 @@ try
         Log( Log_Level::Warning, Log_Sender::API, "A simulation is already running on this chain. No action taken.", idx_image, idx_chain );
         return;
     }
-    if( solver_type < 0 || solver_type > Solver_VP_OSO || solver_type == Solver_LBFGS_Atlas )
+    if( solver_type < 0 || solver_type > Solver_VP_OSO )
     {
         Log( Log_Level::Error, Log_Sender::API,
              "Solver " + std::to_string( solver_type )
-                 + " is not available in spirit_b200 (VP 0, SIB 1, Depondt 2, Heun 3, RK4 4, LBFGS_OSO 5, VP_OSO 7). No action taken.",
+                 + " is not available in spirit_b200 (solver ids 0 ... 7, core/include/Spirit/Simulation.h:33-54). No action taken.",
              idx_image, idx_chain );
         return;
     }

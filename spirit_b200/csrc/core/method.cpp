@@ -78,6 +78,7 @@ std::string Method::SolverName()
         case dev::Solver_RK4: return "RK4";
         case dev::Solver_LBFGS_OSO: return "LBFGS_OSO";
         case dev::Solver_VP_OSO: return "VP_OSO";
+        case dev::Solver_LBFGS_Atlas: return "LBFGS_Atlas";
         default: return "--";
     }
 }
@@ -93,6 +94,7 @@ std::string Method::SolverFullName()
         case dev::Solver_RK4: return "Runge Kutta (4th order)";
         case dev::Solver_LBFGS_OSO: return "Limited memory Broyden-Fletcher-Goldfarb-Shanno using exponential transforms";
         case dev::Solver_VP_OSO: return "Velocity Projection using exponential transforms";
+        case dev::Solver_LBFGS_Atlas: return "Limited memory Broyden-Fletcher-Goldfarb-Shanno using stereographic atlas";
         default: return "--";
     }
 }
@@ -138,10 +140,10 @@ Method_LLG::Method_LLG( std::shared_ptr<Spin_System> system_, int solver_, int i
     solver = solver_;
     if( solver != dev::Solver_VP && solver != dev::Solver_SIB && solver != dev::Solver_Depondt
         && solver != dev::Solver_Heun && solver != dev::Solver_RK4 && solver != dev::Solver_LBFGS_OSO
-        && solver != dev::Solver_VP_OSO )
+        && solver != dev::Solver_LBFGS_Atlas && solver != dev::Solver_VP_OSO )
         throw std::runtime_error(
             "Solver " + std::to_string( solver )
-            + " is not implemented in spirit_b200 (available: VP 0, SIB 1, Depondt 2, Heun 3, RK4 4, LBFGS_OSO 5, VP_OSO 7)" );
+            + " is not implemented in spirit_b200 (available: VP 0, SIB 1, Depondt 2, Heun 3, RK4 4, LBFGS_OSO 5, LBFGS_Atlas 6, VP_OSO 7)" );
 
     // We assume it is not converged before the first iteration (Method_LLG.cpp:44-46)
     max_torque = system->llg_parameters->force_convergence + 1.0;
@@ -223,7 +225,7 @@ void Method_LLG::Iteration( bool hook_follows )
 {
     llg_ = make_params( *system, solver );
     system->device().set_hamiltonian( *system->hamiltonian );
-    if( solver == dev::Solver_LBFGS_OSO || solver == dev::Solver_VP_OSO )
+    if( solver == dev::Solver_LBFGS_OSO || solver == dev::Solver_VP_OSO || solver == dev::Solver_LBFGS_Atlas )
         system->device().oso_iterate( solver, llg_, 1, hook_follows, hook_follows ? &pending_hook_ : nullptr );
     else
         system->device().llg_iterate( solver, llg_, 1, hook_follows, hook_follows ? &pending_hook_ : nullptr );

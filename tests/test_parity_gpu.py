@@ -284,9 +284,23 @@ def test_stencil_variant_probe(cfg, product, monkeypatch):
 OSO_CASES = [CASES[0], CASES[2], CASES[3], CASES[5], CASES[6], CASES[9]]
 
 
-@pytest.mark.parametrize("solver", ["VP_OSO", "LBFGS_OSO"])
+@pytest.fixture
+def serial_oracle():
+    """The reference's lbfgs_atlas_transform_direction updates rho[n] inside an OpenMP loop without a reduction
+    (core/src/engine/Solver_Kernels.cpp:214-238): with several threads its result depends on the interleaving. Run the
+    oracle on one thread where that kernel is compared (TEST INFRASTRUCTURE only)."""
+    import ctypes
+    gomp = ctypes.CDLL("libgomp.so.1")
+    gomp.omp_get_max_threads.restype = ctypes.c_int
+    before = gomp.omp_get_max_threads()
+    gomp.omp_set_num_threads(1)
+    yield
+    gomp.omp_set_num_threads(before)
+
+
+@pytest.mark.parametrize("solver", ["VP_OSO", "LBFGS_OSO", "LBFGS_Atlas"])
 @pytest.mark.parametrize("preset,overrides,extra", OSO_CASES)
-def test_oso_minimisers_match_reference(cfg, product, oracle, solver, preset, overrides, extra):
+def test_oso_minimisers_match_reference(cfg, product, oracle, serial_oracle, solver, preset, overrides, extra):
     """Solver_VP_OSO.hpp:34-115 / Solver_LBFGS_OSO.hpp:39-77 + lbfgs_get_searchdir (Solver_Kernels.hpp:44-190):
     25 iterations in amortised blocks of 5 from the same random state (the L-BFGS memory wraps around several times and
     the step limiter is active at first). The scalars of the recursion are sums over all sites, folded in a different
@@ -306,8 +320,8 @@ def test_oso_minimisers_match_reference(cfg, product, oracle, solver, preset, ov
     o.close()
 
 
-@pytest.mark.parametrize("solver", ["VP_OSO", "LBFGS_OSO"])
-def test_oso_single_shots_match_reference(cfg, product, oracle, solver):
+@pytest.mark.parametrize("solver", ["VP_OSO", "LBFGS_OSO", "LBFGS_Atlas"])
+def test_oso_single_shots_match_reference(cfg, product, oracle, serial_oracle, solver):
     """Simulation_SingleShot x 12 (a hook after every iteration)"""
     p, o = make_case(cfg, product, oracle, "solvers", {}, None)
     for x in (p, o):
@@ -324,8 +338,9 @@ def test_oso_single_shots_match_reference(cfg, product, oracle, solver):
 
 
 def test_oso_skyrmion_relaxation_golden(cfg, product):
-    """core/test/test_solvers.cpp:39-72: LBFGS_OSO and VP_OSO relax the 16x16 skyrmion to E = -5849.69140625, Mz = 2*0.79977"""
-    for solver in ("LBFGS_OSO", "VP_OSO"):
+    """core/test/test_solvers.cpp:39-72: LBFGS_Atlas, LBFGS_OSO and VP_OSO relax the 16x16 skyrmion to E = -5849.69140625,
+    Mz = 2*0.79977"""
+    for solver in ("LBFGS_Atlas", "LBFGS_OSO", "VP_OSO"):
         p = S.Session(product, cfg("solvers"))
         p.plus_z()
         p.skyrmion(5.0, phase=-90.0)
