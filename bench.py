@@ -247,7 +247,7 @@ def run_b200(args):
     k = 1  # stage 2 moves 72 of the 120 B
     achieved = BYTES_STAGE[k] * nos / (stage_ms[k] * 1e-3) / 1e9
     roofline = {
-        "bound": "hbm", "kernel": "k_llg_stage<Depondt,2> (gradient(s) + gradient(s') + virtual forces + Rodrigues rotation)",
+        "bound": "hbm", "kernel": "k_sc6_stage<Depondt,2,...> (gradient(s) recomputed + gradient(s') + virtual forces + Rodrigues rotation)",
         "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
         "peak_source": peak_src, "algorithmic_bytes_per_launch": BYTES_STAGE[k] * nos,
         "stage_ms": [stage_ms[0], stage_ms[1]],
@@ -260,7 +260,7 @@ def run_b200(args):
     traffic_path = os.path.join(ROOT, "profiles", "traffic.json")
     if os.path.exists(traffic_path):
         try:
-            roofline["traffic"] = json.load(open(traffic_path)).get("k_llg_stage_depondt_2_bytes_per_launch_256")
+            roofline["traffic"] = json.load(open(traffic_path)).get("k_sc6_stage_depondt_2_bytes_per_launch_256")
             if cells != (256, 256, 256):
                 roofline["traffic"] = None
         except (ValueError, OSError):
