@@ -192,9 +192,9 @@ dev::LLGParams Method_LLG::make_params( const Spin_System & system, int solver )
             l.stt_pol[d] = P.stt_polarisation_normal[d];
     }
 
-    if( P.temperature_gradient_inclination != 0 )
-        throw std::runtime_error( "spirit_b200: temperature gradients are not implemented (SURVEY.md 8f rank 4)" );
-    l.has_thermal = ( !minimise && P.temperature > 0 ) ? 1 : 0;
+    // Method_LLG.cpp:72: a thermal field exists for T > 0 or a non-zero temperature gradient
+    l.has_tgrad   = ( !minimise && P.temperature_gradient_inclination != 0 ) ? 1 : 0;
+    l.has_thermal = ( !minimise && ( P.temperature > 0 || l.has_tgrad ) ) ? 1 : 0;
     const double epsilon = std::sqrt( 2 * P.damping * P.dt * C::gamma / C::mu_B * C::k_B ) / ( 1 + P.damping * P.damping );
     for( int ib = 0; ib < dev::MAX_BASIS; ++ib )
     {
@@ -208,6 +208,27 @@ dev::LLGParams Method_LLG::make_params( const Spin_System & system, int solver )
         l.half_nc1[ib]       = 0.5 * l.nc1[ib];
         l.half_nc2[ib]       = 0.5 * l.nc2[ib];
         l.thermal_k[ib]      = float( -2.0 * 0.69314718055994531 * l.thermal_scale[ib] * l.thermal_scale[ib] );
+    }
+    if( l.has_tgrad )
+    {
+        // T_i = inclination * (d . r_i) + T - inclination * min(d . bounds_min, d . bounds_max)  (Vectormath.cpp:633-652),
+        // and r_i is affine in the cell indices: r_i = lc * ( (a + u_a) t_a + (b + u_b) t_b + (c + u_c) t_c )
+        Vec3 d = P.temperature_gradient_direction;
+        d.normalize();
+        const double incl = P.temperature_gradient_inclination;
+        const double dmin = std::min( g.bounds_min.dot( d ), g.bounds_max.dot( d ) );
+        l.tgrad_T0        = P.temperature - incl * dmin;
+        for( int k = 0; k < 3; ++k )
+            l.tgrad_cell[k] = incl * g.lattice_constant * g.bravais_vectors[k].dot( d );
+        for( int ib = 0; ib < dev::MAX_BASIS; ++ib )
+        {
+            l.tgrad_basis[ib] = 0;
+            if( ib < g.n_cell_atoms )
+                for( int k = 0; k < 3; ++k )
+                    l.tgrad_basis[ib] += incl * g.lattice_constant * g.cell_atoms[ib][k] * g.bravais_vectors[k].dot( d );
+            const double mu        = ib < g.n_cell_atoms ? g.cell_mu_s[ib] : 1.0;
+            l.thermal_k_per_T[ib] = float( -2.0 * 0.69314718055994531 * epsilon * epsilon / mu );
+        }
     }
     l.half_damping = 0.5 * l.damping;
     l.half_ndtg    = -0.5 * l.dtg;

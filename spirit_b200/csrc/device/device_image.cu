@@ -874,7 +874,7 @@ void launch_stage(
     bool nb1, bool hook, int nblocks, cudaStream_t stream, const StencilParams & p, const LaunchGeom & lg, const LLGParams & l,
     const StageArgs & a, const SC6Launch & sc6, DeviceImage & image, void * out )
 {
-    if( p.sc6 && !hook && !l.has_stt )
+    if( p.sc6 && !hook && !l.has_stt && !l.has_tgrad )
     {
         // nearest-neighbour structure: marching kernel (the hook iteration, which also stores F, Fv and reduces the
         // energy, goes through the generic kernel)

@@ -107,7 +107,20 @@ template<int NB_T>
 __device__ __forceinline__ D3 thermal_field( const StencilParams & p, const LLGParams & l, const Site & site )
 {
     const unsigned plane_site = unsigned( site.a * p.NB + site.ib + p.Na * p.NB * site.b );
-    return thermal_field_at( l, plane_site, unsigned( p.c_begin + site.c ), NB_T == 1 ? 0 : site.ib );
+    const int ib              = NB_T == 1 ? 0 : site.ib;
+    if( l.has_tgrad )
+    {
+        // site temperature of the linear gradient, cut off at zero (get_gradient_distribution, Vectormath.cpp:633-652)
+        double T = l.tgrad_T0 + l.tgrad_cell[0] * site.a + l.tgrad_cell[1] * site.b + l.tgrad_cell[2] * ( p.c_begin + site.c )
+                   + l.tgrad_basis[ib];
+        T = fmin( fmax( T, 0.0 ), 1e30 );
+        unsigned r[4];
+        philox4x32_10(
+            plane_site, unsigned( p.c_begin + site.c ), unsigned( l.iteration ), unsigned( l.iteration >> 32 ), unsigned( l.seed ),
+            unsigned( l.seed >> 32 ), r );
+        return scaled_gaussian3( r[0], r[1], r[2], r[3], l.thermal_k_per_T[ib] * float( T ) );
+    }
+    return thermal_field_at( l, plane_site, unsigned( p.c_begin + site.c ), ib );
 }
 
 // Virtual force (Method_LLG.cpp:131-226): F = -gradient.

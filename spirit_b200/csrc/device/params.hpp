@@ -111,6 +111,14 @@ struct LLGParams
     double half_damping;
     double half_ndtg;
     float thermal_k[MAX_BASIS]; // -2 ln2 thermal_scale^2: Box-Muller radius sqrt(k lg2 u) already carries the amplitude
+    // Linear temperature gradient (Method_LLG.cpp:80-96, Vectormath.cpp:633-652): T_i = clamp( tgrad_T0 + tgrad_cell .
+    // (a, b, c_global) + tgrad_basis[ib], 0, 1e30 ); the radius constant becomes thermal_k_per_T[ib] * T_i
+    int has_tgrad;
+    int pad2;
+    double tgrad_T0;
+    double tgrad_cell[3];
+    double tgrad_basis[MAX_BASIS];
+    float thermal_k_per_T[MAX_BASIS]; // -2 ln2 epsilon^2 / mu_s[ib]
     unsigned philox_key[10][2]; // round keys of Philox4x32-10: (seed_lo + r W0, seed_hi + r W1)
     std::uint64_t seed;      // Philox key
     std::uint64_t iteration; // Philox counter high words: one xi per iteration, shared by all stages

@@ -351,3 +351,30 @@ def test_oso_skyrmion_relaxation_golden(cfg, product):
         m = p.magnetization()
         assert abs(m[2] - 2 * 0.79977) < 1e-4, solver
         p.close()
+
+
+def test_temperature_gradient_langevin_profile(cfg, product):
+    """Linear temperature gradient (Method_LLG.cpp:80-96, Vectormath::get_gradient_distribution): non-interacting spins in
+    a field at a site temperature T(x) = T0 + g x obey <s_z>(x) = coth X - 1/X, X = mu_s mu_B B / (k_B T(x)). The
+    profile along the gradient pins both the amplitude epsilon sqrt(T_i / mu_s) and its dependence on the position."""
+    path = cfg("fd_pairs", pairs=["i j da db dc Jij"], n_basis_cells="64 64 1", external_field_magnitude="10",
+               llg_temperature="5", llg_temperature_gradient_direction="1 0 0", llg_temperature_gradient_inclination="0.25",
+               llg_damping="0.3", llg_dt="1e-3", llg_n_iterations_amortize="100")
+    T = 5.0 + 0.25 * np.arange(64)
+    X = 2.0 * product.Constants_mu_B() * 10.0 / (product.Constants_k_B() * T)
+    langevin = 1.0 / np.tanh(X) - 1.0 / X
+    expected = langevin.reshape(4, 16).mean(axis=1)  # four bands of 16 columns
+    assert expected[0] - expected[3] > 0.25  # the profile is far from flat
+    p = S.Session(product, path)
+    p.plus_z()
+    p.llg_start(S.SOLVER_DEPONDT, n_iterations=6000, n_iterations_log=6000)
+    bands = []
+    for _ in range(16):
+        p.llg_start(S.SOLVER_DEPONDT, n_iterations=500, n_iterations_log=500)
+        sz = p.spins()[:, 2].reshape(64, 64)  # [b][a]
+        bands.append(sz.reshape(64, 4, 16).mean(axis=(0, 2)))
+    bands = np.array(bands)
+    mean, err = bands.mean(axis=0), bands.std(axis=0, ddof=1) / np.sqrt(len(bands))
+    for k in range(4):
+        assert abs(mean[k] - expected[k]) < max(4 * err[k], 0.012), (k, mean[k], expected[k], err[k])
+    p.close()
