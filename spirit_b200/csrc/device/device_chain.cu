@@ -25,6 +25,8 @@
 #include <algorithm>
 #include <cmath>
 #include <cstddef>
+#include "oso.cuh"
+
 #include <cstring>
 #include <stdexcept>
 
@@ -412,6 +414,21 @@ static __global__ void __launch_bounds__( BLOCK_THREADS ) k_chain_stage(
     }
 }
 
+// OSO / atlas minimisers over the chain: total force of every image into F2 (hook, atlas gradient) and s x F into F
+// (the OSO gradient is T(+-s x F), oso.cuh). End / stationary images have F = 0 and do not move.
+static __global__ void __launch_bounds__( BLOCK_THREADS )
+    k_chain_cross( const __grid_constant__ StencilParams p, const __grid_constant__ LaunchGeom lg, const __grid_constant__ ChainView v )
+{
+    const int img = blockIdx.y;
+    Site site;
+    if( !locate_site( p, lg, site, p.NB ) )
+        return;
+    const D3 s = load3( cfield( v.S, v.stride, img ), site.idx );
+    const D3 F = chain_total_force( v, img, site.idx, s );
+    store3( field( v.F2, v.stride, img ), site.idx, F );
+    store3( field( v.F, v.stride, img ), site.idx, cross3( s, F ) );
+}
+
 // Hook of the two-stage solvers: max_i |F_total - (F_total.s)s| per image with the NEW spins, F_total = force of the last
 // (predictor) evaluation (Method_GNEB.cpp:416-424)
 static __global__ void __launch_bounds__( BLOCK_THREADS ) k_chain_hook(
@@ -563,6 +580,7 @@ void DeviceChain::download_effective_field( int img, double * host_aos )
 
 void DeviceChain::vp_reset()
 {
+    oso_.reset();
     auto & b = *buf_;
     // velocity = 0, F = F_prev = 0 (Method_GNEB's constructor evaluates no force, Method_GNEB.cpp:23-73)
     const std::size_t fs = std::size_t( noi_ ) * b.stride * sizeof( double );
@@ -662,13 +680,37 @@ void DeviceChain::iterate( int solver, const GNEBParams & params, int n_iteratio
     const auto & T = *table_->buffers();
     const auto & p = table_->stencil();
     const dim3 grid( T.nblocks, noi_ );
-    if( solver != Solver_VP && solver != Solver_Depondt && solver != Solver_Heun && solver != Solver_SIB )
+    const bool oso = solver == Solver_VP_OSO || solver == Solver_LBFGS_OSO || solver == Solver_LBFGS_Atlas;
+    if( solver != Solver_VP && solver != Solver_Depondt && solver != Solver_Heun && solver != Solver_SIB && !oso )
         throw std::runtime_error( "spirit_b200: GNEB solver id " + std::to_string( solver ) + " is not implemented" );
+    if( oso && sharded_ )
+        throw std::runtime_error( "spirit_b200: VP_OSO / LBFGS_OSO / LBFGS_Atlas are not implemented on a chain sharded over GPUs" );
+    // all local images back to back: one long field for the element-wise passes of oso.cuh
+    const OsoLayout L{ std::size_t( noi_ ) * T.n_storage, p.plane_stride, T.plane_sites };
+    if( oso && !oso_ )
+    {
+        oso_.reset( new OsoState );
+        oso_->allocate( solver, L.n_sites, noi_, ConstField3{ b.view.S }, L, b.stream, launches_ );
+    }
 
     for( int it = 0; it < n_iterations; ++it )
     {
         const bool hk = hook && it == n_iterations - 1;
-        if( solver == Solver_VP )
+        if( oso )
+        {
+            // Solver_VP_OSO.hpp:34-115 / Solver_LBFGS_OSO.hpp:39-77 / Solver_LBFGS_Atlas.hpp:50-107 with noi images
+            evaluate_force( params, 0, 0 );
+            k_chain_cross<<<grid, BLOCK_THREADS, 0, b.stream>>>( p, T.lg, b.view );
+            ++launches_;
+            oso_update( *oso_, solver, Field3{ b.view.S }, ConstField3{ b.view.F }, 1.0, ConstField3{ b.view.F2 }, L, nos_, params.dt, b.stream, launches_ );
+            if( hk )
+            {
+                k_chain_hook<<<grid, BLOCK_THREADS, 0, b.stream>>>( p, T.lg, b.view, b.partials, T.nblocks );
+                reduce_to_slots( S_TQ, 1, true );
+                launches_ += 2;
+            }
+        }
+        else if( solver == Solver_VP )
         {
             evaluate_force( params, 0, 0 );
             const double * F_prev = vp_prev_projected_ ? b.view.Fpr : b.view.F;

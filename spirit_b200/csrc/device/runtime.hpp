@@ -215,10 +215,10 @@ public:
     // effective field (-gradient, unprojected) of image img from the last force evaluation
     void download_effective_field( int img, double * host_aos );
 
-    // n iterations of solver VP / SIB / Depondt / Heun over all images; with `hook` the last iteration also produces
+    // n iterations of solver VP / SIB / Depondt / Heun / VP_OSO / LBFGS_OSO / LBFGS_Atlas over all images; with `hook` the last iteration also produces
     // the quantities of Method_GNEB::Hook_Post_Iteration (Method_GNEB.cpp:410-456)
     void iterate( int solver, const GNEBParams & params, int n_iterations, bool hook, ChainHookResult * result );
-    void vp_reset();
+    void vp_reset(); // also drops the velocity / L-BFGS memory of the OSO / atlas solvers
     void synchronize();
     std::uint64_t kernel_launches() const
     {
@@ -237,6 +237,7 @@ private:
     std::unique_ptr<DeviceChainBuffers> buf_;
     std::uint64_t launches_  = 0;
     bool vp_prev_projected_ = false;
+    std::unique_ptr<OsoState, OsoStateDeleter> oso_; // VP_OSO / LBFGS_OSO / LBFGS_Atlas over the chain (oso.cuh)
 };
 
 } // namespace dev

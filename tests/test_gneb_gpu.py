@@ -165,3 +165,63 @@ def test_gneb_barrier_matches_reference(cfg, product, oracle):
         x.close()
     assert barrier[1] > 30.0
     assert abs(barrier[0] - barrier[1]) <= 1e-8 * abs(barrier[1])
+
+
+@pytest.fixture
+def serial_oracle():
+    """see tests/test_parity_gpu.py::serial_oracle (the reference's atlas chart change races under OpenMP)"""
+    import ctypes
+    gomp = ctypes.CDLL("libgomp.so.1")
+    gomp.omp_get_max_threads.restype = ctypes.c_int
+    before = gomp.omp_get_max_threads()
+    gomp.omp_set_num_threads(1)
+    yield
+    gomp.omp_set_num_threads(before)
+
+
+@pytest.mark.parametrize("solver", ["VP_OSO", "LBFGS_OSO", "LBFGS_Atlas"])
+@pytest.mark.parametrize("types", TYPES)
+def test_gneb_minimisers_match_reference(cfg, product, oracle, serial_oracle, solver, types):
+    """VP_OSO / LBFGS_OSO / LBFGS_Atlas over all images (dot products and the step limit are taken over the whole chain,
+    Solver_Kernels.hpp:44-190, Solver_LBFGS_OSO.hpp:59-69): 30 single shots against the reference"""
+    path = cfg("solvers", n_basis_cells="12 10 1", boundary_conditions="1 0 0")
+    out = []
+    for lib in (product, oracle):
+        x = S.Session(lib, path)
+        make_chain(x, noi=8)
+        for img, t in types.items():
+            x.gneb_set_image_type(t, img)
+        x.gneb_start(S.SOLVERS[solver], single_shot=True)
+        x.n_shot(30)
+        rx, e = x.chain_rx_e()
+        out.append((np.stack([x.spins(i).copy() for i in range(8)]), rx, e, x.chain_max_torque()))
+        x.stop()
+        x.close()
+    (sp, rxp, ep, tp), (so, rxo, eo, to) = out
+    assert np.abs(sp - so).max() < 1e-8
+    assert np.abs(rxp - rxo).max() < 1e-8
+    assert np.abs(ep - eo).max() <= 1e-9 * np.abs(eo).max()
+    assert abs(tp - to) <= 1e-6 * to
+
+
+@pytest.mark.parametrize("solver", ["LBFGS_Atlas", "LBFGS_OSO", "VP_OSO"])
+def test_gneb_barrier_golden_minimisers(cfg, product, solver):
+    """core/test/test_solvers.cpp:74-115 for the three minimisers: saddle point E = -5811.5244140625, M_z = 2 * 0.96657"""
+    p = S.Session(product, cfg("solvers"))
+    p.plus_z()
+    p.skyrmion(5.0, phase=-90.0)
+    p.llg_set(direct_minimization=True)
+    p.llg_start(S.SOLVERS[solver])  # relax the initial skyrmion
+    p.chain_set_length(9)
+    p.jump_to_image(8)
+    p.plus_z()
+    p.jump_to_image(0)
+    p.transition_homogeneous(0, 8)
+    p.gneb_start(S.SOLVERS[solver], n_iterations=20000, n_iterations_log=20000)
+    p.gneb_set_image_type_automatically()
+    p.gneb_start(S.SOLVERS[solver])
+    rx, e = p.chain_rx_e()
+    i_max = int(np.argmax(e))
+    assert abs(e[i_max] - (-5811.5244140625)) < 1e-3
+    assert abs(p.magnetization(i_max)[2] - 2 * 0.96657) < 1e-4
+    p.close()
