@@ -103,6 +103,7 @@ struct DeviceBuffers
     DeviceField F, Fv;             // force / virtual force (hook, VP); F doubles as the effective field
     DeviceField ddi_s, ddi_p;      // DDI gradient fields of s and of the predictor
     DeviceField scratch;           // gradient output for one-off evaluations
+    float * xi = nullptr;          // thermal field of the running iteration as fp32 variates [3 * n_storage] (sc6.cuh)
 
     double * staging   = nullptr; // AoS staging [nos][3]
     double * partials  = nullptr; // [4][nblocks] reduction scratch
@@ -116,6 +117,8 @@ struct DeviceBuffers
             f->release();
         if( staging )
             cudaFree( staging );
+        if( xi )
+            cudaFree( xi );
         if( partials )
             cudaFree( partials );
         if( scalars )

@@ -288,6 +288,7 @@ SC6Geometry make_sc6_geometry( const StencilParams & p, int threads, int ctas_pe
         }
     }
     G.lc   = std::max( 1, env_int( "SPIRIT_B200_SC6_LC", best_lc ) );
+    G.lc   = std::max( 1, env_int( ctas_per_sm > 1 ? "SPIRIT_B200_SC6_LC1" : "SPIRIT_B200_SC6_LC2", G.lc ) ); // per launch shape
     G.grid = dim3( gx, gy, ( p.nc_local + G.lc - 1 ) / G.lc );
     return G;
 }
@@ -980,6 +981,9 @@ void DeviceImage::llg_iterate( int solver, LLGParams & llg, int n_iterations, bo
         a.F_out           = b.F.f();
         a.Fv_out          = b.Fv.f();
         a.energy_partials = b.partials;
+        if( llg.has_thermal && stencil_.sc6 && !b.xi )
+            SB_CUDA_CHECK( cudaMalloc( &b.xi, 3 * b.n_storage * sizeof( float ) ) );
+        a.xi = b.xi;
 
         compute_ddi_gradient( 0 );
         if( solver == Solver_Depondt || solver == Solver_Heun || solver == Solver_SIB )

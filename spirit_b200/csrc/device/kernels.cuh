@@ -289,6 +289,8 @@ struct StageArgs
     Field3 F_out;       // HOOK, stage 1: force -gradient(s)
     Field3 Fv_out;      // HOOK, stage 1: virtual force Fv(s)
     double * energy_partials; // HOOK, last stage
+    float * xi;         // marching kernels at T > 0: the thermal field of the iteration as the fp32 variates it is made of
+                        // (AoSoA-32 like the fields): written by stage 1, read by the later stages
 };
 
 template<int SOLVER, int STAGE, int NB_T, bool HOOK>

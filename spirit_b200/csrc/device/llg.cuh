@@ -83,13 +83,18 @@ __device__ __forceinline__ float unit_open( unsigned r )
 // HBM-bound. Everything downstream of the variates is fp64.
 //   radius  sigma sqrt(-2 ln u) = sqrt(k lg2 u),  k = -2 ln2 sigma^2 (host constant, LLGParams::thermal_k)
 //   angle   2 pi v with v = 1.mantissa in [1, 2): the same point of the circle as v - 1, no subtraction needed
-__device__ __forceinline__ D3 scaled_gaussian3( unsigned r0, unsigned r1, unsigned r2, unsigned r3, float k )
+__device__ __forceinline__ float3 scaled_gaussian3f( unsigned r0, unsigned r1, unsigned r2, unsigned r3, float k )
 {
     const float rad0 = sfu_sqrt( k * sfu_lg2( unit_open( r0 ) ) );
     const float rad1 = sfu_sqrt( k * sfu_lg2( unit_open( r2 ) ) );
     const float ang0 = 6.2831853071795865f * __uint_as_float( ( r1 >> 9 ) | 0x3f800000u );
     const float ang1 = 6.2831853071795865f * __uint_as_float( ( r3 >> 9 ) | 0x3f800000u );
-    return make_d3( double( rad0 * sfu_cos( ang0 ) ), double( rad0 * sfu_sin( ang0 ) ), double( rad1 * sfu_sin( ang1 ) ) );
+    return make_float3( rad0 * sfu_cos( ang0 ), rad0 * sfu_sin( ang0 ), rad1 * sfu_sin( ang1 ) );
+}
+__device__ __forceinline__ D3 scaled_gaussian3( unsigned r0, unsigned r1, unsigned r2, unsigned r3, float k )
+{
+    const float3 v = scaled_gaussian3f( r0, r1, r2, r3, k );
+    return make_d3( double( v.x ), double( v.y ), double( v.z ) );
 }
 
 // xi of the site `plane_site` (index inside its plane, reference order: ib + NB (a + Na b)) of the GLOBAL plane `gplane`

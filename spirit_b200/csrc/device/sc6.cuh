@@ -37,6 +37,11 @@ namespace dev
 #define SB_SC6_THREADS_1W 256
 #define SB_SC6_MINB_1W 3
 #endif
+#ifndef SB_SC6_STORE_XI
+#define SB_SC6_STORE_XI 0 // 1: at T > 0 stage 1 stores the fp32 noise variates and the later stages read them instead of
+                          // regenerating them. Measured (profiles/r1i): 77 fewer instructions in stage 2 and NO gain (0.2977 vs
+                          // 0.2926 ms; stage 1 +6 %): the stages are not bound by their instruction count
+#endif
 #ifndef SB_SC6_THREADS_2W
 #define SB_SC6_THREADS_2W 512
 #define SB_SC6_MINB_2W 1
@@ -207,7 +212,7 @@ __device__ __forceinline__ D3 sc6_virtual_force( const LLGParams & l, const D3 &
 // (llg.cuh, gaussian3). The amplitude epsilon sqrt(T/mu_s) is folded into the radius: sqrt(k lg2 u) with the host
 // constant k = -2 ln2 scale^2, and the angle uniforms stay in [1, 2) turns (sin / cos are periodic): 7 MUFU + 9 fp32
 // instructions + 3 conversions per site.
-__device__ __forceinline__ D3 sc6_thermal_field( const LLGParams & l, unsigned plane_site, unsigned gplane )
+__device__ __forceinline__ float3 sc6_thermal_field( const LLGParams & l, unsigned plane_site, unsigned gplane )
 {
     unsigned c0 = plane_site, c1 = gplane, c2 = unsigned( l.iteration ), c3 = unsigned( l.iteration >> 32 );
 #pragma unroll
@@ -222,7 +227,7 @@ __device__ __forceinline__ D3 sc6_thermal_field( const LLGParams & l, unsigned p
         c0                = n0;
         c2                = n2;
     }
-    return scaled_gaussian3( c0, c1, c2, c3, l.thermal_k[0] );
+    return scaled_gaussian3f( c0, c1, c2, c3, l.thermal_k[0] );
 }
 
 // Element offset (inside the plane pointer of a field) of the plane that holds the c-neighbour `cc` (= c-1 or c+1,
@@ -289,11 +294,16 @@ template<int SOLVER, int STAGE, int SPEC, int MODE, bool BOUNDARY>
 __device__ __forceinline__ void sc6_plane_step(
     const StencilParams & p, const LLGParams & l, const StageArgs & a, const SC6Offsets & o, const int c, const int c1,
     const std::size_t plane_elems, const unsigned plane_site, const unsigned gplane, D3 & s_below, const D3 & s_center, const D3 & s_above,
-    D3 & p_below, const D3 & p_center, const D3 & p_above, SC6Window & ws, SC6Window & wp )
+    D3 & p_below, const D3 & p_center, const D3 & p_above, SC6Window & ws, SC6Window & wp, float3 & xi_pipe )
 {
     using Needs          = StageNeeds<SOLVER, STAGE>;
     constexpr bool HAS_C = ( SPEC & SC6_HAS_C ) != 0;
     constexpr bool COL_S = HAS_C && Needs::Fv_s;  // s needs its c-neighbours
+    // T > 0: stage 1 makes the noise of the iteration (Philox + Box-Muller, ~70 instructions) and stores the three
+    // fp32 variates it consists of (12 B per site); the later stages read them back one plane ahead instead of
+    // regenerating them. Bit-identical to regenerating (the variates ARE fp32), 24 B more traffic per spin-step.
+    constexpr bool XI_LOAD = MODE == SC6_THERMAL && STAGE > 1 && SB_SC6_STORE_XI;
+    const float3 xi_f      = xi_pipe; // of plane c (XI_LOAD)
     constexpr bool COL_P = HAS_C && Needs::Fv_sp; // s' needs its c-neighbours
     const D3 zero        = make_d3( 0.0, 0.0, 0.0 );
 
@@ -331,12 +341,31 @@ __device__ __forceinline__ void sc6_plane_step(
                 p_below = ld3p( a.sp.base + pa2, o.ec );
             sc6_load_inplane<BOUNDARY>( wp, a.sp.base + base1, o );
         }
+        if( XI_LOAD )
+        {
+            const float * q = a.xi + base1 + o.ec;
+            xi_pipe         = make_float3( __ldg( q ), __ldg( q + FIELD_BLOCK ), __ldg( q + 2 * FIELD_BLOCK ) );
+        }
     }
 
     // 3. the rest of plane c
     D3 xi = zero;
     if( MODE == SC6_THERMAL )
-        xi = sc6_thermal_field( l, plane_site, gplane );
+    {
+        float3 f = xi_f;
+        if( !XI_LOAD )
+        {
+            f = sc6_thermal_field( l, plane_site, gplane );
+            if( SB_SC6_STORE_XI && STAGE == 1 )
+            {
+                float * q          = a.xi + base + o.ec;
+                q[0]               = f.x;
+                q[FIELD_BLOCK]     = f.y;
+                q[2 * FIELD_BLOCK] = f.z;
+            }
+        }
+        xi = make_d3( double( f.x ), double( f.y ), double( f.z ) );
+    }
     D3 Fv = zero, Fvp = zero;
     if( Needs::Fv_s )
         Fv = sc6_virtual_force<MODE>( l, s_center, gs, xi );
@@ -415,6 +444,7 @@ __device__ __forceinline__ void sc6_march(
     ws.xm = ws.xp = ws.bm = ws.bp = wp.xm = wp.xp = wp.bm = wp.bp = zero;
     // own-column rings: at plane c0 + k the roles (below, center, above) are ring[k % 3], ring[(k+1) % 3], ring[(k+2) % 3]
     D3 rs[3] = { zero, zero, zero }, rp[3] = { zero, zero, zero };
+    float3 xi_pipe = make_float3( 0.f, 0.f, 0.f ); // stored noise of the next plane
 
     // prologue: plane c0 and the own-column value of plane c0 + 1
     {
@@ -436,6 +466,11 @@ __device__ __forceinline__ void sc6_march(
                 rp[0] = ld3p( a.sp.base + sc6_c_plane( p, c0 - 1 ), o.ec );
             sc6_load_inplane<BOUNDARY>( wp, a.sp.base + base, o );
         }
+        if( MODE == SC6_THERMAL && STAGE > 1 && SB_SC6_STORE_XI )
+        {
+            const float * q = a.xi + base + o.ec;
+            xi_pipe         = make_float3( __ldg( q ), __ldg( q + FIELD_BLOCK ), __ldg( q + 2 * FIELD_BLOCK ) );
+        }
     }
 
     for( int cb = c0; cb < c1; cb += 3 )
@@ -448,7 +483,7 @@ __device__ __forceinline__ void sc6_march(
                 break;
             sc6_plane_step<SOLVER, STAGE, SPEC, MODE, BOUNDARY>(
                 p, l, a, o, c, c1, plane_elems, plane_site, gplane, rs[k], rs[( k + 1 ) % 3], rs[( k + 2 ) % 3], rp[k], rp[( k + 1 ) % 3],
-                rp[( k + 2 ) % 3], ws, wp );
+                rp[( k + 2 ) % 3], ws, wp, xi_pipe );
             ++gplane;
         }
     }
