@@ -42,6 +42,9 @@ namespace dev
                           // regenerating them. Measured (profiles/r1i): 77 fewer instructions in stage 2 and NO gain (0.2977 vs
                           // 0.2926 ms; stage 1 +6 %): the stages are not bound by their instruction count
 #endif
+#ifndef SB_SC6_L2_PREFETCH
+#define SB_SC6_L2_PREFETCH 0 // > 0: prefetch.global.L2 of the own-column sites this many planes ahead (no registers)
+#endif
 #ifndef SB_SC6_THREADS_2W
 #define SB_SC6_THREADS_2W 512
 #define SB_SC6_MINB_2W 1
@@ -91,6 +94,13 @@ __device__ __forceinline__ D3 ld3pv( const double * __restrict__ plane, unsigned
     if( valid )
         r = ld3p( plane, e );
     return r;
+}
+
+__device__ __forceinline__ void sc6_prefetch3( const double * q )
+{
+    asm volatile( "prefetch.global.L2 [%0];" ::"l"( q ) );
+    asm volatile( "prefetch.global.L2 [%0];" ::"l"( q + FIELD_BLOCK ) );
+    asm volatile( "prefetch.global.L2 [%0];" ::"l"( q + 2 * FIELD_BLOCK ) );
 }
 
 // Contribution of the neighbour pair (minus, plus) along one axis:
@@ -340,6 +350,16 @@ __device__ __forceinline__ void sc6_plane_step(
             if( COL_P || c + 2 < c1 )
                 p_below = ld3p( a.sp.base + pa2, o.ec );
             sc6_load_inplane<BOUNDARY>( wp, a.sp.base + base1, o );
+        }
+        if( SB_SC6_L2_PREFETCH > 0 && c + SB_SC6_L2_PREFETCH < c1 )
+        {
+            // the own-column load of plane c + 2 above is the one access of the step that has to come from HBM, with one
+            // plane step of lookahead; pull the lines it will need into L2 well before
+            const std::size_t far = base + std::size_t( SB_SC6_L2_PREFETCH ) * plane_elems + o.ec;
+            if( Needs::Fv_s || true )
+                sc6_prefetch3( a.s.base + far );
+            if( Needs::Fv_sp )
+                sc6_prefetch3( a.sp.base + far );
         }
         if( XI_LOAD )
         {
