@@ -5,7 +5,8 @@
 
 
 
-__global__ void k_chain( int which, double * out, long long * cycles, int iters )
+template<int which>
+__global__ void k_chain( double * out, long long * cycles, int iters )
 {
     double a = threadIdx.x, m = 1.0000001, c = 1e-9;
     unsigned i0 = threadIdx.x, i1 = 0x9E3779B9u;
@@ -47,13 +48,14 @@ int main()
     cudaMalloc( &cyc, sizeof( long long ) );
     const char * names[] = { "DFMA", "DADD", "DMUL", "LOP3", "IMAD.WIDE (+shift)", "MUFU.LG2", "FFMA" };
     const int iters = 4000;
-    for( int which = 0; which < 7; ++which )
-    {
-        k_chain<<<1, 32>>>( which, out, cyc, 10 );
-        k_chain<<<1, 32>>>( which, out, cyc, iters );
-        long long h = 0;
-        cudaMemcpy( &h, cyc, sizeof( h ), cudaMemcpyDeviceToHost );
-        printf( "%-20s dependent-issue latency %.2f cycles\n", names[which], double( h ) / ( 16.0 * iters ) );
+#define RUN( W )                                                                                                       \
+    {                                                                                                                  \
+        k_chain<W><<<1, 32>>>( out, cyc, 10 );                                                                         \
+        k_chain<W><<<1, 32>>>( out, cyc, iters );                                                                      \
+        long long h = 0;                                                                                               \
+        cudaMemcpy( &h, cyc, sizeof( h ), cudaMemcpyDeviceToHost );                                                    \
+        printf( "%-20s dependent-issue latency %.2f cycles\n", names[W], double( h ) / ( 16.0 * iters ) );             \
     }
+    RUN( 0 ) RUN( 1 ) RUN( 2 ) RUN( 3 ) RUN( 4 ) RUN( 5 ) RUN( 6 )
     return 0;
 }
