@@ -41,7 +41,7 @@ namespace dev
 namespace
 {
 
-constexpr int FFT_THREADS  = 1024; // upper bound; launches use fft_threads( work items )
+constexpr int FFT_THREADS  = 512;  // upper bound (128 registers: a radix-16 butterfly lives in 64); launches use fft_threads( work items )
 constexpr int MAX_RADICES  = 16;
 constexpr int MAX_SMEM_FFT = 200 * 1024;
 
@@ -50,6 +50,7 @@ struct FFTPlan1D
     int n       = 1;
     int n_radix = 0;
     int pow2    = 0; // n is a power of two (all strides are powers of two: shifts instead of divisions)
+    int fast16  = 0; // power of two >= 64: radices 16 ... 16 [2 | 4 | 8], served by block_fft16
     int radix[MAX_RADICES];
     const double2 * twiddle = nullptr; // exp(-2 pi i k / n), k < n
 };
@@ -74,11 +75,211 @@ __device__ __forceinline__ double2 tw( const FFTPlan1D & plan, int k )
     return INVERSE ? make_double2( w.x, -w.y ) : w;
 }
 
+// exp(-2 pi i k / 32), k < 32: twiddles of the in-register transforms (lengths up to 32)
+static __constant__ double2 TW32[32] = {
+    { 1, 0 },
+    { 0.98078528040323043, -0.19509032201612825 },
+    { 0.92387953251128674, -0.38268343236508978 },
+    { 0.83146961230254524, -0.55557023301960218 },
+    { 0.70710678118654757, -0.70710678118654746 },
+    { 0.55557023301960229, -0.83146961230254524 },
+    { 0.38268343236508984, -0.92387953251128674 },
+    { 0.19509032201612833, -0.98078528040323043 },
+    { 0, -1 },
+    { -0.19509032201612819, -0.98078528040323043 },
+    { -0.38268343236508973, -0.92387953251128674 },
+    { -0.55557023301960196, -0.83146961230254546 },
+    { -0.70710678118654746, -0.70710678118654757 },
+    { -0.83146961230254535, -0.55557023301960218 },
+    { -0.92387953251128674, -0.38268343236508989 },
+    { -0.98078528040323043, -0.19509032201612861 },
+    { -1, 0 },
+    { -0.98078528040323043, 0.19509032201612836 },
+    { -0.92387953251128685, 0.38268343236508967 },
+    { -0.83146961230254546, 0.55557023301960196 },
+    { -0.70710678118654768, 0.70710678118654746 },
+    { -0.55557023301960218, 0.83146961230254524 },
+    { -0.38268343236509034, 0.92387953251128652 },
+    { -0.19509032201612866, 0.98078528040323032 },
+    { 0, 1 },
+    { 0.1950903220161283, 0.98078528040323043 },
+    { 0.38268343236509, 0.92387953251128663 },
+    { 0.55557023301960184, 0.83146961230254546 },
+    { 0.70710678118654735, 0.70710678118654768 },
+    { 0.83146961230254524, 0.55557023301960218 },
+    { 0.92387953251128652, 0.38268343236509039 },
+    { 0.98078528040323032, 0.19509032201612872 } };
+
+
+// ---------------------------------------------------------------------------------------------
+// Power-of-two lengths >= 64: in-register radix-16 stages. n = 16 * 16 * ... * rem (rem = 2, 4, 8 or nothing): three
+// stages for 4096 instead of six radix-4 ones. A thread owns 16 elements per stage (one radix-16 butterfly, or 16/R
+// butterflies of the last radix R), computed as 4 x 4 (8: 4 x 2) small transforms in registers. The exchange between
+// stages goes through ONE shared buffer in place: all threads read their inputs, barrier, all write their outputs.
+// Between stages the buffer is padded by one element per 16 (index a -> a + a/16), which makes the stride-16 writes of
+// the first stage conflict-free; the first stage reads and the last stage writes the caller's plain layout.
+// Same Stockham indexing as the generic path: inputs a_i = x[q + s (p + m i)], outputs x[q + s (R p + i)].
+// ---------------------------------------------------------------------------------------------
+template<bool INVERSE>
+__device__ __forceinline__ double2 tw32( int k )
+{
+    const double2 w = TW32[k];
+    return INVERSE ? make_double2( w.x, -w.y ) : w;
+}
+template<bool INVERSE>
+__device__ __forceinline__ void dft4_inplace( double2 & a0, double2 & a1, double2 & a2, double2 & a3 )
+{
+    const double2 b0 = cadd( a0, a2 ), b1 = csub( a0, a2 ), b2 = cadd( a1, a3 ), b3 = csub( a1, a3 );
+    const double2 jb3 = INVERSE ? make_double2( -b3.y, b3.x ) : make_double2( b3.y, -b3.x ); // -+ i b3
+    a0 = cadd( b0, b2 );
+    a1 = cadd( b1, jb3 );
+    a2 = csub( b0, b2 );
+    a3 = csub( b1, jb3 );
+}
+// In-register transform of length R, natural order in and out.
+template<bool INVERSE, int R>
+__device__ __forceinline__ void dft_small( double2 ( &a )[R] )
+{
+    if( R == 2 )
+    {
+        const double2 t = a[0];
+        a[0]            = cadd( t, a[1] );
+        a[1]            = csub( t, a[1] );
+    }
+    else if( R == 4 )
+        dft4_inplace<INVERSE>( a[0], a[1 % R], a[2 % R], a[3 % R] );
+    else if( R == 8 )
+    {
+        // n = 2 n1 + n2, k = k1 + 4 k2: y[n2][k1] = DFT4_{n1} x[2 n1 + n2] (left in slot 2 k1 + n2), times W8^{n2 k1},
+        // X[k1 + 4 k2] = DFT2_{n2} y[n2][k1] (left in slot 2 k1 + k2)
+#pragma unroll
+        for( int n2 = 0; n2 < 2; ++n2 )
+            dft4_inplace<INVERSE>( a[n2 % R], a[( 2 + n2 ) % R], a[( 4 + n2 ) % R], a[( 6 + n2 ) % R] );
+#pragma unroll
+        for( int k1 = 1; k1 < 4; ++k1 )
+            a[( 2 * k1 + 1 ) % R] = cmul( a[( 2 * k1 + 1 ) % R], tw32<INVERSE>( 4 * k1 ) );
+        double2 o[R];
+#pragma unroll
+        for( int k1 = 0; k1 < 4; ++k1 )
+        {
+            o[k1 % R]         = cadd( a[( 2 * k1 ) % R], a[( 2 * k1 + 1 ) % R] );
+            o[( k1 + 4 ) % R] = csub( a[( 2 * k1 ) % R], a[( 2 * k1 + 1 ) % R] );
+        }
+#pragma unroll
+        for( int i = 0; i < R; ++i )
+            a[i] = o[i];
+    }
+    else
+    {
+        // n = 4 n1 + n2, k = k1 + 4 k2: y[n2][k1] = DFT4_{n1} x[4 n1 + n2] (slot 4 k1 + n2), times W16^{n2 k1},
+        // X[k1 + 4 k2] = DFT4_{n2} y[n2][k1] (slot 4 k1 + k2)
+#pragma unroll
+        for( int n2 = 0; n2 < 4; ++n2 )
+            dft4_inplace<INVERSE>( a[n2 % R], a[( 4 + n2 ) % R], a[( 8 + n2 ) % R], a[( 12 + n2 ) % R] );
+#pragma unroll
+        for( int k1 = 1; k1 < 4; ++k1 )
+#pragma unroll
+            for( int n2 = 1; n2 < 4; ++n2 )
+                a[( 4 * k1 + n2 ) % R] = cmul( a[( 4 * k1 + n2 ) % R], tw32<INVERSE>( 2 * n2 * k1 ) );
+#pragma unroll
+        for( int k1 = 0; k1 < 4; ++k1 )
+            dft4_inplace<INVERSE>( a[( 4 * k1 ) % R], a[( 4 * k1 + 1 ) % R], a[( 4 * k1 + 2 ) % R], a[( 4 * k1 + 3 ) % R] );
+        double2 o[R];
+#pragma unroll
+        for( int k1 = 0; k1 < 4; ++k1 )
+#pragma unroll
+            for( int k2 = 0; k2 < 4; ++k2 )
+                o[( k1 + 4 * k2 ) % R] = a[( 4 * k1 + k2 ) % R];
+#pragma unroll
+        for( int i = 0; i < R; ++i )
+            a[i] = o[i];
+    }
+}
+
+constexpr int FFT_E = 8, FFT_LG_E = 3; // elements a thread owns in the in-register stages (16: 3 stages for 4096 but
+                                       // the twiddles push ptxas over 128 registers; 8: 4 stages, no spills)
+template<bool INVERSE, int R>
+__device__ __forceinline__ void fft16_stage(
+    const FFTPlan1D & plan, double2 * x, const int ncol, const int lg_ncol, const int s, const int lg_s, const bool first, const bool last )
+{
+    constexpr int PER  = FFT_E / R; // butterflies per thread
+    const int n        = plan.n;
+    const int per_col  = n >> FFT_LG_E;        // threads per transform
+    const int step     = n / R;                // s m: distance of the inputs of a butterfly
+    const bool working = int( threadIdx.x ) < ( per_col << lg_ncol );
+    const int col = threadIdx.x & ( ncol - 1 ), tt = threadIdx.x >> lg_ncol;
+    double2 v[PER][R];
+    if( working )
+    {
+#pragma unroll
+        for( int jj = 0; jj < PER; ++jj )
+        {
+            const int item = tt + per_col * jj; // = q + s p
+#pragma unroll
+            for( int i = 0; i < R; ++i )
+            {
+                const int a   = item + step * i;
+                const int idx = first ? a : a + ( a >> 4 );
+                v[jj][i]      = x[( idx << lg_ncol ) + col];
+            }
+            dft_small<INVERSE, R>( v[jj] );
+        }
+    }
+    __syncthreads();
+    if( working )
+    {
+#pragma unroll
+        for( int jj = 0; jj < PER; ++jj )
+        {
+            const int item = tt + per_col * jj;
+            const int q = item & ( s - 1 ), p = item >> lg_s;
+#pragma unroll
+            for( int i = 0; i < R; ++i )
+            {
+                double2 val = v[jj][i];
+                if( !last && i > 0 )
+                    val = cmul( val, tw<INVERSE>( plan, i * p * s ) ); // w_{n/s}^{p i}; p = 0 in the last stage
+                const int o   = q + s * ( R * p + i );
+                const int idx = last ? o : o + ( o >> 4 );
+                x[( idx << lg_ncol ) + col] = val;
+            }
+        }
+    }
+    __syncthreads();
+}
+
+// In place in x (which needs room for n * ncol * 17 / 16 elements). All threads of the CTA must call;
+// blockDim.x >= n / FFT_E * ncol, ncol a power of two.
+template<bool INVERSE>
+__device__ double2 * block_fft16( const FFTPlan1D & plan, double2 * x, int ncol )
+{
+    const int lg_ncol = 31 - __clz( ncol );
+    int s = 1, lg_s = 0;
+    for( int stage = 0; stage < plan.n_radix; ++stage )
+    {
+        const int r      = plan.radix[stage];
+        const bool first = stage == 0, last = stage == plan.n_radix - 1;
+        if( r == 16 && FFT_E >= 16 )
+            fft16_stage<INVERSE, FFT_E >= 16 ? 16 : 8>( plan, x, ncol, lg_ncol, s, lg_s, first, last );
+        else if( r == 8 )
+            fft16_stage<INVERSE, 8>( plan, x, ncol, lg_ncol, s, lg_s, first, last );
+        else if( r == 4 )
+            fft16_stage<INVERSE, 4>( plan, x, ncol, lg_ncol, s, lg_s, first, last );
+        else
+            fft16_stage<INVERSE, 2>( plan, x, ncol, lg_ncol, s, lg_s, first, last );
+        s *= r;
+        lg_s += 31 - __clz( r );
+    }
+    return x;
+}
+
 // In-shared-memory Stockham autosort FFT of `ncol` independent sequences of length plan.n stored as x[j * ncol + col].
 // Returns the buffer (x or y) that holds the result. All threads of the CTA must call.
 template<bool INVERSE>
 __device__ double2 * block_fft( const FFTPlan1D & plan, double2 * x, double2 * y, int ncol )
 {
+    if( plan.fast16 && ( ncol & ( ncol - 1 ) ) == 0 && int( blockDim.x ) >= ( plan.n >> FFT_LG_E ) * ncol )
+        return block_fft16<INVERSE>( plan, x, ncol );
     const int n = plan.n;
     int s       = 1; // stride = product of the radices already processed
     for( int stage = 0; stage < plan.n_radix; ++stage )
@@ -368,41 +569,6 @@ static __global__ void __launch_bounds__( FFT_THREADS ) k_ddi_c_mult(
 }
 
 
-// exp(-2 pi i k / 32), k < 32: twiddles of the in-register transforms (lengths up to 32)
-static __constant__ double2 TW32[32] = {
-    { 1, 0 },
-    { 0.98078528040323043, -0.19509032201612825 },
-    { 0.92387953251128674, -0.38268343236508978 },
-    { 0.83146961230254524, -0.55557023301960218 },
-    { 0.70710678118654757, -0.70710678118654746 },
-    { 0.55557023301960229, -0.83146961230254524 },
-    { 0.38268343236508984, -0.92387953251128674 },
-    { 0.19509032201612833, -0.98078528040323043 },
-    { 0, -1 },
-    { -0.19509032201612819, -0.98078528040323043 },
-    { -0.38268343236508973, -0.92387953251128674 },
-    { -0.55557023301960196, -0.83146961230254546 },
-    { -0.70710678118654746, -0.70710678118654757 },
-    { -0.83146961230254535, -0.55557023301960218 },
-    { -0.92387953251128674, -0.38268343236508989 },
-    { -0.98078528040323043, -0.19509032201612861 },
-    { -1, 0 },
-    { -0.98078528040323043, 0.19509032201612836 },
-    { -0.92387953251128685, 0.38268343236508967 },
-    { -0.83146961230254546, 0.55557023301960196 },
-    { -0.70710678118654768, 0.70710678118654746 },
-    { -0.55557023301960218, 0.83146961230254524 },
-    { -0.38268343236509034, 0.92387953251128652 },
-    { -0.19509032201612866, 0.98078528040323032 },
-    { 0, 1 },
-    { 0.1950903220161283, 0.98078528040323043 },
-    { 0.38268343236509, 0.92387953251128663 },
-    { 0.55557023301960184, 0.83146961230254546 },
-    { 0.70710678118654735, 0.70710678118654768 },
-    { 0.83146961230254524, 0.55557023301960218 },
-    { 0.92387953251128652, 0.38268343236509039 },
-    { 0.98078528040323032, 0.19509032201612872 } };
-
 // 3': the same for small power-of-two Pc (thin films): ONE THREAD per (kb, ka) column does the length-PC transforms of
 // all three components in registers -- no shared memory, no barriers, fully coalesced along ka. REAL_D: the tensor
 // spectrum is real (single sublattice: D(-r) = D(r)) and stored as doubles, halving the dominant read stream.
@@ -685,10 +851,29 @@ struct DDIPlan
 
 namespace
 {
+bool env_flag_off( const char * name )
+{
+    const char * v = std::getenv( name );
+    return v && v[0] == '0';
+}
+
 void make_plan_1d( FFTPlan1D & plan, double2 *& table, int n )
 {
     plan.n         = n;
-    const auto fac = factorize( n );
+    plan.fast16    = ( ( n & ( n - 1 ) ) == 0 && n >= 64 && !env_flag_off( "SPIRIT_B200_FFT16" ) ) ? 1 : 0;
+    auto fac       = factorize( n );
+    if( plan.fast16 )
+    {
+        fac.clear();
+        int rest = n;
+        while( rest % FFT_E == 0 )
+        {
+            fac.push_back( FFT_E );
+            rest /= FFT_E;
+        }
+        if( rest > 1 )
+            fac.push_back( rest );
+    }
     if( fac.size() > std::size_t( MAX_RADICES ) )
         throw std::runtime_error( "spirit_b200: FFT length with too many factors" );
     plan.n_radix = int( fac.size() );
@@ -814,7 +999,9 @@ DDIPlan * ddi_plan_create( const Hamiltonian & ham, const StencilParams & sp, cu
     plan->ncol_c = choose_ncol( d.Pc, nq, d.Ha );
     plan->smem_a = std::size_t( d.Pa ) * 2 * sizeof( double2 );
     plan->smem_b = std::size_t( d.Pb ) * 2 * sizeof( double2 ) * plan->ncol_b;
-    plan->smem_c = std::size_t( d.Pc ) * 2 * sizeof( double2 ) * plan->ncol_c * nq;
+    // + one sixteenth of a buffer: the padded in-place stages of block_fft16 run past the LAST component's second buffer
+    plan->smem_c = std::size_t( d.Pc ) * 2 * sizeof( double2 ) * plan->ncol_c * nq
+                   + ( std::size_t( d.Pc ) * plan->ncol_c / 16 + 1 ) * sizeof( double2 );
     if( plan->smem_a > std::size_t( MAX_SMEM_FFT ) )
         throw std::runtime_error( "spirit_b200: padded lattice dimension a too long for the shared-memory FFT passes" );
     allow_smem( k_ddi_fwd_a, plan->smem_a );

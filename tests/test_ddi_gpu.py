@@ -19,6 +19,15 @@ DDI_CASES = [
     ("default", {"n_basis_cells": "12 10 1", "boundary_conditions": "0 0 0", "ddi_method": "fft"}),
     ("default", {"n_basis_cells": "10 1 1", "boundary_conditions": "0 0 0", "ddi_method": "fft"}),
     ("cubic256", {"n_basis_cells": "18 14 6", "boundary_conditions": "0 0 0", "ddi_method": "fft", "llg_temperature": "0"}),
+    # padded lengths that are powers of two >= 64: the in-register radix-8 stages (64 = 8.8, 128 = 8.8.2, 256 = 8.8.4, 512, 1024)
+    ("cubic256", {"n_basis_cells": "32 32 2", "boundary_conditions": "0 0 0", "ddi_method": "fft", "llg_temperature": "0"}),
+    ("cubic256", {"n_basis_cells": "64 16 2", "boundary_conditions": "0 0 0", "ddi_method": "fft", "llg_temperature": "0"}),
+    ("cubic256", {"n_basis_cells": "128 32 1", "boundary_conditions": "0 0 0", "ddi_method": "fft", "llg_temperature": "0"}),
+    ("cubic256", {"n_basis_cells": "256 4 2", "boundary_conditions": "0 1 0", "ddi_method": "fft", "llg_temperature": "0",
+                  "ddi_n_periodic_images": "0 2 0"}),
+    ("cubic256", {"n_basis_cells": "512 2 1", "boundary_conditions": "0 0 0", "ddi_method": "fft", "llg_temperature": "0"}),
+    ("cubic256", {"n_basis_cells": "64 64 32", "boundary_conditions": "1 1 0", "ddi_method": "fft", "llg_temperature": "0",
+                  "ddi_n_periodic_images": "1 1 0", "ddi_pb_zero_padding": "0"}),
 ]
 
 
