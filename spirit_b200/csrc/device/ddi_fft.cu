@@ -410,6 +410,46 @@ static __global__ void __launch_bounds__( FFT_THREADS ) k_fft_pass( const __grid
     }
 }
 
+// The same pass for FFTPlan1D::fast16 lengths: ONE shared buffer (block_fft16 works in place), exactly one radix-8 work
+// item per thread ((n / 8) << lg_ncol threads), no integer division (ncol and the per-rank split of the distributed
+// layout are powers of two, lg = 31 stands for "no split"), a thread keeps its column for the whole pass. Half the
+// shared memory and half the threads of k_fft_pass: two or more CTAs per SM, so that the loads of one overlap the
+// butterflies of another.
+__device__ __forceinline__ std::size_t pass_offset16( int j, std::size_t js, int lg_split, std::size_t split_stride )
+{
+    return std::size_t( j >> lg_split ) * split_stride + std::size_t( unsigned( j ) & ( ( 1u << lg_split ) - 1u ) ) * js;
+}
+template<bool INVERSE>
+static __global__ void __launch_bounds__( FFT_THREADS ) k_fft_pass16(
+    const __grid_constant__ FFTPlan1D plan, const __grid_constant__ PassArgs a, const int lg_ncol, const int lg_in_split,
+    const int lg_out_split )
+{
+    extern __shared__ double2 smem[];
+    const int n = plan.n, ncol = 1 << lg_ncol;
+    const int o = blockIdx.y, u0 = blockIdx.x << lg_ncol;
+    const int col = threadIdx.x & ( ncol - 1 ), j0 = threadIdx.x >> lg_ncol, jstep = blockDim.x >> lg_ncol;
+    const bool valid   = u0 + col < a.n_u;
+    const double2 * in = a.in + std::size_t( o ) * a.in_os + u0 + col;
+    for( int j = j0; j < n; j += jstep )
+    {
+        double2 v = make_double2( 0.0, 0.0 );
+        if( valid && j < a.n_in )
+            v = in[pass_offset16( j, a.in_js, lg_in_split, a.in_split_stride )];
+        smem[( j << lg_ncol ) + col] = v;
+    }
+    __syncthreads();
+    block_fft16<INVERSE>( plan, smem, ncol );
+    if( valid )
+    {
+        double2 * out = a.out + std::size_t( o ) * a.out_os + u0 + col;
+        for( int j = j0; j < a.n_out; j += jstep )
+        {
+            const double2 v = smem[( j << lg_ncol ) + col];
+            out[pass_offset16( j, a.out_js, lg_out_split, a.out_split_stride )] = make_double2( a.scale * v.x, a.scale * v.y );
+        }
+    }
+}
+
 // Pass a for a dense REAL input (setup of the tensor spectrum): real row of length n -> half spectrum
 static __global__ void __launch_bounds__( FFT_THREADS ) k_fft_real_rows(
     const __grid_constant__ FFTPlan1D plan, const double * __restrict__ in, double2 * __restrict__ out, int Ha )
@@ -568,6 +608,116 @@ static __global__ void __launch_bounds__( FFT_THREADS ) k_ddi_c_mult(
     }
 }
 
+
+// 3 for one sublattice and a FFTPlan1D::fast16 length Pc: the three components transformed IN PLACE (block_fft16), the
+// tensor multiply in place as well (one sublattice: F(k) needs S(k) of the same point only), (Pc / 8) << lg_ncol threads.
+// The tensor spectrum is stored the way this kernel walks it, D^t[kb][ka tile][comp6][kc][col]: one contiguous block per
+// CTA, read with unit stride (REAL_D: as doubles, the spectrum of a single sublattice is real).
+template<bool REAL_D>
+static __global__ void __launch_bounds__( FFT_THREADS ) k_ddi_c_mult16(
+    const __grid_constant__ FFTPlan1D plan, const __grid_constant__ DDIDims d, double2 * __restrict__ B,
+    const void * __restrict__ Dt_v, const int lg_ncol )
+{
+    extern __shared__ double2 smem[];
+    const int n = plan.n, ncol = 1 << lg_ncol;
+    const int tile_elems   = n << lg_ncol;
+    const int bufp         = tile_elems + ( tile_elems >> 4 ) + 1; // room for the padded layout between the stages
+    const int kb = blockIdx.y, u0 = blockIdx.x << lg_ncol;
+    const int col = threadIdx.x & ( ncol - 1 ), j0 = threadIdx.x >> lg_ncol, jstep = blockDim.x >> lg_ncol;
+    const bool valid       = u0 + col < d.Ha;
+    const std::size_t plane = std::size_t( d.Pb ) * d.Ha;
+    double2 * column       = B + std::size_t( kb ) * d.Ha + u0 + col;
+    // element (q, c) of the column: c_operand without divisions (c = j0 + k jstep walks the per-rank blocks in order)
+    for( int q = 0; q < 3; ++q )
+    {
+        double2 * x = smem + q * bufp;
+        int blk = j0 / d.c_block, rem = j0 - blk * d.c_block;
+        for( int j = j0; j < n; j += jstep )
+        {
+            double2 v = make_double2( 0.0, 0.0 );
+            if( valid && j < d.Nc )
+                v = column[std::size_t( blk ) * d.block_stride + std::size_t( q ) * d.q_stride + std::size_t( rem ) * plane];
+            x[( j << lg_ncol ) + col] = v;
+            rem += jstep;
+            while( rem >= d.c_block )
+            {
+                rem -= d.c_block;
+                ++blk;
+            }
+        }
+    }
+    __syncthreads();
+    for( int q = 0; q < 3; ++q )
+        block_fft16<false>( plan, smem + q * bufp, ncol );
+    {
+        const std::size_t block = ( std::size_t( kb ) * gridDim.x + blockIdx.x ) * 6 * std::size_t( tile_elems );
+        for( int item = threadIdx.x; item < tile_elems; item += blockDim.x )
+        {
+            const double2 sx = smem[item], sy = smem[bufp + item], sz = smem[2 * bufp + item];
+            double2 fx, fy, fz;
+            if( REAL_D )
+            {
+                const double * Dp = static_cast<const double *>( Dt_v ) + block + item;
+                const double Dxx = __ldg( Dp ), Dxy = __ldg( Dp + tile_elems ), Dxz = __ldg( Dp + 2 * tile_elems );
+                const double Dyy = __ldg( Dp + 3 * tile_elems ), Dyz = __ldg( Dp + 4 * tile_elems ), Dzz = __ldg( Dp + 5 * tile_elems );
+                fx = make_double2( Dxx * sx.x + Dxy * sy.x + Dxz * sz.x, Dxx * sx.y + Dxy * sy.y + Dxz * sz.y );
+                fy = make_double2( Dxy * sx.x + Dyy * sy.x + Dyz * sz.x, Dxy * sx.y + Dyy * sy.y + Dyz * sz.y );
+                fz = make_double2( Dxz * sx.x + Dyz * sy.x + Dzz * sz.x, Dxz * sx.y + Dyz * sy.y + Dzz * sz.y );
+            }
+            else
+            {
+                const double2 * Dp = static_cast<const double2 *>( Dt_v ) + block + item;
+                const double2 Dxx = __ldg( Dp ), Dxy = __ldg( Dp + tile_elems ), Dxz = __ldg( Dp + 2 * tile_elems );
+                const double2 Dyy = __ldg( Dp + 3 * tile_elems ), Dyz = __ldg( Dp + 4 * tile_elems ), Dzz = __ldg( Dp + 5 * tile_elems );
+                fx = cadd( cmul( Dxx, sx ), cadd( cmul( Dxy, sy ), cmul( Dxz, sz ) ) );
+                fy = cadd( cmul( Dxy, sx ), cadd( cmul( Dyy, sy ), cmul( Dyz, sz ) ) );
+                fz = cadd( cmul( Dxz, sx ), cadd( cmul( Dyz, sy ), cmul( Dzz, sz ) ) );
+            }
+            smem[item]            = fx;
+            smem[bufp + item]     = fy;
+            smem[2 * bufp + item] = fz;
+        }
+    }
+    __syncthreads();
+    for( int q = 0; q < 3; ++q )
+        block_fft16<true>( plan, smem + q * bufp, ncol );
+    if( valid )
+        for( int q = 0; q < 3; ++q )
+        {
+            const double2 * x = smem + q * bufp;
+            int blk = j0 / d.c_block, rem = j0 - blk * d.c_block;
+            for( int j = j0; j < d.Nc; j += jstep )
+            {
+                column[std::size_t( blk ) * d.block_stride + std::size_t( q ) * d.q_stride + std::size_t( rem ) * plane] = x[( j << lg_ncol ) + col];
+                rem += jstep;
+                while( rem >= d.c_block )
+                {
+                    rem -= d.c_block;
+                    ++blk;
+                }
+            }
+        }
+}
+
+// D^[comp6][kc][kb][ka] -> D^t[kb][ka tile][comp6][kc][col] (setup). Columns past Ha in the last tile stay zero.
+template<bool REAL_D>
+static __global__ void k_ddi_tile_tensor( const __grid_constant__ DDIDims d, const double2 * __restrict__ Dhat, void * __restrict__ Dt_v, const int lg_ncol )
+{
+    const std::size_t half = std::size_t( d.Pc ) * d.Pb * d.Ha;
+    const std::size_t i    = blockIdx.x * std::size_t( blockDim.x ) + threadIdx.x;
+    if( i >= 6 * half )
+        return;
+    const int ka = int( i % d.Ha ), kb = int( ( i / d.Ha ) % d.Pb ), kc = int( ( i / ( std::size_t( d.Ha ) * d.Pb ) ) % d.Pc );
+    const int comp = int( i / half );
+    const int ntiles = ( d.Ha + ( 1 << lg_ncol ) - 1 ) >> lg_ncol;
+    const std::size_t tile_elems = std::size_t( d.Pc ) << lg_ncol;
+    const std::size_t o = ( ( std::size_t( kb ) * ntiles + ( ka >> lg_ncol ) ) * 6 + comp ) * tile_elems + ( std::size_t( kc ) << lg_ncol )
+                          + ( ka & ( ( 1 << lg_ncol ) - 1 ) );
+    if( REAL_D )
+        static_cast<double *>( Dt_v )[o] = Dhat[i].x;
+    else
+        static_cast<double2 *>( Dt_v )[o] = Dhat[i];
+}
 
 // 3': the same for small power-of-two Pc (thin films): ONE THREAD per (kb, ka) column does the length-PC transforms of
 // all three components in registers -- no shared memory, no barriers, fully coalesced along ka. REAL_D: the tensor
@@ -737,6 +887,117 @@ static __global__ void __launch_bounds__( FFT_THREADS ) k_ddi_inv_a(
     }
 }
 
+// 1 and 5 for even Pa with a FFTPlan1D::fast16 half length m = Pa / 2: the real row as a complex sequence of half the
+// length, z_j = x_2j + i x_2j+1, one complex transform of length m (plan_h), and the split / merge step
+//   forward   X_k = E_k + w^k O_k,  E_k = (Z_k + conj Z_{m-k}) / 2,  O_k = -i (Z_k - conj Z_{m-k}) / 2,  w = exp(-2 pi i / Pa)
+//   inverse   Z_k = (X_k + conj X_{m-k}) + i w^{-k} (X_k - conj X_{m-k})   ->   Pa x_2j = Re z_j, Pa x_2j+1 = Im z_j
+// instead of a length-Pa complex transform with zero imaginary parts: half the butterflies, half the shared memory.
+// A CTA takes 1 << lg_nrow consecutive rows (b + Nb c) of one component as the "columns" of block_fft16;
+// (m / 8) << lg_nrow threads. Thread -> (4 consecutive elements of a row, row, group of 4): global accesses are 64-byte
+// segments along the row, shared-memory accesses of a warp stay inside one 512-byte window.
+__device__ __forceinline__ void row_map( int lg_nrow, int & row, int & jlow, int & jhigh, int & jhigh_step )
+{
+    const int t = threadIdx.x;
+    jlow        = t & 3;
+    row         = ( t >> 2 ) & ( ( 1 << lg_nrow ) - 1 );
+    jhigh       = t >> ( 2 + lg_nrow );
+    jhigh_step  = blockDim.x >> ( 2 + lg_nrow );
+}
+
+static __global__ void __launch_bounds__( FFT_THREADS ) k_ddi_fwd_a16(
+    const __grid_constant__ FFTPlan1D plan_h, const double2 * __restrict__ tw_full, const __grid_constant__ DDIDims d,
+    ConstField3 spins, double2 * __restrict__ A, const int lg_nrow )
+{
+    extern __shared__ double2 smem[];
+    const int m = plan_h.n, nrow = 1 << lg_nrow;
+    int rl, jlow, jhigh, jstep;
+    row_map( lg_nrow, rl, jlow, jhigh, jstep );
+    const int q = blockIdx.y, comp = q % 3, ib = q / 3;
+    const int row    = ( blockIdx.x << lg_nrow ) + rl;
+    const bool valid = row < d.Nb * d.Nc;
+    const int b = row % d.Nb, c = row / d.Nb;
+    const std::size_t site0 = std::size_t( d.Na ) * d.NB * b + std::size_t( d.plane_stride ) * ( c + d.halo ) + ib;
+    const double mu         = d.mu_s[ib];
+    for( int jh = jhigh; 4 * jh < m; jh += jstep )
+    {
+        const int j = 4 * jh + jlow;
+        double2 z   = make_double2( 0.0, 0.0 );
+        if( valid && 2 * j < d.Na )
+        {
+            z.x = mu * __ldg( spins.base + elem_offset( site0 + std::size_t( d.NB ) * ( 2 * j ) ) + comp * FIELD_BLOCK );
+            if( 2 * j + 1 < d.Na )
+                z.y = mu * __ldg( spins.base + elem_offset( site0 + std::size_t( d.NB ) * ( 2 * j + 1 ) ) + comp * FIELD_BLOCK );
+        }
+        smem[( j << lg_nrow ) + rl] = z;
+    }
+    __syncthreads();
+    block_fft16<false>( plan_h, smem, nrow );
+    if( !valid )
+        return;
+    double2 * out = A + ( ( std::size_t( q ) * d.Nc + c ) * d.Nb + b ) * d.Ha;
+    for( int jh = jhigh; 4 * jh < m; jh += jstep )
+    {
+        const int k      = 4 * jh + jlow;
+        const double2 Zk = smem[( k << lg_nrow ) + rl];
+        const double2 Zm = smem[( ( ( m - k ) & ( m - 1 ) ) << lg_nrow ) + rl]; // Z_m = Z_0
+        const double2 E  = make_double2( 0.5 * ( Zk.x + Zm.x ), 0.5 * ( Zk.y - Zm.y ) );
+        const double2 O  = make_double2( 0.5 * ( Zk.y + Zm.y ), -0.5 * ( Zk.x - Zm.x ) );
+        out[k]           = cadd( E, cmul( __ldg( tw_full + k ), O ) );
+    }
+    if( jhigh == 0 && jlow == 0 )
+    {
+        const double2 Z0 = smem[rl];
+        out[m]           = make_double2( Z0.x - Z0.y, 0.0 );
+    }
+}
+
+static __global__ void __launch_bounds__( FFT_THREADS ) k_ddi_inv_a16(
+    const __grid_constant__ FFTPlan1D plan_h, const double2 * __restrict__ tw_full, const __grid_constant__ DDIDims d,
+    const double2 * __restrict__ A, Field3 g, const double inv_P, const int lg_nrow )
+{
+    extern __shared__ double2 smem[];
+    const int m = plan_h.n, nrow = 1 << lg_nrow;
+    int rl, jlow, jhigh, jstep;
+    row_map( lg_nrow, rl, jlow, jhigh, jstep );
+    const int q = blockIdx.y, comp = q % 3, ib = q / 3;
+    const int row    = ( blockIdx.x << lg_nrow ) + rl;
+    const bool valid = row < d.Nb * d.Nc;
+    const int b = row % d.Nb, c = row / d.Nb;
+    const double2 * in = A + ( ( std::size_t( q ) * d.Nc + c ) * d.Nb + b ) * d.Ha;
+    for( int jh = jhigh; 4 * jh < m; jh += jstep )
+    {
+        const int k = 4 * jh + jlow;
+        double2 Z   = make_double2( 0.0, 0.0 );
+        if( valid )
+        {
+            const double2 Xk = in[k], Xm = in[m - k];
+            const double2 S  = make_double2( Xk.x + Xm.x, Xk.y - Xm.y ); // X_k + conj X_{m-k}
+            const double2 D  = make_double2( Xk.x - Xm.x, Xk.y + Xm.y ); // X_k - conj X_{m-k}
+            const double2 w  = __ldg( tw_full + k );                     // exp(-2 pi i k / Pa); the inverse needs its conjugate
+            const double2 T  = cmul( make_double2( w.x, -w.y ), D );
+            Z                = make_double2( S.x - T.y, S.y + T.x ); // S + i T
+        }
+        smem[( k << lg_nrow ) + rl] = Z;
+    }
+    __syncthreads();
+    block_fft16<true>( plan_h, smem, nrow );
+    if( !valid )
+        return;
+    const std::size_t site0 = std::size_t( d.Na ) * d.NB * b + std::size_t( d.plane_stride ) * ( c + d.halo ) + ib;
+    const double f          = -d.mu_s[ib] * inv_P;
+    for( int jh = jhigh; 4 * jh < m; jh += jstep )
+    {
+        const int j = 4 * jh + jlow;
+        if( 2 * j < d.Na )
+        {
+            const double2 z = smem[( j << lg_nrow ) + rl];
+            g.base[elem_offset( site0 + std::size_t( d.NB ) * ( 2 * j ) ) + comp * FIELD_BLOCK] = f * z.x;
+            if( 2 * j + 1 < d.Na )
+                g.base[elem_offset( site0 + std::size_t( d.NB ) * ( 2 * j + 1 ) ) + comp * FIELD_BLOCK] = f * z.y;
+        }
+    }
+}
+
 // Dipole tensor component `comp6` of sublattice pair (b1, b2) on the padded lattice, with periodic images
 // (FFT_Dipole_Matrices, Hamiltonian_Heisenberg.cpp:1406-1499)
 struct TensorGeom
@@ -830,6 +1091,18 @@ struct DDIPlan
     int ncol_b = 1, ncol_c = 1;
     std::size_t smem_a = 0, smem_b = 0, smem_c = 0;
     std::uint64_t launches_setup = 0;
+    // fast variants (power-of-two lengths, see k_fft_pass16 / k_ddi_c_mult16 / k_ddi_fwd_a16)
+    struct Fast
+    {
+        bool on = false;
+        int lg = 0, threads = 0; // lg(columns or rows per CTA), CTA size
+        std::size_t smem = 0;
+    } fast_a, fast_b, fast_c;
+    FFTPlan1D plan_ah;             // length Pa / 2
+    double2 * twiddle_ah = nullptr;
+    int lg_split         = 31;     // lg of the per-rank kb block (distributed layout), 31: no split
+    void * Dt            = nullptr; // tensor spectrum in the tile order of k_ddi_c_mult16
+    bool Dt_real         = false;
 
     ~DDIPlan()
     {
@@ -840,6 +1113,10 @@ struct DDIPlan
             cudaFree( Dhat );
         if( Dhat_real )
             cudaFree( Dhat_real );
+        if( Dt )
+            cudaFree( Dt );
+        if( twiddle_ah )
+            cudaFree( twiddle_ah );
         if( A )
             cudaFree( A );
         if( B )
@@ -1010,6 +1287,49 @@ DDIPlan * ddi_plan_create( const Hamiltonian & ham, const StencilParams & sp, cu
     allow_smem( k_fft_pass<false>, std::max( plan->smem_b, std::size_t( d.Pc ) * 2 * sizeof( double2 ) * plan->ncol_b ) );
     allow_smem( k_fft_pass<true>, plan->smem_b );
     allow_smem( k_ddi_c_mult, plan->smem_c );
+    {
+        // (n / 8) << lg threads, about 256 per CTA; one in-place buffer of n << lg elements (+ 1/16 padding) per transform set
+        const bool allow = !env_flag_off( "SPIRIT_B200_FFT_FAST" );
+        auto shape       = []( DDIPlan::Fast & f, int n, int n_buffers )
+        {
+            f.lg = 0;
+            while( f.lg < 4 && ( n << ( f.lg + 1 ) ) <= 2048 )
+                ++f.lg;
+            f.threads = ( n >> FFT_LG_E ) << f.lg;
+            f.smem    = std::size_t( n_buffers ) * ( ( std::size_t( n ) << f.lg ) * 17 / 16 + 1 ) * sizeof( double2 );
+            f.on      = f.threads >= 32 && f.threads <= FFT_THREADS && f.smem <= std::size_t( 220 * 1024 );
+        };
+        const bool pow2_world = ( world & ( world - 1 ) ) == 0;
+        if( allow && plan->plan[1].fast16 && pow2_world )
+        {
+            shape( plan->fast_b, d.Pb, 1 );
+            if( world > 1 )
+                plan->lg_split = 31 - __builtin_clz( unsigned( kbl ) );
+        }
+        if( allow && plan->plan[2].fast16 && d.NB == 1 )
+            shape( plan->fast_c, d.Pc, 3 );
+        if( allow && d.Pa % 2 == 0 && d.Pa >= 128 && ( d.Pa & ( d.Pa - 1 ) ) == 0 && !env_flag_off( "SPIRIT_B200_FFT16" ) )
+        {
+            make_plan_1d( plan->plan_ah, plan->twiddle_ah, d.Pa / 2 );
+            if( plan->plan_ah.fast16 )
+                shape( plan->fast_a, d.Pa / 2, 1 );
+        }
+        if( plan->fast_b.on )
+        {
+            allow_smem( k_fft_pass16<false>, plan->fast_b.smem );
+            allow_smem( k_fft_pass16<true>, plan->fast_b.smem );
+        }
+        if( plan->fast_c.on )
+        {
+            allow_smem( k_ddi_c_mult16<false>, plan->fast_c.smem );
+            allow_smem( k_ddi_c_mult16<true>, plan->fast_c.smem );
+        }
+        if( plan->fast_a.on )
+        {
+            allow_smem( k_ddi_fwd_a16, plan->fast_a.smem );
+            allow_smem( k_ddi_inv_a16, plan->fast_a.smem );
+        }
+    }
 
     const std::size_t half       = std::size_t( d.Pc ) * d.Pb * d.Ha; // full half-spectrum of one tensor component
     const std::size_t half_local = std::size_t( d.Pc ) * kbl * d.Ha;  // the local kb range of it
@@ -1084,7 +1404,11 @@ DDIPlan * ddi_plan_create( const Hamiltonian & ham, const StencilParams & sp, cu
     cudaFree( tmp2 );
 
     // Single sublattice: D(-r) = D(r), the spectrum is real. Verify numerically, then keep only the real parts.
-    if( d.NB == 1 && ( d.Pc & ( d.Pc - 1 ) ) == 0 && d.Pc <= 32 )
+    const bool small_c = d.NB == 1 && ( d.Pc & ( d.Pc - 1 ) ) == 0 && d.Pc <= 32;
+    if( small_c )
+        plan->fast_c.on = false; // the in-register kernel serves thin films
+    bool spectrum_real = false;
+    if( small_c || plan->fast_c.on )
     {
         const std::size_t n_all = std::size_t( 6 * d.n_inter ) * half_local;
         const int blocks        = 1024;
@@ -1106,7 +1430,8 @@ DDIPlan * ddi_plan_create( const Hamiltonian & ham, const StencilParams & sp, cu
         // The imaginary parts are pure round-off of the forward transforms (a few ulp of the largest element times
         // log2 P): mathematically zero. 1e-12 relative is 4 orders above what is observed and far below any signal.
         // (world > 1: every rank must take the same decision -> only for the undistributed plan.)
-        if( world == 1 && max_imag <= 1e-12 * max_abs )
+        spectrum_real = world == 1 && max_imag <= 1e-12 * max_abs;
+        if( spectrum_real && small_c )
         {
             SB_CUDA_CHECK( cudaMalloc( &plan->Dhat_real, n_all * sizeof( double ) ) );
             k_ddi_take_real<<<unsigned( ( n_all + 255 ) / 256 ), 256, 0, stream>>>( plan->Dhat, plan->Dhat_real, n_all );
@@ -1114,6 +1439,26 @@ DDIPlan * ddi_plan_create( const Hamiltonian & ham, const StencilParams & sp, cu
             cudaFree( plan->Dhat );
             plan->Dhat = nullptr;
         }
+    }
+    if( plan->fast_c.on )
+    {
+        // re-order the spectrum into the tiles k_ddi_c_mult16 reads (one sublattice: 6 components)
+        const int lg            = plan->fast_c.lg;
+        const std::size_t tiles = std::size_t( ( d.Ha + ( 1 << lg ) - 1 ) >> lg );
+        const std::size_t n_t   = std::size_t( kbl ) * tiles * 6 * ( std::size_t( d.Pc ) << lg );
+        plan->Dt_real           = spectrum_real;
+        const std::size_t bytes = n_t * ( spectrum_real ? sizeof( double ) : sizeof( double2 ) );
+        SB_CUDA_CHECK( cudaMalloc( &plan->Dt, bytes ) );
+        SB_CUDA_CHECK( cudaMemsetAsync( plan->Dt, 0, bytes, stream ) );
+        const std::size_t n_in = 6 * half_local;
+        if( spectrum_real )
+            k_ddi_tile_tensor<true><<<unsigned( ( n_in + 255 ) / 256 ), 256, 0, stream>>>( dc, plan->Dhat, plan->Dt, lg );
+        else
+            k_ddi_tile_tensor<false><<<unsigned( ( n_in + 255 ) / 256 ), 256, 0, stream>>>( dc, plan->Dhat, plan->Dt, lg );
+        SB_CUDA_CHECK( cudaGetLastError() );
+        SB_CUDA_CHECK( cudaStreamSynchronize( stream ) );
+        cudaFree( plan->Dhat );
+        plan->Dhat = nullptr;
     }
     return plan.release();
 }
@@ -1127,7 +1472,11 @@ int ddi_gradient( DDIPlan & plan, ConstField3 spins, Field3 g_ddi, cudaStream_t 
     const int nq       = 3 * d.NB;
     const int kbl      = dc.Pb;
     const int rows     = d.Nb * d.Nc;
-    k_ddi_fwd_a<<<dim3( rows, d.NB ), fft_threads( d.Pa / 4 ), plan.smem_a, stream>>>( plan.plan[0], d, spins, plan.A );
+    if( plan.fast_a.on )
+        k_ddi_fwd_a16<<<dim3( ( rows + ( 1 << plan.fast_a.lg ) - 1 ) >> plan.fast_a.lg, nq ), plan.fast_a.threads, plan.fast_a.smem, stream>>>(
+            plan.plan_ah, plan.plan[0].twiddle, d, spins, plan.A, plan.fast_a.lg );
+    else
+        k_ddi_fwd_a<<<dim3( rows, d.NB ), fft_threads( d.Pa / 4 ), plan.smem_a, stream>>>( plan.plan[0], d, spins, plan.A );
     // forward b: A[q][c][b][ka] -> B; outer index o = q * ncl + c. Single device: B[o][kb][ka]; distributed: the kb axis
     // is cut into per-rank blocks, B[r][o][kb % kbl][ka], so that block r is what rank r needs
     PassArgs pb{};
@@ -1143,7 +1492,11 @@ int ddi_gradient( DDIPlan & plan, ConstField3 spins, Field3 g_ddi, cudaStream_t 
         pb.out_os = std::size_t( d.Pb ) * d.Ha;
     pb.n_u = d.Ha, pb.n_o = nq * d.Nc, pb.n_in = d.Nb, pb.n_out = d.Pb, pb.ncol = plan.ncol_b, pb.scale = 1.0;
     const dim3 grid_b( ( d.Ha + plan.ncol_b - 1 ) / plan.ncol_b, pb.n_o );
-    k_fft_pass<false><<<grid_b, fft_threads( d.Pb / 4 * plan.ncol_b ), plan.smem_b, stream>>>( plan.plan[1], pb );
+    const dim3 grid_b16( ( d.Ha + ( 1 << plan.fast_b.lg ) - 1 ) >> plan.fast_b.lg, pb.n_o );
+    if( plan.fast_b.on )
+        k_fft_pass16<false><<<grid_b16, plan.fast_b.threads, plan.fast_b.smem, stream>>>( plan.plan[1], pb, plan.fast_b.lg, 31, plan.lg_split );
+    else
+        k_fft_pass<false><<<grid_b, fft_threads( d.Pb / 4 * plan.ncol_b ), plan.smem_b, stream>>>( plan.plan[1], pb );
 
     double2 * operand = plan.B;
     const std::size_t block_doubles = 2 * dc.block_stride; // one per-rank block, in doubles
@@ -1183,6 +1536,14 @@ int ddi_gradient( DDIPlan & plan, ConstField3 spins, Field3 g_ddi, cudaStream_t 
         }
 #undef SB_DDI_SMALL
     }
+    else if( plan.fast_c.on )
+    {
+        const dim3 grid( ( d.Ha + ( 1 << plan.fast_c.lg ) - 1 ) >> plan.fast_c.lg, kbl );
+        if( plan.Dt_real )
+            k_ddi_c_mult16<true><<<grid, plan.fast_c.threads, plan.fast_c.smem, stream>>>( plan.plan[2], dc, operand, plan.Dt, plan.fast_c.lg );
+        else
+            k_ddi_c_mult16<false><<<grid, plan.fast_c.threads, plan.fast_c.smem, stream>>>( plan.plan[2], dc, operand, plan.Dt, plan.fast_c.lg );
+    }
     else
     {
         if( !plan.Dhat )
@@ -1215,9 +1576,16 @@ int ddi_gradient( DDIPlan & plan, ConstField3 spins, Field3 g_ddi, cudaStream_t 
     else
         ib.in_os = std::size_t( d.Pb ) * d.Ha;
     ib.n_u = d.Ha, ib.n_o = nq * d.Nc, ib.n_in = d.Pb, ib.n_out = d.Nb, ib.ncol = plan.ncol_b, ib.scale = 1.0;
-    k_fft_pass<true><<<grid_b, fft_threads( d.Pb / 4 * plan.ncol_b ), plan.smem_b, stream>>>( plan.plan[1], ib );
+    if( plan.fast_b.on )
+        k_fft_pass16<true><<<grid_b16, plan.fast_b.threads, plan.fast_b.smem, stream>>>( plan.plan[1], ib, plan.fast_b.lg, plan.lg_split, 31 );
+    else
+        k_fft_pass<true><<<grid_b, fft_threads( d.Pb / 4 * plan.ncol_b ), plan.smem_b, stream>>>( plan.plan[1], ib );
     const double inv_P = 1.0 / ( double( d.Pa ) * d.Pb * d.Pc );
-    k_ddi_inv_a<<<dim3( rows, d.NB ), fft_threads( d.Pa / 4 ), plan.smem_a, stream>>>( plan.plan[0], d, plan.A, g_ddi, inv_P );
+    if( plan.fast_a.on )
+        k_ddi_inv_a16<<<dim3( ( rows + ( 1 << plan.fast_a.lg ) - 1 ) >> plan.fast_a.lg, nq ), plan.fast_a.threads, plan.fast_a.smem, stream>>>(
+            plan.plan_ah, plan.plan[0].twiddle, d, plan.A, g_ddi, inv_P, plan.fast_a.lg );
+    else
+        k_ddi_inv_a<<<dim3( rows, d.NB ), fft_threads( d.Pa / 4 ), plan.smem_a, stream>>>( plan.plan[0], d, plan.A, g_ddi, inv_P );
     SB_CUDA_CHECK( cudaGetLastError() );
     return 5;
 }
