@@ -26,6 +26,7 @@
 #include "../core/constants.hpp"
 #include "../core/hamiltonian.hpp"
 
+#include <algorithm>
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
@@ -430,22 +431,33 @@ static __global__ void __launch_bounds__( FFT_THREADS ) k_fft_pass16(
     const int col = threadIdx.x & ( ncol - 1 ), j0 = threadIdx.x >> lg_ncol, jstep = blockDim.x >> lg_ncol;
     const bool valid   = u0 + col < a.n_u;
     const double2 * in = a.in + std::size_t( o ) * a.in_os + u0 + col;
-    for( int j = j0; j < n; j += jstep )
+    // exactly FFT_E elements per thread (blockDim = (n / FFT_E) << lg_ncol): all loads in flight before the first store
+    double2 v[FFT_E];
+#pragma unroll
+    for( int k = 0; k < FFT_E; ++k )
     {
-        double2 v = make_double2( 0.0, 0.0 );
+        const int j = j0 + k * jstep;
+        v[k]        = make_double2( 0.0, 0.0 );
         if( valid && j < a.n_in )
-            v = in[pass_offset16( j, a.in_js, lg_in_split, a.in_split_stride )];
-        smem[( j << lg_ncol ) + col] = v;
+            v[k] = in[pass_offset16( j, a.in_js, lg_in_split, a.in_split_stride )];
     }
+#pragma unroll
+    for( int k = 0; k < FFT_E; ++k )
+        smem[( ( j0 + k * jstep ) << lg_ncol ) + col] = v[k];
     __syncthreads();
     block_fft16<INVERSE>( plan, smem, ncol );
     if( valid )
     {
         double2 * out = a.out + std::size_t( o ) * a.out_os + u0 + col;
-        for( int j = j0; j < a.n_out; j += jstep )
+#pragma unroll
+        for( int k = 0; k < FFT_E; ++k )
         {
-            const double2 v = smem[( j << lg_ncol ) + col];
-            out[pass_offset16( j, a.out_js, lg_out_split, a.out_split_stride )] = make_double2( a.scale * v.x, a.scale * v.y );
+            const int j = j0 + k * jstep;
+            if( j < a.n_out )
+            {
+                const double2 w = smem[( j << lg_ncol ) + col];
+                out[pass_offset16( j, a.out_js, lg_out_split, a.out_split_stride )] = make_double2( a.scale * w.x, a.scale * w.y );
+            }
         }
     }
 }
@@ -628,29 +640,50 @@ static __global__ void __launch_bounds__( FFT_THREADS ) k_ddi_c_mult16(
     const std::size_t plane = std::size_t( d.Pb ) * d.Ha;
     double2 * column       = B + std::size_t( kb ) * d.Ha + u0 + col;
     // element (q, c) of the column: c_operand without divisions (c = j0 + k jstep walks the per-rank blocks in order)
+    // pull the tensor block of this CTA towards L2 while the spectra are loaded and transformed
+    {
+        const std::size_t elem  = REAL_D ? sizeof( double ) : sizeof( double2 );
+        const std::size_t bytes = 6 * std::size_t( tile_elems ) * elem;
+        const char * Dblock     = static_cast<const char *>( Dt_v ) + ( std::size_t( kb ) * gridDim.x + blockIdx.x ) * bytes;
+        for( std::size_t off = std::size_t( threadIdx.x ) * 128; off < bytes; off += std::size_t( blockDim.x ) * 128 )
+            asm volatile( "prefetch.global.L2 [%0];" ::"l"( Dblock + off ) );
+    }
+    // element (q, c) of the column = c_operand; exactly FFT_E planes c = j0 + k jstep per thread and component
+    std::size_t off_c[FFT_E];
+#pragma unroll
+    for( int k = 0; k < FFT_E; ++k )
+    {
+        const int c = j0 + k * jstep;
+        if( d.block_stride == 0 )
+            off_c[k] = std::size_t( c ) * plane;
+        else
+        {
+            const int blk = c / d.c_block;
+            off_c[k]      = std::size_t( blk ) * d.block_stride + std::size_t( c - blk * d.c_block ) * plane;
+        }
+    }
     for( int q = 0; q < 3; ++q )
     {
-        double2 * x = smem + q * bufp;
-        int blk = j0 / d.c_block, rem = j0 - blk * d.c_block;
-        for( int j = j0; j < n; j += jstep )
+        double2 * x            = smem + q * bufp;
+        const double2 * column_q = column + std::size_t( q ) * d.q_stride;
+        double2 v[FFT_E];
+#pragma unroll
+        for( int k = 0; k < FFT_E; ++k )
         {
-            double2 v = make_double2( 0.0, 0.0 );
-            if( valid && j < d.Nc )
-                v = column[std::size_t( blk ) * d.block_stride + std::size_t( q ) * d.q_stride + std::size_t( rem ) * plane];
-            x[( j << lg_ncol ) + col] = v;
-            rem += jstep;
-            while( rem >= d.c_block )
-            {
-                rem -= d.c_block;
-                ++blk;
-            }
+            v[k] = make_double2( 0.0, 0.0 );
+            if( valid && j0 + k * jstep < d.Nc )
+                v[k] = column_q[off_c[k]];
         }
+#pragma unroll
+        for( int k = 0; k < FFT_E; ++k )
+            x[( ( j0 + k * jstep ) << lg_ncol ) + col] = v[k];
     }
     __syncthreads();
     for( int q = 0; q < 3; ++q )
         block_fft16<false>( plan, smem + q * bufp, ncol );
     {
         const std::size_t block = ( std::size_t( kb ) * gridDim.x + blockIdx.x ) * 6 * std::size_t( tile_elems );
+#pragma unroll 4
         for( int item = threadIdx.x; item < tile_elems; item += blockDim.x )
         {
             const double2 sx = smem[item], sy = smem[bufp + item], sz = smem[2 * bufp + item];
@@ -684,18 +717,12 @@ static __global__ void __launch_bounds__( FFT_THREADS ) k_ddi_c_mult16(
     if( valid )
         for( int q = 0; q < 3; ++q )
         {
-            const double2 * x = smem + q * bufp;
-            int blk = j0 / d.c_block, rem = j0 - blk * d.c_block;
-            for( int j = j0; j < d.Nc; j += jstep )
-            {
-                column[std::size_t( blk ) * d.block_stride + std::size_t( q ) * d.q_stride + std::size_t( rem ) * plane] = x[( j << lg_ncol ) + col];
-                rem += jstep;
-                while( rem >= d.c_block )
-                {
-                    rem -= d.c_block;
-                    ++blk;
-                }
-            }
+            const double2 * x  = smem + q * bufp;
+            double2 * column_q = column + std::size_t( q ) * d.q_stride;
+#pragma unroll
+            for( int k = 0; k < FFT_E; ++k )
+                if( j0 + k * jstep < d.Nc )
+                    column_q[off_c[k]] = x[( ( j0 + k * jstep ) << lg_ncol ) + col];
         }
 }
 
@@ -918,18 +945,23 @@ static __global__ void __launch_bounds__( FFT_THREADS ) k_ddi_fwd_a16(
     const int b = row % d.Nb, c = row / d.Nb;
     const std::size_t site0 = std::size_t( d.Na ) * d.NB * b + std::size_t( d.plane_stride ) * ( c + d.halo ) + ib;
     const double mu         = d.mu_s[ib];
-    for( int jh = jhigh; 4 * jh < m; jh += jstep )
+    // exactly FFT_E elements per thread
+    double2 zz[FFT_E];
+#pragma unroll
+    for( int k = 0; k < FFT_E; ++k )
     {
-        const int j = 4 * jh + jlow;
-        double2 z   = make_double2( 0.0, 0.0 );
+        const int j = 4 * ( jhigh + k * jstep ) + jlow;
+        zz[k]       = make_double2( 0.0, 0.0 );
         if( valid && 2 * j < d.Na )
         {
-            z.x = mu * __ldg( spins.base + elem_offset( site0 + std::size_t( d.NB ) * ( 2 * j ) ) + comp * FIELD_BLOCK );
+            zz[k].x = __ldg( spins.base + elem_offset( site0 + std::size_t( d.NB ) * ( 2 * j ) ) + comp * FIELD_BLOCK );
             if( 2 * j + 1 < d.Na )
-                z.y = mu * __ldg( spins.base + elem_offset( site0 + std::size_t( d.NB ) * ( 2 * j + 1 ) ) + comp * FIELD_BLOCK );
+                zz[k].y = __ldg( spins.base + elem_offset( site0 + std::size_t( d.NB ) * ( 2 * j + 1 ) ) + comp * FIELD_BLOCK );
         }
-        smem[( j << lg_nrow ) + rl] = z;
     }
+#pragma unroll
+    for( int k = 0; k < FFT_E; ++k )
+        smem[( ( 4 * ( jhigh + k * jstep ) + jlow ) << lg_nrow ) + rl] = make_double2( mu * zz[k].x, mu * zz[k].y );
     __syncthreads();
     block_fft16<false>( plan_h, smem, nrow );
     if( !valid )
@@ -964,9 +996,10 @@ static __global__ void __launch_bounds__( FFT_THREADS ) k_ddi_inv_a16(
     const bool valid = row < d.Nb * d.Nc;
     const int b = row % d.Nb, c = row / d.Nb;
     const double2 * in = A + ( ( std::size_t( q ) * d.Nc + c ) * d.Nb + b ) * d.Ha;
-    for( int jh = jhigh; 4 * jh < m; jh += jstep )
+#pragma unroll
+    for( int kk = 0; kk < FFT_E; ++kk )
     {
-        const int k = 4 * jh + jlow;
+        const int k = 4 * ( jhigh + kk * jstep ) + jlow;
         double2 Z   = make_double2( 0.0, 0.0 );
         if( valid )
         {
@@ -1290,11 +1323,13 @@ DDIPlan * ddi_plan_create( const Hamiltonian & ham, const StencilParams & sp, cu
     {
         // (n / 8) << lg threads, about 256 per CTA; one in-place buffer of n << lg elements (+ 1/16 padding) per transform set
         const bool allow = !env_flag_off( "SPIRIT_B200_FFT_FAST" );
-        auto shape       = []( DDIPlan::Fast & f, int n, int n_buffers )
+        auto shape       = []( DDIPlan::Fast & f, int n, int n_buffers, const char * tune )
         {
             f.lg = 0;
             while( f.lg < 4 && ( n << ( f.lg + 1 ) ) <= 2048 )
                 ++f.lg;
+            if( const char * v = std::getenv( tune ) ) // tuning runs (profiles/): columns per CTA
+                f.lg = std::max( 0, std::min( 5, std::atoi( v ) ) );
             f.threads = ( n >> FFT_LG_E ) << f.lg;
             f.smem    = std::size_t( n_buffers ) * ( ( std::size_t( n ) << f.lg ) * 17 / 16 + 1 ) * sizeof( double2 );
             f.on      = f.threads >= 32 && f.threads <= FFT_THREADS && f.smem <= std::size_t( 220 * 1024 );
@@ -1302,17 +1337,17 @@ DDIPlan * ddi_plan_create( const Hamiltonian & ham, const StencilParams & sp, cu
         const bool pow2_world = ( world & ( world - 1 ) ) == 0;
         if( allow && plan->plan[1].fast16 && pow2_world )
         {
-            shape( plan->fast_b, d.Pb, 1 );
+            shape( plan->fast_b, d.Pb, 1, "SPIRIT_B200_FFT_LG_B" );
             if( world > 1 )
                 plan->lg_split = 31 - __builtin_clz( unsigned( kbl ) );
         }
         if( allow && plan->plan[2].fast16 && d.NB == 1 )
-            shape( plan->fast_c, d.Pc, 3 );
+            shape( plan->fast_c, d.Pc, 3, "SPIRIT_B200_FFT_LG_C" );
         if( allow && d.Pa % 2 == 0 && d.Pa >= 128 && ( d.Pa & ( d.Pa - 1 ) ) == 0 && !env_flag_off( "SPIRIT_B200_FFT16" ) )
         {
             make_plan_1d( plan->plan_ah, plan->twiddle_ah, d.Pa / 2 );
             if( plan->plan_ah.fast16 )
-                shape( plan->fast_a, d.Pa / 2, 1 );
+                shape( plan->fast_a, d.Pa / 2, 1, "SPIRIT_B200_FFT_LG_A" );
         }
         if( plan->fast_b.on )
         {

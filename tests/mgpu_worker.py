@@ -74,9 +74,10 @@ def main():
 def ddi_distributed(lib, rank, world, tmp):
     """dipole-dipole FFT convolution on a slab decomposition (all-to-all transposes) vs the same lattice on one GPU"""
     failures = []
-    Na, Nb, Nc = 16, 8, 8
-    plane = Na * Nb
-    for bc, solver in (("0 0 0", "Depondt"), ("1 1 0", "SIB"), ("0 0 0", "VP")):
+    # the second lattice has padded lengths 128 x 64 x 64: the power-of-two pass kernels with the per-rank kb blocks
+    for Na, Nb, Nc, bc, solver in ((16, 8, 8, "0 0 0", "Depondt"), (16, 8, 8, "1 1 0", "SIB"), (16, 8, 8, "0 0 0", "VP"),
+                                   (64, 32, 32, "0 0 0", "Depondt"), (64, 32, 32, "1 1 0", "SIB")):
+        plane = Na * Nb
         over = dict(boundary_conditions=bc, ddi_method="fft", ddi_n_periodic_images="2 2 0", llg_n_iterations_amortize=3)
         s_global = unit_random(Na * Nb * Nc, 33)
         c_begin, nc_local = slab.partition(Nc, world)[rank]
@@ -100,8 +101,8 @@ def ddi_distributed(lib, rank, world, tmp):
             dev = np.abs(np.concatenate(parts) - ref).max()
             moved = np.abs(ref - s_global).max()
             ok = dev <= 1e-13 and moved > 1e-4 and abs(e_slab - g.energy()) <= 1e-11 * abs(g.energy())
-            print("DDI distributed bc=%s %-8s: max deviation %.3e, moved %.2e, E slab %.12e global %.12e %s" % (
-                bc, solver, dev, moved, e_slab, g.energy(), "OK" if ok else "FAIL"), flush=True)
+            print("DDI distributed %dx%dx%d bc=%s %-8s: max deviation %.3e, moved %.2e, E slab %.12e global %.12e %s" % (
+                Na, Nb, Nc, bc, solver, dev, moved, e_slab, g.energy(), "OK" if ok else "FAIL"), flush=True)
             if not ok:
                 failures.append(("ddi", bc, solver))
             g.close()
