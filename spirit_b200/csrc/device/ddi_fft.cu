@@ -933,13 +933,13 @@ __device__ __forceinline__ void row_map( int lg_nrow, int & row, int & jlow, int
 
 static __global__ void __launch_bounds__( FFT_THREADS ) k_ddi_fwd_a16(
     const __grid_constant__ FFTPlan1D plan_h, const double2 * __restrict__ tw_full, const __grid_constant__ DDIDims d,
-    ConstField3 spins, double2 * __restrict__ A, const int lg_nrow )
+    ConstField3 spins, double2 * __restrict__ A, const int lg_nrow, const int q0 )
 {
     extern __shared__ double2 smem[];
     const int m = plan_h.n, nrow = 1 << lg_nrow;
     int rl, jlow, jhigh, jstep;
     row_map( lg_nrow, rl, jlow, jhigh, jstep );
-    const int q = blockIdx.y, comp = q % 3, ib = q / 3;
+    const int q = q0 + blockIdx.y, comp = q % 3, ib = q / 3;
     const int row    = ( blockIdx.x << lg_nrow ) + rl;
     const bool valid = row < d.Nb * d.Nc;
     const int b = row % d.Nb, c = row / d.Nb;
@@ -985,13 +985,13 @@ static __global__ void __launch_bounds__( FFT_THREADS ) k_ddi_fwd_a16(
 
 static __global__ void __launch_bounds__( FFT_THREADS ) k_ddi_inv_a16(
     const __grid_constant__ FFTPlan1D plan_h, const double2 * __restrict__ tw_full, const __grid_constant__ DDIDims d,
-    const double2 * __restrict__ A, Field3 g, const double inv_P, const int lg_nrow )
+    const double2 * __restrict__ A, Field3 g, const double inv_P, const int lg_nrow, const int q0 )
 {
     extern __shared__ double2 smem[];
     const int m = plan_h.n, nrow = 1 << lg_nrow;
     int rl, jlow, jhigh, jstep;
     row_map( lg_nrow, rl, jlow, jhigh, jstep );
-    const int q = blockIdx.y, comp = q % 3, ib = q / 3;
+    const int q = q0 + blockIdx.y, comp = q % 3, ib = q / 3;
     const int row    = ( blockIdx.x << lg_nrow ) + rl;
     const bool valid = row < d.Nb * d.Nc;
     const int b = row % d.Nb, c = row / d.Nb;
@@ -1136,6 +1136,10 @@ struct DDIPlan
     int lg_split         = 31;     // lg of the per-rank kb block (distributed layout), 31: no split
     void * Dt            = nullptr; // tensor spectrum in the tile order of k_ddi_c_mult16
     bool Dt_real         = false;
+    // distributed: the all-to-alls run on their own stream, one component at a time, under the passes of the others
+    cudaStream_t comm_stream = nullptr;
+    cudaEvent_t ev_q[3 * MAX_BASIS] = {};
+    cudaEvent_t ev_all = nullptr;
 
     ~DDIPlan()
     {
@@ -1148,6 +1152,13 @@ struct DDIPlan
             cudaFree( Dhat_real );
         if( Dt )
             cudaFree( Dt );
+        if( comm_stream )
+            cudaStreamDestroy( comm_stream );
+        for( auto e : ev_q )
+            if( e )
+                cudaEventDestroy( e );
+        if( ev_all )
+            cudaEventDestroy( ev_all );
         if( twiddle_ah )
             cudaFree( twiddle_ah );
         if( A )
@@ -1364,6 +1375,15 @@ DDIPlan * ddi_plan_create( const Hamiltonian & ham, const StencilParams & sp, cu
             allow_smem( k_ddi_fwd_a16, plan->fast_a.smem );
             allow_smem( k_ddi_inv_a16, plan->fast_a.smem );
         }
+        if( world > 1 && plan->fast_a.on && plan->fast_b.on && !env_flag_off( "SPIRIT_B200_DDI_PIPELINE" ) )
+        {
+            int least = 0, greatest = 0;
+            SB_CUDA_CHECK( cudaDeviceGetStreamPriorityRange( &least, &greatest ) );
+            SB_CUDA_CHECK( cudaStreamCreateWithPriority( &plan->comm_stream, cudaStreamNonBlocking, greatest ) );
+            for( int q = 0; q < nq; ++q )
+                SB_CUDA_CHECK( cudaEventCreateWithFlags( &plan->ev_q[q], cudaEventDisableTiming ) );
+            SB_CUDA_CHECK( cudaEventCreateWithFlags( &plan->ev_all, cudaEventDisableTiming ) );
+        }
     }
 
     const std::size_t half       = std::size_t( d.Pc ) * d.Pb * d.Ha; // full half-spectrum of one tensor component
@@ -1498,56 +1518,15 @@ DDIPlan * ddi_plan_create( const Hamiltonian & ham, const StencilParams & sp, cu
     return plan.release();
 }
 
-// One DDI gradient evaluation: spins -> g_ddi field. Returns the number of kernels launched.
-int ddi_gradient( DDIPlan & plan, ConstField3 spins, Field3 g_ddi, cudaStream_t stream )
+namespace
+{
+// step 3 (c-transforms + tensor multiply) on the operand in per-rank block layout
+void launch_c_mult( DDIPlan & plan, double2 * operand, cudaStream_t stream )
 {
     const DDIDims & d  = plan.dims;
     const DDIDims & dc = plan.dims_c;
-    const int world    = plan.world;
     const int nq       = 3 * d.NB;
     const int kbl      = dc.Pb;
-    const int rows     = d.Nb * d.Nc;
-    if( plan.fast_a.on )
-        k_ddi_fwd_a16<<<dim3( ( rows + ( 1 << plan.fast_a.lg ) - 1 ) >> plan.fast_a.lg, nq ), plan.fast_a.threads, plan.fast_a.smem, stream>>>(
-            plan.plan_ah, plan.plan[0].twiddle, d, spins, plan.A, plan.fast_a.lg );
-    else
-        k_ddi_fwd_a<<<dim3( rows, d.NB ), fft_threads( d.Pa / 4 ), plan.smem_a, stream>>>( plan.plan[0], d, spins, plan.A );
-    // forward b: A[q][c][b][ka] -> B; outer index o = q * ncl + c. Single device: B[o][kb][ka]; distributed: the kb axis
-    // is cut into per-rank blocks, B[r][o][kb % kbl][ka], so that block r is what rank r needs
-    PassArgs pb{};
-    pb.in = plan.A, pb.out = plan.B;
-    pb.in_os = std::size_t( d.Nb ) * d.Ha, pb.in_js = pb.out_js = d.Ha;
-    pb.out_os = std::size_t( kbl ) * d.Ha * ( world > 1 ? 1 : world );
-    if( world > 1 )
-    {
-        pb.out_split        = kbl;
-        pb.out_split_stride = dc.block_stride;
-    }
-    else
-        pb.out_os = std::size_t( d.Pb ) * d.Ha;
-    pb.n_u = d.Ha, pb.n_o = nq * d.Nc, pb.n_in = d.Nb, pb.n_out = d.Pb, pb.ncol = plan.ncol_b, pb.scale = 1.0;
-    const dim3 grid_b( ( d.Ha + plan.ncol_b - 1 ) / plan.ncol_b, pb.n_o );
-    const dim3 grid_b16( ( d.Ha + ( 1 << plan.fast_b.lg ) - 1 ) >> plan.fast_b.lg, pb.n_o );
-    if( plan.fast_b.on )
-        k_fft_pass16<false><<<grid_b16, plan.fast_b.threads, plan.fast_b.smem, stream>>>( plan.plan[1], pb, plan.fast_b.lg, 31, plan.lg_split );
-    else
-        k_fft_pass<false><<<grid_b, fft_threads( d.Pb / 4 * plan.ncol_b ), plan.smem_b, stream>>>( plan.plan[1], pb );
-
-    double2 * operand = plan.B;
-    const std::size_t block_doubles = 2 * dc.block_stride; // one per-rank block, in doubles
-    if( world > 1 )
-    {
-        // all-to-all: my block r -> rank r's block (my rank): "my planes, kb range of r" becomes "planes of r, my kb range"
-        comm_group_begin();
-        for( int r = 0; r < world; ++r )
-        {
-            comm_send( reinterpret_cast<const double *>( plan.B + std::size_t( r ) * dc.block_stride ), block_doubles, r, stream );
-            comm_recv( reinterpret_cast<double *>( plan.C + std::size_t( r ) * dc.block_stride ), block_doubles, r, stream );
-        }
-        comm_group_end();
-        operand = plan.C;
-    }
-
     const bool small_c = d.NB == 1 && ( dc.Pc & ( dc.Pc - 1 ) ) == 0 && dc.Pc <= 32;
     if( small_c )
     {
@@ -1586,6 +1565,132 @@ int ddi_gradient( DDIPlan & plan, ConstField3 spins, Field3 g_ddi, cudaStream_t 
         k_ddi_c_mult<<<dim3( ( d.Ha + plan.ncol_c - 1 ) / plan.ncol_c, kbl ), fft_threads( std::max( 1, dc.Pc / 4 ) * plan.ncol_c * nq ), plan.smem_c, stream>>>(
             plan.plan[2], dc, operand, plan.Dhat, plan.ncol_c );
     }
+}
+} // namespace
+
+namespace
+{
+
+// Distributed evaluation with the transposes hidden: component q travels (NCCL send / recv on the plan's own stream)
+// while the a- and b-passes of component q + 1 run, and on the way back the inverse passes of component q run while
+// component q + 1 travels. Same kernels, same per-rank block layout, same result as the plain sequence below.
+int ddi_gradient_pipelined( DDIPlan & plan, ConstField3 spins, Field3 g_ddi, cudaStream_t stream )
+{
+    const DDIDims & d  = plan.dims;
+    const DDIDims & dc = plan.dims_c;
+    const int world = plan.world, nq = 3 * d.NB, kbl = dc.Pb, ncl = d.Nc, rows = d.Nb * d.Nc;
+    cudaStream_t cs                  = plan.comm_stream;
+    const std::size_t comp_elems     = dc.q_stride; // one component inside a per-rank block: ncl * kbl * Ha
+    const dim3 grid_a( ( rows + ( 1 << plan.fast_a.lg ) - 1 ) >> plan.fast_a.lg, 1 );
+    const dim3 grid_b( ( d.Ha + ( 1 << plan.fast_b.lg ) - 1 ) >> plan.fast_b.lg, ncl );
+    auto all_to_all = [&]( const double2 * from, double2 * to, int q )
+    {
+        comm_group_begin();
+        for( int r = 0; r < world; ++r )
+        {
+            const std::size_t off = std::size_t( r ) * dc.block_stride + std::size_t( q ) * comp_elems;
+            comm_send( reinterpret_cast<const double *>( from + off ), 2 * comp_elems, r, cs );
+            comm_recv( reinterpret_cast<double *>( to + off ), 2 * comp_elems, r, cs );
+        }
+        comm_group_end();
+    };
+    for( int q = 0; q < nq; ++q )
+    {
+        k_ddi_fwd_a16<<<grid_a, plan.fast_a.threads, plan.fast_a.smem, stream>>>(
+            plan.plan_ah, plan.plan[0].twiddle, d, spins, plan.A, plan.fast_a.lg, q );
+        PassArgs pb{};
+        pb.in    = plan.A + std::size_t( q ) * ncl * d.Nb * d.Ha;
+        pb.out   = plan.B + std::size_t( q ) * comp_elems;
+        pb.in_os = std::size_t( d.Nb ) * d.Ha, pb.in_js = pb.out_js = d.Ha;
+        pb.out_os = std::size_t( kbl ) * d.Ha, pb.out_split = kbl, pb.out_split_stride = dc.block_stride;
+        pb.n_u = d.Ha, pb.n_o = ncl, pb.n_in = d.Nb, pb.n_out = d.Pb, pb.ncol = 1 << plan.fast_b.lg, pb.scale = 1.0;
+        k_fft_pass16<false><<<grid_b, plan.fast_b.threads, plan.fast_b.smem, stream>>>( plan.plan[1], pb, plan.fast_b.lg, 31, plan.lg_split );
+        SB_CUDA_CHECK( cudaEventRecord( plan.ev_q[q], stream ) );
+        SB_CUDA_CHECK( cudaStreamWaitEvent( cs, plan.ev_q[q], 0 ) );
+        all_to_all( plan.B, plan.C, q );
+    }
+    SB_CUDA_CHECK( cudaEventRecord( plan.ev_all, cs ) );
+    SB_CUDA_CHECK( cudaStreamWaitEvent( stream, plan.ev_all, 0 ) );
+    launch_c_mult( plan, plan.C, stream );
+    SB_CUDA_CHECK( cudaEventRecord( plan.ev_all, stream ) );
+    SB_CUDA_CHECK( cudaStreamWaitEvent( cs, plan.ev_all, 0 ) );
+    const double inv_P = 1.0 / ( double( d.Pa ) * d.Pb * d.Pc );
+    for( int q = 0; q < nq; ++q )
+    {
+        all_to_all( plan.C, plan.B, q );
+        SB_CUDA_CHECK( cudaEventRecord( plan.ev_q[q], cs ) );
+    }
+    for( int q = 0; q < nq; ++q )
+    {
+        SB_CUDA_CHECK( cudaStreamWaitEvent( stream, plan.ev_q[q], 0 ) );
+        PassArgs ib{};
+        ib.in     = plan.B + std::size_t( q ) * comp_elems;
+        ib.out    = plan.A + std::size_t( q ) * ncl * d.Nb * d.Ha;
+        ib.out_os = std::size_t( d.Nb ) * d.Ha, ib.in_js = ib.out_js = d.Ha;
+        ib.in_os = std::size_t( kbl ) * d.Ha, ib.in_split = kbl, ib.in_split_stride = dc.block_stride;
+        ib.n_u = d.Ha, ib.n_o = ncl, ib.n_in = d.Pb, ib.n_out = d.Nb, ib.ncol = 1 << plan.fast_b.lg, ib.scale = 1.0;
+        k_fft_pass16<true><<<grid_b, plan.fast_b.threads, plan.fast_b.smem, stream>>>( plan.plan[1], ib, plan.fast_b.lg, plan.lg_split, 31 );
+        k_ddi_inv_a16<<<grid_a, plan.fast_a.threads, plan.fast_a.smem, stream>>>(
+            plan.plan_ah, plan.plan[0].twiddle, d, plan.A, g_ddi, inv_P, plan.fast_a.lg, q );
+    }
+    SB_CUDA_CHECK( cudaGetLastError() );
+    return 4 * nq + 1;
+}
+} // namespace
+
+// One DDI gradient evaluation: spins -> g_ddi field. Returns the number of kernels launched.
+int ddi_gradient( DDIPlan & plan, ConstField3 spins, Field3 g_ddi, cudaStream_t stream )
+{
+    if( plan.comm_stream )
+        return ddi_gradient_pipelined( plan, spins, g_ddi, stream );
+    const DDIDims & d  = plan.dims;
+    const DDIDims & dc = plan.dims_c;
+    const int world    = plan.world;
+    const int nq       = 3 * d.NB;
+    const int kbl      = dc.Pb;
+    const int rows     = d.Nb * d.Nc;
+    if( plan.fast_a.on )
+        k_ddi_fwd_a16<<<dim3( ( rows + ( 1 << plan.fast_a.lg ) - 1 ) >> plan.fast_a.lg, nq ), plan.fast_a.threads, plan.fast_a.smem, stream>>>(
+            plan.plan_ah, plan.plan[0].twiddle, d, spins, plan.A, plan.fast_a.lg, 0 );
+    else
+        k_ddi_fwd_a<<<dim3( rows, d.NB ), fft_threads( d.Pa / 4 ), plan.smem_a, stream>>>( plan.plan[0], d, spins, plan.A );
+    // forward b: A[q][c][b][ka] -> B; outer index o = q * ncl + c. Single device: B[o][kb][ka]; distributed: the kb axis
+    // is cut into per-rank blocks, B[r][o][kb % kbl][ka], so that block r is what rank r needs
+    PassArgs pb{};
+    pb.in = plan.A, pb.out = plan.B;
+    pb.in_os = std::size_t( d.Nb ) * d.Ha, pb.in_js = pb.out_js = d.Ha;
+    pb.out_os = std::size_t( kbl ) * d.Ha * ( world > 1 ? 1 : world );
+    if( world > 1 )
+    {
+        pb.out_split        = kbl;
+        pb.out_split_stride = dc.block_stride;
+    }
+    else
+        pb.out_os = std::size_t( d.Pb ) * d.Ha;
+    pb.n_u = d.Ha, pb.n_o = nq * d.Nc, pb.n_in = d.Nb, pb.n_out = d.Pb, pb.ncol = plan.ncol_b, pb.scale = 1.0;
+    const dim3 grid_b( ( d.Ha + plan.ncol_b - 1 ) / plan.ncol_b, pb.n_o );
+    const dim3 grid_b16( ( d.Ha + ( 1 << plan.fast_b.lg ) - 1 ) >> plan.fast_b.lg, pb.n_o );
+    if( plan.fast_b.on )
+        k_fft_pass16<false><<<grid_b16, plan.fast_b.threads, plan.fast_b.smem, stream>>>( plan.plan[1], pb, plan.fast_b.lg, 31, plan.lg_split );
+    else
+        k_fft_pass<false><<<grid_b, fft_threads( d.Pb / 4 * plan.ncol_b ), plan.smem_b, stream>>>( plan.plan[1], pb );
+
+    double2 * operand = plan.B;
+    const std::size_t block_doubles = 2 * dc.block_stride; // one per-rank block, in doubles
+    if( world > 1 )
+    {
+        // all-to-all: my block r -> rank r's block (my rank): "my planes, kb range of r" becomes "planes of r, my kb range"
+        comm_group_begin();
+        for( int r = 0; r < world; ++r )
+        {
+            comm_send( reinterpret_cast<const double *>( plan.B + std::size_t( r ) * dc.block_stride ), block_doubles, r, stream );
+            comm_recv( reinterpret_cast<double *>( plan.C + std::size_t( r ) * dc.block_stride ), block_doubles, r, stream );
+        }
+        comm_group_end();
+        operand = plan.C;
+    }
+
+    launch_c_mult( plan, operand, stream );
 
     if( world > 1 )
     {
@@ -1618,7 +1723,7 @@ int ddi_gradient( DDIPlan & plan, ConstField3 spins, Field3 g_ddi, cudaStream_t 
     const double inv_P = 1.0 / ( double( d.Pa ) * d.Pb * d.Pc );
     if( plan.fast_a.on )
         k_ddi_inv_a16<<<dim3( ( rows + ( 1 << plan.fast_a.lg ) - 1 ) >> plan.fast_a.lg, nq ), plan.fast_a.threads, plan.fast_a.smem, stream>>>(
-            plan.plan_ah, plan.plan[0].twiddle, d, plan.A, g_ddi, inv_P, plan.fast_a.lg );
+            plan.plan_ah, plan.plan[0].twiddle, d, plan.A, g_ddi, inv_P, plan.fast_a.lg, 0 );
     else
         k_ddi_inv_a<<<dim3( rows, d.NB ), fft_threads( d.Pa / 4 ), plan.smem_a, stream>>>( plan.plan[0], d, plan.A, g_ddi, inv_P );
     SB_CUDA_CHECK( cudaGetLastError() );
