@@ -197,7 +197,13 @@ __device__ __forceinline__ void dft_small( double2 ( &a )[R] )
     }
 }
 
-constexpr int FFT_E = 8, FFT_LG_E = 3; // elements a thread owns in the in-register stages (16: 3 stages for 4096 but
+#ifndef SB_FFT_LG_E
+#define SB_FFT_LG_E 3 // tuning builds (spirit_b200/build.py SPIRIT_B200_DEFINES): 2 = radix-4 stages
+#endif
+#ifndef SB_FFT16_MINB
+#define SB_FFT16_MINB 1 // CTAs per SM the fast kernels are compiled for (register cap 65536 / (512 * MINB))
+#endif
+constexpr int FFT_LG_E = SB_FFT_LG_E, FFT_E = 1 << FFT_LG_E; // elements a thread owns in the in-register stages (16: 3 stages for 4096 but
                                        // the twiddles push ptxas over 128 registers; 8: 4 stages, no spills)
 template<bool INVERSE, int R>
 __device__ __forceinline__ void fft16_stage(
@@ -261,9 +267,9 @@ __device__ double2 * block_fft16( const FFTPlan1D & plan, double2 * x, int ncol 
         const int r      = plan.radix[stage];
         const bool first = stage == 0, last = stage == plan.n_radix - 1;
         if( r == 16 && FFT_E >= 16 )
-            fft16_stage<INVERSE, FFT_E >= 16 ? 16 : 8>( plan, x, ncol, lg_ncol, s, lg_s, first, last );
-        else if( r == 8 )
-            fft16_stage<INVERSE, 8>( plan, x, ncol, lg_ncol, s, lg_s, first, last );
+            fft16_stage<INVERSE, FFT_E >= 16 ? 16 : FFT_E>( plan, x, ncol, lg_ncol, s, lg_s, first, last );
+        else if( r == 8 && FFT_E >= 8 )
+            fft16_stage<INVERSE, FFT_E >= 8 ? 8 : FFT_E>( plan, x, ncol, lg_ncol, s, lg_s, first, last );
         else if( r == 4 )
             fft16_stage<INVERSE, 4>( plan, x, ncol, lg_ncol, s, lg_s, first, last );
         else
@@ -421,7 +427,7 @@ __device__ __forceinline__ std::size_t pass_offset16( int j, std::size_t js, int
     return std::size_t( j >> lg_split ) * split_stride + std::size_t( unsigned( j ) & ( ( 1u << lg_split ) - 1u ) ) * js;
 }
 template<bool INVERSE>
-static __global__ void __launch_bounds__( FFT_THREADS ) k_fft_pass16(
+static __global__ void __launch_bounds__( FFT_THREADS, SB_FFT16_MINB ) k_fft_pass16(
     const __grid_constant__ FFTPlan1D plan, const __grid_constant__ PassArgs a, const int lg_ncol, const int lg_in_split,
     const int lg_out_split )
 {
@@ -626,7 +632,7 @@ static __global__ void __launch_bounds__( FFT_THREADS ) k_ddi_c_mult(
 // The tensor spectrum is stored the way this kernel walks it, D^t[kb][ka tile][comp6][kc][col]: one contiguous block per
 // CTA, read with unit stride (REAL_D: as doubles, the spectrum of a single sublattice is real).
 template<bool REAL_D>
-static __global__ void __launch_bounds__( FFT_THREADS ) k_ddi_c_mult16(
+static __global__ void __launch_bounds__( FFT_THREADS, SB_FFT16_MINB ) k_ddi_c_mult16(
     const __grid_constant__ FFTPlan1D plan, const __grid_constant__ DDIDims d, double2 * __restrict__ B,
     const void * __restrict__ Dt_v, const int lg_ncol )
 {
@@ -931,7 +937,7 @@ __device__ __forceinline__ void row_map( int lg_nrow, int & row, int & jlow, int
     jhigh_step  = blockDim.x >> ( 2 + lg_nrow );
 }
 
-static __global__ void __launch_bounds__( FFT_THREADS ) k_ddi_fwd_a16(
+static __global__ void __launch_bounds__( FFT_THREADS, SB_FFT16_MINB ) k_ddi_fwd_a16(
     const __grid_constant__ FFTPlan1D plan_h, const double2 * __restrict__ tw_full, const __grid_constant__ DDIDims d,
     ConstField3 spins, double2 * __restrict__ A, const int lg_nrow, const int q0 )
 {
@@ -983,7 +989,7 @@ static __global__ void __launch_bounds__( FFT_THREADS ) k_ddi_fwd_a16(
     }
 }
 
-static __global__ void __launch_bounds__( FFT_THREADS ) k_ddi_inv_a16(
+static __global__ void __launch_bounds__( FFT_THREADS, SB_FFT16_MINB ) k_ddi_inv_a16(
     const __grid_constant__ FFTPlan1D plan_h, const double2 * __restrict__ tw_full, const __grid_constant__ DDIDims d,
     const double2 * __restrict__ A, Field3 g, const double inv_P, const int lg_nrow, const int q0 )
 {
@@ -1473,19 +1479,29 @@ DDIPlan * ddi_plan_create( const Hamiltonian & ham, const StencilParams & sp, cu
         std::vector<double> h( 2 * blocks );
         SB_CUDA_CHECK( cudaMemcpyAsync( h.data(), part, h.size() * sizeof( double ), cudaMemcpyDeviceToHost, stream ) );
         SB_CUDA_CHECK( cudaStreamSynchronize( stream ) );
-        cudaFree( part );
         double max_imag = 0, max_abs = 0;
         for( int i = 0; i < blocks; ++i )
         {
             max_imag = std::max( max_imag, h[2 * i] );
             max_abs  = std::max( max_abs, h[2 * i + 1] );
         }
+        if( world > 1 )
+        {
+            // every rank takes the same decision: maxima over the whole spectrum, not over the local kb range
+            const double mine[2] = { max_imag, max_abs };
+            double all[2];
+            SB_CUDA_CHECK( cudaMemcpyAsync( part, mine, sizeof( mine ), cudaMemcpyHostToDevice, stream ) );
+            comm_allreduce( part, 2, true, stream );
+            SB_CUDA_CHECK( cudaMemcpyAsync( all, part, sizeof( all ), cudaMemcpyDeviceToHost, stream ) );
+            SB_CUDA_CHECK( cudaStreamSynchronize( stream ) );
+            max_imag = all[0], max_abs = all[1];
+        }
+        cudaFree( part );
         if( std::getenv( "SPIRIT_B200_DDI_VERBOSE" ) )
             std::fprintf( stderr, "spirit_b200 ddi: max |Im D^| = %.3e, max |D^| = %.3e\n", max_imag, max_abs );
         // The imaginary parts are pure round-off of the forward transforms (a few ulp of the largest element times
         // log2 P): mathematically zero. 1e-12 relative is 4 orders above what is observed and far below any signal.
-        // (world > 1: every rank must take the same decision -> only for the undistributed plan.)
-        spectrum_real = world == 1 && max_imag <= 1e-12 * max_abs;
+        spectrum_real = max_imag <= 1e-12 * max_abs;
         if( spectrum_real && small_c )
         {
             SB_CUDA_CHECK( cudaMalloc( &plan->Dhat_real, n_all * sizeof( double ) ) );

@@ -28,6 +28,13 @@ DDI_CASES = [
     ("cubic256", {"n_basis_cells": "512 2 1", "boundary_conditions": "0 0 0", "ddi_method": "fft", "llg_temperature": "0"}),
     ("cubic256", {"n_basis_cells": "64 64 32", "boundary_conditions": "1 1 0", "ddi_method": "fft", "llg_temperature": "0",
                   "ddi_n_periodic_images": "1 1 0", "ddi_pb_zero_padding": "0"}),
+    # the fast pass kernels in mixed company: 2-atom basis (half-length a-pass over 6 components, shared-memory c-pass),
+    # un-padded periodic a (no zero half), a length that is not a power of two next to two that are
+    ("ddi", {"n_basis_cells": "64 32 2", "boundary_conditions": "0 0 0"}),
+    ("ddi", {"n_basis_cells": "32 32 32", "boundary_conditions": "0 0 0"}),
+    ("cubic256", {"n_basis_cells": "128 16 2", "boundary_conditions": "1 0 0", "ddi_method": "fft", "llg_temperature": "0",
+                  "ddi_n_periodic_images": "2 0 0", "ddi_pb_zero_padding": "0"}),
+    ("cubic256", {"n_basis_cells": "36 32 32", "boundary_conditions": "0 0 0", "ddi_method": "fft", "llg_temperature": "0"}),
 ]
 
 
