@@ -280,6 +280,90 @@ __device__ double2 * block_fft16( const FFTPlan1D & plan, double2 * x, int ncol 
     return x;
 }
 
+// ---------------------------------------------------------------------------------------------
+// The same transform with the length as a template parameter (n = 1 << LOGN, 64 <= n <= 4096): the stage loop is unrolled
+// at compile time, strides, radices and the padding arithmetic are immediates. With a run-time length ptxas hoists the
+// index arithmetic of every stage variant out of the stage loop (216 registers uncapped, spills under the 128 cap).
+// Used by the fast pass kernels below, which are instantiated per length and selected on the host.
+// ---------------------------------------------------------------------------------------------
+#ifndef SB_FFT_TW_CHAIN_LOGN
+#define SB_FFT_TW_CHAIN_LOGN 6 // from this length on the twiddles of a butterfly are powers of ONE table entry (measured: faster at every length, profiles/r1u)
+#endif
+template<bool INVERSE, int LOGN, int R, int LG_S, bool FIRST, bool LAST>
+__device__ __forceinline__ void fft_stage_ct( const double2 * __restrict__ twiddle, double2 * x, const int lg_ncol, const int col, const int tt )
+{
+    constexpr int N = 1 << LOGN, PER = FFT_E / R, PER_COL = N >> FFT_LG_E, STEP = N / R, S = 1 << LG_S;
+    // long transforms: R - 1 look-ups per butterfly are gathers of 16 bytes from as many cache lines per thread, which
+    // cost more than the butterfly; there the powers w^2 .. w^(R-1) of the one entry w = w_{n/s}^p are multiplied up
+    constexpr bool CHAIN = LOGN >= SB_FFT_TW_CHAIN_LOGN;
+    double2 v[PER][R];
+    double2 w1[PER];
+    if( !LAST && CHAIN )
+    {
+#pragma unroll
+        for( int jj = 0; jj < PER; ++jj )
+            w1[jj] = __ldg( twiddle + ( ( ( tt + PER_COL * jj ) >> LG_S ) << LG_S ) );
+    }
+#pragma unroll
+    for( int jj = 0; jj < PER; ++jj )
+    {
+        const int item = tt + PER_COL * jj; // = q + s p
+#pragma unroll
+        for( int i = 0; i < R; ++i )
+        {
+            const int a   = item + STEP * i;
+            const int idx = FIRST ? a : a + ( a >> 4 );
+            v[jj][i]      = x[( idx << lg_ncol ) + col];
+        }
+        dft_small<INVERSE, R>( v[jj] );
+    }
+    __syncthreads();
+#pragma unroll
+    for( int jj = 0; jj < PER; ++jj )
+    {
+        const int item = tt + PER_COL * jj;
+        const int q = item & ( S - 1 ), p = item >> LG_S;
+        double2 wc = make_double2( 1.0, 0.0 );
+#pragma unroll
+        for( int i = 0; i < R; ++i )
+        {
+            double2 val = v[jj][i];
+            if( !LAST && i > 0 )
+            {
+                if( CHAIN )
+                {
+                    const double2 w = INVERSE ? make_double2( w1[jj].x, -w1[jj].y ) : w1[jj];
+                    wc              = i == 1 ? w : cmul( wc, w );
+                }
+                else
+                {
+                    const double2 w = __ldg( twiddle + ( ( i * p ) << LG_S ) ); // w_{n/s}^{p i}
+                    wc              = INVERSE ? make_double2( w.x, -w.y ) : w;
+                }
+                val = cmul( val, wc );
+            }
+            const int o   = q + S * ( R * p + i );
+            const int idx = LAST ? o : o + ( o >> 4 );
+            x[( idx << lg_ncol ) + col] = val;
+        }
+    }
+    __syncthreads();
+}
+// stages: radix FFT_E while it divides what is left, then the rest (2 or 4) -- the plan of make_plan_1d for fast16 lengths
+template<bool INVERSE, int LOGN, int LG_S = 0>
+__device__ __forceinline__ void block_fft_ct( const double2 * __restrict__ twiddle, double2 * x, const int lg_ncol, const int col, const int tt )
+{
+    constexpr int LEFT = LOGN - LG_S;
+    if constexpr( LEFT >= FFT_LG_E )
+    {
+        fft_stage_ct<INVERSE, LOGN, FFT_E, LG_S, LG_S == 0, LEFT == FFT_LG_E>( twiddle, x, lg_ncol, col, tt );
+        if constexpr( LEFT > FFT_LG_E )
+            block_fft_ct<INVERSE, LOGN, LG_S + FFT_LG_E>( twiddle, x, lg_ncol, col, tt );
+    }
+    else
+        fft_stage_ct<INVERSE, LOGN, ( 1 << LEFT ), LG_S, LG_S == 0, true>( twiddle, x, lg_ncol, col, tt );
+}
+
 // In-shared-memory Stockham autosort FFT of `ncol` independent sequences of length plan.n stored as x[j * ncol + col].
 // Returns the buffer (x or y) that holds the result. All threads of the CTA must call.
 template<bool INVERSE>
@@ -426,13 +510,13 @@ __device__ __forceinline__ std::size_t pass_offset16( int j, std::size_t js, int
 {
     return std::size_t( j >> lg_split ) * split_stride + std::size_t( unsigned( j ) & ( ( 1u << lg_split ) - 1u ) ) * js;
 }
-template<bool INVERSE>
+template<bool INVERSE, int LOGN>
 static __global__ void __launch_bounds__( FFT_THREADS, SB_FFT16_MINB ) k_fft_pass16(
     const __grid_constant__ FFTPlan1D plan, const __grid_constant__ PassArgs a, const int lg_ncol, const int lg_in_split,
     const int lg_out_split )
 {
     extern __shared__ double2 smem[];
-    const int n = plan.n, ncol = 1 << lg_ncol;
+    const int ncol = 1 << lg_ncol;
     const int o = blockIdx.y, u0 = blockIdx.x << lg_ncol;
     const int col = threadIdx.x & ( ncol - 1 ), j0 = threadIdx.x >> lg_ncol, jstep = blockDim.x >> lg_ncol;
     const bool valid   = u0 + col < a.n_u;
@@ -451,7 +535,7 @@ static __global__ void __launch_bounds__( FFT_THREADS, SB_FFT16_MINB ) k_fft_pas
     for( int k = 0; k < FFT_E; ++k )
         smem[( ( j0 + k * jstep ) << lg_ncol ) + col] = v[k];
     __syncthreads();
-    block_fft16<INVERSE>( plan, smem, ncol );
+    block_fft_ct<INVERSE, LOGN>( plan.twiddle, smem, lg_ncol, col, j0 );
     if( valid )
     {
         double2 * out = a.out + std::size_t( o ) * a.out_os + u0 + col;
@@ -631,13 +715,14 @@ static __global__ void __launch_bounds__( FFT_THREADS ) k_ddi_c_mult(
 // tensor multiply in place as well (one sublattice: F(k) needs S(k) of the same point only), (Pc / 8) << lg_ncol threads.
 // The tensor spectrum is stored the way this kernel walks it, D^t[kb][ka tile][comp6][kc][col]: one contiguous block per
 // CTA, read with unit stride (REAL_D: as doubles, the spectrum of a single sublattice is real).
-template<bool REAL_D>
+template<bool REAL_D, int LOGN>
 static __global__ void __launch_bounds__( FFT_THREADS, SB_FFT16_MINB ) k_ddi_c_mult16(
     const __grid_constant__ FFTPlan1D plan, const __grid_constant__ DDIDims d, double2 * __restrict__ B,
     const void * __restrict__ Dt_v, const int lg_ncol )
 {
     extern __shared__ double2 smem[];
-    const int n = plan.n, ncol = 1 << lg_ncol;
+    constexpr int n = 1 << LOGN;
+    const int ncol  = 1 << lg_ncol;
     const int tile_elems   = n << lg_ncol;
     const int bufp         = tile_elems + ( tile_elems >> 4 ) + 1; // room for the padded layout between the stages
     const int kb = blockIdx.y, u0 = blockIdx.x << lg_ncol;
@@ -655,19 +740,15 @@ static __global__ void __launch_bounds__( FFT_THREADS, SB_FFT16_MINB ) k_ddi_c_m
             asm volatile( "prefetch.global.L2 [%0];" ::"l"( Dblock + off ) );
     }
     // element (q, c) of the column = c_operand; exactly FFT_E planes c = j0 + k jstep per thread and component
-    std::size_t off_c[FFT_E];
-#pragma unroll
-    for( int k = 0; k < FFT_E; ++k )
+    // (recomputed where it is used: eight 64-bit offsets held across the transforms cost more in spills than this arithmetic)
+    auto off_c = [&]( int k ) -> std::size_t
     {
         const int c = j0 + k * jstep;
         if( d.block_stride == 0 )
-            off_c[k] = std::size_t( c ) * plane;
-        else
-        {
-            const int blk = c / d.c_block;
-            off_c[k]      = std::size_t( blk ) * d.block_stride + std::size_t( c - blk * d.c_block ) * plane;
-        }
-    }
+            return std::size_t( c ) * plane;
+        const int blk = c / d.c_block;
+        return std::size_t( blk ) * d.block_stride + std::size_t( c - blk * d.c_block ) * plane;
+    };
     for( int q = 0; q < 3; ++q )
     {
         double2 * x            = smem + q * bufp;
@@ -678,15 +759,16 @@ static __global__ void __launch_bounds__( FFT_THREADS, SB_FFT16_MINB ) k_ddi_c_m
         {
             v[k] = make_double2( 0.0, 0.0 );
             if( valid && j0 + k * jstep < d.Nc )
-                v[k] = column_q[off_c[k]];
+                v[k] = column_q[off_c( k )];
         }
 #pragma unroll
         for( int k = 0; k < FFT_E; ++k )
             x[( ( j0 + k * jstep ) << lg_ncol ) + col] = v[k];
     }
     __syncthreads();
+#pragma unroll 1
     for( int q = 0; q < 3; ++q )
-        block_fft16<false>( plan, smem + q * bufp, ncol );
+        block_fft_ct<false, LOGN>( plan.twiddle, smem + q * bufp, lg_ncol, col, j0 );
     {
         const std::size_t block = ( std::size_t( kb ) * gridDim.x + blockIdx.x ) * 6 * std::size_t( tile_elems );
 #pragma unroll 4
@@ -718,8 +800,9 @@ static __global__ void __launch_bounds__( FFT_THREADS, SB_FFT16_MINB ) k_ddi_c_m
         }
     }
     __syncthreads();
+#pragma unroll 1
     for( int q = 0; q < 3; ++q )
-        block_fft16<true>( plan, smem + q * bufp, ncol );
+        block_fft_ct<true, LOGN>( plan.twiddle, smem + q * bufp, lg_ncol, col, j0 );
     if( valid )
         for( int q = 0; q < 3; ++q )
         {
@@ -728,7 +811,7 @@ static __global__ void __launch_bounds__( FFT_THREADS, SB_FFT16_MINB ) k_ddi_c_m
 #pragma unroll
             for( int k = 0; k < FFT_E; ++k )
                 if( j0 + k * jstep < d.Nc )
-                    column_q[off_c[k]] = x[( ( j0 + k * jstep ) << lg_ncol ) + col];
+                    column_q[off_c( k )] = x[( ( j0 + k * jstep ) << lg_ncol ) + col];
         }
 }
 
@@ -937,12 +1020,13 @@ __device__ __forceinline__ void row_map( int lg_nrow, int & row, int & jlow, int
     jhigh_step  = blockDim.x >> ( 2 + lg_nrow );
 }
 
+template<int LOGM>
 static __global__ void __launch_bounds__( FFT_THREADS, SB_FFT16_MINB ) k_ddi_fwd_a16(
     const __grid_constant__ FFTPlan1D plan_h, const double2 * __restrict__ tw_full, const __grid_constant__ DDIDims d,
     ConstField3 spins, double2 * __restrict__ A, const int lg_nrow, const int q0 )
 {
     extern __shared__ double2 smem[];
-    const int m = plan_h.n, nrow = 1 << lg_nrow;
+    constexpr int m = 1 << LOGM;
     int rl, jlow, jhigh, jstep;
     row_map( lg_nrow, rl, jlow, jhigh, jstep );
     const int q = q0 + blockIdx.y, comp = q % 3, ib = q / 3;
@@ -969,7 +1053,7 @@ static __global__ void __launch_bounds__( FFT_THREADS, SB_FFT16_MINB ) k_ddi_fwd
     for( int k = 0; k < FFT_E; ++k )
         smem[( ( 4 * ( jhigh + k * jstep ) + jlow ) << lg_nrow ) + rl] = make_double2( mu * zz[k].x, mu * zz[k].y );
     __syncthreads();
-    block_fft16<false>( plan_h, smem, nrow );
+    block_fft_ct<false, LOGM>( plan_h.twiddle, smem, lg_nrow, threadIdx.x & ( ( 1 << lg_nrow ) - 1 ), threadIdx.x >> lg_nrow );
     if( !valid )
         return;
     double2 * out = A + ( ( std::size_t( q ) * d.Nc + c ) * d.Nb + b ) * d.Ha;
@@ -989,12 +1073,13 @@ static __global__ void __launch_bounds__( FFT_THREADS, SB_FFT16_MINB ) k_ddi_fwd
     }
 }
 
+template<int LOGM>
 static __global__ void __launch_bounds__( FFT_THREADS, SB_FFT16_MINB ) k_ddi_inv_a16(
     const __grid_constant__ FFTPlan1D plan_h, const double2 * __restrict__ tw_full, const __grid_constant__ DDIDims d,
     const double2 * __restrict__ A, Field3 g, const double inv_P, const int lg_nrow, const int q0 )
 {
     extern __shared__ double2 smem[];
-    const int m = plan_h.n, nrow = 1 << lg_nrow;
+    constexpr int m = 1 << LOGM;
     int rl, jlow, jhigh, jstep;
     row_map( lg_nrow, rl, jlow, jhigh, jstep );
     const int q = q0 + blockIdx.y, comp = q % 3, ib = q / 3;
@@ -1019,7 +1104,7 @@ static __global__ void __launch_bounds__( FFT_THREADS, SB_FFT16_MINB ) k_ddi_inv
         smem[( k << lg_nrow ) + rl] = Z;
     }
     __syncthreads();
-    block_fft16<true>( plan_h, smem, nrow );
+    block_fft_ct<true, LOGM>( plan_h.twiddle, smem, lg_nrow, threadIdx.x & ( ( 1 << lg_nrow ) - 1 ), threadIdx.x >> lg_nrow );
     if( !valid )
         return;
     const std::size_t site0 = std::size_t( d.Na ) * d.NB * b + std::size_t( d.plane_stride ) * ( c + d.halo ) + ib;
@@ -1241,6 +1326,85 @@ void allow_smem( K kernel, std::size_t bytes )
 {
     SB_CUDA_CHECK( cudaFuncSetAttribute( kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int( bytes ) ) );
 }
+// Host-side selection of the per-length instantiations of the fast kernels (n = 64 .. 4096)
+int ilog2( int n )
+{
+    return 31 - __builtin_clz( unsigned( n ) );
+}
+#define SB_FOR_LOGN( C ) C( 6 ) C( 7 ) C( 8 ) C( 9 ) C( 10 ) C( 11 ) C( 12 )
+template<bool INVERSE>
+void launch_pass16(
+    const DDIPlan::Fast & f, dim3 grid, cudaStream_t stream, const FFTPlan1D & plan, const PassArgs & a, int lg_in, int lg_out, bool configure = false )
+{
+    switch( ilog2( plan.n ) )
+    {
+#define C( L )                                                                                                         \
+    case L:                                                                                                            \
+        if( configure )                                                                                                \
+            allow_smem( k_fft_pass16<INVERSE, L>, f.smem );                                                            \
+        else                                                                                                           \
+            k_fft_pass16<INVERSE, L><<<grid, f.threads, f.smem, stream>>>( plan, a, f.lg, lg_in, lg_out );             \
+        break;
+        SB_FOR_LOGN( C )
+#undef C
+        default: throw std::logic_error( "spirit_b200: no fast pass kernel for this length" );
+    }
+}
+template<bool REAL_D>
+void launch_c_mult16(
+    const DDIPlan::Fast & f, dim3 grid, cudaStream_t stream, const FFTPlan1D & plan, const DDIDims & dc, double2 * operand, const void * Dt,
+    bool configure = false )
+{
+    switch( ilog2( plan.n ) )
+    {
+#define C( L )                                                                                                         \
+    case L:                                                                                                            \
+        if( configure )                                                                                                \
+            allow_smem( k_ddi_c_mult16<REAL_D, L>, f.smem );                                                           \
+        else                                                                                                           \
+            k_ddi_c_mult16<REAL_D, L><<<grid, f.threads, f.smem, stream>>>( plan, dc, operand, Dt, f.lg );             \
+        break;
+        SB_FOR_LOGN( C )
+#undef C
+        default: throw std::logic_error( "spirit_b200: no fast c-pass kernel for this length" );
+    }
+}
+void launch_fwd_a16(
+    const DDIPlan::Fast & f, dim3 grid, cudaStream_t stream, const FFTPlan1D & plan_h, const double2 * tw_full, const DDIDims & d,
+    ConstField3 spins, double2 * A, int q0, bool configure = false )
+{
+    switch( ilog2( plan_h.n ) )
+    {
+#define C( L )                                                                                                         \
+    case L:                                                                                                            \
+        if( configure )                                                                                                \
+            allow_smem( k_ddi_fwd_a16<L>, f.smem );                                                                    \
+        else                                                                                                           \
+            k_ddi_fwd_a16<L><<<grid, f.threads, f.smem, stream>>>( plan_h, tw_full, d, spins, A, f.lg, q0 );           \
+        break;
+        SB_FOR_LOGN( C )
+#undef C
+        default: throw std::logic_error( "spirit_b200: no fast a-pass kernel for this length" );
+    }
+}
+void launch_inv_a16(
+    const DDIPlan::Fast & f, dim3 grid, cudaStream_t stream, const FFTPlan1D & plan_h, const double2 * tw_full, const DDIDims & d,
+    const double2 * A, Field3 g, double inv_P, int q0, bool configure = false )
+{
+    switch( ilog2( plan_h.n ) )
+    {
+#define C( L )                                                                                                         \
+    case L:                                                                                                            \
+        if( configure )                                                                                                \
+            allow_smem( k_ddi_inv_a16<L>, f.smem );                                                                    \
+        else                                                                                                           \
+            k_ddi_inv_a16<L><<<grid, f.threads, f.smem, stream>>>( plan_h, tw_full, d, A, g, inv_P, f.lg, q0 );        \
+        break;
+        SB_FOR_LOGN( C )
+#undef C
+        default: throw std::logic_error( "spirit_b200: no fast a-pass kernel for this length" );
+    }
+}
 } // namespace
 
 void ddi_plan_destroy( DDIPlan * p )
@@ -1366,20 +1530,24 @@ DDIPlan * ddi_plan_create( const Hamiltonian & ham, const StencilParams & sp, cu
             if( plan->plan_ah.fast16 )
                 shape( plan->fast_a, d.Pa / 2, 1, "SPIRIT_B200_FFT_LG_A" );
         }
+        // lengths up to 4096 have instantiations
+        plan->fast_b.on = plan->fast_b.on && d.Pb <= 4096;
+        plan->fast_c.on = plan->fast_c.on && d.Pc <= 4096;
+        plan->fast_a.on = plan->fast_a.on && d.Pa / 2 <= 4096;
         if( plan->fast_b.on )
         {
-            allow_smem( k_fft_pass16<false>, plan->fast_b.smem );
-            allow_smem( k_fft_pass16<true>, plan->fast_b.smem );
+            launch_pass16<false>( plan->fast_b, dim3(), stream, plan->plan[1], PassArgs{}, 0, 0, true );
+            launch_pass16<true>( plan->fast_b, dim3(), stream, plan->plan[1], PassArgs{}, 0, 0, true );
         }
         if( plan->fast_c.on )
         {
-            allow_smem( k_ddi_c_mult16<false>, plan->fast_c.smem );
-            allow_smem( k_ddi_c_mult16<true>, plan->fast_c.smem );
+            launch_c_mult16<false>( plan->fast_c, dim3(), stream, plan->plan[2], plan->dims_c, nullptr, nullptr, true );
+            launch_c_mult16<true>( plan->fast_c, dim3(), stream, plan->plan[2], plan->dims_c, nullptr, nullptr, true );
         }
         if( plan->fast_a.on )
         {
-            allow_smem( k_ddi_fwd_a16, plan->fast_a.smem );
-            allow_smem( k_ddi_inv_a16, plan->fast_a.smem );
+            launch_fwd_a16( plan->fast_a, dim3(), stream, plan->plan_ah, nullptr, d, ConstField3{}, nullptr, 0, true );
+            launch_inv_a16( plan->fast_a, dim3(), stream, plan->plan_ah, nullptr, d, nullptr, Field3{}, 0.0, 0, true );
         }
         if( world > 1 && plan->fast_a.on && plan->fast_b.on && !env_flag_off( "SPIRIT_B200_DDI_PIPELINE" ) )
         {
@@ -1570,9 +1738,9 @@ void launch_c_mult( DDIPlan & plan, double2 * operand, cudaStream_t stream )
     {
         const dim3 grid( ( d.Ha + ( 1 << plan.fast_c.lg ) - 1 ) >> plan.fast_c.lg, kbl );
         if( plan.Dt_real )
-            k_ddi_c_mult16<true><<<grid, plan.fast_c.threads, plan.fast_c.smem, stream>>>( plan.plan[2], dc, operand, plan.Dt, plan.fast_c.lg );
+            launch_c_mult16<true>( plan.fast_c, grid, stream, plan.plan[2], dc, operand, plan.Dt );
         else
-            k_ddi_c_mult16<false><<<grid, plan.fast_c.threads, plan.fast_c.smem, stream>>>( plan.plan[2], dc, operand, plan.Dt, plan.fast_c.lg );
+            launch_c_mult16<false>( plan.fast_c, grid, stream, plan.plan[2], dc, operand, plan.Dt );
     }
     else
     {
@@ -1612,15 +1780,14 @@ int ddi_gradient_pipelined( DDIPlan & plan, ConstField3 spins, Field3 g_ddi, cud
     };
     for( int q = 0; q < nq; ++q )
     {
-        k_ddi_fwd_a16<<<grid_a, plan.fast_a.threads, plan.fast_a.smem, stream>>>(
-            plan.plan_ah, plan.plan[0].twiddle, d, spins, plan.A, plan.fast_a.lg, q );
+        launch_fwd_a16( plan.fast_a, grid_a, stream, plan.plan_ah, plan.plan[0].twiddle, d, spins, plan.A, q );
         PassArgs pb{};
         pb.in    = plan.A + std::size_t( q ) * ncl * d.Nb * d.Ha;
         pb.out   = plan.B + std::size_t( q ) * comp_elems;
         pb.in_os = std::size_t( d.Nb ) * d.Ha, pb.in_js = pb.out_js = d.Ha;
         pb.out_os = std::size_t( kbl ) * d.Ha, pb.out_split = kbl, pb.out_split_stride = dc.block_stride;
         pb.n_u = d.Ha, pb.n_o = ncl, pb.n_in = d.Nb, pb.n_out = d.Pb, pb.ncol = 1 << plan.fast_b.lg, pb.scale = 1.0;
-        k_fft_pass16<false><<<grid_b, plan.fast_b.threads, plan.fast_b.smem, stream>>>( plan.plan[1], pb, plan.fast_b.lg, 31, plan.lg_split );
+        launch_pass16<false>( plan.fast_b, grid_b, stream, plan.plan[1], pb, 31, plan.lg_split );
         SB_CUDA_CHECK( cudaEventRecord( plan.ev_q[q], stream ) );
         SB_CUDA_CHECK( cudaStreamWaitEvent( cs, plan.ev_q[q], 0 ) );
         all_to_all( plan.B, plan.C, q );
@@ -1645,9 +1812,8 @@ int ddi_gradient_pipelined( DDIPlan & plan, ConstField3 spins, Field3 g_ddi, cud
         ib.out_os = std::size_t( d.Nb ) * d.Ha, ib.in_js = ib.out_js = d.Ha;
         ib.in_os = std::size_t( kbl ) * d.Ha, ib.in_split = kbl, ib.in_split_stride = dc.block_stride;
         ib.n_u = d.Ha, ib.n_o = ncl, ib.n_in = d.Pb, ib.n_out = d.Nb, ib.ncol = 1 << plan.fast_b.lg, ib.scale = 1.0;
-        k_fft_pass16<true><<<grid_b, plan.fast_b.threads, plan.fast_b.smem, stream>>>( plan.plan[1], ib, plan.fast_b.lg, plan.lg_split, 31 );
-        k_ddi_inv_a16<<<grid_a, plan.fast_a.threads, plan.fast_a.smem, stream>>>(
-            plan.plan_ah, plan.plan[0].twiddle, d, plan.A, g_ddi, inv_P, plan.fast_a.lg, q );
+        launch_pass16<true>( plan.fast_b, grid_b, stream, plan.plan[1], ib, plan.lg_split, 31 );
+        launch_inv_a16( plan.fast_a, grid_a, stream, plan.plan_ah, plan.plan[0].twiddle, d, plan.A, g_ddi, inv_P, q );
     }
     SB_CUDA_CHECK( cudaGetLastError() );
     return 4 * nq + 1;
@@ -1666,8 +1832,9 @@ int ddi_gradient( DDIPlan & plan, ConstField3 spins, Field3 g_ddi, cudaStream_t 
     const int kbl      = dc.Pb;
     const int rows     = d.Nb * d.Nc;
     if( plan.fast_a.on )
-        k_ddi_fwd_a16<<<dim3( ( rows + ( 1 << plan.fast_a.lg ) - 1 ) >> plan.fast_a.lg, nq ), plan.fast_a.threads, plan.fast_a.smem, stream>>>(
-            plan.plan_ah, plan.plan[0].twiddle, d, spins, plan.A, plan.fast_a.lg, 0 );
+        launch_fwd_a16(
+            plan.fast_a, dim3( ( rows + ( 1 << plan.fast_a.lg ) - 1 ) >> plan.fast_a.lg, nq ), stream, plan.plan_ah, plan.plan[0].twiddle, d, spins,
+            plan.A, 0 );
     else
         k_ddi_fwd_a<<<dim3( rows, d.NB ), fft_threads( d.Pa / 4 ), plan.smem_a, stream>>>( plan.plan[0], d, spins, plan.A );
     // forward b: A[q][c][b][ka] -> B; outer index o = q * ncl + c. Single device: B[o][kb][ka]; distributed: the kb axis
@@ -1687,7 +1854,7 @@ int ddi_gradient( DDIPlan & plan, ConstField3 spins, Field3 g_ddi, cudaStream_t 
     const dim3 grid_b( ( d.Ha + plan.ncol_b - 1 ) / plan.ncol_b, pb.n_o );
     const dim3 grid_b16( ( d.Ha + ( 1 << plan.fast_b.lg ) - 1 ) >> plan.fast_b.lg, pb.n_o );
     if( plan.fast_b.on )
-        k_fft_pass16<false><<<grid_b16, plan.fast_b.threads, plan.fast_b.smem, stream>>>( plan.plan[1], pb, plan.fast_b.lg, 31, plan.lg_split );
+        launch_pass16<false>( plan.fast_b, grid_b16, stream, plan.plan[1], pb, 31, plan.lg_split );
     else
         k_fft_pass<false><<<grid_b, fft_threads( d.Pb / 4 * plan.ncol_b ), plan.smem_b, stream>>>( plan.plan[1], pb );
 
@@ -1733,13 +1900,14 @@ int ddi_gradient( DDIPlan & plan, ConstField3 spins, Field3 g_ddi, cudaStream_t 
         ib.in_os = std::size_t( d.Pb ) * d.Ha;
     ib.n_u = d.Ha, ib.n_o = nq * d.Nc, ib.n_in = d.Pb, ib.n_out = d.Nb, ib.ncol = plan.ncol_b, ib.scale = 1.0;
     if( plan.fast_b.on )
-        k_fft_pass16<true><<<grid_b16, plan.fast_b.threads, plan.fast_b.smem, stream>>>( plan.plan[1], ib, plan.fast_b.lg, plan.lg_split, 31 );
+        launch_pass16<true>( plan.fast_b, grid_b16, stream, plan.plan[1], ib, plan.lg_split, 31 );
     else
         k_fft_pass<true><<<grid_b, fft_threads( d.Pb / 4 * plan.ncol_b ), plan.smem_b, stream>>>( plan.plan[1], ib );
     const double inv_P = 1.0 / ( double( d.Pa ) * d.Pb * d.Pc );
     if( plan.fast_a.on )
-        k_ddi_inv_a16<<<dim3( ( rows + ( 1 << plan.fast_a.lg ) - 1 ) >> plan.fast_a.lg, nq ), plan.fast_a.threads, plan.fast_a.smem, stream>>>(
-            plan.plan_ah, plan.plan[0].twiddle, d, plan.A, g_ddi, inv_P, plan.fast_a.lg, 0 );
+        launch_inv_a16(
+            plan.fast_a, dim3( ( rows + ( 1 << plan.fast_a.lg ) - 1 ) >> plan.fast_a.lg, nq ), stream, plan.plan_ah, plan.plan[0].twiddle, d, plan.A,
+            g_ddi, inv_P, 0 );
     else
         k_ddi_inv_a<<<dim3( rows, d.NB ), fft_threads( d.Pa / 4 ), plan.smem_a, stream>>>( plan.plan[0], d, plan.A, g_ddi, inv_P );
     SB_CUDA_CHECK( cudaGetLastError() );
