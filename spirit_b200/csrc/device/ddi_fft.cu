@@ -638,7 +638,6 @@ static __global__ void __launch_bounds__( FFT_THREADS ) k_ddi_c_mult(
     const std::size_t buf = std::size_t( n ) * ncol;
     const int kb = blockIdx.y, u0 = blockIdx.x * ncol;
     const int nc = min( ncol, d.Ha - u0 );
-    const std::size_t c_stride = std::size_t( d.Pb ) * d.Ha;
     // load + forward transform every component
     __shared__ int result_in_y; // all transforms have the same number of stages: same final buffer
     for( int q = 0; q < nq; ++q )
@@ -1487,7 +1486,9 @@ DDIPlan * ddi_plan_create( const Hamiltonian & ham, const StencilParams & sp, cu
     make_plan_1d( plan->plan[1], plan->twiddle[1], d.Pb );
     make_plan_1d( plan->plan[2], plan->twiddle[2], d.Pc );
     plan->ncol_b = choose_ncol( d.Pb, 1, d.Ha );
-    plan->ncol_c = choose_ncol( d.Pc, nq, d.Ha );
+    // (the generic c-pass holds 3 NB components x 2 buffers of a column: lengths it cannot hold are served by the fast kernel only)
+    const bool generic_c_fits = std::size_t( d.Pc ) * 2 * sizeof( double2 ) * nq <= std::size_t( MAX_SMEM_FFT );
+    plan->ncol_c              = generic_c_fits ? choose_ncol( d.Pc, nq, d.Ha ) : 1;
     plan->smem_a = std::size_t( d.Pa ) * 2 * sizeof( double2 );
     plan->smem_b = std::size_t( d.Pb ) * 2 * sizeof( double2 ) * plan->ncol_b;
     // + one sixteenth of a buffer: the padded in-place stages of block_fft16 run past the LAST component's second buffer
@@ -1498,9 +1499,10 @@ DDIPlan * ddi_plan_create( const Hamiltonian & ham, const StencilParams & sp, cu
     allow_smem( k_ddi_fwd_a, plan->smem_a );
     allow_smem( k_ddi_inv_a, plan->smem_a );
     allow_smem( k_fft_real_rows, plan->smem_a );
-    allow_smem( k_fft_pass<false>, std::max( plan->smem_b, std::size_t( d.Pc ) * 2 * sizeof( double2 ) * plan->ncol_b ) );
+    allow_smem( k_fft_pass<false>, plan->smem_b ); // (the c-pass of the tensor setup raises it to its own need below)
     allow_smem( k_fft_pass<true>, plan->smem_b );
-    allow_smem( k_ddi_c_mult, plan->smem_c );
+    if( generic_c_fits )
+        allow_smem( k_ddi_c_mult, plan->smem_c );
     {
         // (n / 8) << lg threads, about 256 per CTA; one in-place buffer of n << lg elements (+ 1/16 padding) per transform set
         const bool allow = !env_flag_off( "SPIRIT_B200_FFT_FAST" );
@@ -1636,6 +1638,8 @@ DDIPlan * ddi_plan_create( const Hamiltonian & ham, const StencilParams & sp, cu
     const bool small_c = d.NB == 1 && ( d.Pc & ( d.Pc - 1 ) ) == 0 && d.Pc <= 32;
     if( small_c )
         plan->fast_c.on = false; // the in-register kernel serves thin films
+    if( !generic_c_fits && !plan->fast_c.on )
+        throw std::runtime_error( "spirit_b200: padded lattice dimension c too long for the shared-memory FFT passes" );
     bool spectrum_real = false;
     if( small_c || plan->fast_c.on )
     {

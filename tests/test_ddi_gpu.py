@@ -90,3 +90,42 @@ def test_ddi_steps(cfg, product, oracle, solver, preset, overrides):
         assert np.abs(p.spins() - o.spins()).max() < 1e-10
     p.close()
     o.close()
+
+
+# ---------------------------------------------------------------------------------------------------------------------------
+# Every per-length instantiation of the fast pass kernels (64 ... 4096) against the reference. The reference's FFT path
+# needs Na >= Nb >= Nc, so long b- and c-axes are checked through a symmetry of the simple cubic lattice with isotropic
+# exchange + dipolar coupling only (no DMI, no anisotropy, no field): exchanging two lattice axes AND the same two spin
+# components maps a configuration and its gradient onto those of the lattice with the two axis lengths exchanged.
+# ---------------------------------------------------------------------------------------------------------------------------
+ISOTROPIC = {"boundary_conditions": "0 0 0", "ddi_method": "fft", "llg_temperature": "0", "dij": "0", "n_shells_dmi": "0",
+             "anisotropy_magnitude": "0", "external_field_magnitude": "0"}
+AXIS_SWAPS = {"a": (None, None), "b": ((0, 2, 1, 3), [1, 0, 2]), "c": ((2, 1, 0, 3), [2, 1, 0])}
+
+
+def _swap(field, cells, axis):
+    """field [nos][3] on the lattice `cells` = (Na, Nb, Nc) -> the same field on the lattice with `axis` and a exchanged"""
+    perm, comps = AXIS_SWAPS[axis]
+    if perm is None:
+        return field
+    f4 = field.reshape(cells[2], cells[1], cells[0], 3)
+    return np.ascontiguousarray(f4.transpose(perm)[..., comps]).reshape(-1, 3)
+
+
+@pytest.mark.parametrize("axis,n_long", [("a", 64), ("a", 256), ("a", 1024), ("a", 2048),
+                                         ("b", 64), ("b", 128), ("b", 256), ("b", 512), ("b", 1024), ("b", 2048),
+                                         ("c", 64), ("c", 128), ("c", 256), ("c", 512), ("c", 1024), ("c", 2048)])
+def test_ddi_every_transform_length_vs_reference(cfg, product, oracle, axis, n_long):
+    short = 8
+    cells_o = (n_long, short, short)  # the reference always sees the long axis as a
+    cells_p = {"a": (n_long, short, short), "b": (short, n_long, short), "c": (short, short, n_long)}[axis]
+    p = S.Session(product, cfg("cubic256", n_basis_cells="%d %d %d" % cells_p, **ISOTROPIC))
+    o = S.Session(oracle, cfg("cubic256", n_basis_cells="%d %d %d" % cells_o, **ISOTROPIC))
+    s_p = unit_random(p.nos, 11)
+    s_o = _swap(s_p, cells_p, axis)
+    gp, ep = p.gradient_and_energy(s_p)
+    go, eo = o.gradient_and_energy(s_o)
+    assert np.abs(_swap(gp, cells_p, axis) - go).max() <= 1e-12 * np.abs(go).max()
+    assert abs(ep - eo) <= 1e-12 * np.abs(go).sum()
+    p.close()
+    o.close()

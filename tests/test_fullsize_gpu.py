@@ -137,3 +137,22 @@ def test_gneb_64_images_replicate_the_reference_chain(cfg, product, oracle):
     assert np.abs(rx - reps * rx_ref).max() <= 1e-9 * reps * rx_ref.max()
     assert np.abs(e - reps * reps * e_ref).max() <= 1e-10 * np.abs(reps * reps * e_ref).max()
     p.close()
+
+
+def test_dipolar_fast_passes_equal_generic_passes_at_256_cubed(cfg, product, monkeypatch):
+    """BASELINE configs[4] per-GPU size: the per-length in-place pass kernels (half-length real a-pass, real tile-ordered
+    tensor) against the generic two-buffer mixed-radix passes of the same library, which are pinned against the reference at
+    the sizes it can run (tests/test_ddi_gpu.py). Two independent code paths, one answer."""
+    import os
+    over = dict(n_basis_cells="256 256 256", boundary_conditions="0 0 0", ddi_method="fft", llg_temperature="0")
+    fast = S.Session(product, cfg("cubic256", **over))
+    s = unit_random(fast.nos, 5)
+    g_fast, e_fast = fast.gradient_and_energy(s)
+    fast.close()
+    monkeypatch.setenv("SPIRIT_B200_FFT_FAST", "0")
+    generic = S.Session(product, cfg("cubic256", **over))
+    g_gen, e_gen = generic.gradient_and_energy(s)
+    generic.close()
+    assert np.abs(g_fast).max() > 1.0
+    assert np.abs(g_fast - g_gen).max() <= 1e-12 * np.abs(g_gen).max()
+    assert abs(e_fast - e_gen) <= 1e-12 * np.abs(g_gen).sum()
