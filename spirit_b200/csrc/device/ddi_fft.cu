@@ -510,42 +510,56 @@ __device__ __forceinline__ std::size_t pass_offset16( int j, std::size_t js, int
 {
     return std::size_t( j >> lg_split ) * split_stride + std::size_t( unsigned( j ) & ( ( 1u << lg_split ) - 1u ) ) * js;
 }
-template<bool INVERSE, int LOGN>
+// LG_SEQ: the CTA takes (1 << LG_SEQ) groups of ncol columns, adjacent in memory, loads and stores them together (so that
+// a row of the tile is (ncol << LG_SEQ) x 16 contiguous bytes: for the long transforms, where ncol = 1, a full 32-byte
+// sector instead of half of one) and transforms the groups one after the other, each in its own dense buffer.
+template<bool INVERSE, int LOGN, int LG_SEQ>
 static __global__ void __launch_bounds__( FFT_THREADS, SB_FFT16_MINB ) k_fft_pass16(
     const __grid_constant__ FFTPlan1D plan, const __grid_constant__ PassArgs a, const int lg_ncol, const int lg_in_split,
     const int lg_out_split )
 {
     extern __shared__ double2 smem[];
-    const int ncol = 1 << lg_ncol;
-    const int o = blockIdx.y, u0 = blockIdx.x << lg_ncol;
-    const int col = threadIdx.x & ( ncol - 1 ), j0 = threadIdx.x >> lg_ncol, jstep = blockDim.x >> lg_ncol;
-    const bool valid   = u0 + col < a.n_u;
-    const double2 * in = a.in + std::size_t( o ) * a.in_os + u0 + col;
-    // exactly FFT_E elements per thread (blockDim = (n / FFT_E) << lg_ncol): all loads in flight before the first store
-    double2 v[FFT_E];
+    constexpr int NSEQ = 1 << LG_SEQ;
+    const int lg_tile  = lg_ncol + LG_SEQ;                                          // columns of the CTA = 1 << lg_tile
+    const int bufp     = ( ( 1 << LOGN ) << lg_ncol ) + ( ( ( 1 << LOGN ) << lg_ncol ) >> 4 ) + 1; // elements per group buffer
+    const int o = blockIdx.y, u0 = blockIdx.x << lg_tile;
+    const int ctile = threadIdx.x & ( ( 1 << lg_tile ) - 1 ), j0 = threadIdx.x >> lg_tile, jstep = blockDim.x >> lg_tile;
+    const int col   = ctile & ( ( 1 << lg_ncol ) - 1 );
+    double2 * mine  = smem + ( ctile >> lg_ncol ) * bufp; // buffer of this thread's column group (load / store phases)
+    const bool valid   = u0 + ctile < a.n_u;
+    const double2 * in = a.in + std::size_t( o ) * a.in_os + u0 + ctile;
+    // exactly FFT_E * NSEQ elements per thread (blockDim = (n / FFT_E) << lg_ncol): FFT_E loads in flight before their stores
 #pragma unroll
-    for( int k = 0; k < FFT_E; ++k )
+    for( int h = 0; h < NSEQ; ++h )
     {
-        const int j = j0 + k * jstep;
-        v[k]        = make_double2( 0.0, 0.0 );
-        if( valid && j < a.n_in )
-            v[k] = in[pass_offset16( j, a.in_js, lg_in_split, a.in_split_stride )];
-    }
-#pragma unroll
-    for( int k = 0; k < FFT_E; ++k )
-        smem[( ( j0 + k * jstep ) << lg_ncol ) + col] = v[k];
-    __syncthreads();
-    block_fft_ct<INVERSE, LOGN>( plan.twiddle, smem, lg_ncol, col, j0 );
-    if( valid )
-    {
-        double2 * out = a.out + std::size_t( o ) * a.out_os + u0 + col;
+        double2 v[FFT_E];
 #pragma unroll
         for( int k = 0; k < FFT_E; ++k )
+        {
+            const int j = j0 + ( h * FFT_E + k ) * jstep;
+            v[k]        = make_double2( 0.0, 0.0 );
+            if( valid && j < a.n_in )
+                v[k] = in[pass_offset16( j, a.in_js, lg_in_split, a.in_split_stride )];
+        }
+#pragma unroll
+        for( int k = 0; k < FFT_E; ++k )
+            mine[( ( j0 + ( h * FFT_E + k ) * jstep ) << lg_ncol ) + col] = v[k];
+    }
+    __syncthreads();
+#pragma unroll 1
+    for( int g = 0; g < NSEQ; ++g )
+        block_fft_ct<INVERSE, LOGN>(
+            plan.twiddle, smem + g * bufp, lg_ncol, int( threadIdx.x ) & ( ( 1 << lg_ncol ) - 1 ), int( threadIdx.x ) >> lg_ncol );
+    if( valid )
+    {
+        double2 * out = a.out + std::size_t( o ) * a.out_os + u0 + ctile;
+#pragma unroll
+        for( int k = 0; k < FFT_E * NSEQ; ++k )
         {
             const int j = j0 + k * jstep;
             if( j < a.n_out )
             {
-                const double2 w = smem[( j << lg_ncol ) + col];
+                const double2 w = mine[( j << lg_ncol ) + col];
                 out[pass_offset16( j, a.out_js, lg_out_split, a.out_split_stride )] = make_double2( a.scale * w.x, a.scale * w.y );
             }
         }
@@ -1219,6 +1233,7 @@ struct DDIPlan
     {
         bool on = false;
         int lg = 0, threads = 0; // lg(columns or rows per CTA), CTA size
+        int lg_seq = 0;          // b-pass: lg(column groups a CTA transforms one after the other)
         std::size_t smem = 0;
     } fast_a, fast_b, fast_c;
     FFTPlan1D plan_ah;             // length Pa / 2
@@ -1339,10 +1354,14 @@ void launch_pass16(
     {
 #define C( L )                                                                                                         \
     case L:                                                                                                            \
-        if( configure )                                                                                                \
-            allow_smem( k_fft_pass16<INVERSE, L>, f.smem );                                                            \
+        if( configure && f.lg_seq )                                                                                    \
+            allow_smem( k_fft_pass16<INVERSE, L, 1>, f.smem );                                                         \
+        else if( configure )                                                                                           \
+            allow_smem( k_fft_pass16<INVERSE, L, 0>, f.smem );                                                         \
+        else if( f.lg_seq )                                                                                            \
+            k_fft_pass16<INVERSE, L, 1><<<grid, f.threads, f.smem, stream>>>( plan, a, f.lg, lg_in, lg_out );          \
         else                                                                                                           \
-            k_fft_pass16<INVERSE, L><<<grid, f.threads, f.smem, stream>>>( plan, a, f.lg, lg_in, lg_out );             \
+            k_fft_pass16<INVERSE, L, 0><<<grid, f.threads, f.smem, stream>>>( plan, a, f.lg, lg_in, lg_out );          \
         break;
         SB_FOR_LOGN( C )
 #undef C
@@ -1521,6 +1540,17 @@ DDIPlan * ddi_plan_create( const Hamiltonian & ham, const StencilParams & sp, cu
         if( allow && plan->plan[1].fast16 && pow2_world )
         {
             shape( plan->fast_b, d.Pb, 1, "SPIRIT_B200_FFT_LG_B" );
+            // two column groups per CTA, loaded / stored together and transformed in turn: rows of the tile twice as long (a
+            // whole sector where a CTA holds one column, lengths >= 2048; a whole 128-byte line at 512). Measured: profiles/r1y
+            plan->fast_b.lg_seq = 1;
+            if( const char * v = std::getenv( "SPIRIT_B200_FFT_SEQ_B" ) )
+                plan->fast_b.lg_seq = std::atoi( v ) ? 1 : 0;
+            if( plan->fast_b.lg_seq )
+            {
+                plan->fast_b.smem *= 2;
+                if( plan->fast_b.smem > std::size_t( 220 * 1024 ) )
+                    plan->fast_b.lg_seq = 0, plan->fast_b.smem /= 2;
+            }
             if( world > 1 )
                 plan->lg_split = 31 - __builtin_clz( unsigned( kbl ) );
         }
@@ -1770,7 +1800,8 @@ int ddi_gradient_pipelined( DDIPlan & plan, ConstField3 spins, Field3 g_ddi, cud
     cudaStream_t cs                  = plan.comm_stream;
     const std::size_t comp_elems     = dc.q_stride; // one component inside a per-rank block: ncl * kbl * Ha
     const dim3 grid_a( ( rows + ( 1 << plan.fast_a.lg ) - 1 ) >> plan.fast_a.lg, 1 );
-    const dim3 grid_b( ( d.Ha + ( 1 << plan.fast_b.lg ) - 1 ) >> plan.fast_b.lg, ncl );
+    const int lg_tile_b = plan.fast_b.lg + plan.fast_b.lg_seq;
+    const dim3 grid_b( ( d.Ha + ( 1 << lg_tile_b ) - 1 ) >> lg_tile_b, ncl );
     auto all_to_all = [&]( const double2 * from, double2 * to, int q )
     {
         comm_group_begin();
@@ -1856,7 +1887,8 @@ int ddi_gradient( DDIPlan & plan, ConstField3 spins, Field3 g_ddi, cudaStream_t 
         pb.out_os = std::size_t( d.Pb ) * d.Ha;
     pb.n_u = d.Ha, pb.n_o = nq * d.Nc, pb.n_in = d.Nb, pb.n_out = d.Pb, pb.ncol = plan.ncol_b, pb.scale = 1.0;
     const dim3 grid_b( ( d.Ha + plan.ncol_b - 1 ) / plan.ncol_b, pb.n_o );
-    const dim3 grid_b16( ( d.Ha + ( 1 << plan.fast_b.lg ) - 1 ) >> plan.fast_b.lg, pb.n_o );
+    const int lg_tile_b = plan.fast_b.lg + plan.fast_b.lg_seq;
+    const dim3 grid_b16( ( d.Ha + ( 1 << lg_tile_b ) - 1 ) >> lg_tile_b, pb.n_o );
     if( plan.fast_b.on )
         launch_pass16<false>( plan.fast_b, grid_b16, stream, plan.plan[1], pb, 31, plan.lg_split );
     else
