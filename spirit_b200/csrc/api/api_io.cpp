@@ -1,0 +1,282 @@
+// Spirit/IO.h: spin configurations and chains as OVF 2.0 files (core/src/Spirit/IO.cpp:86-860). The configurations are
+// the host copies the API works on between simulations; nothing here touches the device.
+#include "api_common.hpp"
+
+#include "../core/ovf.hpp"
+
+#include <Spirit/Chain.h>
+#include <Spirit/IO.h>
+#include <Spirit/State.h>
+#include <Spirit/Version.h>
+
+#include <algorithm>
+#include <string>
+
+using namespace sb;
+
+namespace
+{
+// Header values of a spin system (OVF_File.cpp:14-43): the basis atoms are folded into the x axis, lengths in nm
+ovf::Segment segment_of( const Spin_System & system )
+{
+    const Geometry & g = *system.geometry;
+    ovf::Segment seg;
+    seg.meshtype   = "rectangular";
+    seg.meshunit   = "nm";
+    seg.n_cells[0] = g.n_cells[0] * g.n_cell_atoms;
+    seg.n_cells[1] = g.n_cells[1];
+    seg.n_cells[2] = g.n_cells[2];
+    seg.N          = system.nos;
+    for( int i = 0; i < 3; ++i )
+    {
+        seg.bounds_min[i] = g.bounds_min[i] * 0.1;
+        seg.bounds_max[i] = g.bounds_max[i] * 0.1;
+        seg.origin[i]     = 0;
+        seg.step_size[i]  = g.lattice_constant * g.bravais_vectors[i][i] * 0.1;
+    }
+    return seg;
+}
+ovf::Segment spin_segment( const Spin_System & system, const std::string & comment )
+{
+    ovf::Segment seg = segment_of( system );
+    seg.title        = std::string( "SPIRIT Version " ) + Spirit_Version_Full();
+    seg.comment      = comment;
+    seg.valuedim     = 3;
+    seg.valuelabels  = "spin_x spin_y spin_z";
+    seg.valueunits   = "none none none";
+    return seg;
+}
+void check_format( int format )
+{
+    if( format < ovf::BIN || format > ovf::CSV )
+        throw std::runtime_error( "Invalid file format index " + std::to_string( format ) );
+}
+void warn_extension( const char * file, int idx_image, int idx_chain )
+{
+    const std::string name( file );
+    const std::size_t dot = name.rfind( '.' );
+    if( dot == std::string::npos || name.substr( dot ) != ".ovf" )
+        Log( Log_Level::Warning, Log_Sender::API,
+             "The file \"" + name + "\" is written in OVF format but has different extension. It is recommend to use the appropriate \".ovf\" extension",
+             idx_image, idx_chain );
+}
+// One segment of `file` into the spins of `image` (IO.cpp:224-277): at most nos rows, 3 columns, then every spin is
+// normalised; (near-)zero vectors become +z (vacancies of a defect build)
+void read_spins( const ovf::File & file, int idx_in_file, Spin_System & image, int idx_image, int idx_chain )
+{
+    ovf::Segment seg = file.read_segment_header( idx_in_file );
+    if( seg.N < image.nos )
+        Log( Log_Level::Warning, Log_Sender::API,
+             "OVF file \"" + file.name + "\": segment " + std::to_string( idx_in_file + 1 ) + "/" + std::to_string( file.n_segments ) + " contains only "
+                 + std::to_string( seg.N ) + " spins while the system contains " + std::to_string( image.nos ) + ".",
+             idx_image, idx_chain );
+    else if( seg.N > image.nos )
+        Log( Log_Level::Warning, Log_Sender::API,
+             "OVF file \"" + file.name + "\": segment " + std::to_string( idx_in_file + 1 ) + "/" + std::to_string( file.n_segments ) + " contains "
+                 + std::to_string( seg.N ) + " spins while the system contains only " + std::to_string( image.nos )
+                 + ". Reading only part of the segment data.",
+             idx_image, idx_chain );
+    if( seg.valuedim != 3 )
+        throw std::runtime_error(
+            "Segment " + std::to_string( idx_in_file + 1 ) + "/" + std::to_string( file.n_segments ) + " in OVF file \"" + file.name
+            + "\" should have 3 columns, but only has " + std::to_string( seg.valuedim ) + ". Will not read." );
+    static_assert( sizeof( Vec3 ) == 3 * sizeof( double ), "spins are packed triples of doubles" );
+    file.read_segment_data( idx_in_file, seg, std::min( seg.N, image.nos ), &image.spins[0].x );
+    for( int i = 0; i < image.nos; ++i )
+    {
+        Vec3 & s = image.spins[i];
+        if( s.norm() < 1e-5 )
+            s = Vec3{ 0, 0, 1 };
+        else
+            s.normalize();
+    }
+}
+} // namespace
+
+int IO_N_Images_In_File( State *, const char * file, int idx_image, int idx_chain ) noexcept
+try
+{
+    ovf::File f( file );
+    if( f.is_ovf )
+        return f.n_segments;
+    Log( Log_Level::Warning, Log_Sender::API, std::string( "File \"" ) + file + "\" is not OVF. Cannot measure number of images.", idx_image, idx_chain );
+    return -1;
+}
+SB_API_CATCH_RET( -1 )
+
+void IO_Positions_Write( State * state, const char * file, int format, const char * comment, int idx_image, int idx_chain ) noexcept
+try
+{
+    auto image = resolve( state, idx_image, idx_chain ).image;
+    ImageLock lock( *image );
+    check_format( format );
+    warn_extension( file, idx_image, idx_chain );
+    ovf::Segment seg = segment_of( *image );
+    seg.title        = std::string( "SPIRIT Version " ) + Spirit_Version_Full();
+    seg.comment      = comment;
+    seg.valuedim     = 3;
+    seg.valuelabels  = "position_x position_y position_z";
+    seg.valueunits   = "none none none";
+    ovf::File( file ).write_segment( seg, &image->geometry->positions()[0].x, format );
+    Log( Log_Level::Info, Log_Sender::API, std::string( "Wrote positions to file \"" ) + file + "\"", idx_image, idx_chain );
+}
+SB_API_CATCH_VOID
+
+void IO_Image_Read( State * state, const char * file, int idx_image_infile, int idx_image, int idx_chain ) noexcept
+try
+{
+    auto image = resolve( state, idx_image, idx_chain ).image;
+    ImageLock lock( *image );
+    ovf::File f( file );
+    if( !f.found )
+        throw std::runtime_error( std::string( "Unable open file \"" ) + file + "\", are you sure it exists?" );
+    if( !f.is_ovf )
+        throw std::runtime_error( std::string( "File \"" ) + file + "\" does not seem to be in valid OVF format. Message: " + f.message );
+    read_spins( f, idx_image_infile, *image, idx_image, idx_chain );
+    Log( Log_Level::Info, Log_Sender::API, std::string( "Read image from file \"" ) + file + "\"", idx_image, idx_chain );
+}
+SB_API_CATCH_VOID
+
+void IO_Image_Write( State * state, const char * file, int format, const char * comment, int idx_image, int idx_chain ) noexcept
+try
+{
+    auto image = resolve( state, idx_image, idx_chain ).image;
+    ImageLock lock( *image );
+    check_format( format );
+    warn_extension( file, idx_image, idx_chain );
+    ovf::File( file ).write_segment( spin_segment( *image, comment ), &image->spins[0].x, format );
+    Log( Log_Level::Info, Log_Sender::API, std::string( "Wrote spins to file \"" ) + file + "\"", idx_image, idx_chain );
+}
+SB_API_CATCH_VOID
+
+void IO_Image_Append( State * state, const char * file, int format, const char * comment, int idx_image, int idx_chain ) noexcept
+try
+{
+    auto image = resolve( state, idx_image, idx_chain ).image;
+    ImageLock lock( *image );
+    check_format( format );
+    warn_extension( file, idx_image, idx_chain );
+    ovf::File( file ).append_segment( spin_segment( *image, comment ), &image->spins[0].x, format );
+    Log( Log_Level::Info, Log_Sender::API, std::string( "Appended spins to file \"" ) + file + "\"", idx_image, idx_chain );
+}
+SB_API_CATCH_VOID
+
+void IO_Chain_Read( State * state, const char * file, int start_image_infile, int end_image_infile, int insert_idx, int idx_chain ) noexcept
+{
+    int idx_image = insert_idx;
+    try
+    {
+        auto chain = resolve( state, idx_image, idx_chain ).chain;
+        int noi    = chain->noi;
+        if( insert_idx < 0 )
+            insert_idx = 0;
+        if( insert_idx > noi )
+            Log( Log_Level::Error, Log_Sender::API,
+                 "IO_Chain_Read: Tried to start reading chain on invalid index(insert_idx=" + std::to_string( insert_idx ) + ", but chain has "
+                     + std::to_string( noi ) + " images)",
+                 insert_idx, idx_chain );
+        ovf::File f( file );
+        if( !f.found )
+            throw std::runtime_error( std::string( "Unable open file \"" ) + file + "\", are you sure it exists?" );
+        if( !f.is_ovf )
+            throw std::runtime_error( std::string( "IO_Chain_Read: File \"" ) + file + "\" is not OVF. Message: " + f.message );
+        const int noi_infile = f.n_segments;
+        if( start_image_infile < 0 )
+            start_image_infile = 0;
+        if( end_image_infile < 0 )
+            end_image_infile = noi_infile - 1;
+        if( end_image_infile < start_image_infile || end_image_infile >= noi_infile )
+        {
+            Log( Log_Level::Warning, Log_Sender::API,
+                 "IO_Chain_Read: specified invalid reading range (start_image_infile=" + std::to_string( start_image_infile )
+                     + ", end_image_infile=" + std::to_string( end_image_infile ) + "). Set to read entire file \"" + file + "\" ("
+                     + std::to_string( noi_infile ) + " images).",
+                 insert_idx, idx_chain );
+            end_image_infile = noi_infile - 1;
+        }
+        if( start_image_infile >= noi_infile )
+            throw std::runtime_error(
+                "Specified starting index " + std::to_string( start_image_infile ) + ", but file \"" + file + "\" contains only "
+                + std::to_string( noi_infile ) + " images." );
+        const int noi_to_read = end_image_infile - start_image_infile + 1;
+        const int noi_to_add  = noi_to_read - ( noi - insert_idx );
+        if( noi_to_add > 0 )
+        {
+            // the chain grows by copies of its last image (IO.cpp:514-520)
+            Chain_Image_to_Clipboard( state, noi - 1, idx_chain );
+            Chain_Set_Length( state, noi + noi_to_add, idx_chain );
+        }
+        {
+            chain->Lock();
+            try
+            {
+                // (the reference's loop bounds, IO.cpp:523: images insert_idx .. noi_to_read - 1)
+                for( int i = insert_idx; i < noi_to_read; ++i )
+                    read_spins( f, start_image_infile++, *chain->images[i], i, idx_chain );
+            }
+            catch( ... )
+            {
+                chain->Unlock();
+                throw;
+            }
+            chain->Unlock();
+        }
+        Chain_Setup_Data( state, idx_chain );
+        Log( Log_Level::Info, Log_Sender::API, std::string( "Read chain from file \"" ) + file + "\"", insert_idx, idx_chain );
+    }
+    catch( ... )
+    {
+        sb::handle_exception_api( __func__, idx_image, idx_chain );
+    }
+}
+
+namespace
+{
+void chain_to_file( State * state, const char * file, int format, const char * comment, int idx_chain, bool append )
+{
+    int idx_image = 0;
+    auto chain    = resolve( state, idx_image, idx_chain ).chain;
+    check_format( format );
+    chain->Lock();
+    try
+    {
+        ovf::File f( file );
+        for( int i = 0; i < chain->noi; ++i )
+        {
+            const std::string desc = "Image " + std::to_string( i + 1 ) + " of " + std::to_string( chain->noi ) + ". " + comment;
+            const ovf::Segment seg = spin_segment( *chain->images[i], desc );
+            if( i == 0 && !append )
+                f.write_segment( seg, &chain->images[i]->spins[0].x, format );
+            else
+                f.append_segment( seg, &chain->images[i]->spins[0].x, format );
+        }
+    }
+    catch( ... )
+    {
+        chain->Unlock();
+        throw;
+    }
+    chain->Unlock();
+    Log( Log_Level::Info, Log_Sender::API, std::string( append ? "Appended chain to file \"" : "Wrote chain to file \"" ) + file + "\"", 0, idx_chain );
+}
+} // namespace
+
+void IO_Chain_Write( State * state, const char * file, int format, const char * comment, int idx_chain ) noexcept
+{
+    int idx_image = 0;
+    try
+    {
+        chain_to_file( state, file, format, comment, idx_chain, false );
+    }
+    SB_API_CATCH_VOID
+}
+
+void IO_Chain_Append( State * state, const char * file, int format, const char * comment, int idx_chain ) noexcept
+{
+    int idx_image = 0;
+    try
+    {
+        chain_to_file( state, file, format, comment, idx_chain, true );
+    }
+    SB_API_CATCH_VOID
+}

@@ -252,6 +252,28 @@ class Session:
         self.lib.Parameters_GNEB_Set_Image_Type_Automatically(self.state, -1)
 
     # ---- device (product only) ---------------------------------------------------------------------------------------
+    # ---- OVF files (Spirit/IO.h) ----------------------------------------------------------------------------------------
+    def n_images_in_file(self, path):
+        return self.lib.IO_N_Images_In_File(self.state, str(path).encode(), -1, -1)
+
+    def image_write(self, path, fmt=2, comment="-", idx_image=-1):
+        self.lib.IO_Image_Write(self.state, str(path).encode(), fmt, comment.encode(), idx_image, -1)
+
+    def image_append(self, path, fmt=2, comment="-", idx_image=-1):
+        self.lib.IO_Image_Append(self.state, str(path).encode(), fmt, comment.encode(), idx_image, -1)
+
+    def image_read(self, path, idx_image_infile=0, idx_image=-1):
+        self.lib.IO_Image_Read(self.state, str(path).encode(), idx_image_infile, idx_image, -1)
+
+    def chain_write(self, path, fmt=3, comment="-"):
+        self.lib.IO_Chain_Write(self.state, str(path).encode(), fmt, comment.encode(), -1)
+
+    def chain_append(self, path, fmt=3, comment="-"):
+        self.lib.IO_Chain_Append(self.state, str(path).encode(), fmt, comment.encode(), -1)
+
+    def chain_read(self, path, start=0, end=-1, insert_idx=0):
+        self.lib.IO_Chain_Read(self.state, str(path).encode(), start, end, insert_idx, -1)
+
     def upload(self, idx_image=-1):
         if self.lib.SpiritB200_Upload(self.state, idx_image) < 0:
             raise RuntimeError("SpiritB200_Upload failed (no CUDA device?)")

@@ -1,0 +1,144 @@
+"""OVF files (Spirit/IO.h, SURVEY.md 8f rank 2: the data format either side of the hot path) against the reference's reader
+and writer (its bundled ovf library): what one library writes the other must read back to the same spins, in every format,
+for single images, appended segments and chains. CPU only -- the configurations are the host copies of the API."""
+import numpy as np
+import pytest
+
+from spirit_b200 import session as S
+
+BIN, BIN4, BIN8, TEXT, CSV = 0, 1, 2, 3, 4
+FORMATS = [(BIN, 3e-16), (BIN4, 1e-7), (BIN8, 3e-16), (TEXT, 1e-11), (CSV, 1e-11)]  # (the readers normalise what they read)
+LATTICES = [("solvers", {"n_basis_cells": "7 5 1"}), ("cubic256", {"n_basis_cells": "6 5 4"}), ("ddi", {"ddi_method": "none", "n_basis_cells": "4 3 2"})]
+
+
+def pair(cfg, product, oracle, preset="solvers", **over):
+    path = cfg(preset, **over)
+    return S.Session(product, path), S.Session(oracle, path)
+
+
+@pytest.mark.parametrize("fmt,tol", FORMATS)
+@pytest.mark.parametrize("preset,over", LATTICES)
+def test_image_written_here_is_read_by_the_reference_and_back(cfg, product, oracle, tmp_path, preset, over, fmt, tol):
+    p, o = pair(cfg, product, oracle, preset, **over)
+    p.random()
+    want = p.spins().copy()
+    ours, theirs = tmp_path / "ours.ovf", tmp_path / "theirs.ovf"
+    p.image_write(ours, fmt, "written by spirit_b200")
+    assert p.n_images_in_file(ours) == 1 and o.n_images_in_file(ours) == 1
+    o.plus_z()
+    o.image_read(ours)
+    assert np.abs(o.spins() - want).max() <= tol
+    # the other direction: the reference writes, this library reads
+    o.image_write(theirs, fmt, "written by the reference")
+    written = o.spins().copy()
+    p.plus_z()
+    p.image_read(theirs)
+    assert np.abs(p.spins() - written).max() <= tol
+    # and both readers agree on both files to the last bit
+    for path in (ours, theirs):
+        p.plus_z(), o.plus_z()
+        p.image_read(path), o.image_read(path)
+        assert np.array_equal(p.spins(), o.spins())
+    p.close(), o.close()
+
+
+def test_append_counts_segments_in_files_of_either_library(cfg, product, oracle, tmp_path):
+    p, o = pair(cfg, product, oracle)
+    states = []
+    mixed = tmp_path / "mixed.ovf"
+    for k, (who, fmt) in enumerate([(p, BIN8), (o, TEXT), (p, CSV), (o, BIN4), (p, BIN4), (o, BIN8), (p, TEXT)]):
+        who.random()
+        states.append(who.spins().copy())
+        who.image_append(mixed, fmt, "segment %d" % k)  # the first append creates the file
+        assert p.n_images_in_file(mixed) == k + 1 and o.n_images_in_file(mixed) == k + 1
+    for k, want in enumerate(states):
+        for who in (p, o):
+            who.plus_z()
+            who.image_read(mixed, idx_image_infile=k)
+            assert np.abs(who.spins() - want).max() <= 1e-7
+        assert np.array_equal(p.spins(), o.spins())
+    # an image write replaces the file
+    p.image_write(mixed, BIN8)
+    assert o.n_images_in_file(mixed) == 1
+    p.close(), o.close()
+
+
+@pytest.mark.parametrize("fmt", [TEXT, BIN8])
+def test_chain_files(cfg, product, oracle, tmp_path, fmt):
+    tol = 1e-11 if fmt == TEXT else 3e-16  # 12 decimals in text files; readers normalise what they read (last bit)
+    p, o = pair(cfg, product, oracle)
+    for x in (p, o):
+        x.chain_set_length(4)
+    images = []
+    for i in range(4):
+        p.jump_to_image(i)
+        p.random()
+        images.append(p.spins().copy())
+    ours = tmp_path / "chain.ovf"
+    p.chain_write(ours, fmt, "a chain")
+    assert o.n_images_in_file(ours) == 4
+    o.chain_read(ours)
+    assert o.noi == 4
+    for i in range(4):
+        assert np.abs(o.spins(i) - images[i]).max() <= tol
+    # the reference writes the chain, a one-image state here grows to hold it (IO.cpp:511-520)
+    theirs = tmp_path / "chain_ref.ovf"
+    o.chain_write(theirs, fmt, "reference chain")
+    q = S.Session(product, cfg("solvers"))
+    assert q.noi == 1
+    q.chain_read(theirs)
+    assert q.noi == 4
+    for i in range(4):
+        assert np.abs(q.spins(i) - o.spins(i)).max() <= tol
+    # a sub-range of the file, and appending a chain to a file
+    r, ro = pair(cfg, product, oracle)
+    for x in (r, ro):
+        x.chain_read(theirs, start=1, end=2)
+        assert x.noi == 2
+    for i in range(2):
+        assert np.array_equal(r.spins(i), ro.spins(i)) and np.abs(r.spins(i) - o.spins(i + 1)).max() <= tol
+    p.chain_append(ours, fmt, "again")
+    assert p.n_images_in_file(ours) == 8 and o.n_images_in_file(ours) == 8
+    for x in (p, o, q, r, ro):
+        x.close()
+
+
+def test_reading_a_file_of_another_size_or_shape(cfg, product, oracle, tmp_path):
+    """more / fewer rows than spins: the common part is read (IO.cpp:233-251); the rest keeps its values, all are normalised"""
+    small_p, small_o = pair(cfg, product, oracle, n_basis_cells="4 4 1")
+    big_p, big_o = pair(cfg, product, oracle, n_basis_cells="6 5 1")
+    small_p.random(), big_p.random()
+    f_small, f_big = tmp_path / "small.ovf", tmp_path / "big.ovf"
+    small_p.image_write(f_small, BIN8), big_p.image_write(f_big, TEXT)
+    for a, b, f in ((big_p, big_o, f_small), (small_p, small_o, f_big)):
+        a.plus_z(), b.plus_z()
+        a.image_read(f), b.image_read(f)
+        assert np.array_equal(a.spins(), b.spins())
+        assert np.abs(np.linalg.norm(a.spins(), axis=1) - 1).max() < 1e-15
+    # not an OVF file, a missing file, a segment that does not exist: nothing changes, nothing is thrown
+    junk = tmp_path / "junk.ovf"
+    junk.write_text("1 2 3\n4 5 6\n")
+    before = small_p.spins().copy()
+    assert small_p.n_images_in_file(junk) == -1 and small_o.n_images_in_file(junk) == -1
+    small_p.image_read(tmp_path / "missing.ovf")
+    small_p.image_read(f_small, idx_image_infile=5)
+    assert np.array_equal(small_p.spins(), before)
+    for x in (small_p, small_o, big_p, big_o):
+        x.close()
+
+
+def test_header_of_a_written_file(cfg, product, tmp_path):
+    """the keywords a third-party OVF 2.0 reader needs, with the reference's conventions (basis atoms folded into xnodes, nm)"""
+    p = S.Session(product, cfg("ddi", ddi_method="none", n_basis_cells="4 3 2"))
+    f = tmp_path / "h.ovf"
+    p.image_write(f, TEXT, "a remark")
+    text = f.read_text()
+    lines = [l.strip() for l in text.splitlines()]
+    assert lines[0] == "# OOMMF OVF 2.0" and "# Segment count: 000001" in lines
+    for want in ("# Begin: Segment", "# Begin: Header", "# Desc: a remark", "# valuedim: 3   ## field dimensionality",
+                 "# valueunits: none none none", "# valuelabels: spin_x spin_y spin_z", "# meshunit: nm", "# meshtype: rectangular",
+                 "# xnodes: 8", "# ynodes: 3", "# znodes: 2", "# End: Header", "# Begin: Data Text", "# End: Data Text", "# End: Segment"):
+        assert want in lines, want
+    data = [l for l in text.splitlines() if l and not l.startswith("#")]
+    assert len(data) == p.nos and all(len(l) == 66 for l in data)  # three columns of width 22
+    p.close()
