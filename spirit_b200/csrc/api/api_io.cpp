@@ -2,6 +2,7 @@
 // the host copies the API works on between simulations; nothing here touches the device.
 #include "api_common.hpp"
 
+#include "../core/io.hpp"
 #include "../core/ovf.hpp"
 
 #include <Spirit/Chain.h>
@@ -16,36 +17,8 @@ using namespace sb;
 
 namespace
 {
-// Header values of a spin system (OVF_File.cpp:14-43): the basis atoms are folded into the x axis, lengths in nm
-ovf::Segment segment_of( const Spin_System & system )
-{
-    const Geometry & g = *system.geometry;
-    ovf::Segment seg;
-    seg.meshtype   = "rectangular";
-    seg.meshunit   = "nm";
-    seg.n_cells[0] = g.n_cells[0] * g.n_cell_atoms;
-    seg.n_cells[1] = g.n_cells[1];
-    seg.n_cells[2] = g.n_cells[2];
-    seg.N          = system.nos;
-    for( int i = 0; i < 3; ++i )
-    {
-        seg.bounds_min[i] = g.bounds_min[i] * 0.1;
-        seg.bounds_max[i] = g.bounds_max[i] * 0.1;
-        seg.origin[i]     = 0;
-        seg.step_size[i]  = g.lattice_constant * g.bravais_vectors[i][i] * 0.1;
-    }
-    return seg;
-}
-ovf::Segment spin_segment( const Spin_System & system, const std::string & comment )
-{
-    ovf::Segment seg = segment_of( system );
-    seg.title        = std::string( "SPIRIT Version " ) + Spirit_Version_Full();
-    seg.comment      = comment;
-    seg.valuedim     = 3;
-    seg.valuelabels  = "spin_x spin_y spin_z";
-    seg.valueunits   = "none none none";
-    return seg;
-}
+using sb::io::segment_of;
+using sb::io::spin_segment;
 void check_format( int format )
 {
     if( format < ovf::BIN || format > ovf::CSV )
@@ -112,7 +85,7 @@ try
     check_format( format );
     warn_extension( file, idx_image, idx_chain );
     ovf::Segment seg = segment_of( *image );
-    seg.title        = std::string( "SPIRIT Version " ) + Spirit_Version_Full();
+    seg.title        = std::string( "SPIRIT Version " ) + io::version_full();
     seg.comment      = comment;
     seg.valuedim     = 3;
     seg.valuelabels  = "position_x position_y position_z";

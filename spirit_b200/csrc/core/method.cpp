@@ -1,4 +1,7 @@
 #include "method.hpp"
+
+#include "io.hpp"
+#include "ovf.hpp"
 #include "constants.hpp"
 #include "logging.hpp"
 
@@ -26,10 +29,12 @@ Method::Method( std::shared_ptr<Parameters_Method> parameters_, int idx_image_, 
     for( int i = 0; i < 7; ++i )
         t_iterations.push_back( std::chrono::system_clock::now() );
     t_start = t_last = std::chrono::system_clock::now();
+    starttime        = io::current_date_time();
 }
 
 void Method::Iterate()
 {
+    starttime = io::current_date_time();
     t_start = t_last = std::chrono::system_clock::now();
     auto t_current   = t_start;
 
@@ -297,12 +302,143 @@ void Method_LLG::Finalize()
     system->iteration_allowed = false;
 }
 
-void Method_LLG::Save_Current( bool, bool )
+namespace
 {
-    // Method_LLG.cpp:312-315 (history); file output is not written
+// fmt's "{:^20}": centred in `width` columns, the odd blank goes to the right
+std::string centred( const std::string & text, std::size_t width = 20 )
+{
+    if( text.size() >= width )
+        return text;
+    const std::size_t left = ( width - text.size() ) / 2;
+    return std::string( left, ' ' ) + text + std::string( width - text.size() - left, ' ' );
+}
+std::string fixed10( double v )
+{
+    char buf[64];
+    std::snprintf( buf, sizeof( buf ), "%.10f", v );
+    return buf;
+}
+std::string shortest( double v )
+{
+    char buf[64];
+    for( int prec = 1; prec <= 17; ++prec )
+    {
+        std::snprintf( buf, sizeof( buf ), "%.*g", prec, v );
+        if( std::strtod( buf, nullptr ) == v )
+            break;
+    }
+    return buf;
+}
+// Energy tables of one image (Datawriter.cpp:116-184): a header line with centred column titles and one line per call
+void write_energy_header( const Spin_System & s, const std::string & file, bool readability )
+{
+    std::string separator, line;
+    for( const char * column : { "iteration", "E_tot" } )
+    {
+        if( readability )
+            separator += "----------------------++";
+        line += " " + centred( column ) + " ||";
+    }
+    bool first = true;
+    for( const auto & pair : s.E_array )
+    {
+        if( !first )
+        {
+            line += "|";
+            if( readability )
+                separator += "+";
+        }
+        first = false;
+        line += " " + centred( pair.first ) + " ";
+        if( readability )
+            separator += "----------------------";
+    }
+    line += "\n";
+    separator += "\n";
+    std::string header = readability ? separator + line + separator : line;
+    if( !readability )
+        std::replace( header.begin(), header.end(), '|', ' ' );
+    std::ofstream( file, std::ios::trunc ) << header;
+}
+void append_image_energy( const Spin_System & s, long iteration, const std::string & file, bool normalize, bool readability )
+{
+    const double norm = normalize ? 1.0 / double( s.nos ) : 1.0;
+    std::string line   = " " + centred( std::to_string( iteration ) ) + " || " + centred( fixed10( s.E * norm ) ) + " |";
+    for( const auto & pair : s.E_array )
+        line += "| " + centred( fixed10( pair.second * norm ) ) + " ";
+    line += "\n";
+    if( !readability )
+        std::replace( line.begin(), line.end(), '|', ' ' );
+    std::ofstream( file, std::ios::app ) << line;
+}
+} // namespace
+
+// Method_LLG.cpp:310-500: the histories, and -- with llg_output_any -- the files of the reference: spins at the start, at the
+// end, per log step and as an appended archive (OVF, format llg_output_vf_filetype), energy tables next to them. The spins
+// are the host copies (Sync_Host precedes every call). Per-spin energy files (llg_output_energy_spin_resolved) are not written.
+void Method_LLG::Save_Current( bool initial, bool final )
+{
     history_iteration.push_back( int( iteration ) );
     history_max_torque.push_back( max_torque );
     history_energy.push_back( system->E );
+
+    const Parameters_LLG & P = *system->llg_parameters;
+    if( !P.output_any )
+        return;
+    char s_img[16];
+    std::snprintf( s_img, sizeof( s_img ), "%02d", idx_image );
+    const int width = P.n_iterations > 0 ? int( std::log10( double( P.n_iterations ) ) ) : 0;
+    char s_iter[32];
+    std::snprintf( s_iter, sizeof( s_iter ), "%0*ld", width, iteration );
+    const std::string tag    = P.output_file_tag == "<time>" ? starttime + "_" : ( P.output_file_tag.empty() ? "" : P.output_file_tag + "_" );
+    const std::string spins  = P.output_folder + "/" + tag + "Image-" + s_img + "_Spins";
+    const std::string energy = P.output_folder + "/" + tag + "Image-" + s_img + "_Energy";
+
+    auto write_configuration = [&]( const std::string & suffix, bool append )
+    {
+        try
+        {
+            ovf::Segment seg = io::spin_segment(
+                *system, "LLG simulation (" + SolverFullName() + " solver)\n# Desc:      Iteration: " + std::to_string( iteration )
+                             + "\n# Desc:      Maximum torque: " + shortest( max_torque ) );
+            ovf::File file( spins + suffix + ".ovf" );
+            if( append )
+                file.append_segment( seg, system->spins.scalars(), P.output_vf_filetype );
+            else
+                file.write_segment( seg, system->spins.scalars(), P.output_vf_filetype );
+        }
+        catch( const std::exception & e )
+        {
+            Log( Log_Level::Error, Log_Sender::LLG, std::string( "LLG output failed: " ) + e.what(), idx_image, idx_chain );
+        }
+    };
+    auto write_energy = [&]( const std::string & suffix, bool append )
+    {
+        const std::string file = energy + suffix + ".txt";
+        if( !append || !std::ifstream( file ).good() )
+            write_energy_header( *system, file, P.output_energy_add_readability_lines );
+        append_image_energy( *system, iteration, file, P.output_energy_divide_by_nspins, P.output_energy_add_readability_lines );
+        if( !append && P.output_energy_spin_resolved )
+            Log( Log_Level::Warning, Log_Sender::LLG, "llg_output_energy_spin_resolved: per-spin energy files are not written", idx_image, idx_chain );
+    };
+    if( initial && P.output_initial )
+    {
+        write_configuration( "-initial", false );
+        write_energy( "-initial", false );
+    }
+    else if( final && P.output_final )
+    {
+        write_configuration( "-final", false );
+        write_energy( "-final", false );
+    }
+    if( P.output_configuration_step )
+        write_configuration( std::string( "_" ) + s_iter, false );
+    if( P.output_energy_step )
+        write_energy( std::string( "_" ) + s_iter, false );
+    if( P.output_configuration_archive )
+        write_configuration( "-archive", true );
+    if( P.output_energy_archive )
+        write_energy( "-archive", true );
 }
 
 void Method_LLG::Sync_Host()

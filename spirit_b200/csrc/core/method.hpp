@@ -1,8 +1,8 @@
 // Iterative methods: the outer loop of Engine::Method (core/src/engine/Method.cpp:57-113) and the LLG
 // and GNEB methods. The host keeps the control flow (stop criteria, amortisation, hooks, histories);
 // every Iteration() is a handful of fused kernel launches on the image's stream
-// (device/kernels.cuh). File output (Save_Current's OVF / energy tables) is not part of the hot path
-// and is not written; the histories it maintains are.
+// (device/kernels.cuh). Save_Current keeps the histories and, for LLG with llg_output_any, writes the reference's
+// spin (OVF) and energy files from the host copies at the log steps.
 #pragma once
 
 #include "state.hpp"
@@ -57,6 +57,7 @@ public:
     long iteration = 0, step = 0;
     long n_iterations = 0, n_iterations_log = 0, n_iterations_amortize = 1, n_log = 0;
     int idx_image, idx_chain;
+    std::string starttime; // tag of output file names (llg_output_file_tag <time>)
     double max_torque = 0;
     std::shared_ptr<Parameters_Method> parameters;
     std::vector<int> history_iteration;

@@ -142,3 +142,44 @@ def test_header_of_a_written_file(cfg, product, tmp_path):
     data = [l for l in text.splitlines() if l and not l.startswith("#")]
     assert len(data) == p.nos and all(len(l) == 66 for l in data)  # three columns of width 22
     p.close()
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("solver", [S.SOLVER_DEPONDT, S.SOLVER_VP])
+def test_llg_output_files_match_the_reference(cfg, product, oracle, tmp_path, solver):
+    """llg_output_*: same file names, spins within the single-step tolerance, same energy tables (Method_LLG.cpp:310-500)"""
+    import os
+    folders = {}
+    for name, lib in (("product", product), ("oracle", oracle)):
+        out = tmp_path / name
+        out.mkdir()
+        folders[name] = out
+        path = cfg("solvers", llg_output_any=1, llg_output_initial=1, llg_output_final=1, llg_output_configuration_step=1,
+                   llg_output_configuration_archive=1, llg_output_energy_step=1, llg_output_energy_archive=1,
+                   llg_output_energy_divide_by_nspins=0, llg_output_configuration_filetype=3, llg_output_folder=str(out),
+                   output_file_tag="run", llg_n_iterations=40, llg_n_iterations_log=10, llg_force_convergence="1e-14")
+        x = S.Session(lib, path, quiet=False)  # (a quiet state writes no files, State.cpp:60-75)
+        x.plus_z()
+        x.skyrmion(5.0, phase=-90.0)
+        x.llg_start(solver, n_iterations=40, n_iterations_log=10)
+        x.close()
+    names = {k: sorted(os.listdir(v)) for k, v in folders.items()}
+    assert names["product"] == names["oracle"] and len(names["product"]) >= 12, names
+    reader_p, reader_o = S.Session(product, cfg("solvers")), S.Session(oracle, cfg("solvers"))
+    for f in names["product"]:
+        fp, fo = folders["product"] / f, folders["oracle"] / f
+        if f.endswith(".ovf"):
+            n = reader_o.n_images_in_file(fo)
+            assert reader_p.n_images_in_file(fp) == n and reader_o.n_images_in_file(fp) == n
+            for k in range(n):
+                reader_p.image_read(fp, k), reader_o.image_read(fo, k)
+                assert np.abs(reader_p.spins() - reader_o.spins()).max() < 1e-9, (f, k)
+        else:
+            tp, to = fp.read_text().splitlines(), fo.read_text().splitlines()
+            assert len(tp) == len(to) and len(tp) >= 2, f
+            assert tp[0].split() == to[0].split(), f  # column titles
+            for lp, lo in zip(tp[1:], to[1:]):
+                vp, vo = [float(v) for v in lp.split()], [float(v) for v in lo.split()]
+                assert vp[0] == vo[0] and abs(vp[1] - vo[1]) <= 1e-8 * max(1.0, abs(vo[1])), (f, lp, lo)  # iteration, E_tot
+                assert len(vp) == len(vo)
+    reader_p.close(), reader_o.close()
