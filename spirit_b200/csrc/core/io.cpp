@@ -1,7 +1,11 @@
 #include "io.hpp"
 
+#include <algorithm>
 #include <chrono>
+#include <cstdio>
+#include <cstdlib>
 #include <ctime>
+#include <fstream>
 
 namespace sb
 {
@@ -47,6 +51,92 @@ std::string current_date_time()
     char buf[64];
     std::strftime( buf, sizeof( buf ), "%Y-%m-%d_%H-%M-%S", &parts );
     return buf;
+}
+
+std::string centred( const std::string & text, std::size_t width )
+{
+    if( text.size() >= width )
+        return text;
+    const std::size_t left = ( width - text.size() ) / 2;
+    return std::string( left, ' ' ) + text + std::string( width - text.size() - left, ' ' );
+}
+std::string fixed10( double v )
+{
+    char buf[64];
+    std::snprintf( buf, sizeof( buf ), "%.10f", v );
+    return buf;
+}
+std::string shortest( double v )
+{
+    char buf[64];
+    for( int prec = 1; prec <= 17; ++prec )
+    {
+        std::snprintf( buf, sizeof( buf ), "%.*g", prec, v );
+        if( std::strtod( buf, nullptr ) == v )
+            break;
+    }
+    return buf;
+}
+
+void write_energy_header( const Spin_System & s, const std::string & file, const std::vector<std::string> & columns, bool readability )
+{
+    std::string separator, line;
+    for( const auto & column : columns )
+    {
+        if( readability )
+            separator += "----------------------++";
+        line += " " + centred( column ) + " ||";
+    }
+    bool first = true;
+    for( const auto & pair : s.E_array )
+    {
+        if( !first )
+        {
+            line += "|";
+            if( readability )
+                separator += "+";
+        }
+        first = false;
+        line += " " + centred( pair.first ) + " ";
+        if( readability )
+            separator += "----------------------";
+    }
+    line += "\n";
+    separator += "\n";
+    std::string header = readability ? separator + line + separator : line;
+    if( !readability )
+        std::replace( header.begin(), header.end(), '|', ' ' );
+    std::ofstream( file, std::ios::trunc ) << header;
+}
+
+void append_image_energy( const Spin_System & s, long iteration, const std::string & file, bool normalize, bool readability )
+{
+    const double norm = normalize ? 1.0 / double( s.nos ) : 1.0;
+    std::string line   = " " + centred( std::to_string( iteration ) ) + " || " + centred( fixed10( s.E * norm ) ) + " |";
+    for( const auto & pair : s.E_array )
+        line += "| " + centred( fixed10( pair.second * norm ) ) + " ";
+    line += "\n";
+    if( !readability )
+        std::replace( line.begin(), line.end(), '|', ' ' );
+    std::ofstream( file, std::ios::app ) << line;
+}
+
+void write_chain_energies( const Chain & chain, const std::string & file, bool normalize, bool readability )
+{
+    const double norm = normalize ? 1.0 / double( chain.images[0]->nos ) : 1.0;
+    write_energy_header( *chain.images[0], file, { "image", "Rx", "E_tot" }, true );
+    std::ofstream out( file, std::ios::app );
+    for( int i = 0; i < chain.noi; ++i )
+    {
+        const Spin_System & s = *chain.images[i];
+        std::string line = " " + centred( std::to_string( i ) ) + " || " + centred( fixed10( chain.Rx[i] ) ) + " || " + centred( fixed10( s.E * norm ) ) + " |";
+        for( const auto & pair : s.E_array )
+            line += "| " + centred( fixed10( pair.second * norm ) ) + " ";
+        line += "\n";
+        if( !readability )
+            std::replace( line.begin(), line.end(), '|', ' ' );
+        out << line;
+    }
 }
 
 } // namespace io

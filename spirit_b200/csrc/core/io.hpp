@@ -6,6 +6,7 @@
 #include "state.hpp"
 
 #include <string>
+#include <vector>
 
 namespace sb
 {
@@ -22,6 +23,16 @@ ovf::Segment segment_of( const Spin_System & system );
 ovf::Segment spin_segment( const Spin_System & system, const std::string & comment );
 // "%Y-%m-%d_%H-%M-%S" of now (local time)
 std::string current_date_time();
+
+// Energy tables (core/src/io/Datawriter.cpp:116-234): fmt's "{:^20}" / "{:^20.10f}" columns
+std::string centred( const std::string & text, std::size_t width = 20 );
+std::string fixed10( double v );
+std::string shortest( double v ); // shortest decimal string that reads back exactly (fmt's "{}")
+// header line: the given first columns, then one column per energy contribution of `s`
+void write_energy_header( const Spin_System & s, const std::string & file, const std::vector<std::string> & columns, bool readability );
+void append_image_energy( const Spin_System & s, long iteration, const std::string & file, bool normalize, bool readability );
+// one line per image: image, Rx, E_tot, contributions (the header always carries the separator lines, as in the reference)
+void write_chain_energies( const Chain & chain, const std::string & file, bool normalize, bool readability );
 
 } // namespace io
 } // namespace sb

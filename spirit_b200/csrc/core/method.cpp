@@ -302,77 +302,6 @@ void Method_LLG::Finalize()
     system->iteration_allowed = false;
 }
 
-namespace
-{
-// fmt's "{:^20}": centred in `width` columns, the odd blank goes to the right
-std::string centred( const std::string & text, std::size_t width = 20 )
-{
-    if( text.size() >= width )
-        return text;
-    const std::size_t left = ( width - text.size() ) / 2;
-    return std::string( left, ' ' ) + text + std::string( width - text.size() - left, ' ' );
-}
-std::string fixed10( double v )
-{
-    char buf[64];
-    std::snprintf( buf, sizeof( buf ), "%.10f", v );
-    return buf;
-}
-std::string shortest( double v )
-{
-    char buf[64];
-    for( int prec = 1; prec <= 17; ++prec )
-    {
-        std::snprintf( buf, sizeof( buf ), "%.*g", prec, v );
-        if( std::strtod( buf, nullptr ) == v )
-            break;
-    }
-    return buf;
-}
-// Energy tables of one image (Datawriter.cpp:116-184): a header line with centred column titles and one line per call
-void write_energy_header( const Spin_System & s, const std::string & file, bool readability )
-{
-    std::string separator, line;
-    for( const char * column : { "iteration", "E_tot" } )
-    {
-        if( readability )
-            separator += "----------------------++";
-        line += " " + centred( column ) + " ||";
-    }
-    bool first = true;
-    for( const auto & pair : s.E_array )
-    {
-        if( !first )
-        {
-            line += "|";
-            if( readability )
-                separator += "+";
-        }
-        first = false;
-        line += " " + centred( pair.first ) + " ";
-        if( readability )
-            separator += "----------------------";
-    }
-    line += "\n";
-    separator += "\n";
-    std::string header = readability ? separator + line + separator : line;
-    if( !readability )
-        std::replace( header.begin(), header.end(), '|', ' ' );
-    std::ofstream( file, std::ios::trunc ) << header;
-}
-void append_image_energy( const Spin_System & s, long iteration, const std::string & file, bool normalize, bool readability )
-{
-    const double norm = normalize ? 1.0 / double( s.nos ) : 1.0;
-    std::string line   = " " + centred( std::to_string( iteration ) ) + " || " + centred( fixed10( s.E * norm ) ) + " |";
-    for( const auto & pair : s.E_array )
-        line += "| " + centred( fixed10( pair.second * norm ) ) + " ";
-    line += "\n";
-    if( !readability )
-        std::replace( line.begin(), line.end(), '|', ' ' );
-    std::ofstream( file, std::ios::app ) << line;
-}
-} // namespace
-
 // Method_LLG.cpp:310-500: the histories, and -- with llg_output_any -- the files of the reference: spins at the start, at the
 // end, per log step and as an appended archive (OVF, format llg_output_vf_filetype), energy tables next to them. The spins
 // are the host copies (Sync_Host precedes every call). Per-spin energy files (llg_output_energy_spin_resolved) are not written.
@@ -400,7 +329,7 @@ void Method_LLG::Save_Current( bool initial, bool final )
         {
             ovf::Segment seg = io::spin_segment(
                 *system, "LLG simulation (" + SolverFullName() + " solver)\n# Desc:      Iteration: " + std::to_string( iteration )
-                             + "\n# Desc:      Maximum torque: " + shortest( max_torque ) );
+                             + "\n# Desc:      Maximum torque: " + io::shortest( max_torque ) );
             ovf::File file( spins + suffix + ".ovf" );
             if( append )
                 file.append_segment( seg, system->spins.scalars(), P.output_vf_filetype );
@@ -416,8 +345,8 @@ void Method_LLG::Save_Current( bool initial, bool final )
     {
         const std::string file = energy + suffix + ".txt";
         if( !append || !std::ifstream( file ).good() )
-            write_energy_header( *system, file, P.output_energy_add_readability_lines );
-        append_image_energy( *system, iteration, file, P.output_energy_divide_by_nspins, P.output_energy_add_readability_lines );
+            io::write_energy_header( *system, file, { "iteration", "E_tot" }, P.output_energy_add_readability_lines );
+        io::append_image_energy( *system, iteration, file, P.output_energy_divide_by_nspins, P.output_energy_add_readability_lines );
         if( !append && P.output_energy_spin_resolved )
             Log( Log_Level::Warning, Log_Sender::LLG, "llg_output_energy_spin_resolved: per-spin energy files are not written", idx_image, idx_chain );
     };

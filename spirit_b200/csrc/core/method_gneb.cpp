@@ -1,4 +1,7 @@
 #include "method_gneb.hpp"
+
+#include "io.hpp"
+#include "ovf.hpp"
 #include "constants.hpp"
 #include "logging.hpp"
 
@@ -122,11 +125,63 @@ void Method_GNEB::Finalize()
     chain->iteration_allowed = false;
 }
 
-void Method_GNEB::Save_Current( bool, bool )
+// Method_GNEB.cpp:600-715: histories, and with gneb_output_any the chain (one OVF segment per image) and its energy table at
+// the start, at the end and per log step. Interpolated energy tables (gneb_output_energies_interpolated) are not written.
+void Method_GNEB::Save_Current( bool initial, bool final )
 {
     history_iteration.push_back( int( iteration ) );
     history_max_torque.push_back( max_torque );
     history_energy.push_back( chain->images[chain->idx_active_image]->E );
+
+    const Parameters_GNEB & P = *chain->gneb_parameters;
+    if( !P.output_any )
+        return;
+    char s_iter[32];
+    std::snprintf( s_iter, sizeof( s_iter ), "%06ld", iteration );
+    const std::string tag  = P.output_file_tag == "<time>" ? starttime + "_" : ( P.output_file_tag.empty() ? "" : P.output_file_tag + "_" );
+    const std::string pre  = P.output_folder + "/" + tag + "Chain";
+    const std::string base = "GNEB simulation (" + SolverFullName() + " solver)\n# Desc:      Iteration: " + std::to_string( iteration )
+                             + "\n# Desc:      Maximum torque: " + io::shortest( max_torque );
+    auto write_chain = [&]( const std::string & suffix )
+    {
+        try
+        {
+            ovf::File file( pre + suffix + ".ovf" );
+            for( int i = 0; i < chain->noi; ++i )
+            {
+                const ovf::Segment seg = io::spin_segment(
+                    *chain->images[i], base + "\n# Desc: Image " + std::to_string( i ) + " of " + std::to_string( chain->noi ) );
+                if( i == 0 )
+                    file.write_segment( seg, chain->images[i]->spins.scalars(), P.output_vf_filetype );
+                else
+                    file.append_segment( seg, chain->images[i]->spins.scalars(), P.output_vf_filetype );
+            }
+        }
+        catch( const std::exception & e )
+        {
+            Log( Log_Level::Error, Log_Sender::GNEB, std::string( "GNEB output failed: " ) + e.what(), -1, idx_chain );
+        }
+    };
+    auto write_energies = [&]( const std::string & suffix )
+    {
+        io::write_chain_energies( *chain, pre + "_Energies" + suffix + ".txt", P.output_energies_divide_by_nspins, P.output_energies_add_readability_lines );
+        if( P.output_energies_interpolated )
+            Log( Log_Level::Warning, Log_Sender::GNEB, "gneb_output_energies_interpolated: interpolated energy tables are not written", -1, idx_chain );
+    };
+    if( initial && P.output_initial )
+    {
+        write_chain( "-initial" );
+        write_energies( "-initial" );
+    }
+    else if( final && P.output_final )
+    {
+        write_chain( "-final" );
+        write_energies( "-final" );
+    }
+    if( P.output_chain_step )
+        write_chain( std::string( "_" ) + s_iter );
+    if( P.output_energies_step )
+        write_energies( std::string( "_" ) + s_iter );
 }
 
 void Method_GNEB::Sync_Host()

@@ -183,3 +183,41 @@ def test_llg_output_files_match_the_reference(cfg, product, oracle, tmp_path, so
                 assert vp[0] == vo[0] and abs(vp[1] - vo[1]) <= 1e-8 * max(1.0, abs(vo[1])), (f, lp, lo)  # iteration, E_tot
                 assert len(vp) == len(vo)
     reader_p.close(), reader_o.close()
+
+
+@pytest.mark.gpu
+def test_gneb_output_files_match_the_reference(cfg, product, oracle, tmp_path):
+    """gneb_output_*: chain files (one OVF segment per image) and chain energy tables (Method_GNEB.cpp:600-715)"""
+    import os
+    from tests.test_gneb_gpu import make_chain
+    folders = {}
+    for name, lib in (("product", product), ("oracle", oracle)):
+        out = tmp_path / name
+        out.mkdir()
+        folders[name] = out
+        path = cfg("solvers", n_basis_cells="10 10 1", gneb_output_any=1, gneb_output_initial=1, gneb_output_final=1,
+                   gneb_output_chain_step=1, gneb_output_energies_step=1, gneb_output_energies_divide_by_nspins=0,
+                   gneb_output_chain_filetype=3, gneb_output_folder=str(out), output_file_tag="path",
+                   gneb_n_iterations=30, gneb_n_iterations_log=10, gneb_force_convergence="1e-14")
+        x = S.Session(lib, path, quiet=False)
+        make_chain(x, noi=5)
+        x.gneb_start(S.SOLVER_VP, n_iterations=30, n_iterations_log=10)
+        x.close()
+    names = {k: sorted(os.listdir(v)) for k, v in folders.items()}
+    assert names["product"] == names["oracle"] and len(names["product"]) >= 10, names
+    reader_p, reader_o = S.Session(product, cfg("solvers", n_basis_cells="10 10 1")), S.Session(oracle, cfg("solvers", n_basis_cells="10 10 1"))
+    for f in names["product"]:
+        fp, fo = folders["product"] / f, folders["oracle"] / f
+        if f.endswith(".ovf"):
+            assert reader_p.n_images_in_file(fp) == 5 and reader_o.n_images_in_file(fo) == 5 and reader_o.n_images_in_file(fp) == 5
+            for k in range(5):
+                reader_p.image_read(fp, k), reader_o.image_read(fo, k)
+                assert np.abs(reader_p.spins() - reader_o.spins()).max() < 1e-9, (f, k)
+        else:
+            tp, to = fp.read_text().splitlines(), fo.read_text().splitlines()
+            assert len(tp) == len(to) == 3 + 5, f  # separator, titles, separator, one line per image
+            assert tp[0] == to[0] and tp[1].split("|")[:4] == to[1].split("|")[:4], f
+            for lp, lo in zip(tp[3:], to[3:]):
+                vp, vo = [float(v) for v in lp.split()], [float(v) for v in lo.split()]
+                assert vp[0] == vo[0] and abs(vp[1] - vo[1]) <= 1e-8 and abs(vp[2] - vo[2]) <= 1e-8 * max(1.0, abs(vo[2])), (f, lp, lo)
+    reader_p.close(), reader_o.close()
