@@ -134,6 +134,98 @@ try
 }
 SB_API_CATCH_VOID
 
+namespace
+{
+// The cut of the cell parallelogram and the orientation of its two triangles, as the reference's Delaunay triangulation of the
+// (stretched) cell corners gives them (Vectormath.cpp:516-575). Observed on the reference for the degenerate square cell: a-b.
+struct CellTriangulation
+{
+    int diag;       // 0: triangles (a, b, a+b), (a, b, 0); 1: (0, a, a+b), (0, a+b, b)
+    double sign[2]; // z-orientation of the two triangles in that vertex order
+};
+CellTriangulation cell_triangulation( const Geometry & g )
+{
+    if( g.n_cell_atoms != 1 )
+        throw std::runtime_error( "the topological charge is implemented for lattices with one basis atom" );
+    const Vec3 ta = g.bravais_vectors[0] * g.lattice_constant, tb = g.bravais_vectors[1] * g.lattice_constant;
+    const Vec3 p0 = g.positions()[0];
+    const double k = 0.1; // the reference stretches the corners away from the centre
+    const Vec3 P0 = p0 - ( ta + tb ) * k, Pab = ta + tb + p0 + ( ta + tb ) * k, Pb = tb + p0 - ( ta - tb ) * k, Pa = ta + p0 + ( ta - tb ) * k;
+    auto angle = []( const Vec3 & at, const Vec3 & u, const Vec3 & v )
+    {
+        const double ux = u.x - at.x, uy = u.y - at.y, vx = v.x - at.x, vy = v.y - at.y;
+        return std::atan2( std::abs( ux * vy - uy * vx ), ux * vx + uy * vy );
+    };
+    // Delaunay: the diagonal a-b is kept when the angles opposite to it (at 0 and at a+b) sum to at most pi
+    const double opposite = angle( P0, Pa, Pb ) + angle( Pab, Pa, Pb );
+    CellTriangulation t;
+    t.diag      = opposite <= constants::Pi + 1e-9 ? 0 : 1;
+    auto orient = []( const Vec3 & q0, const Vec3 & q1, const Vec3 & q2 )
+    {
+        const double nz = ( q0.x - q1.x ) * ( q0.y - q2.y ) - ( q0.y - q1.y ) * ( q0.x - q2.x );
+        return nz < 0 ? -1.0 : 1.0;
+    };
+    if( t.diag == 0 )
+        t.sign[0] = orient( Pa, Pb, Pab ), t.sign[1] = orient( Pa, Pb, P0 );
+    else
+        t.sign[0] = orient( P0, Pa, Pab ), t.sign[1] = orient( P0, Pab, Pb );
+    return t;
+}
+} // namespace
+
+// Quantities.cpp:62-87
+float Quantity_Get_Topological_Charge( State * state, int idx_image, int idx_chain ) noexcept
+try
+{
+    auto image = resolve( state, idx_image, idx_chain ).image;
+    if( image->geometry->dimensionality != 2 )
+        return 0;
+    const CellTriangulation t = cell_triangulation( *image->geometry );
+    image->sync_to_device();
+    return float( image->device().topological_charge( t.diag, t.sign[0], t.sign[1], nullptr ) );
+}
+SB_API_CATCH_RET( 0 )
+
+// Quantities.cpp:89-133: charge and site indices of every triangle that counts; returns their number. The triangles of a
+// family are in the reference's order (b outer, a inner); which family comes first is the triangulation library's choice there.
+int Quantity_Get_Topological_Charge_Density( State * state, float * charge_density, int * triangle_indices, int idx_image, int idx_chain ) noexcept
+try
+{
+    auto image         = resolve( state, idx_image, idx_chain ).image;
+    const Geometry & g = *image->geometry;
+    if( g.dimensionality != 2 )
+        return 0;
+    const CellTriangulation t = cell_triangulation( g );
+    const int Na = g.n_cells[0], Nb = g.n_cells[1];
+    const auto & bc = image->hamiltonian->boundary_conditions;
+    std::vector<double> density;
+    if( charge_density && triangle_indices )
+    {
+        density.resize( 2 * std::size_t( Na ) * Nb );
+        image->sync_to_device();
+        image->device().topological_charge( t.diag, t.sign[0], t.sign[1], density.data() );
+    }
+    int n = 0;
+    for( int family = 0; family < 2; ++family )
+        for( int b = 0; b < Nb; ++b )
+            for( int a = 0; a < Na; ++a )
+            {
+                if( !( ( a + 1 < Na || bc[0] ) && ( b + 1 < Nb || bc[1] ) ) )
+                    continue;
+                if( charge_density && triangle_indices )
+                {
+                    const int i0 = a + Na * b, ia = ( a + 1 ) % Na + Na * b, ib = a + Na * ( ( b + 1 ) % Nb ), iab = ( a + 1 ) % Na + Na * ( ( b + 1 ) % Nb );
+                    const int tri[2][2][3] = { { { ia, ib, iab }, { ia, ib, i0 } }, { { i0, ia, iab }, { i0, iab, ib } } };
+                    charge_density[n] = float( density[std::size_t( family ) * Na * Nb + i0] );
+                    for( int k = 0; k < 3; ++k )
+                        triangle_indices[3 * n + k] = tri[t.diag][family][k];
+                }
+                ++n;
+            }
+    return n;
+}
+SB_API_CATCH_RET( 0 )
+
 // ---- Geometry ----
 namespace
 {

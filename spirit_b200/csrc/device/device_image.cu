@@ -816,6 +816,31 @@ void DeviceImage::magnetization( double m[3], bool weighted )
         m[d] = b.h_scalars[6 + d] / double( nos_ );
 }
 
+double DeviceImage::topological_charge( int diag, double sign0, double sign1, double * density_host )
+{
+    auto & b        = *buf_;
+    const int cells = stencil_.Na * stencil_.Nb;
+    const int nb    = ( cells + BLOCK_THREADS - 1 ) / BLOCK_THREADS;
+    if( stencil_.NB != 1 )
+        throw std::runtime_error( "spirit_b200: topological charge is implemented for one basis atom" );
+    double *density = nullptr, *partials = nullptr;
+    SB_CUDA_CHECK( cudaMalloc( &partials, std::size_t( nb ) * sizeof( double ) ) );
+    if( density_host )
+        SB_CUDA_CHECK( cudaMalloc( &density, 2 * std::size_t( cells ) * sizeof( double ) ) );
+    k_topological_charge<<<nb, BLOCK_THREADS, 0, b.stream>>>( stencil_, b.spins.c(), diag, sign0, sign1, density, partials );
+    k_reduce_sum<<<1, BLOCK_THREADS, 0, b.stream>>>( partials, nb, b.scalars + 6 );
+    launches_ += 2;
+    SB_CUDA_CHECK( cudaGetLastError() );
+    SB_CUDA_CHECK( cudaMemcpyAsync( b.h_scalars + 6, b.scalars + 6, sizeof( double ), cudaMemcpyDeviceToHost, b.stream ) );
+    if( density_host )
+        SB_CUDA_CHECK( cudaMemcpyAsync( density_host, density, 2 * std::size_t( cells ) * sizeof( double ), cudaMemcpyDeviceToHost, b.stream ) );
+    SB_CUDA_CHECK( cudaStreamSynchronize( b.stream ) );
+    cudaFree( partials );
+    if( density )
+        cudaFree( density );
+    return b.h_scalars[6];
+}
+
 // ---------------------------------------------------------------------------------------------
 void DeviceImage::ensure_work_fields( int solver )
 {

@@ -530,5 +530,56 @@ static __global__ void __launch_bounds__( BLOCK_THREADS ) k_magnetization(
         partials[2 * nblocks + blockIdx.x] = v;
 }
 
+// Topological charge of a planar lattice with one basis atom (TopologicalChargeDensity, Vectormath.cpp:504-631): every cell
+// (a, b) carries the two triangles of its parallelogram (0, a, b, a+b), cut along the diagonal the Delaunay triangulation of
+// the reference picks (diag 0: a-b, 1: 0-(a+b)); a triangle counts when its translations are inside the lattice or allowed
+// by the boundary conditions. Charge of a triangle: sign / (4 pi) * 2 atan2( s1.(s2 x s3), 1 + s1.s2 + s1.s3 + s2.s3 ).
+// density (nullable): [2][Na*Nb], 0 for triangles that do not count; partials [nblocks].
+static __global__ void __launch_bounds__( BLOCK_THREADS ) k_topological_charge(
+    const __grid_constant__ StencilParams p, ConstField3 s, int diag, double sign0, double sign1, double * __restrict__ density,
+    double * __restrict__ partials )
+{
+    const int cell  = blockIdx.x * blockDim.x + threadIdx.x;
+    const int cells = p.Na * p.Nb;
+    double q0 = 0, q1 = 0;
+    if( cell < cells )
+    {
+        const int a = cell % p.Na, b = cell / p.Na;
+        const bool allowed = ( a + 1 < p.Na || p.bc[0] ) && ( b + 1 < p.Nb || p.bc[1] );
+        if( allowed )
+        {
+            const std::size_t plane = std::size_t( p.plane_stride ) * p.halo;
+            const int an = ( a + 1 ) % p.Na, bn = ( b + 1 ) % p.Nb;
+            const D3 s0 = load3( s, plane + a + std::size_t( p.Na ) * b ), sa = load3( s, plane + an + std::size_t( p.Na ) * b );
+            const D3 sb = load3( s, plane + a + std::size_t( p.Na ) * bn ), sab = load3( s, plane + an + std::size_t( p.Na ) * bn );
+            auto solid = []( const D3 & v1, const D3 & v2, const D3 & v3 )
+            {
+                const double x = dot3( v1, cross3( v2, v3 ) );
+                const double y = 1 + dot3( v1, v2 ) + dot3( v1, v3 ) + dot3( v2, v3 );
+                return 2 * atan2( x, y );
+            };
+            const double f = 1.0 / ( 4.0 * 3.14159265358979323846 );
+            if( diag == 0 )
+            {
+                q0 = sign0 * f * solid( sa, sb, sab );
+                q1 = sign1 * f * solid( sa, sb, s0 );
+            }
+            else
+            {
+                q0 = sign0 * f * solid( s0, sa, sab );
+                q1 = sign1 * f * solid( s0, sab, sb );
+            }
+        }
+        if( density )
+        {
+            density[cell]         = q0;
+            density[cells + cell] = q1;
+        }
+    }
+    const double v = block_sum( q0 + q1 );
+    if( threadIdx.x == 0 )
+        partials[blockIdx.x] = v;
+}
+
 } // namespace dev
 } // namespace sb

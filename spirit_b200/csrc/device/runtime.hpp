@@ -107,6 +107,8 @@ public:
     int energy_contributions( const Hamiltonian & ham, double * totals, double * per_spin_host );
     // mean of mu_s * s (Vectormath.cpp:495-502), or the plain mean of s if !weighted (Vectormath.cpp:150-160)
     void magnetization( double m[3], bool weighted );
+    // topological charge of the plane c = 0 (one basis atom); density_host (nullable): [2][Na*Nb] charges per triangle
+    double topological_charge( int diag, double sign0, double sign1, double * density_host );
 
     // n iterations of an LLG solver; if `hook` the last iteration also produces the quantities of
     // Method_LLG::Hook_Post_Iteration (Method_LLG.cpp:246-301) and the effective field buffer.
