@@ -253,3 +253,68 @@ void IO_Chain_Append( State * state, const char * file, int format, const char *
     }
     SB_API_CATCH_VOID
 }
+
+// IO.cpp:851-950: total and per-term energy of every spin as an OVF field with 1 + n_terms columns
+void IO_Image_Write_Energy_per_Spin( State * state, const char * file, int format, int idx_image, int idx_chain ) noexcept
+try
+{
+    auto image = resolve( state, idx_image, idx_chain ).image;
+    ImageLock lock( *image );
+    check_format( format );
+    warn_extension( file, idx_image, idx_chain );
+    Spin_System & sys = *image;
+    sys.UpdateEnergy();
+    const int n_terms = int( sys.E_array.size() );
+    std::vector<double> totals( static_cast<std::size_t>( n_terms ), 0.0 );
+    std::vector<double> per_term( static_cast<std::size_t>( n_terms ) * sys.nos, 0.0 );
+    sys.device().energy_contributions( *sys.hamiltonian, totals.data(), per_term.data() );
+    const int width = 1 + n_terms;
+    std::vector<double> data( std::size_t( width ) * sys.nos, 0.0 );
+    for( int i = 0; i < sys.nos; ++i )
+    {
+        double e = 0;
+        for( int t = 0; t < n_terms; ++t )
+        {
+            const double v                         = per_term[std::size_t( t ) * sys.nos + i];
+            data[std::size_t( i ) * width + 1 + t] = v;
+            e += v;
+        }
+        data[std::size_t( i ) * width] = e;
+    }
+    ovf::Segment seg = segment_of( sys );
+    seg.title        = std::string( "SPIRIT Version " ) + io::version_full();
+    seg.comment      = "Energy per spin. Total=" + io::shortest( sys.E ) + "meV";
+    seg.valuelabels  = "Total";
+    seg.valueunits   = "meV";
+    for( const auto & pair : sys.E_array )
+    {
+        seg.comment += ", " + pair.first + "=" + io::shortest( pair.second ) + "meV";
+        seg.valuelabels += " " + pair.first;
+        seg.valueunits += " meV";
+    }
+    seg.valuedim = width;
+    ovf::File( file ).write_segment( seg, data.data(), format );
+    Log( Log_Level::Info, Log_Sender::API, std::string( "Wrote energies per spin to file \"" ) + file + "\"", idx_image, idx_chain );
+}
+SB_API_CATCH_VOID
+
+// IO.cpp:952-972
+void IO_Image_Write_Energy( State * state, const char * file, int idx_image, int idx_chain ) noexcept
+try
+{
+    auto image = resolve( state, idx_image, idx_chain ).image;
+    io::write_image_energy( *image, file, true, true );
+}
+SB_API_CATCH_VOID
+
+// IO.cpp:975-992
+void IO_Chain_Write_Energies( State * state, const char * file, int idx_chain ) noexcept
+{
+    int idx_image = -1;
+    try
+    {
+        auto chain = resolve( state, idx_image, idx_chain ).chain;
+        io::write_chain_energies( *chain, file, true, true );
+    }
+    SB_API_CATCH_VOID
+}

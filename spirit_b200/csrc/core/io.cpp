@@ -121,6 +121,19 @@ void append_image_energy( const Spin_System & s, long iteration, const std::stri
     std::ofstream( file, std::ios::app ) << line;
 }
 
+void write_image_energy( const Spin_System & s, const std::string & file, bool normalize, bool readability )
+{
+    const double norm = normalize ? 1.0 / double( s.nos ) : 1.0;
+    write_energy_header( s, file, { "E_tot" }, true );
+    std::string line = " " + centred( fixed10( s.E * norm ) ) + " |";
+    for( const auto & pair : s.E_array )
+        line += "| " + centred( fixed10( pair.second * norm ) ) + " ";
+    line += "\n";
+    if( !readability )
+        std::replace( line.begin(), line.end(), '|', ' ' );
+    std::ofstream( file, std::ios::app ) << line;
+}
+
 void write_chain_energies( const Chain & chain, const std::string & file, bool normalize, bool readability )
 {
     const double norm = normalize ? 1.0 / double( chain.images[0]->nos ) : 1.0;

@@ -31,6 +31,8 @@ std::string shortest( double v ); // shortest decimal string that reads back exa
 // header line: the given first columns, then one column per energy contribution of `s`
 void write_energy_header( const Spin_System & s, const std::string & file, const std::vector<std::string> & columns, bool readability );
 void append_image_energy( const Spin_System & s, long iteration, const std::string & file, bool normalize, bool readability );
+// one line: E_tot, contributions, under a header with separator lines (Write_Image_Energy, Datawriter.cpp:186-206)
+void write_image_energy( const Spin_System & s, const std::string & file, bool normalize, bool readability );
 // one line per image: image, Rx, E_tot, contributions (the header always carries the separator lines, as in the reference)
 void write_chain_energies( const Chain & chain, const std::string & file, bool normalize, bool readability );
 

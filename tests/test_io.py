@@ -221,3 +221,39 @@ def test_gneb_output_files_match_the_reference(cfg, product, oracle, tmp_path):
                 vp, vo = [float(v) for v in lp.split()], [float(v) for v in lo.split()]
                 assert vp[0] == vo[0] and abs(vp[1] - vo[1]) <= 1e-8 and abs(vp[2] - vo[2]) <= 1e-8 * max(1.0, abs(vo[2])), (f, lp, lo)
     reader_p.close(), reader_o.close()
+
+
+@pytest.mark.gpu
+def test_energy_files_match_the_reference(cfg, product, oracle, tmp_path):
+    """IO_Image_Write_Energy, IO_Image_Write_Energy_per_Spin, IO_Chain_Write_Energies (IO.cpp:851-992)"""
+    p, o = pair(cfg, product, oracle, "cubic256", n_basis_cells="6 5 4", llg_temperature=0)
+    s = p.spins().copy()  # State_Setup ends with the same random configuration in both
+    assert np.array_equal(s, o.spins())
+    files = {}
+    for name, x in (("p", p), ("o", o)):
+        x.update_data()
+        e, es, ce = tmp_path / (name + "_E.txt"), tmp_path / (name + "_Es.ovf"), tmp_path / (name + "_chain.txt")
+        x.lib.IO_Image_Write_Energy(x.state, str(e).encode(), -1, -1)
+        x.lib.IO_Image_Write_Energy_per_Spin(x.state, str(es).encode(), BIN8, -1, -1)
+        x.chain_update_data()
+        x.lib.IO_Chain_Write_Energies(x.state, str(ce).encode(), -1)
+        files[name] = (e, es, ce)
+    for k in (0, 2):  # the two tables: identical titles, numbers to 1e-9 relative
+        tp, to = files["p"][k].read_text().splitlines(), files["o"][k].read_text().splitlines()
+        assert len(tp) == len(to) and tp[:3] == to[:3]
+        for lp, lo in zip(tp[3:], to[3:]):
+            vp = np.array([float(v) for v in lp.replace("|", " ").split()])
+            vo = np.array([float(v) for v in lo.replace("|", " ").split()])
+            assert vp.shape == vo.shape and np.abs(vp - vo).max() <= 1e-9 * max(1.0, np.abs(vo).max())
+    # per-spin energies: an OVF field with 1 + n_terms columns
+    hp, ho = files["p"][1].read_bytes(), files["o"][1].read_bytes()
+    def block(raw):
+        head, _, rest = raw.partition(b"# Begin: Data Binary 8\n")
+        labels = [l for l in head.decode().splitlines() if l.startswith("# valuelabels:")][0].split(":")[1].split()
+        data = np.frombuffer(rest[8:8 + 8 * len(labels) * 120], dtype="<f8").reshape(120, len(labels))
+        return labels, data
+    lp, dp = block(hp)
+    lo, do = block(ho)
+    assert lp == lo and lp[0] == "Total" and len(lp) >= 4
+    assert np.abs(dp - do).max() <= 1e-12 * np.abs(do).max()
+    p.close(), o.close()
