@@ -95,26 +95,27 @@ __device__ __forceinline__ double * globals( const ChainView & v )
     return v.scal + std::size_t( S_N_SLOTS ) * v.noi;
 }
 
-// row r of `partials` ([rows][n]) -> out[r]
-static __global__ void __launch_bounds__( BLOCK_THREADS ) k_reduce_rows( const double * __restrict__ partials, int n, double * __restrict__ out )
+// row r of slot k of `partials` ([slots][rows][n]) -> out[k * out_stride + r]; blockIdx = (row, slot): the slots of one
+// evaluation are reduced by ONE launch (the reductions are a sixth of a GNEB iteration at 64 x 256^2, profiles/r1zz)
+static __global__ void __launch_bounds__( BLOCK_THREADS ) k_reduce_rows( const double * __restrict__ partials, int n, double * __restrict__ out, int out_stride )
 {
-    const double * row = partials + std::size_t( blockIdx.x ) * n;
+    const double * row = partials + ( std::size_t( blockIdx.y ) * gridDim.x + blockIdx.x ) * n;
     double v           = 0;
     for( int i = threadIdx.x; i < n; i += BLOCK_THREADS )
         v += row[i];
     v = block_sum( v );
     if( threadIdx.x == 0 )
-        out[blockIdx.x] = v;
+        out[std::size_t( blockIdx.y ) * out_stride + blockIdx.x] = v;
 }
-static __global__ void __launch_bounds__( BLOCK_THREADS ) k_reduce_rows_max( const double * __restrict__ partials, int n, double * __restrict__ out )
+static __global__ void __launch_bounds__( BLOCK_THREADS ) k_reduce_rows_max( const double * __restrict__ partials, int n, double * __restrict__ out, int out_stride )
 {
-    const double * row = partials + std::size_t( blockIdx.x ) * n;
+    const double * row = partials + ( std::size_t( blockIdx.y ) * gridDim.x + blockIdx.x ) * n;
     double v           = 0;
     for( int i = threadIdx.x; i < n; i += BLOCK_THREADS )
         v = fmax( v, row[i] );
     v = block_max( v );
     if( threadIdx.x == 0 )
-        out[blockIdx.x] = v;
+        out[std::size_t( blockIdx.y ) * out_stride + blockIdx.x] = v;
 }
 
 // Gradient and energy of every image + squared geodesic distance to the previous image (Method_GNEB.cpp:95-128)
@@ -648,15 +649,11 @@ void DeviceChain::reduce_to_slots( int first_slot, int n_slots, bool max )
     const auto & T = *table_->buffers();
     if( sharded_ )
         SB_CUDA_CHECK( cudaMemsetAsync( b.scal + std::size_t( first_slot ) * noi_global_, 0, std::size_t( n_slots ) * noi_global_ * sizeof( double ), b.stream ) );
-    for( int k = 0; k < n_slots; ++k )
-    {
-        double * out          = b.scal + std::size_t( first_slot + k ) * noi_global_ + i_begin_;
-        const double * rows   = b.partials + std::size_t( k ) * noi_ * T.nblocks;
-        if( max )
-            k_reduce_rows_max<<<noi_, BLOCK_THREADS, 0, b.stream>>>( rows, T.nblocks, out );
-        else
-            k_reduce_rows<<<noi_, BLOCK_THREADS, 0, b.stream>>>( rows, T.nblocks, out );
-    }
+    double * out = b.scal + std::size_t( first_slot ) * noi_global_ + i_begin_;
+    if( max )
+        k_reduce_rows_max<<<dim3( noi_, n_slots ), BLOCK_THREADS, 0, b.stream>>>( b.partials, T.nblocks, out, noi_global_ );
+    else
+        k_reduce_rows<<<dim3( noi_, n_slots ), BLOCK_THREADS, 0, b.stream>>>( b.partials, T.nblocks, out, noi_global_ );
     share_slots( first_slot, n_slots, max );
 }
 
