@@ -18,9 +18,19 @@
 //   4 k_fft_pass (b)   inverse, keep b < Nb:  B -> A
 //   5 k_ddi_inv_a      Hermitian extension, inverse a-transform, keep a < Na, g_ddi = -mu_s * result / P written as
 //                      a field (AoSoA-32) that the stencil kernels add to the gradient
-// Every pass is a batch of shared-memory Stockham FFTs (mixed radix 4 / 2 / generic prime, fp64, twiddles from a
-// precomputed table), `ncol` adjacent transforms per CTA so that strided passes still move contiguous segments.
-// cuFFT is not used by the product; the tests compare against the reference's FFT and direct-sum paths.
+// Every pass is a batch of shared-memory FFTs, `ncol` adjacent transforms per CTA so that strided passes still move
+// contiguous segments. Two families of kernels serve them:
+//   * power-of-two lengths 64 ... 4096 (every zero-padded power-of-two lattice): k_ddi_fwd_a16 / k_ddi_inv_a16 (real rows as
+//     complex sequences of half the length), k_fft_pass16, k_ddi_c_mult16 -- instantiated per length (block_fft_ct: stage
+//     loop unrolled at compile time), radix-8 butterflies in registers, IN PLACE in one padded shared buffer, twiddles of a
+//     butterfly as powers of one table entry, tensor spectrum real (one sublattice) and stored in the c-pass's tile order;
+//     thin films (Pc <= 32) do the c-transforms in registers (k_ddi_c_mult_small);
+//   * any other length and any basis: k_ddi_fwd_a, k_fft_pass, k_ddi_c_mult, k_ddi_inv_a -- mixed-radix (4 / 2 / generic
+//     prime) Stockham passes between two shared buffers.
+// Slabs over several GPUs: the kb axis of B is cut into per-rank blocks, the all-to-alls travel one component at a time on
+// their own stream under the passes of the other components (ddi_gradient_pipelined).
+// cuFFT is not used by the product; the tests compare against the reference's FFT and direct-sum paths, every per-length
+// instantiation included (tests/test_ddi_gpu.py).
 #include "device_buffers.cuh"
 
 #include "../core/constants.hpp"
