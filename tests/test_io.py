@@ -257,3 +257,97 @@ def test_energy_files_match_the_reference(cfg, product, oracle, tmp_path):
     assert lp == lo and lp[0] == "Total" and len(lp) >= 4
     assert np.abs(dp - do).max() <= 1e-12 * np.abs(do).max()
     p.close(), o.close()
+
+
+HAND = """# OOMMF OVF 2.0
+#
+# Segment count: 000002
+#
+# Begin: Segment
+# Begin: Header
+#
+# Title: by hand
+# Desc: first line of the description
+# Desc: second line
+## a remark line inside the header
+# valuedim: 3   ## field dimensionality
+# valueunits: none none none
+# valuelabels: spin_x spin_y spin_z
+# meshunit: nm
+# xmin: 0
+# ymin: 0
+# zmin: 0
+# xmax: 1
+# ymax: 1
+# zmax: 1
+# meshtype: rectangular
+# xbase: 0
+# ybase: 0
+# zbase: 0
+# xstepsize: 1
+# ystepsize: 1
+# zstepsize: 1
+# xnodes: 4
+# ynodes: 2
+# znodes: 1
+# End: Header
+# Begin: Data Text
+%s
+# End: Data Text
+# End: Segment
+#
+# Begin: Segment
+# Begin: Header
+# Title: second segment, CSV, upper-case keywords are not required by the format
+# valuedim: 3
+# valueunits: none none none
+# valuelabels: spin_x spin_y spin_z
+# meshunit: nm
+# xmin: 0
+# ymin: 0
+# zmin: 0
+# xmax: 1
+# ymax: 1
+# zmax: 1
+# meshtype: rectangular
+# xbase: 0
+# ybase: 0
+# zbase: 0
+# xstepsize: 1
+# ystepsize: 1
+# zstepsize: 1
+# xnodes: 4
+# ynodes: 2
+# znodes: 1
+# End: Header
+# Begin: Data CSV
+%s
+# End: Data CSV
+# End: Segment
+"""
+
+
+def test_hand_written_files_are_read_like_the_reference_reads_them(cfg, product, oracle, tmp_path):
+    """text and CSV blocks with irregular spacing, scientific notation, unnormalised and zero vectors, multi-line
+    descriptions, remark lines; CRLF line ends"""
+    rng = np.random.default_rng(3)
+    v = rng.standard_normal((8, 3)) * 3.0
+    v[5] = 0.0  # a zero vector: read as +z (IO.cpp:267-270)
+    v = np.array([[float("%.9e" % b) if i == 1 else b for i, b in enumerate(row)] for row in v])  # column 2 is written with 10 digits
+    text = "\n".join("  %.17g   %.9e\t%r" % tuple(float(x) for x in row) for row in v)
+    csv = "\n".join("%.17g, %.17g ,%.17g," % tuple(row[::-1]) for row in v)
+    p, o = pair(cfg, product, oracle, n_basis_cells="4 2 1")
+    for name, content in (("unix.ovf", HAND % (text, csv)), ("dos.ovf", (HAND % (text, csv)).replace("\n", "\r\n"))):
+        f = tmp_path / name
+        f.write_bytes(content.encode())
+        assert p.n_images_in_file(f) == o.n_images_in_file(f) == 2, name
+        for k in range(2):
+            p.plus_z(), o.plus_z()
+            p.image_read(f, k), o.image_read(f, k)
+            got, ref = p.spins(), o.spins()
+            assert np.array_equal(got, ref), (name, k)
+            want = (v if k == 0 else v[:, ::-1]).copy()
+            want[5] = (0, 0, 1)
+            want /= np.linalg.norm(want, axis=1)[:, None]
+            assert np.abs(got - want).max() < 1e-9
+    p.close(), o.close()
