@@ -19,4 +19,26 @@ SPIRIT_API int Log_Get_N_Entries( State * state ) SPIRIT_NOEXCEPT;
 SPIRIT_API int Log_Get_N_Errors( State * state ) SPIRIT_NOEXCEPT;
 /* Log.h:110 */
 SPIRIT_API int Log_Get_N_Warnings( State * state ) SPIRIT_NOEXCEPT;
+/* Log.h:70 */
+SPIRIT_API void Log_Append( State * state ) SPIRIT_NOEXCEPT;
+/* Log.h:73 */
+SPIRIT_API void Log_Dump( State * state ) SPIRIT_NOEXCEPT;
+/* Log.h:90 */
+SPIRIT_API void Log_Set_Output_File_Tag( State * state, const char * tag ) SPIRIT_NOEXCEPT;
+/* Log.h:93 */
+SPIRIT_API void Log_Set_Output_Folder( State * state, const char * folder ) SPIRIT_NOEXCEPT;
+/* Log.h:99 */
+SPIRIT_API void Log_Set_Output_To_File( State * state, bool output, int level ) SPIRIT_NOEXCEPT;
+/* Log.h:107 */
+SPIRIT_API const char * Log_Get_Output_File_Tag( State * state ) SPIRIT_NOEXCEPT;
+/* Log.h:110 */
+SPIRIT_API const char * Log_Get_Output_Folder( State * state ) SPIRIT_NOEXCEPT;
+/* Log.h:113 */
+SPIRIT_API bool Log_Get_Output_To_Console( State * state ) SPIRIT_NOEXCEPT;
+/* Log.h:116 */
+SPIRIT_API int Log_Get_Output_Console_Level( State * state ) SPIRIT_NOEXCEPT;
+/* Log.h:119 */
+SPIRIT_API bool Log_Get_Output_To_File( State * state ) SPIRIT_NOEXCEPT;
+/* Log.h:122 */
+SPIRIT_API int Log_Get_Output_File_Level( State * state ) SPIRIT_NOEXCEPT;
 #endif

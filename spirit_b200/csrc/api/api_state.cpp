@@ -156,6 +156,52 @@ void Log_Set_Output_To_Console( State *, bool output, int level ) noexcept
     Log.messages_to_console = output;
     Log.level_console       = Log_Level( std::max( 0, std::min( 6, level ) ) );
 }
+// Log.h:70-122
+void Log_Append( State * ) noexcept
+{
+    Log.Append_to_File();
+}
+void Log_Dump( State * ) noexcept
+{
+    Log.Dump_to_File();
+}
+void Log_Set_Output_File_Tag( State *, const char * tag ) noexcept
+{
+    Log.file_tag = tag ? tag : "";
+}
+void Log_Set_Output_Folder( State *, const char * folder ) noexcept
+{
+    Log.output_folder = folder ? folder : ".";
+}
+void Log_Set_Output_To_File( State *, bool output, int level ) noexcept
+{
+    Log.messages_to_file = output;
+    Log.level_file       = Log_Level( std::max( 0, std::min( 6, level ) ) );
+}
+const char * Log_Get_Output_File_Tag( State * ) noexcept
+{
+    return Log.file_tag.c_str();
+}
+const char * Log_Get_Output_Folder( State * ) noexcept
+{
+    return Log.output_folder.c_str();
+}
+bool Log_Get_Output_To_Console( State * ) noexcept
+{
+    return Log.messages_to_console;
+}
+int Log_Get_Output_Console_Level( State * ) noexcept
+{
+    return int( Log.level_console );
+}
+bool Log_Get_Output_To_File( State * ) noexcept
+{
+    return Log.messages_to_file;
+}
+int Log_Get_Output_File_Level( State * ) noexcept
+{
+    return int( Log.level_file );
+}
 int Log_Get_N_Entries( State * ) noexcept { return Log.n_entries; }
 int Log_Get_N_Errors( State * ) noexcept { return Log.n_errors; }
 int Log_Get_N_Warnings( State * ) noexcept { return Log.n_warnings; }

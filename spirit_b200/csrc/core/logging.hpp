@@ -43,6 +43,12 @@ struct Logger
     std::string output_folder = ".";
     std::string file_tag      = "";
     int n_entries = 0, n_errors = 0, n_warnings = 0;
+    // formatted entries (level <= level_file) waiting for / already written to the log file (Logging.cpp:160-225)
+    std::vector<std::string> file_lines;
+    std::size_t n_lines_written = 0;
+    std::string file_name() const; // Log_<tag>.txt, Log.txt without a tag, Log_<start time>.txt for the tag "<time>"
+    void Append_to_File();         // lines not yet written; no-op unless messages_to_file
+    void Dump_to_File();           // the whole log
 
     void operator()( Log_Level level, Log_Sender sender, const std::string & message, int idx_image = -1, int idx_chain = -1 );
     void SendBlock( Log_Level level, Log_Sender sender, const std::vector<std::string> & messages, int idx_image = -1, int idx_chain = -1 );
