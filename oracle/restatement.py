@@ -20,6 +20,8 @@ Reference locations (relative to /root/reference/core):
   rotate                    src/engine/Vectormath.cpp:474-485
   GNEB force, tangents      src/engine/Method_GNEB.cpp:87-258, src/engine/Manifoldmath.cpp:115-213
   constants                 include/utility/Constants.hpp:18-46
+  topological charge        src/engine/Vectormath.cpp:462-472,504-631
+  dipolar direct sum        src/engine/Hamiltonian_Heisenberg.cpp:1016-1071
 """
 import numpy as np
 
@@ -252,3 +254,66 @@ def gneb_two_stage_single_shots(model, imgs, types, k_spring, n_steps, solver):
         else:
             raise ValueError(solver)
     return imgs, E, Rx
+
+
+# ---------------------------------------------------------------------------------------------------------------------------
+# Topological charge of a planar lattice with one basis atom (src/engine/Vectormath.cpp:462-472,504-631): the cell
+# parallelogram (0, a, b, a+b) is cut along the a-b diagonal (the Delaunay choice for square and hexagonal cells, the
+# reference's library picks it for the degenerate square cell too); a triangle counts when its translations are inside the
+# lattice or allowed by the boundary conditions; charge = sign / (4 pi) * 2 atan2( s1.(s2 x s3), 1 + s1.s2 + s1.s3 + s2.s3 ).
+# ---------------------------------------------------------------------------------------------------------------------------
+def solid_angle(s1, s2, s3):
+    x = np.einsum("...i,...i", s1, np.cross(s2, s3))
+    y = 1 + np.einsum("...i,...i", s1, s2) + np.einsum("...i,...i", s1, s3) + np.einsum("...i,...i", s2, s3)
+    return 2 * np.arctan2(x, y)
+
+
+def topological_charge(spins, n_cells, bc, ta=(1.0, 0.0), tb=(0.0, 1.0)):
+    """spins [Nb*Na][3] (a fastest), bc = (periodic a, periodic b); ta, tb: the in-plane bravais vectors.
+    Returns (total charge, {sorted site triple: charge})."""
+    Na, Nb = n_cells
+    s = np.asarray(spins, dtype=float).reshape(Nb, Na, 3)
+    ta, tb = np.asarray(ta, dtype=float), np.asarray(tb, dtype=float)
+
+    def orientation(p0, p1, p2):  # z of (p0 - p1) x (p0 - p2)
+        u, v = p0 - p1, p0 - p2
+        return 1.0 if u[0] * v[1] - u[1] * v[0] > 0 else -1.0
+
+    k = 0.1  # the reference stretches the corners of the cell away from its centre before triangulating
+    P0, Pab, Pb, Pa = -k * (ta + tb), (1 + k) * (ta + tb), tb - k * (ta - tb), ta + k * (ta - tb)
+    sign = (orientation(Pa, Pb, Pab), orientation(Pa, Pb, P0))
+    total, per_triangle = 0.0, {}
+    for b in range(Nb):
+        for a in range(Na):
+            if not ((a + 1 < Na or bc[0]) and (b + 1 < Nb or bc[1])):
+                continue
+            an, bn = (a + 1) % Na, (b + 1) % Nb
+            i0, ia, ib, iab = a + Na * b, an + Na * b, a + Na * bn, an + Na * bn
+            for sg, (i1, i2, i3), (v1, v2, v3) in ((sign[0], (ia, ib, iab), (s[b, an], s[bn, a], s[bn, an])),
+                                                   (sign[1], (ia, ib, i0), (s[b, an], s[bn, a], s[b, a]))):
+                q = sg / (4 * np.pi) * solid_angle(v1, v2, v3)
+                per_triangle[tuple(sorted((i1, i2, i3)))] = q
+                total += q
+    return total, per_triangle
+
+
+# ---------------------------------------------------------------------------------------------------------------------------
+# Dipole-dipole gradient as the plain O(N^2) sum over an open simple-cubic lattice (Gradient_DDI_Direct,
+# src/engine/Hamiltonian_Heisenberg.cpp:1016-1071):  g_i -= mu_i C sum_j mu_j (3 (s_j.r) r / r^5 - s_j / r^3),
+# C = mu_0 mu_B^2 / (4 pi 1e-30), r in Angstrom. What the zero-padded FFT convolution of the product must reproduce.
+# ---------------------------------------------------------------------------------------------------------------------------
+def ddi_gradient_direct(spins, n_cells, mu_s=2.0, lattice_constant=1.0):
+    Na, Nb, Nc = n_cells
+    mu_0 = 2.0133545e-28  # T^2 m^3 / meV (include/utility/Constants.hpp)
+    C = mu_0 * mu_B ** 2 / (4 * np.pi * 1e-30)
+    idx = np.arange(Na * Nb * Nc)
+    pos = np.stack([idx % Na, (idx // Na) % Nb, idx // (Na * Nb)], axis=1) * float(lattice_constant)
+    s = np.asarray(spins, dtype=float)
+    g = np.zeros_like(s)
+    for i in range(len(s)):
+        r = pos - pos[i]
+        d = np.linalg.norm(r, axis=1)
+        d[i] = np.inf
+        sr = np.einsum("ij,ij->i", s, r)
+        g[i] = -mu_s * mu_s * C * ((3 * sr / d ** 5)[:, None] * r - s / (d ** 3)[:, None]).sum(axis=0)
+    return g

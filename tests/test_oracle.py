@@ -120,3 +120,43 @@ def test_reference_skyrmion_relaxation_golden_value(cfg, oracle):
     assert abs(o.energy() - (-5849.69140625)) < 1e-3
     assert abs(o.magnetization()[2] - 2 * 0.79977) < 1e-4
     o.close()
+
+
+def _oracle_density(o):
+    import ctypes
+    n = o.lib.Quantity_Get_Topological_Charge_Density(o.state, None, None, -1, -1)
+    q, tri = (ctypes.c_float * n)(), (ctypes.c_int * (3 * n))()
+    o.lib.Quantity_Get_Topological_Charge_Density(o.state, q, tri, -1, -1)
+    t = np.array(tri).reshape(-1, 3)
+    return {tuple(sorted(map(int, row))): float(v) for row, v in zip(t, np.array(q))}
+
+
+@pytest.mark.parametrize("lattice,bc", [("sc", "0 0 0"), ("sc", "1 1 0"), ("sc", "1 0 0"), ("hex2d", "0 0 0"), ("hex2d", "1 1 0")])
+def test_restatement_topological_charge_matches_compiled_reference(cfg, oracle, lattice, bc):
+    """pins oracle/restatement.py::topological_charge (cut of the cell, orientation, boundary rule) to the reference"""
+
+    o = S.Session(oracle, cfg("cubic256", n_basis_cells="9 7 1", bravais_lattice=lattice, boundary_conditions=bc))
+    periodic = [int(v) for v in bc.split()][:2]
+    tb = (0.5, 0.5 * np.sqrt(3.0)) if lattice == "hex2d" else (0.0, 1.0)
+    for make in (lambda x: (x.plus_z(), x.skyrmion(2.5, phase=-90.0)), lambda x: x.random()):
+        make(o)
+        total, per_triangle = R.topological_charge(o.spins(), (9, 7), periodic, tb=tb)
+        ref = _oracle_density(o)
+        assert set(ref) == set(per_triangle)
+        assert max(abs(per_triangle[t] - ref[t]) for t in ref) < 1e-6  # the API returns floats
+        assert abs(total - o.lib.Quantity_Get_Topological_Charge(o.state, -1, -1)) < 2e-6 * max(1.0, abs(total))
+    o.close()
+
+
+def test_restatement_direct_dipolar_sum_matches_compiled_reference(cfg, oracle):
+    """pins oracle/restatement.py::ddi_gradient_direct to the reference's direct sum AND to its FFT convolution"""
+
+    over = dict(n_basis_cells="5 4 3", boundary_conditions="0 0 0", jij="0", dij="0", n_shells_dmi="0", anisotropy_magnitude="0",
+                external_field_magnitude="0", llg_temperature="0")
+    for method in ({"ddi_method": "cutoff", "ddi_radius": "-1"}, {"ddi_method": "fft"}):
+        o = S.Session(oracle, cfg("cubic256", **dict(over, **method)))
+        s = o.spins().copy()
+        g_ref, _ = o.gradient_and_energy(s)
+        g = R.ddi_gradient_direct(s, (5, 4, 3), mu_s=2.0)
+        assert np.abs(g - g_ref).max() <= 1e-12 * np.abs(g_ref).max()
+        o.close()
