@@ -1,7 +1,7 @@
 /* Spin configurations and chains on disk: OVF 2.0 files as the reference reads and writes them.
  * Replaces the vector-field part of core/include/Spirit/IO.h:26-103 (implementation: core/src/Spirit/IO.cpp:165-860,
- * core/src/io/OVF_File.cpp:14-43, core/thirdparty/ovf) and the energy files (IO.h:118-130). Neighbour lists, interpolated
- * chain energies and eigenmodes are not provided. */
+ * core/src/io/OVF_File.cpp:14-43, core/thirdparty/ovf) and the energy files (IO.h:118-130). The interpolated chain energies and the eigenmode files are in Compat.h
+ * (not provided). */
 #ifndef SPIRIT_B200_IO_H
 #define SPIRIT_B200_IO_H
 #include "Export.h"
@@ -32,6 +32,10 @@ SPIRIT_API void IO_Chain_Read( State * state, const char * file, int start_image
 SPIRIT_API void IO_Chain_Write( State * state, const char * file, int format SPIRIT_DEFAULT( IO_Fileformat_OVF_text ), const char * comment SPIRIT_DEFAULT( "-" ), int idx_chain SPIRIT_DEFAULT( -1 ) ) SPIRIT_NOEXCEPT;
 /* IO.h:97 */
 SPIRIT_API void IO_Chain_Append( State * state, const char * file, int format SPIRIT_DEFAULT( IO_Fileformat_OVF_text ), const char * comment SPIRIT_DEFAULT( "-" ), int idx_chain SPIRIT_DEFAULT( -1 ) ) SPIRIT_NOEXCEPT;
+/* IO.h:105 */
+SPIRIT_API void IO_Image_Write_Neighbours_Exchange( State * state, const char * file, int idx_image SPIRIT_DEFAULT( -1 ), int idx_chain SPIRIT_DEFAULT( -1 ) ) SPIRIT_NOEXCEPT;
+/* IO.h:109 */
+SPIRIT_API void IO_Image_Write_Neighbours_DMI( State * state, const char * file, int idx_image SPIRIT_DEFAULT( -1 ), int idx_chain SPIRIT_DEFAULT( -1 ) ) SPIRIT_NOEXCEPT;
 /* IO.h:118 */
 SPIRIT_API void IO_Image_Write_Energy_per_Spin( State * state, const char * file, int format, int idx_image SPIRIT_DEFAULT( -1 ), int idx_chain SPIRIT_DEFAULT( -1 ) ) SPIRIT_NOEXCEPT;
 /* IO.h:121 */

@@ -11,6 +11,8 @@
 #include <Spirit/Version.h>
 
 #include <algorithm>
+#include <cstdio>
+#include <fstream>
 #include <string>
 
 using namespace sb;
@@ -318,3 +320,57 @@ void IO_Chain_Write_Energies( State * state, const char * file, int idx_chain ) 
     }
     SB_API_CATCH_VOID
 }
+
+// IO.cpp:730-790 / Datawriter.cpp:22-113: the pair lists the stencil kernels work on, as text tables. The lists are the
+// redundant ones (both directions of every pair), like those of the reference's OpenMP and CUDA builds: no mirrored lines.
+namespace
+{
+std::string fixed8( double v )
+{
+    char buf[64];
+    std::snprintf( buf, sizeof( buf ), "%.8f", v );
+    return buf;
+}
+std::string pair_columns( const Pair & p )
+{
+    return io::centred( std::to_string( p.i ), 3 ) + " " + io::centred( std::to_string( p.j ), 3 ) + "    " + io::centred( std::to_string( p.translations[0] ), 3 )
+           + " " + io::centred( std::to_string( p.translations[1] ), 3 ) + " " + io::centred( std::to_string( p.translations[2] ), 3 ) + "    ";
+}
+} // namespace
+
+void IO_Image_Write_Neighbours_Exchange( State * state, const char * file, int idx_image, int idx_chain ) noexcept
+try
+{
+    auto image            = resolve( state, idx_image, idx_chain ).image;
+    const Hamiltonian & h = *image->hamiltonian;
+    std::string out       = "###    Interaction neighbours:\n";
+    out += "n_neighbours_exchange " + std::to_string( h.exchange_pairs.size() ) + "\n";
+    if( !h.exchange_pairs.empty() )
+    {
+        out += io::centred( "i", 3 ) + " " + io::centred( "j", 3 ) + "    " + io::centred( "da", 3 ) + " " + io::centred( "db", 3 ) + " " + io::centred( "dc", 3 )
+               + "    " + io::centred( "Jij", 15 ) + "\n";
+        for( std::size_t k = 0; k < h.exchange_pairs.size(); ++k )
+            out += pair_columns( h.exchange_pairs[k] ) + io::centred( fixed8( h.exchange_magnitudes[k] ), 15 ) + "\n";
+    }
+    std::ofstream( file, std::ios::trunc ) << out;
+}
+SB_API_CATCH_VOID
+
+void IO_Image_Write_Neighbours_DMI( State * state, const char * file, int idx_image, int idx_chain ) noexcept
+try
+{
+    auto image            = resolve( state, idx_image, idx_chain ).image;
+    const Hamiltonian & h = *image->hamiltonian;
+    std::string out       = "###    Interaction neighbours:\n";
+    out += "n_neighbours_dmi " + std::to_string( h.dmi_pairs.size() ) + "\n";
+    if( !h.dmi_pairs.empty() )
+    {
+        out += io::centred( "i", 3 ) + " " + io::centred( "j", 3 ) + "    " + io::centred( "da", 3 ) + " " + io::centred( "db", 3 ) + " " + io::centred( "dc", 3 )
+               + "    " + io::centred( "Dij", 15 ) + " " + io::centred( "Dijx", 15 ) + " " + io::centred( "Dijy", 15 ) + " " + io::centred( "Dijz", 15 ) + "\n";
+        for( std::size_t k = 0; k < h.dmi_pairs.size(); ++k )
+            out += pair_columns( h.dmi_pairs[k] ) + io::centred( fixed8( h.dmi_magnitudes[k] ), 15 ) + " " + io::centred( fixed8( h.dmi_normals[k].x ), 15 ) + " "
+                   + io::centred( fixed8( h.dmi_normals[k].y ), 15 ) + " " + io::centred( fixed8( h.dmi_normals[k].z ), 15 ) + "\n";
+    }
+    std::ofstream( file, std::ios::trunc ) << out;
+}
+SB_API_CATCH_VOID

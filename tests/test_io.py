@@ -351,3 +351,18 @@ def test_hand_written_files_are_read_like_the_reference_reads_them(cfg, product,
             want /= np.linalg.norm(want, axis=1)[:, None]
             assert np.abs(got - want).max() < 1e-9
     p.close(), o.close()
+
+
+@pytest.mark.parametrize("preset,over", [("solvers", {}), ("cubic256", {"n_basis_cells": "4 4 4", "n_shells_exchange": "3", "jij": "10 5 2.5",
+                                                                      "n_shells_dmi": "2", "dij": "6 3"}), ("default", {"n_basis_cells": "6 5 2"}),
+                                         ("ddi", {"ddi_method": "none"})])
+def test_neighbour_files_are_identical_to_the_reference(cfg, product, oracle, tmp_path, preset, over):
+    """IO_Image_Write_Neighbours_Exchange / _DMI: the pair lists the stencil kernels work on, byte for byte"""
+    p, o = pair(cfg, product, oracle, preset, **over)
+    for kind in ("Exchange", "DMI"):
+        fp, fo = tmp_path / ("p_%s.txt" % kind), tmp_path / ("o_%s.txt" % kind)
+        getattr(p.lib, "IO_Image_Write_Neighbours_" + kind)(p.state, str(fp).encode(), -1, -1)
+        getattr(o.lib, "IO_Image_Write_Neighbours_" + kind)(o.state, str(fo).encode(), -1, -1)
+        assert fp.read_text() == fo.read_text(), kind
+        assert len(fp.read_text().splitlines()) >= 2
+    p.close(), o.close()
