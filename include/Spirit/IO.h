@@ -16,6 +16,8 @@ typedef struct State State;
 #define IO_Fileformat_OVF_text 3
 #define IO_Fileformat_OVF_csv 4
 
+/* IO.h:46 */
+SPIRIT_API int IO_System_From_Config( State * state, const char * file, int idx_image SPIRIT_DEFAULT( -1 ), int idx_chain SPIRIT_DEFAULT( -1 ) ) SPIRIT_NOEXCEPT;
 /* IO.h:50 */
 SPIRIT_API void IO_Positions_Write( State * state, const char * file, int format SPIRIT_DEFAULT( IO_Fileformat_OVF_bin ), const char * comment SPIRIT_DEFAULT( "-" ), int idx_image SPIRIT_DEFAULT( -1 ), int idx_chain SPIRIT_DEFAULT( -1 ) ) SPIRIT_NOEXCEPT;
 /* IO.h:60 */

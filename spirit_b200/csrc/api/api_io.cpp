@@ -6,6 +6,7 @@
 #include "../core/ovf.hpp"
 
 #include <Spirit/Chain.h>
+#include <Spirit/Configurations.h>
 #include <Spirit/IO.h>
 #include <Spirit/State.h>
 #include <Spirit/Version.h>
@@ -374,3 +375,34 @@ try
     std::ofstream( file, std::ios::trunc ) << out;
 }
 SB_API_CATCH_VOID
+
+// IO.cpp:36-85: the image becomes the system described by another input file (same number of spins as every image of the
+// chain), and starts from a random configuration
+int IO_System_From_Config( State * state, const char * file, int idx_image, int idx_chain ) noexcept
+try
+{
+    auto ref  = resolve( state, idx_image, idx_chain );
+    auto image = ref.image;
+    std::shared_ptr<Spin_System> system = config::Spin_System_from_Config( file );
+    for( const auto & other : ref.chain->images )
+        if( other->nos != system->nos )
+            return 0;
+    {
+        ImageLock lock( *image );
+        image->drop_device();
+        image->nos             = system->nos;
+        image->spins           = system->spins;
+        image->effective_field = system->effective_field;
+        image->E               = system->E;
+        image->E_array         = system->E_array;
+        image->M               = system->M;
+        image->geometry        = std::make_shared<Geometry>( *system->geometry );
+        image->hamiltonian     = std::make_shared<Hamiltonian>( *system->hamiltonian );
+        image->hamiltonian->geometry = image->geometry;
+        image->llg_parameters        = std::make_shared<Parameters_LLG>( *system->llg_parameters );
+    }
+    const float position[3] = { 0, 0, 0 }, rectangular[3] = { -1, -1, -1 };
+    Configuration_Random( state, position, rectangular, -1, -1, false, false, idx_image, idx_chain );
+    return 1;
+}
+SB_API_CATCH_RET( 0 )

@@ -366,3 +366,21 @@ def test_neighbour_files_are_identical_to_the_reference(cfg, product, oracle, tm
         assert fp.read_text() == fo.read_text(), kind
         assert len(fp.read_text().splitlines()) >= 2
     p.close(), o.close()
+
+
+def test_system_from_config_matches_the_reference(cfg, product, oracle):
+    """IO_System_From_Config (IO.cpp:36-85): the image takes geometry, Hamiltonian and parameters of another input file"""
+    first = cfg("solvers", n_basis_cells="6 6 1")
+    second = cfg("cubic256", n_basis_cells="4 3 3", n_shells_exchange="2", jij="7 2", llg_temperature="0", llg_seed="77")
+    wrong = cfg("solvers", n_basis_cells="5 5 1")
+    p, o = S.Session(product, first), S.Session(oracle, first)
+    for x in (p, o):
+        assert x.lib.IO_System_From_Config(x.state, wrong.encode(), -1, -1) == 0  # another number of spins: refused
+        assert x.lib.IO_System_From_Config(x.state, second.encode(), -1, -1) == 1
+    assert p.nos == o.nos == 36
+    for kind in (0, 1):
+        a, b = p.pairs(kind), o.pairs(kind)
+        assert np.array_equal(a[0], b[0]) and np.array_equal(a[1], b[1])
+    assert np.array_equal(p.spins(), o.spins())  # the random configuration of the new system's generator
+    assert abs(np.linalg.norm(p.spins(), axis=1) - 1).max() < 1e-15
+    p.close(), o.close()
