@@ -384,3 +384,38 @@ def test_system_from_config_matches_the_reference(cfg, product, oracle):
     assert np.array_equal(p.spins(), o.spins())  # the random configuration of the new system's generator
     assert abs(np.linalg.norm(p.spins(), axis=1) - 1).max() < 1e-15
     p.close(), o.close()
+
+
+def test_random_sequences_of_writes_and_appends_round_trip(cfg, product, oracle, tmp_path):
+    """property test: any sequence of write / append calls in any format leaves a file whose segments both libraries read back
+    as the configurations that were written (tolerance of the format)"""
+    from hypothesis import given, settings, strategies as st
+    p, o = pair(cfg, product, oracle, n_basis_cells="5 3 2")
+    tol = {BIN: 3e-16, BIN4: 1e-7, BIN8: 3e-16, TEXT: 1e-11, CSV: 1e-11}
+    counter = [0]
+
+    @settings(max_examples=25, deadline=None)
+    @given(st.lists(st.tuples(st.booleans(), st.sampled_from([BIN, BIN4, BIN8, TEXT, CSV]), st.integers(0, 2 ** 31 - 1)), min_size=1, max_size=6))
+    def run(ops):
+        counter[0] += 1
+        f = tmp_path / ("seq_%d.ovf" % counter[0])
+        expected = []
+        for append, fmt, seed in ops:
+            rng = np.random.default_rng(seed)
+            s = rng.standard_normal((p.nos, 3))
+            s /= np.linalg.norm(s, axis=1)[:, None]
+            p.set_spins(s)
+            if append:
+                p.image_append(f, fmt, "seed %d" % seed)
+                expected.append((p.spins().copy(), tol[fmt]))
+            else:
+                p.image_write(f, fmt, "seed %d" % seed)
+                expected = [(p.spins().copy(), tol[fmt])]
+        assert p.n_images_in_file(f) == len(expected) == o.n_images_in_file(f)
+        for k, (want, t) in enumerate(expected):
+            p.plus_z(), o.plus_z()
+            p.image_read(f, k), o.image_read(f, k)
+            assert np.abs(p.spins() - want).max() <= t and np.array_equal(p.spins(), o.spins())
+
+    run()
+    p.close(), o.close()
