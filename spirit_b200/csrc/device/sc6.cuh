@@ -45,6 +45,17 @@ namespace dev
 #ifndef SB_SC6_L2_PREFETCH
 #define SB_SC6_L2_PREFETCH 0 // > 0: prefetch.global.L2 of the own-column sites this many planes ahead (no registers)
 #endif
+// Tuning builds only (profiles/r1zz_ptxas_study_plain_variants.txt): compile the rare terms' uniform tests out of the plane loop.
+// A library built with any of these set serves only Hamiltonians without that term (no run-time check).
+#ifndef SB_SC6_NO_ANISO_FULL
+#define SB_SC6_NO_ANISO_FULL 0
+#endif
+#ifndef SB_SC6_NO_EXTRAS
+#define SB_SC6_NO_EXTRAS 0
+#endif
+#ifndef SB_SC6_NO_STT
+#define SB_SC6_NO_STT 0
+#endif
 #ifndef SB_SC6_THREADS_2W
 #define SB_SC6_THREADS_2W 512
 #define SB_SC6_MINB_2W 1
@@ -152,13 +163,13 @@ __device__ __forceinline__ D3 sc6_gradient(
     g.x = fma( p.sc6_A[0], si.x, g.x );
     g.y = fma( p.sc6_A[1], si.y, g.y );
     g.z = fma( p.sc6_A[2], si.z, g.z );
-    if( p.sc6_aniso_full ) // off-diagonal elements: anisotropy axes that are not lattice axes
+    if( !SB_SC6_NO_ANISO_FULL && p.sc6_aniso_full ) // off-diagonal elements: anisotropy axes that are not lattice axes
     {
         g.x = fma( p.sc6_A[3], si.y, fma( p.sc6_A[4], si.z, g.x ) );
         g.y = fma( p.sc6_A[3], si.x, fma( p.sc6_A[5], si.z, g.y ) );
         g.z = fma( p.sc6_A[4], si.x, fma( p.sc6_A[5], si.y, g.z ) );
     }
-    if( p.sc6_extras )
+    if( !SB_SC6_NO_EXTRAS && p.sc6_extras )
     {
         if( p.has_cubic )
         {
@@ -207,7 +218,7 @@ __device__ __forceinline__ D3 sc6_virtual_force( const LLGParams & l, const D3 &
     fv.x = fma( s.y, w.z, fma( -s.z, w.y, fv.x ) );
     fv.y = fma( s.z, w.x, fma( -s.x, w.z, fv.y ) );
     fv.z = fma( s.x, w.y, fma( -s.y, w.x, fv.z ) );
-    if( MODE != SC6_MINIMISE && l.has_stt )
+    if( !SB_SC6_NO_STT && MODE != SC6_MINIMISE && l.has_stt )
     {
         const D3 pol = make_d3( l.stt_pol[0], l.stt_pol[1], l.stt_pol[2] );
         const D3 pxs = cross3( pol, s );
