@@ -75,4 +75,8 @@ SPIRIT_API int SpiritB200_Chain_Shard_Setup( State * state, int i_begin, int noi
 /* The same iterations with a CUDA event between the stage kernels: stage_ms[k] = mean milliseconds of stage k+1
  * (Depondt/Heun/SIB: 2 stages, RK4: 4). Returns the number of stages, < 0 on error. For per-kernel rooflines. */
 SPIRIT_API int SpiritB200_LLG_Profile_Stages( State * state, int solver_type, int n_iterations, double * stage_ms, int max_stages, int idx_image ) SPIRIT_NOEXCEPT;
+/* Host-side probe: the triangles (3 site indices each) the topological charge is summed over (Vectormath.cpp:504-631:
+ * Delaunay triangulation of the basis cell, repeated over the lattice with the boundary rule). Returns their number;
+ * triangle_indices may be NULL. No device needed. */
+SPIRIT_API int SpiritB200_Topology_Triangles( State * state, int * triangle_indices, int idx_image ) SPIRIT_NOEXCEPT;
 #endif

@@ -317,3 +317,56 @@ def ddi_gradient_direct(spins, n_cells, mu_s=2.0, lattice_constant=1.0):
         sr = np.einsum("ij,ij->i", s, r)
         g[i] = -mu_s * mu_s * C * ((3 * sr / d ** 5)[:, None] * r - s / (d ** 3)[:, None]).sum(axis=0)
     return g
+
+
+def topological_charge_basis(spins, n_cells, bc, basis, ta, tb):
+    """The same for a cell with several basis atoms (lattice coordinates `basis`, atom 0 at the origin): Delaunay triangulation
+    of the basis atoms and the corners a+b, b, a of the cell (corners stretched by 10 %, Vectormath.cpp:516-548), every
+    triple whose circumcircle holds no other point; site order ib + NB (a + Na b). Returns (total, {sorted triple: charge})."""
+    import itertools
+    Na, Nb = n_cells
+    NB = len(basis)
+    ta, tb = np.asarray(ta, dtype=float), np.asarray(tb, dtype=float)
+    s = np.asarray(spins, dtype=float).reshape(Nb, Na, NB, 3)
+    pos = [b[0] * ta + b[1] * tb for b in basis]
+    k = 0.1
+    pts = [p.copy() for p in pos]
+    pts[0] = pts[0] - k * (ta + tb)
+    pts += [ta + tb + pos[0] + k * (ta + tb), tb + pos[0] - k * (ta - tb), ta + pos[0] + k * (ta - tb)]
+    triangles = []
+    for i, j, l in itertools.combinations(range(len(pts)), 3):
+        A, B, C = pts[i], pts[j], pts[l]
+        d = 2 * (A[0] * (B[1] - C[1]) + B[0] * (C[1] - A[1]) + C[0] * (A[1] - B[1]))
+        if abs(d) < 1e-12:
+            continue
+        ux = ((A @ A) * (B[1] - C[1]) + (B @ B) * (C[1] - A[1]) + (C @ C) * (A[1] - B[1])) / d
+        uy = ((A @ A) * (C[0] - B[0]) + (B @ B) * (A[0] - C[0]) + (C @ C) * (B[0] - A[0])) / d
+        centre = np.array([ux, uy])
+        r2 = (A - centre) @ (A - centre)
+        if all((pts[m] - centre) @ (pts[m] - centre) > r2 * (1 + 1e-9) for m in range(len(pts)) if m not in (i, j, l)):
+            nz = (A[0] - B[0]) * (A[1] - C[1]) - (A[1] - B[1]) * (A[0] - C[0])
+            triangles.append(((i, j, l), 1.0 if nz > 0 else -1.0))
+    total, per_triangle = 0.0, {}
+    for (verts, sign) in triangles:
+        for b in range(Nb):
+            for a in range(Na):
+                a_ok, b_ok = (a + 1 < Na or bc[0]), (b + 1 < Nb or bc[1])
+                an, bn = (a + 1) % Na, (b + 1) % Nb
+                sites, vecs = [], []
+                for v in verts:
+                    if v < NB:
+                        sites.append(v + NB * (a + Na * b)), vecs.append(s[b, a, v])
+                    elif v == NB + 2 and a_ok:
+                        sites.append(NB * (an + Na * b)), vecs.append(s[b, an, 0])
+                    elif v == NB + 1 and b_ok:
+                        sites.append(NB * (a + Na * bn)), vecs.append(s[bn, a, 0])
+                    elif v == NB and a_ok and b_ok:
+                        sites.append(NB * (an + Na * bn)), vecs.append(s[bn, an, 0])
+                    else:
+                        sites = None
+                        break
+                if sites:
+                    q = sign / (4 * np.pi) * solid_angle(*vecs)
+                    per_triangle[tuple(sorted(sites))] = q
+                    total += q
+    return total, per_triangle

@@ -6,6 +6,7 @@
 #include <Spirit/Quantities.h>
 #include <Spirit/Simulation.h>
 #include <Spirit/System.h>
+#include <spirit_b200.h>
 
 #include <cstring>
 
@@ -145,8 +146,6 @@ struct CellTriangulation
 };
 CellTriangulation cell_triangulation( const Geometry & g )
 {
-    if( g.n_cell_atoms != 1 )
-        throw std::runtime_error( "the topological charge is implemented for lattices with one basis atom" );
     const Vec3 ta = g.bravais_vectors[0] * g.lattice_constant, tb = g.bravais_vectors[1] * g.lattice_constant;
     const Vec3 p0 = g.positions()[0];
     const double k = 0.1; // the reference stretches the corners away from the centre
@@ -171,7 +170,129 @@ CellTriangulation cell_triangulation( const Geometry & g )
         t.sign[0] = orient( P0, Pa, Pab ), t.sign[1] = orient( P0, Pab, Pb );
     return t;
 }
+// Any number of basis atoms: Delaunay triangulation of the basis atoms of one cell and the corners a+b, b, a (ids NB,
+// NB + 1, NB + 2), corners stretched by 10 % as in the reference (Vectormath.cpp:516-548). Few points: every triple whose
+// circumcircle contains no other point is a triangle. One basis atom goes through cell_triangulation (the square cell is
+// degenerate: four points on one circle) and is expressed in the same vertex ids.
+struct CellTriangles
+{
+    int n = 0;
+    int vertex[16][3];
+    double sign[16];
+};
+CellTriangles cell_triangles( const Geometry & g )
+{
+    CellTriangles out;
+    const int NB = g.n_cell_atoms;
+    if( NB == 1 )
+    {
+        const CellTriangulation t = cell_triangulation( g );
+        const int ids[2][2][3]    = { { { NB + 2, NB + 1, NB }, { NB + 2, NB + 1, 0 } }, { { 0, NB + 2, NB }, { 0, NB, NB + 1 } } };
+        out.n                     = 2;
+        for( int k = 0; k < 2; ++k )
+        {
+            for( int c = 0; c < 3; ++c )
+                out.vertex[k][c] = ids[t.diag][k][c];
+            out.sign[k] = t.sign[k];
+        }
+        return out;
+    }
+    const Vec3 ta = g.bravais_vectors[0] * g.lattice_constant, tb = g.bravais_vectors[1] * g.lattice_constant;
+    const auto & positions = g.positions();
+    const Vec3 p0          = positions[0];
+    const double k         = 0.1;
+    std::vector<std::array<double, 2>> pts;
+    for( int i = 0; i < NB; ++i )
+        pts.push_back( { positions[i].x, positions[i].y } );
+    pts[0] = { p0.x - k * ( ta.x + tb.x ), p0.y - k * ( ta.y + tb.y ) };
+    pts.push_back( { ta.x + tb.x + p0.x + k * ( ta.x + tb.x ), ta.y + tb.y + p0.y + k * ( ta.y + tb.y ) } ); // a + b
+    pts.push_back( { tb.x + p0.x - k * ( ta.x - tb.x ), tb.y + p0.y - k * ( ta.y - tb.y ) } );               // b
+    pts.push_back( { ta.x + p0.x + k * ( ta.x - tb.x ), ta.y + p0.y + k * ( ta.y - tb.y ) } );               // a
+    const int n_pts = int( pts.size() );
+    double area_triangles = 0;
+    for( int i = 0; i < n_pts; ++i )
+        for( int j = i + 1; j < n_pts; ++j )
+            for( int l = j + 1; l < n_pts; ++l )
+            {
+                const auto &A = pts[i], &B = pts[j], &C = pts[l];
+                const double d = 2 * ( A[0] * ( B[1] - C[1] ) + B[0] * ( C[1] - A[1] ) + C[0] * ( A[1] - B[1] ) );
+                if( std::abs( d ) < 1e-12 )
+                    continue; // collinear
+                const double a2 = A[0] * A[0] + A[1] * A[1], b2 = B[0] * B[0] + B[1] * B[1], c2 = C[0] * C[0] + C[1] * C[1];
+                const double ux = ( a2 * ( B[1] - C[1] ) + b2 * ( C[1] - A[1] ) + c2 * ( A[1] - B[1] ) ) / d;
+                const double uy = ( a2 * ( C[0] - B[0] ) + b2 * ( A[0] - C[0] ) + c2 * ( B[0] - A[0] ) ) / d;
+                const double r2 = ( A[0] - ux ) * ( A[0] - ux ) + ( A[1] - uy ) * ( A[1] - uy );
+                bool empty      = true;
+                for( int m = 0; m < n_pts && empty; ++m )
+                    if( m != i && m != j && m != l )
+                        empty = ( pts[m][0] - ux ) * ( pts[m][0] - ux ) + ( pts[m][1] - uy ) * ( pts[m][1] - uy ) > r2 * ( 1 + 1e-9 );
+                if( !empty )
+                    continue;
+                if( out.n >= 16 )
+                    throw std::runtime_error( "topological charge: too many triangles per cell" );
+                out.vertex[out.n][0] = i, out.vertex[out.n][1] = j, out.vertex[out.n][2] = l;
+                // orientation of the triangle in this vertex order: z of (p0 - p1) x (p0 - p2)
+                const double nz = ( A[0] - B[0] ) * ( A[1] - C[1] ) - ( A[1] - B[1] ) * ( A[0] - C[0] );
+                out.sign[out.n] = nz < 0 ? -1.0 : 1.0;
+                area_triangles += 0.5 * std::abs( nz );
+                ++out.n;
+            }
+    // a triangulation of the stretched parallelogram covers it exactly; anything else is a degenerate (co-circular) cell
+    const auto &Q0 = pts[0], &Qab = pts[NB], &Qb = pts[NB + 1], &Qa = pts[NB + 2];
+    const double area_cell = 0.5 * std::abs( ( Qa[0] - Q0[0] ) * ( Qab[1] - Q0[1] ) - ( Qa[1] - Q0[1] ) * ( Qab[0] - Q0[0] ) )
+                             + 0.5 * std::abs( ( Qab[0] - Q0[0] ) * ( Qb[1] - Q0[1] ) - ( Qab[1] - Q0[1] ) * ( Qb[0] - Q0[0] ) );
+    if( std::abs( area_triangles - area_cell ) > 1e-6 * area_cell )
+        throw std::runtime_error( "topological charge: the basis cell has no unique Delaunay triangulation (or a basis atom lies outside the cell)" );
+    return out;
+}
+// site index of vertex `id` of the cell (a, b), or -1 when its translation is not allowed (Vectormath.cpp:577-606)
+int triangle_site( int id, int NB, int a, int b, int Na, int Nb, const std::array<int, 3> & bc )
+{
+    const bool a_ok = a + 1 < Na || bc[0], b_ok = b + 1 < Nb || bc[1];
+    if( id < NB )
+        return id + NB * ( a + Na * b );
+    if( id == NB + 2 )
+        return a_ok ? NB * ( ( a + 1 ) % Na + Na * b ) : -1;
+    if( id == NB + 1 )
+        return b_ok ? NB * ( a + Na * ( ( b + 1 ) % Nb ) ) : -1;
+    return a_ok && b_ok ? NB * ( ( a + 1 ) % Na + Na * ( ( b + 1 ) % Nb ) ) : -1;
+}
+// all triangles that count, reference order (triangle of the cell outermost, then b, then a): 3 site indices each
+std::vector<std::array<int, 4>> counted_triangles( const Geometry & g, const std::array<int, 3> & bc, const CellTriangles & t )
+{
+    std::vector<std::array<int, 4>> out; // site0, site1, site2, index into the density array [k][b][a]
+    const int Na = g.n_cells[0], Nb = g.n_cells[1], NB = g.n_cell_atoms;
+    for( int k = 0; k < t.n; ++k )
+        for( int b = 0; b < Nb; ++b )
+            for( int a = 0; a < Na; ++a )
+            {
+                const int s0 = triangle_site( t.vertex[k][0], NB, a, b, Na, Nb, bc ), s1 = triangle_site( t.vertex[k][1], NB, a, b, Na, Nb, bc ),
+                          s2 = triangle_site( t.vertex[k][2], NB, a, b, Na, Nb, bc );
+                if( s0 >= 0 && s1 >= 0 && s2 >= 0 )
+                    out.push_back( { s0, s1, s2, ( k * Nb + b ) * Na + a } );
+            }
+    return out;
+}
 } // namespace
+
+// Host-side probe (include/spirit_b200.h): the triangles the topological charge is summed over; no device needed
+int SpiritB200_Topology_Triangles( State * state, int * triangle_indices, int idx_image ) noexcept
+{
+    int idx_chain = -1;
+    try
+    {
+        auto image = resolve( state, idx_image, idx_chain ).image;
+        if( image->geometry->dimensionality != 2 )
+            return 0;
+        const auto tris = counted_triangles( *image->geometry, image->hamiltonian->boundary_conditions, cell_triangles( *image->geometry ) );
+        if( triangle_indices )
+            for( std::size_t i = 0; i < tris.size(); ++i )
+                for( int c = 0; c < 3; ++c )
+                    triangle_indices[3 * i + c] = tris[i][c];
+        return int( tris.size() );
+    }
+    SB_API_CATCH_RET( -1 )
+}
 
 // Quantities.cpp:62-87
 float Quantity_Get_Topological_Charge( State * state, int idx_image, int idx_chain ) noexcept
@@ -180,6 +301,12 @@ try
     auto image = resolve( state, idx_image, idx_chain ).image;
     if( image->geometry->dimensionality != 2 )
         return 0;
+    if( image->geometry->n_cell_atoms > 1 )
+    {
+        const CellTriangles t = cell_triangles( *image->geometry );
+        image->sync_to_device();
+        return float( image->device().topological_charge_table( t.n, t.vertex, t.sign, nullptr ) );
+    }
     const CellTriangulation t = cell_triangulation( *image->geometry );
     image->sync_to_device();
     return float( image->device().topological_charge( t.diag, t.sign[0], t.sign[1], nullptr ) );
@@ -195,6 +322,24 @@ try
     const Geometry & g = *image->geometry;
     if( g.dimensionality != 2 )
         return 0;
+    if( g.n_cell_atoms > 1 )
+    {
+        const CellTriangles t = cell_triangles( g );
+        const auto tris       = counted_triangles( g, image->hamiltonian->boundary_conditions, t );
+        if( charge_density && triangle_indices )
+        {
+            std::vector<double> all( std::size_t( t.n ) * g.n_cells[0] * g.n_cells[1] );
+            image->sync_to_device();
+            image->device().topological_charge_table( t.n, t.vertex, t.sign, all.data() );
+            for( std::size_t i = 0; i < tris.size(); ++i )
+            {
+                charge_density[i] = float( all[std::size_t( tris[i][3] )] );
+                for( int c = 0; c < 3; ++c )
+                    triangle_indices[3 * i + c] = tris[i][c];
+            }
+        }
+        return int( tris.size() );
+    }
     const CellTriangulation t = cell_triangulation( g );
     const int Na = g.n_cells[0], Nb = g.n_cells[1];
     const auto & bc = image->hamiltonian->boundary_conditions;

@@ -841,6 +841,39 @@ double DeviceImage::topological_charge( int diag, double sign0, double sign1, do
     return b.h_scalars[6];
 }
 
+double DeviceImage::topological_charge_table( int n, const int ( *vertex )[3], const double * sign, double * density_host )
+{
+    auto & b        = *buf_;
+    const int cells = stencil_.Na * stencil_.Nb;
+    const int nb    = ( cells + BLOCK_THREADS - 1 ) / BLOCK_THREADS;
+    if( n < 1 || n > 16 )
+        throw std::runtime_error( "spirit_b200: topological charge: unsupported number of triangles per cell" );
+    TopologyTable t{};
+    t.n = n;
+    for( int k = 0; k < n; ++k )
+    {
+        for( int c = 0; c < 3; ++c )
+            t.vertex[k][c] = vertex[k][c];
+        t.sign[k] = sign[k];
+    }
+    double *density = nullptr, *partials = nullptr;
+    SB_CUDA_CHECK( cudaMalloc( &partials, std::size_t( nb ) * sizeof( double ) ) );
+    if( density_host )
+        SB_CUDA_CHECK( cudaMalloc( &density, std::size_t( n ) * cells * sizeof( double ) ) );
+    k_topological_charge_table<<<nb, BLOCK_THREADS, 0, b.stream>>>( stencil_, b.spins.c(), t, density, partials );
+    k_reduce_sum<<<1, BLOCK_THREADS, 0, b.stream>>>( partials, nb, b.scalars + 6 );
+    launches_ += 2;
+    SB_CUDA_CHECK( cudaGetLastError() );
+    SB_CUDA_CHECK( cudaMemcpyAsync( b.h_scalars + 6, b.scalars + 6, sizeof( double ), cudaMemcpyDeviceToHost, b.stream ) );
+    if( density_host )
+        SB_CUDA_CHECK( cudaMemcpyAsync( density_host, density, std::size_t( n ) * cells * sizeof( double ), cudaMemcpyDeviceToHost, b.stream ) );
+    SB_CUDA_CHECK( cudaStreamSynchronize( b.stream ) );
+    cudaFree( partials );
+    if( density )
+        cudaFree( density );
+    return b.h_scalars[6];
+}
+
 // ---------------------------------------------------------------------------------------------
 void DeviceImage::ensure_work_fields( int solver )
 {

@@ -581,5 +581,72 @@ static __global__ void __launch_bounds__( BLOCK_THREADS ) k_topological_charge(
         partials[blockIdx.x] = v;
 }
 
+// The same for any number of basis atoms: the triangles of one cell come as a table (Delaunay triangulation of the basis
+// atoms and the three neighbouring corners of the cell, made on the host as in Vectormath.cpp:516-575). Vertex v < NB is
+// basis atom v of the cell (a, b); NB + 2 / NB + 1 / NB are atom 0 of the cells (a+1, b) / (a, b+1) / (a+1, b+1), which
+// count only when that translation stays inside the lattice or is allowed by the boundary conditions.
+struct TopologyTable
+{
+    int n;
+    int vertex[16][3];
+    double sign[16];
+};
+static __global__ void __launch_bounds__( BLOCK_THREADS ) k_topological_charge_table(
+    const __grid_constant__ StencilParams p, ConstField3 s, const __grid_constant__ TopologyTable t, double * __restrict__ density,
+    double * __restrict__ partials )
+{
+    const int cell  = blockIdx.x * blockDim.x + threadIdx.x;
+    const int cells = p.Na * p.Nb;
+    double sum      = 0;
+    if( cell < cells )
+    {
+        const int a = cell % p.Na, b = cell / p.Na;
+        const bool a_ok = a + 1 < p.Na || p.bc[0], b_ok = b + 1 < p.Nb || p.bc[1];
+        const int an = ( a + 1 ) % p.Na, bn = ( b + 1 ) % p.Nb;
+        const std::size_t plane = std::size_t( p.plane_stride ) * p.halo;
+        for( int k = 0; k < t.n; ++k )
+        {
+            bool valid = true;
+            D3 v[3];
+            for( int c = 0; c < 3; ++c )
+            {
+                const int id = t.vertex[k][c];
+                std::size_t site;
+                if( id < p.NB )
+                    site = std::size_t( id ) + std::size_t( p.NB ) * ( a + std::size_t( p.Na ) * b );
+                else if( id == p.NB + 2 )
+                {
+                    valid = valid && a_ok;
+                    site  = std::size_t( p.NB ) * ( an + std::size_t( p.Na ) * b );
+                }
+                else if( id == p.NB + 1 )
+                {
+                    valid = valid && b_ok;
+                    site  = std::size_t( p.NB ) * ( a + std::size_t( p.Na ) * bn );
+                }
+                else
+                {
+                    valid = valid && a_ok && b_ok;
+                    site  = std::size_t( p.NB ) * ( an + std::size_t( p.Na ) * bn );
+                }
+                v[c] = load3( s, plane + site );
+            }
+            double q = 0;
+            if( valid )
+            {
+                const double x = dot3( v[0], cross3( v[1], v[2] ) );
+                const double y = 1 + dot3( v[0], v[1] ) + dot3( v[0], v[2] ) + dot3( v[1], v[2] );
+                q              = t.sign[k] * ( 1.0 / ( 4.0 * 3.14159265358979323846 ) ) * 2 * atan2( x, y );
+            }
+            if( density )
+                density[std::size_t( k ) * cells + cell] = q;
+            sum += q;
+        }
+    }
+    const double total = block_sum( sum );
+    if( threadIdx.x == 0 )
+        partials[blockIdx.x] = total;
+}
+
 } // namespace dev
 } // namespace sb

@@ -109,6 +109,8 @@ public:
     void magnetization( double m[3], bool weighted );
     // topological charge of the plane c = 0 (one basis atom); density_host (nullable): [2][Na*Nb] charges per triangle
     double topological_charge( int diag, double sign0, double sign1, double * density_host );
+    // any basis: n triangles per cell, vertex ids as in k_topological_charge_table; density_host (nullable): [n][Na*Nb]
+    double topological_charge_table( int n, const int ( *vertex )[3], const double * sign, double * density_host );
 
     // n iterations of an LLG solver; if `hook` the last iteration also produces the quantities of
     // Method_LLG::Hook_Post_Iteration (Method_LLG.cpp:246-301) and the effective field buffer.

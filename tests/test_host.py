@@ -98,3 +98,36 @@ def test_setters_and_getters_round_trip(cfg, product, oracle):
                      lib.Parameters_LLG_Get_Convergence(x.state, -1, -1), x.pairs(0)[1].tolist(), x.pairs(1)[2].tolist()))
         x.close()
     assert vals[0] == vals[1]
+
+
+TOPOLOGY_CASES = [
+    ("solvers", None, {"n_basis_cells": "6 5 1", "boundary_conditions": "0 0 0"}),
+    ("solvers", None, {"n_basis_cells": "6 5 1", "boundary_conditions": "1 1 0"}),
+    ("cubic256", None, {"n_basis_cells": "6 5 1", "bravais_lattice": "hex2d", "boundary_conditions": "1 0 0"}),
+    ("cubic256", ["basis", "2", "0 0 0", "0.333 0.333 0.0"], {"n_basis_cells": "5 4 1", "bravais_lattice": "hex2d", "boundary_conditions": "0 0 0"}),
+    ("cubic256", ["basis", "2", "0 0 0", "0.333 0.333 0.0"], {"n_basis_cells": "5 4 1", "bravais_lattice": "hex2d", "boundary_conditions": "1 1 0"}),
+    ("cubic256", ["basis", "2", "0 0 0", "0.5 0.5 0.0"], {"n_basis_cells": "4 3 1", "bravais_lattice": "sc", "boundary_conditions": "1 0 0"}),
+    ("cubic256", ["basis", "3", "0 0 0", "0.5 0.2 0.0", "0.2 0.6 0"], {"n_basis_cells": "4 3 1", "bravais_lattice": "sc", "boundary_conditions": "0 0 0"}),
+]
+
+
+@pytest.mark.parametrize("preset,block,overrides", TOPOLOGY_CASES)
+def test_topological_charge_triangles_match_reference(tmp_path, product, oracle, preset, block, overrides):
+    """the triangles the topological charge is summed over (Delaunay triangulation of the basis cell + boundary rule,
+    Vectormath.cpp:504-631) -- host side, no device: the same set of site triples as the reference uses"""
+    import ctypes
+    from tests import cfgs
+    path = tmp_path / "t.cfg"
+    path.write_text(cfgs.render(preset, block=block, **overrides))
+    p, o = S.Session(product, str(path)), S.Session(oracle, str(path))
+    n_o = o.lib.Quantity_Get_Topological_Charge_Density(o.state, None, None, -1, -1)
+    q, tri_o = (ctypes.c_float * n_o)(), (ctypes.c_int * (3 * n_o))()
+    o.lib.Quantity_Get_Topological_Charge_Density(o.state, q, tri_o, -1, -1)
+    n_p = p.lib.SpiritB200_Topology_Triangles(p.state, None, -1)
+    assert n_p == n_o and n_o > 0
+    tri_p = (ctypes.c_int * (3 * n_p))()
+    assert p.lib.SpiritB200_Topology_Triangles(p.state, tri_p, -1) == n_p
+    ref = sorted(tuple(sorted(map(int, r))) for r in np.array(tri_o).reshape(-1, 3))
+    got = sorted(tuple(sorted(map(int, r))) for r in np.array(tri_p).reshape(-1, 3))
+    assert got == ref
+    p.close(), o.close()

@@ -160,3 +160,24 @@ def test_restatement_direct_dipolar_sum_matches_compiled_reference(cfg, oracle):
         g = R.ddi_gradient_direct(s, (5, 4, 3), mu_s=2.0)
         assert np.abs(g - g_ref).max() <= 1e-12 * np.abs(g_ref).max()
         o.close()
+
+
+@pytest.mark.parametrize("lattice,block,basis,bc", [
+    ("hex2d", ["basis", "2", "0 0 0", "0.333 0.333 0.0"], [(0, 0), (0.333, 0.333)], "1 1 0"),
+    ("hex2d", ["basis", "2", "0 0 0", "0.333 0.333 0.0"], [(0, 0), (0.333, 0.333)], "0 0 0"),
+    ("sc", ["basis", "3", "0 0 0", "0.5 0.2 0.0", "0.2 0.6 0"], [(0, 0), (0.5, 0.2), (0.2, 0.6)], "1 0 0")])
+def test_restatement_topological_charge_with_basis_matches_compiled_reference(tmp_path, oracle, lattice, block, basis, bc):
+    from tests import cfgs
+    path = tmp_path / "b.cfg"
+    path.write_text(cfgs.render("cubic256", block=block, n_basis_cells="8 6 1", bravais_lattice=lattice, boundary_conditions=bc))
+    o = S.Session(oracle, str(path))
+    periodic = [int(v) for v in bc.split()][:2]
+    tb = (0.5, 0.5 * np.sqrt(3.0)) if lattice == "hex2d" else (0.0, 1.0)
+    for make in (lambda x: (x.plus_z(), x.skyrmion(2.0, phase=-90.0)), lambda x: x.random()):
+        make(o)
+        total, per_triangle = R.topological_charge_basis(o.spins(), (8, 6), periodic, basis, (1.0, 0.0), tb)
+        ref = _oracle_density(o)
+        assert set(ref) == set(per_triangle)
+        assert max(abs(per_triangle[t] - ref[t]) for t in ref) < 1e-6
+        assert abs(total - o.lib.Quantity_Get_Topological_Charge(o.state, -1, -1)) < 2e-6 * max(1.0, abs(total))
+    o.close()
