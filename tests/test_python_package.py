@@ -67,3 +67,31 @@ def test_reference_python_package_runs_on_this_library(tmp_path, cfg, product):
     env = dict(os.environ, PYTHONPATH=str(tmp_path / "site"))
     r = subprocess.run([sys.executable, str(driver), cfg("solvers", n_basis_cells="7 5 1"), str(out)], env=env, capture_output=True, text=True, timeout=300)
     assert r.returncode == 0 and "PYTHON_PACKAGE_OK" in r.stdout, (r.stdout[-2000:], r.stderr[-3000:])
+
+
+REF_TESTS = "/root/reference/core/python/test"
+# the reference's own unittest files that need no compute (the others -- system, quantities -- evaluate energies /
+# magnetisation and need the device; simulation.py only checks that the calls return)
+HOST_ONLY = ["state", "configuration", "constants", "geometry", "log", "parameters", "chain", "transition", "hamiltonian", "io_test", "simulation"]
+
+
+@pytest.mark.skipif(not os.path.isdir(REF_TESTS), reason="reference tree not mounted")
+@pytest.mark.parametrize("name", HOST_ONLY)
+def test_reference_python_unittests_pass_on_this_library(tmp_path, name):
+    """core/python/test/<name>.py, unchanged, with this library behind the unchanged package"""
+    core = tmp_path / "core"
+    (core / "python").mkdir(parents=True)
+    shutil.copytree(REF_PKG, core / "python" / "spirit")
+    shutil.copytree(REF_TESTS, core / "python" / "test")
+    shutil.copytree("/root/reference/core/test/input", core / "test" / "input")
+    pkg = core / "python" / "spirit"
+    shutil.copy(os.path.join(ROOT, "spirit_b200", "libSpirit.so"), pkg / "libSpirit.so")
+    (pkg / "scalar.py").write_text("import ctypes\nscalar = ctypes.c_double\n")
+    (pkg / "version.py").write_text('version_major = 2\nversion_minor = 2\nversion_patch = 0\nversion = "2.2.0"\nrevision = "spirit_b200"\n'
+                                    'version_full = "2.2.0 (spirit_b200)"\ncompiler = "nvcc"\ncompiler_version = ""\ncompiler_full = "nvcc"\n'
+                                    'scalartype = "double"\npinning = "OFF"\ndefects = "OFF"\ncuda = "ON"\nopenmp = "OFF"\nthreads = "OFF"\nfftw = "OFF"\n')
+    if not (pkg / "__init__.py").exists():
+        (pkg / "__init__.py").write_text("")
+    r = subprocess.run([sys.executable, str(core / "python" / "test" / (name + ".py"))], cwd=str(core), capture_output=True, text=True, timeout=300)
+    tail = (r.stdout + r.stderr)[-1500:]
+    assert r.returncode == 0 and "OK" in tail.splitlines()[-1], tail
