@@ -67,6 +67,21 @@ void read_spins( const ovf::File & file, int idx_in_file, Spin_System & image, i
             s.normalize();
     }
 }
+// image `idx_in_file` of a plain column file (Dataparser.cpp:23-51): rows idx nos .. (idx + 1) nos - 1, as many as there are
+void read_spins_columns( const std::vector<double> & rows, int idx_in_file, Spin_System & image )
+{
+    const std::size_t n_rows = rows.size() / 3, first = std::size_t( image.nos ) * std::size_t( std::max( idx_in_file, 0 ) );
+    for( int i = 0; i < image.nos && first + i < n_rows; ++i )
+        image.spins[i] = Vec3{ rows[3 * ( first + i )], rows[3 * ( first + i ) + 1], rows[3 * ( first + i ) + 2] };
+    for( int i = 0; i < image.nos; ++i )
+    {
+        Vec3 & s = image.spins[i];
+        if( s.norm() < 1e-5 )
+            s = Vec3{ 0, 0, 1 };
+        else
+            s.normalize();
+    }
+}
 } // namespace
 
 int IO_N_Images_In_File( State *, const char * file, int idx_image, int idx_chain ) noexcept
@@ -107,7 +122,14 @@ try
     if( !f.found )
         throw std::runtime_error( std::string( "Unable open file \"" ) + file + "\", are you sure it exists?" );
     if( !f.is_ovf )
-        throw std::runtime_error( std::string( "File \"" ) + file + "\" does not seem to be in valid OVF format. Message: " + f.message );
+    {
+        Log( Log_Level::Error, Log_Sender::API,
+             std::string( "File \"" ) + file + "\" does not seem to be in valid OVF format. Message: " + f.message
+                 + ". Will try to read as data column text format file.",
+             idx_image, idx_chain );
+        read_spins_columns( io::read_column_text( file ), idx_image_infile, *image );
+        return;
+    }
     read_spins( f, idx_image_infile, *image, idx_image, idx_chain );
     Log( Log_Level::Info, Log_Sender::API, std::string( "Read image from file \"" ) + file + "\"", idx_image, idx_chain );
 }
@@ -154,9 +176,14 @@ void IO_Chain_Read( State * state, const char * file, int start_image_infile, in
         ovf::File f( file );
         if( !f.found )
             throw std::runtime_error( std::string( "Unable open file \"" ) + file + "\", are you sure it exists?" );
+        std::vector<double> columns; // plain column file: nos rows per image (Dataparser.cpp:53-110)
         if( !f.is_ovf )
-            throw std::runtime_error( std::string( "IO_Chain_Read: File \"" ) + file + "\" is not OVF. Message: " + f.message );
-        const int noi_infile = f.n_segments;
+        {
+            Log( Log_Level::Warning, Log_Sender::API, std::string( "IO_Chain_Read: File \"" ) + file + "\" seems to not be OVF. Trying to read column data",
+                 insert_idx, idx_chain );
+            columns = io::read_column_text( file );
+        }
+        const int noi_infile = f.is_ovf ? f.n_segments : int( columns.size() / 3 / std::size_t( chain->images[0]->nos ) );
         if( start_image_infile < 0 )
             start_image_infile = 0;
         if( end_image_infile < 0 )
@@ -188,7 +215,13 @@ void IO_Chain_Read( State * state, const char * file, int start_image_infile, in
             {
                 // (the reference's loop bounds, IO.cpp:523: images insert_idx .. noi_to_read - 1)
                 for( int i = insert_idx; i < noi_to_read; ++i )
-                    read_spins( f, start_image_infile++, *chain->images[i], i, idx_chain );
+                {
+                    if( f.is_ovf )
+                        read_spins( f, start_image_infile, *chain->images[i], i, idx_chain );
+                    else
+                        read_spins_columns( columns, start_image_infile, *chain->images[i] );
+                    ++start_image_infile;
+                }
             }
             catch( ... )
             {

@@ -1,11 +1,13 @@
 #include "io.hpp"
 
 #include <algorithm>
+#include <cctype>
 #include <chrono>
 #include <cstdio>
 #include <cstdlib>
 #include <ctime>
 #include <fstream>
+#include <stdexcept>
 
 namespace sb
 {
@@ -51,6 +53,40 @@ std::string current_date_time()
     char buf[64];
     std::strftime( buf, sizeof( buf ), "%Y-%m-%d_%H-%M-%S", &parts );
     return buf;
+}
+
+std::vector<double> read_column_text( const std::string & file )
+{
+    std::ifstream in( file );
+    if( !in )
+        throw std::runtime_error( "Unable open file \"" + file + "\", are you sure it exists?" );
+    std::vector<double> rows;
+    std::string line;
+    while( std::getline( in, line ) )
+    {
+        const std::size_t remark = line.find( '#' );
+        if( remark != std::string::npos )
+            line.erase( remark );
+        const char * p = line.c_str();
+        double v[3];
+        int have = 0;
+        while( *p && have < 3 )
+        {
+            while( *p && ( std::isspace( static_cast<unsigned char>( *p ) ) || *p == ',' ) )
+                ++p;
+            if( !*p )
+                break;
+            char * end = nullptr;
+            v[have]    = std::strtod( p, &end );
+            if( end == p )
+                break;
+            ++have;
+            p = end;
+        }
+        if( have == 3 )
+            rows.insert( rows.end(), v, v + 3 );
+    }
+    return rows;
 }
 
 std::string centred( const std::string & text, std::size_t width )

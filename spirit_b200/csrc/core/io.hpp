@@ -24,6 +24,10 @@ ovf::Segment spin_segment( const Spin_System & system, const std::string & comme
 // "%Y-%m-%d_%H-%M-%S" of now (local time)
 std::string current_date_time();
 
+// Plain column files (no OVF header; core/src/io/Dataparser.cpp:23-51): everything after a '#' is a remark, a data line holds
+// three numbers separated by blanks and / or commas. Returns the rows [n][3] of the whole file.
+std::vector<double> read_column_text( const std::string & file );
+
 // Energy tables (core/src/io/Datawriter.cpp:116-234): fmt's "{:^20}" / "{:^20.10f}" columns
 std::string centred( const std::string & text, std::size_t width = 20 );
 std::string fixed10( double v );
