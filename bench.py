@@ -244,23 +244,42 @@ def run_b200(args):
         peak, peak_src = float(json.load(open(peaks_path))["hbm_gbs"]), "MEASURED_PEAKS.json hbm_gbs"
     else:
         peak, peak_src = FALLBACK_HBM_GBS, "fallback (B200_PROFILING.md)"
-    k = 1  # stage 2 moves 72 of the 120 B
-    achieved = BYTES_STAGE[k] * nos / (stage_ms[k] * 1e-3) / 1e9
-    roofline = {
-        "bound": "hbm", "kernel": "k_sc6_stage<Depondt,2,...> (gradient(s) recomputed + gradient(s') + virtual forces + Rodrigues rotation)",
-        "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
-        "peak_source": peak_src, "algorithmic_bytes_per_launch": BYTES_STAGE[k] * nos,
-        "stage_ms": [stage_ms[0], stage_ms[1]],
-        "stage1": {"achieved": BYTES_STAGE[0] * nos / (stage_ms[0] * 1e-3) / 1e9, "bytes_per_spin": BYTES_STAGE[0]},
-        "step": {"achieved": BYTES_PER_SPIN_STEP * nos * args.steps / (ms * 1e-3) / 1e9 / world * world,
-                 "bytes_per_spin_step": BYTES_PER_SPIN_STEP},
-    }
+    fused = p.step_variant(S.SOLVER_DEPONDT) == 2
+    if fused:
+        # ONE kernel per iteration (sc6_fused.cuh). Algorithmic bytes per launch: SURVEY.md 8d's 120 B per spin-step (the
+        # two-pass model the target is quoted on) x the spin-steps one launch processes. The fused kernel's own minimum
+        # is 48 B per spin-step (read s, write s_new): `achieved_min_traffic` states the same time against that figure.
+        achieved = BYTES_PER_SPIN_STEP * nos / (stage_ms[0] * 1e-3) / 1e9
+        roofline = {
+            "bound": "hbm", "kernel": "k_sc6_fused<Depondt,...> (predictor + corrector of one iteration in one launch: gradient(s), "
+                                      "noise, virtual force, rotation, s' through shared memory, gradient(s'), rotation)",
+            "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
+            "peak_source": peak_src, "algorithmic_bytes_per_launch": BYTES_PER_SPIN_STEP * nos,
+            "model": "SURVEY.md 8d: 120 B per spin-step (R s | W s' | R s, s' | W s_new)",
+            "kernel_ms": stage_ms[0],
+            "min_traffic": {"bytes_per_spin_step": 48.0, "achieved": 48.0 * nos / (stage_ms[0] * 1e-3) / 1e9,
+                            "frac": 48.0 * nos / (stage_ms[0] * 1e-3) / 1e9 / peak,
+                            "note": "the fused kernel reads s once and writes s_new once; s' never leaves the SM"},
+            "step": {"bytes_per_spin_step": BYTES_PER_SPIN_STEP},
+        }
+    else:
+        k = 1  # stage 2 moves 72 of the 120 B
+        achieved = BYTES_STAGE[k] * nos / (stage_ms[k] * 1e-3) / 1e9
+        roofline = {
+            "bound": "hbm", "kernel": "k_sc6_stage<Depondt,2,...> (gradient(s) recomputed + gradient(s') + virtual forces + Rodrigues rotation)",
+            "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
+            "peak_source": peak_src, "algorithmic_bytes_per_launch": BYTES_STAGE[k] * nos,
+            "stage_ms": [stage_ms[0], stage_ms[1]],
+            "stage1": {"achieved": BYTES_STAGE[0] * nos / (stage_ms[0] * 1e-3) / 1e9, "bytes_per_spin": BYTES_STAGE[0]},
+            "step": {"bytes_per_spin_step": BYTES_PER_SPIN_STEP},
+        }
     roofline["step"]["achieved"] = BYTES_PER_SPIN_STEP * (value / world) / 1e9
     roofline["step"]["frac"] = roofline["step"]["achieved"] / peak
     traffic_path = os.path.join(ROOT, "profiles", "traffic.json")
     if os.path.exists(traffic_path):
         try:
-            roofline["traffic"] = json.load(open(traffic_path)).get("k_sc6_stage_depondt_2_bytes_per_launch_256")
+            roofline["traffic"] = json.load(open(traffic_path)).get(
+                "k_sc6_fused_depondt_bytes_per_launch_256" if fused else "k_sc6_stage_depondt_2_bytes_per_launch_256")
             if cells != (256, 256, 256):
                 roofline["traffic"] = None
         except (ValueError, OSError):

@@ -47,6 +47,10 @@ SPIRIT_API unsigned long long SpiritB200_Kernel_Launches( State * state, int idx
 /* Which stage kernels serve the image's Hamiltonian: 1 the nearest-neighbour marching kernels, 0 the generic gather
  * kernels; < 0 on error. No counterpart in the reference (its CUDA backend has one kernel per term). */
 SPIRIT_API int SpiritB200_Stencil_Variant( State * state, int idx_image ) SPIRIT_NOEXCEPT;
+/* Which kernels run one iteration of `solver_type` on the image with its current Hamiltonian and LLG parameters:
+ * 2 ONE fused predictor + corrector kernel per iteration (Depondt / Heun / SIB on the nearest-neighbour stencil: spins read
+ * once and written once), 1 one marching kernel per solver stage, 0 the generic gather kernels; < 0 on error. */
+SPIRIT_API int SpiritB200_Step_Variant( State * state, int solver_type, int idx_image ) SPIRIT_NOEXCEPT;
 /* Upload the image's host spins to HBM (and build the device tables) / download spins + effective field */
 SPIRIT_API int SpiritB200_Upload( State * state, int idx_image ) SPIRIT_NOEXCEPT;
 SPIRIT_API int SpiritB200_Download( State * state, int idx_image ) SPIRIT_NOEXCEPT;

@@ -17,13 +17,17 @@ for spec in sys.argv[1:]:
             pass
         elif k.startswith("SPIRIT_"):
             env[k] = v
+        elif k == "FUSED_LC":
+            env["SPIRIT_B200_FUSED_LC"] = v
         else:
             env["SPIRIT_B200_SC6_" + k] = v
     r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--steps", "100", "--warmup", "10", "--no-e2e", "--no-cpu-baseline"],
                        env=env, capture_output=True, text=True)
     try:
         d = json.loads([l for l in r.stdout.splitlines() if l.startswith("{")][-1])
-        print("%-50s %.4e spin-steps/s  %.4f ms/step  stages %s  frac %.3f" % (
-            spec, d["value"], d["ms_per_step"], ["%.4f" % x for x in d["roofline"]["stage_ms"]], d["roofline"]["step"]["frac"]), flush=True)
+        rf = d["roofline"]
+        kernels = rf["stage_ms"] if "stage_ms" in rf else [rf["kernel_ms"]]  # two-pass stages, or the one fused kernel
+        print("%-50s %.4e spin-steps/s  %.4f ms/step  kernel(s) %s ms  frac %.3f" % (
+            spec, d["value"], d["ms_per_step"], ["%.4f" % x for x in kernels], rf["step"]["frac"]), flush=True)
     except Exception as e:  # noqa: BLE001
         print(spec, "FAILED", e, r.stderr[-500:], flush=True)

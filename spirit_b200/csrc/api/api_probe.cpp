@@ -213,6 +213,28 @@ catch( ... )
     return 0;
 }
 
+int SpiritB200_Step_Variant( State * state, int solver_type, int idx_image ) noexcept
+try
+{
+    int idx_chain = -1;
+    auto image    = resolve( state, idx_image, idx_chain ).image;
+    ImageLock lock( *image );
+    auto & d = image->device();
+    d.set_hamiltonian( *image->hamiltonian );
+    if( solver_type >= dev::Solver_VP && solver_type <= dev::Solver_RK4 )
+    {
+        const dev::LLGParams l = Method_LLG::make_params( *image, solver_type );
+        if( d.fused_usable( solver_type, l ) )
+            return 2;
+    }
+    return d.stencil_variant();
+}
+catch( ... )
+{
+    handle_exception_api( __func__, idx_image );
+    return -1;
+}
+
 int SpiritB200_Stencil_Variant( State * state, int idx_image ) noexcept
 try
 {

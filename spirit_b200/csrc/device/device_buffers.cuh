@@ -4,6 +4,7 @@
 
 #include "kernels.cuh"
 #include "sc6.cuh"
+#include "sc6_fused.cuh"
 #include "runtime.hpp"
 
 #include <stdexcept>
@@ -85,6 +86,7 @@ int ddi_gradient( DDIPlan & plan, ConstField3 spins, Field3 g_ddi, cudaStream_t 
 struct DeviceBuffers
 {
     SC6Launch sc6;
+    FusedGeometry fused; // launch shape of the fused two-stage kernels (sc6_fused.cuh)
     cudaStream_t stream = nullptr;
     cudaEvent_t ev_start = nullptr, ev_stop = nullptr;
     // slab decomposition: halo exchanges run on their own stream so that they overlap the interior of a stage

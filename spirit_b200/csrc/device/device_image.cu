@@ -301,6 +301,36 @@ SC6Launch make_sc6_launch( const StencilParams & p )
     return L;
 }
 
+// Tiles and march length of the fused two-stage kernels: one CTA per SM; a c-segment of lc planes costs lc corrector
+// plane steps and lc + 2 predictor plane steps (~ 1.6 extra plane steps per segment); short segments fill the last wave.
+FusedGeometry make_fused_geometry( const StencilParams & p )
+{
+    FusedGeometry G;
+    const int gx = ( p.Na + FUSED_TX - 1 ) / FUSED_TX, gy = ( p.Nb + FUSED_TY - 1 ) / FUSED_TY;
+    int n_sm = 148, dev = 0;
+    if( cudaGetDevice( &dev ) == cudaSuccess )
+        cudaDeviceGetAttribute( &n_sm, cudaDevAttrMultiProcessorCount, dev );
+    int best_lc = p.nc_local;
+    double best = 1e300;
+    for( int nseg = 1; nseg <= p.nc_local; ++nseg )
+    {
+        const int lc = ( p.nc_local + nseg - 1 ) / nseg;
+        if( lc < 4 && p.nc_local >= 4 )
+            break;
+        const int segs     = ( p.nc_local + lc - 1 ) / lc;
+        const double waves = std::ceil( double( gx ) * gy * segs / n_sm );
+        const double cost  = waves * ( lc + 1.6 );
+        if( cost < best * ( 1 - 1e-9 ) )
+        {
+            best    = cost;
+            best_lc = lc;
+        }
+    }
+    G.lc   = std::max( 1, env_int( "SPIRIT_B200_FUSED_LC", best_lc ) );
+    G.grid = dim3( gx, gy, ( p.nc_local + G.lc - 1 ) / G.lc );
+    return G;
+}
+
 LaunchGeom make_geom( const StencilParams & p )
 {
     LaunchGeom lg;
@@ -340,11 +370,13 @@ DeviceImage::DeviceImage( const Geometry & g )
     b.plane_sites         = stencil_.Na * stencil_.NB * stencil_.Nb;
     b.n_storage           = std::size_t( stencil_.plane_stride ) * ( stencil_.nc_local + 2 * stencil_.halo );
     b.sc6             = make_sc6_launch( stencil_ );
+    b.fused           = make_fused_geometry( stencil_ );
     SB_CUDA_CHECK( cudaStreamCreateWithFlags( &b.stream, cudaStreamNonBlocking ) );
     SB_CUDA_CHECK( cudaEventCreate( &b.ev_start ) );
     SB_CUDA_CHECK( cudaEventCreate( &b.ev_stop ) );
     b.spins.allocate( b.n_storage );
-    SB_CUDA_CHECK( cudaMalloc( &b.partials, 4 * std::size_t( b.nblocks ) * sizeof( double ) ) );
+    const std::size_t fused_ctas = std::size_t( b.fused.grid.x ) * b.fused.grid.y * b.fused.grid.z;
+    SB_CUDA_CHECK( cudaMalloc( &b.partials, ( 4 * std::size_t( b.nblocks ) + 2 * fused_ctas ) * sizeof( double ) ) );
     SB_CUDA_CHECK( cudaMalloc( &b.scalars, 16 * sizeof( double ) ) );
     SB_CUDA_CHECK( cudaMemset( b.scalars, 0, 16 * sizeof( double ) ) );
     SB_CUDA_CHECK( cudaHostAlloc( &b.h_scalars, 16 * sizeof( double ), cudaHostAllocDefault ) );
@@ -596,6 +628,10 @@ void DeviceImage::set_hamiltonian( const Hamiltonian & ham )
         }
         const char * off = std::getenv( "SPIRIT_B200_GENERIC_STENCIL" ); // tests: force the generic gather kernels
         p.sc6            = ( ok && !( off && off[0] == '1' ) ) ? 1 : 0;
+    }
+    {
+        const char * off = std::getenv( "SPIRIT_B200_NO_FUSED" ); // tests / A-B runs: force the two-pass marching kernels
+        fused_disabled_  = off && off[0] == '1';
     }
 
     // Uniaxial anisotropy
@@ -909,6 +945,22 @@ int DeviceImage::stencil_variant() const
     return 1;
 }
 
+// The fused two-stage kernels (sc6_fused.cuh) serve Depondt, Heun and SIB on the nearest-neighbour stencil when nothing
+// global has to happen between predictor and corrector (no dipolar field) and the rare per-site terms are absent.
+bool DeviceImage::fused_usable( int solver, const LLGParams & l ) const
+{
+    if( fused_disabled_ || slab_ )
+        return false;
+    if( solver != Solver_Depondt && solver != Solver_Heun && solver != Solver_SIB )
+        return false;
+    const StencilParams & p = stencil_;
+    if( !p.sc6 || p.has_ddi || l.has_stt || l.has_tgrad )
+        return false;
+    if( p.sc6_axis[2] && p.Nc < 2 )
+        return false;
+    return true;
+}
+
 namespace
 {
 template<int SOLVER, int STAGE>
@@ -1044,7 +1096,34 @@ void DeviceImage::llg_iterate( int solver, LLGParams & llg, int n_iterations, bo
         a.xi = b.xi;
 
         compute_ddi_gradient( 0 );
-        if( solver == Solver_Depondt || solver == Solver_Heun || solver == Solver_SIB )
+        if( fused_usable( solver, llg ) )
+        {
+            // predictor and corrector in one launch: the spins are read once and written once (sc6_fused.cuh)
+            const int ncta = int( b.fused.grid.x * b.fused.grid.y * b.fused.grid.z );
+            FusedArgs fa{};
+            fa.s               = b.spins.c();
+            fa.out             = b.next.f();
+            fa.F_out           = b.F.f();
+            fa.energy_partials = b.partials;
+            fa.torque_partials = b.partials + ncta;
+            if( solver == Solver_Depondt )
+                sc6_fused_depondt( hk, b.sc6.spec, b.fused, b.stream, stencil_, llg, fa );
+            else if( solver == Solver_Heun )
+                sc6_fused_heun( hk, b.sc6.spec, b.fused, b.stream, stencil_, llg, fa );
+            else
+                sc6_fused_sib( hk, b.sc6.spec, b.fused, b.stream, stencil_, llg, fa );
+            ++launches_;
+            mark();
+            mark();
+            if( hk )
+            {
+                k_reduce_sum<<<1, BLOCK_THREADS, 0, b.stream>>>( b.partials, ncta, b.scalars + 4 );
+                k_reduce_max<<<1, BLOCK_THREADS, 0, b.stream>>>( b.partials + ncta, ncta, b.scalars + 5 );
+                launches_ += 2;
+            }
+            std::swap( b.spins, b.next );
+        }
+        else if( solver == Solver_Depondt || solver == Solver_Heun || solver == Solver_SIB )
         {
             a.out = b.pred.f();
             if( solver == Solver_Depondt )
@@ -1135,7 +1214,7 @@ void DeviceImage::llg_iterate( int solver, LLGParams & llg, int n_iterations, bo
         else
             throw std::runtime_error( "spirit_b200: solver id " + std::to_string( solver ) + " is not implemented" );
 
-        if( hk && solver != Solver_VP )
+        if( hk && solver != Solver_VP && !fused_usable( solver, llg ) )
         {
             k_reduce_sum<<<1, BLOCK_THREADS, 0, b.stream>>>( b.partials, b.nblocks, b.scalars + 4 );
             k_hook<<<b.nblocks, BLOCK_THREADS, 0, b.stream>>>(

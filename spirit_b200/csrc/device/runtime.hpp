@@ -142,6 +142,8 @@ public:
     // Which stage kernels serve this image: 1 nearest-neighbour marching kernels (sc6.cuh), 0 generic gather kernels.
     // Valid after the device tables are built.
     int stencil_variant() const;
+    // true: Depondt / Heun / SIB iterations of this image run as ONE fused predictor + corrector kernel (sc6_fused.cuh)
+    bool fused_usable( int solver, const LLGParams & l ) const;
 
     DeviceBuffers * buffers()
     {
@@ -176,6 +178,7 @@ private:
     bool vp_initialized_        = false;
     bool vp_prev_projected_     = false; // the last VP iteration ran a hook: F_prev is the projected force (in Fv)
     bool effective_field_in_Fv_ = false;
+    bool fused_disabled_        = false; // SPIRIT_B200_NO_FUSED=1 when the device tables were built
     std::vector<void *> * stage_events_ = nullptr; // when set, llg_iterate records an event after every stage kernel
     std::unique_ptr<OsoState, OsoStateDeleter> oso_; // fields and scalars of the OSO minimisers (device_oso.cu)
 };

@@ -150,7 +150,12 @@ __device__ __forceinline__ void sc6_axis_gradient( const StencilParams & p, cons
 //   start value: -mu_s B n (Zeeman, Hamiltonian_Heisenberg.cpp:768-783; zero without a field)
 //   on-site quadratic form: g += A s with A = -2 sum_k K_k n_k n_k^T (uniaxial anisotropies, :785-800)
 //   rare terms behind one uniform flag: cubic anisotropy (:802-820), precomputed dipolar field
-template<int SPEC>
+// RARE: how the rare terms (off-diagonal anisotropy elements, cubic anisotropy, dipolar field) are reached.
+//   0  two uniform tests (two-pass kernels)
+//   1  nested: the off-diagonal anisotropy elements sit behind the same flag as the others (sc6_extras includes
+//      sc6_aniso_full): one test in the common case (fused kernels)
+//   2  none: the caller guarantees !sc6_extras (plain march of the fused kernels: no branch inside the gradient)
+template<int SPEC, int RARE = 0>
 __device__ __forceinline__ D3 sc6_gradient(
     const StencilParams & p, const D3 & si, const D3 & xm, const D3 & xp, const D3 & bm, const D3 & bp, const D3 & cm,
     const D3 & cp, const double * __restrict__ ddi_plane, unsigned e )
@@ -163,14 +168,20 @@ __device__ __forceinline__ D3 sc6_gradient(
     g.x = fma( p.sc6_A[0], si.x, g.x );
     g.y = fma( p.sc6_A[1], si.y, g.y );
     g.z = fma( p.sc6_A[2], si.z, g.z );
-    if( !SB_SC6_NO_ANISO_FULL && p.sc6_aniso_full ) // off-diagonal elements: anisotropy axes that are not lattice axes
+    if( RARE == 0 && !SB_SC6_NO_ANISO_FULL && p.sc6_aniso_full ) // off-diagonal elements: anisotropy axes that are not lattice axes
     {
         g.x = fma( p.sc6_A[3], si.y, fma( p.sc6_A[4], si.z, g.x ) );
         g.y = fma( p.sc6_A[3], si.x, fma( p.sc6_A[5], si.z, g.y ) );
         g.z = fma( p.sc6_A[4], si.x, fma( p.sc6_A[5], si.y, g.z ) );
     }
-    if( !SB_SC6_NO_EXTRAS && p.sc6_extras )
+    if( RARE != 2 && !SB_SC6_NO_EXTRAS && p.sc6_extras )
     {
+        if( RARE == 1 && p.sc6_aniso_full )
+        {
+            g.x = fma( p.sc6_A[3], si.y, fma( p.sc6_A[4], si.z, g.x ) );
+            g.y = fma( p.sc6_A[3], si.x, fma( p.sc6_A[5], si.z, g.y ) );
+            g.z = fma( p.sc6_A[4], si.x, fma( p.sc6_A[5], si.y, g.z ) );
+        }
         if( p.has_cubic )
         {
             const double k = -2.0 * p.K4[0];
@@ -192,7 +203,7 @@ __device__ __forceinline__ D3 sc6_gradient(
 // Virtual force from the gradient g = -F (Method_LLG.cpp:131-226), signs folded into nc1 = -dtg/mu_s, nc2 = alpha nc1:
 //   dynamics:      Fv = nc1 g + xi + s x (nc2 g + alpha xi)
 //   minimisation:  Fv = -dtg' s x g
-template<int MODE>
+template<int MODE, bool WITH_STT = true>
 __device__ __forceinline__ D3 sc6_virtual_force( const LLGParams & l, const D3 & s, const D3 & g, const D3 & xi )
 {
     D3 w, fv;
@@ -218,7 +229,7 @@ __device__ __forceinline__ D3 sc6_virtual_force( const LLGParams & l, const D3 &
     fv.x = fma( s.y, w.z, fma( -s.z, w.y, fv.x ) );
     fv.y = fma( s.z, w.x, fma( -s.x, w.z, fv.y ) );
     fv.z = fma( s.x, w.y, fma( -s.y, w.x, fv.z ) );
-    if( !SB_SC6_NO_STT && MODE != SC6_MINIMISE && l.has_stt )
+    if( WITH_STT && !SB_SC6_NO_STT && MODE != SC6_MINIMISE && l.has_stt )
     {
         const D3 pol = make_d3( l.stt_pol[0], l.stt_pol[1], l.stt_pol[2] );
         const D3 pxs = cross3( pol, s );

@@ -34,13 +34,15 @@ __device__ __forceinline__ D3 make_d3( double x, double y, double z )
     r.z = z;
     return r;
 }
+// Explicit fused multiply-adds in a fixed order: which product the compiler would contract into an FMA depends on the
+// code around the call, and every kernel (and every code path inside a kernel) must produce the same bits for a site.
 __device__ __forceinline__ double dot3( const D3 & a, const D3 & b )
 {
-    return a.x * b.x + a.y * b.y + a.z * b.z;
+    return fma( a.z, b.z, fma( a.y, b.y, a.x * b.x ) );
 }
 __device__ __forceinline__ D3 cross3( const D3 & a, const D3 & b )
 {
-    return make_d3( a.y * b.z - a.z * b.y, a.z * b.x - a.x * b.z, a.x * b.y - a.y * b.x );
+    return make_d3( fma( a.y, b.z, -( a.z * b.y ) ), fma( a.z, b.x, -( a.x * b.z ) ), fma( a.x, b.y, -( a.y * b.x ) ) );
 }
 
 // Field layout in HBM: "AoSoA-32". Sites are grouped in blocks of 32 consecutive storage indices; a block stores

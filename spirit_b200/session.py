@@ -293,5 +293,9 @@ class Session:
         """1: nearest-neighbour marching kernels, 0: generic gather kernels (include/spirit_b200.h)"""
         return self.lib.SpiritB200_Stencil_Variant(self.state, idx_image)
 
+    def step_variant(self, solver, idx_image=-1):
+        """2: one fused predictor + corrector kernel per iteration, 1: one marching kernel per stage, 0: generic gather"""
+        return self.lib.SpiritB200_Step_Variant(self.state, solver, idx_image)
+
     def kernel_launches(self, idx_image=-1):
         return self.lib.SpiritB200_Kernel_Launches(self.state, idx_image)

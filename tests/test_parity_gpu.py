@@ -24,11 +24,13 @@ def unit_random(n, seed):
     return np.stack([r * np.cos(phi), r * np.sin(phi), z], axis=1)
 
 
-@pytest.fixture(params=["specialised", "generic"])
+@pytest.fixture(params=["fused", "two-pass", "generic"])
 def stencil_path(request, monkeypatch):
-    """Run the test through the nearest-neighbour marching kernels (where the Hamiltonian has that structure) and
-    through the generic gather kernels (SPIRIT_B200_GENERIC_STENCIL=1, read when the device tables are built)"""
+    """Run the test through the three kernel families that can serve a nearest-neighbour Hamiltonian (all read when the
+    device tables are built): the fused predictor + corrector kernel (sc6_fused.cuh; Depondt, Heun, SIB), the two-pass
+    marching kernels (sc6.cuh; SPIRIT_B200_NO_FUSED=1) and the generic gather kernels (SPIRIT_B200_GENERIC_STENCIL=1)"""
     monkeypatch.setenv("SPIRIT_B200_GENERIC_STENCIL", "1" if request.param == "generic" else "0")
+    monkeypatch.setenv("SPIRIT_B200_NO_FUSED", "1" if request.param == "two-pass" else "0")
     return request.param
 
 
@@ -141,7 +143,12 @@ def test_single_steps(cfg, product, oracle, solver, preset, overrides, extra, st
 
 BLOCK_CASES = [CASES[0], CASES[1], CASES[2], CASES[3], CASES[4], CASES[5], CASES[6],
                ("cubic256", {"n_basis_cells": "130 5 9", "boundary_conditions": "1 0 1"}, None),
-               ("cubic256", {"n_basis_cells": "20 20 40", "boundary_conditions": "0 1 0", "dm_chirality": "2"}, "aniso")]
+               ("cubic256", {"n_basis_cells": "20 20 40", "boundary_conditions": "0 1 0", "dm_chirality": "2"}, "aniso"),
+               # whole tiles of the fused kernel for tile heights 13 and 16 (its interior variant), several c-segments
+               ("cubic256", {"n_basis_cells": "64 208 6"}, None),
+               ("cubic256", {"n_basis_cells": "96 52 11", "boundary_conditions": "0 0 0", "external_field_magnitude": "3"}, "aniso"),
+               ("cubic256", {"n_basis_cells": "32 48 2", "boundary_conditions": "1 1 0"}, None),
+               ("default", {"n_basis_cells": "100 100 1"}, None)]
 
 
 @pytest.mark.parametrize("solver", ["Depondt", "Heun", "SIB", "RK4"])
@@ -163,6 +170,32 @@ def test_iterate_block(cfg, product, oracle, solver, preset, overrides, extra, s
     assert np.abs(p.effective_field() - fo).max() <= 1e-9 * max(np.abs(fo).max(), 1e-300)
     p.close()
     o.close()
+
+
+@pytest.mark.parametrize("solver", ["Depondt", "Heun", "SIB"])
+@pytest.mark.parametrize("cells,bc,T", [("64 208 6", "1 1 1", 0.0), ("64 208 6", "1 1 1", 10.0), ("70 30 9", "1 0 0", 10.0),
+                                        ("96 52 40", "0 1 1", 5.0), ("48 48 1", "1 1 0", 10.0)])
+def test_fused_equals_two_pass(cfg, product, monkeypatch, solver, cells, bc, T):
+    """The fused predictor + corrector kernel against the two-pass marching kernels from the same state, also at T > 0:
+    the thermal field is a function of (site, plane, iteration) only, so even the rim sites that neighbouring CTAs
+    recompute see the same noise. 9 iterations in blocks of 3 (hook variant on every third); spins equal to 1e-14,
+    hook energy and torque to 1e-12."""
+    out = []
+    for no_fused in ("0", "1"):
+        monkeypatch.setenv("SPIRIT_B200_GENERIC_STENCIL", "0")
+        monkeypatch.setenv("SPIRIT_B200_NO_FUSED", no_fused)
+        p = S.Session(product, cfg("cubic256", n_basis_cells=cells, boundary_conditions=bc, llg_n_iterations_amortize=3,
+                                   llg_seed=4711))
+        p.llg_set(temperature=T, damping=0.3, dt=1e-3)
+        p.set_spins(unit_random(p.nos, 21))
+        p.llg_start(S.SOLVERS[solver], n_iterations=9, n_iterations_log=9)
+        out.append((p.spins().copy(), p.energy(), p.max_torque(), p.effective_field().copy()))
+        p.close()
+    (sf, ef, tf, ff), (st, et, tt, ft) = out
+    assert np.abs(sf - st).max() < 1e-14
+    assert abs(ef - et) <= 1e-12 * abs(et)
+    assert abs(tf - tt) <= 1e-12 * tt
+    assert np.abs(ff - ft).max() <= 1e-12 * np.abs(ft).max()
 
 
 def test_vp_amortized_block(cfg, product, oracle):
