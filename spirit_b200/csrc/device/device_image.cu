@@ -1117,9 +1117,8 @@ void DeviceImage::llg_iterate( int solver, LLGParams & llg, int n_iterations, bo
             mark();
             if( hk )
             {
-                k_reduce_sum<<<1, BLOCK_THREADS, 0, b.stream>>>( b.partials, ncta, b.scalars + 4 );
-                k_reduce_max<<<1, BLOCK_THREADS, 0, b.stream>>>( b.partials + ncta, ncta, b.scalars + 5 );
-                launches_ += 2;
+                k_reduce_hook<<<1, BLOCK_THREADS, 0, b.stream>>>( b.partials, b.partials + ncta, ncta, b.scalars + 4 );
+                launches_ += 1;
             }
             std::swap( b.spins, b.next );
         }

@@ -123,6 +123,25 @@ static __global__ void __launch_bounds__( BLOCK_THREADS ) k_reduce_max( const do
         out[0] = v;
 }
 
+// The two hook scalars of an iteration block in one launch: out[0] = sum of sums[0..n), out[1] = max of maxs[0..n)
+static __global__ void __launch_bounds__( BLOCK_THREADS )
+    k_reduce_hook( const double * __restrict__ sums, const double * __restrict__ maxs, int n, double * __restrict__ out )
+{
+    double v = 0, m = 0;
+    for( int i = threadIdx.x; i < n; i += BLOCK_THREADS )
+    {
+        v += sums[i];
+        m = fmax( m, maxs[i] );
+    }
+    v = block_sum( v );
+    m = block_max( m );
+    if( threadIdx.x == 0 )
+    {
+        out[0] = v;
+        out[1] = m;
+    }
+}
+
 // ---------------------------------------------------------------------------------------------
 // Layout conversion at the C-API boundary: host arrays are AoS [nos][3] in the reference's site
 // order; device fields are planar with (optional) halo planes.

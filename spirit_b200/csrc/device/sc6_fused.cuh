@@ -54,7 +54,10 @@ constexpr int FUSED_RS      = FUSED_TX + 2;                // row stride of a sh
 constexpr int FUSED_CS      = ( FUSED_TY + 2 ) * FUSED_RS; // component stride
 constexpr int FUSED_BS      = 3 * FUSED_CS;                // buffer stride
 constexpr int FUSED_NBUF    = 4;
-constexpr std::size_t FUSED_SMEM = ( std::size_t( FUSED_NBUF ) * FUSED_BS + 2 * FUSED_WARPS + 16 ) * sizeof( double );
+constexpr int FUSED_RED          = FUSED_NBUF * FUSED_BS;           // hook reduction scratch: 2 doubles per warp
+constexpr int FUSED_STASH        = FUSED_RED + 2 * FUSED_WARPS + 2; // hook: gradient of s, two plane buffers (own slots only)
+constexpr std::size_t FUSED_SMEM = std::size_t( FUSED_STASH ) * sizeof( double );
+constexpr std::size_t FUSED_SMEM_HOOK = std::size_t( FUSED_STASH + 2 * FUSED_BS ) * sizeof( double );
 static_assert( 2 * FUSED_TY <= 32, "rim columns must fit one warp" );
 
 struct FusedArgs
@@ -75,7 +78,7 @@ struct FusedGeometry
 };
 
 // storage plane (inside a field) of the local plane m, m in [-2, nc_local + 1]
-__device__ __forceinline__ std::size_t fused_plane( const StencilParams & p, int m )
+__device__ __forceinline__ unsigned fused_plane( const StencilParams & p, int m )
 {
     if( p.halo == 0 )
     {
@@ -83,9 +86,15 @@ __device__ __forceinline__ std::size_t fused_plane( const StencilParams & p, int
             m += p.Nc;
         else if( m >= p.Nc )
             m -= p.Nc;
-        return std::size_t( m );
+        return unsigned( m );
     }
-    return std::size_t( m + p.halo );
+    return unsigned( m + p.halo );
+}
+// first element of a storage plane: a 32 x 32 -> 64 bit product of two uniform values (one uniform-datapath instruction;
+// with a 64-bit plane size the compiler does this arithmetic per thread)
+__device__ __forceinline__ std::uint64_t fused_plane_offset( unsigned plane, unsigned plane_elems )
+{
+    return std::uint64_t( plane ) * plane_elems;
 }
 
 // Philox counter word of the local plane q: its GLOBAL plane (periodic wrap for the planes recomputed beyond the lattice ends)
@@ -112,7 +121,7 @@ __device__ __forceinline__ D3 fused_lds3( const double * buf, int so, bool valid
 __device__ __forceinline__ void fused_reduce_hook( double * sm, double e_acc, double t_acc, const FusedArgs & a )
 {
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    double * red = sm + FUSED_NBUF * FUSED_BS;
+    double * red = sm + FUSED_RED;
     e_acc        = warp_sum( e_acc );
     t_acc        = warp_max( t_acc );
     __syncthreads();
@@ -217,8 +226,8 @@ __device__ __forceinline__ void sc6_fused_march(
         o.ebm         = unsigned( elem_offset( p.Na * bm + x ) );
         o.ebp         = unsigned( elem_offset( p.Na * bp + x ) );
     }
-    const std::size_t plane_elems = 3 * std::size_t( p.plane_stride );
-    const unsigned plane_site     = unsigned( p.Na * b + x );
+    const unsigned plane_elems = 3u * unsigned( p.plane_stride );
+    const unsigned plane_site  = unsigned( p.Na * b + x );
 
     // ---- the march ----------------------------------------------------------------------------------------------------
     // body k handles the predictor of plane q = q0 + k and the corrector of plane q - LAG
@@ -233,15 +242,15 @@ __device__ __forceinline__ void sc6_fused_march(
         const double * sb = a.s.base;
         if( HAS_C )
         {
-            r[0] = ld3p( sb + fused_plane( p, q0 - 1 ) * plane_elems, o.ec );
-            r[2] = ld3p( sb + fused_plane( p, q0 + 1 ) * plane_elems, o.ec );
+            r[0] = ld3p( sb + fused_plane_offset( fused_plane( p, q0 - 1 ), plane_elems ), o.ec );
+            r[2] = ld3p( sb + fused_plane_offset( fused_plane( p, q0 + 1 ), plane_elems ), o.ec );
         }
-        const double * pl = sb + fused_plane( p, q0 ) * plane_elems;
+        const double * pl = sb + fused_plane_offset( fused_plane( p, q0 ), plane_elems );
         r[1]              = ld3p( pl, o.ec );
         if( SB_FUSED_PREFETCH )
             sc6_load_inplane<BOUNDARY>( ws, pl, o );
     }
-    D3 Fv_prev = zero, g_prev = zero, p_center = zero, p_below = zero;
+    D3 Fv_prev = zero, p_center = zero, p_below = zero;
     float3 xi_prev = make_float3( 0.f, 0.f, 0.f );
     double e_acc = 0.0, t_acc = 0.0;
 
@@ -278,7 +287,7 @@ __device__ __forceinline__ void sc6_fused_march(
                 // Order matters to ptxas: (1) the loads, (2) the noise of the plane (Philox + Box-Muller, ~75 integer / SFU
                 // instructions that depend on nothing), (3) the gradient that consumes the loads.
                 if( !SB_FUSED_PREFETCH )
-                    sc6_load_inplane<BOUNDARY>( ws, sb + fused_plane( p, q ) * plane_elems, o );
+                    sc6_load_inplane<BOUNDARY>( ws, sb + fused_plane_offset( fused_plane( p, q ), plane_elems ), o );
                 D3 xid = zero;
                 if( SB_FUSED_NOISE_FIRST && MODE == SC6_THERMAL && q_valid )
                 {
@@ -294,13 +303,13 @@ __device__ __forceinline__ void sc6_fused_march(
                 if( k + 1 < nbodies )
                 {
                     if( SB_FUSED_PREFETCH )
-                        sc6_load_inplane<BOUNDARY>( ws, sb + fused_plane( p, q + 1 ) * plane_elems, o );
+                        sc6_load_inplane<BOUNDARY>( ws, sb + fused_plane_offset( fused_plane( p, q + 1 ), plane_elems ), o );
                     // (the own-column value fetched ahead comes from HBM: issued after the gradient so that it does not share
                     // a scoreboard with the in-plane loads the gradient waits for)
                     if( HAS_C )
-                        s_incoming = ld3p( sb + fused_plane( p, q + 2 ) * plane_elems, o.ec );
+                        s_incoming = ld3p( sb + fused_plane_offset( fused_plane( p, q + 2 ), plane_elems ), o.ec );
                     else
-                        r[( u + 2 ) & 3] = ld3p( sb + fused_plane( p, q + 1 ) * plane_elems, o.ec );
+                        r[( u + 2 ) & 3] = ld3p( sb + fused_plane_offset( fused_plane( p, q + 1 ), plane_elems ), o.ec );
                 }
                 if( q_valid )
                 {
@@ -315,6 +324,15 @@ __device__ __forceinline__ void sc6_fused_march(
                     buf_q[so]                = spn.x;
                     buf_q[so + FUSED_CS]     = spn.y;
                     buf_q[so + 2 * FUSED_CS] = spn.z;
+                    if( HOOK && HAS_C )
+                    {
+                        // the corrector of this plane (next body, same thread) turns the gradient into the projected
+                        // effective field: through shared memory instead of 6 registers held across the body
+                        double * st         = sm + FUSED_STASH + ( u & 1 ) * FUSED_BS + so;
+                        st[0]               = gs.x;
+                        st[FUSED_CS]        = gs.y;
+                        st[2 * FUSED_CS]    = gs.z;
+                    }
                 }
             }
             __syncthreads();
@@ -350,7 +368,7 @@ __device__ __forceinline__ void sc6_fused_march(
                 const D3 Fv_s = HAS_C ? Fv_prev : Fv;
                 D3 acc        = zero;
                 const D3 out  = solver_update<SOLVER, 2>( si, Fv_s, pc, Fvp, acc );
-                double * qo   = a.out.base + std::size_t( c + p.halo ) * plane_elems + o.ec;
+                double * qo   = a.out.base + fused_plane_offset( unsigned( c + p.halo ), plane_elems ) + o.ec;
                 qo[0]               = out.x;
                 qo[FIELD_BLOCK]     = out.y;
                 qo[2 * FIELD_BLOCK] = out.z;
@@ -368,9 +386,14 @@ __device__ __forceinline__ void sc6_fused_march(
                     const double d = dot3( Fv_s, out );
                     const D3 tq    = make_d3( Fv_s.x - d * out.x, Fv_s.y - d * out.y, Fv_s.z - d * out.z );
                     t_acc          = fmax( t_acc, dot3( tq, tq ) );
-                    const D3 g1    = HAS_C ? g_prev : gs; // F = -g
+                    D3 g1 = gs; // F = -g
+                    if( HAS_C )
+                    {
+                        const double * st = sm + FUSED_STASH + ( ( u + 1 ) & 1 ) * FUSED_BS + so;
+                        g1                = make_d3( st[0], st[FUSED_CS], st[2 * FUSED_CS] );
+                    }
                     const double f = dot3( g1, out );
-                    double * qf    = a.F_out.base + std::size_t( c + p.halo ) * plane_elems + o.ec;
+                    double * qf    = a.F_out.base + fused_plane_offset( unsigned( c + p.halo ), plane_elems ) + o.ec;
                     qf[0]               = f * out.x - g1.x;
                     qf[FIELD_BLOCK]     = f * out.y - g1.y;
                     qf[2 * FIELD_BLOCK] = f * out.z - g1.z;
@@ -380,8 +403,6 @@ __device__ __forceinline__ void sc6_fused_march(
             {
                 Fv_prev = Fv;
                 xi_prev = xi;
-                if( HOOK )
-                    g_prev = gs;
                 if( SB_FUSED_PBELOW_REG )
                     p_below = p_center;
                 p_center = spn;
@@ -392,6 +413,7 @@ __device__ __forceinline__ void sc6_fused_march(
     if( HOOK )
         fused_reduce_hook( sm, e_acc, t_acc, a );
 }
+
 
 template<int SOLVER, int SPEC, int MODE, bool HOOK>
 static __global__ void __launch_bounds__( FUSED_THREADS, 1 ) k_sc6_fused(
@@ -422,10 +444,12 @@ void sc6_fused_launch_one( const FusedGeometry & G, cudaStream_t stream, const S
     static bool configured = false;
     if( !configured )
     {
-        cudaFuncSetAttribute( k_sc6_fused<SOLVER, SPEC, MODE, HOOK>, cudaFuncAttributeMaxDynamicSharedMemorySize, int( FUSED_SMEM ) );
+        cudaFuncSetAttribute(
+            k_sc6_fused<SOLVER, SPEC, MODE, HOOK>, cudaFuncAttributeMaxDynamicSharedMemorySize, int( HOOK ? FUSED_SMEM_HOOK : FUSED_SMEM ) );
         configured = true;
     }
-    k_sc6_fused<SOLVER, SPEC, MODE, HOOK><<<G.grid, FUSED_THREADS, FUSED_SMEM, stream>>>( p, G.lc, G.seg_first, G.seg_stride, l, a );
+    k_sc6_fused<SOLVER, SPEC, MODE, HOOK><<<G.grid, FUSED_THREADS, HOOK ? FUSED_SMEM_HOOK : FUSED_SMEM, stream>>>(
+        p, G.lc, G.seg_first, G.seg_stride, l, a );
 }
 
 template<int SOLVER, bool HOOK>

@@ -2,9 +2,7 @@
 `make -C oracle ref_tests` from the reference tree and linked against THIS library, run on the GPU: the reference's
 assertions (all eight solvers relax the skyrmion to its golden energy, the GNEB saddle point, topological charge +-1, ...)
 on the CUDA path. The binaries live in oracle/_ref/ref_tests (built where the reference is mounted, shipped with the
-snapshot). These first ran on a GPU only at the end of round 1 (the GPU budget was spent when they were added), hence
-xfail(strict=False): a failure is reported, not fatal; the same physics is asserted by tests/test_parity_gpu.py and
-tests/test_gneb_gpu.py, which are green."""
+snapshot). They passed on the B200 at the end of round 1 (GPUTEST_r01: 3 xpassed) and are plain tests since."""
 import os
 import subprocess
 
@@ -16,7 +14,6 @@ RT = os.path.join(ROOT, "oracle", "_ref", "ref_tests")
 pytestmark = [pytest.mark.gpu, pytest.mark.skipif(not os.path.exists(os.path.join(RT, "test_solvers")), reason="oracle/_ref/ref_tests not built")]
 
 
-@pytest.mark.xfail(strict=False, reason="first GPU run of the reference's binaries happens at round end")
 @pytest.mark.parametrize("name", ["test_io", "test_api", "test_solvers"])
 def test_reference_catch2_binary_on_the_gpu_library(name):
     r = subprocess.run([os.path.join(RT, name)], cwd=os.path.join(RT, "run"), capture_output=True, text=True, timeout=1200)
