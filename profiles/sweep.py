@@ -21,7 +21,7 @@ for spec in sys.argv[1:]:
             env["SPIRIT_B200_FUSED_LC"] = v
         else:
             env["SPIRIT_B200_SC6_" + k] = v
-    r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--steps", "100", "--warmup", "10", "--no-e2e", "--no-cpu-baseline"],
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--steps", "100", "--warmup", "10", "--no-e2e", "--no-cpu-baseline", "--no-extras"],
                        env=env, capture_output=True, text=True)
     try:
         d = json.loads([l for l in r.stdout.splitlines() if l.startswith("{")][-1])

@@ -9,6 +9,7 @@
 
 #include <stdexcept>
 #include <string>
+#include <vector>
 
 namespace sb
 {
@@ -45,6 +46,10 @@ struct DeviceField
 {
     double * base = nullptr;
     std::size_t n = 0; // storage sites (padded planes, including halo planes); a multiple of 32
+    // slab decomposition with peer-mapped memory: the same field of the rank below / above in THIS process' address space
+    // (cudaIpcOpenMemHandle; travels with the field when two fields are swapped). Null: not mapped / no neighbour.
+    double * peer_lo = nullptr;
+    double * peer_hi = nullptr;
 
     void allocate( std::size_t n_ )
     {
@@ -58,6 +63,7 @@ struct DeviceField
             cudaFree( base );
         base = nullptr;
         n    = 0;
+        peer_lo = peer_hi = nullptr;
     }
     bool allocated() const
     {
@@ -93,6 +99,15 @@ struct DeviceBuffers
     cudaStream_t comm_stream = nullptr; // NCCL halo exchange (high priority)
     cudaStream_t bnd_stream  = nullptr; // the boundary segments of a stage (high priority), concurrent with the interior
     cudaEvent_t ev_boundary = nullptr, ev_comm = nullptr, ev_ready = nullptr;
+    // peer-mapped halo exchange (device_image.cu, slab_peer_setup): step counters written by the neighbouring ranks with
+    // stream memory operations. flags[0]: steps finished by the rank below, flags[1]: by the rank above.
+    unsigned * peer_flags    = nullptr; // own (cudaMalloc, 2 words)
+    unsigned * peer_flag_lo  = nullptr; // flags[1] of the rank below (I am its upper neighbour), peer-mapped
+    unsigned * peer_flag_hi  = nullptr; // flags[0] of the rank above
+    int peer_state           = 0;       // 0 not tried, 1 ready, -1 unavailable (NCCL exchange stays)
+    int peer_lo_nc           = 0;
+    unsigned peer_step       = 0;       // fused iterations done with the peer-store exchange
+    std::vector<void *> peer_opened;    // cudaIpcOpenMemHandle mappings to close
 
     LaunchGeom lg{};
     int nblocks            = 0;
@@ -117,6 +132,10 @@ struct DeviceBuffers
     {
         for( DeviceField * f : { &spins, &pred, &next, &pred2, &acc, &F, &Fv, &ddi_s, &ddi_p, &scratch } )
             f->release();
+        for( void * q : peer_opened )
+            cudaIpcCloseMemHandle( q );
+        if( peer_flags )
+            cudaFree( peer_flags );
         if( staging )
             cudaFree( staging );
         if( xi )

@@ -117,6 +117,7 @@ struct NcclApi
     int ( *Send )( const void *, std::size_t, int, int, ncclComm_t, cudaStream_t )               = nullptr;
     int ( *Recv )( void *, std::size_t, int, int, ncclComm_t, cudaStream_t )                     = nullptr;
     int ( *AllReduce )( const void *, void *, std::size_t, int, int, ncclComm_t, cudaStream_t ) = nullptr;
+    int ( *AllGather )( const void *, void *, std::size_t, int, ncclComm_t, cudaStream_t )      = nullptr;
     int ( *GroupStart )()                                                                        = nullptr;
     int ( *GroupEnd )()                                                                          = nullptr;
     const char * ( *GetErrorString )( int )                                                      = nullptr;
@@ -124,7 +125,7 @@ struct NcclApi
     int rank = 0, world = 1;
 };
 NcclApi g_nccl;
-constexpr int NCCL_FLOAT64 = 8, NCCL_SUM = 0, NCCL_MAX = 2;
+constexpr int NCCL_FLOAT64 = 8, NCCL_INT8 = 0, NCCL_SUM = 0, NCCL_MAX = 2;
 
 void nccl_load()
 {
@@ -154,6 +155,7 @@ void nccl_load()
     g_nccl.Send           = reinterpret_cast<decltype( g_nccl.Send )>( sym( "ncclSend" ) );
     g_nccl.Recv           = reinterpret_cast<decltype( g_nccl.Recv )>( sym( "ncclRecv" ) );
     g_nccl.AllReduce      = reinterpret_cast<decltype( g_nccl.AllReduce )>( sym( "ncclAllReduce" ) );
+    g_nccl.AllGather      = reinterpret_cast<decltype( g_nccl.AllGather )>( sym( "ncclAllGather" ) );
     g_nccl.GroupStart     = reinterpret_cast<decltype( g_nccl.GroupStart )>( sym( "ncclGroupStart" ) );
     g_nccl.GroupEnd       = reinterpret_cast<decltype( g_nccl.GroupEnd )>( sym( "ncclGroupEnd" ) );
     g_nccl.GetErrorString = reinterpret_cast<decltype( g_nccl.GetErrorString )>( sym( "ncclGetErrorString" ) );
@@ -237,6 +239,158 @@ int comm_rank()
 int comm_world()
 {
     return g_nccl.world;
+}
+
+
+// ---------------------------------------------------------------------------------------------
+// Peer-mapped memory for the ranks of one node (NVLink / NVSwitch): the buffers of the neighbouring ranks are mapped into
+// this process with CUDA IPC, kernels store halo planes straight into them, and the ranks keep in step with 32-bit
+// counters written / awaited by stream memory operations (no kernel, no NCCL call per iteration).
+// The driver entry points come from the runtime (cudaGetDriverEntryPoint): no link-time dependency on libcuda.
+// ---------------------------------------------------------------------------------------------
+namespace
+{
+struct StreamMemOps
+{
+    // CUresult cuStreamWriteValue32( CUstream, CUdeviceptr, cuuint32_t, unsigned flags ), cuStreamWaitValue32 alike
+    int ( *write32 )( cudaStream_t, unsigned long long, unsigned, unsigned ) = nullptr;
+    int ( *wait32 )( cudaStream_t, unsigned long long, unsigned, unsigned )  = nullptr;
+    bool tried = false, ok = false;
+};
+StreamMemOps g_memops;
+constexpr unsigned CU_WAIT_GEQ = 0x0; // CU_STREAM_WAIT_VALUE_GEQ
+
+bool stream_memops_available()
+{
+    if( !g_memops.tried )
+    {
+        g_memops.tried = true;
+        void *w = nullptr, *q = nullptr;
+        cudaDriverEntryPointQueryResult r1, r2;
+        if( cudaGetDriverEntryPoint( "cuStreamWriteValue32", &w, cudaEnableDefault, &r1 ) == cudaSuccess && r1 == cudaDriverEntryPointSuccess
+            && cudaGetDriverEntryPoint( "cuStreamWaitValue32", &q, cudaEnableDefault, &r2 ) == cudaSuccess && r2 == cudaDriverEntryPointSuccess
+            && w && q )
+        {
+            g_memops.write32 = reinterpret_cast<decltype( g_memops.write32 )>( w );
+            g_memops.wait32  = reinterpret_cast<decltype( g_memops.wait32 )>( q );
+            g_memops.ok      = true;
+        }
+        else
+            cudaGetLastError();
+    }
+    return g_memops.ok;
+}
+
+// every rank contributes `bytes` bytes; all[r * bytes ...] = what rank r contributed (NCCL all-gather through device staging)
+void allgather_bytes( const void * mine, std::size_t bytes, std::vector<char> & all, cudaStream_t stream )
+{
+    const int world = g_nccl.world;
+    char *d_in = nullptr, *d_out = nullptr;
+    SB_CUDA_CHECK( cudaMalloc( &d_in, bytes ) );
+    SB_CUDA_CHECK( cudaMalloc( &d_out, bytes * world ) );
+    SB_CUDA_CHECK( cudaMemcpyAsync( d_in, mine, bytes, cudaMemcpyHostToDevice, stream ) );
+    nccl_check( g_nccl.AllGather( d_in, d_out, bytes, NCCL_INT8, g_nccl.comm, stream ), "ncclAllGather" );
+    all.resize( bytes * world );
+    SB_CUDA_CHECK( cudaMemcpyAsync( all.data(), d_out, bytes * world, cudaMemcpyDeviceToHost, stream ) );
+    SB_CUDA_CHECK( cudaStreamSynchronize( stream ) );
+    cudaFree( d_in );
+    cudaFree( d_out );
+}
+} // namespace
+
+// Collective over all ranks (every rank reaches its first fused iteration on a slab at the same point of the program):
+// maps the two configuration buffers and the step counters of the neighbouring ranks. On any failure the image keeps the
+// NCCL exchange (peer_state = -1) -- on ALL ranks, because the decision is made from gathered data.
+void DeviceImage::slab_peer_setup()
+{
+    auto & b = *buf_;
+    if( b.peer_state != 0 )
+        return;
+    b.peer_state = -1;
+    const char * off = std::getenv( "SPIRIT_B200_NO_PEER" );
+    const int world = g_nccl.world, rank = g_nccl.rank;
+    struct Record
+    {
+        cudaIpcMemHandle_t spins, next, flags;
+        int nc_local, ok, pid_lo, pid_hi;
+    } mine{};
+    bool ok = !( off && off[0] == '1' ) && stream_memops_available() && b.spins.allocated() && b.next.allocated();
+    if( ok && !b.peer_flags )
+    {
+        ok = cudaMalloc( &b.peer_flags, 2 * sizeof( unsigned ) ) == cudaSuccess;
+        if( ok )
+            SB_CUDA_CHECK( cudaMemset( b.peer_flags, 0, 2 * sizeof( unsigned ) ) );
+    }
+    if( ok && world > 1 )
+        ok = cudaIpcGetMemHandle( &mine.spins, b.spins.base ) == cudaSuccess && cudaIpcGetMemHandle( &mine.next, b.next.base ) == cudaSuccess
+             && cudaIpcGetMemHandle( &mine.flags, b.peer_flags ) == cudaSuccess;
+    if( !ok )
+        cudaGetLastError();
+    mine.nc_local = stencil_.nc_local;
+    mine.ok       = ok ? 1 : 0;
+    const bool periodic = stencil_.bc[2] != 0;
+    const int lower = rank > 0 ? rank - 1 : ( periodic ? world - 1 : -1 );
+    const int upper = rank < world - 1 ? rank + 1 : ( periodic ? 0 : -1 );
+    if( world == 1 )
+    {
+        // one slab that is periodic in c: its own planes wrap around
+        if( !ok )
+            return;
+        b.spins.peer_lo = b.spins.peer_hi = periodic ? b.spins.base : nullptr;
+        b.next.peer_lo = b.next.peer_hi = periodic ? b.next.base : nullptr;
+        b.peer_lo_nc                    = stencil_.nc_local;
+        b.peer_state                    = 1;
+        return;
+    }
+    std::vector<char> all;
+    SB_CUDA_CHECK( cudaStreamSynchronize( b.stream ) );
+    allgather_bytes( &mine, sizeof( Record ), all, b.stream );
+    const Record * rec = reinterpret_cast<const Record *>( all.data() );
+    for( int r = 0; r < world; ++r )
+        if( !rec[r].ok )
+            return; // same decision on every rank
+    // open the neighbours' buffers (one mapping per remote allocation, also when both neighbours are the same rank)
+    auto open = [&]( const cudaIpcMemHandle_t & h ) -> void * {
+        void * q = nullptr;
+        if( cudaIpcOpenMemHandle( &q, h, cudaIpcMemLazyEnablePeerAccess ) != cudaSuccess )
+        {
+            cudaGetLastError();
+            return nullptr;
+        }
+        b.peer_opened.push_back( q );
+        return q;
+    };
+    int mapped = 1;
+    double *lo_spins = nullptr, *lo_next = nullptr, *hi_spins = nullptr, *hi_next = nullptr;
+    unsigned *lo_flags = nullptr, *hi_flags = nullptr;
+    if( lower >= 0 )
+    {
+        lo_spins = static_cast<double *>( open( rec[lower].spins ) );
+        lo_next  = static_cast<double *>( open( rec[lower].next ) );
+        lo_flags = static_cast<unsigned *>( open( rec[lower].flags ) );
+        mapped   = mapped && lo_spins && lo_next && lo_flags;
+    }
+    if( upper >= 0 && upper == lower )
+        hi_spins = lo_spins, hi_next = lo_next, hi_flags = lo_flags;
+    else if( upper >= 0 )
+    {
+        hi_spins = static_cast<double *>( open( rec[upper].spins ) );
+        hi_next  = static_cast<double *>( open( rec[upper].next ) );
+        hi_flags = static_cast<unsigned *>( open( rec[upper].flags ) );
+        mapped   = mapped && hi_spins && hi_next && hi_flags;
+    }
+    // second round: did every rank manage to map its neighbours?
+    allgather_bytes( &mapped, sizeof( int ), all, b.stream );
+    for( int r = 0; r < world; ++r )
+        if( !reinterpret_cast<const int *>( all.data() )[r] )
+            return;
+    b.spins.peer_lo = lo_spins, b.spins.peer_hi = hi_spins;
+    b.next.peer_lo = lo_next, b.next.peer_hi = hi_next;
+    b.peer_flag_lo = lo_flags ? lo_flags + 1 : nullptr; // I am the upper neighbour of the rank below
+    b.peer_flag_hi = hi_flags;                          // and the lower neighbour of the rank above
+    b.peer_lo_nc   = lower >= 0 ? rec[lower].nc_local : 0;
+    b.peer_step    = 0;
+    b.peer_state   = 1;
 }
 
 namespace
@@ -399,7 +553,9 @@ void DeviceImage::set_slab( int c_begin, int Nc_global )
         throw std::runtime_error( "spirit_b200: slab outside of the global lattice" );
     stencil_.Nc      = Nc_global;
     stencil_.c_begin = c_begin;
-    stencil_.halo    = 1; // grown by set_hamiltonian if the pair list reaches further in c
+    // two halo planes per side: the fused predictor + corrector kernels recompute the predictor of the first halo plane from
+    // the second (one exchange per iteration instead of one per stage); slabs thinner than that keep one
+    stencil_.halo    = stencil_.nc_local >= 2 ? 2 : 1;
     slab_            = true;
     ham_revision_    = ~std::uint64_t( 0 );
     b.n_storage      = std::size_t( stencil_.plane_stride ) * ( stencil_.nc_local + 2 * stencil_.halo );
@@ -680,7 +836,10 @@ void DeviceImage::set_hamiltonian( const Hamiltonian & ham )
         p.sc6_g0[d] = p.has_zeeman ? -p.zeeman[0][d] : 0.0;
     {
         int spec = 0;
-        if( p.sc6_axis[2] )
+        // a single open plane: the c-neighbours exist in the pair list but never contribute (idx_from_pair rejects them for
+        // every site), so the marching kernels need not carry the c-direction at all (2-D systems: configs[0], GNEB images)
+        const bool c_dead = !slab_ && p.Nc == 1 && !p.bc[2];
+        if( p.sc6_axis[2] && !c_dead )
             spec |= SC6_HAS_C;
         for( int d = 0; d < 3; ++d )
             if( p.sc6_dflags[d] & ~( 1 << d ) )
@@ -949,14 +1108,14 @@ int DeviceImage::stencil_variant() const
 // global has to happen between predictor and corrector (no dipolar field) and the rare per-site terms are absent.
 bool DeviceImage::fused_usable( int solver, const LLGParams & l ) const
 {
-    if( fused_disabled_ || slab_ )
+    if( fused_disabled_ || ( slab_ && stencil_.halo < 2 ) )
         return false;
     if( solver != Solver_Depondt && solver != Solver_Heun && solver != Solver_SIB )
         return false;
     const StencilParams & p = stencil_;
     if( !p.sc6 || p.has_ddi || l.has_stt || l.has_tgrad )
         return false;
-    if( p.sc6_axis[2] && p.Nc < 2 )
+    if( ( buf_->sc6.spec & SC6_HAS_C ) && p.Nc < 2 )
         return false;
     return true;
 }
@@ -1106,13 +1265,65 @@ void DeviceImage::llg_iterate( int solver, LLGParams & llg, int n_iterations, bo
             fa.F_out           = b.F.f();
             fa.energy_partials = b.partials;
             fa.torque_partials = b.partials + ncta;
-            if( solver == Solver_Depondt )
-                sc6_fused_depondt( hk, b.sc6.spec, b.fused, b.stream, stencil_, llg, fa );
-            else if( solver == Solver_Heun )
-                sc6_fused_heun( hk, b.sc6.spec, b.fused, b.stream, stencil_, llg, fa );
+            auto launch = [&]( const FusedGeometry & G, cudaStream_t st ) {
+                if( solver == Solver_Depondt )
+                    sc6_fused_depondt( hk, b.sc6.spec, G, st, stencil_, llg, fa );
+                else if( solver == Solver_Heun )
+                    sc6_fused_heun( hk, b.sc6.spec, G, st, stencil_, llg, fa );
+                else
+                    sc6_fused_sib( hk, b.sc6.spec, G, st, stencil_, llg, fa );
+                ++launches_;
+            };
+            const int nseg = int( b.fused.grid.z );
+            if( slab_ )
+                slab_peer_setup();
+            if( slab_ && b.peer_state == 1 )
+            {
+                // halo exchange inside the kernel: the CTAs at the slab ends store their planes into the neighbours' halo
+                // planes (peer-mapped memory). Before the launch: the neighbours have finished the previous iteration (their
+                // stores into my halo planes are complete, and they no longer read the buffer I am about to write into).
+                const unsigned long long f = reinterpret_cast<unsigned long long>( b.peer_flags );
+                if( b.peer_step > 0 && g_nccl.world > 1 )
+                {
+                    if( b.peer_flag_lo && g_memops.wait32( b.stream, f, b.peer_step, CU_WAIT_GEQ ) != 0 )
+                        throw std::runtime_error( "spirit_b200: cuStreamWaitValue32 failed" );
+                    if( b.peer_flag_hi && g_memops.wait32( b.stream, f + sizeof( unsigned ), b.peer_step, CU_WAIT_GEQ ) != 0 )
+                        throw std::runtime_error( "spirit_b200: cuStreamWaitValue32 failed" );
+                }
+                fa.peer_lo_out = b.next.peer_lo;
+                fa.peer_hi_out = b.next.peer_hi;
+                fa.peer_lo_nc  = b.peer_lo_nc;
+                launch( b.fused, b.stream );
+                ++b.peer_step;
+                if( g_nccl.world > 1 )
+                {
+                    if( b.peer_flag_lo && g_memops.write32( b.stream, reinterpret_cast<unsigned long long>( b.peer_flag_lo ), b.peer_step, 0 ) != 0 )
+                        throw std::runtime_error( "spirit_b200: cuStreamWriteValue32 failed" );
+                    if( b.peer_flag_hi && g_memops.write32( b.stream, reinterpret_cast<unsigned long long>( b.peer_flag_hi ), b.peer_step, 0 ) != 0 )
+                        throw std::runtime_error( "spirit_b200: cuStreamWriteValue32 failed" );
+                }
+            }
+            else if( slab_ && nseg >= 3 )
+            {
+                // slab: the two c-segments at the slab ends first (high-priority stream); while their first / last two planes
+                // travel to the neighbouring ranks the interior segments run
+                FusedGeometry part = b.fused;
+                part.grid.z        = 2;
+                part.seg_first     = 0;
+                part.seg_stride    = nseg - 1;
+                launch( part, cudaStream_t( boundary_stream() ) );
+                exchange_halo_begin( &b.next, true );
+                part.grid.z     = nseg - 2;
+                part.seg_first  = 1;
+                part.seg_stride = 1;
+                launch( part, b.stream );
+                exchange_halo_end();
+            }
             else
-                sc6_fused_sib( hk, b.sc6.spec, b.fused, b.stream, stencil_, llg, fa );
-            ++launches_;
+            {
+                launch( b.fused, b.stream );
+                exchange_halo( &b.next );
+            }
             mark();
             mark();
             if( hk )

@@ -164,6 +164,7 @@ public:
 
 private:
     void ensure_work_fields( int solver );
+    void slab_peer_setup(); // maps the neighbouring ranks' configuration buffers (CUDA IPC) for the in-kernel halo exchange
     void allreduce_scalars( int first, int count, bool max );
     // DDI gradient field of a configuration (0: spins -> ddi_s, 1: pred -> ddi_p, 2: pred2 -> ddi_p); no-op without DDI
     void compute_ddi_gradient( int which_config );

@@ -67,6 +67,12 @@ struct FusedArgs
     Field3 F_out;             // HOOK: effective field -gradient(s), projected tangentially to the NEW spins
     double * energy_partials; // HOOK: per CTA, energy of the predictor configuration (the last force evaluation)
     double * torque_partials; // HOOK: per CTA, max |Fv - (Fv.s_new) s_new|^2 with Fv the predictor's virtual force
+    // Slab decomposition with peer-mapped memory (NVLink): the CTAs that produce the first / last `halo` planes of the slab
+    // also store them into the halo planes of the neighbouring ranks' `out` field -- the halo exchange is part of this
+    // kernel. Null: no neighbour on that side (or the exchange is done by the host: NCCL send / recv).
+    double * peer_lo_out; // `out` field of the rank below: my planes c < halo are its planes halo + peer_lo_nc + c
+    double * peer_hi_out; // `out` field of the rank above: my planes c >= nc_local - halo are its planes c - (nc_local - halo)
+    int peer_lo_nc;       // nc_local of the rank below
 };
 
 struct FusedGeometry
@@ -118,7 +124,7 @@ __device__ __forceinline__ D3 fused_lds3( const double * buf, int so, bool valid
 }
 
 // Deterministic two-level reduction of the hook quantities of a CTA: warp tree, then thread 0 folds the warps in order.
-__device__ __forceinline__ void fused_reduce_hook( double * sm, double e_acc, double t_acc, const FusedArgs & a )
+__device__ __forceinline__ void fused_reduce_hook( double * sm, double e_acc, double t_acc, const FusedArgs & a, const int cta )
 {
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     double * red = sm + FUSED_RED;
@@ -139,7 +145,6 @@ __device__ __forceinline__ void fused_reduce_hook( double * sm, double e_acc, do
             e += red[w];
             t = fmax( t, red[FUSED_WARPS + w] );
         }
-        const int cta          = blockIdx.x + gridDim.x * ( blockIdx.y + gridDim.y * blockIdx.z );
         a.energy_partials[cta] = e;
         a.torque_partials[cta] = t;
     }
@@ -148,7 +153,7 @@ __device__ __forceinline__ void fused_reduce_hook( double * sm, double e_acc, do
 // RARE: how sc6_gradient reaches the rare terms (1: behind one uniform flag, 2: the Hamiltonian has none -- no test at all)
 template<int SOLVER, int SPEC, int MODE, bool HOOK, bool BOUNDARY, int RARE>
 __device__ __forceinline__ void sc6_fused_march(
-    const StencilParams & p, const LLGParams & l, const FusedArgs & a, double * __restrict__ sm, const int c0, const int c1 )
+    const StencilParams & p, const LLGParams & l, const FusedArgs & a, double * __restrict__ sm, const int c0, const int c1, const int cta )
 {
     constexpr bool HAS_C = ( SPEC & SC6_HAS_C ) != 0;
     constexpr int LAG    = HAS_C ? 1 : 0; // the corrector runs LAG planes behind the predictor
@@ -372,6 +377,24 @@ __device__ __forceinline__ void sc6_fused_march(
                 qo[0]               = out.x;
                 qo[FIELD_BLOCK]     = out.y;
                 qo[2 * FIELD_BLOCK] = out.z;
+                if( HAS_C && p.halo > 0 )
+                {
+                    // halo exchange by peer stores (uniform tests: only the CTAs at the slab ends get here with a pointer)
+                    if( a.peer_lo_out && c < p.halo )
+                    {
+                        double * qp = a.peer_lo_out + fused_plane_offset( unsigned( p.halo + a.peer_lo_nc + c ), plane_elems ) + o.ec;
+                        qp[0]               = out.x;
+                        qp[FIELD_BLOCK]     = out.y;
+                        qp[2 * FIELD_BLOCK] = out.z;
+                    }
+                    if( a.peer_hi_out && c >= p.nc_local - p.halo )
+                    {
+                        double * qp = a.peer_hi_out + fused_plane_offset( unsigned( c - ( p.nc_local - p.halo ) ), plane_elems ) + o.ec;
+                        qp[0]               = out.x;
+                        qp[FIELD_BLOCK]     = out.y;
+                        qp[2 * FIELD_BLOCK] = out.z;
+                    }
+                }
                 if( HOOK )
                 {
                     // energy of the predictor configuration from its total gradient (site_energy, stencil.cuh):
@@ -411,7 +434,7 @@ __device__ __forceinline__ void sc6_fused_march(
     }
 
     if( HOOK )
-        fused_reduce_hook( sm, e_acc, t_acc, a );
+        fused_reduce_hook( sm, e_acc, t_acc, a, cta );
 }
 
 
@@ -421,8 +444,10 @@ static __global__ void __launch_bounds__( FUSED_THREADS, 1 ) k_sc6_fused(
     const __grid_constant__ LLGParams l, const __grid_constant__ FusedArgs a )
 {
     extern __shared__ double fused_smem[];
-    const int c0 = ( seg_first + int( blockIdx.z ) * seg_stride ) * lc;
-    const int c1 = min( c0 + lc, p.nc_local );
+    const int seg = seg_first + int( blockIdx.z ) * seg_stride;
+    const int c0  = seg * lc;
+    const int c1  = min( c0 + lc, p.nc_local );
+    const int cta = blockIdx.x + gridDim.x * ( blockIdx.y + gridDim.y * seg ); // slot of the hook partials (over ALL segments)
 
     // Does this CTA touch an open boundary or the ragged edge of the lattice? (uniform)
     const int x0 = blockIdx.x * FUSED_TX, b0 = blockIdx.y * FUSED_TY;
@@ -431,11 +456,11 @@ static __global__ void __launch_bounds__( FUSED_THREADS, 1 ) k_sc6_fused(
     if( ( SPEC & SC6_HAS_C ) && !p.bc[2] )
         boundary = boundary || ( p.c_begin + c0 <= 1 ) || ( p.c_begin + c1 >= p.Nc - 1 );
     if( boundary )
-        sc6_fused_march<SOLVER, SPEC, MODE, HOOK, true, 1>( p, l, a, fused_smem, c0, c1 );
+        sc6_fused_march<SOLVER, SPEC, MODE, HOOK, true, 1>( p, l, a, fused_smem, c0, c1, cta );
     else if( !SB_FUSED_RARE_SPLIT || p.sc6_extras )
-        sc6_fused_march<SOLVER, SPEC, MODE, HOOK, false, 1>( p, l, a, fused_smem, c0, c1 );
+        sc6_fused_march<SOLVER, SPEC, MODE, HOOK, false, 1>( p, l, a, fused_smem, c0, c1, cta );
     else
-        sc6_fused_march<SOLVER, SPEC, MODE, HOOK, false, 2>( p, l, a, fused_smem, c0, c1 );
+        sc6_fused_march<SOLVER, SPEC, MODE, HOOK, false, 2>( p, l, a, fused_smem, c0, c1, cta );
 }
 
 template<int SOLVER, int SPEC, int MODE, bool HOOK>

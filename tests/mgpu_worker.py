@@ -26,10 +26,14 @@ def main():
     lib.SpiritB200_Set_Device(local)
     slab.init_comm(lib, dist, rank, world)
     tmp = tempfile.mkdtemp()
-    Na, Nb, Nc = 24, 10, 12
     failures = []
-    for bc_c in (1, 0):
-        for solver, temperature in (("Depondt", 0.0), ("Depondt", 5.0), ("Heun", 0.0), ("SIB", 0.0), ("RK4", 0.0), ("VP", 0.0)):
+    # the second lattice is cut into several c-segments per slab: the fused kernel launches the two end segments first and
+    # exchanges two halo planes per side while the interior segments run
+    cases = [(24, 10, 12, bc_c, solver, T) for bc_c in (1, 0)
+             for solver, T in (("Depondt", 0.0), ("Depondt", 5.0), ("Heun", 0.0), ("SIB", 0.0), ("RK4", 0.0), ("VP", 0.0))]
+    cases += [(40, 20, 48, bc_c, solver, T) for bc_c in (1, 0) for solver, T in (("Depondt", 0.0), ("Depondt", 5.0), ("SIB", 5.0))]
+    for Na, Nb, Nc, bc_c, solver, temperature in cases:
+        if True:
             over = dict(boundary_conditions="1 0 %d" % bc_c, llg_temperature=temperature, llg_n_iterations_amortize=4)
             s_global = unit_random(Na * Nb * Nc, 21)
             c_begin, nc_local = slab.partition(Nc, world)[rank]
@@ -39,6 +43,7 @@ def main():
             assert lib.SpiritB200_Slab_Setup(p.state, c_begin, Nc, -1) == 0
             plane = Na * Nb
             p.set_spins(s_global[c_begin * plane:(c_begin + nc_local) * plane])
+            variant = p.step_variant(S.SOLVERS[solver])
             p.llg_start(S.SOLVERS[solver], n_iterations=8, n_iterations_log=8)
             mine = p.spins().copy()
             e_slab = p.energy()
@@ -57,8 +62,8 @@ def main():
                 # VP couples all sites through two global sums whose summation order depends on the decomposition
                 tol = 1e-12 if solver == "VP" else 0.0
                 ok = dev <= tol and moved > 1e-4 and abs(e_slab - g.energy()) <= 1e-12 * abs(g.energy())
-                print("bc_c=%d %-8s T=%g: max deviation %.3e, moved %.2e, E slab %.12e global %.12e %s" % (
-                    bc_c, solver, temperature, dev, moved, e_slab, g.energy(), "OK" if ok else "FAIL"), flush=True)
+                print("%dx%dx%d bc_c=%d %-8s T=%g (step variant %d): max deviation %.3e, moved %.2e, E slab %.12e global %.12e %s" % (
+                    Na, Nb, Nc, bc_c, solver, temperature, variant, dev, moved, e_slab, g.energy(), "OK" if ok else "FAIL"), flush=True)
                 if not ok:
                     failures.append((bc_c, solver, temperature))
                 g.close()
