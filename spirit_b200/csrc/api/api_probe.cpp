@@ -257,6 +257,7 @@ try
     int idx_chain = -1;
     auto image    = resolve( state, idx_image, idx_chain ).image;
     ImageLock lock( *image );
+    image->device_is_newer = false; // an explicit upload: the host copy wins
     image->sync_to_device();
     image->device().synchronize();
     return 0;
@@ -274,6 +275,7 @@ try
     auto image    = resolve( state, idx_image, idx_chain ).image;
     ImageLock lock( *image );
     image->device().download_spins( image->spins.scalars() );
+    image->device_is_newer = false;
     return 0;
 }
 catch( ... )

@@ -240,6 +240,7 @@ try
                 && 0 == std::fmod( double( method->iteration ), double( method->n_iterations_log ) ) )
             {
                 ++method->step;
+                method->Sync_Host(); // the files of a log step hold the spins of that step, as in Method::Iterate
                 method->Save_Current( false, false );
             }
             ++method->iteration;

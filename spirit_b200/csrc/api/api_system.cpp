@@ -114,6 +114,7 @@ void Quantity_Get_Average_Spin( State * state, float s[3], int idx_image, int id
 try
 {
     auto image = resolve( state, idx_image, idx_chain ).image;
+    ImageLock lock( *image );
     double m[3];
     image->sync_to_device();
     image->device().magnetization( m, false );
@@ -126,6 +127,7 @@ void Quantity_Get_Magnetization( State * state, float m[3], int idx_image, int i
 try
 {
     auto image = resolve( state, idx_image, idx_chain ).image;
+    ImageLock lock( *image );
     double mag[3];
     image->sync_to_device();
     image->device().magnetization( mag, true );
@@ -299,6 +301,7 @@ float Quantity_Get_Topological_Charge( State * state, int idx_image, int idx_cha
 try
 {
     auto image = resolve( state, idx_image, idx_chain ).image;
+    ImageLock lock( *image );
     if( image->geometry->dimensionality != 2 )
         return 0;
     if( image->geometry->n_cell_atoms > 1 )
@@ -319,6 +322,7 @@ int Quantity_Get_Topological_Charge_Density( State * state, float * charge_densi
 try
 {
     auto image         = resolve( state, idx_image, idx_chain ).image;
+    ImageLock lock( *image );
     const Geometry & g = *image->geometry;
     if( g.dimensionality != 2 )
         return 0;

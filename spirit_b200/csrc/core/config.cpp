@@ -505,6 +505,116 @@ static void Pairs_from_File( const std::string & pairs_file, const Geometry & ge
     }
 }
 
+
+// Per-atom anisotropy table (Dataparser.cpp:97-260, Anisotropy_from_File): a header line with the columns
+// i, K, Kx Ky Kz (or Ka Kb Kc, in units of the Bravais vectors), K4 in any order (the first six columns count), then one
+// line per basis atom. Without a K column the magnitude is the norm of the vector. Entries with K == 0 / K4 == 0 are
+// dropped, like in the reference.
+static void Anisotropy_from_File( const std::string & file, const Geometry & geometry, Hamiltonian & ham )
+{
+    ConfigFile f( file );
+    int n_anisotropy = 0;
+    if( f.Find( "n_anisotropy" ) )
+        f.iss >> n_anisotropy;
+    else
+    {
+        n_anisotropy = int( 1e8 );
+        f.To_Start();
+    }
+    std::vector<std::string> columns( 6 );
+    int col_i = -1, col_K = -1, col_Kx = -1, col_Ky = -1, col_Kz = -1, col_Ka = -1, col_Kb = -1, col_Kc = -1, col_K4 = -1;
+    f.GetLine();
+    for( std::size_t i = 0; i < columns.size(); ++i )
+    {
+        f.iss >> columns[i];
+        const std::string c = lower( columns[i] );
+        if( c == "i" )
+            col_i = int( i );
+        else if( c == "k" )
+            col_K = int( i );
+        else if( c == "kx" )
+            col_Kx = int( i );
+        else if( c == "ky" )
+            col_Ky = int( i );
+        else if( c == "kz" )
+            col_Kz = int( i );
+        else if( c == "ka" )
+            col_Ka = int( i );
+        else if( c == "kb" )
+            col_Kb = int( i );
+        else if( c == "kc" )
+            col_Kc = int( i );
+        else if( c == "k4" )
+            col_K4 = int( i );
+    }
+    const bool K_magnitude = col_K >= 0;
+    const bool K_xyz = col_Kx >= 0 && col_Ky >= 0 && col_Kz >= 0, K_abc = col_Ka >= 0 && col_Kb >= 0 && col_Kc >= 0;
+    if( !K_xyz && !K_abc )
+        Log( Log_Level::Warning, Log_Sender::IO, "No anisotropy data could be found in header of file \"" + file + "\"" );
+
+    ham.anisotropy_indices.clear();
+    ham.anisotropy_magnitudes.clear();
+    ham.anisotropy_normals.clear();
+    ham.cubic_anisotropy_indices.clear();
+    ham.cubic_anisotropy_magnitudes.clear();
+    int spin_i = 0, i_anisotropy = 0;
+    double spin_K = 0, k1 = 0, k2 = 0, k3 = 0, spin_K4 = 0; // values persist over lines that do not set them, as in the reference
+    while( f.GetLine() && i_anisotropy < n_anisotropy )
+    {
+        std::string sdump;
+        for( int i = 0; i < int( columns.size() ); ++i )
+        {
+            if( i == col_i )
+                f.iss >> spin_i;
+            else if( i == col_K )
+                f.iss >> spin_K;
+            else if( ( i == col_Kx && K_xyz ) || ( i == col_Ka && K_abc ) )
+                f.iss >> k1;
+            else if( ( i == col_Ky && K_xyz ) || ( i == col_Kb && K_abc ) )
+                f.iss >> k2;
+            else if( ( i == col_Kz && K_xyz ) || ( i == col_Kc && K_abc ) )
+                f.iss >> k3;
+            else if( i == col_K4 )
+                f.iss >> spin_K4;
+            else
+                f.iss >> sdump;
+        }
+        Vec3 K_temp{ k1, k2, k3 };
+        if( K_abc )
+        {
+            const double lc = geometry.lattice_constant;
+            k1              = K_temp.dot( lc * geometry.bravais_vectors[0] );
+            k2              = K_temp.dot( lc * geometry.bravais_vectors[1] );
+            k3              = K_temp.dot( lc * geometry.bravais_vectors[2] );
+            K_temp          = Vec3{ k1, k2, k3 };
+        }
+        if( K_magnitude )
+        {
+            K_temp.normalize();
+            if( K_temp.norm() == 0 )
+                K_temp = Vec3{ 0, 0, 1 };
+        }
+        else
+        {
+            spin_K = K_temp.norm();
+            if( spin_K != 0 )
+                K_temp.normalize();
+        }
+        if( spin_K != 0 )
+        {
+            ham.anisotropy_indices.push_back( spin_i );
+            ham.anisotropy_magnitudes.push_back( spin_K );
+            ham.anisotropy_normals.push_back( K_temp );
+        }
+        if( spin_K4 != 0 )
+        {
+            ham.cubic_anisotropy_indices.push_back( spin_i );
+            ham.cubic_anisotropy_magnitudes.push_back( spin_K4 );
+        }
+        ++i_anisotropy;
+    }
+}
+
 // ---------------------------------------------------------------------------------------------
 // Heisenberg Hamiltonian (Configparser.cpp:1195-1633)
 // ---------------------------------------------------------------------------------------------
@@ -516,6 +626,7 @@ std::shared_ptr<Hamiltonian> Hamiltonian_from_Config( const std::string & config
     Vec3 B_normal{ 0, 0, 1 }, K_normal{ 0, 0, 1 };
     std::size_t n_shells_exchange = 0, n_shells_dmi = 0;
     int dm_chirality = 1;
+    bool anisotropy_from_file = false;
 
     if( !config_file.empty() )
     {
@@ -524,7 +635,7 @@ std::shared_ptr<Hamiltonian> Hamiltonian_from_Config( const std::string & config
             ConfigFile f( config_file );
             f.Read_Single( hamiltonian_type, "hamiltonian" );
             if( hamiltonian_type != "heisenberg_neighbours" && hamiltonian_type != "heisenberg_pairs" )
-                throw std::runtime_error(
+                throw Unsupported(
                     "Hamiltonian type \"" + hamiltonian_type
                     + "\" is outside the hot path of spirit_b200 (only heisenberg_neighbours / heisenberg_pairs)" );
 
@@ -539,12 +650,24 @@ std::shared_ptr<Hamiltonian> Hamiltonian_from_Config( const std::string & config
             if( B_normal.norm() < 1e-8 )
                 B_normal = { 0, 0, 1 };
 
-            if( f.Find( "n_anisotropy" ) || f.Find( "anisotropy_file" ) )
-                throw std::runtime_error( "per-atom anisotropy tables (n_anisotropy / anisotropy_file) are not supported" );
-            f.Read_Single( K, "anisotropy_magnitude" );
-            f.Read_3( K_normal, "anisotropy_normal" );
-            K_normal.normalize();
-            f.Read_Single( K4, "cubic_anisotropy_magnitude" );
+            // per-atom anisotropy table in the config file itself or in a file of its own (Configparser.cpp:1352-1385)
+            std::string anisotropy_file;
+            if( f.Find( "n_anisotropy" ) )
+                anisotropy_file = config_file;
+            else if( f.Find( "anisotropy_file" ) )
+                f.iss >> anisotropy_file;
+            if( !anisotropy_file.empty() )
+            {
+                Anisotropy_from_File( anisotropy_file, *geometry, *ham );
+                anisotropy_from_file = true;
+            }
+            else
+            {
+                f.Read_Single( K, "anisotropy_magnitude" );
+                f.Read_3( K_normal, "anisotropy_normal" );
+                K_normal.normalize();
+                f.Read_Single( K4, "cubic_anisotropy_magnitude" );
+            }
 
             if( hamiltonian_type == "heisenberg_pairs" )
             {
@@ -592,8 +715,14 @@ std::shared_ptr<Hamiltonian> Hamiltonian_from_Config( const std::string & config
                 int nq = 0;
                 f.iss >> nq;
                 if( nq > 0 )
-                    throw std::runtime_error( "quadruplet interactions are outside the hot path of spirit_b200" );
+                    throw Unsupported( "quadruplet interactions are outside the hot path of spirit_b200" );
             }
+        }
+        catch( const Unsupported & )
+        {
+            // physics this library does not compute: the State must not come up with a silently different Hamiltonian
+            // (the reference fails State_Setup for a Hamiltonian it cannot build); State_Setup returns nullptr
+            throw;
         }
         catch( const std::exception & e )
         {
@@ -604,14 +733,14 @@ std::shared_ptr<Hamiltonian> Hamiltonian_from_Config( const std::string & config
     // Hamiltonian_Heisenberg.cpp:35 -- the field is stored in meV per mu_B
     ham->external_field_magnitude = B * constants::mu_B;
     ham->external_field_normal    = B_normal;
-    if( K != 0 )
+    if( !anisotropy_from_file && K != 0 )
         for( int i = 0; i < geometry->n_cell_atoms; ++i )
         {
             ham->anisotropy_indices.push_back( i );
             ham->anisotropy_magnitudes.push_back( K );
             ham->anisotropy_normals.push_back( K_normal );
         }
-    if( K4 != 0 )
+    if( !anisotropy_from_file && K4 != 0 )
         for( int i = 0; i < geometry->n_cell_atoms; ++i )
         {
             ham->cubic_anisotropy_indices.push_back( i );

@@ -15,6 +15,13 @@ namespace sb
 namespace config
 {
 
+// Input that asks for physics outside this library (another Hamiltonian type, quadruplets): State_Setup fails with it
+// instead of coming up with a Hamiltonian that silently lacks terms.
+struct Unsupported : std::runtime_error
+{
+    using std::runtime_error::runtime_error;
+};
+
 // Keyword scanner over one file, loaded once
 class ConfigFile
 {

@@ -154,6 +154,7 @@ Method_LLG::Method_LLG( std::shared_ptr<Spin_System> system_, int solver_, int i
     max_torque = system->llg_parameters->force_convergence + 1.0;
 
     // Constructor-time force evaluation + hook (Method_LLG.cpp:57-62)
+    system->device_is_newer = false; // a new method starts from the host configuration
     system->sync_to_device();
     system->device().oso_reset(); // Method_Solver<...OSO>::Initialize: zero velocity / empty L-BFGS memory
     llg_          = make_params( *system, solver );
@@ -256,7 +257,8 @@ void Method_LLG::Iteration( bool hook_follows )
     else
         system->device().llg_iterate( solver, llg_, 1, hook_follows, hook_follows ? &pending_hook_ : nullptr );
     ++system->llg_parameters->philox_counter;
-    hook_pending_ = hook_follows;
+    hook_pending_           = hook_follows;
+    system->device_is_newer = true;
 }
 
 double Method_LLG::Iterate_Device_Resident( const std::shared_ptr<Spin_System> & system, int solver, int n_iterations )
@@ -274,6 +276,7 @@ double Method_LLG::Iterate_Device_Resident( const std::shared_ptr<Spin_System> &
     const double ms = d.timer_stop();
     system->llg_parameters->philox_counter = l.iteration;
     system->E                              = result.energy;
+    system->device_is_newer                = true; // until SpiritB200_Download / the next upload
     return ms;
 }
 
@@ -375,10 +378,12 @@ void Method_LLG::Sync_Host()
     auto & d = system->device();
     d.download_spins( system->spins.scalars() );
     d.download_effective_field( system->effective_field.scalars() );
+    system->device_is_newer = false;
 }
 
 void Method_LLG::Sync_Device()
 {
+    system->device_is_newer = false;
     system->sync_to_device();
 }
 

@@ -87,7 +87,8 @@ void Spin_System::sync_to_device()
 {
     auto & d = device();
     d.set_hamiltonian( *hamiltonian );
-    d.upload_spins( spins.scalars() );
+    if( !device_is_newer )
+        d.upload_spins( spins.scalars() );
 }
 
 // Spin_System.cpp:115-129: per-term energies and their sum

@@ -163,8 +163,12 @@ struct Spin_System
     {
         device_.reset();
     }
-    // Push host spins / Hamiltonian to the device
+    // Push host spins / Hamiltonian to the device. While a method iterates on the device-resident spins the device copy is
+    // the newer one (device_is_newer): then only the Hamiltonian tables are refreshed, so that a query from another
+    // thread (Quantity_Get_*, System_Update_Data) evaluates the LIVE spins instead of rewinding the run to the host copy
+    // of the last log step.
     void sync_to_device();
+    bool device_is_newer = false; // set by the method's iterations, cleared when the host copy is refreshed (Sync_Host)
 
     // One-off evaluations on the device (Spin_System.cpp:115-141)
     void UpdateEnergy();

@@ -461,6 +461,7 @@ __device__ double2 * block_fft( const FFTPlan1D & plan, double2 * x, double2 * y
 // Generic strided pass: transforms along j of  in[o * in_os + j * in_js + u]  for u < n_u (contiguous), o < n_o.
 // Inputs j >= n_in are zero (not read), outputs j >= n_out are dropped. A CTA handles `ncol` consecutive u of one o.
 // ---------------------------------------------------------------------------------------------
+constexpr int DDI_MAX_PEERS = 8;
 struct PassArgs
 {
     const double2 * in;
@@ -473,6 +474,12 @@ struct PassArgs
     // per-rank blocks so that the all-to-all moves one contiguous block per peer.
     int in_split, out_split;
     std::size_t in_split_stride, out_split_stride;
+    // distributed convolution over peer-mapped memory (k_fft_pass16 only): block r of the split axis lives in the memory of
+    // rank r. in_peer[r] / out_peer[r] point at this rank's block inside rank r's operand (in place of in / out +
+    // r * split_stride); the transposes of the convolution are these remote loads / stores.
+    int use_in_peer, use_out_peer;
+    const double2 * in_peer[DDI_MAX_PEERS];
+    double2 * out_peer[DDI_MAX_PEERS];
 };
 __device__ __forceinline__ std::size_t pass_offset( int j, std::size_t js, int split, std::size_t split_stride )
 {
@@ -549,7 +556,13 @@ static __global__ void __launch_bounds__( FFT_THREADS, SB_FFT16_MINB ) k_fft_pas
             const int j = j0 + ( h * FFT_E + k ) * jstep;
             v[k]        = make_double2( 0.0, 0.0 );
             if( valid && j < a.n_in )
-                v[k] = in[pass_offset16( j, a.in_js, lg_in_split, a.in_split_stride )];
+            {
+                if( a.use_in_peer )
+                    v[k] = a.in_peer[j >> lg_in_split]
+                                    [std::size_t( o ) * a.in_os + u0 + ctile + std::size_t( unsigned( j ) & ( ( 1u << lg_in_split ) - 1u ) ) * a.in_js];
+                else
+                    v[k] = in[pass_offset16( j, a.in_js, lg_in_split, a.in_split_stride )];
+            }
         }
 #pragma unroll
         for( int k = 0; k < FFT_E; ++k )
@@ -570,7 +583,12 @@ static __global__ void __launch_bounds__( FFT_THREADS, SB_FFT16_MINB ) k_fft_pas
             if( j < a.n_out )
             {
                 const double2 w = mine[( j << lg_ncol ) + col];
-                out[pass_offset16( j, a.out_js, lg_out_split, a.out_split_stride )] = make_double2( a.scale * w.x, a.scale * w.y );
+                if( a.use_out_peer )
+                    a.out_peer[j >> lg_out_split]
+                              [std::size_t( o ) * a.out_os + u0 + ctile + std::size_t( unsigned( j ) & ( ( 1u << lg_out_split ) - 1u ) ) * a.out_js]
+                        = make_double2( a.scale * w.x, a.scale * w.y );
+                else
+                    out[pass_offset16( j, a.out_js, lg_out_split, a.out_split_stride )] = make_double2( a.scale * w.x, a.scale * w.y );
             }
         }
     }
@@ -1251,6 +1269,17 @@ struct DDIPlan
     int lg_split         = 31;     // lg of the per-rank kb block (distributed layout), 31: no split
     void * Dt            = nullptr; // tensor spectrum in the tile order of k_ddi_c_mult16
     bool Dt_real         = false;
+    // distributed over peer-mapped memory (NVLink): no all-to-all at all. The forward b-pass stores its per-rank kb blocks
+    // straight into the c-pass operand of their owners, the inverse b-pass loads its input from there; the c-pass operand
+    // is double-buffered (evaluation e uses C2[e & 1]) and the ranks meet at two counters per evaluation.
+    bool peer               = false;
+    double2 * C2[2]         = { nullptr, nullptr };
+    std::vector<void *> C2_peer[2];  // [buffer][rank]
+    unsigned * flags        = nullptr; // [world]: flags[r] = barriers rank r has arrived at
+    std::vector<void *> flags_peer;  // [rank]: the flags array of every rank
+    std::vector<void *> peer_opened;
+    unsigned barrier_count  = 0;
+    unsigned evaluation     = 0;
     // distributed: the all-to-alls run on their own stream, one component at a time, under the passes of the others
     cudaStream_t comm_stream = nullptr;
     cudaEvent_t ev_q[3 * MAX_BASIS] = {};
@@ -1282,6 +1311,13 @@ struct DDIPlan
             cudaFree( B );
         if( C )
             cudaFree( C );
+        for( void * q : peer_opened )
+            cudaIpcCloseMemHandle( q );
+        for( double2 * c : C2 )
+            if( c )
+                cudaFree( c );
+        if( flags )
+            cudaFree( flags );
     }
 };
 
@@ -1608,9 +1644,39 @@ DDIPlan * ddi_plan_create( const Hamiltonian & ham, const StencilParams & sp, cu
     const std::size_t n_B        = std::size_t( nq ) * ncl * d.Pb * d.Ha;
     SB_CUDA_CHECK( cudaMalloc( &plan->Dhat, std::size_t( 6 * d.n_inter ) * half_local * sizeof( double2 ) ) );
     SB_CUDA_CHECK( cudaMalloc( &plan->A, std::size_t( nq ) * ncl * d.Nb * d.Ha * sizeof( double2 ) ) );
-    SB_CUDA_CHECK( cudaMalloc( &plan->B, n_B * sizeof( double2 ) ) );
-    if( world > 1 )
-        SB_CUDA_CHECK( cudaMalloc( &plan->C, n_B * sizeof( double2 ) ) );
+    if( world > 1 && world <= DDI_MAX_PEERS && plan->fast_a.on && plan->fast_b.on && plan->lg_split != 31 )
+    {
+        // peer-mapped operands (collective; the same outcome on every rank)
+        SB_CUDA_CHECK( cudaStreamSynchronize( stream ) );
+        bool ok = peer_memops_available();
+        for( int k = 0; k < 2; ++k )
+            ok = cudaMalloc( &plan->C2[k], n_B * sizeof( double2 ) ) == cudaSuccess && ok;
+        ok = cudaMalloc( &plan->flags, std::size_t( world ) * sizeof( unsigned ) ) == cudaSuccess && ok;
+        if( !ok )
+            cudaGetLastError();
+        else
+            SB_CUDA_CHECK( cudaMemset( plan->flags, 0, std::size_t( world ) * sizeof( unsigned ) ) );
+        // every rank takes part in every collective call, whatever its own outcome so far
+        const bool m0 = peer_map_all( ok ? plan->C2[0] : nullptr, plan->C2_peer[0], plan->peer_opened, stream );
+        const bool m1 = peer_map_all( ok ? plan->C2[1] : nullptr, plan->C2_peer[1], plan->peer_opened, stream );
+        const bool m2 = peer_map_all( ok ? plan->flags : nullptr, plan->flags_peer, plan->peer_opened, stream );
+        plan->peer    = m0 && m1 && m2;
+        if( !plan->peer )
+        {
+            for( double2 *& c : plan->C2 )
+            {
+                if( c )
+                    cudaFree( c );
+                c = nullptr;
+            }
+        }
+    }
+    if( !plan->peer )
+    {
+        SB_CUDA_CHECK( cudaMalloc( &plan->B, n_B * sizeof( double2 ) ) );
+        if( world > 1 )
+            SB_CUDA_CHECK( cudaMalloc( &plan->C, n_B * sizeof( double2 ) ) );
+    }
 
     // tensor spectrum, one component at a time: real D -> rows (a) -> b -> c on the WHOLE padded lattice (every rank
     // computes it redundantly: the tensor is analytic, no communication), then the local kb range is kept
@@ -1799,6 +1865,67 @@ void launch_c_mult( DDIPlan & plan, double2 * operand, cudaStream_t stream )
 namespace
 {
 
+// Distributed evaluation over peer-mapped memory: the transposes are the stores of the forward b-pass (into the c-pass
+// operands of the ranks that own each kb block) and the loads of the inverse b-pass (from there). Two meetings of all ranks
+// per evaluation, done with 32-bit counters and stream memory operations: (1) every rank has stored its blocks, before the
+// c-passes; (2) every c-pass is done, before the inverse b-passes read. The operand is double-buffered, so the stores of the
+// next evaluation cannot overtake the loads of this one (a rank reaches meeting (1) of evaluation e + 1 only after its
+// loads of evaluation e).
+void ddi_peer_barrier( DDIPlan & plan, cudaStream_t stream )
+{
+    const unsigned value = ++plan.barrier_count;
+    for( int r = 0; r < plan.world; ++r )
+        if( r != plan.rank )
+            peer_write32( stream, static_cast<unsigned *>( plan.flags_peer[r] ) + plan.rank, value );
+    for( int r = 0; r < plan.world; ++r )
+        if( r != plan.rank )
+            peer_wait_geq32( stream, plan.flags + r, value );
+}
+
+int ddi_gradient_peer( DDIPlan & plan, ConstField3 spins, Field3 g_ddi, cudaStream_t stream )
+{
+    const DDIDims & d  = plan.dims;
+    const DDIDims & dc = plan.dims_c;
+    const int world = plan.world, nq = 3 * d.NB, kbl = dc.Pb, ncl = d.Nc, rows = d.Nb * d.Nc;
+    const int buf                = int( plan.evaluation++ & 1u );
+    const std::size_t comp_elems = dc.q_stride; // one component inside a per-rank block: ncl * kbl * Ha
+    const dim3 grid_a( ( rows + ( 1 << plan.fast_a.lg ) - 1 ) >> plan.fast_a.lg, 1 );
+    const int lg_tile_b = plan.fast_b.lg + plan.fast_b.lg_seq;
+    const dim3 grid_b( ( d.Ha + ( 1 << lg_tile_b ) - 1 ) >> lg_tile_b, ncl );
+    for( int q = 0; q < nq; ++q )
+    {
+        launch_fwd_a16( plan.fast_a, grid_a, stream, plan.plan_ah, plan.plan[0].twiddle, d, spins, plan.A, q );
+        PassArgs pb{};
+        pb.in    = plan.A + std::size_t( q ) * ncl * d.Nb * d.Ha;
+        pb.in_os = std::size_t( d.Nb ) * d.Ha, pb.in_js = pb.out_js = d.Ha;
+        pb.out_os = std::size_t( kbl ) * d.Ha, pb.out_split = kbl, pb.out_split_stride = dc.block_stride;
+        pb.n_u = d.Ha, pb.n_o = ncl, pb.n_in = d.Nb, pb.n_out = d.Pb, pb.ncol = 1 << plan.fast_b.lg, pb.scale = 1.0;
+        pb.use_out_peer = 1;
+        for( int r = 0; r < world; ++r ) // my block inside rank r's operand: [source rank][component][plane][kb][ka]
+            pb.out_peer[r] = static_cast<double2 *>( plan.C2_peer[buf][r] ) + std::size_t( plan.rank ) * dc.block_stride + std::size_t( q ) * comp_elems;
+        launch_pass16<false>( plan.fast_b, grid_b, stream, plan.plan[1], pb, 31, plan.lg_split );
+    }
+    ddi_peer_barrier( plan, stream );
+    launch_c_mult( plan, plan.C2[buf], stream );
+    ddi_peer_barrier( plan, stream );
+    const double inv_P = 1.0 / ( double( d.Pa ) * d.Pb * d.Pc );
+    for( int q = 0; q < nq; ++q )
+    {
+        PassArgs ib{};
+        ib.out    = plan.A + std::size_t( q ) * ncl * d.Nb * d.Ha;
+        ib.out_os = std::size_t( d.Nb ) * d.Ha, ib.in_js = ib.out_js = d.Ha;
+        ib.in_os = std::size_t( kbl ) * d.Ha, ib.in_split = kbl, ib.in_split_stride = dc.block_stride;
+        ib.n_u = d.Ha, ib.n_o = ncl, ib.n_in = d.Pb, ib.n_out = d.Nb, ib.ncol = 1 << plan.fast_b.lg, ib.scale = 1.0;
+        ib.use_in_peer = 1;
+        for( int r = 0; r < world; ++r ) // the kb block of rank r for my planes: block `my rank` of rank r's operand
+            ib.in_peer[r] = static_cast<const double2 *>( plan.C2_peer[buf][r] ) + std::size_t( plan.rank ) * dc.block_stride + std::size_t( q ) * comp_elems;
+        launch_pass16<true>( plan.fast_b, grid_b, stream, plan.plan[1], ib, plan.lg_split, 31 );
+        launch_inv_a16( plan.fast_a, grid_a, stream, plan.plan_ah, plan.plan[0].twiddle, d, plan.A, g_ddi, inv_P, q );
+    }
+    SB_CUDA_CHECK( cudaGetLastError() );
+    return 4 * nq + 1;
+}
+
 // Distributed evaluation with the transposes hidden: component q travels (NCCL send / recv on the plan's own stream)
 // while the a- and b-passes of component q + 1 run, and on the way back the inverse passes of component q run while
 // component q + 1 travels. Same kernels, same per-rank block layout, same result as the plain sequence below.
@@ -1868,6 +1995,8 @@ int ddi_gradient_pipelined( DDIPlan & plan, ConstField3 spins, Field3 g_ddi, cud
 // One DDI gradient evaluation: spins -> g_ddi field. Returns the number of kernels launched.
 int ddi_gradient( DDIPlan & plan, ConstField3 spins, Field3 g_ddi, cudaStream_t stream )
 {
+    if( plan.peer )
+        return ddi_gradient_peer( plan, spins, g_ddi, stream );
     if( plan.comm_stream )
         return ddi_gradient_pipelined( plan, spins, g_ddi, stream );
     const DDIDims & d  = plan.dims;

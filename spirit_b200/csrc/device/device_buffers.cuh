@@ -83,6 +83,14 @@ struct DeviceField
     }
 };
 
+// device/device_image.cu: peer-mapped memory of the other ranks of the node (CUDA IPC over NVLink) and stream-ordered counters
+// peer_map_all: COLLECTIVE over all ranks of the communicator. peers[r] = the buffer `local` of rank r in this process'
+// address space (peers[rank] = local). Returns false -- on every rank alike -- when the mapping is not available.
+bool peer_map_all( void * local, std::vector<void *> & peers, std::vector<void *> & opened, cudaStream_t stream );
+bool peer_memops_available();
+void peer_write32( cudaStream_t stream, unsigned * address, unsigned value );      // after the work enqueued so far, system-wide fence
+void peer_wait_geq32( cudaStream_t stream, unsigned * address, unsigned value );   // the stream waits until *address >= value
+
 // device/ddi_fft.cu
 struct DDIPlan;
 DDIPlan * ddi_plan_create( const Hamiltonian & ham, const StencilParams & sp, cudaStream_t stream );

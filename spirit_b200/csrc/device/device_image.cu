@@ -298,6 +298,70 @@ void allgather_bytes( const void * mine, std::size_t bytes, std::vector<char> & 
 }
 } // namespace
 
+bool peer_memops_available()
+{
+    return stream_memops_available();
+}
+void peer_write32( cudaStream_t stream, unsigned * address, unsigned value )
+{
+    if( !stream_memops_available() || g_memops.write32( stream, reinterpret_cast<unsigned long long>( address ), value, 0 ) != 0 )
+        throw std::runtime_error( "spirit_b200: cuStreamWriteValue32 failed" );
+}
+void peer_wait_geq32( cudaStream_t stream, unsigned * address, unsigned value )
+{
+    if( !stream_memops_available() || g_memops.wait32( stream, reinterpret_cast<unsigned long long>( address ), value, CU_WAIT_GEQ ) != 0 )
+        throw std::runtime_error( "spirit_b200: cuStreamWaitValue32 failed" );
+}
+
+bool peer_map_all( void * local, std::vector<void *> & peers, std::vector<void *> & opened, cudaStream_t stream )
+{
+    const int world = g_nccl.world, rank = g_nccl.rank;
+    peers.assign( std::size_t( world ), nullptr );
+    struct Record
+    {
+        cudaIpcMemHandle_t handle;
+        int ok;
+    } mine{};
+    const char * off = std::getenv( "SPIRIT_B200_NO_PEER" );
+    mine.ok = ( !( off && off[0] == '1' ) && g_nccl.comm && stream_memops_available() && local
+                && cudaIpcGetMemHandle( &mine.handle, local ) == cudaSuccess )
+                  ? 1
+                  : 0;
+    if( !mine.ok )
+        cudaGetLastError();
+    if( !g_nccl.comm )
+        return false;
+    std::vector<char> all;
+    allgather_bytes( &mine, sizeof( Record ), all, stream );
+    const Record * rec = reinterpret_cast<const Record *>( all.data() );
+    for( int r = 0; r < world; ++r )
+        if( !rec[r].ok )
+            return false;
+    int mapped = 1;
+    for( int r = 0; r < world; ++r )
+    {
+        if( r == rank )
+        {
+            peers[r] = local;
+            continue;
+        }
+        void * q = nullptr;
+        if( cudaIpcOpenMemHandle( &q, rec[r].handle, cudaIpcMemLazyEnablePeerAccess ) != cudaSuccess )
+        {
+            cudaGetLastError();
+            mapped = 0;
+            break;
+        }
+        opened.push_back( q );
+        peers[r] = q;
+    }
+    allgather_bytes( &mapped, sizeof( int ), all, stream );
+    for( int r = 0; r < world; ++r )
+        if( !reinterpret_cast<const int *>( all.data() )[r] )
+            return false;
+    return true;
+}
+
 // Collective over all ranks (every rank reaches its first fused iteration on a slab at the same point of the program):
 // maps the two configuration buffers and the step counters of the neighbouring ranks. On any failure the image keeps the
 // NCCL exchange (peer_state = -1) -- on ALL ranks, because the decision is made from gathered data.

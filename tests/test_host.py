@@ -131,3 +131,43 @@ def test_topological_charge_triangles_match_reference(tmp_path, product, oracle,
     got = sorted(tuple(sorted(map(int, r))) for r in np.array(tri_p).reshape(-1, 3))
     assert got == ref
     p.close(), o.close()
+
+
+ANISOTROPY_TABLES = [
+    ["n_anisotropy 2", "i K Kx Ky Kz K4", "0 1.5 0 0 1 0.0", "1 0.7 1 1 0 0.25"],
+    ["n_anisotropy 2", "i Ka Kb Kc", "0 0.0 0.0 2.0", "1 0.5 0.5 0.0"],
+    ["n_anisotropy 1", "K4 i Kz Ky Kx", "0.3 1 0.6 0.0 0.8"],
+]
+
+
+@pytest.mark.parametrize("table", ANISOTROPY_TABLES)
+def test_anisotropy_table_is_parsed_like_the_reference(tmp_path, product, oracle, table):
+    """n_anisotropy (per-atom anisotropy table, Configparser.cpp:1352-1385, Dataparser.cpp:97-260): what the getters report
+    (the first entry) equals the reference; the gradient with the whole table is compared on the GPU (tests/test_parity_gpu.py)"""
+    import ctypes
+    from tests import cfgs
+    path = tmp_path / "a.cfg"
+    path.write_text(cfgs.render("cubic256", block=["basis", "2", "0 0 0", "0.5 0.5 0.5"] + table, n_basis_cells="4 3 2"))
+    vals = []
+    for lib in (product, oracle):
+        x = S.Session(lib, str(path))
+        mag, nrm, k4 = ctypes.c_float(0), (ctypes.c_float * 3)(), ctypes.c_float(0)
+        lib.Hamiltonian_Get_Anisotropy(x.state, ctypes.byref(mag), nrm, -1, -1)
+        lib.Hamiltonian_Get_Cubic_Anisotropy(x.state, ctypes.byref(k4), -1, -1)
+        vals.append((mag.value, tuple(nrm), k4.value))
+        x.close()
+    assert vals[0] == vals[1]
+
+
+def test_unsupported_hamiltonian_fails_state_setup(tmp_path, product):
+    """Input that asks for physics outside the library must not produce a State with a silently different Hamiltonian
+    (DESIGN.md 8): State_Setup returns NULL, as the reference does for a Hamiltonian it cannot build"""
+    from tests import cfgs
+    for extra in (["hamiltonian gaussian"], ["n_interaction_quadruplets 1", "i j da_j db_j dc_j k da_k db_k dc_k l da_l db_l dc_l Q",
+                                             "0 0 1 0 0 0 0 1 0 0 1 1 0 0 3.0"]):
+        path = tmp_path / "u.cfg"
+        text = cfgs.render("cubic256", n_basis_cells="4 3 2")
+        if extra[0].startswith("hamiltonian"):
+            text = "\n".join(l for l in text.split("\n") if not l.startswith("hamiltonian ")) + "\n"
+        path.write_text(text + "\n".join(extra) + "\n")
+        assert not product.State_Setup(str(path).encode(), True)

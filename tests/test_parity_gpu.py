@@ -99,6 +99,27 @@ def test_gradient_and_energy(cfg, product, oracle, preset, overrides, extra):
     o.close()
 
 
+@pytest.mark.parametrize("table", [["n_anisotropy 2", "i K Kx Ky Kz K4", "0 1.5 0 0 1 0.0", "1 0.7 1 1 0 0.25"],
+                                   ["n_anisotropy 2", "i Ka Kb Kc", "0 0.0 0.0 2.0", "1 0.5 0.5 0.0"]])
+def test_gradient_with_anisotropy_table(tmp_path, product, oracle, table):
+    """per-atom anisotropy tables (n_anisotropy): different axes and magnitudes on the two atoms of the basis, cubic term on one"""
+    from tests import cfgs
+    path = tmp_path / "a.cfg"
+    path.write_text(cfgs.render("cubic256", block=["basis", "2", "0 0 0", "0.5 0.5 0.5"] + table, n_basis_cells="6 5 4"))
+    p, o = S.Session(product, str(path)), S.Session(oracle, str(path))
+    s = unit_random(p.nos, 3)
+    gp, ep = p.gradient_and_energy(s)
+    go, eo = o.gradient_and_energy(s)
+    assert np.abs(gp - go).max() <= GRAD_RTOL * np.abs(go).max()
+    assert abs(ep - eo) <= 1e-11 * abs(eo)
+    cp, co = p.energy_contributions(s), o.energy_contributions(s)
+    assert list(cp.keys()) == list(co.keys())
+    for name in co:
+        assert abs(cp[name][0] - co[name][0]) <= 1e-11 * max(abs(co[name][0]), 1.0), name
+    p.close()
+    o.close()
+
+
 @pytest.mark.parametrize("preset,overrides,extra", [CASES[0], CASES[3], CASES[6], CASES[9]])
 def test_energy_contributions(cfg, product, oracle, preset, overrides, extra):
     p, o = make_case(cfg, product, oracle, preset, overrides, extra)
