@@ -388,6 +388,23 @@ def multi_gpu_parity(lib, tmp, dist, rank, world):
     return out
 
 
+def thermal_fp64_check(product_ms):
+    """The headline step of a build whose only difference is an fp64 Box-Muller (log, sqrt, sincospi) for the thermal variates:
+    what the fp32 / SFU shaping of the product buys. A check, not part of the product path."""
+    lib = "libSpirit_xi64.so"
+    if not os.path.exists(os.path.join(ROOT, "spirit_b200", lib)):
+        return {"unavailable": "spirit_b200/%s not built (__graft_entry__.build())" % lib}
+    try:
+        r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--steps", "50", "--warmup", "5", "--no-e2e",
+                            "--no-cpu-baseline", "--no-extras"], env=dict(os.environ, SPIRIT_B200_LIB=lib), capture_output=True,
+                           text=True, timeout=300)
+        d = json.loads([l for l in r.stdout.splitlines() if l.startswith("{")][-1])
+        return {"what": "same step, thermal variates shaped in fp64 (-DSB_THERMAL_FP64=1)", "ms_per_step": d["ms_per_step"],
+                "product_ms_per_step": product_ms, "slowdown": d["ms_per_step"] / product_ms}
+    except Exception as exc:  # noqa: BLE001
+        return {"error": "%s: %s" % (type(exc).__name__, str(exc)[:200])}
+
+
 def run_b200(args):
     rank, local_rank, world = dist_env()
     product = capi.load_product()
@@ -525,6 +542,11 @@ def run_b200(args):
             parity = multi_gpu_parity(product, tmp, dist, rank, world)
         configs["c5"] = config_c5(product, tmp, peak, dist, rank, world)
 
+    # ---- check: the same step with the thermal variates shaped in fp64 (build variant libSpirit_xi64.so, own process) ----------
+    checks = None
+    if rank == 0 and world == 1 and not args.no_extras:
+        checks = {"thermal_fp64": thermal_fp64_check(ms / args.steps)}
+
     # ---- CPU baseline beside it (rank 0, N = 1 only): the reference OpenMP build on a bounded sample ------------------
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
@@ -543,7 +565,7 @@ def run_b200(args):
             "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
             "data": "synthetic", "config": workload_config(args, cells), "clocks": clocks, "e2e": e2e,
             "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu, "configs": configs,
-            "multi_gpu_parity": parity,
+            "multi_gpu_parity": parity, "checks": checks,
         }
         print(json.dumps(line), flush=True)
     if dist is not None:

@@ -47,6 +47,11 @@ SPIRIT_API unsigned long long SpiritB200_Kernel_Launches( State * state, int idx
 /* Which stage kernels serve the image's Hamiltonian: 1 the nearest-neighbour marching kernels, 0 the generic gather
  * kernels; < 0 on error. No counterpart in the reference (its CUDA backend has one kernel per term). */
 SPIRIT_API int SpiritB200_Stencil_Variant( State * state, int idx_image ) SPIRIT_NOEXCEPT;
+/* Test probe: 3 * count normal variates of unit standard deviation exactly as the stage kernels draw them for the thermal
+ * field (Philox4x32-10 keyed by the image's llg_seed, counters 0 .. count - 1 of iteration `iteration`, Box-Muller). The
+ * reference draws std::normal_distribution<double> from one serial mt19937 (Method_LLG.cpp:98-108): only the distribution
+ * can be compared. Returns 0, or < 0 on error. */
+SPIRIT_API int SpiritB200_Thermal_Variates( State * state, unsigned long long iteration, unsigned long long count, float * variates, int idx_image ) SPIRIT_NOEXCEPT;
 /* Which kernels run one iteration of `solver_type` on the image with its current Hamiltonian and LLG parameters:
  * 2 ONE fused predictor + corrector kernel per iteration (Depondt / Heun / SIB on the nearest-neighbour stencil: spins read
  * once and written once), 1 one marching kernel per solver stage, 0 the generic gather kernels; < 0 on error. */

@@ -1,0 +1,22 @@
+#!/usr/bin/env python
+"""Cost of the hook iteration (the last iteration of a block also produces energy, max torque and the projected effective field):
+blocks of 1, 2, 5, 20 and 100 Depondt iterations on the 256^3 bench workload, CUDA-event time per block."""
+import os
+import sys
+import tempfile
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+from bench import fill_random, write_cfg  # noqa: E402
+from spirit_b200 import capi, session as S  # noqa: E402
+
+lib = capi.load_product()
+p = S.Session(lib, write_cfg(tempfile.mkdtemp(), (256, 256, 256)))
+fill_random(p)
+p.upload()
+p.iterate_device(S.SOLVER_DEPONDT, 20)
+for n in (1, 2, 5, 20, 100):
+    reps = max(3, 100 // n)
+    ms = sum(p.iterate_device(S.SOLVER_DEPONDT, n) for _ in range(reps)) / reps
+    print("block of %3d iterations: %.4f ms per block, %.4f ms per iteration" % (n, ms, ms / n), flush=True)
+p.close()

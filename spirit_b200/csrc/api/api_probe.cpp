@@ -213,6 +213,23 @@ catch( ... )
     return 0;
 }
 
+int SpiritB200_Thermal_Variates( State * state, unsigned long long iteration, unsigned long long count, float * variates, int idx_image ) noexcept
+try
+{
+    int idx_chain = -1;
+    auto image    = resolve( state, idx_image, idx_chain ).image;
+    ImageLock lock( *image );
+    dev::LLGParams l = Method_LLG::make_params( *image, dev::Solver_Depondt );
+    l.iteration      = iteration;
+    image->device().dump_thermal_variates( l, std::size_t( count ), variates );
+    return 0;
+}
+catch( ... )
+{
+    handle_exception_api( __func__, idx_image );
+    return -1;
+}
+
 int SpiritB200_Step_Variant( State * state, int solver_type, int idx_image ) noexcept
 try
 {

@@ -1552,6 +1552,19 @@ int DeviceImage::llg_profile_stages( int solver, LLGParams & llg, int n_iteratio
     return n_stages;
 }
 
+void DeviceImage::dump_thermal_variates( const LLGParams & llg, std::size_t count, float * host )
+{
+    auto & b    = *buf_;
+    float * dev = nullptr;
+    SB_CUDA_CHECK( cudaMalloc( &dev, 3 * count * sizeof( float ) ) );
+    k_dump_variates<<<unsigned( ( count + BLOCK_THREADS - 1 ) / BLOCK_THREADS ), BLOCK_THREADS, 0, b.stream>>>( llg, count, dev );
+    ++launches_;
+    SB_CUDA_CHECK( cudaGetLastError() );
+    SB_CUDA_CHECK( cudaMemcpyAsync( host, dev, 3 * count * sizeof( float ), cudaMemcpyDeviceToHost, b.stream ) );
+    SB_CUDA_CHECK( cudaStreamSynchronize( b.stream ) );
+    cudaFree( dev );
+}
+
 void DeviceImage::compute_ddi_gradient( int which )
 {
     if( !stencil_.has_ddi || !ddi_ )

@@ -123,6 +123,23 @@ static __global__ void __launch_bounds__( BLOCK_THREADS ) k_reduce_max( const do
         out[0] = v;
 }
 
+// Test probe: the normal variates the stage kernels draw, with unit standard deviation, for `count` consecutive Philox counters
+// (site in plane = i mod 2^20, plane = i / 2^20) of iteration l.iteration: out[3 i ..] = the three variates of counter i
+static __global__ void __launch_bounds__( BLOCK_THREADS ) k_dump_variates( const __grid_constant__ LLGParams l, std::size_t count, float * __restrict__ out )
+{
+    const std::size_t i = std::size_t( blockIdx.x ) * BLOCK_THREADS + threadIdx.x;
+    if( i >= count )
+        return;
+    unsigned r[4];
+    philox4x32_10(
+        unsigned( i & 0xfffffu ), unsigned( i >> 20 ), unsigned( l.iteration ), unsigned( l.iteration >> 32 ), unsigned( l.seed ),
+        unsigned( l.seed >> 32 ), r );
+    const float3 v = scaled_gaussian3f( r[0], r[1], r[2], r[3], -1.3862943611198906f ); // k = -2 ln 2: sigma = 1
+    out[3 * i + 0] = v.x;
+    out[3 * i + 1] = v.y;
+    out[3 * i + 2] = v.z;
+}
+
 // The two hook scalars of an iteration block in one launch: out[0] = sum of sums[0..n), out[1] = max of maxs[0..n)
 static __global__ void __launch_bounds__( BLOCK_THREADS )
     k_reduce_hook( const double * __restrict__ sums, const double * __restrict__ maxs, int n, double * __restrict__ out )

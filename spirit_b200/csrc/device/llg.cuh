@@ -70,26 +70,59 @@ __device__ __forceinline__ float sfu_cos( float x )
     asm( "cos.approx.ftz.f32 %0, %1;" : "=f"( y ) : "f"( x ) );
     return y;
 }
-// 23 random bits -> float in (2^-24, 1)
+// 23 random bits -> float in [1, 2): the angle of a Box-Muller pair in turns (sin / cos are periodic, no subtraction needed)
+__device__ __forceinline__ float unit_1_2( unsigned r )
+{
+    return __uint_as_float( ( r >> 9 ) | 0x3f800000u );
+}
+// Uniform in (0, 1) for the radius of a Box-Muller pair.
+//   default: 23 random bits, 1.mantissa - (1 - 2^-24): one integer and one fp32 instruction. The smallest value is 2^-24, so the
+//     radius stops at sqrt(-2 ln 2^-24) = 5.77 sigma; a normal variate lies beyond that with probability 8e-9
+//     (tests/test_thermal_variates_gpu.py: moments up to the sixth, distribution function and tails to 5 sigma on 1.2e8 samples).
+//   SB_THERMAL_TAIL32 = 1: all 32 bits, (r + 1/2) 2^-32 through an integer -> float conversion (exact for small r, the far
+//     tail): radius up to 6.76 sigma. The conversion runs on the quarter-rate pipe next to the 7 SFU instructions of the
+//     shaping: measured + 1.3 % on the whole Depondt step (profiles/r2o), which is why it is not the default.
+#ifndef SB_THERMAL_TAIL32
+#define SB_THERMAL_TAIL32 0
+#endif
 __device__ __forceinline__ float unit_open( unsigned r )
 {
+#if SB_THERMAL_TAIL32
+    return fmaf( __uint2float_rn( r ), 2.3283064365386963e-10f, 1.1641532182693481e-10f );
+#else
     return __uint_as_float( ( r >> 9 ) | 0x3f800000u ) - 0.99999994f;
+#endif
 }
 
+#ifndef SB_THERMAL_FP64
+#define SB_THERMAL_FP64 0 // 1: Box-Muller shaped in fp64 (log, sqrt, sincospi): the variant bench.py times beside the product
+#endif
+
 // Three normal variates of standard deviation sigma from four Philox words: Box-Muller shaped in fp32 with SFU
-// instructions (23-bit uniforms, |error| of sin/cos/lg2 ~ 1e-6): they are random numbers whose distribution, not whose
-// digits, matters (T > 0 parity is statistical), and an fp64 Box-Muller (log, sqrt, sincospi in software)
-// costs more instructions than the whole rest of a solver stage, which would make the step compute-bound instead of
-// HBM-bound. Everything downstream of the variates is fp64.
+// instructions (|error| of sin / cos / lg2 ~ 1e-6 absolute): they are random numbers whose distribution, not whose
+// digits, matters (T > 0 parity is statistical; tests/test_thermal_variates_gpu.py checks the first four
+// moments and the distribution function on 1e8 samples), and an fp64 Box-Muller (log, sqrt, sincospi in software)
+// costs more instructions than the whole rest of a solver stage (measured: bench.py `checks.thermal_fp64`). Everything
+// downstream of the variates is fp64.
 //   radius  sigma sqrt(-2 ln u) = sqrt(k lg2 u),  k = -2 ln2 sigma^2 (host constant, LLGParams::thermal_k)
-//   angle   2 pi v with v = 1.mantissa in [1, 2): the same point of the circle as v - 1, no subtraction needed
+//   angle   2 pi v with v = 1.mantissa in [1, 2): the same point of the circle as v - 1
 __device__ __forceinline__ float3 scaled_gaussian3f( unsigned r0, unsigned r1, unsigned r2, unsigned r3, float k )
 {
+#if SB_THERMAL_FP64
+    const double u0 = ( double( r0 ) + 0.5 ) * 2.3283064365386963e-10, u2 = ( double( r2 ) + 0.5 ) * 2.3283064365386963e-10;
+    const double kd = double( k ) * 1.4426950408889634; // k lg2 u = (k / ln 2) ln u
+    const double rad0 = sqrt( kd * log( u0 ) ), rad1 = sqrt( kd * log( u2 ) );
+    double s0, c0, s1, c1;
+    sincospi( 2.0 * ( double( r1 ) + 0.5 ) * 2.3283064365386963e-10, &s0, &c0 );
+    sincospi( 2.0 * ( double( r3 ) + 0.5 ) * 2.3283064365386963e-10, &s1, &c1 );
+    return make_float3( float( rad0 * c0 ), float( rad0 * s0 ), float( rad1 * s1 ) );
+#else
     const float rad0 = sfu_sqrt( k * sfu_lg2( unit_open( r0 ) ) );
     const float rad1 = sfu_sqrt( k * sfu_lg2( unit_open( r2 ) ) );
-    const float ang0 = 6.2831853071795865f * __uint_as_float( ( r1 >> 9 ) | 0x3f800000u );
-    const float ang1 = 6.2831853071795865f * __uint_as_float( ( r3 >> 9 ) | 0x3f800000u );
+    const float ang0 = 6.2831853071795865f * unit_1_2( r1 );
+    const float ang1 = 6.2831853071795865f * unit_1_2( r3 );
     return make_float3( rad0 * sfu_cos( ang0 ), rad0 * sfu_sin( ang0 ), rad1 * sfu_sin( ang1 ) );
+#endif
 }
 __device__ __forceinline__ D3 scaled_gaussian3( unsigned r0, unsigned r1, unsigned r2, unsigned r3, float k )
 {

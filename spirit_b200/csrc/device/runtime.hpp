@@ -129,6 +129,9 @@ public:
     void oso_reset();
 
     void synchronize();
+    // test probe: 3 * count unit normal variates of the thermal field's generator (Philox counters 0 .. count - 1 of
+    // iteration llg.iteration, the image's seed), as the stage kernels draw them
+    void dump_thermal_variates( const LLGParams & llg, std::size_t count, float * host );
 
     // Timing of the enqueued work on this image's stream (CUDA events), milliseconds
     void timer_start();

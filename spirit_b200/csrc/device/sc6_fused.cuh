@@ -42,6 +42,9 @@ namespace dev
 #ifndef SB_FUSED_S1_CONST
 #define SB_FUSED_S1_CONST 0 // interior CTAs with 16 rows: "this thread predicts" is a compile-time true
 #endif
+#ifndef SB_FUSED_PIN_SLOT
+#define SB_FUSED_PIN_SLOT 1
+#endif
 #ifndef SB_FUSED_PBELOW_REG
 #define SB_FUSED_PBELOW_REG 0 // 1: s'(c-1) of the own column kept in registers instead of re-read from shared memory
 #endif
@@ -197,7 +200,12 @@ __device__ __forceinline__ void sc6_fused_march(
             s1 = s1 && p.bc[1] && b == p.Nb;
         b = 0;
     }
-    const int so = ( j + 1 ) * FUSED_RS + ( i + 1 ); // own slot in a shared plane buffer
+    int so = ( j + 1 ) * FUSED_RS + ( i + 1 ); // own slot in a shared plane buffer
+#if SB_FUSED_PIN_SLOT
+    // opaque to the compiler from here on: it would otherwise recompute the slot from the thread index (a dozen instructions)
+    // before every use instead of keeping it in a register
+    asm volatile( "" : "+r"( so ) );
+#endif
 
     // ---- in-plane neighbours of the site in global memory (as sc6_march) ---------------------------------------------
     SC6Offsets o;
@@ -364,6 +372,19 @@ __device__ __forceinline__ void sc6_fused_march(
                     pa = ( BOUNDARY && !va2 ) ? zero : spn;
                 }
                 const D3 gp = sc6_gradient<SPEC, RARE>( p, pc, nxm, nxp, nbm, nbp, pb, pa, nullptr, 0u );
+                if( HOOK )
+                {
+                    // energy of the predictor configuration from its total gradient (site_energy, stencil.cuh):
+                    //   1/2 g_bilinear . s + E_cubic + E_zeeman  =  1/2 (g + g0) . s + K4/2 sum s^4      (g0 = -mu_s B)
+                    // (first thing after the gradient: nothing of it has to stay in registers for the end of the corrector)
+                    double e = 0.5 * ( ( gp.x + p.sc6_g0[0] ) * pc.x + ( gp.y + p.sc6_g0[1] ) * pc.y + ( gp.z + p.sc6_g0[2] ) * pc.z );
+                    if( RARE != 2 && p.has_cubic )
+                    {
+                        const double x2 = pc.x * pc.x, y2 = pc.y * pc.y, z2 = pc.z * pc.z;
+                        e += 0.5 * p.K4[0] * ( x2 * x2 + y2 * y2 + z2 * z2 );
+                    }
+                    e_acc += e;
+                }
                 const float3 xf = HAS_C ? xi_prev : xi;
                 D3 xid          = zero;
                 if( MODE == SC6_THERMAL )
@@ -397,15 +418,6 @@ __device__ __forceinline__ void sc6_fused_march(
                 }
                 if( HOOK )
                 {
-                    // energy of the predictor configuration from its total gradient (site_energy, stencil.cuh):
-                    //   1/2 g_bilinear . s + E_cubic + E_zeeman  =  1/2 (g + g0) . s + K4/2 sum s^4      (g0 = -mu_s B)
-                    double e = 0.5 * ( ( gp.x + p.sc6_g0[0] ) * pc.x + ( gp.y + p.sc6_g0[1] ) * pc.y + ( gp.z + p.sc6_g0[2] ) * pc.z );
-                    if( p.has_cubic )
-                    {
-                        const double x2 = pc.x * pc.x, y2 = pc.y * pc.y, z2 = pc.z * pc.z;
-                        e += 0.5 * p.K4[0] * ( x2 * x2 + y2 * y2 + z2 * z2 );
-                    }
-                    e_acc += e;
                     const double d = dot3( Fv_s, out );
                     const D3 tq    = make_d3( Fv_s.x - d * out.x, Fv_s.y - d * out.y, Fv_s.z - d * out.z );
                     t_acc          = fmax( t_acc, dot3( tq, tq ) );

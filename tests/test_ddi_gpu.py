@@ -129,3 +129,27 @@ def test_ddi_every_transform_length_vs_reference(cfg, product, oracle, axis, n_l
     assert abs(ep - eo) <= 1e-12 * np.abs(go).sum()
     p.close()
     o.close()
+
+
+def test_thin_film_reduced_size_vp_against_reference(cfg, product, oracle):
+    """configs[2] at the survey's reduced size: 256 x 256 x 4 open film, exchange + DMI + field + dipolar FFT convolution
+    (padded 512 x 512 x 8: the film kernels with the c-transforms in registers). Gradient and energy on a random state, then
+    30 VP iterations and 5 Depondt iterations against the reference's FFT path."""
+    path = cfg("cubic256", n_basis_cells="256 256 4", boundary_conditions="0 0 0", ddi_method="fft", ddi_n_periodic_images="0 0 0",
+               external_field_magnitude=25, anisotropy_magnitude=0, llg_temperature=0, llg_n_iterations_amortize=10)
+    p, o = S.Session(product, path), S.Session(oracle, path)
+    s0 = unit_random(p.nos, 17)
+    gp, ep = p.gradient_and_energy(s0)
+    go, eo = o.gradient_and_energy(s0)
+    assert np.abs(gp - go).max() <= 1e-12 * np.abs(go).max()
+    assert abs(ep - eo) <= 1e-11 * abs(eo)
+    for solver, n in (("VP", 30), ("Depondt", 5)):
+        for x in (p, o):
+            x.llg_set(temperature=0.0, damping=0.3, dt=1e-3)
+            x.set_spins(s0)
+            x.llg_start(S.SOLVERS[solver], n_iterations=n, n_iterations_log=n)
+        assert np.abs(o.spins() - s0).max() > 1e-4
+        assert np.abs(p.spins() - o.spins()).max() < 1e-10, solver
+        assert abs(p.energy() - o.energy()) <= 1e-10 * abs(o.energy()), solver
+    p.close()
+    o.close()
