@@ -206,9 +206,9 @@ def workload_config(args, cells):
             "ends store their two outermost planes into the neighbours' halo planes over NVLink (peer-mapped memory), ranks keep "
             "in step with stream memory operations: no collective on the data path" % (
                 args.gpus, cells[0], cells[1], cells[2] * args.gpus, cells[0], cells[1], cells[2])),
-        "e2e_call": "one Simulation_LLG_Start(Solver_Depondt, n_iterations=steps) call: spins in pinned host memory before, spins + "
-                    "effective field in host memory after (H2D 24 B/spin + D2H 48 B/spin inside the timed region), energy/torque "
-                    "read back every %d steps" % E2E_BLOCK,
+        "e2e_call": "one Simulation_LLG_Start(Solver_Depondt, n_iterations=steps) call: spins in pinned host memory before and after "
+                    "(H2D 24 B/spin + D2H 24 B/spin inside the timed region), energy/torque read back every %d steps; the effective "
+                    "field of the last hook stays on the device and is mirrored when System_Get_Effective_Field asks for it" % E2E_BLOCK,
     }
 
 
@@ -294,33 +294,75 @@ def config_c3(lib, tmp, peak):
 
 
 @guarded
-def config_c4(lib, tmp, peak):
+def config_c4(lib, tmp, peak, dist=None, rank=0, world=1):
     """configs[3]: GNEB skyrmion collapse, 64 images of 256x256x1 (the reference's solvers.cfg physics: the barrier of its own
-    GNEB test, core/test/test_solvers.cpp:74-103), climbing image, VP"""
-    p = S.Session(lib, write_cfg(tmp, (256, 256, 1), "c4.cfg", preset="solvers", gneb_n_iterations_amortize=50,
+    GNEB test, core/test/test_solvers.cpp:74-103), climbing image, VP. N > 1: whole images per GPU (64 / N consecutive images
+    each, SpiritB200_Chain_Shard_Setup): boundary images to the neighbouring ranks and the per-image scalars shared per force
+    evaluation; the same chain, so the barrier must be the N = 1 one."""
+    noi = 64
+    p = S.Session(lib, write_cfg(tmp, (256, 256, 1), "c4_%d.cfg" % rank, preset="solvers", gneb_n_iterations_amortize=50,
                                  llg_n_iterations_amortize=100, llg_force_convergence="1e-7"))
     p.plus_z()
     p.skyrmion(5.0, phase=-90.0)
     p.llg_set(direct_minimization=True)
     p.llg_start(S.SOLVER_VP, n_iterations=20000, n_iterations_log=20000)  # relax the metastable skyrmion of image 0
-    p.chain_set_length(64)
-    p.jump_to_image(63)
+    p.chain_set_length(noi)
+    p.jump_to_image(noi - 1)
     p.plus_z()
     p.jump_to_image(0)
-    p.transition_homogeneous(0, 63)
+    p.transition_homogeneous(0, noi - 1)
+    i_begin, n_local = 0, noi
+    if world > 1:
+        # every rank built the same initial chain on the host; it keeps its consecutive images
+        from spirit_b200 import slab
+        i_begin, n_local = slab.partition(noi, world)[rank]
+        images0 = [p.spins(i).copy() for i in range(i_begin, i_begin + n_local)]
+        p.close()
+        p = S.Session(lib, write_cfg(tmp, (256, 256, 1), "c4s_%d.cfg" % rank, preset="solvers", gneb_n_iterations_amortize=50))
+        p.chain_set_length(n_local)
+        for i in range(n_local):
+            p.set_spins(images0[i], idx_image=i)
+        if lib.SpiritB200_Chain_Shard_Setup(p.state, i_begin, noi) != 0:
+            raise RuntimeError("SpiritB200_Chain_Shard_Setup failed")
+
+    def energies():
+        rx, e = p.chain_rx_e()
+        if world == 1:
+            return np.asarray(e)
+        parts = [None] * world
+        dist.all_gather_object(parts, np.asarray(e))
+        return np.concatenate(parts)
+
     p.gneb_start(S.SOLVER_VP, n_iterations=3000, n_iterations_log=3000)
-    p.gneb_set_image_type_automatically()
+    if world == 1:
+        p.gneb_set_image_type_automatically()
+    else:  # Parameters_GNEB_Set_Image_Type_Automatically over the whole chain (maxima climb, minima fall)
+        e = energies()
+        for g in range(max(1, i_begin), min(noi - 1, i_begin + n_local)):
+            if e[g - 1] < e[g] > e[g + 1]:
+                p.gneb_set_image_type(S.GNEB_CLIMBING, g - i_begin)
+            elif e[g - 1] > e[g] < e[g + 1]:
+                p.gneb_set_image_type(S.GNEB_FALLING, g - i_begin)
     p.gneb_start(S.SOLVER_VP, n_iterations=3000, n_iterations_log=3000)
     n = 1000
+    if dist is not None:
+        dist.barrier()
     t0 = time.perf_counter()
     p.gneb_start(S.SOLVER_VP, n_iterations=n, n_iterations_log=n)
     dt = time.perf_counter() - t0
-    rx, e = p.chain_rx_e()
+    tq = float(p.chain_max_torque())
+    if dist is not None:
+        import torch
+        t = torch.tensor([dt, tq], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        dt, tq = float(t[0].item()), float(t[1].item())
+    e = energies()
     k = int(np.argmax(e))
     out = {"workload": "configs[3]: GNEB skyrmion collapse, 64 images of 256x256x1, climbing image (set automatically), VP; timed "
-                       "through Simulation_GNEB_Start incl. H2D / D2H of the chain",
-           "iterations_per_s": n / dt, "image_spin_steps_per_s": 64 * 65536 * n / dt, "barrier_meV": float(e[k] - e[0]),
-           "saddle_image": k, "max_torque": float(p.chain_max_torque()), "iterations_before_timing": 6000}
+                       "through Simulation_GNEB_Start incl. H2D / D2H of the chain; %s" % (
+                           "one GPU" if world == 1 else "%d images per GPU on %d GPUs (max over ranks)" % (noi // world, world)),
+           "n_gpus": world, "iterations_per_s": n / dt, "image_spin_steps_per_s": noi * 65536 * n / dt, "barrier_meV": float(e[k] - e[0]),
+           "saddle_image": k, "max_torque": tq, "iterations_before_timing": 6000}
     p.close()
     return out
 
@@ -512,8 +554,9 @@ def run_b200(args):
 
     # ---- end to end through the C API with host buffers ---------------------------------------------------------------------
     # ONE reference-facing call for the K timed steps: Simulation_LLG_Start(Solver_Depondt, n_iterations=K). Before the call
-    # the spins are in (pinned) host memory behind System_Get_Spin_Directions, after it spins AND effective field are back
-    # in host memory; every llg_n_iterations_amortize (= 100) steps the hook reads energy and max torque back to the host.
+    # the spins are in (pinned) host memory behind System_Get_Spin_Directions, after it the new spins are back there; every
+    # llg_n_iterations_amortize (= 100) steps the hook reads energy and max torque back to the host. (The effective field is
+    # mirrored lazily, on System_Get_Effective_Field: not part of this call.)
     e2e = None
     if not args.no_e2e:
         p.llg_start(S.SOLVER_DEPONDT, n_iterations=E2E_BLOCK, n_iterations_log=E2E_BLOCK)  # warm-up call
@@ -526,7 +569,7 @@ def run_b200(args):
         e2e_launches = p.kernel_launches() - l1
         n_hooks = max(1, args.steps // E2E_BLOCK)
         e2e = {"value": nos * world * args.steps / te, "unit": UNIT,
-               "h2d_bytes_per_step": 24.0 * nos / args.steps, "d2h_bytes_per_step": (48.0 * nos + 16.0 * n_hooks) / args.steps,
+               "h2d_bytes_per_step": 24.0 * nos / args.steps, "d2h_bytes_per_step": (24.0 * nos + 16.0 * n_hooks) / args.steps,
                "calls": 1, "iterations_per_call": args.steps, "seconds": te, "gpu_launches": int(e2e_launches)}
     p.close()
 
@@ -540,6 +583,8 @@ def run_b200(args):
             configs["c4"] = config_c4(product, tmp, peak)
         else:
             parity = multi_gpu_parity(product, tmp, dist, rank, world)
+            if 64 % world == 0:
+                configs["c4"] = config_c4(product, tmp, peak, dist, rank, world)
         configs["c5"] = config_c5(product, tmp, peak, dist, rank, world)
 
     # ---- check: the same step with the thermal variates shaped in fp64 (build variant libSpirit_xi64.so, own process) ----------

@@ -251,6 +251,20 @@ def gneb_two_stage_single_shots(model, imgs, types, k_spring, n_steps, solver):
             pred = [normalize(s + k) for s, k in zip(imgs, k1)]
             Fvp, E, Rx = fv(pred)
             imgs = [normalize(s + 0.5 * k - 0.5 * np.cross(sp, fp)) for s, k, sp, fp in zip(imgs, k1, pred, Fvp)]
+        elif solver == "RK4":
+            # Solver_RK4.hpp:41-147 over noi images (Method_GNEB.cpp:749 instantiates it; Simulation_GNEB_Start does not
+            # dispatch to it, so the compiled reference cannot be the oracle for this combination)
+            k1 = [-np.cross(s, f) for s, f in zip(imgs, Fv)]
+            pred = [normalize(s + 0.5 * k) for s, k in zip(imgs, k1)]
+            Fvp, _, _ = fv(pred)
+            k2 = [-np.cross(sp, fp) for sp, fp in zip(pred, Fvp)]
+            pred = [normalize(s + 0.5 * k) for s, k in zip(imgs, k2)]
+            Fvp, _, _ = fv(pred)
+            k3 = [-np.cross(sp, fp) for sp, fp in zip(pred, Fvp)]
+            pred = [normalize(s + k) for s, k in zip(imgs, k3)]
+            Fvp, E, Rx = fv(pred)
+            k4 = [-np.cross(sp, fp) for sp, fp in zip(pred, Fvp)]
+            imgs = [normalize(s + a / 6 + b / 3 + c / 3 + d / 6) for s, a, b, c, d in zip(imgs, k1, k2, k3, k4)]
         else:
             raise ValueError(solver)
     return imgs, E, Rx

@@ -165,12 +165,13 @@ try
         Log( Log_Level::Error, Log_Sender::API, "There are less than 3 images in the chain. GNEB cannot be started.", -1, idx_chain );
         return;
     }
-    // The reference offers VP, SIB, Depondt, Heun (and the OSO/LBFGS solvers) for GNEB but no RK4 branch (Simulation.cpp:278-303)
+    // The reference's API offers VP, SIB, Depondt, Heun and the OSO / LBFGS solvers for GNEB (Simulation.cpp:278-303); its
+    // engine also instantiates Method_GNEB<RK4> (Method_GNEB.cpp:749) without an API branch for it. Accepted here.
     if( solver_type != Solver_VP && solver_type != Solver_SIB && solver_type != Solver_Depondt && solver_type != Solver_Heun
-        && solver_type != Solver_LBFGS_OSO && solver_type != Solver_LBFGS_Atlas && solver_type != Solver_VP_OSO )
+        && solver_type != sb::dev::Solver_RK4 && solver_type != Solver_LBFGS_OSO && solver_type != Solver_LBFGS_Atlas && solver_type != Solver_VP_OSO )
     {
         Log( Log_Level::Error, Log_Sender::API,
-             "Solver " + std::to_string( solver_type ) + " is not available for GNEB in spirit_b200 (VP 0, SIB 1, Depondt 2, Heun 3, LBFGS_OSO 5, LBFGS_Atlas 6, VP_OSO 7). No action taken.",
+             "Solver " + std::to_string( solver_type ) + " is not available for GNEB in spirit_b200 (VP 0, SIB 1, Depondt 2, Heun 3, RK4 4, LBFGS_OSO 5, LBFGS_Atlas 6, VP_OSO 7). No action taken.",
              -1, idx_chain );
         return;
     }

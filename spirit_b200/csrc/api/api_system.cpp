@@ -34,7 +34,13 @@ SB_API_CATCH_RET( nullptr )
 scalar * System_Get_Effective_Field( State * state, int idx_image, int idx_chain ) noexcept
 try
 {
-    return resolve( state, idx_image, idx_chain ).image->effective_field.scalars();
+    auto image = resolve( state, idx_image, idx_chain ).image;
+    if( image->effective_field_stale )
+    {
+        ImageLock lock( *image );
+        image->refresh_effective_field_mirror(); // the field of the last hook is still on the device
+    }
+    return image->effective_field.scalars();
 }
 SB_API_CATCH_RET( nullptr )
 
@@ -105,6 +111,7 @@ try
 {
     auto image = resolve( state, idx_image, idx_chain ).image;
     ImageLock lock( *image );
+    image->refresh_effective_field_mirror();
     image->UpdateEnergy();
 }
 SB_API_CATCH_VOID

@@ -377,8 +377,8 @@ void Method_LLG::Sync_Host()
 {
     auto & d = system->device();
     d.download_spins( system->spins.scalars() );
-    d.download_effective_field( system->effective_field.scalars() );
-    system->device_is_newer = false;
+    system->effective_field_stale = true; // mirrored on demand (Spin_System::refresh_effective_field_mirror)
+    system->device_is_newer       = false;
 }
 
 void Method_LLG::Sync_Device()

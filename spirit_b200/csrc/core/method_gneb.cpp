@@ -46,13 +46,6 @@ Method_GNEB::Method_GNEB( std::shared_ptr<Chain> chain_, int solver_, int idx_ch
 {
     solver          = solver_;
     const auto & P  = *chain->gneb_parameters;
-    // Not implemented (none of them is on the BASELINE configurations): refuse loudly instead of computing something else
-    if( P.spring_force_ratio > 0 )
-        throw std::runtime_error( "spirit_b200: gneb_spring_force_ratio > 0 (energy-weighted springs) is not implemented" );
-    if( P.path_shortening_constant > 0 )
-        throw std::runtime_error( "spirit_b200: gneb_path_shortening_constant > 0 is not implemented" );
-    if( P.moving_endpoints || P.translating_endpoints )
-        throw std::runtime_error( "spirit_b200: GNEB moving / translating endpoints are not implemented" );
 
     // We assume that the chain is not converged before the first iteration (Method_GNEB.cpp:53-55)
     max_torque     = P.force_convergence + 1.0;
@@ -81,6 +74,14 @@ static dev::GNEBParams gneb_params( const Chain & chain )
     g.dtg             = g.dt * constants::gamma / constants::mu_B;
     for( int i = 0; i < chain.noi; ++i )
         g.image_type.push_back( int( chain.image_type[i] ) );
+    const auto & P               = *chain.gneb_parameters;
+    g.spring_force_ratio         = P.spring_force_ratio;
+    g.path_shortening_constant   = P.path_shortening_constant;
+    g.moving_endpoints           = P.moving_endpoints;
+    g.translating_endpoints      = P.translating_endpoints;
+    g.escape_first               = P.escape_first;
+    g.equilibrium_delta_Rx_left  = P.equilibrium_delta_Rx_left;
+    g.equilibrium_delta_Rx_right = P.equilibrium_delta_Rx_right;
     return g;
 }
 

@@ -63,7 +63,7 @@ Spin_System::Spin_System(
 Spin_System::Spin_System( const Spin_System & other )
         : nos( other.nos ),
           spins( other.spins ),
-          effective_field( other.effective_field ),
+          effective_field( ( const_cast<Spin_System &>( other ).refresh_effective_field_mirror(), other.effective_field ) ),
           E( other.E ),
           E_array( other.E_array ),
           M( other.M )
@@ -113,6 +113,16 @@ void Spin_System::UpdateEffectiveField()
     sync_to_device();
     device().update_effective_field();
     device().download_effective_field( effective_field.scalars() );
+    effective_field_stale = false;
+}
+
+void Spin_System::refresh_effective_field_mirror()
+{
+    if( !effective_field_stale )
+        return;
+    effective_field_stale = false;
+    if( device_ )
+        device_->download_effective_field( effective_field.scalars() );
 }
 
 // ---------------------------------------------------------------------------------------------

@@ -161,6 +161,8 @@ struct Spin_System
     }
     void drop_device()
     {
+        if( device_ && effective_field_stale )
+            refresh_effective_field_mirror(); // the field of the last run lives only there
         device_.reset();
     }
     // Push host spins / Hamiltonian to the device. While a method iterates on the device-resident spins the device copy is
@@ -169,6 +171,12 @@ struct Spin_System
     // of the last log step.
     void sync_to_device();
     bool device_is_newer = false; // set by the method's iterations, cleared when the host copy is refreshed (Sync_Host)
+    // The host mirror of the effective field is refreshed LAZILY: a finished LLG run leaves the field of its last hook on the
+    // device and marks the mirror stale; System_Get_Effective_Field (every call), System_Update_Data and the copy operations
+    // bring it up to date. The spins are mirrored eagerly (they are the state); the field is a derived quantity that most
+    // callers never read, and mirroring it doubles the device -> host traffic of every Simulation_*_Start call.
+    bool effective_field_stale = false;
+    void refresh_effective_field_mirror();
 
     // One-off evaluations on the device (Spin_System.cpp:115-141)
     void UpdateEnergy();

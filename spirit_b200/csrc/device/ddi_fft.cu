@@ -594,6 +594,89 @@ static __global__ void __launch_bounds__( FFT_THREADS, SB_FFT16_MINB ) k_fft_pas
     }
 }
 
+// ---------------------------------------------------------------------------------------------
+// The same pass as a PERSISTENT, software-pipelined kernel: every CTA walks tiles blockIdx.x, blockIdx.x + gridDim.x, ... of
+// the (o, column group) space with TWO tile buffers. The tile after the current one is fetched with 16-byte asynchronous
+// copies (cp.async / LDGSTS: global -> shared without passing through registers, zero-filled where the input is known to be
+// zero) issued before the butterflies of the current tile, so the memory system works under the radix stages instead of
+// waiting for them. One barrier per tile on top of those of the stages: a thread waits for its own copies, the barrier makes
+// everybody's visible AND says that the buffer of the previous tile has been stored and may be refilled.
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ void cp_async16( void * smem_dst, const void * src, bool nonzero )
+{
+    const unsigned dst = unsigned( __cvta_generic_to_shared( smem_dst ) );
+    const int bytes    = nonzero ? 16 : 0; // src-size 0: the 16 bytes are zero-filled, src is not read
+    asm volatile( "cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"( dst ), "l"( src ), "r"( bytes ) : "memory" );
+}
+__device__ __forceinline__ void cp_async_commit()
+{
+    asm volatile( "cp.async.commit_group;" ::: "memory" );
+}
+__device__ __forceinline__ void cp_async_wait_all()
+{
+    asm volatile( "cp.async.wait_group 0;" ::: "memory" );
+}
+
+template<bool INVERSE, int LOGN>
+static __global__ void __launch_bounds__( FFT_THREADS, SB_FFT16_MINB ) k_fft_pass16p(
+    const __grid_constant__ FFTPlan1D plan, const __grid_constant__ PassArgs a, const int lg_ncol, const int lg_in_split,
+    const int lg_out_split, const int n_tiles_u, const int n_tiles )
+{
+    extern __shared__ double2 smem[];
+    const int bufp = ( ( 1 << LOGN ) << lg_ncol ) + ( ( ( 1 << LOGN ) << lg_ncol ) >> 4 ) + 1; // elements per tile buffer
+    const int col = threadIdx.x & ( ( 1 << lg_ncol ) - 1 ), j0 = threadIdx.x >> lg_ncol, jstep = blockDim.x >> lg_ncol;
+    // exactly FFT_E elements per thread and tile (blockDim = (n / FFT_E) << lg_ncol)
+    auto fetch = [&]( int tile, double2 * buf )
+    {
+        const int o = tile / n_tiles_u, u = ( ( tile - o * n_tiles_u ) << lg_ncol ) + col;
+        const bool valid        = u < a.n_u;
+        const std::size_t base  = std::size_t( o ) * a.in_os + u;
+#pragma unroll
+        for( int k = 0; k < FFT_E; ++k )
+        {
+            const int j          = j0 + k * jstep;
+            const bool nonzero   = valid && j < a.n_in;
+            const double2 * src = a.in;
+            if( nonzero )
+                src = a.use_in_peer ? a.in_peer[j >> lg_in_split] + base + std::size_t( unsigned( j ) & ( ( 1u << lg_in_split ) - 1u ) ) * a.in_js
+                                    : a.in + base + pass_offset16( j, a.in_js, lg_in_split, a.in_split_stride );
+            cp_async16( buf + ( j << lg_ncol ) + col, src, nonzero );
+        }
+        cp_async_commit();
+    };
+    int tile  = blockIdx.x;
+    int stage = 0;
+    if( tile < n_tiles )
+        fetch( tile, smem );
+    for( ; tile < n_tiles; tile += gridDim.x, stage ^= 1 )
+    {
+        cp_async_wait_all();
+        __syncthreads();
+        if( tile + int( gridDim.x ) < n_tiles )
+            fetch( tile + gridDim.x, smem + ( stage ^ 1 ) * bufp );
+        double2 * x = smem + stage * bufp;
+        block_fft_ct<INVERSE, LOGN>( plan.twiddle, x, lg_ncol, col, j0 );
+        const int o = tile / n_tiles_u, u = ( ( tile - o * n_tiles_u ) << lg_ncol ) + col;
+        if( u < a.n_u )
+        {
+            const std::size_t base = std::size_t( o ) * a.out_os + u;
+#pragma unroll
+            for( int k = 0; k < FFT_E; ++k )
+            {
+                const int j = j0 + k * jstep;
+                if( j < a.n_out )
+                {
+                    const double2 w = x[( j << lg_ncol ) + col];
+                    double2 * dst   = a.use_out_peer
+                                          ? a.out_peer[j >> lg_out_split] + base + std::size_t( unsigned( j ) & ( ( 1u << lg_out_split ) - 1u ) ) * a.out_js
+                                          : a.out + base + pass_offset16( j, a.out_js, lg_out_split, a.out_split_stride );
+                    *dst = make_double2( a.scale * w.x, a.scale * w.y );
+                }
+            }
+        }
+    }
+}
+
 // Pass a for a dense REAL input (setup of the tensor spectrum): real row of length n -> half spectrum
 static __global__ void __launch_bounds__( FFT_THREADS ) k_fft_real_rows(
     const __grid_constant__ FFTPlan1D plan, const double * __restrict__ in, double2 * __restrict__ out, int Ha )
@@ -627,7 +710,15 @@ struct DDIDims
     // single device: c_block = Nc, q_stride = Nc Pb Ha (plain [q][c][kb][ka]); distributed: one block per source rank
     int c_block;
     std::size_t block_stride, q_stride;
+    // Mirror symmetries of the tensor spectrum of one sublattice on an orthorhombic, axis-aligned lattice: D_aa is even in
+    // every k, D_ab (a != b) odd in k_a and k_b. Bit 0: only kc <= Pc / 2 is stored, bit 1: only kb <= Pb / 2 (one device);
+    // the multiply kernels read the mirrored entry with the sign of the component. Verified numerically at setup.
+    int mirror;
 };
+__device__ __host__ __forceinline__ int mirror_len( int P, bool on )
+{
+    return on ? P / 2 + 1 : P;
+}
 __device__ __forceinline__ std::size_t c_operand( const DDIDims & d, int q, int c )
 {
     return std::size_t( c / d.c_block ) * d.block_stride + std::size_t( q ) * d.q_stride + std::size_t( c % d.c_block ) * ( std::size_t( d.Pb ) * d.Ha );
@@ -771,12 +862,16 @@ static __global__ void __launch_bounds__( FFT_THREADS, SB_FFT16_MINB ) k_ddi_c_m
     const bool valid       = u0 + col < d.Ha;
     const std::size_t plane = std::size_t( d.Pb ) * d.Ha;
     double2 * column       = B + std::size_t( kb ) * d.Ha + u0 + col;
-    // element (q, c) of the column: c_operand without divisions (c = j0 + k jstep walks the per-rank blocks in order)
+    // mirrored tensor (REAL_D only): row kbr of the stored spectrum, n_kc entries along kc, signs of the odd components
+    const bool mir_c = REAL_D && ( d.mirror & 1 ), mir_b = REAL_D && ( d.mirror & 2 ) && 2 * kb > d.Pb;
+    const int kbr    = mir_b ? d.Pb - kb : kb;
+    const double sgb = mir_b ? -1.0 : 1.0;
+    const int tile_d = mirror_len( n, mir_c ) << lg_ncol; // elements of one component of the CTA's tensor block
     // pull the tensor block of this CTA towards L2 while the spectra are loaded and transformed
     {
         const std::size_t elem  = REAL_D ? sizeof( double ) : sizeof( double2 );
-        const std::size_t bytes = 6 * std::size_t( tile_elems ) * elem;
-        const char * Dblock     = static_cast<const char *>( Dt_v ) + ( std::size_t( kb ) * gridDim.x + blockIdx.x ) * bytes;
+        const std::size_t bytes = 6 * std::size_t( tile_d ) * elem;
+        const char * Dblock     = static_cast<const char *>( Dt_v ) + ( std::size_t( kbr ) * gridDim.x + blockIdx.x ) * bytes;
         for( std::size_t off = std::size_t( threadIdx.x ) * 128; off < bytes; off += std::size_t( blockDim.x ) * 128 )
             asm volatile( "prefetch.global.L2 [%0];" ::"l"( Dblock + off ) );
     }
@@ -811,7 +906,7 @@ static __global__ void __launch_bounds__( FFT_THREADS, SB_FFT16_MINB ) k_ddi_c_m
     for( int q = 0; q < 3; ++q )
         block_fft_ct<false, LOGN>( plan.twiddle, smem + q * bufp, lg_ncol, col, j0 );
     {
-        const std::size_t block = ( std::size_t( kb ) * gridDim.x + blockIdx.x ) * 6 * std::size_t( tile_elems );
+        const std::size_t block = ( std::size_t( kbr ) * gridDim.x + blockIdx.x ) * 6 * std::size_t( tile_d );
 #pragma unroll 4
         for( int item = threadIdx.x; item < tile_elems; item += blockDim.x )
         {
@@ -819,9 +914,13 @@ static __global__ void __launch_bounds__( FFT_THREADS, SB_FFT16_MINB ) k_ddi_c_m
             double2 fx, fy, fz;
             if( REAL_D )
             {
-                const double * Dp = static_cast<const double *>( Dt_v ) + block + item;
-                const double Dxx = __ldg( Dp ), Dxy = __ldg( Dp + tile_elems ), Dxz = __ldg( Dp + 2 * tile_elems );
-                const double Dyy = __ldg( Dp + 3 * tile_elems ), Dyz = __ldg( Dp + 4 * tile_elems ), Dzz = __ldg( Dp + 5 * tile_elems );
+                const int kc       = item >> lg_ncol;
+                const bool up      = mir_c && 2 * kc > n;
+                const int item_d   = up ? ( ( n - kc ) << lg_ncol ) + ( item & ( ncol - 1 ) ) : item;
+                const double sgc   = up ? -1.0 : 1.0;
+                const double * Dp = static_cast<const double *>( Dt_v ) + block + item_d;
+                const double Dxx = __ldg( Dp ), Dxy = sgb * __ldg( Dp + tile_d ), Dxz = sgc * __ldg( Dp + 2 * tile_d );
+                const double Dyy = __ldg( Dp + 3 * tile_d ), Dyz = sgb * sgc * __ldg( Dp + 4 * tile_d ), Dzz = __ldg( Dp + 5 * tile_d );
                 fx = make_double2( Dxx * sx.x + Dxy * sy.x + Dxz * sz.x, Dxx * sx.y + Dxy * sy.y + Dxz * sz.y );
                 fy = make_double2( Dxy * sx.x + Dyy * sy.x + Dyz * sz.x, Dxy * sx.y + Dyy * sy.y + Dyz * sz.y );
                 fz = make_double2( Dxz * sx.x + Dyz * sy.x + Dzz * sz.x, Dxz * sx.y + Dyz * sy.y + Dzz * sz.y );
@@ -867,7 +966,10 @@ static __global__ void k_ddi_tile_tensor( const __grid_constant__ DDIDims d, con
     const int ka = int( i % d.Ha ), kb = int( ( i / d.Ha ) % d.Pb ), kc = int( ( i / ( std::size_t( d.Ha ) * d.Pb ) ) % d.Pc );
     const int comp = int( i / half );
     const int ntiles = ( d.Ha + ( 1 << lg_ncol ) - 1 ) >> lg_ncol;
-    const std::size_t tile_elems = std::size_t( d.Pc ) << lg_ncol;
+    // mirrored storage (REAL_D; d.mirror bit 1 only on one device, where d.Pb is the whole axis): the upper halves are dropped
+    if( REAL_D && ( ( ( d.mirror & 1 ) && 2 * kc > d.Pc ) || ( ( d.mirror & 2 ) && 2 * kb > d.Pb ) ) )
+        return;
+    const std::size_t tile_elems = std::size_t( mirror_len( d.Pc, REAL_D && ( d.mirror & 1 ) ) ) << lg_ncol;
     const std::size_t o = ( ( std::size_t( kb ) * ntiles + ( ka >> lg_ncol ) ) * 6 + comp ) * tile_elems + ( std::size_t( kc ) << lg_ncol )
                           + ( ka & ( ( 1 << lg_ncol ) - 1 ) );
     if( REAL_D )
@@ -928,7 +1030,12 @@ static __global__ void __launch_bounds__( 128 ) k_ddi_c_mult_small(
         return;
     const std::size_t c_stride = std::size_t( d.Pb ) * d.Ha;
     const std::size_t col      = std::size_t( kb ) * d.Ha + ka;
-    const std::size_t dcomp    = std::size_t( PC ) * d.Pb * d.Ha;
+    // tensor: [comp6][kc][kb][ka], with REAL_D possibly mirrored (DDIDims::mirror): [comp6][kc <= PC/2][kb <= Pb/2][ka]
+    const bool mir_c = REAL_D && ( d.mirror & 1 ), mir_b = REAL_D && ( d.mirror & 2 ) && 2 * kb > d.Pb;
+    const double sgb = mir_b ? -1.0 : 1.0;
+    const std::size_t d_cstride = std::size_t( mirror_len( d.Pb, REAL_D && ( d.mirror & 2 ) ) ) * d.Ha;
+    const std::size_t d_col     = std::size_t( mir_b ? d.Pb - kb : kb ) * d.Ha + ka;
+    const std::size_t dcomp     = std::size_t( mirror_len( PC, mir_c ) ) * d_cstride;
     double2 sx[PC], sy[PC], sz[PC];
 #pragma unroll
     for( int j = 0; j < PC; ++j )
@@ -944,13 +1051,15 @@ static __global__ void __launch_bounds__( 128 ) k_ddi_c_mult_small(
 #pragma unroll
     for( int kc = 0; kc < PC; ++kc )
     {
-        const std::size_t dk = std::size_t( kc ) * c_stride + col;
+        const bool up        = mir_c && 2 * kc > PC;
+        const double sgc     = up ? -1.0 : 1.0;
+        const std::size_t dk = std::size_t( up ? PC - kc : kc ) * d_cstride + d_col;
         double2 fx, fy, fz;
         if( REAL_D )
         {
             const double * Dp = static_cast<const double *>( Dhat_v ) + dk;
-            const double Dxx = __ldg( Dp ), Dxy = __ldg( Dp + dcomp ), Dxz = __ldg( Dp + 2 * dcomp );
-            const double Dyy = __ldg( Dp + 3 * dcomp ), Dyz = __ldg( Dp + 4 * dcomp ), Dzz = __ldg( Dp + 5 * dcomp );
+            const double Dxx = __ldg( Dp ), Dxy = sgb * __ldg( Dp + dcomp ), Dxz = sgc * __ldg( Dp + 2 * dcomp );
+            const double Dyy = __ldg( Dp + 3 * dcomp ), Dyz = sgb * sgc * __ldg( Dp + 4 * dcomp ), Dzz = __ldg( Dp + 5 * dcomp );
             fx = make_double2( Dxx * sx[kc].x + Dxy * sy[kc].x + Dxz * sz[kc].x, Dxx * sx[kc].y + Dxy * sy[kc].y + Dxz * sz[kc].y );
             fy = make_double2( Dxy * sx[kc].x + Dyy * sy[kc].x + Dyz * sz[kc].x, Dxy * sx[kc].y + Dyy * sy[kc].y + Dyz * sz[kc].y );
             fz = make_double2( Dxz * sx[kc].x + Dyz * sy[kc].x + Dzz * sz[kc].x, Dxz * sx[kc].y + Dyz * sy[kc].y + Dzz * sz[kc].y );
@@ -997,11 +1106,41 @@ static __global__ void k_ddi_imag_check( const double2 * __restrict__ D, std::si
     if( threadIdx.x == 0 )
         out[2 * blockIdx.x + 1] = ma;
 }
-static __global__ void k_ddi_take_real( const double2 * __restrict__ in, double * __restrict__ out, std::size_t n )
+// real parts of D^[comp6][kc][kb][ka] -> [comp6][kc < n_kc][kb < n_kb][ka] (n_k = P / 2 + 1 along a mirrored axis, else P)
+static __global__ void k_ddi_take_real( const __grid_constant__ DDIDims d, const double2 * __restrict__ in, double * __restrict__ out )
 {
+    const int n_kc = mirror_len( d.Pc, d.mirror & 1 ), n_kb = mirror_len( d.Pb, d.mirror & 2 );
+    const std::size_t n = std::size_t( 6 ) * n_kc * n_kb * d.Ha;
     const std::size_t i = blockIdx.x * std::size_t( blockDim.x ) + threadIdx.x;
-    if( i < n )
-        out[i] = in[i].x;
+    if( i >= n )
+        return;
+    const int ka = int( i % d.Ha ), kb = int( ( i / d.Ha ) % n_kb ), kc = int( ( i / ( std::size_t( d.Ha ) * n_kb ) ) % n_kc );
+    const int comp = int( i / ( std::size_t( d.Ha ) * n_kb * n_kc ) );
+    out[i] = in[( ( std::size_t( comp ) * d.Pc + kc ) * d.Pb + kb ) * d.Ha + ka].x;
+}
+// max | D^(.., P - k, ..) - sign D^(.., k, ..) | for the mirror along c (out[2 blk]) and along b (out[2 blk + 1]), sign = -1 for
+// the components that are odd along that axis (xz, yz along c; xy, yz along b). d.Pb must be the whole b axis for the b check.
+static __global__ void k_ddi_mirror_check( const __grid_constant__ DDIDims d, const double2 * __restrict__ D, double * __restrict__ out )
+{
+    const std::size_t half = std::size_t( d.Pc ) * d.Pb * d.Ha;
+    double mc = 0, mb = 0;
+    for( std::size_t i = blockIdx.x * std::size_t( blockDim.x ) + threadIdx.x; i < 6 * half; i += std::size_t( gridDim.x ) * blockDim.x )
+    {
+        const int ka = int( i % d.Ha ), kb = int( ( i / d.Ha ) % d.Pb ), kc = int( ( i / ( std::size_t( d.Ha ) * d.Pb ) ) % d.Pc );
+        const int comp = int( i / half );
+        const double v = D[i].x;
+        const double sc = ( comp == 2 || comp == 4 ) ? -1.0 : 1.0, sb = ( comp == 1 || comp == 4 ) ? -1.0 : 1.0;
+        const std::size_t ic = ( ( std::size_t( comp ) * d.Pc + ( d.Pc - kc ) % d.Pc ) * d.Pb + kb ) * d.Ha + ka;
+        const std::size_t ib = ( ( std::size_t( comp ) * d.Pc + kc ) * d.Pb + ( d.Pb - kb ) % d.Pb ) * d.Ha + ka;
+        mc = fmax( mc, fabs( D[ic].x - sc * v ) );
+        mb = fmax( mb, fabs( D[ib].x - sb * v ) );
+    }
+    mc = block_max( mc );
+    if( threadIdx.x == 0 )
+        out[2 * blockIdx.x] = mc;
+    mb = block_max( mb );
+    if( threadIdx.x == 0 )
+        out[2 * blockIdx.x + 1] = mb;
 }
 
 // 5: inverse a-pass (C2R through a complex transform of the Hermitian-extended row) fused with
@@ -1262,6 +1401,7 @@ struct DDIPlan
         bool on = false;
         int lg = 0, threads = 0; // lg(columns or rows per CTA), CTA size
         int lg_seq = 0;          // b-pass: lg(column groups a CTA transforms one after the other)
+        int pipe_ctas = 0;       // > 0: the persistent pipelined kernel (k_fft_pass16p) with this many CTAs (two tile buffers in smem)
         std::size_t smem = 0;
     } fast_a, fast_b, fast_c;
     FFTPlan1D plan_ah;             // length Pa / 2
@@ -1396,6 +1536,20 @@ template<bool INVERSE>
 void launch_pass16(
     const DDIPlan::Fast & f, dim3 grid, cudaStream_t stream, const FFTPlan1D & plan, const PassArgs & a, int lg_in, int lg_out, bool configure = false )
 {
+    if( f.pipe_ctas && !configure )
+    {
+        const int n_tiles_u = ( a.n_u + ( 1 << f.lg ) - 1 ) >> f.lg, n_tiles = n_tiles_u * a.n_o;
+        const dim3 pgrid( std::min( n_tiles, f.pipe_ctas ) );
+        switch( ilog2( plan.n ) )
+        {
+#define C( L )                                                                                                         \
+    case L: k_fft_pass16p<INVERSE, L><<<pgrid, f.threads, f.smem, stream>>>( plan, a, f.lg, lg_in, lg_out, n_tiles_u, n_tiles ); break;
+            SB_FOR_LOGN( C )
+#undef C
+            default: throw std::logic_error( "spirit_b200: no fast pass kernel for this length" );
+        }
+        return;
+    }
     switch( ilog2( plan.n ) )
     {
 #define C( L )                                                                                                         \
@@ -1413,6 +1567,37 @@ void launch_pass16(
 #undef C
         default: throw std::logic_error( "spirit_b200: no fast pass kernel for this length" );
     }
+}
+// The pipelined pass: two tile buffers; persistent grid = CTAs that fit on the device at once. Returns false (and leaves f
+// unchanged) when two buffers do not fit into shared memory.
+bool configure_pass16_pipelined( DDIPlan::Fast & f, int n )
+{
+    const std::size_t smem = 2 * ( ( std::size_t( n ) << f.lg ) * 17 / 16 + 1 ) * sizeof( double2 );
+    if( smem > std::size_t( 220 * 1024 ) )
+        return false;
+    int dev = 0, sms = 0, per_sm_f = 0, per_sm_i = 0;
+    SB_CUDA_CHECK( cudaGetDevice( &dev ) );
+    SB_CUDA_CHECK( cudaDeviceGetAttribute( &sms, cudaDevAttrMultiProcessorCount, dev ) );
+    switch( ilog2( n ) )
+    {
+#define C( L )                                                                                                         \
+    case L:                                                                                                            \
+        allow_smem( k_fft_pass16p<false, L>, smem );                                                                   \
+        allow_smem( k_fft_pass16p<true, L>, smem );                                                                    \
+        SB_CUDA_CHECK( cudaOccupancyMaxActiveBlocksPerMultiprocessor( &per_sm_f, k_fft_pass16p<false, L>, f.threads, smem ) ); \
+        SB_CUDA_CHECK( cudaOccupancyMaxActiveBlocksPerMultiprocessor( &per_sm_i, k_fft_pass16p<true, L>, f.threads, smem ) );  \
+        break;
+        SB_FOR_LOGN( C )
+#undef C
+        default: return false;
+    }
+    const int per_sm = std::min( per_sm_f, per_sm_i );
+    if( per_sm < 1 )
+        return false;
+    f.smem      = smem;
+    f.lg_seq    = 0;
+    f.pipe_ctas = per_sm * sms;
+    return true;
 }
 template<bool REAL_D>
 void launch_c_mult16(
@@ -1612,7 +1797,19 @@ DDIPlan * ddi_plan_create( const Hamiltonian & ham, const StencilParams & sp, cu
         plan->fast_b.on = plan->fast_b.on && d.Pb <= 4096;
         plan->fast_c.on = plan->fast_c.on && d.Pc <= 4096;
         plan->fast_a.on = plan->fast_a.on && d.Pa / 2 <= 4096;
-        if( plan->fast_b.on )
+        if( plan->fast_b.on && !env_flag_off( "SPIRIT_B200_FFT_PIPE_B" ) )
+        {
+            // persistent pipelined b-pass; its own tile width (columns per CTA) may differ from the plain kernel's
+            DDIPlan::Fast f = plan->fast_b;
+            if( const char * v = std::getenv( "SPIRIT_B200_FFT_PIPE_LG_B" ) )
+            {
+                f.lg      = std::max( 0, std::min( 5, std::atoi( v ) ) );
+                f.threads = ( d.Pb >> FFT_LG_E ) << f.lg;
+            }
+            if( f.threads >= 32 && f.threads <= FFT_THREADS && configure_pass16_pipelined( f, d.Pb ) )
+                plan->fast_b = f;
+        }
+        if( plan->fast_b.on && !plan->fast_b.pipe_ctas )
         {
             launch_pass16<false>( plan->fast_b, dim3(), stream, plan->plan[1], PassArgs{}, 0, 0, true );
             launch_pass16<true>( plan->fast_b, dim3(), stream, plan->plan[1], PassArgs{}, 0, 0, true );
@@ -1780,10 +1977,45 @@ DDIPlan * ddi_plan_create( const Hamiltonian & ham, const StencilParams & sp, cu
         // The imaginary parts are pure round-off of the forward transforms (a few ulp of the largest element times
         // log2 P): mathematically zero. 1e-12 relative is 4 orders above what is observed and far below any signal.
         spectrum_real = max_imag <= 1e-12 * max_abs;
+        // Mirror symmetries (orthorhombic axis-aligned lattices, open or padded directions): checked on the spectrum itself,
+        // along c on every rank's kb range (all ranks must agree), along b on one device only (a rank holds a kb block).
+        if( spectrum_real && d.n_inter == 1 && !env_flag_off( "SPIRIT_B200_DDI_MIRROR" ) )
+        {
+            double * mpart = nullptr;
+            SB_CUDA_CHECK( cudaMalloc( &mpart, 2 * blocks * sizeof( double ) ) );
+            k_ddi_mirror_check<<<blocks, BLOCK_THREADS, 0, stream>>>( dc, plan->Dhat, mpart );
+            SB_CUDA_CHECK( cudaMemcpyAsync( h.data(), mpart, h.size() * sizeof( double ), cudaMemcpyDeviceToHost, stream ) );
+            SB_CUDA_CHECK( cudaStreamSynchronize( stream ) );
+            double dev_c = 0, dev_b = 0;
+            for( int i = 0; i < blocks; ++i )
+            {
+                dev_c = std::max( dev_c, h[2 * i] );
+                dev_b = std::max( dev_b, h[2 * i + 1] );
+            }
+            if( world > 1 )
+            {
+                double all = dev_c;
+                SB_CUDA_CHECK( cudaMemcpyAsync( mpart, &all, sizeof( all ), cudaMemcpyHostToDevice, stream ) );
+                comm_allreduce( mpart, 1, true, stream );
+                SB_CUDA_CHECK( cudaMemcpyAsync( &all, mpart, sizeof( all ), cudaMemcpyDeviceToHost, stream ) );
+                SB_CUDA_CHECK( cudaStreamSynchronize( stream ) );
+                dev_c = all;
+            }
+            cudaFree( mpart );
+            int mirror = 0;
+            if( dev_c <= 1e-12 * max_abs )
+                mirror |= 1;
+            if( world == 1 && dev_b <= 1e-12 * max_abs )
+                mirror |= 2;
+            if( std::getenv( "SPIRIT_B200_DDI_VERBOSE" ) )
+                std::fprintf( stderr, "spirit_b200 ddi: mirror deviations c %.3e b %.3e -> mirror %d\n", dev_c, dev_b, mirror );
+            plan->dims.mirror = plan->dims_c.mirror = dc.mirror = mirror;
+        }
         if( spectrum_real && small_c )
         {
-            SB_CUDA_CHECK( cudaMalloc( &plan->Dhat_real, n_all * sizeof( double ) ) );
-            k_ddi_take_real<<<unsigned( ( n_all + 255 ) / 256 ), 256, 0, stream>>>( plan->Dhat, plan->Dhat_real, n_all );
+            const std::size_t n_kept = std::size_t( 6 ) * mirror_len( dc.Pc, dc.mirror & 1 ) * mirror_len( dc.Pb, dc.mirror & 2 ) * dc.Ha;
+            SB_CUDA_CHECK( cudaMalloc( &plan->Dhat_real, n_kept * sizeof( double ) ) );
+            k_ddi_take_real<<<unsigned( ( n_kept + 255 ) / 256 ), 256, 0, stream>>>( dc, plan->Dhat, plan->Dhat_real );
             SB_CUDA_CHECK( cudaStreamSynchronize( stream ) );
             cudaFree( plan->Dhat );
             plan->Dhat = nullptr;
@@ -1794,7 +2026,7 @@ DDIPlan * ddi_plan_create( const Hamiltonian & ham, const StencilParams & sp, cu
         // re-order the spectrum into the tiles k_ddi_c_mult16 reads (one sublattice: 6 components)
         const int lg            = plan->fast_c.lg;
         const std::size_t tiles = std::size_t( ( d.Ha + ( 1 << lg ) - 1 ) >> lg );
-        const std::size_t n_t   = std::size_t( kbl ) * tiles * 6 * ( std::size_t( d.Pc ) << lg );
+        const std::size_t n_t   = std::size_t( mirror_len( kbl, dc.mirror & 2 ) ) * tiles * 6 * ( std::size_t( mirror_len( d.Pc, dc.mirror & 1 ) ) << lg );
         plan->Dt_real           = spectrum_real;
         const std::size_t bytes = n_t * ( spectrum_real ? sizeof( double ) : sizeof( double2 ) );
         SB_CUDA_CHECK( cudaMalloc( &plan->Dt, bytes ) );

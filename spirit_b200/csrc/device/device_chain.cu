@@ -46,15 +46,27 @@ enum Slot
     S_RX,     // reaction coordinate
     S_TT,     // t.t
     S_FT,     // P(F_g).t = F_g.t
+    S_PG2,    // |P(F_g)|^2                       (the three after S_FT are reduced together with it)
+    S_TP2,    // |s(i+1) - s(i)|^2   of the images' spins (path shortening)
+    S_TM2,    // |s(i) - s(i-1)|^2
+    S_SHG,    // f . F_go   f = secant difference, F_go = gradient force orthogonal to the tangent (path shortening)
+    S_SHT,    // f . t
+    S_SHF,    // f . f
+    S_CG,     // coefficient of P(F_g) in the total force (1; the rotational coefficient at moving end images)
     S_CT,     // coefficient of t in the total force
+    S_CSH,    // path shortening: F += csh ( f - sha F_go - shb t )
+    S_SHA,
+    S_SHB,
+    S_LEN,    // length of the path segment ending at this image in normalised (Rx, E) (energy-weighted springs)
     S_ZERO,   // 1: the total force of this image is zero (end image / stationary)
     S_TQ,     // max torque^2 (hook)
     S_VP,     // partial v.F per image
     S_VP2,    // partial F.F per image
     S_N_SLOTS
 };
-// global scalars behind the per-image slots: [0] ratio_prev, [1] ratio, [2] degenerate flag
-constexpr int G_RATIO_PREV = 0, G_RATIO = 1, G_DEGENERATE = 2, G_N = 4;
+// global scalars behind the per-image slots: [0] ratio_prev, [1] ratio, [2] degenerate flag, [3] / [4] translation of the
+// left / right end image along its tangent (translating endpoints)
+constexpr int G_RATIO_PREV = 0, G_RATIO = 1, G_DEGENERATE = 2, G_TRANS_L = 3, G_TRANS_R = 4, G_N = 6;
 
 struct ChainView
 {
@@ -65,11 +77,16 @@ struct ChainView
     double * F;   // total force of the first evaluation of the iteration ("forces")
     double * F2;  // total force of the predictor evaluation / new force of VP
     double * Fpr; // VP: force projected by the hook (F_prev of the next iteration)
+    double * P2;  // RK4: second predictor configuration
+    double * Acc; // RK4: running sum k1/6 + k2/3 + k3/3
     std::size_t stride; // doubles per image and field
     double * scal;      // [S_N_SLOTS][noi] + G_N   (noi = GLOBAL number of images)
     int noi;            // global number of images of the chain
     int n_local;        // images held by this rank: global indices [i_begin, i_begin + n_local)
     int i_begin;
+    int moving_endpoints; // the end images feel a force too (Method_GNEB.cpp:261-355)
+    int shortening;       // path shortening force on the normal images
+    double * Ddi;         // dipolar gradient field of the evaluated configurations (null without dipolar interaction)
 };
 // Field pointers are offset by one image, so that local index -1 / n_local address the halo images received from the
 // neighbouring ranks (images sharded over GPUs); unsharded chains have no halo and i_begin = 0.
@@ -132,9 +149,10 @@ static __global__ void __launch_bounds__( BLOCK_THREADS ) k_chain_gradient(
     if( active )
     {
         const ConstField3 s  = cfield( conf, v.stride, img );
-        const ConstField3 no = cfield( conf, v.stride, img ); // no DDI field in the chain path
+        // dipolar field of this image's configuration (computed before this kernel, one convolution per image); unused without
+        const ConstField3 dd = cfield( v.Ddi ? v.Ddi : conf, v.stride, img );
         const D3 si          = load3( s, site.idx );
-        const SiteGradient g = site_gradient<NB_T>( p, s, no, site, si );
+        const SiteGradient g = site_gradient<NB_T>( p, s, dd, site, si );
         const D3 gt          = total( g );
         store3( field( v.Fg, v.stride, img ), site.idx, make_d3( -gt.x, -gt.y, -gt.z ) );
         e = site_energy<NB_T>( p, site, si, g );
@@ -179,7 +197,7 @@ static __global__ void __launch_bounds__( BLOCK_THREADS ) k_chain_tangent(
     const int g   = v.i_begin + img;
     Site site;
     const bool active = locate_site( p, lg, site, p.NB );
-    double tt = 0, ft = 0;
+    double tt = 0, ft = 0, pg2 = 0, tp2 = 0, tm2 = 0;
     if( active )
     {
         const D3 s = load3( cfield( conf, v.stride, img ), site.idx );
@@ -235,16 +253,121 @@ static __global__ void __launch_bounds__( BLOCK_THREADS ) k_chain_tangent(
         const D3 Fg = load3( cfield( v.Fg, v.stride, img ), site.idx );
         // projected gradient force . tangent (for interior images t is perpendicular to s, so this is also F_g.t)
         const double d = dot3( Fg, s );
-        ft             = ( Fg.x - d * s.x ) * t.x + ( Fg.y - d * s.y ) * t.y + ( Fg.z - d * s.z ) * t.z;
+        const D3 Pg    = make_d3( Fg.x - d * s.x, Fg.y - d * s.y, Fg.z - d * s.z );
+        ft             = dot3( Pg, t );
+        pg2            = dot3( Pg, Pg );
         if( g == 0 || g == v.noi - 1 )
             ft = dot3( Fg, t ); // dE/dRx at the end images uses the unprojected effective field (Method_GNEB.cpp:433-437)
+        else if( v.shortening )
+        {
+            // secants of the IMAGES' spins (not of a predictor configuration: Method_GNEB.cpp:209-214 reads chain->images)
+            const D3 s0 = load3( cfield( v.S, v.stride, img ), site.idx );
+            const D3 sp = load3( cfield( v.S, v.stride, img + 1 ), site.idx );
+            const D3 sm = load3( cfield( v.S, v.stride, img - 1 ), site.idx );
+            const D3 a  = make_d3( sp.x - s0.x, sp.y - s0.y, sp.z - s0.z );
+            const D3 b  = make_d3( s0.x - sm.x, s0.y - sm.y, s0.z - sm.z );
+            tp2         = dot3( a, a );
+            tm2         = dot3( b, b );
+        }
     }
-    tt = block_sum( tt );
-    if( threadIdx.x == 0 )
-        partials[( std::size_t( 0 ) * v.n_local + img ) * nblocks + blockIdx.x] = tt;
-    ft = block_sum( ft );
-    if( threadIdx.x == 0 )
-        partials[( std::size_t( 1 ) * v.n_local + img ) * nblocks + blockIdx.x] = ft;
+    const double vals[5] = { tt, ft, pg2, tp2, tm2 };
+    for( int k = 0; k < ( v.shortening || v.moving_endpoints ? 5 : 2 ); ++k )
+    {
+        const double r = block_sum( vals[k] );
+        if( threadIdx.x == 0 )
+            partials[( std::size_t( k ) * v.n_local + img ) * nblocks + blockIdx.x] = r;
+    }
+}
+
+// Path shortening (Method_GNEB.cpp:206-233), second pass: with the norms of the secants and of the gradient force known, the
+// scalar products of f = t+/|t+| - t-/|t-| with the gradient force orthogonal to the tangent, with the tangent and with itself
+__device__ __forceinline__ D3 chain_secant_difference( const ChainView & v, int img, std::size_t idx )
+{
+    const int g     = v.i_begin + img;
+    const double ip = rsqrt( slot( v, S_TP2 )[g] ), im = rsqrt( slot( v, S_TM2 )[g] );
+    const D3 s0     = load3( cfield( v.S, v.stride, img ), idx );
+    const D3 sp     = load3( cfield( v.S, v.stride, img + 1 ), idx );
+    const D3 sm     = load3( cfield( v.S, v.stride, img - 1 ), idx );
+    return make_d3(
+        ( sp.x - s0.x ) * ip - ( s0.x - sm.x ) * im, ( sp.y - s0.y ) * ip - ( s0.y - sm.y ) * im, ( sp.z - s0.z ) * ip - ( s0.z - sm.z ) * im );
+}
+static __global__ void __launch_bounds__( BLOCK_THREADS ) k_chain_shrink(
+    const __grid_constant__ StencilParams p, const __grid_constant__ LaunchGeom lg, const __grid_constant__ ChainView v,
+    const double * __restrict__ conf, double * __restrict__ partials, int nblocks )
+{
+    const int img = blockIdx.y;
+    const int g   = v.i_begin + img;
+    Site site;
+    const bool active = locate_site( p, lg, site, p.NB );
+    double vals[3]    = { 0, 0, 0 };
+    if( active && g > 0 && g < v.noi - 1 )
+    {
+        const D3 s      = load3( cfield( conf, v.stride, img ), site.idx );
+        const D3 Fg     = load3( cfield( v.Fg, v.stride, img ), site.idx );
+        const D3 t      = load3( cfield( v.T, v.stride, img ), site.idx );
+        const double d  = dot3( Fg, s );
+        const double c  = slot( v, S_FT )[g] / slot( v, S_TT )[g];
+        const D3 Fgo    = make_d3( Fg.x - d * s.x - c * t.x, Fg.y - d * s.y - c * t.y, Fg.z - d * s.z - c * t.z );
+        const D3 f      = chain_secant_difference( v, img, site.idx );
+        vals[0]         = dot3( f, Fgo );
+        vals[1]         = dot3( f, t );
+        vals[2]         = dot3( f, f );
+    }
+    for( int k = 0; k < 3; ++k )
+    {
+        const double r = block_sum( vals[k] );
+        if( threadIdx.x == 0 )
+            partials[( std::size_t( k ) * v.n_local + img ) * nblocks + blockIdx.x] = r;
+    }
+}
+
+// Translating endpoints (Method_GNEB.cpp:268-305): the two end images are pushed along their tangents by the mean of their
+// gradient forces, the force of the other end rotated site by site from the other end's spin onto this one. One launch over
+// the sites; partial sums of F_translation_left . t_0 and F_translation_right . t_last (t not normalised here).
+__device__ __forceinline__ D3 rotate_between( const D3 & from, const D3 & to, const D3 & x, bool transpose )
+{
+    // rotation about from x to by the angle between them (Eigen::AngleAxis); identity for collinear spins
+    const double c = dot3( from, to );
+    if( fabs( c ) >= 1.0 )
+        return x;
+    D3 axis        = cross3( from, to );
+    const double n = sqrt( dot3( axis, axis ) );
+    if( n == 0 )
+        return x;
+    axis            = make_d3( axis.x / n, axis.y / n, axis.z / n );
+    const double an = transpose ? -acos( c ) : acos( c );
+    const double sn = sin( an ), cs = cos( an );
+    const D3 axx    = cross3( axis, x );
+    const double ad = dot3( axis, x ) * ( 1 - cs );
+    return make_d3( x.x * cs + axx.x * sn + axis.x * ad, x.y * cs + axx.y * sn + axis.y * ad, x.z * cs + axx.z * sn + axis.z * ad );
+}
+static __global__ void __launch_bounds__( BLOCK_THREADS ) k_chain_translation(
+    const __grid_constant__ StencilParams p, const __grid_constant__ LaunchGeom lg, const __grid_constant__ ChainView v,
+    const double * __restrict__ conf, double * __restrict__ partials, int nblocks )
+{
+    Site site;
+    const bool active = locate_site( p, lg, site, p.NB );
+    double vals[2]    = { 0, 0 };
+    if( active )
+    {
+        const int last = v.noi - 1;
+        const D3 cl = load3( cfield( conf, v.stride, 0 ), site.idx ), cr = load3( cfield( conf, v.stride, last ), site.idx );
+        D3 Fl = load3( cfield( v.Fg, v.stride, 0 ), site.idx ), Fr = load3( cfield( v.Fg, v.stride, last ), site.idx );
+        const double dl = dot3( Fl, cl ), dr = dot3( Fr, cr ); // gradient forces projected to the tangent planes of the configurations
+        Fl = make_d3( Fl.x - dl * cl.x, Fl.y - dl * cl.y, Fl.z - dl * cl.z );
+        Fr = make_d3( Fr.x - dr * cr.x, Fr.y - dr * cr.y, Fr.z - dr * cr.z );
+        const D3 sl = load3( cfield( v.S, v.stride, 0 ), site.idx ), sr = load3( cfield( v.S, v.stride, last ), site.idx ); // images' spins
+        const D3 Frr = rotate_between( sl, sr, Fr, false ), Flr = rotate_between( sl, sr, Fl, true );
+        const D3 tl = load3( cfield( v.T, v.stride, 0 ), site.idx ), tr = load3( cfield( v.T, v.stride, last ), site.idx );
+        vals[0]     = -0.5 * ( ( Fl.x + Frr.x ) * tl.x + ( Fl.y + Frr.y ) * tl.y + ( Fl.z + Frr.z ) * tl.z );
+        vals[1]     = -0.5 * ( ( Flr.x + Fr.x ) * tr.x + ( Flr.y + Fr.y ) * tr.y + ( Flr.z + Fr.z ) * tr.z );
+    }
+    for( int k = 0; k < 2; ++k )
+    {
+        const double r = block_sum( vals[k] );
+        if( threadIdx.x == 0 )
+            partials[std::size_t( k ) * nblocks + blockIdx.x] = r;
+    }
 }
 
 struct ChainTypes
@@ -252,28 +375,134 @@ struct ChainTypes
     int type[256];
 };
 
-// Per-image coefficients of the total force (Method_GNEB.cpp:175-258), one thread per image
-static __global__ void k_chain_coeffs( const __grid_constant__ ChainView v, const __grid_constant__ ChainTypes types, double spring_constant )
+struct ChainForceParams
+{
+    double spring_constant, spring_force_ratio, path_shortening_constant;
+    int moving_endpoints, translating_endpoints, escape_first;
+    double delta_Rx0_left, delta_Rx0_right;
+    int nos;
+};
+
+// Energy-weighted springs (Method_GNEB.cpp:137-170): lengths of the path segments in the normalised (Rx, E) plane from a cubic
+// Hermite interpolation of the energy along the path (Cubic_Hermite_Spline.cpp:11-48) with 20 points per segment. One thread.
+static __global__ void k_chain_lengths( const __grid_constant__ ChainView v, double ratio )
+{
+    const double * Rx = slot( v, S_RX );
+    const double * E  = slot( v, S_E );
+    double * len      = slot( v, S_LEN );
+    const int noi = v.noi, n_int = 20;
+    const double ratio_E = fmin( 1.0, ratio ), ratio_Rx = 1 - ratio_E;
+    auto slope = [&]( int i ) { // dE/dRx as the reference takes it: effective field . normalised tangent
+        const double tt = slot( v, S_TT )[i];
+        return tt > 0 ? slot( v, S_FT )[i] / sqrt( tt ) : 0.0;
+    };
+    auto point = [&]( int i, int j, double & x, double & e ) { // interpolation point j of segment i (j = 0: image i)
+        const double t   = j / double( n_int + 1 );
+        const double t2 = t * t, t3 = t2 * t;
+        const double h00 = 2 * t3 - 3 * t2 + 1, h10 = -2 * t3 + 3 * t2, h01 = t3 - 2 * t2 + t, h11 = t3 - t2;
+        x                = Rx[i] + t * ( Rx[i + 1] - Rx[i] );
+        e                = h00 * E[i] + h10 * E[i + 1] + h01 * slope( i ) * ( Rx[i] - Rx[i + 1] ) + h11 * slope( i + 1 ) * ( Rx[i] - Rx[i + 1] );
+    };
+    // ranges of the interpolated curve
+    double xmin = Rx[noi - 1], xmax = Rx[noi - 1], emin = E[noi - 1], emax = E[noi - 1];
+    for( int i = 0; i < noi - 1; ++i )
+        for( int j = 0; j <= n_int; ++j )
+        {
+            double x, e;
+            point( i, j, x, e );
+            xmin = fmin( xmin, x ), xmax = fmax( xmax, x ), emin = fmin( emin, e ), emax = fmax( emax, e );
+        }
+    const double range_Rx = xmax - xmin, range_E = emax - emin;
+    len[0] = 0;
+    for( int img = 1; img < noi; ++img )
+    {
+        double l = 0, x0, e0;
+        point( img - 1, 0, x0, e0 );
+        for( int j = 1; j <= n_int + 1; ++j )
+        {
+            double x1, e1;
+            if( j <= n_int )
+                point( img - 1, j, x1, e1 );
+            else if( img < noi - 1 )
+                point( img, 0, x1, e1 );
+            else
+                x1 = Rx[noi - 1], e1 = E[noi - 1];
+            // the reference sums i = 1 .. n_interpolations of its flat index: the last sub-interval of a segment (up to the
+            // next image) belongs to the sum of that segment only through idx = (img - 1)(n + 1) + i <= img (n + 1) - 1
+            if( j <= n_int )
+            {
+                const double dRx = ratio_Rx * ( x1 - x0 ) / range_Rx, dE = ratio_E * ( e1 - e0 ) / range_E;
+                l += sqrt( dRx * dRx + dE * dE );
+            }
+            x0 = x1, e0 = e1;
+        }
+        len[img] = l * range_Rx;
+    }
+}
+
+// Per-image coefficients of the total force (Method_GNEB.cpp:175-355), one thread per image:
+//   F = cg P(F_g) + ct t + csh ( f - sha F_go - shb t )
+static __global__ void k_chain_coeffs( const __grid_constant__ ChainView v, const __grid_constant__ ChainTypes types, const __grid_constant__ ChainForceParams P )
 {
     const int img = blockIdx.x * blockDim.x + threadIdx.x; // local image; types are indexed locally
     if( img >= v.n_local )
         return;
     const int g = v.i_begin + img;
-    double ct = 0, zero = 0;
-    if( g == 0 || g == v.noi - 1 || types.type[img] == 3 )
+    double cg = 1, ct = 0, zero = 0, csh = 0, sha = 0, shb = 0;
+    const double tt = slot( v, S_TT )[g], ft = slot( v, S_FT )[g];
+    const double * Rx = slot( v, S_RX );
+    const bool end    = g == 0 || g == v.noi - 1;
+    if( end && P.moving_endpoints )
+    {
+        // rotational part of the gradient force + spring towards the equilibrium distance to the neighbour + translation
+        double rc = 1;
+        if( P.escape_first )
+        {
+            const double pl = slot( v, S_FT )[0] / sqrt( slot( v, S_TT )[0] );
+            const double pr = slot( v, S_FT )[v.noi - 1] / sqrt( slot( v, S_TT )[v.noi - 1] );
+            if( pl > pr )
+                rc = 0;
+        }
+        const double nt         = sqrt( tt );
+        const double projection = ft / nt; // F_gradient . normalised tangent
+        const double delta_Rx0  = g == 0 ? P.delta_Rx0_left : P.delta_Rx0_right;
+        const double delta_Rx   = g == 0 ? Rx[1] - Rx[0] : Rx[v.noi - 1] - Rx[v.noi - 2];
+        const double k          = ( g == 0 ? 1.0 : -1.0 ) * P.spring_constant;
+        // project_parallel( F_translation, normalised tangent ): (sum F_translation . t / |t|) t / |t|
+        const double alpha = P.translating_endpoints ? globals( v )[g == 0 ? G_TRANS_L : G_TRANS_R] / tt : 0.0;
+        cg                 = rc;
+        ct                 = ( -rc * projection + k * ( delta_Rx - delta_Rx0 ) ) / nt + alpha;
+    }
+    else if( end || types.type[img] == 3 )
         zero = 1;
+    else if( types.type[img] == 1 ) // climbing: invert the component along the tangent
+        ct = -2.0 * ft / tt;
+    else if( types.type[img] == 2 ) // falling: gradient force only
+        ct = 0;
     else
     {
-        const double tt = slot( v, S_TT )[g], ft = slot( v, S_FT )[g];
-        const double * Rx = slot( v, S_RX );
-        if( types.type[img] == 1 ) // climbing: invert the component along the tangent
-            ct = -2.0 * ft / tt;
-        else if( types.type[img] == 2 ) // falling: gradient force only
-            ct = 0;
-        else // normal: orthogonal to the tangent + spring force along it
-            ct = -ft / tt + spring_constant * ( Rx[g + 1] - 2 * Rx[g] + Rx[g - 1] ) / sqrt( tt );
+        // normal: orthogonal to the tangent + spring force along it
+        const double d = P.spring_force_ratio > 0 ? P.spring_constant * ( slot( v, S_LEN )[g + 1] - slot( v, S_LEN )[g] )
+                                                  : P.spring_constant * ( Rx[g + 1] - 2 * Rx[g] + Rx[g - 1] );
+        ct             = -ft / tt + d / sqrt( tt );
+        if( P.path_shortening_constant > 0 )
+        {
+            // f projected orthogonally to the normalised gradient force and to the normalised tangent (orthogonal to each
+            // other), normalised, scaled by max( |F_go|, nos * constant )
+            const double go2      = slot( v, S_PG2 )[g] - ft * ft / tt; // |F_go|^2
+            const double gradnorm = sqrt( go2 );
+            const double fg = slot( v, S_SHG )[g], fT = slot( v, S_SHT )[g], ff = slot( v, S_SHF )[g];
+            sha               = fg / go2; // ( f . F_go / |F_go| ) F_go / |F_go|
+            shb               = fT / tt;
+            const double n2   = ff - fg * fg / go2 - fT * fT / tt;
+            csh               = fmax( gradnorm, P.nos * P.path_shortening_constant ) / sqrt( n2 );
+        }
     }
+    slot( v, S_CG )[g]   = cg;
     slot( v, S_CT )[g]   = ct;
+    slot( v, S_CSH )[g]  = csh;
+    slot( v, S_SHA )[g]  = sha;
+    slot( v, S_SHB )[g]  = shb;
     slot( v, S_ZERO )[g] = zero;
 }
 
@@ -286,8 +515,19 @@ __device__ __forceinline__ D3 chain_total_force( const ChainView & v, int img, s
     const D3 Fg     = load3( cfield( v.Fg, v.stride, img ), idx );
     const D3 t      = load3( cfield( v.T, v.stride, img ), idx );
     const double d  = dot3( Fg, s );
-    const double ct = slot( v, S_CT )[g];
-    return make_d3( Fg.x - d * s.x + ct * t.x, Fg.y - d * s.y + ct * t.y, Fg.z - d * s.z + ct * t.z );
+    const double cg = slot( v, S_CG )[g], ct = slot( v, S_CT )[g];
+    const D3 Pg     = make_d3( Fg.x - d * s.x, Fg.y - d * s.y, Fg.z - d * s.z );
+    D3 F            = make_d3( cg * Pg.x + ct * t.x, cg * Pg.y + ct * t.y, cg * Pg.z + ct * t.z );
+    const double csh = slot( v, S_CSH )[g];
+    if( csh != 0.0 )
+    {
+        const double c = slot( v, S_FT )[g] / slot( v, S_TT )[g], sha = slot( v, S_SHA )[g], shb = slot( v, S_SHB )[g];
+        const D3 f     = chain_secant_difference( v, img, idx );
+        F.x += csh * ( f.x - sha * ( Pg.x - c * t.x ) - shb * t.x );
+        F.y += csh * ( f.y - sha * ( Pg.y - c * t.y ) - shb * t.y );
+        F.z += csh * ( f.z - sha * ( Pg.z - c * t.z ) - shb * t.z );
+    }
+    return F;
 }
 
 // VP, part A (Solver_VP.hpp:29-79): F_new, v = ratio_prev F_old + (F_prev + F_new)/2, partial sums of v.F_new, F_new.F_new
@@ -371,6 +611,20 @@ static __global__ void __launch_bounds__( BLOCK_THREADS ) k_chain_vp_b(
     }
 }
 
+// Total force of every image at configuration `conf` into F2. Needed before a kernel that overwrites the images' spins when the
+// force reads the NEIGHBOURING images' spins (path shortening: the secants are taken between the images, Method_GNEB.cpp:209-214):
+// computed inside the updating kernel, a thread could read a neighbour's spin that is already updated.
+static __global__ void __launch_bounds__( BLOCK_THREADS ) k_chain_force_at(
+    const __grid_constant__ StencilParams p, const __grid_constant__ LaunchGeom lg, const __grid_constant__ ChainView v, const double * __restrict__ conf )
+{
+    const int img = blockIdx.y;
+    Site site;
+    if( !locate_site( p, lg, site, p.NB ) )
+        return;
+    const D3 c = load3( cfield( conf, v.stride, img ), site.idx );
+    store3( field( v.F2, v.stride, img ), site.idx, chain_total_force( v, img, site.idx, c ) );
+}
+
 // Stages of the two-stage solvers over all images. Virtual force: Fv = dtg s x F, zero for the end images
 // (Method_GNEB.cpp:359-391). Stage 1 assembles F(s) and writes the predictor; stage 2 assembles F(s') and updates s.
 template<int SOLVER, int STAGE>
@@ -382,7 +636,7 @@ static __global__ void __launch_bounds__( BLOCK_THREADS ) k_chain_stage(
     if( !locate_site( p, lg, site, p.NB ) )
         return;
     const int g    = v.i_begin + img;
-    const bool end = g == 0 || g == v.noi - 1;
+    const bool end = !v.moving_endpoints && ( g == 0 || g == v.noi - 1 );
     const D3 s     = load3( cfield( v.S, v.stride, img ), site.idx );
     D3 acc         = make_d3( 0, 0, 0 );
     if( STAGE == 1 )
@@ -400,8 +654,10 @@ static __global__ void __launch_bounds__( BLOCK_THREADS ) k_chain_stage(
     else
     {
         const D3 sp = load3( cfield( v.P, v.stride, img ), site.idx );
-        const D3 F2 = chain_total_force( v, img, site.idx, sp );
-        store3( field( v.F2, v.stride, img ), site.idx, F2 );
+        // with path shortening F2 was computed by k_chain_force_at before this launch (it reads the neighbours' spins)
+        const D3 F2 = v.shortening ? load3( cfield( v.F2, v.stride, img ), site.idx ) : chain_total_force( v, img, site.idx, sp );
+        if( !v.shortening )
+            store3( field( v.F2, v.stride, img ), site.idx, F2 );
         D3 Fv = make_d3( 0, 0, 0 ), Fvp = make_d3( 0, 0, 0 );
         if( !end )
         {
@@ -413,6 +669,43 @@ static __global__ void __launch_bounds__( BLOCK_THREADS ) k_chain_stage(
         }
         store3( field( v.S, v.stride, img ), site.idx, solver_update<SOLVER, 2>( s, Fv, sp, Fvp, acc ) );
     }
+}
+
+// RK4 over all images (Solver_RK4.hpp:41-147): stage n evaluates the force at configuration n (s, s + k1/2, s + k2/2, s + k3),
+// k_n = -(conf_n x Fv_n) with Fv = dtg conf x F (zero at the end images), and the new spins are |s + k1/6 + k2/3 + k3/3 + k4/6|.
+// `conf` is the configuration the force was just evaluated at, `out` the configuration this stage writes.
+template<int STAGE>
+static __global__ void __launch_bounds__( BLOCK_THREADS ) k_chain_rk4(
+    const __grid_constant__ StencilParams p, const __grid_constant__ LaunchGeom lg, const __grid_constant__ ChainView v, double dtg,
+    const double * __restrict__ conf, double * __restrict__ out )
+{
+    const int img = blockIdx.y;
+    Site site;
+    if( !locate_site( p, lg, site, p.NB ) )
+        return;
+    const int g    = v.i_begin + img;
+    const bool end = !v.moving_endpoints && ( g == 0 || g == v.noi - 1 );
+    const D3 s     = load3( cfield( v.S, v.stride, img ), site.idx );
+    const D3 c     = STAGE == 1 ? s : load3( cfield( conf, v.stride, img ), site.idx );
+    const D3 F     = ( STAGE == 4 && v.shortening ) ? load3( cfield( v.F2, v.stride, img ), site.idx ) // k_chain_force_at ran before
+                                                    : chain_total_force( v, img, site.idx, c );
+    if( STAGE == 1 )
+        store3( field( v.F, v.stride, img ), site.idx, F ); // "forces": the hook projects the force of the first evaluation
+    if( STAGE == 4 && !v.shortening )
+        store3( field( v.F2, v.stride, img ), site.idx, F ); // F_total of the last evaluation: max torque
+    D3 Fv = make_d3( 0, 0, 0 );
+    if( !end )
+    {
+        const D3 x = cross3( c, F );
+        Fv         = make_d3( dtg * x.x, dtg * x.y, dtg * x.z );
+    }
+    D3 acc = make_d3( 0, 0, 0 );
+    if( STAGE > 1 )
+        acc = load3( cfield( v.Acc, v.stride, img ), site.idx );
+    const D3 o = solver_update<Solver_RK4, STAGE>( s, Fv, c, Fv, acc );
+    if( STAGE < 4 )
+        store3( field( v.Acc, v.stride, img ), site.idx, acc );
+    store3( field( out, v.stride, img ), site.idx, o );
 }
 
 // OSO / atlas minimisers over the chain: total force of every image into F2 (hook, atlas gradient) and s x F into F
@@ -460,7 +753,9 @@ struct DeviceChainBuffers
 {
     cudaStream_t stream = nullptr;
     double * fields     = nullptr; // 7 x [noi][stride]
-    double * partials   = nullptr; // [2][noi][nblocks]
+    double * ddi        = nullptr; // dipolar gradient fields of the evaluated configurations [noi + 2][stride] (on demand)
+    double * rk4        = nullptr; // RK4: second predictor and accumulator, 2 x [noi + 2][stride] (on demand)
+    double * partials   = nullptr; // [5][noi][nblocks]
     double * scal       = nullptr;
     double * h_scal     = nullptr; // pinned mirror
     double * staging    = nullptr; // AoS [nos][3]
@@ -472,6 +767,10 @@ struct DeviceChainBuffers
     {
         if( fields )
             cudaFree( fields );
+        if( ddi )
+            cudaFree( ddi );
+        if( rk4 )
+            cudaFree( rk4 );
         if( partials )
             cudaFree( partials );
         if( scal )
@@ -508,7 +807,7 @@ DeviceChain::DeviceChain( const Geometry & geometry, int noi, int i_begin, int n
     SB_CUDA_CHECK( cudaStreamCreateWithFlags( &b.stream, cudaStreamNonBlocking ) );
     SB_CUDA_CHECK( cudaMalloc( &b.fields, 7 * fs * sizeof( double ) ) );
     SB_CUDA_CHECK( cudaMemset( b.fields, 0, 7 * fs * sizeof( double ) ) );
-    SB_CUDA_CHECK( cudaMalloc( &b.partials, 2 * std::size_t( noi ) * T.nblocks * sizeof( double ) ) );
+    SB_CUDA_CHECK( cudaMalloc( &b.partials, 5 * std::size_t( noi ) * T.nblocks * sizeof( double ) ) );
     SB_CUDA_CHECK( cudaMalloc( &b.scal, b.n_scal * sizeof( double ) ) );
     SB_CUDA_CHECK( cudaMemset( b.scal, 0, b.n_scal * sizeof( double ) ) );
     SB_CUDA_CHECK( cudaHostAlloc( &b.h_scal, b.n_scal * sizeof( double ), cudaHostAllocDefault ) );
@@ -525,15 +824,39 @@ DeviceChain::DeviceChain( const Geometry & geometry, int noi, int i_begin, int n
     b.view.noi     = noi_global_;
     b.view.n_local = noi_;
     b.view.i_begin = i_begin_;
+    b.view.moving_endpoints = 0;
+    b.view.shortening       = 0;
+    b.view.Ddi              = nullptr;
+    b.view.P2               = nullptr;
+    b.view.Acc              = nullptr;
+}
+
+void DeviceChain::ensure_ddi_field()
+{
+    auto & b = *buf_;
+    if( b.ddi )
+        return;
+    const std::size_t fs = std::size_t( noi_ + 2 ) * b.stride;
+    SB_CUDA_CHECK( cudaMalloc( &b.ddi, fs * sizeof( double ) ) );
+    SB_CUDA_CHECK( cudaMemset( b.ddi, 0, fs * sizeof( double ) ) );
 }
 
 DeviceChain::~DeviceChain() = default;
 
 void DeviceChain::set_hamiltonian( const Hamiltonian & ham )
 {
+    // every image is evaluated with this Hamiltonian (Method_GNEB.cpp:99-100 calls each image's own; they are copies of one
+    // another in a chain); with a dipolar term one convolution per image and evaluation fills the field the stencil adds
     table_->set_hamiltonian( ham );
     if( table_->stencil().has_ddi )
-        throw std::runtime_error( "spirit_b200: GNEB with dipole-dipole interaction is not implemented" );
+    {
+        if( sharded_ )
+            throw std::runtime_error( "spirit_b200: GNEB with dipole-dipole interaction on a chain sharded over GPUs is not implemented" );
+        ensure_ddi_field();
+        buf_->view.Ddi = buf_->ddi + buf_->stride;
+    }
+    else
+        buf_->view.Ddi = nullptr;
 }
 
 void DeviceChain::synchronize()
@@ -621,9 +944,17 @@ void DeviceChain::evaluate_force( const GNEBParams & params, int which_configura
     auto & b          = *buf_;
     const auto & T    = *table_->buffers();
     const auto & p    = table_->stencil();
-    double * cf       = which_configuration == 0 ? b.view.S : b.view.P;
+    double * cf       = which_configuration == 0 ? b.view.S : ( which_configuration == 1 ? b.view.P : b.view.P2 );
     const dim3 grid( T.nblocks, noi_ );
+    b.view.moving_endpoints = params.moving_endpoints ? 1 : 0;
+    b.view.shortening       = params.path_shortening_constant > 0 ? 1 : 0;
+    if( sharded_ && ( params.moving_endpoints || params.path_shortening_constant > 0 || params.spring_force_ratio > 0 ) )
+        throw std::runtime_error( "spirit_b200: moving endpoints, path shortening and energy-weighted springs are not implemented on a chain "
+                                  "sharded over GPUs" );
     exchange_halo_images( cf );
+    if( b.view.Ddi )
+        for( int img = 0; img < noi_; ++img ) // one dipolar convolution per image (shared plan: one after the other)
+            table_->ddi_gradient_of( cf + b.stride * img, b.view.Ddi + b.stride * img, b.stream );
     if( p.NB == 1 )
         k_chain_gradient<1><<<grid, BLOCK_THREADS, 0, b.stream>>>( p, T.lg, b.view, cf, b.partials, T.nblocks );
     else
@@ -632,12 +963,40 @@ void DeviceChain::evaluate_force( const GNEBParams & params, int which_configura
     reduce_to_slots( S_E, 2, false );
     k_chain_rx<<<1, 1, 0, b.stream>>>( b.view );
     k_chain_tangent<<<grid, BLOCK_THREADS, 0, b.stream>>>( p, T.lg, b.view, cf, b.partials, T.nblocks );
-    reduce_to_slots( S_TT, 2, false );
+    reduce_to_slots( S_TT, ( b.view.shortening || b.view.moving_endpoints ) ? 5 : 2, false );
+    launches_ += 6;
+    if( b.view.shortening )
+    {
+        k_chain_shrink<<<grid, BLOCK_THREADS, 0, b.stream>>>( p, T.lg, b.view, cf, b.partials, T.nblocks );
+        reduce_to_slots( S_SHG, 3, false );
+        launches_ += 2;
+    }
+    if( params.moving_endpoints && params.translating_endpoints )
+    {
+        k_chain_translation<<<dim3( T.nblocks, 1 ), BLOCK_THREADS, 0, b.stream>>>( p, T.lg, b.view, cf, b.partials, T.nblocks );
+        k_reduce_rows<<<dim3( 1, 2 ), BLOCK_THREADS, 0, b.stream>>>(
+            b.partials, T.nblocks, b.scal + std::size_t( S_N_SLOTS ) * noi_global_ + G_TRANS_L, 1 );
+        launches_ += 2;
+    }
+    if( params.spring_force_ratio > 0 )
+    {
+        k_chain_lengths<<<1, 1, 0, b.stream>>>( b.view, params.spring_force_ratio );
+        ++launches_;
+    }
     ChainTypes types{};
     for( int i = 0; i < noi_; ++i )
         types.type[i] = i < int( params.image_type.size() ) ? params.image_type[i] : 0;
-    k_chain_coeffs<<<( noi_ + 63 ) / 64, 64, 0, b.stream>>>( b.view, types, params.spring_constant );
-    launches_ += 6;
+    ChainForceParams P{};
+    P.spring_constant          = params.spring_constant;
+    P.spring_force_ratio       = params.spring_force_ratio;
+    P.path_shortening_constant = params.path_shortening_constant;
+    P.moving_endpoints         = params.moving_endpoints ? 1 : 0;
+    P.translating_endpoints    = params.translating_endpoints ? 1 : 0;
+    P.escape_first             = params.escape_first ? 1 : 0;
+    P.delta_Rx0_left           = params.equilibrium_delta_Rx_left;
+    P.delta_Rx0_right          = params.equilibrium_delta_Rx_right;
+    P.nos                      = nos_;
+    k_chain_coeffs<<<( noi_ + 63 ) / 64, 64, 0, b.stream>>>( b.view, types, P );
     SB_CUDA_CHECK( cudaGetLastError() );
 }
 
@@ -678,8 +1037,16 @@ void DeviceChain::iterate( int solver, const GNEBParams & params, int n_iteratio
     const auto & p = table_->stencil();
     const dim3 grid( T.nblocks, noi_ );
     const bool oso = solver == Solver_VP_OSO || solver == Solver_LBFGS_OSO || solver == Solver_LBFGS_Atlas;
-    if( solver != Solver_VP && solver != Solver_Depondt && solver != Solver_Heun && solver != Solver_SIB && !oso )
+    if( solver != Solver_VP && solver != Solver_Depondt && solver != Solver_Heun && solver != Solver_SIB && solver != Solver_RK4 && !oso )
         throw std::runtime_error( "spirit_b200: GNEB solver id " + std::to_string( solver ) + " is not implemented" );
+    if( solver == Solver_RK4 && !b.rk4 )
+    {
+        const std::size_t fs = std::size_t( noi_ + 2 ) * b.stride;
+        SB_CUDA_CHECK( cudaMalloc( &b.rk4, 2 * fs * sizeof( double ) ) );
+        SB_CUDA_CHECK( cudaMemset( b.rk4, 0, 2 * fs * sizeof( double ) ) );
+        b.view.P2  = b.rk4 + b.stride;
+        b.view.Acc = b.rk4 + fs + b.stride;
+    }
     if( oso && sharded_ )
         throw std::runtime_error( "spirit_b200: VP_OSO / LBFGS_OSO / LBFGS_Atlas are not implemented on a chain sharded over GPUs" );
     // all local images back to back: one long field for the element-wise passes of oso.cuh
@@ -727,11 +1094,40 @@ void DeviceChain::iterate( int solver, const GNEBParams & params, int n_iteratio
             std::swap( b.view.F, b.view.F2 );
             vp_prev_projected_ = hk;
         }
+        else if( solver == Solver_RK4 )
+        {
+            // configurations: s -> P (s + k1/2) -> P2 (s + k2/2) -> P (s + k3) -> s
+            evaluate_force( params, 0, 0 );
+            k_chain_rk4<1><<<grid, BLOCK_THREADS, 0, b.stream>>>( p, T.lg, b.view, params.dtg, b.view.S, b.view.P );
+            evaluate_force( params, 1, 0 );
+            k_chain_rk4<2><<<grid, BLOCK_THREADS, 0, b.stream>>>( p, T.lg, b.view, params.dtg, b.view.P, b.view.P2 );
+            evaluate_force( params, 2, 0 );
+            k_chain_rk4<3><<<grid, BLOCK_THREADS, 0, b.stream>>>( p, T.lg, b.view, params.dtg, b.view.P2, b.view.P );
+            evaluate_force( params, 1, 0 );
+            if( b.view.shortening )
+            {
+                k_chain_force_at<<<grid, BLOCK_THREADS, 0, b.stream>>>( p, T.lg, b.view, b.view.P );
+                ++launches_;
+            }
+            k_chain_rk4<4><<<grid, BLOCK_THREADS, 0, b.stream>>>( p, T.lg, b.view, params.dtg, b.view.P, b.view.S );
+            launches_ += 4;
+            if( hk )
+            {
+                k_chain_hook<<<grid, BLOCK_THREADS, 0, b.stream>>>( p, T.lg, b.view, b.partials, T.nblocks );
+                reduce_to_slots( S_TQ, 1, true );
+                launches_ += 2;
+            }
+        }
         else
         {
             for( int stage = 1; stage <= 2; ++stage )
             {
                 evaluate_force( params, stage - 1, 0 );
+                if( stage == 2 && b.view.shortening )
+                {
+                    k_chain_force_at<<<grid, BLOCK_THREADS, 0, b.stream>>>( p, T.lg, b.view, b.view.P );
+                    ++launches_;
+                }
                 if( solver == Solver_Depondt )
                     launch_chain_stages<Solver_Depondt>( *this, b, T, p, noi_, params.dtg, stage );
                 else if( solver == Solver_Heun )

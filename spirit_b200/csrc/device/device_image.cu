@@ -1552,6 +1552,18 @@ int DeviceImage::llg_profile_stages( int solver, LLGParams & llg, int n_iteratio
     return n_stages;
 }
 
+bool DeviceImage::ddi_gradient_of( const double * configuration_base, double * out_base, void * stream )
+{
+    if( !stencil_.has_ddi || !ddi_ )
+        return false;
+    ConstField3 c;
+    c.base = configuration_base;
+    Field3 o;
+    o.base = out_base;
+    launches_ += ddi_gradient( *ddi_, c, o, cudaStream_t( stream ) );
+    return true;
+}
+
 void DeviceImage::dump_thermal_variates( const LLGParams & llg, std::size_t count, float * host )
 {
     auto & b    = *buf_;

@@ -98,6 +98,10 @@ public:
     void download_spins( double * host_aos );
     void download_effective_field( double * host_aos );
 
+    // dipolar gradient field of an arbitrary configuration on this image's lattice (GNEB: one call per image); no-op
+    // returning false without a dipolar plan
+    bool ddi_gradient_of( const double * configuration_base, double * out_base, void * stream );
+
     // One-off evaluations on the device-resident spins (System_Update_Data, tests).
     // gradient_host_aos may be null. Hamiltonian_Heisenberg.cpp:670-766
     void gradient_and_energy( double * gradient_host_aos, double * energy );
@@ -194,6 +198,15 @@ struct GNEBParams
     double dt              = 1e-3; // llg_dt of the images (VP uses it raw, Solver_VP.hpp:95-110)
     double dtg             = 0;    // dt * gamma / mu_B: Fv = dtg s x F (Method_GNEB.cpp:359-391)
     std::vector<int> image_type;   // 0 normal, 1 climbing, 2 falling, 3 stationary
+    // Method_GNEB.cpp:137-170, 243-245: with a ratio > 0 the spring force equalises path lengths in the (Rx, E) plane
+    double spring_force_ratio = 0;
+    // :206-233: > 0 adds a force that shortens the path orthogonally to the gradient force and the tangent
+    double path_shortening_constant = 0;
+    // :261-355: the end images move too: rotational part of the gradient force, a spring that keeps their distance to the
+    // neighbouring image, optionally a common translation; escape_first switches the rotational part off while the energy
+    // rises along the tangent at the left end faster than at the right one
+    bool moving_endpoints = false, translating_endpoints = false, escape_first = false;
+    double equilibrium_delta_Rx_left = 1, equilibrium_delta_Rx_right = 1;
 };
 
 struct ChainHookResult
@@ -242,6 +255,7 @@ private:
     void share_slots( int first_slot, int n_slots, bool max );
     void reduce_to_slots( int first_slot, int n_slots, bool max );
 
+    void ensure_ddi_field();
     int noi_ = 0, nos_ = 0, i_begin_ = 0, noi_global_ = 0;
     bool sharded_ = false;
     std::unique_ptr<DeviceImage> table_; // owns the stencil tables (shared Hamiltonian)

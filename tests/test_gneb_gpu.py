@@ -225,3 +225,94 @@ def test_gneb_barrier_golden_minimisers(cfg, product, solver):
     assert abs(e[i_max] - (-5811.5244140625)) < 1e-3
     assert abs(p.magnetization(i_max)[2] - 2 * 0.96657) < 1e-4
     p.close()
+
+
+def _chain_run(lib, path, options, solver, n, types=None, noi=8):
+    x = S.Session(lib, path)
+    make_chain(x, noi=noi)
+    for img, t in (types or {}).items():
+        x.gneb_set_image_type(t, img)
+    L, st = x.lib, x.state
+    if "ratio" in options:
+        L.Parameters_GNEB_Set_Spring_Force_Ratio(st, options["ratio"], -1)
+    if "shortening" in options:
+        L.Parameters_GNEB_Set_Path_Shortening_Constant(st, options["shortening"], -1)
+    if options.get("moving"):
+        L.Parameters_GNEB_Set_Moving_Endpoints(st, True, -1)
+        L.Parameters_GNEB_Set_Equilibrium_Delta_Rx(st, options.get("dl", 1.0), options.get("dr", 1.0), -1)
+    if options.get("translating"):
+        L.Parameters_GNEB_Set_Translating_Endpoints(st, True, -1)
+    x.gneb_start(S.SOLVERS[solver], single_shot=True)
+    x.n_shot(n)
+    rx, e = x.chain_rx_e()
+    out = (np.stack([x.spins(i).copy() for i in range(noi)]), rx, e, x.chain_max_torque())
+    x.stop()
+    x.close()
+    return out
+
+
+FORCE_OPTIONS = [
+    {"ratio": 0.3},                                            # energy-weighted springs (Method_GNEB.cpp:137-170)
+    {"ratio": 1.0},
+    {"shortening": 0.05},                                      # path shortening (:206-233); nos * constant above |F_go|
+    {"shortening": 1e-6},                                      # ... below it
+    {"moving": True, "dl": 0.4, "dr": 0.7},                    # moving endpoints (:261-355)
+    {"moving": True, "translating": True, "dl": 0.5, "dr": 0.5},
+    {"ratio": 0.5, "shortening": 1e-4, "moving": True, "translating": True},
+]
+
+
+@pytest.mark.parametrize("types", TYPES)
+def test_gneb_rk4_matches_restatement(cfg, product, types):
+    """RK4 over all images of a chain (Solver_RK4.hpp:41-147 with the GNEB force; Method_GNEB.cpp:749 instantiates the
+    combination, but the reference's Simulation_GNEB_Start (Simulation.cpp:279-303) refuses solver RK4, so the compiled
+    reference cannot run it: the NumPy restatement is the oracle here, as for SIB)"""
+    from oracle import restatement as R
+    p = S.Session(product, cfg("solvers", n_basis_cells="12 10 1", boundary_conditions="1 0 0"))
+    make_chain(p, noi=8)
+    imgs0 = [p.spins(i).copy() for i in range(8)]
+    t = [R.NORMAL] * 8
+    for img, ty in types.items():
+        p.gneb_set_image_type(ty, img)
+        t[img] = ty
+    p.gneb_start(S.SOLVERS["RK4"], single_shot=True)
+    p.n_shot(6)
+    m = R.Model((12, 10, 1), (1, 0, 0), K=0.25)
+    imgs, E, Rx = R.gneb_two_stage_single_shots(m, imgs0, t, 1.0, 6, "RK4")
+    assert np.abs(np.stack([p.spins(i) for i in range(8)]) - np.stack(imgs)).max() < 1e-10
+    rx, e = p.chain_rx_e()
+    assert np.abs(rx - np.array(Rx)).max() < 1e-10
+    assert np.abs(e - np.array(E)).max() <= 1e-11 * np.abs(E).max()
+    p.stop()
+    p.close()
+
+
+@pytest.mark.parametrize("solver,n", [("VP", 30), ("Depondt", 8)])
+@pytest.mark.parametrize("options", FORCE_OPTIONS)
+def test_gneb_force_options_match_reference(cfg, product, oracle, solver, n, options):
+    """The optional parts of the GNEB force -- energy-weighted springs, path shortening, moving and translating endpoints --
+    against the compiled reference, single shots from the same chain (one climbing image)"""
+    path = cfg("solvers", n_basis_cells="12 10 1", boundary_conditions="1 0 0")
+    (sp, rxp, ep, tp), (so, rxo, eo, to) = [_chain_run(lib, path, options, solver, n, {3: S.GNEB_CLIMBING}) for lib in (product, oracle)]
+    assert np.abs(sp - so).max() < 1e-9, np.abs(sp - so).max()
+    assert np.abs(rxp - rxo).max() < 1e-9
+    assert np.abs(ep - eo).max() <= 1e-10 * np.abs(eo).max()
+    assert abs(tp - to) <= 1e-8 * to
+    if options.get("moving"):
+        # the end images did move
+        x = S.Session(product, path)
+        make_chain(x, noi=8)
+        assert np.abs(sp[0] - x.spins(0)).max() > 1e-6
+        x.close()
+
+
+@pytest.mark.parametrize("solver,n", [("VP", 12), ("Depondt", 4)])
+def test_gneb_with_dipolar_interaction_matches_reference(cfg, product, oracle, solver, n):
+    """GNEB over images whose Hamiltonian has the dipolar FFT convolution (Method_GNEB.cpp:99-100 evaluates every image with
+    its own Hamiltonian): one convolution per image and force evaluation"""
+    path = cfg("solvers", n_basis_cells="12 10 1", boundary_conditions="0 0 0", ddi_method="fft", ddi_n_periodic_images="0 0 0")
+    (sp, rxp, ep, tp), (so, rxo, eo, to) = [_chain_run(lib, path, {}, solver, n, {2: S.GNEB_CLIMBING}, noi=5) for lib in (product, oracle)]
+    assert np.abs(sp - so).max() < 1e-9
+    assert np.abs(rxp - rxo).max() < 1e-9
+    assert np.abs(ep - eo).max() <= 1e-10 * np.abs(eo).max()
+    assert abs(tp - to) <= 1e-8 * to
