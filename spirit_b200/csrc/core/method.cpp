@@ -189,9 +189,32 @@ dev::LLGParams Method_LLG::make_params( const Spin_System & system, int solver )
     l.has_stt = 0;
     if( !minimise && P.stt_magnitude > 0 )
     {
-        if( P.stt_use_gradient )
-            throw std::runtime_error( "spirit_b200: llg_stt_use_gradient 1 (spin-current gradient term) is not implemented" );
         l.has_stt = 1;
+        if( P.stt_use_gradient )
+        {
+            // gradient approximation for in-plane currents (Method_LLG.cpp:184-205): s_c_grad = jacobian(s) je, the jacobian from
+            // finite differences along the lattice translations times the inverse of the matrix of lattice vectors
+            if( const_cast<Spin_System &>( system ).device().is_slab() )
+                throw std::runtime_error( "spirit_b200: llg_stt_use_gradient 1 is not implemented on a lattice cut into slabs over GPUs" );
+            double B[3][3]; // columns: lattice_constant * bravais vectors
+            for( int c = 0; c < 3; ++c )
+                for( int r = 0; r < 3; ++r )
+                    B[r][c] = g.lattice_constant * g.bravais_vectors[c][r];
+            const double det = B[0][0] * ( B[1][1] * B[2][2] - B[1][2] * B[2][1] ) - B[0][1] * ( B[1][0] * B[2][2] - B[1][2] * B[2][0] )
+                               + B[0][2] * ( B[1][0] * B[2][1] - B[1][1] * B[2][0] );
+            double inv[3][3];
+            inv[0][0] = ( B[1][1] * B[2][2] - B[1][2] * B[2][1] ) / det, inv[0][1] = ( B[0][2] * B[2][1] - B[0][1] * B[2][2] ) / det;
+            inv[0][2] = ( B[0][1] * B[1][2] - B[0][2] * B[1][1] ) / det, inv[1][0] = ( B[1][2] * B[2][0] - B[1][0] * B[2][2] ) / det;
+            inv[1][1] = ( B[0][0] * B[2][2] - B[0][2] * B[2][0] ) / det, inv[1][2] = ( B[0][2] * B[1][0] - B[0][0] * B[1][2] ) / det;
+            inv[2][0] = ( B[1][0] * B[2][1] - B[1][1] * B[2][0] ) / det, inv[2][1] = ( B[0][1] * B[2][0] - B[0][0] * B[2][1] ) / det;
+            inv[2][2] = ( B[0][0] * B[1][1] - B[0][1] * B[1][0] ) / det;
+            for( int t = 0; t < 3; ++t )
+                l.stt_w[t] = inv[t][0] * P.stt_polarisation_normal[0] + inv[t][1] * P.stt_polarisation_normal[1]
+                             + inv[t][2] * P.stt_polarisation_normal[2];
+            l.stt_g1  = l.dtg * P.stt_magnitude * ( P.damping - P.beta );
+            l.stt_g2  = l.dtg * P.stt_magnitude * ( 1 + P.beta * P.damping );
+            l.has_stt = 2;
+        }
         l.stt_c1  = -l.dtg * P.stt_magnitude * ( P.damping - P.beta );
         l.stt_c2  = -l.dtg * P.stt_magnitude * ( 1 + P.beta * P.damping );
         for( int d = 0; d < 3; ++d )

@@ -1302,6 +1302,144 @@ static __global__ void __launch_bounds__( FFT_THREADS, SB_FFT16_MINB ) k_ddi_inv
     }
 }
 
+// Persistent, software-pipelined forms of the two a-pass kernels above (one sublattice, even Na): tiles (row group, component)
+// blockIdx.x, blockIdx.x + gridDim.x, ...; the rows of the NEXT tile are fetched with 16-byte asynchronous copies under the
+// transform of the current one (see k_fft_pass16p). Forward: a pair (x_2j, x_2j+1) of the spin row IS the complex element z_j
+// (adjacent doubles of an AoSoA block), copied straight into the transform buffer, mu_s applied to the output. Inverse: the raw
+// half-spectrum rows land in a two-deep ring and the Hermitian merge step fills the transform buffer from there.
+template<int LOGM>
+static __global__ void __launch_bounds__( FFT_THREADS, SB_FFT16_MINB ) k_ddi_fwd_a16p(
+    const __grid_constant__ FFTPlan1D plan_h, const double2 * __restrict__ tw_full, const __grid_constant__ DDIDims d,
+    ConstField3 spins, double2 * __restrict__ A, const int lg_nrow, const int q0, const int n_rg, const int n_tiles )
+{
+    extern __shared__ double2 smem[];
+    constexpr int m = 1 << LOGM;
+    const int bufp  = ( m << lg_nrow ) + ( ( m << lg_nrow ) >> 4 ) + 1;
+    int rl, jlow, jhigh, jstep;
+    row_map( lg_nrow, rl, jlow, jhigh, jstep );
+    const int rows = d.Nb * d.Nc;
+    auto fetch = [&]( int tile, double2 * buf )
+    {
+        const int qi = tile / n_rg, row = ( ( tile - qi * n_rg ) << lg_nrow ) + rl;
+        const bool valid = row < rows;
+        const int b = row % d.Nb, c = row / d.Nb;
+        const std::size_t site0 = std::size_t( d.Na ) * b + std::size_t( d.plane_stride ) * ( c + d.halo );
+        const double * comp     = spins.base + ( ( q0 + qi ) % 3 ) * FIELD_BLOCK;
+#pragma unroll
+        for( int k = 0; k < FFT_E; ++k )
+        {
+            const int j        = 4 * ( jhigh + k * jstep ) + jlow;
+            const bool nonzero = valid && 2 * j < d.Na;
+            cp_async16( buf + ( j << lg_nrow ) + rl, nonzero ? comp + elem_offset( site0 + 2 * j ) : spins.base, nonzero );
+        }
+        cp_async_commit();
+    };
+    int tile = blockIdx.x, stage = 0;
+    if( tile < n_tiles )
+        fetch( tile, smem );
+    for( ; tile < n_tiles; tile += gridDim.x, stage ^= 1 )
+    {
+        cp_async_wait_all();
+        __syncthreads();
+        if( tile + int( gridDim.x ) < n_tiles )
+            fetch( tile + gridDim.x, smem + ( stage ^ 1 ) * bufp );
+        double2 * x = smem + stage * bufp;
+        block_fft_ct<false, LOGM>( plan_h.twiddle, x, lg_nrow, threadIdx.x & ( ( 1 << lg_nrow ) - 1 ), threadIdx.x >> lg_nrow );
+        const int qi = tile / n_rg, row = ( ( tile - qi * n_rg ) << lg_nrow ) + rl;
+        if( row < rows )
+        {
+            const int q = q0 + qi, b = row % d.Nb, c = row / d.Nb;
+            const double h = 0.5 * d.mu_s[0];
+            double2 * out  = A + ( ( std::size_t( q ) * d.Nc + c ) * d.Nb + b ) * d.Ha;
+            for( int jh = jhigh; 4 * jh < m; jh += jstep )
+            {
+                const int k      = 4 * jh + jlow;
+                const double2 Zk = x[( k << lg_nrow ) + rl];
+                const double2 Zm = x[( ( ( m - k ) & ( m - 1 ) ) << lg_nrow ) + rl]; // Z_m = Z_0
+                const double2 E  = make_double2( h * ( Zk.x + Zm.x ), h * ( Zk.y - Zm.y ) );
+                const double2 O  = make_double2( h * ( Zk.y + Zm.y ), -h * ( Zk.x - Zm.x ) );
+                out[k]           = cadd( E, cmul( __ldg( tw_full + k ), O ) );
+            }
+            if( jhigh == 0 && jlow == 0 )
+            {
+                const double2 Z0 = x[rl];
+                out[m]           = make_double2( d.mu_s[0] * ( Z0.x - Z0.y ), 0.0 );
+            }
+        }
+    }
+}
+
+template<int LOGM>
+static __global__ void __launch_bounds__( FFT_THREADS, SB_FFT16_MINB ) k_ddi_inv_a16p(
+    const __grid_constant__ FFTPlan1D plan_h, const double2 * __restrict__ tw_full, const __grid_constant__ DDIDims d,
+    const double2 * __restrict__ A, Field3 g, const double inv_P, const int lg_nrow, const int q0, const int n_rg, const int n_tiles )
+{
+    extern __shared__ double2 smem[];
+    constexpr int m = 1 << LOGM;
+    const int rawp  = ( m + 1 ) << lg_nrow; // one raw tile: rows of m + 1 elements
+    double2 * x     = smem + 2 * rawp;      // the transform buffer behind the two raw tiles
+    int rl, jlow, jhigh, jstep;
+    row_map( lg_nrow, rl, jlow, jhigh, jstep );
+    const int rows = d.Nb * d.Nc;
+    auto fetch = [&]( int tile, double2 * raw )
+    {
+        const int qi = tile / n_rg, row = ( ( tile - qi * n_rg ) << lg_nrow ) + rl;
+        const bool valid = row < rows;
+        const int b = row % d.Nb, c = row / d.Nb;
+        const double2 * in = valid ? A + ( ( std::size_t( q0 + qi ) * d.Nc + c ) * d.Nb + b ) * d.Ha : A;
+#pragma unroll
+        for( int kk = 0; kk < FFT_E; ++kk )
+        {
+            const int k = 4 * ( jhigh + kk * jstep ) + jlow;
+            cp_async16( raw + ( k << lg_nrow ) + rl, valid ? in + k : A, valid );
+        }
+        if( jhigh == 0 && jlow == 0 )
+            cp_async16( raw + ( m << lg_nrow ) + rl, valid ? in + m : A, valid );
+        cp_async_commit();
+    };
+    int tile = blockIdx.x, stage = 0;
+    if( tile < n_tiles )
+        fetch( tile, smem );
+    for( ; tile < n_tiles; tile += gridDim.x, stage ^= 1 )
+    {
+        cp_async_wait_all();
+        __syncthreads();
+        if( tile + int( gridDim.x ) < n_tiles )
+            fetch( tile + gridDim.x, smem + ( stage ^ 1 ) * rawp );
+        const double2 * raw = smem + stage * rawp;
+#pragma unroll
+        for( int kk = 0; kk < FFT_E; ++kk )
+        {
+            const int k      = 4 * ( jhigh + kk * jstep ) + jlow;
+            const double2 Xk = raw[( k << lg_nrow ) + rl], Xm = raw[( ( m - k ) << lg_nrow ) + rl];
+            const double2 S  = make_double2( Xk.x + Xm.x, Xk.y - Xm.y ); // X_k + conj X_{m-k}
+            const double2 D  = make_double2( Xk.x - Xm.x, Xk.y + Xm.y ); // X_k - conj X_{m-k}
+            const double2 w  = __ldg( tw_full + k );                     // exp(-2 pi i k / Pa); the inverse needs its conjugate
+            const double2 T  = cmul( make_double2( w.x, -w.y ), D );
+            x[( k << lg_nrow ) + rl] = make_double2( S.x - T.y, S.y + T.x ); // S + i T
+        }
+        __syncthreads();
+        block_fft_ct<true, LOGM>( plan_h.twiddle, x, lg_nrow, threadIdx.x & ( ( 1 << lg_nrow ) - 1 ), threadIdx.x >> lg_nrow );
+        const int qi = tile / n_rg, row = ( ( tile - qi * n_rg ) << lg_nrow ) + rl;
+        if( row < rows )
+        {
+            const int b = row % d.Nb, c = row / d.Nb;
+            const std::size_t site0 = std::size_t( d.Na ) * b + std::size_t( d.plane_stride ) * ( c + d.halo );
+            double * comp           = g.base + ( ( q0 + qi ) % 3 ) * FIELD_BLOCK;
+            const double f          = -d.mu_s[0] * inv_P;
+            for( int jh = jhigh; 4 * jh < m; jh += jstep )
+            {
+                const int j = 4 * jh + jlow;
+                if( 2 * j < d.Na )
+                {
+                    const double2 z = x[( j << lg_nrow ) + rl];
+                    *reinterpret_cast<double2 *>( comp + elem_offset( site0 + 2 * j ) ) = make_double2( f * z.x, f * z.y );
+                }
+            }
+        }
+    }
+}
+
 // Dipole tensor component `comp6` of sublattice pair (b1, b2) on the padded lattice, with periodic images
 // (FFT_Dipole_Matrices, Hamiltonian_Heisenberg.cpp:1406-1499)
 struct TensorGeom
@@ -1379,6 +1517,12 @@ std::vector<int> factorize( int n )
 } // namespace
 
 // ---------------------------------------------------------------------------------------------
+// launch shapes of the pipelined a-passes (k_ddi_fwd_a16p / k_ddi_inv_a16p)
+struct APipe
+{
+    int ctas_fwd = 0, ctas_inv = 0;
+    std::size_t smem_fwd = 0, smem_inv = 0;
+};
 struct DDIPlan
 {
     DDIDims dims{};   // local planes: a- and b-passes
@@ -1404,6 +1548,8 @@ struct DDIPlan
         int pipe_ctas = 0;       // > 0: the persistent pipelined kernel (k_fft_pass16p) with this many CTAs (two tile buffers in smem)
         std::size_t smem = 0;
     } fast_a, fast_b, fast_c;
+    APipe apipe;
+    bool a_pipe = false;           // the a-passes run as the persistent pipelined kernels
     FFTPlan1D plan_ah;             // length Pa / 2
     double2 * twiddle_ah = nullptr;
     int lg_split         = 31;     // lg of the per-rank kb block (distributed layout), 31: no split
@@ -1618,6 +1764,65 @@ void launch_c_mult16(
         default: throw std::logic_error( "spirit_b200: no fast c-pass kernel for this length" );
     }
 }
+// the pipelined a-passes: smem_inv_p bytes for the inverse (two raw tiles + transform buffer), 2 x f.smem for the forward
+bool configure_a16_pipelined( const DDIPlan::Fast & f, int m, APipe & ap )
+{
+    ap.smem_fwd = 2 * f.smem;
+    ap.smem_inv = 2 * ( ( std::size_t( m ) + 1 ) << f.lg ) * sizeof( double2 ) + f.smem;
+    if( ap.smem_fwd > std::size_t( 220 * 1024 ) || ap.smem_inv > std::size_t( 220 * 1024 ) )
+        return false;
+    int dev = 0, sms = 0, pf = 0, pi = 0;
+    SB_CUDA_CHECK( cudaGetDevice( &dev ) );
+    SB_CUDA_CHECK( cudaDeviceGetAttribute( &sms, cudaDevAttrMultiProcessorCount, dev ) );
+    switch( ilog2( m ) )
+    {
+#define C( L )                                                                                                         \
+    case L:                                                                                                            \
+        allow_smem( k_ddi_fwd_a16p<L>, ap.smem_fwd );                                                                  \
+        allow_smem( k_ddi_inv_a16p<L>, ap.smem_inv );                                                                  \
+        SB_CUDA_CHECK( cudaOccupancyMaxActiveBlocksPerMultiprocessor( &pf, k_ddi_fwd_a16p<L>, f.threads, ap.smem_fwd ) ); \
+        SB_CUDA_CHECK( cudaOccupancyMaxActiveBlocksPerMultiprocessor( &pi, k_ddi_inv_a16p<L>, f.threads, ap.smem_inv ) ); \
+        break;
+        SB_FOR_LOGN( C )
+#undef C
+        default: return false;
+    }
+    if( pf < 1 || pi < 1 )
+        return false;
+    ap.ctas_fwd = pf * sms;
+    ap.ctas_inv = pi * sms;
+    return true;
+}
+void launch_fwd_a16p(
+    const DDIPlan::Fast & f, const APipe & ap, int n_rg, int nq, cudaStream_t stream, const FFTPlan1D & plan_h, const double2 * tw_full,
+    const DDIDims & d, ConstField3 spins, double2 * A, int q0 )
+{
+    const int n_tiles = n_rg * nq;
+    const dim3 grid( std::min( n_tiles, ap.ctas_fwd ) );
+    switch( ilog2( plan_h.n ) )
+    {
+#define C( L )                                                                                                         \
+    case L: k_ddi_fwd_a16p<L><<<grid, f.threads, ap.smem_fwd, stream>>>( plan_h, tw_full, d, spins, A, f.lg, q0, n_rg, n_tiles ); break;
+        SB_FOR_LOGN( C )
+#undef C
+        default: throw std::logic_error( "spirit_b200: no fast a-pass kernel for this length" );
+    }
+}
+void launch_inv_a16p(
+    const DDIPlan::Fast & f, const APipe & ap, int n_rg, int nq, cudaStream_t stream, const FFTPlan1D & plan_h, const double2 * tw_full,
+    const DDIDims & d, const double2 * A, Field3 g, double inv_P, int q0 )
+{
+    const int n_tiles = n_rg * nq;
+    const dim3 grid( std::min( n_tiles, ap.ctas_inv ) );
+    switch( ilog2( plan_h.n ) )
+    {
+#define C( L )                                                                                                         \
+    case L: k_ddi_inv_a16p<L><<<grid, f.threads, ap.smem_inv, stream>>>( plan_h, tw_full, d, A, g, inv_P, f.lg, q0, n_rg, n_tiles ); break;
+        SB_FOR_LOGN( C )
+#undef C
+        default: throw std::logic_error( "spirit_b200: no fast a-pass kernel for this length" );
+    }
+}
 void launch_fwd_a16(
     const DDIPlan::Fast & f, dim3 grid, cudaStream_t stream, const FFTPlan1D & plan_h, const double2 * tw_full, const DDIDims & d,
     ConstField3 spins, double2 * A, int q0, bool configure = false )
@@ -1756,10 +1961,15 @@ DDIPlan * ddi_plan_create( const Hamiltonian & ham, const StencilParams & sp, cu
     {
         // (n / 8) << lg threads, about 256 per CTA; one in-place buffer of n << lg elements (+ 1/16 padding) per transform set
         const bool allow = !env_flag_off( "SPIRIT_B200_FFT_FAST" );
-        auto shape       = []( DDIPlan::Fast & f, int n, int n_buffers, const char * tune )
+        // `elements`: transform-set size a CTA aims at (n << lg <= elements). The passes are bound by barriers and fixed
+        // latencies inside a CTA, not by bytes in flight: many small CTAs per SM (independent barrier domains) beat few large
+        // ones (profiles/r2u_sweep.txt, r2v_sweep.txt: 256^3 12.2 -> 11.1 ms, 512^3 112 -> 107 ms per SIB iteration)
+        auto shape       = []( DDIPlan::Fast & f, int n, int n_buffers, const char * tune, int elements = 2048 )
         {
             f.lg = 0;
-            while( f.lg < 4 && ( n << ( f.lg + 1 ) ) <= 2048 )
+            while( f.lg < 4 && ( n << ( f.lg + 1 ) ) <= elements )
+                ++f.lg;
+            while( ( ( n >> FFT_LG_E ) << f.lg ) < 32 ) // at least one warp
                 ++f.lg;
             if( const char * v = std::getenv( tune ) ) // tuning runs (profiles/): columns per CTA
                 f.lg = std::max( 0, std::min( 5, std::atoi( v ) ) );
@@ -1770,10 +1980,11 @@ DDIPlan * ddi_plan_create( const Hamiltonian & ham, const StencilParams & sp, cu
         const bool pow2_world = ( world & ( world - 1 ) ) == 0;
         if( allow && plan->plan[1].fast16 && pow2_world )
         {
-            shape( plan->fast_b, d.Pb, 1, "SPIRIT_B200_FFT_LG_B" );
-            // two column groups per CTA, loaded / stored together and transformed in turn: rows of the tile twice as long (a
-            // whole sector where a CTA holds one column, lengths >= 2048; a whole 128-byte line at 512). Measured: profiles/r1y
-            plan->fast_b.lg_seq = 1;
+            // up to length 512: 128 threads (1024 elements) and one column group; longer: two column groups per CTA, loaded /
+            // stored together and transformed in turn (rows of the tile twice as long: a whole sector where a CTA holds one
+            // column, lengths >= 2048). Measured: profiles/r1y, r2v
+            shape( plan->fast_b, d.Pb, 1, "SPIRIT_B200_FFT_LG_B", d.Pb <= 512 ? 1024 : 2048 );
+            plan->fast_b.lg_seq = d.Pb <= 512 ? 0 : 1;
             if( const char * v = std::getenv( "SPIRIT_B200_FFT_SEQ_B" ) )
                 plan->fast_b.lg_seq = std::atoi( v ) ? 1 : 0;
             if( plan->fast_b.lg_seq )
@@ -1791,13 +2002,13 @@ DDIPlan * ddi_plan_create( const Hamiltonian & ham, const StencilParams & sp, cu
         {
             make_plan_1d( plan->plan_ah, plan->twiddle_ah, d.Pa / 2 );
             if( plan->plan_ah.fast16 )
-                shape( plan->fast_a, d.Pa / 2, 1, "SPIRIT_B200_FFT_LG_A" );
+                shape( plan->fast_a, d.Pa / 2, 1, "SPIRIT_B200_FFT_LG_A", 256 ); // one or two warps per CTA
         }
         // lengths up to 4096 have instantiations
         plan->fast_b.on = plan->fast_b.on && d.Pb <= 4096;
         plan->fast_c.on = plan->fast_c.on && d.Pc <= 4096;
         plan->fast_a.on = plan->fast_a.on && d.Pa / 2 <= 4096;
-        if( plan->fast_b.on && !env_flag_off( "SPIRIT_B200_FFT_PIPE_B" ) )
+        if( plan->fast_b.on && std::getenv( "SPIRIT_B200_FFT_PIPE_B" ) && !env_flag_off( "SPIRIT_B200_FFT_PIPE_B" ) )
         {
             // persistent pipelined b-pass; its own tile width (columns per CTA) may differ from the plain kernel's
             DDIPlan::Fast f = plan->fast_b;
@@ -1819,6 +2030,16 @@ DDIPlan * ddi_plan_create( const Hamiltonian & ham, const StencilParams & sp, cu
             launch_c_mult16<false>( plan->fast_c, dim3(), stream, plan->plan[2], plan->dims_c, nullptr, nullptr, true );
             launch_c_mult16<true>( plan->fast_c, dim3(), stream, plan->plan[2], plan->dims_c, nullptr, nullptr, true );
         }
+        // pipelined (cp.async double-buffered, persistent) forms, where they measured faster than the plain kernels: the a-passes
+        // of long rows (film, half length 2048: 0.54 / 0.65 -> 0.51 / 0.55 ms, profiles/r2t); short rows and the b-passes are
+        // served as well or better by small plain CTAs (profiles/r2s, r2t, r2u). SPIRIT_B200_FFT_PIPE_A / _B = 1 / 0 force them.
+        auto env_choice = []( const char * name, bool otherwise )
+        {
+            const char * v = std::getenv( name );
+            return v ? v[0] != '0' : otherwise;
+        };
+        if( plan->fast_a.on && d.NB == 1 && d.Na % 2 == 0 && d.plane_stride % 2 == 0 && env_choice( "SPIRIT_B200_FFT_PIPE_A", d.Pa / 2 >= 1024 ) )
+            plan->a_pipe = configure_a16_pipelined( plan->fast_a, d.Pa / 2, plan->apipe );
         if( plan->fast_a.on )
         {
             launch_fwd_a16( plan->fast_a, dim3(), stream, plan->plan_ah, nullptr, d, ConstField3{}, nullptr, 0, true );
@@ -2046,6 +2267,25 @@ DDIPlan * ddi_plan_create( const Hamiltonian & ham, const StencilParams & sp, cu
 
 namespace
 {
+// a-passes of components q0 .. q0 + nq - 1 (fast kernels), plain or pipelined
+void run_fwd_a16( DDIPlan & plan, ConstField3 spins, int q0, int nq, cudaStream_t stream )
+{
+    const DDIDims & d = plan.dims;
+    const int n_rg    = ( d.Nb * d.Nc + ( 1 << plan.fast_a.lg ) - 1 ) >> plan.fast_a.lg;
+    if( plan.a_pipe )
+        launch_fwd_a16p( plan.fast_a, plan.apipe, n_rg, nq, stream, plan.plan_ah, plan.plan[0].twiddle, d, spins, plan.A, q0 );
+    else
+        launch_fwd_a16( plan.fast_a, dim3( n_rg, nq ), stream, plan.plan_ah, plan.plan[0].twiddle, d, spins, plan.A, q0 );
+}
+void run_inv_a16( DDIPlan & plan, Field3 g_ddi, double inv_P, int q0, int nq, cudaStream_t stream )
+{
+    const DDIDims & d = plan.dims;
+    const int n_rg    = ( d.Nb * d.Nc + ( 1 << plan.fast_a.lg ) - 1 ) >> plan.fast_a.lg;
+    if( plan.a_pipe )
+        launch_inv_a16p( plan.fast_a, plan.apipe, n_rg, nq, stream, plan.plan_ah, plan.plan[0].twiddle, d, plan.A, g_ddi, inv_P, q0 );
+    else
+        launch_inv_a16( plan.fast_a, dim3( n_rg, nq ), stream, plan.plan_ah, plan.plan[0].twiddle, d, plan.A, g_ddi, inv_P, q0 );
+}
 // step 3 (c-transforms + tensor multiply) on the operand in per-rank block layout
 void launch_c_mult( DDIPlan & plan, double2 * operand, cudaStream_t stream )
 {
@@ -2126,7 +2366,7 @@ int ddi_gradient_peer( DDIPlan & plan, ConstField3 spins, Field3 g_ddi, cudaStre
     const dim3 grid_b( ( d.Ha + ( 1 << lg_tile_b ) - 1 ) >> lg_tile_b, ncl );
     for( int q = 0; q < nq; ++q )
     {
-        launch_fwd_a16( plan.fast_a, grid_a, stream, plan.plan_ah, plan.plan[0].twiddle, d, spins, plan.A, q );
+        run_fwd_a16( plan, spins, q, 1, stream );
         PassArgs pb{};
         pb.in    = plan.A + std::size_t( q ) * ncl * d.Nb * d.Ha;
         pb.in_os = std::size_t( d.Nb ) * d.Ha, pb.in_js = pb.out_js = d.Ha;
@@ -2152,7 +2392,7 @@ int ddi_gradient_peer( DDIPlan & plan, ConstField3 spins, Field3 g_ddi, cudaStre
         for( int r = 0; r < world; ++r ) // the kb block of rank r for my planes: block `my rank` of rank r's operand
             ib.in_peer[r] = static_cast<const double2 *>( plan.C2_peer[buf][r] ) + std::size_t( plan.rank ) * dc.block_stride + std::size_t( q ) * comp_elems;
         launch_pass16<true>( plan.fast_b, grid_b, stream, plan.plan[1], ib, plan.lg_split, 31 );
-        launch_inv_a16( plan.fast_a, grid_a, stream, plan.plan_ah, plan.plan[0].twiddle, d, plan.A, g_ddi, inv_P, q );
+        run_inv_a16( plan, g_ddi, inv_P, q, 1, stream );
     }
     SB_CUDA_CHECK( cudaGetLastError() );
     return 4 * nq + 1;
@@ -2184,7 +2424,7 @@ int ddi_gradient_pipelined( DDIPlan & plan, ConstField3 spins, Field3 g_ddi, cud
     };
     for( int q = 0; q < nq; ++q )
     {
-        launch_fwd_a16( plan.fast_a, grid_a, stream, plan.plan_ah, plan.plan[0].twiddle, d, spins, plan.A, q );
+        run_fwd_a16( plan, spins, q, 1, stream );
         PassArgs pb{};
         pb.in    = plan.A + std::size_t( q ) * ncl * d.Nb * d.Ha;
         pb.out   = plan.B + std::size_t( q ) * comp_elems;
@@ -2217,7 +2457,7 @@ int ddi_gradient_pipelined( DDIPlan & plan, ConstField3 spins, Field3 g_ddi, cud
         ib.in_os = std::size_t( kbl ) * d.Ha, ib.in_split = kbl, ib.in_split_stride = dc.block_stride;
         ib.n_u = d.Ha, ib.n_o = ncl, ib.n_in = d.Pb, ib.n_out = d.Nb, ib.ncol = 1 << plan.fast_b.lg, ib.scale = 1.0;
         launch_pass16<true>( plan.fast_b, grid_b, stream, plan.plan[1], ib, plan.lg_split, 31 );
-        launch_inv_a16( plan.fast_a, grid_a, stream, plan.plan_ah, plan.plan[0].twiddle, d, plan.A, g_ddi, inv_P, q );
+        run_inv_a16( plan, g_ddi, inv_P, q, 1, stream );
     }
     SB_CUDA_CHECK( cudaGetLastError() );
     return 4 * nq + 1;
@@ -2238,9 +2478,7 @@ int ddi_gradient( DDIPlan & plan, ConstField3 spins, Field3 g_ddi, cudaStream_t 
     const int kbl      = dc.Pb;
     const int rows     = d.Nb * d.Nc;
     if( plan.fast_a.on )
-        launch_fwd_a16(
-            plan.fast_a, dim3( ( rows + ( 1 << plan.fast_a.lg ) - 1 ) >> plan.fast_a.lg, nq ), stream, plan.plan_ah, plan.plan[0].twiddle, d, spins,
-            plan.A, 0 );
+        run_fwd_a16( plan, spins, 0, nq, stream );
     else
         k_ddi_fwd_a<<<dim3( rows, d.NB ), fft_threads( d.Pa / 4 ), plan.smem_a, stream>>>( plan.plan[0], d, spins, plan.A );
     // forward b: A[q][c][b][ka] -> B; outer index o = q * ncl + c. Single device: B[o][kb][ka]; distributed: the kb axis
@@ -2312,9 +2550,7 @@ int ddi_gradient( DDIPlan & plan, ConstField3 spins, Field3 g_ddi, cudaStream_t 
         k_fft_pass<true><<<grid_b, fft_threads( d.Pb / 4 * plan.ncol_b ), plan.smem_b, stream>>>( plan.plan[1], ib );
     const double inv_P = 1.0 / ( double( d.Pa ) * d.Pb * d.Pc );
     if( plan.fast_a.on )
-        launch_inv_a16(
-            plan.fast_a, dim3( ( rows + ( 1 << plan.fast_a.lg ) - 1 ) >> plan.fast_a.lg, nq ), stream, plan.plan_ah, plan.plan[0].twiddle, d, plan.A,
-            g_ddi, inv_P, 0 );
+        run_inv_a16( plan, g_ddi, inv_P, 0, nq, stream );
     else
         k_ddi_inv_a<<<dim3( rows, d.NB ), fft_threads( d.Pa / 4 ), plan.smem_a, stream>>>( plan.plan[0], d, plan.A, g_ddi, inv_P );
     SB_CUDA_CHECK( cudaGetLastError() );

@@ -1047,13 +1047,17 @@ void DeviceChain::iterate( int solver, const GNEBParams & params, int n_iteratio
         b.view.P2  = b.rk4 + b.stride;
         b.view.Acc = b.rk4 + fs + b.stride;
     }
-    if( oso && sharded_ )
-        throw std::runtime_error( "spirit_b200: VP_OSO / LBFGS_OSO / LBFGS_Atlas are not implemented on a chain sharded over GPUs" );
+    // images sharded over GPUs: the dot products of the minimisers run over all images of the chain (all-reduce). The atlas
+    // solver's chart check compares the spins of IMAGE 0 with the charts of every image (Solver_Kernels.cpp:155-184), which only
+    // the rank holding image 0 could do: refused.
+    if( solver == Solver_LBFGS_Atlas && sharded_ )
+        throw std::runtime_error( "spirit_b200: LBFGS_Atlas is not implemented on a chain sharded over GPUs" );
     // all local images back to back: one long field for the element-wise passes of oso.cuh
     const OsoLayout L{ std::size_t( noi_ ) * T.n_storage, p.plane_stride, T.plane_sites };
     if( oso && !oso_ )
     {
         oso_.reset( new OsoState );
+        oso_->distributed = sharded_;
         oso_->allocate( solver, L.n_sites, noi_, ConstField3{ b.view.S }, L, b.stream, launches_ );
     }
 

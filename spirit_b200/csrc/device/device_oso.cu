@@ -14,7 +14,7 @@
 // All element-wise passes run over the flat storage of the fields (AoSoA blocks; padding entries are zero and stay
 // zero). The scalars of the recursion (rho, alpha, ...) are folded on the device in a fixed order and read back by the
 // host, which owns the control flow of the recursion (restart on a non-positive curvature) exactly as the reference
-// does. Single GPU only: on a slab decomposition the solvers refuse (the dot products would need an all-reduce each).
+// does. On a slab decomposition every one of these scalars is summed over the ranks before the host reads it.
 #include "oso.cuh"
 
 namespace sb
@@ -36,15 +36,21 @@ void DeviceImage::oso_iterate( int solver, LLGParams & llg, int n_iterations, bo
 {
     if( solver != Solver_LBFGS_OSO && solver != Solver_VP_OSO && solver != Solver_LBFGS_Atlas )
         throw std::runtime_error( "spirit_b200: solver id " + std::to_string( solver ) + " is not an OSO / atlas solver" );
-    if( slab_ )
-        throw std::runtime_error( "spirit_b200: VP_OSO / LBFGS_OSO / LBFGS_Atlas are not implemented on a slab decomposition" );
     auto & b = *buf_;
     ensure_work_fields( Solver_VP );
-    const OsoLayout L{ b.n_storage, stencil_.plane_stride, b.plane_sites };
+    // Slab of a lattice: the element-wise passes run over the OWNED planes (the halo planes in front of them are skipped by
+    // offsetting the field views: whole planes are whole AoSoA blocks), every dot product is summed over the ranks
+    // (Solver_LBFGS_OSO.hpp:39-77 takes them over the whole field) and the rotated spins refresh the neighbours' halo planes.
+    const std::size_t skip = slab_ ? 3 * std::size_t( stencil_.halo ) * stencil_.plane_stride : 0;
+    const std::size_t n_owned = slab_ ? std::size_t( stencil_.plane_stride ) * stencil_.nc_local : b.n_storage;
+    const OsoLayout L{ n_owned, stencil_.plane_stride, b.plane_sites };
+    const Field3 S{ b.spins.base + skip };
+    const int nos_lattice = slab_ ? int( std::size_t( nos_ ) / stencil_.nc_local * stencil_.Nc ) : nos_;
     if( !oso_ )
     {
         oso_.reset( new OsoState );
-        oso_->allocate( solver, b.n_storage, 1, b.spins.c(), L, b.stream, launches_ );
+        oso_->distributed = slab_ && comm_world() > 1;
+        oso_->allocate( solver, n_owned, 1, ConstField3{ S.base }, L, b.stream, launches_ );
     }
     for( int it = 0; it < n_iterations; ++it )
     {
@@ -62,7 +68,11 @@ void DeviceImage::oso_iterate( int solver, LLGParams & llg, int n_iterations, bo
             ++launches_;
         }
         // Fv = dtg (s x F)  ->  s x F = Fv / dtg
-        oso_update( *oso_, solver, b.spins.f(), b.Fv.c(), 1.0 / llg.dtg, b.F.c(), L, nos_, llg.dt, b.stream, launches_ );
+        oso_update(
+            *oso_, solver, S, ConstField3{ b.Fv.base + skip }, 1.0 / llg.dtg, ConstField3{ b.F.base + skip }, L, nos_lattice, llg.dt, b.stream,
+            launches_ );
+        if( slab_ )
+            exchange_halo( &b.spins );
         if( hk )
         {
             k_hook<<<b.nblocks, BLOCK_THREADS, 0, b.stream>>>( stencil_, b.lg, b.spins.c(), b.F.f(), b.Fv.c(), b.partials + b.nblocks );
@@ -75,6 +85,8 @@ void DeviceImage::oso_iterate( int solver, LLGParams & llg, int n_iterations, bo
     SB_CUDA_CHECK( cudaGetLastError() );
     if( hook )
     {
+        allreduce_scalars( 4, 1, false ); // energy
+        allreduce_scalars( 5, 1, true );  // max torque^2
         SB_CUDA_CHECK( cudaMemcpyAsync( b.h_scalars + 4, b.scalars + 4, 2 * sizeof( double ), cudaMemcpyDeviceToHost, b.stream ) );
         SB_CUDA_CHECK( cudaStreamSynchronize( b.stream ) );
         if( result )

@@ -354,6 +354,8 @@ static __global__ void __launch_bounds__( BLOCK_THREADS ) k_llg_stage(
             const D3 gt          = total( g );
             const D3 F           = make_d3( -gt.x, -gt.y, -gt.z );
             Fv                   = virtual_force<NB_T>( l, site, si, F, xi );
+            if( l.has_stt == 2 )
+                Fv = add3( Fv, stt_gradient_term<NB_T>( p, l, a.s, site, si ) );
             if( HOOK && STAGE == 1 )
             {
                 store3( a.F_out, site.idx, F );
@@ -366,6 +368,8 @@ static __global__ void __launch_bounds__( BLOCK_THREADS ) k_llg_stage(
             const SiteGradient g = site_gradient<NB_T>( p, a.sp, a.ddi_sp, site, spi );
             const D3 gt          = total( g );
             Fvp                  = virtual_force<NB_T>( l, site, spi, make_d3( -gt.x, -gt.y, -gt.z ), xi );
+            if( l.has_stt == 2 )
+                Fvp = add3( Fvp, stt_gradient_term<NB_T>( p, l, a.sp, site, spi ) );
             if( HOOK && last_stage )
                 e = site_energy<NB_T>( p, site, spi, g );
         }
@@ -533,7 +537,10 @@ static __global__ void __launch_bounds__( BLOCK_THREADS ) k_force_and_virtual(
         const D3 gt          = total( g );
         const D3 F           = make_d3( -gt.x, -gt.y, -gt.z );
         store3( F_out, site.idx, F );
-        store3( Fv_out, site.idx, virtual_force<NB_T>( l, site, si, F, xi ) );
+        D3 Fv = virtual_force<NB_T>( l, site, si, F, xi );
+        if( l.has_stt == 2 )
+            Fv = add3( Fv, stt_gradient_term<NB_T>( p, l, s, site, si ) );
+        store3( Fv_out, site.idx, Fv );
         e = site_energy<NB_T>( p, site, si, g );
     }
     e = block_sum( e );

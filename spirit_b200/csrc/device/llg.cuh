@@ -182,7 +182,7 @@ __device__ __forceinline__ D3 virtual_force_ib( const LLGParams & l, int ib, con
     }
     const D3 sxw = cross3( s, w );
     fv           = make_d3( fv.x + sxw.x, fv.y + sxw.y, fv.z + sxw.z );
-    if( l.has_stt )
+    if( l.has_stt == 1 )
     {
         // monolayer approximation: Fv += c1 * pol + c2 * (pol x s)   (Method_LLG.cpp:207-212)
         const D3 pol = make_d3( l.stt_pol[0], l.stt_pol[1], l.stt_pol[2] );
@@ -199,6 +199,50 @@ __device__ __forceinline__ D3
 virtual_force( const LLGParams & l, const Site & site, const D3 & s, const D3 & F, const D3 & xi )
 {
     return virtual_force_ib( l, NB_T == 1 ? 0 : site.ib, s, F, xi );
+}
+
+// Spin-transfer torque in the gradient approximation (Method_LLG.cpp:184-205 with Vectormath::jacobian, Vectormath.cpp:816-903):
+// finite differences of the configuration `conf` along the three lattice translations of the SAME basis atom, central where
+// both neighbours exist, one-sided (and doubled) at an open boundary, contracted with the current direction.
+template<int NB_T>
+__device__ __forceinline__ D3
+stt_gradient_term( const StencilParams & p, const LLGParams & l, const ConstField3 & conf, const Site & site, const D3 & s )
+{
+    const int NB = NB_T > 0 ? NB_T : p.NB;
+    const int x  = site.a * NB + ( NB_T == 1 ? 0 : site.ib );
+    D3 grad      = make_d3( 0, 0, 0 );
+#pragma unroll
+    for( int t = 0; t < 3; ++t )
+    {
+        const int n   = t == 0 ? p.Na : ( t == 1 ? p.Nb : p.Nc );
+        const int pos = t == 0 ? site.a : ( t == 1 ? site.b : site.c );
+        D3 m0 = s, m1 = s;
+        double factor = 0.5;
+        for( int side = 0; side < 2; ++side )
+        {
+            int q      = pos + ( side == 0 ? 1 : -1 );
+            bool valid = true;
+            if( q < 0 || q >= n )
+            {
+                valid = p.bc[t] != 0;
+                q     = q < 0 ? q + n : q - n;
+            }
+            if( valid )
+            {
+                const int j = t == 0 ? storage_index( p, q * NB + ( x - site.a * NB ), site.b, site.c )
+                                     : ( t == 1 ? storage_index( p, x, q, site.c ) : storage_index( p, x, site.b, q ) );
+                ( side == 0 ? m0 : m1 ) = load3( conf, j );
+            }
+            else
+                factor *= 2;
+        }
+        const double w = l.stt_w[t] * factor;
+        grad.x += w * ( m0.x - m1.x );
+        grad.y += w * ( m0.y - m1.y );
+        grad.z += w * ( m0.z - m1.z );
+    }
+    const D3 gxs = cross3( grad, s );
+    return make_d3( l.stt_g1 * grad.x + l.stt_g2 * gxs.x, l.stt_g1 * grad.y + l.stt_g2 * gxs.y, l.stt_g1 * grad.z + l.stt_g2 * gxs.z );
 }
 
 // Taylor coefficients of sin(t)/t and (1-cos t)/t^2 in x = t^2: (-1)^k/(2k+1)! and (-1)^k/(2k+2)!. In constant

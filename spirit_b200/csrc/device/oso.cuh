@@ -321,12 +321,15 @@ struct LbfgsEngine
     std::uint64_t * launches  = nullptr;
     double rho[MEM] = { 0, 0, 0 }, alpha[MEM] = { 0, 0, 0 };
     int local_iter  = 0;
+    bool distributed = false; // the fields are one rank's part (slab / image shard): every dot product is summed over the ranks
 
     // fold `count` partial arrays into scalars[0..count) and bring them to the host
     void fetch( int count )
     {
         for( int k = 0; k < count; ++k )
             k_reduce_sum<<<1, BLOCK_THREADS, 0, stream>>>( partials + std::size_t( k ) * nb, nb, scalars + k );
+        if( distributed )
+            comm_allreduce( scalars, count, false, stream );
         SB_CUDA_CHECK( cudaMemcpyAsync( h_scalars, scalars, count * sizeof( double ), cudaMemcpyDeviceToHost, stream ) );
         SB_CUDA_CHECK( cudaStreamSynchronize( stream ) );
         *launches += count;
@@ -418,6 +421,7 @@ struct OsoState
     LbfgsEngine lbfgs;
     int nblocks        = 0;
     int n_images       = 1;
+    bool distributed   = false; // slab of a lattice / shard of a chain: scalars are reduced over the ranks (set before allocate)
     double * partials  = nullptr; // [max(3, n_images)][nblocks]
     double * scalars   = nullptr; // device [max(4, n_images)]
     double * h_scalars = nullptr;
@@ -457,6 +461,7 @@ struct OsoState
             lbfgs.h_scalars = h_scalars;
             lbfgs.stream    = stream;
             lbfgs.launches  = &launches;
+            lbfgs.distributed = distributed;
         }
         if( !lbfgs_solver || atlas )
             zero( vel ); // VP_OSO: velocity; atlas: charts a3 (first n_sites doubles) and the chart-change flag behind them
@@ -536,6 +541,8 @@ inline void oso_update(
         k_oso_gradient<true><<<nb, BLOCK_THREADS, 0, stream>>>( C, o.grad.f(), o.vel.f(), L, inv_c_factor, half_inv_m, p0, p1 );
         k_reduce_sum<<<1, BLOCK_THREADS, 0, stream>>>( p0, nb, o.scalars );
         k_reduce_sum<<<1, BLOCK_THREADS, 0, stream>>>( p1, nb, o.scalars + 1 );
+        if( o.distributed )
+            comm_allreduce( o.scalars, 2, false, stream ); // the projection is taken over the whole lattice / chain
         k_vp_oso_update<<<nb, BLOCK_THREADS, 0, stream>>>( S, o.grad.c(), o.vel.f(), L, o.scalars, dt, half_inv_m );
         launches += 4;
         return;
@@ -564,6 +571,14 @@ inline void oso_update(
         sumsq = 0;
         for( int i = 0; i < o.n_images; ++i )
             sumsq = std::max( sumsq, o.h_scalars[i] );
+        if( o.distributed )
+        {
+            // images sharded over ranks: the largest step of ANY image of the chain
+            SB_CUDA_CHECK( cudaMemcpyAsync( o.scalars, &sumsq, sizeof( double ), cudaMemcpyHostToDevice, stream ) );
+            comm_allreduce( o.scalars, 1, true, stream );
+            SB_CUDA_CHECK( cudaMemcpyAsync( &sumsq, o.scalars, sizeof( double ), cudaMemcpyDeviceToHost, stream ) );
+            SB_CUDA_CHECK( cudaStreamSynchronize( stream ) );
+        }
     }
     const double rms     = std::sqrt( sumsq / double( nos_per_image ) );
     const double scaling = rms > maxmove ? maxmove / rms : 1.0;
@@ -586,6 +601,16 @@ inline void oso_update(
     int flag = 0;
     SB_CUDA_CHECK( cudaMemcpyAsync( &flag, chart_flag, sizeof( int ), cudaMemcpyDeviceToHost, stream ) );
     SB_CUDA_CHECK( cudaStreamSynchronize( stream ) );
+    if( o.distributed )
+    {
+        // a chart change anywhere changes the charts everywhere (Solver_Kernels.cpp:155-184 decides on the whole field)
+        double any = flag ? 1.0 : 0.0;
+        SB_CUDA_CHECK( cudaMemcpyAsync( o.scalars, &any, sizeof( double ), cudaMemcpyHostToDevice, stream ) );
+        comm_allreduce( o.scalars, 1, true, stream );
+        SB_CUDA_CHECK( cudaMemcpyAsync( &any, o.scalars, sizeof( double ), cudaMemcpyDeviceToHost, stream ) );
+        SB_CUDA_CHECK( cudaStreamSynchronize( stream ) );
+        flag = any != 0.0;
+    }
     if( flag )
     {
         AtlasMemory mem;

@@ -94,10 +94,15 @@ struct LLGParams
     double damping;   // alpha
     double dt;        // raw llg_dt (VP uses it directly, Solver_VP.hpp:95-110)
     int direct_minimization; // Fv = dtg * s x F
-    int has_stt;      // monolayer spin-transfer torque (Method_LLG.cpp:207-212)
+    int has_stt;      // 1: monolayer spin-transfer torque (Method_LLG.cpp:207-212), 2: gradient approximation (:184-205)
     double stt_c1;    // -dtg*a_j*(alpha-beta)
     double stt_c2;    // -dtg*a_j*(1+beta*alpha)
     double stt_pol[3];
+    // gradient approximation: s_c_grad = jacobian(s) je = sum_t stt_w[t] f_t (s(+t) - s(-t)), t = a, b, c lattice translations,
+    // stt_w = (lattice_constant [ta tb tc])^-1 je, f_t = 1/2 (central) or 1 (one-sided at an open boundary) -- Vectormath.cpp:816-903;
+    // Fv += stt_g1 s_c_grad + stt_g2 s_c_grad x s with stt_g1 = dtg a_j (alpha - beta), stt_g2 = dtg a_j (1 + beta alpha)
+    double stt_w[3];
+    double stt_g1, stt_g2;
     int has_thermal;  // Method_LLG.cpp:65-110,215-219
     int pad;
     double thermal_scale[MAX_BASIS]; // epsilon*sqrt(T/mu_s[ib])

@@ -40,6 +40,10 @@ __device__ __forceinline__ double dot3( const D3 & a, const D3 & b )
 {
     return fma( a.z, b.z, fma( a.y, b.y, a.x * b.x ) );
 }
+__device__ __forceinline__ D3 add3( const D3 & a, const D3 & b )
+{
+    return make_d3( a.x + b.x, a.y + b.y, a.z + b.z );
+}
 __device__ __forceinline__ D3 cross3( const D3 & a, const D3 & b )
 {
     return make_d3( fma( a.y, b.z, -( a.z * b.y ) ), fma( a.z, b.x, -( a.x * b.z ) ), fma( a.x, b.y, -( a.y * b.x ) ) );

@@ -30,7 +30,8 @@ def main():
     # the second lattice is cut into several c-segments per slab: the fused kernel launches the two end segments first and
     # exchanges two halo planes per side while the interior segments run
     cases = [(24, 10, 12, bc_c, solver, T) for bc_c in (1, 0)
-             for solver, T in (("Depondt", 0.0), ("Depondt", 5.0), ("Heun", 0.0), ("SIB", 0.0), ("RK4", 0.0), ("VP", 0.0))]
+             for solver, T in (("Depondt", 0.0), ("Depondt", 5.0), ("Heun", 0.0), ("SIB", 0.0), ("RK4", 0.0), ("VP", 0.0),
+                               ("VP_OSO", 0.0), ("LBFGS_OSO", 0.0), ("LBFGS_Atlas", 0.0))]
     cases += [(40, 20, 48, bc_c, solver, T) for bc_c in (1, 0) for solver, T in (("Depondt", 0.0), ("Depondt", 5.0), ("SIB", 5.0))]
     for Na, Nb, Nc, bc_c, solver, temperature in cases:
         if True:
@@ -60,7 +61,8 @@ def main():
                 dev = np.abs(np.concatenate(parts) - ref).max()
                 moved = np.abs(ref - s_global).max()
                 # VP couples all sites through two global sums whose summation order depends on the decomposition
-                tol = 1e-12 if solver == "VP" else 0.0
+                # (the minimisers too: every dot product of the L-BFGS recursion is a sum over all slabs)
+                tol = 1e-12 if solver == "VP" else (1e-10 if "OSO" in solver or "Atlas" in solver else 0.0)
                 ok = dev <= tol and moved > 1e-4 and abs(e_slab - g.energy()) <= 1e-12 * abs(g.energy())
                 print("%dx%dx%d bc_c=%d %-8s T=%g (step variant %d): max deviation %.3e, moved %.2e, E slab %.12e global %.12e %s" % (
                     Na, Nb, Nc, bc_c, solver, temperature, variant, dev, moved, e_slab, g.energy(), "OK" if ok else "FAIL"), flush=True)
@@ -127,7 +129,8 @@ def gneb_sharded(lib, rank, world, tmp):
     images0 = [full.spins(i).copy() for i in range(noi)]
     full.close()
     i_begin, n_local = slab.partition(noi, world)[rank]
-    for solver, n, types in (("VP", 30, {3: S.GNEB_CLIMBING}), ("Depondt", 8, {2: S.GNEB_FALLING, 5: S.GNEB_CLIMBING}), ("Heun", 8, {})):
+    for solver, n, types in (("VP", 30, {3: S.GNEB_CLIMBING}), ("Depondt", 8, {2: S.GNEB_FALLING, 5: S.GNEB_CLIMBING}), ("Heun", 8, {}),
+                             ("VP_OSO", 20, {3: S.GNEB_CLIMBING}), ("LBFGS_OSO", 12, {4: S.GNEB_CLIMBING})):
         p = S.Session(lib, path)
         p.set_anisotropy(0.25, (0, 0, 1))
         p.chain_set_length(n_local)
@@ -162,7 +165,8 @@ def gneb_sharded(lib, rank, world, tmp):
             drx = np.abs(np.concatenate([x[1] for x in parts]) - rx_ref).max()
             de = np.abs(np.concatenate([x[2] for x in parts]) - e_ref).max()
             dtq = max(abs(x[3] - tq_ref) for x in parts)
-            ok = dev <= 1e-13 and drx <= 1e-12 and de <= 1e-10 and dtq <= 1e-12 * tq_ref
+            oso = "OSO" in solver  # dot products over all images: summation order depends on the sharding
+            ok = dev <= (1e-10 if oso else 1e-13) and drx <= (1e-9 if oso else 1e-12) and de <= (1e-8 if oso else 1e-10) and dtq <= (1e-8 if oso else 1e-12) * tq_ref
             print("GNEB sharded %-8s: spins %.3e Rx %.3e E %.3e torque %.3e %s" % (solver, dev, drx, de, dtq, "OK" if ok else "FAIL"), flush=True)
             if not ok:
                 failures.append(("gneb", solver))

@@ -4,6 +4,8 @@ Tolerances are BASELINE.json's: gradient and energy 1e-12 relative (fp64), singl
 Both libraries are driven through identical C API calls so both see identical (float-narrowed) parameters
 (SURVEY.md 8c hazard 5).
 """
+import ctypes
+
 import numpy as np
 import pytest
 
@@ -436,3 +438,45 @@ def test_temperature_gradient_langevin_profile(cfg, product):
     for k in range(4):
         assert abs(mean[k] - expected[k]) < max(4 * err[k], 0.012), (k, mean[k], expected[k], err[k])
     p.close()
+
+
+STT_CASES = [
+    # lattice / boundary conditions of the finite differences: periodic, open (one-sided differences), single cells along an axis,
+    # a two-atom basis on skewed Bravais vectors (inverse of the lattice matrix), several shells
+    ("solvers", {"n_basis_cells": "12 9 1"}),
+    ("cubic256", {"n_basis_cells": "9 7 5", "boundary_conditions": "0 1 0", "llg_temperature": "0"}),
+    ("cubic256", {"n_basis_cells": "6 5 4", "boundary_conditions": "0 0 0", "llg_temperature": "0"}),
+    ("ddi", {"ddi_method": "none", "n_basis_cells": "5 4 3"}),
+]
+
+
+@pytest.mark.parametrize("gradient", [0, 1])
+@pytest.mark.parametrize("solver", ["Depondt", "Heun", "SIB", "RK4"])
+@pytest.mark.parametrize("preset,overrides", STT_CASES)
+def test_spin_transfer_torque(cfg, product, oracle, solver, preset, overrides, gradient):
+    """Spin-transfer torque in Calculate_Force_Virtual: the monolayer approximation (Method_LLG.cpp:207-212) and the gradient
+    approximation for in-plane currents (Method_LLG.cpp:184-205 with Vectormath::jacobian, Vectormath.cpp:816-903)"""
+    extra = "pairs2" if preset == "ddi" else None
+    kw = dict(overrides, llg_stt_use_gradient=gradient, llg_stt_magnitude="1.7", llg_stt_polarisation_normal="0.6 -0.3 0.74",
+              llg_beta="0.12", llg_damping="0.25")
+    p, o = make_case(cfg, product, oracle, preset, kw, extra)
+    s0 = unit_random(p.nos, 5)
+    for x in (p, o):
+        x.set_spins(s0)
+        x.llg_start(S.SOLVERS[solver], single_shot=True)
+        x.n_shot(6)
+    ref = o.spins().copy()
+    dev = np.abs(p.spins() - ref).max()
+    assert np.abs(ref - s0).max() > 1e-4
+    assert dev < STEP_ATOL, dev
+    for x in (p, o):
+        x.stop()
+    # the torque does something: the same steps without it end elsewhere
+    o.set_spins(s0)
+    o.lib.Parameters_LLG_Set_STT(o.state, bool(gradient), 0.0, (ctypes.c_float * 3)(0.6, -0.3, 0.74), -1, -1)
+    o.llg_start(S.SOLVERS[solver], single_shot=True)
+    o.n_shot(6)
+    assert np.abs(o.spins() - ref).max() > 1e-6
+    o.stop()
+    p.close()
+    o.close()
