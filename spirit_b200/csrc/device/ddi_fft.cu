@@ -52,7 +52,10 @@ namespace dev
 namespace
 {
 
-constexpr int FFT_THREADS  = 512;  // upper bound (128 registers: a radix-16 butterfly lives in 64); launches use fft_threads( work items )
+#ifndef SB_FFT_THREADS
+#define SB_FFT_THREADS 512 // tuning builds: 256 lifts the register cap of the fast kernels to 255 (radix-16 stages without spills)
+#endif
+constexpr int FFT_THREADS  = SB_FFT_THREADS;  // upper bound (128 registers: a radix-16 butterfly lives in 64); launches use fft_threads( work items )
 constexpr int MAX_RADICES  = 16;
 constexpr int MAX_SMEM_FFT = 200 * 1024;
 
@@ -480,6 +483,10 @@ struct PassArgs
     int use_in_peer, use_out_peer;
     const double2 * in_peer[DDI_MAX_PEERS];
     double2 * out_peer[DDI_MAX_PEERS];
+    // pencil decomposition (ka cut over the ranks): the OUTER index o = q * opeer_planes + c (c a global plane) selects the
+    // destination: rank c / opeer_ncl, whose buffer out_peer[rank] holds element (q, c % opeer_ncl) at ((q * opeer_ncl) +
+    // c % opeer_ncl) * out_os. The inverse b-pass stores its rows straight into the a-pass operand of the rank that owns the plane.
+    int opeer_planes, opeer_ncl;
 };
 __device__ __forceinline__ std::size_t pass_offset( int j, std::size_t js, int split, std::size_t split_stride )
 {
@@ -576,6 +583,11 @@ static __global__ void __launch_bounds__( FFT_THREADS, SB_FFT16_MINB ) k_fft_pas
     if( valid )
     {
         double2 * out = a.out + std::size_t( o ) * a.out_os + u0 + ctile;
+        if( a.opeer_planes )
+        {
+            const int q = o / a.opeer_planes, c = o - q * a.opeer_planes, r = c / a.opeer_ncl;
+            out         = a.out_peer[r] + std::size_t( q * a.opeer_ncl + ( c - r * a.opeer_ncl ) ) * a.out_os + u0 + ctile;
+        }
 #pragma unroll
         for( int k = 0; k < FFT_E * NSEQ; ++k )
         {
@@ -660,6 +672,12 @@ static __global__ void __launch_bounds__( FFT_THREADS, SB_FFT16_MINB ) k_fft_pas
         if( u < a.n_u )
         {
             const std::size_t base = std::size_t( o ) * a.out_os + u;
+            double2 * obase        = nullptr;
+            if( a.opeer_planes )
+            {
+                const int q = o / a.opeer_planes, c = o - q * a.opeer_planes, r = c / a.opeer_ncl;
+                obase       = a.out_peer[r] + std::size_t( q * a.opeer_ncl + ( c - r * a.opeer_ncl ) ) * a.out_os + u;
+            }
 #pragma unroll
             for( int k = 0; k < FFT_E; ++k )
             {
@@ -669,7 +687,7 @@ static __global__ void __launch_bounds__( FFT_THREADS, SB_FFT16_MINB ) k_fft_pas
                     const double2 w = x[( j << lg_ncol ) + col];
                     double2 * dst   = a.use_out_peer
                                           ? a.out_peer[j >> lg_out_split] + base + std::size_t( unsigned( j ) & ( ( 1u << lg_out_split ) - 1u ) ) * a.out_js
-                                          : a.out + base + pass_offset16( j, a.out_js, lg_out_split, a.out_split_stride );
+                                          : ( obase ? obase : a.out + base ) + pass_offset16( j, a.out_js, lg_out_split, a.out_split_stride );
                     *dst = make_double2( a.scale * w.x, a.scale * w.y );
                 }
             }
@@ -1200,10 +1218,25 @@ __device__ __forceinline__ void row_map( int lg_nrow, int & row, int & jlow, int
     jhigh_step  = blockDim.x >> ( 2 + lg_nrow );
 }
 
+// Pencil decomposition over several GPUs: the ka axis of the half spectrum is cut into per-rank blocks of `kblock` (the last rank
+// also takes ka = Pa / 2), and the forward a-pass stores element ka of the row (q, global plane, b) straight into the b-pass
+// operand of the rank that owns it (peer-mapped memory, NVLink): AT_r[q][c_global][b][ka - r kblock], rows of w[r] elements.
+struct APush
+{
+    int on, lg_kblock, world, planes, c_begin;
+    int w[DDI_MAX_PEERS];
+    double2 * base[DDI_MAX_PEERS];
+};
+__device__ __forceinline__ double2 * apush_dst( const APush & ap, int q, int c, int b, int Nb, int k )
+{
+    const int r = min( k >> ap.lg_kblock, ap.world - 1 );
+    return ap.base[r] + ( ( std::size_t( q ) * ap.planes + ap.c_begin + c ) * Nb + b ) * ap.w[r] + ( k - ( r << ap.lg_kblock ) );
+}
+
 template<int LOGM>
 static __global__ void __launch_bounds__( FFT_THREADS, SB_FFT16_MINB ) k_ddi_fwd_a16(
     const __grid_constant__ FFTPlan1D plan_h, const double2 * __restrict__ tw_full, const __grid_constant__ DDIDims d,
-    ConstField3 spins, double2 * __restrict__ A, const int lg_nrow, const int q0 )
+    ConstField3 spins, double2 * __restrict__ A, const int lg_nrow, const int q0, const __grid_constant__ APush ap )
 {
     extern __shared__ double2 smem[];
     constexpr int m = 1 << LOGM;
@@ -1244,19 +1277,27 @@ static __global__ void __launch_bounds__( FFT_THREADS, SB_FFT16_MINB ) k_ddi_fwd
         const double2 Zm = smem[( ( ( m - k ) & ( m - 1 ) ) << lg_nrow ) + rl]; // Z_m = Z_0
         const double2 E  = make_double2( 0.5 * ( Zk.x + Zm.x ), 0.5 * ( Zk.y - Zm.y ) );
         const double2 O  = make_double2( 0.5 * ( Zk.y + Zm.y ), -0.5 * ( Zk.x - Zm.x ) );
-        out[k]           = cadd( E, cmul( __ldg( tw_full + k ), O ) );
+        const double2 X  = cadd( E, cmul( __ldg( tw_full + k ), O ) );
+        if( ap.on )
+            *apush_dst( ap, q, c, b, d.Nb, k ) = X;
+        else
+            out[k] = X;
     }
     if( jhigh == 0 && jlow == 0 )
     {
         const double2 Z0 = smem[rl];
-        out[m]           = make_double2( Z0.x - Z0.y, 0.0 );
+        const double2 X  = make_double2( Z0.x - Z0.y, 0.0 );
+        if( ap.on )
+            *apush_dst( ap, q, c, b, d.Nb, m ) = X;
+        else
+            out[m] = X;
     }
 }
 
 template<int LOGM>
 static __global__ void __launch_bounds__( FFT_THREADS, SB_FFT16_MINB ) k_ddi_inv_a16(
     const __grid_constant__ FFTPlan1D plan_h, const double2 * __restrict__ tw_full, const __grid_constant__ DDIDims d,
-    const double2 * __restrict__ A, Field3 g, const double inv_P, const int lg_nrow, const int q0 )
+    const double2 * __restrict__ A, Field3 g, const double inv_P, const int lg_nrow, const int q0, const __grid_constant__ APush ap )
 {
     extern __shared__ double2 smem[];
     constexpr int m = 1 << LOGM;
@@ -1274,7 +1315,9 @@ static __global__ void __launch_bounds__( FFT_THREADS, SB_FFT16_MINB ) k_ddi_inv
         double2 Z   = make_double2( 0.0, 0.0 );
         if( valid )
         {
-            const double2 Xk = in[k], Xm = in[m - k];
+            // pencil decomposition: element k of the row lives in the operand of the rank that owns the ka block (pulled over NVLink)
+            const double2 Xk = ap.on ? *apush_dst( ap, q, c, b, d.Nb, k ) : in[k];
+            const double2 Xm = ap.on ? *apush_dst( ap, q, c, b, d.Nb, m - k ) : in[m - k];
             const double2 S  = make_double2( Xk.x + Xm.x, Xk.y - Xm.y ); // X_k + conj X_{m-k}
             const double2 D  = make_double2( Xk.x - Xm.x, Xk.y + Xm.y ); // X_k - conj X_{m-k}
             const double2 w  = __ldg( tw_full + k );                     // exp(-2 pi i k / Pa); the inverse needs its conjugate
@@ -1310,7 +1353,8 @@ static __global__ void __launch_bounds__( FFT_THREADS, SB_FFT16_MINB ) k_ddi_inv
 template<int LOGM>
 static __global__ void __launch_bounds__( FFT_THREADS, SB_FFT16_MINB ) k_ddi_fwd_a16p(
     const __grid_constant__ FFTPlan1D plan_h, const double2 * __restrict__ tw_full, const __grid_constant__ DDIDims d,
-    ConstField3 spins, double2 * __restrict__ A, const int lg_nrow, const int q0, const int n_rg, const int n_tiles )
+    ConstField3 spins, double2 * __restrict__ A, const int lg_nrow, const int q0, const int n_rg, const int n_tiles,
+    const __grid_constant__ APush ap )
 {
     extern __shared__ double2 smem[];
     constexpr int m = 1 << LOGM;
@@ -1358,12 +1402,20 @@ static __global__ void __launch_bounds__( FFT_THREADS, SB_FFT16_MINB ) k_ddi_fwd
                 const double2 Zm = x[( ( ( m - k ) & ( m - 1 ) ) << lg_nrow ) + rl]; // Z_m = Z_0
                 const double2 E  = make_double2( h * ( Zk.x + Zm.x ), h * ( Zk.y - Zm.y ) );
                 const double2 O  = make_double2( h * ( Zk.y + Zm.y ), -h * ( Zk.x - Zm.x ) );
-                out[k]           = cadd( E, cmul( __ldg( tw_full + k ), O ) );
+                const double2 X  = cadd( E, cmul( __ldg( tw_full + k ), O ) );
+                if( ap.on )
+                    *apush_dst( ap, q, c, b, d.Nb, k ) = X;
+                else
+                    out[k] = X;
             }
             if( jhigh == 0 && jlow == 0 )
             {
                 const double2 Z0 = x[rl];
-                out[m]           = make_double2( d.mu_s[0] * ( Z0.x - Z0.y ), 0.0 );
+                const double2 X  = make_double2( d.mu_s[0] * ( Z0.x - Z0.y ), 0.0 );
+                if( ap.on )
+                    *apush_dst( ap, q, c, b, d.Nb, m ) = X;
+                else
+                    out[m] = X;
             }
         }
     }
@@ -1372,7 +1424,8 @@ static __global__ void __launch_bounds__( FFT_THREADS, SB_FFT16_MINB ) k_ddi_fwd
 template<int LOGM>
 static __global__ void __launch_bounds__( FFT_THREADS, SB_FFT16_MINB ) k_ddi_inv_a16p(
     const __grid_constant__ FFTPlan1D plan_h, const double2 * __restrict__ tw_full, const __grid_constant__ DDIDims d,
-    const double2 * __restrict__ A, Field3 g, const double inv_P, const int lg_nrow, const int q0, const int n_rg, const int n_tiles )
+    const double2 * __restrict__ A, Field3 g, const double inv_P, const int lg_nrow, const int q0, const int n_rg, const int n_tiles,
+    const __grid_constant__ APush ap )
 {
     extern __shared__ double2 smem[];
     constexpr int m = 1 << LOGM;
@@ -1391,10 +1444,11 @@ static __global__ void __launch_bounds__( FFT_THREADS, SB_FFT16_MINB ) k_ddi_inv
         for( int kk = 0; kk < FFT_E; ++kk )
         {
             const int k = 4 * ( jhigh + kk * jstep ) + jlow;
-            cp_async16( raw + ( k << lg_nrow ) + rl, valid ? in + k : A, valid );
+            const double2 * src = !valid ? A : ( ap.on ? apush_dst( ap, q0 + qi, c, b, d.Nb, k ) : in + k );
+            cp_async16( raw + ( k << lg_nrow ) + rl, src, valid );
         }
         if( jhigh == 0 && jlow == 0 )
-            cp_async16( raw + ( m << lg_nrow ) + rl, valid ? in + m : A, valid );
+            cp_async16( raw + ( m << lg_nrow ) + rl, !valid ? A : ( ap.on ? apush_dst( ap, q0 + qi, c, b, d.Nb, m ) : in + m ), valid );
         cp_async_commit();
     };
     int tile = blockIdx.x, stage = 0;
@@ -1550,6 +1604,18 @@ struct DDIPlan
     } fast_a, fast_b, fast_c;
     APipe apipe;
     bool a_pipe = false;           // the a-passes run as the persistent pipelined kernels
+    // pencil decomposition over ranks (ka cut into per-rank blocks): see ddi_gradient_pencil
+    bool pencil = false, pencil_overlap = false;
+    // pencil transposes by the copy engines (ddi_gradient_pencil_dma): the a-passes stay local, 2-D peer copies carry the ka blocks
+    bool pencil_dma = false;
+    double2 * A_recv = nullptr;    // [q][ncl][Nb][Ha]: the inverse a-pass operand, filled by the ranks' copies
+    std::vector<void *> A_recv_peer;
+    cudaStream_t copy_stream[DDI_MAX_PEERS] = {};
+    cudaEvent_t ev_dma[4 * 3] = {};
+    APush push{};                  // destinations of the forward a-pass / sources of the inverse a-pass (on = 0 without pencils)
+    double2 * AT = nullptr;        // [q][Nc_global][Nb][w]: the b-pass operand of this rank's ka block, written by all ranks
+    double2 * BT = nullptr;        // [q][Nc_global][Pb][w]: the c-pass operand
+    std::vector<void *> AT_peer;
     FFTPlan1D plan_ah;             // length Pa / 2
     double2 * twiddle_ah = nullptr;
     int lg_split         = 31;     // lg of the per-rank kb block (distributed layout), 31: no split
@@ -1593,6 +1659,18 @@ struct DDIPlan
             cudaFree( twiddle_ah );
         if( A )
             cudaFree( A );
+        if( A_recv )
+            cudaFree( A_recv );
+        for( auto st : copy_stream )
+            if( st )
+                cudaStreamDestroy( st );
+        for( auto e : ev_dma )
+            if( e )
+                cudaEventDestroy( e );
+        if( AT )
+            cudaFree( AT );
+        if( BT )
+            cudaFree( BT );
         if( B )
             cudaFree( B );
         if( C )
@@ -1795,14 +1873,14 @@ bool configure_a16_pipelined( const DDIPlan::Fast & f, int m, APipe & ap )
 }
 void launch_fwd_a16p(
     const DDIPlan::Fast & f, const APipe & ap, int n_rg, int nq, cudaStream_t stream, const FFTPlan1D & plan_h, const double2 * tw_full,
-    const DDIDims & d, ConstField3 spins, double2 * A, int q0 )
+    const DDIDims & d, ConstField3 spins, double2 * A, int q0, const APush & push )
 {
     const int n_tiles = n_rg * nq;
     const dim3 grid( std::min( n_tiles, ap.ctas_fwd ) );
     switch( ilog2( plan_h.n ) )
     {
 #define C( L )                                                                                                         \
-    case L: k_ddi_fwd_a16p<L><<<grid, f.threads, ap.smem_fwd, stream>>>( plan_h, tw_full, d, spins, A, f.lg, q0, n_rg, n_tiles ); break;
+    case L: k_ddi_fwd_a16p<L><<<grid, f.threads, ap.smem_fwd, stream>>>( plan_h, tw_full, d, spins, A, f.lg, q0, n_rg, n_tiles, push ); break;
         SB_FOR_LOGN( C )
 #undef C
         default: throw std::logic_error( "spirit_b200: no fast a-pass kernel for this length" );
@@ -1810,14 +1888,14 @@ void launch_fwd_a16p(
 }
 void launch_inv_a16p(
     const DDIPlan::Fast & f, const APipe & ap, int n_rg, int nq, cudaStream_t stream, const FFTPlan1D & plan_h, const double2 * tw_full,
-    const DDIDims & d, const double2 * A, Field3 g, double inv_P, int q0 )
+    const DDIDims & d, const double2 * A, Field3 g, double inv_P, int q0, const APush & push )
 {
     const int n_tiles = n_rg * nq;
     const dim3 grid( std::min( n_tiles, ap.ctas_inv ) );
     switch( ilog2( plan_h.n ) )
     {
 #define C( L )                                                                                                         \
-    case L: k_ddi_inv_a16p<L><<<grid, f.threads, ap.smem_inv, stream>>>( plan_h, tw_full, d, A, g, inv_P, f.lg, q0, n_rg, n_tiles ); break;
+    case L: k_ddi_inv_a16p<L><<<grid, f.threads, ap.smem_inv, stream>>>( plan_h, tw_full, d, A, g, inv_P, f.lg, q0, n_rg, n_tiles, push ); break;
         SB_FOR_LOGN( C )
 #undef C
         default: throw std::logic_error( "spirit_b200: no fast a-pass kernel for this length" );
@@ -1825,7 +1903,7 @@ void launch_inv_a16p(
 }
 void launch_fwd_a16(
     const DDIPlan::Fast & f, dim3 grid, cudaStream_t stream, const FFTPlan1D & plan_h, const double2 * tw_full, const DDIDims & d,
-    ConstField3 spins, double2 * A, int q0, bool configure = false )
+    ConstField3 spins, double2 * A, int q0, bool configure = false, const APush & push = APush{} )
 {
     switch( ilog2( plan_h.n ) )
     {
@@ -1834,7 +1912,7 @@ void launch_fwd_a16(
         if( configure )                                                                                                \
             allow_smem( k_ddi_fwd_a16<L>, f.smem );                                                                    \
         else                                                                                                           \
-            k_ddi_fwd_a16<L><<<grid, f.threads, f.smem, stream>>>( plan_h, tw_full, d, spins, A, f.lg, q0 );           \
+            k_ddi_fwd_a16<L><<<grid, f.threads, f.smem, stream>>>( plan_h, tw_full, d, spins, A, f.lg, q0, push );     \
         break;
         SB_FOR_LOGN( C )
 #undef C
@@ -1843,7 +1921,7 @@ void launch_fwd_a16(
 }
 void launch_inv_a16(
     const DDIPlan::Fast & f, dim3 grid, cudaStream_t stream, const FFTPlan1D & plan_h, const double2 * tw_full, const DDIDims & d,
-    const double2 * A, Field3 g, double inv_P, int q0, bool configure = false )
+    const double2 * A, Field3 g, double inv_P, int q0, bool configure = false, const APush & push = APush{} )
 {
     switch( ilog2( plan_h.n ) )
     {
@@ -1852,7 +1930,7 @@ void launch_inv_a16(
         if( configure )                                                                                                \
             allow_smem( k_ddi_inv_a16<L>, f.smem );                                                                    \
         else                                                                                                           \
-            k_ddi_inv_a16<L><<<grid, f.threads, f.smem, stream>>>( plan_h, tw_full, d, A, g, inv_P, f.lg, q0 );        \
+            k_ddi_inv_a16<L><<<grid, f.threads, f.smem, stream>>>( plan_h, tw_full, d, A, g, inv_P, f.lg, q0, push );  \
         break;
         SB_FOR_LOGN( C )
 #undef C
@@ -1913,8 +1991,9 @@ DDIPlan * ddi_plan_create( const Hamiltonian & ham, const StencilParams & sp, cu
         }
     if( d.Pb % world != 0 )
         throw std::runtime_error( "spirit_b200: the padded b dimension must be divisible by the number of ranks" );
-    const int kbl = d.Pb / world;
-    const int nq  = 3 * d.NB;
+    int kbl      = d.Pb / world; // kb range of this rank's c-pass (the whole axis on one device and with ka pencils)
+    const int nq = 3 * d.NB;
+    int ka0 = 0, Ha_loc = 0;     // ka pencils: this rank's block of the half spectrum
     d.c_block      = d.Nc;
     d.q_stride     = std::size_t( d.Nc ) * d.Pb * d.Ha;
     d.block_stride = 0;
@@ -2045,7 +2124,69 @@ DDIPlan * ddi_plan_create( const Hamiltonian & ham, const StencilParams & sp, cu
             launch_fwd_a16( plan->fast_a, dim3(), stream, plan->plan_ah, nullptr, d, ConstField3{}, nullptr, 0, true );
             launch_inv_a16( plan->fast_a, dim3(), stream, plan->plan_ah, nullptr, d, nullptr, Field3{}, 0.0, 0, true );
         }
-        if( world > 1 && plan->fast_a.on && plan->fast_b.on && !env_flag_off( "SPIRIT_B200_DDI_PIPELINE" ) )
+        // Several ranks, fast kernels, peer-mapped memory: ka PENCILS (ddi_gradient_pencil). The transposes move the a-pass output
+        // (b not yet padded: half the volume of the kb-block transposes below) and are the stores / loads of the a-pass kernels.
+        if( world > 1 && world <= DDI_MAX_PEERS && pow2_world && plan->fast_a.on && plan->fast_b.on && d.NB == 1 && ( d.Pa / 2 ) % world == 0
+            && !env_flag_off( "SPIRIT_B200_DDI_PENCIL" ) && peer_memops_available() )
+        {
+            plan->pencil   = true;
+            const int kblk = d.Pa / 2 / world;
+            ka0            = rank * kblk;
+            Ha_loc         = kblk + ( rank == world - 1 ? 1 : 0 );
+            kbl            = d.Pb;
+            dc             = dg;
+            dc.Ha          = Ha_loc;
+            dc.c_block     = Nc_global;
+            dc.q_stride    = std::size_t( Nc_global ) * d.Pb * Ha_loc;
+            dc.block_stride = 0;
+            plan->lg_split = 31;
+            plan->push.on        = 1;
+            plan->push.lg_kblock = ilog2( kblk );
+            plan->push.world     = world;
+            plan->push.planes    = Nc_global;
+            plan->push.c_begin   = rank * ncl;
+            for( int r = 0; r < world; ++r )
+                plan->push.w[r] = kblk + ( r == world - 1 ? 1 : 0 );
+            // Overlapped schedule (ddi_gradient_pencil): the a-passes, whose speed is set by NVLink, run as PERSISTENT kernels on a
+            // bounded number of CTAs per SM, so that the b- and c-passes of the other components (own stream) share the SMs with them
+            if( const char * v = std::getenv( "SPIRIT_B200_DDI_PENCIL_DMA" ) )
+                plan->pencil_dma = v[0] != '0';
+            if( plan->pencil_dma )
+            {
+                plan->push.on = 0; // the a-passes read / write this rank's own staging buffers
+                int least = 0, greatest = 0;
+                SB_CUDA_CHECK( cudaDeviceGetStreamPriorityRange( &least, &greatest ) );
+                SB_CUDA_CHECK( cudaStreamCreateWithPriority( &plan->comm_stream, cudaStreamNonBlocking, greatest ) );
+                for( int r = 0; r < world; ++r )
+                    SB_CUDA_CHECK( cudaStreamCreateWithPriority( &plan->copy_stream[r], cudaStreamNonBlocking, greatest ) );
+                for( auto & e : plan->ev_dma )
+                    SB_CUDA_CHECK( cudaEventCreateWithFlags( &e, cudaEventDisableTiming ) );
+            }
+            plan->pencil_overlap = !plan->pencil_dma && !env_flag_off( "SPIRIT_B200_DDI_PENCIL_OVERLAP" ) && d.Na % 2 == 0 && d.plane_stride % 2 == 0;
+            if( plan->pencil_overlap )
+            {
+                plan->a_pipe = configure_a16_pipelined( plan->fast_a, d.Pa / 2, plan->apipe );
+                plan->pencil_overlap = plan->a_pipe;
+            }
+            if( plan->pencil_overlap )
+            {
+                int cap = 4; // CTAs per SM of the persistent a-passes
+                if( const char * v = std::getenv( "SPIRIT_B200_DDI_PENCIL_CTAS" ) )
+                    cap = std::max( 1, std::atoi( v ) );
+                int dev = 0, sms = 0;
+                SB_CUDA_CHECK( cudaGetDevice( &dev ) );
+                SB_CUDA_CHECK( cudaDeviceGetAttribute( &sms, cudaDevAttrMultiProcessorCount, dev ) );
+                plan->apipe.ctas_fwd = std::min( plan->apipe.ctas_fwd, cap * sms );
+                plan->apipe.ctas_inv = std::min( plan->apipe.ctas_inv, cap * sms );
+                int least = 0, greatest = 0;
+                SB_CUDA_CHECK( cudaDeviceGetStreamPriorityRange( &least, &greatest ) );
+                SB_CUDA_CHECK( cudaStreamCreateWithPriority( &plan->comm_stream, cudaStreamNonBlocking, greatest ) );
+                for( int q = 0; q < 2 * nq; ++q )
+                    SB_CUDA_CHECK( cudaEventCreateWithFlags( &plan->ev_q[q], cudaEventDisableTiming ) );
+                SB_CUDA_CHECK( cudaEventCreateWithFlags( &plan->ev_all, cudaEventDisableTiming ) );
+            }
+        }
+        if( world > 1 && !plan->pencil && plan->fast_a.on && plan->fast_b.on && !env_flag_off( "SPIRIT_B200_DDI_PIPELINE" ) )
         {
             int least = 0, greatest = 0;
             SB_CUDA_CHECK( cudaDeviceGetStreamPriorityRange( &least, &greatest ) );
@@ -2057,11 +2198,39 @@ DDIPlan * ddi_plan_create( const Hamiltonian & ham, const StencilParams & sp, cu
     }
 
     const std::size_t half       = std::size_t( d.Pc ) * d.Pb * d.Ha; // full half-spectrum of one tensor component
-    const std::size_t half_local = std::size_t( d.Pc ) * kbl * d.Ha;  // the local kb range of it
+    if( !plan->pencil )
+        Ha_loc = d.Ha;
+    const std::size_t half_local = std::size_t( d.Pc ) * kbl * Ha_loc; // the local kb range (ka pencils: the local ka block) of it
     const std::size_t full       = std::size_t( d.Pc ) * d.Pb * d.Pa;
     const std::size_t n_B        = std::size_t( nq ) * ncl * d.Pb * d.Ha;
     SB_CUDA_CHECK( cudaMalloc( &plan->Dhat, std::size_t( 6 * d.n_inter ) * half_local * sizeof( double2 ) ) );
-    SB_CUDA_CHECK( cudaMalloc( &plan->A, std::size_t( nq ) * ncl * d.Nb * d.Ha * sizeof( double2 ) ) );
+    if( plan->pencil )
+    {
+        // b- and c-pass operands of the local ka block; AT is written (forward a-pass) and read (inverse a-pass) by every rank
+        SB_CUDA_CHECK( cudaStreamSynchronize( stream ) );
+        SB_CUDA_CHECK( cudaMalloc( &plan->AT, std::size_t( nq ) * Nc_global * d.Nb * Ha_loc * sizeof( double2 ) ) );
+        SB_CUDA_CHECK( cudaMalloc( &plan->BT, std::size_t( nq ) * Nc_global * d.Pb * Ha_loc * sizeof( double2 ) ) );
+        SB_CUDA_CHECK( cudaMalloc( &plan->flags, std::size_t( world ) * sizeof( unsigned ) ) );
+        SB_CUDA_CHECK( cudaMemset( plan->flags, 0, std::size_t( world ) * sizeof( unsigned ) ) );
+        const bool m0 = peer_map_all( plan->AT, plan->AT_peer, plan->peer_opened, stream );
+        const bool m1 = peer_map_all( plan->flags, plan->flags_peer, plan->peer_opened, stream );
+        if( !m0 || !m1 )
+            throw std::runtime_error( "spirit_b200: the distributed dipolar convolution could not map its operands into the peers' address "
+                                      "spaces (CUDA IPC); SPIRIT_B200_DDI_PENCIL=0 selects the decomposition with an NCCL fallback" );
+        for( int r = 0; r < world; ++r )
+            plan->push.base[r] = static_cast<double2 *>( plan->AT_peer[r] );
+        // (collective calls: every rank takes the same branch, the choice comes from the environment of the job)
+        if( plan->pencil_dma )
+        {
+            const std::size_t n_A = std::size_t( nq ) * ncl * d.Nb * d.Ha;
+            SB_CUDA_CHECK( cudaMalloc( &plan->A, n_A * sizeof( double2 ) ) );
+            SB_CUDA_CHECK( cudaMalloc( &plan->A_recv, n_A * sizeof( double2 ) ) );
+            if( !peer_map_all( plan->A_recv, plan->A_recv_peer, plan->peer_opened, stream ) )
+                throw std::runtime_error( "spirit_b200: the distributed dipolar convolution could not map its operands into the peers' address spaces" );
+        }
+    }
+    else
+        SB_CUDA_CHECK( cudaMalloc( &plan->A, std::size_t( nq ) * ncl * d.Nb * d.Ha * sizeof( double2 ) ) );
     if( world > 1 && world <= DDI_MAX_PEERS && plan->fast_a.on && plan->fast_b.on && plan->lg_split != 31 )
     {
         // peer-mapped operands (collective; the same outcome on every rank)
@@ -2089,7 +2258,7 @@ DDIPlan * ddi_plan_create( const Hamiltonian & ham, const StencilParams & sp, cu
             }
         }
     }
-    if( !plan->peer )
+    if( !plan->peer && !plan->pencil )
     {
         SB_CUDA_CHECK( cudaMalloc( &plan->B, n_B * sizeof( double2 ) ) );
         if( world > 1 )
@@ -2144,7 +2313,12 @@ DDIPlan * ddi_plan_create( const Hamiltonian & ham, const StencilParams & sp, cu
                 const std::size_t smem_c1 = std::size_t( d.Pc ) * 2 * sizeof( double2 ) * pc.ncol;
                 allow_smem( k_fft_pass<false>, std::max( plan->smem_b, smem_c1 ) );
                 k_fft_pass<false><<<dim3( ( pc.n_u + pc.ncol - 1 ) / pc.ncol, 1 ), fft_threads( std::max( 1, d.Pc / 4 ) * pc.ncol ), smem_c1, stream>>>( plan->plan[2], pc );
-                // keep the local kb range: [kc][kb in range][ka]
+                // keep the local kb range: [kc][kb in range][ka]   (ka pencils: [kc][kb][ka in block])
+                if( plan->pencil )
+                    SB_CUDA_CHECK( cudaMemcpy2DAsync(
+                        Dout, std::size_t( Ha_loc ) * sizeof( double2 ), tmp1 + ka0, std::size_t( d.Ha ) * sizeof( double2 ),
+                        std::size_t( Ha_loc ) * sizeof( double2 ), std::size_t( d.Pc ) * d.Pb, cudaMemcpyDeviceToDevice, stream ) );
+                else
                 SB_CUDA_CHECK( cudaMemcpy2DAsync(
                     Dout, std::size_t( kbl ) * d.Ha * sizeof( double2 ), tmp1 + std::size_t( rank ) * kbl * d.Ha,
                     std::size_t( d.Pb ) * d.Ha * sizeof( double2 ), std::size_t( kbl ) * d.Ha * sizeof( double2 ), d.Pc,
@@ -2226,7 +2400,7 @@ DDIPlan * ddi_plan_create( const Hamiltonian & ham, const StencilParams & sp, cu
             int mirror = 0;
             if( dev_c <= 1e-12 * max_abs )
                 mirror |= 1;
-            if( world == 1 && dev_b <= 1e-12 * max_abs )
+            if( ( world == 1 || plan->pencil ) && dev_b <= 1e-12 * max_abs ) // (needs the whole kb axis on this rank)
                 mirror |= 2;
             if( std::getenv( "SPIRIT_B200_DDI_VERBOSE" ) )
                 std::fprintf( stderr, "spirit_b200 ddi: mirror deviations c %.3e b %.3e -> mirror %d\n", dev_c, dev_b, mirror );
@@ -2246,7 +2420,7 @@ DDIPlan * ddi_plan_create( const Hamiltonian & ham, const StencilParams & sp, cu
     {
         // re-order the spectrum into the tiles k_ddi_c_mult16 reads (one sublattice: 6 components)
         const int lg            = plan->fast_c.lg;
-        const std::size_t tiles = std::size_t( ( d.Ha + ( 1 << lg ) - 1 ) >> lg );
+        const std::size_t tiles = std::size_t( ( dc.Ha + ( 1 << lg ) - 1 ) >> lg );
         const std::size_t n_t   = std::size_t( mirror_len( kbl, dc.mirror & 2 ) ) * tiles * 6 * ( std::size_t( mirror_len( d.Pc, dc.mirror & 1 ) ) << lg );
         plan->Dt_real           = spectrum_real;
         const std::size_t bytes = n_t * ( spectrum_real ? sizeof( double ) : sizeof( double2 ) );
@@ -2273,18 +2447,19 @@ void run_fwd_a16( DDIPlan & plan, ConstField3 spins, int q0, int nq, cudaStream_
     const DDIDims & d = plan.dims;
     const int n_rg    = ( d.Nb * d.Nc + ( 1 << plan.fast_a.lg ) - 1 ) >> plan.fast_a.lg;
     if( plan.a_pipe )
-        launch_fwd_a16p( plan.fast_a, plan.apipe, n_rg, nq, stream, plan.plan_ah, plan.plan[0].twiddle, d, spins, plan.A, q0 );
+        launch_fwd_a16p( plan.fast_a, plan.apipe, n_rg, nq, stream, plan.plan_ah, plan.plan[0].twiddle, d, spins, plan.A, q0, plan.push );
     else
-        launch_fwd_a16( plan.fast_a, dim3( n_rg, nq ), stream, plan.plan_ah, plan.plan[0].twiddle, d, spins, plan.A, q0 );
+        launch_fwd_a16( plan.fast_a, dim3( n_rg, nq ), stream, plan.plan_ah, plan.plan[0].twiddle, d, spins, plan.A, q0, false, plan.push );
 }
 void run_inv_a16( DDIPlan & plan, Field3 g_ddi, double inv_P, int q0, int nq, cudaStream_t stream )
 {
-    const DDIDims & d = plan.dims;
+    const DDIDims & d   = plan.dims;
+    const double2 * src = plan.A_recv ? plan.A_recv : plan.A;
     const int n_rg    = ( d.Nb * d.Nc + ( 1 << plan.fast_a.lg ) - 1 ) >> plan.fast_a.lg;
     if( plan.a_pipe )
-        launch_inv_a16p( plan.fast_a, plan.apipe, n_rg, nq, stream, plan.plan_ah, plan.plan[0].twiddle, d, plan.A, g_ddi, inv_P, q0 );
+        launch_inv_a16p( plan.fast_a, plan.apipe, n_rg, nq, stream, plan.plan_ah, plan.plan[0].twiddle, d, src, g_ddi, inv_P, q0, plan.push );
     else
-        launch_inv_a16( plan.fast_a, dim3( n_rg, nq ), stream, plan.plan_ah, plan.plan[0].twiddle, d, plan.A, g_ddi, inv_P, q0 );
+        launch_inv_a16( plan.fast_a, dim3( n_rg, nq ), stream, plan.plan_ah, plan.plan[0].twiddle, d, src, g_ddi, inv_P, q0, false, plan.push );
 }
 // step 3 (c-transforms + tensor multiply) on the operand in per-rank block layout
 void launch_c_mult( DDIPlan & plan, double2 * operand, cudaStream_t stream )
@@ -2296,7 +2471,7 @@ void launch_c_mult( DDIPlan & plan, double2 * operand, cudaStream_t stream )
     const bool small_c = d.NB == 1 && ( dc.Pc & ( dc.Pc - 1 ) ) == 0 && dc.Pc <= 32;
     if( small_c )
     {
-        const dim3 grid( ( d.Ha + 127 ) / 128, kbl );
+        const dim3 grid( ( dc.Ha + 127 ) / 128, kbl );
         const void * D = plan.Dhat_real ? static_cast<const void *>( plan.Dhat_real ) : static_cast<const void *>( plan.Dhat );
 #define SB_DDI_SMALL( PC )                                                                                             \
     case PC:                                                                                                           \
@@ -2318,7 +2493,7 @@ void launch_c_mult( DDIPlan & plan, double2 * operand, cudaStream_t stream )
     }
     else if( plan.fast_c.on )
     {
-        const dim3 grid( ( d.Ha + ( 1 << plan.fast_c.lg ) - 1 ) >> plan.fast_c.lg, kbl );
+        const dim3 grid( ( dc.Ha + ( 1 << plan.fast_c.lg ) - 1 ) >> plan.fast_c.lg, kbl );
         if( plan.Dt_real )
             launch_c_mult16<true>( plan.fast_c, grid, stream, plan.plan[2], dc, operand, plan.Dt );
         else
@@ -2328,7 +2503,7 @@ void launch_c_mult( DDIPlan & plan, double2 * operand, cudaStream_t stream )
     {
         if( !plan.Dhat )
             throw std::logic_error( "spirit_b200: real tensor spectrum with the shared-memory multiply kernel" );
-        k_ddi_c_mult<<<dim3( ( d.Ha + plan.ncol_c - 1 ) / plan.ncol_c, kbl ), fft_threads( std::max( 1, dc.Pc / 4 ) * plan.ncol_c * nq ), plan.smem_c, stream>>>(
+        k_ddi_c_mult<<<dim3( ( dc.Ha + plan.ncol_c - 1 ) / plan.ncol_c, kbl ), fft_threads( std::max( 1, dc.Pc / 4 ) * plan.ncol_c * nq ), plan.smem_c, stream>>>(
             plan.plan[2], dc, operand, plan.Dhat, plan.ncol_c );
     }
 }
@@ -2396,6 +2571,231 @@ int ddi_gradient_peer( DDIPlan & plan, ConstField3 spins, Field3 g_ddi, cudaStre
     }
     SB_CUDA_CHECK( cudaGetLastError() );
     return 4 * nq + 1;
+}
+
+// Distributed evaluation with ka PENCILS. Every rank runs the a-passes on its planes and the b- and c-passes on its block of ka,
+// for all planes of the lattice:
+//   1 forward a-pass of the local planes; element ka of a row is stored into the operand AT of the rank that owns ka (peer-mapped
+//     memory, NVLink): the transpose IS the store of the kernel, contiguous runs of a whole ka block per row
+//   -- meeting of all ranks (32-bit counters, stream memory operations) --
+//   2 b-pass, c-pass x tensor x inverse c-pass, inverse b-pass on [3][Nc_global][b][ka block]: the kernels of one device
+//   -- meeting --
+//   3 inverse a-pass of the local planes, its rows gathered from the ranks' AT (loads over NVLink)
+// The transposed data is the a-pass output, where b is not yet zero-padded: half the volume of a transpose of the b-pass output
+// (the kb-block decompositions below). One buffer suffices: a rank only ever touches the rows of its own planes in a peer's AT.
+// SPIRIT_B200_DDI_TIMING=1: CUDA events around the phases of the pencil evaluation, averages printed every 8 evaluations
+// (profiles/: where the time of a distributed evaluation goes; one stream, so the events serialise nothing)
+struct PhaseTimer
+{
+    static constexpr int N = 8;
+    cudaEvent_t ev[N] = {};
+    double sum[N]     = {};
+    int count = 0, on = -1;
+    bool enabled()
+    {
+        if( on < 0 )
+        {
+            on = std::getenv( "SPIRIT_B200_DDI_TIMING" ) ? 1 : 0;
+            if( on )
+                for( auto & e : ev )
+                    cudaEventCreate( &e );
+        }
+        return on == 1;
+    }
+    void mark( int i, cudaStream_t stream )
+    {
+        if( enabled() )
+            cudaEventRecord( ev[i], stream );
+    }
+    void finish( int n_marks, int rank, cudaStream_t stream, const char * const * names )
+    {
+        if( !enabled() )
+            return;
+        cudaStreamSynchronize( stream );
+        for( int i = 1; i < n_marks; ++i )
+        {
+            float ms = 0;
+            cudaEventElapsedTime( &ms, ev[i - 1], ev[i] );
+            sum[i] += ms;
+        }
+        if( ++count % 8 == 0 )
+        {
+            std::fprintf( stderr, "spirit_b200 ddi timing rank %d:", rank );
+            for( int i = 1; i < n_marks; ++i )
+            {
+                std::fprintf( stderr, " %s %.3f", names[i], sum[i] / 8 );
+                sum[i] = 0;
+            }
+            std::fprintf( stderr, " ms\n" );
+        }
+    }
+};
+PhaseTimer g_phase_timer;
+
+int ddi_gradient_pencil( DDIPlan & plan, ConstField3 spins, Field3 g_ddi, cudaStream_t stream )
+{
+    const DDIDims & d  = plan.dims;
+    const DDIDims & dc = plan.dims_c;
+    const int nq = 3, w = dc.Ha, planes = dc.Nc;
+    if( plan.pencil_dma )
+    {
+        // The a-passes stay local; the ka blocks travel as 2-D peer copies on the copy engines (one stream per destination), one
+        // component at a time, under the passes of the other components: no SM takes part in the transposes.
+        cudaStream_t cs     = plan.comm_stream;
+        const int world = plan.world, rank = plan.rank, ncl = d.Nc, kblk = 1 << plan.push.lg_kblock;
+        const int lg_tile_b = plan.fast_b.lg + plan.fast_b.lg_seq;
+        const dim3 grid_b( ( w + ( 1 << lg_tile_b ) - 1 ) >> lg_tile_b, planes );
+        const unsigned base = plan.barrier_count;
+        plan.barrier_count += 2 * nq;
+        const std::size_t at_q = std::size_t( planes ) * d.Nb * w, bt_q = std::size_t( planes ) * d.Pb * w;
+        const std::size_t a_q  = std::size_t( ncl ) * d.Nb * d.Ha, rows = std::size_t( ncl ) * d.Nb, E = sizeof( double2 );
+        auto wait_all = [&]( cudaStream_t st, unsigned value )
+        {
+            for( int r = 0; r < world; ++r )
+                if( r != rank )
+                    peer_wait_geq32( st, plan.flags + r, value );
+        };
+        for( int q = 0; q < nq; ++q )
+        {
+            run_fwd_a16( plan, spins, q, 1, stream ); // -> A[q][c][b][ka]
+            SB_CUDA_CHECK( cudaEventRecord( plan.ev_dma[q], stream ) );
+            for( int r = 0; r < world; ++r )
+            {
+                cudaStream_t st = plan.copy_stream[r];
+                const int wr    = plan.push.w[r];
+                SB_CUDA_CHECK( cudaStreamWaitEvent( st, plan.ev_dma[q], 0 ) );
+                // my planes' rows of component q, columns of rank r's ka block -> AT of rank r
+                double2 * dst = static_cast<double2 *>( plan.AT_peer[r] ) + ( std::size_t( q ) * planes + std::size_t( rank ) * ncl ) * d.Nb * wr;
+                SB_CUDA_CHECK( cudaMemcpy2DAsync(
+                    dst, wr * E, plan.A + q * a_q + std::size_t( r ) * kblk, d.Ha * E, wr * E, rows, cudaMemcpyDeviceToDevice, st ) );
+                if( r != rank )
+                    peer_write32( st, static_cast<unsigned *>( plan.flags_peer[r] ) + rank, base + 1 + q );
+                else
+                    SB_CUDA_CHECK( cudaEventRecord( plan.ev_dma[3 + q], st ) );
+            }
+            SB_CUDA_CHECK( cudaStreamWaitEvent( cs, plan.ev_dma[3 + q], 0 ) );
+            wait_all( cs, base + 1 + q );
+            PassArgs pb{};
+            pb.in = plan.AT + q * at_q, pb.out = plan.BT + q * bt_q;
+            pb.in_os = std::size_t( d.Nb ) * w, pb.out_os = std::size_t( d.Pb ) * w, pb.in_js = pb.out_js = w;
+            pb.n_u = w, pb.n_o = planes, pb.n_in = d.Nb, pb.n_out = d.Pb, pb.ncol = 1 << plan.fast_b.lg, pb.scale = 1.0;
+            launch_pass16<false>( plan.fast_b, grid_b, cs, plan.plan[1], pb, 31, 31 );
+        }
+        launch_c_mult( plan, plan.BT, cs );
+        const double inv_P = 1.0 / ( double( d.Pa ) * d.Pb * d.Pc );
+        for( int q = 0; q < nq; ++q )
+        {
+            PassArgs ib{};
+            ib.in = plan.BT + q * bt_q, ib.out = plan.AT + q * at_q;
+            ib.in_os = std::size_t( d.Pb ) * w, ib.out_os = std::size_t( d.Nb ) * w, ib.in_js = ib.out_js = w;
+            ib.n_u = w, ib.n_o = planes, ib.n_in = d.Pb, ib.n_out = d.Nb, ib.ncol = 1 << plan.fast_b.lg, ib.scale = 1.0;
+            launch_pass16<true>( plan.fast_b, grid_b, cs, plan.plan[1], ib, 31, 31 );
+            SB_CUDA_CHECK( cudaEventRecord( plan.ev_dma[6 + q], cs ) );
+            for( int r = 0; r < world; ++r )
+            {
+                cudaStream_t st = plan.copy_stream[r];
+                SB_CUDA_CHECK( cudaStreamWaitEvent( st, plan.ev_dma[6 + q], 0 ) );
+                // the rows of rank r's planes, my ka block -> the inverse a-pass operand of rank r
+                double2 * dst = static_cast<double2 *>( plan.A_recv_peer[r] ) + q * a_q + std::size_t( rank ) * kblk;
+                const double2 * src = plan.AT + ( std::size_t( q ) * planes + std::size_t( r ) * ncl ) * d.Nb * w;
+                SB_CUDA_CHECK( cudaMemcpy2DAsync( dst, d.Ha * E, src, w * E, w * E, rows, cudaMemcpyDeviceToDevice, st ) );
+                if( r != rank )
+                    peer_write32( st, static_cast<unsigned *>( plan.flags_peer[r] ) + rank, base + 1 + nq + q );
+                else
+                    SB_CUDA_CHECK( cudaEventRecord( plan.ev_dma[9 + q], st ) );
+            }
+            SB_CUDA_CHECK( cudaStreamWaitEvent( stream, plan.ev_dma[9 + q], 0 ) );
+            wait_all( stream, base + 1 + nq + q );
+            run_inv_a16( plan, g_ddi, inv_P, q, 1, stream );
+        }
+        SB_CUDA_CHECK( cudaGetLastError() );
+        return 4 * nq + 1;
+    }
+    if( plan.pencil_overlap && !g_phase_timer.enabled() )
+    {
+        // Per component: a-pass + push on `stream`, everything on the local ka block on the plan's own stream `cs`; a component's
+        // b-pass starts when every rank has pushed that component (one meeting per component and direction), under the a-pass of
+        // the next component; on the way back the pull + inverse a-pass of component q runs under the inverse b-pass of q + 1.
+        cudaStream_t cs     = plan.comm_stream;
+        const int lg_tile_b = plan.fast_b.lg + plan.fast_b.lg_seq;
+        const dim3 grid_b( ( w + ( 1 << lg_tile_b ) - 1 ) >> lg_tile_b, planes );
+        auto signal = [&]( cudaStream_t st, unsigned value )
+        {
+            for( int r = 0; r < plan.world; ++r )
+                if( r != plan.rank )
+                    peer_write32( st, static_cast<unsigned *>( plan.flags_peer[r] ) + plan.rank, value );
+        };
+        auto wait_all = [&]( cudaStream_t st, unsigned value )
+        {
+            for( int r = 0; r < plan.world; ++r )
+                if( r != plan.rank )
+                    peer_wait_geq32( st, plan.flags + r, value );
+        };
+        const unsigned base = plan.barrier_count;
+        plan.barrier_count += 2 * nq;
+        const std::size_t at_q = std::size_t( planes ) * d.Nb * w, bt_q = std::size_t( planes ) * d.Pb * w;
+        for( int q = 0; q < nq; ++q )
+        {
+            run_fwd_a16( plan, spins, q, 1, stream );
+            signal( stream, base + 1 + q );
+            SB_CUDA_CHECK( cudaEventRecord( plan.ev_q[q], stream ) );
+            SB_CUDA_CHECK( cudaStreamWaitEvent( cs, plan.ev_q[q], 0 ) );
+            wait_all( cs, base + 1 + q );
+            PassArgs pb{};
+            pb.in = plan.AT + q * at_q, pb.out = plan.BT + q * bt_q;
+            pb.in_os = std::size_t( d.Nb ) * w, pb.out_os = std::size_t( d.Pb ) * w, pb.in_js = pb.out_js = w;
+            pb.n_u = w, pb.n_o = planes, pb.n_in = d.Nb, pb.n_out = d.Pb, pb.ncol = 1 << plan.fast_b.lg, pb.scale = 1.0;
+            launch_pass16<false>( plan.fast_b, grid_b, cs, plan.plan[1], pb, 31, 31 );
+        }
+        launch_c_mult( plan, plan.BT, cs );
+        const double inv_P = 1.0 / ( double( d.Pa ) * d.Pb * d.Pc );
+        for( int q = 0; q < nq; ++q )
+        {
+            PassArgs ib{};
+            ib.in = plan.BT + q * bt_q, ib.out = plan.AT + q * at_q;
+            ib.in_os = std::size_t( d.Pb ) * w, ib.out_os = std::size_t( d.Nb ) * w, ib.in_js = ib.out_js = w;
+            ib.n_u = w, ib.n_o = planes, ib.n_in = d.Pb, ib.n_out = d.Nb, ib.ncol = 1 << plan.fast_b.lg, ib.scale = 1.0;
+            launch_pass16<true>( plan.fast_b, grid_b, cs, plan.plan[1], ib, 31, 31 );
+            signal( cs, base + 1 + nq + q );
+            SB_CUDA_CHECK( cudaEventRecord( plan.ev_q[nq + q], cs ) );
+            SB_CUDA_CHECK( cudaStreamWaitEvent( stream, plan.ev_q[nq + q], 0 ) );
+            wait_all( stream, base + 1 + nq + q );
+            run_inv_a16( plan, g_ddi, inv_P, q, 1, stream );
+        }
+        SB_CUDA_CHECK( cudaGetLastError() );
+        return 4 * nq + 1;
+    }
+    PhaseTimer & T = g_phase_timer;
+    T.mark( 0, stream );
+    run_fwd_a16( plan, spins, 0, nq, stream );
+    T.mark( 1, stream );
+    ddi_peer_barrier( plan, stream );
+    T.mark( 2, stream );
+    const int lg_tile_b = plan.fast_b.lg + plan.fast_b.lg_seq;
+    const dim3 grid_b( ( w + ( 1 << lg_tile_b ) - 1 ) >> lg_tile_b, nq * planes );
+    PassArgs pb{};
+    pb.in = plan.AT, pb.out = plan.BT;
+    pb.in_os = std::size_t( d.Nb ) * w, pb.out_os = std::size_t( d.Pb ) * w, pb.in_js = pb.out_js = w;
+    pb.n_u = w, pb.n_o = nq * planes, pb.n_in = d.Nb, pb.n_out = d.Pb, pb.ncol = 1 << plan.fast_b.lg, pb.scale = 1.0;
+    launch_pass16<false>( plan.fast_b, grid_b, stream, plan.plan[1], pb, 31, 31 );
+    T.mark( 3, stream );
+    launch_c_mult( plan, plan.BT, stream );
+    T.mark( 4, stream );
+    PassArgs ib{};
+    ib.in = plan.BT, ib.out = plan.AT;
+    ib.in_os = std::size_t( d.Pb ) * w, ib.out_os = std::size_t( d.Nb ) * w, ib.in_js = ib.out_js = w;
+    ib.n_u = w, ib.n_o = nq * planes, ib.n_in = d.Pb, ib.n_out = d.Nb, ib.ncol = 1 << plan.fast_b.lg, ib.scale = 1.0;
+    launch_pass16<true>( plan.fast_b, grid_b, stream, plan.plan[1], ib, 31, 31 );
+    T.mark( 5, stream );
+    ddi_peer_barrier( plan, stream );
+    T.mark( 6, stream );
+    const double inv_P = 1.0 / ( double( d.Pa ) * d.Pb * d.Pc );
+    run_inv_a16( plan, g_ddi, inv_P, 0, nq, stream );
+    T.mark( 7, stream );
+    static const char * const names[8] = { "", "a+push", "wait", "b", "c", "b^-1", "wait", "pull+a^-1" };
+    T.finish( 8, plan.rank, stream, names );
+    SB_CUDA_CHECK( cudaGetLastError() );
+    return 5;
 }
 
 // Distributed evaluation with the transposes hidden: component q travels (NCCL send / recv on the plan's own stream)
@@ -2467,6 +2867,8 @@ int ddi_gradient_pipelined( DDIPlan & plan, ConstField3 spins, Field3 g_ddi, cud
 // One DDI gradient evaluation: spins -> g_ddi field. Returns the number of kernels launched.
 int ddi_gradient( DDIPlan & plan, ConstField3 spins, Field3 g_ddi, cudaStream_t stream )
 {
+    if( plan.pencil )
+        return ddi_gradient_pencil( plan, spins, g_ddi, stream );
     if( plan.peer )
         return ddi_gradient_peer( plan, spins, g_ddi, stream );
     if( plan.comm_stream )

@@ -152,10 +152,52 @@ static __global__ void __launch_bounds__( BLOCK_THREADS ) k_chain_gradient(
         // dipolar field of this image's configuration (computed before this kernel, one convolution per image); unused without
         const ConstField3 dd = cfield( v.Ddi ? v.Ddi : conf, v.stride, img );
         const D3 si          = load3( s, site.idx );
+        if( NB_T == 1 && p.sc6 && !p.sc6_extras && !v.Ddi )
+        {
+            // nearest-neighbour structure (the images of the BASELINE chain): the six neighbours by index arithmetic, pairs +-r
+            // combined (sc6.cuh) instead of the walk over the neighbour table; an open boundary contributes a zero spin
+            const D3 zero = make_d3( 0, 0, 0 );
+            auto neighbour = [&]( int axis, int dir ) -> D3
+            {
+                if( !p.sc6_axis[axis] )
+                    return zero;
+                const int n = axis == 0 ? p.Na : ( axis == 1 ? p.Nb : p.Nc );
+                int q       = ( axis == 0 ? site.a : ( axis == 1 ? site.b : site.c ) ) + dir;
+                if( q < 0 || q >= n )
+                {
+                    if( !p.bc[axis] )
+                        return zero;
+                    q = q < 0 ? q + n : q - n;
+                }
+                return load3( s, axis == 0 ? storage_index( p, q, site.b, site.c )
+                                           : ( axis == 1 ? storage_index( p, site.a, q, site.c ) : storage_index( p, site.a, site.b, q ) ) );
+            };
+            const D3 g0 = make_d3( p.sc6_g0[0], p.sc6_g0[1], p.sc6_g0[2] );
+            D3 g        = g0;
+            sc6_axis_gradient<0, true>( p, neighbour( 0, -1 ), neighbour( 0, 1 ), g );
+            sc6_axis_gradient<1, true>( p, neighbour( 1, -1 ), neighbour( 1, 1 ), g );
+            if( p.sc6_axis[2] )
+                sc6_axis_gradient<2, true>( p, neighbour( 2, -1 ), neighbour( 2, 1 ), g );
+            g.x = fma( p.sc6_A[0], si.x, g.x );
+            g.y = fma( p.sc6_A[1], si.y, g.y );
+            g.z = fma( p.sc6_A[2], si.z, g.z );
+            if( p.sc6_aniso_full )
+            {
+                g.x = fma( p.sc6_A[3], si.y, fma( p.sc6_A[4], si.z, g.x ) );
+                g.y = fma( p.sc6_A[3], si.x, fma( p.sc6_A[5], si.z, g.y ) );
+                g.z = fma( p.sc6_A[4], si.x, fma( p.sc6_A[5], si.y, g.z ) );
+            }
+            store3( field( v.Fg, v.stride, img ), site.idx, make_d3( -g.x, -g.y, -g.z ) );
+            // E = 1/2 (g - g0) . s + g0 . s: the bilinear terms count half, the Zeeman term (g0 = -mu_s B n) whole
+            e = 0.5 * ( ( g.x + g0.x ) * si.x + ( g.y + g0.y ) * si.y + ( g.z + g0.z ) * si.z );
+        }
+        else
+        {
         const SiteGradient g = site_gradient<NB_T>( p, s, dd, site, si );
         const D3 gt          = total( g );
         store3( field( v.Fg, v.stride, img ), site.idx, make_d3( -gt.x, -gt.y, -gt.z ) );
         e = site_energy<NB_T>( p, site, si, g );
+        }
         if( gi > 0 )
         {
             const D3 sp = load3( cfield( conf, v.stride, img - 1 ), site.idx );

@@ -83,7 +83,10 @@ def ddi_distributed(lib, rank, world, tmp):
     failures = []
     # the second lattice has padded lengths 128 x 64 x 64: the power-of-two pass kernels with the per-rank kb blocks
     for Na, Nb, Nc, bc, solver in ((16, 8, 8, "0 0 0", "Depondt"), (16, 8, 8, "1 1 0", "SIB"), (16, 8, 8, "0 0 0", "VP"),
-                                   (64, 32, 32, "0 0 0", "Depondt"), (64, 32, 32, "1 1 0", "SIB")):
+                                   (64, 32, 32, "0 0 0", "Depondt"), (64, 32, 32, "1 1 0", "SIB"),
+                                   # ka pencils (padded a of at least 128, fast kernels): open, c periodic (un-padded c), long a
+                                   (64, 32, 32, "0 0 0", "SIB"), (64, 16, 64, "0 0 1", "Heun"), (256, 16, 16, "0 1 0", "Depondt"),
+                                   (64, 32, 32, "0 0 0", "VP")):
         plane = Na * Nb
         over = dict(boundary_conditions=bc, ddi_method="fft", ddi_n_periodic_images="2 2 0", llg_n_iterations_amortize=3)
         s_global = unit_random(Na * Nb * Nc, 33)
