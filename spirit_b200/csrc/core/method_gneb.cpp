@@ -51,6 +51,26 @@ Method_GNEB::Method_GNEB( std::shared_ptr<Chain> chain_, int solver_, int idx_ch
     max_torque     = P.force_convergence + 1.0;
     max_torque_all = std::vector<double>( chain->noi, 0.0 );
 
+    // The device chain evaluates every image with ONE set of tables (images of a chain are copies of one another). The reference
+    // calls each image's own Hamiltonian and llg dt (Method_GNEB.cpp:99-100, 359-391): a chain whose images differ in what the
+    // tables are built from is refused instead of being computed with image 0's parameters.
+    {
+        const auto & h0 = *chain->images[0]->hamiltonian;
+        for( int i = 1; i < chain->noi; ++i )
+        {
+            const auto & h = *chain->images[i]->hamiltonian;
+            const bool same = h.boundary_conditions == h0.boundary_conditions && h.external_field_magnitude == h0.external_field_magnitude
+                              && h.external_field_normal.x == h0.external_field_normal.x && h.external_field_normal.y == h0.external_field_normal.y
+                              && h.external_field_normal.z == h0.external_field_normal.z && h.anisotropy_magnitudes == h0.anisotropy_magnitudes
+                              && h.cubic_anisotropy_magnitudes == h0.cubic_anisotropy_magnitudes && h.exchange_magnitudes == h0.exchange_magnitudes
+                              && h.dmi_magnitudes == h0.dmi_magnitudes && h.ddi_method == h0.ddi_method
+                              && chain->images[i]->llg_parameters->dt == chain->images[0]->llg_parameters->dt;
+            if( !same )
+                throw std::runtime_error(
+                    "spirit_b200: GNEB over images with different Hamiltonian parameters or llg_dt (image " + std::to_string( i )
+                    + " differs from image 0) is not implemented: the device chain uses one set of interaction tables" );
+        }
+    }
     device_ = std::make_unique<dev::DeviceChain>( *chain->images[0]->geometry, chain->noi, chain->shard_begin, chain->shard_noi_global );
     device_->set_hamiltonian( *chain->images[0]->hamiltonian );
     Sync_Device();

@@ -194,6 +194,7 @@ void File::scan()
 {
     found = is_ovf = false;
     n_segments     = 0;
+    count_pos_     = std::string::npos; // a rescan of a replaced file must not patch the counter at a stale offset
     segments_.clear();
     contents_.clear();
     std::ifstream in( name, std::ios::binary );
