@@ -973,6 +973,342 @@ static __global__ void __launch_bounds__( FFT_THREADS, SB_FFT16_MINB ) k_ddi_c_m
         }
 }
 
+// ---------------------------------------------------------------------------------------------
+// Halves of a stage, for kernels that keep the inputs of a transform's first stage or the outputs of its last stage in
+// registers instead of passing them through shared memory: with the thread mapping of fft_stage_ct (thread tt of a column owns
+// the radix-8 butterfly tt of every stage) the FFT_E elements j = tt + (n / 8) m, m < 8, are
+//   * exactly the inputs of the thread's first-stage butterfly (a = tt + STEP i, STEP = n / 8), and
+//   * exactly the outputs of its last-stage butterflies (o = item + (n / R) i with item = tt + (n / 8) jj: m = jj + (8 / R) i),
+// forward and inverse alike. A pass that loads its column as "element m of thread tt" can therefore start the first butterfly on
+// the loaded registers and store the last butterflies' results straight to their destination: two of the 2 x stages + 2
+// shared-memory round trips and two CTA barriers per transform disappear, and the c-pass, whose inverse transform starts where
+// the forward one ended, can do forward last stage -> tensor multiply -> inverse first stage without leaving the registers.
+// ---------------------------------------------------------------------------------------------
+template<int LOGN, int R, bool FIRST>
+__device__ __forceinline__ void stage_fetch( const double2 * x, const int lg_ncol, const int col, const int tt, double2 ( &v )[FFT_E / R][R] )
+{
+    constexpr int N = 1 << LOGN, PER = FFT_E / R, PER_COL = N >> FFT_LG_E, STEP = N / R;
+#pragma unroll
+    for( int jj = 0; jj < PER; ++jj )
+#pragma unroll
+        for( int i = 0; i < R; ++i )
+        {
+            const int a   = tt + PER_COL * jj + STEP * i;
+            const int idx = FIRST ? a : a + ( a >> 4 );
+            v[jj][i]      = x[( idx << lg_ncol ) + col];
+        }
+}
+// twiddles and stores of a stage whose butterflies (dft_small) have been done in v. No barrier: the caller orders it after
+// the reads of the same buffer.
+template<bool INVERSE, int LOGN, int R, int LG_S, bool LAST>
+__device__ __forceinline__ void stage_emit(
+    const double2 * __restrict__ twiddle, double2 * x, const int lg_ncol, const int col, const int tt, const double2 ( &v )[FFT_E / R][R] )
+{
+    constexpr int N = 1 << LOGN, PER = FFT_E / R, PER_COL = N >> FFT_LG_E, S = 1 << LG_S;
+    constexpr bool CHAIN = LOGN >= SB_FFT_TW_CHAIN_LOGN;
+#pragma unroll
+    for( int jj = 0; jj < PER; ++jj )
+    {
+        const int item = tt + PER_COL * jj;
+        const int q = item & ( S - 1 ), p = item >> LG_S;
+        double2 w1 = make_double2( 1.0, 0.0 ), wc = make_double2( 1.0, 0.0 );
+        if( !LAST && CHAIN )
+        {
+            w1 = __ldg( twiddle + ( p << LG_S ) );
+            if( INVERSE )
+                w1.y = -w1.y;
+        }
+#pragma unroll
+        for( int i = 0; i < R; ++i )
+        {
+            double2 val = v[jj][i];
+            if( !LAST && i > 0 )
+            {
+                if( CHAIN )
+                    wc = i == 1 ? w1 : cmul( wc, w1 );
+                else
+                {
+                    const double2 w = __ldg( twiddle + ( ( i * p ) << LG_S ) );
+                    wc              = INVERSE ? make_double2( w.x, -w.y ) : w;
+                }
+                val = cmul( val, wc );
+            }
+            const int o   = q + S * ( R * p + i );
+            const int idx = LAST ? o : o + ( o >> 4 );
+            x[( idx << lg_ncol ) + col] = val;
+        }
+    }
+}
+// the radix-8 stages LG_S, LG_S + 3, ... that are neither the first nor the last of the transform
+template<bool INVERSE, int LOGN, int LG_S, int LG_S_LAST>
+__device__ __forceinline__ void middle_stages_ct( const double2 * __restrict__ twiddle, double2 * x, const int lg_ncol, const int col, const int tt )
+{
+    if constexpr( LG_S < LG_S_LAST )
+    {
+        fft_stage_ct<INVERSE, LOGN, FFT_E, LG_S, false, false>( twiddle, x, lg_ncol, col, tt );
+        middle_stages_ct<INVERSE, LOGN, LG_S + FFT_LG_E, LG_S_LAST>( twiddle, x, lg_ncol, col, tt );
+    }
+}
+// radix and first stride exponent of the last stage of block_fft_ct's plan
+template<int LOGN>
+struct LastStage
+{
+    static constexpr int REM = LOGN % FFT_LG_E, LG_R = REM ? REM : FFT_LG_E, R = 1 << LG_R, LG_S = LOGN - LG_R, PER = FFT_E / R;
+};
+
+// CTA shape the register-resident c-pass is compiled for, per length (measured, profiles/r2ze): up to 512 elements two columns
+// per CTA are 128 threads, three CTAs per SM leave 168 registers (the 24 complex values fit without spills; a 128-register cap
+// spills 250-300 bytes per thread); 1024 elements need 256 threads for two columns (one column per CTA moves half sectors:
+// 512^3 c-pass 26 -> 32 ms), two CTAs per SM, 128 registers with those spills; longer columns: one column per CTA.
+#ifndef SB_CF_MINB
+#define SB_CF_MINB 3
+#endif
+template<int LOGN>
+struct CFBounds
+{
+    static constexpr int T    = LOGN <= 9 ? 128 : ( LOGN <= 11 ? 256 : 512 );
+    static constexpr int MINB = LOGN <= 9 ? SB_CF_MINB : ( LOGN <= 11 ? 2 : 1 );
+};
+inline int cf_threads( int n )
+{
+    return n <= 512 ? 128 : ( n <= 2048 ? 256 : 512 );
+}
+
+// k_fft_pass16 with the register-resident first / last stages: a thread loads the elements j0 + kk jstep, kk < 8 NSEQ, of its
+// column (jstep = n / (8 NSEQ)), which are the inputs of the first-stage butterflies tt_b = j0 + b jstep, b < NSEQ (kk = NSEQ i + b),
+// of that column's group; the last stage stores its results from the registers, one group after the other.
+template<bool INVERSE, int LOGN, int LG_SEQ>
+static __global__ void __launch_bounds__( FFT_THREADS, SB_FFT16_MINB ) k_fft_pass16r(
+    const __grid_constant__ FFTPlan1D plan, const __grid_constant__ PassArgs a, const int lg_ncol, const int lg_in_split,
+    const int lg_out_split )
+{
+    extern __shared__ double2 smem[];
+    if constexpr( FFT_E != 8 )
+        return;
+    using L            = LastStage<LOGN>;
+    constexpr int NSEQ = 1 << LG_SEQ, PER_COL = ( 1 << LOGN ) >> FFT_LG_E;
+    const int lg_tile  = lg_ncol + LG_SEQ;
+    const int bufp     = ( ( 1 << LOGN ) << lg_ncol ) + ( ( ( 1 << LOGN ) << lg_ncol ) >> 4 ) + 1;
+    const int o = blockIdx.y, u0 = blockIdx.x << lg_tile;
+    {
+        const int ctile = threadIdx.x & ( ( 1 << lg_tile ) - 1 ), j0 = threadIdx.x >> lg_tile, jstep = blockDim.x >> lg_tile;
+        double2 * mine  = smem + ( ctile >> lg_ncol ) * bufp;
+        const bool valid   = u0 + ctile < a.n_u;
+        const double2 * in = a.in + std::size_t( o ) * a.in_os + u0 + ctile;
+        double2 v[NSEQ][1][FFT_E];
+#pragma unroll
+        for( int i = 0; i < FFT_E; ++i )
+#pragma unroll
+            for( int b = 0; b < NSEQ; ++b )
+            {
+                const int j = j0 + ( NSEQ * i + b ) * jstep;
+                v[b][0][i]  = make_double2( 0.0, 0.0 );
+                if( valid && j < a.n_in )
+                {
+                    if( a.use_in_peer )
+                        v[b][0][i] = a.in_peer[j >> lg_in_split]
+                                              [std::size_t( o ) * a.in_os + u0 + ctile + std::size_t( unsigned( j ) & ( ( 1u << lg_in_split ) - 1u ) ) * a.in_js];
+                    else
+                        v[b][0][i] = in[pass_offset16( j, a.in_js, lg_in_split, a.in_split_stride )];
+                }
+            }
+#pragma unroll
+        for( int b = 0; b < NSEQ; ++b )
+        {
+            dft_small<INVERSE, FFT_E>( v[b][0] );
+            stage_emit<INVERSE, LOGN, FFT_E, 0, false>( plan.twiddle, mine, lg_ncol, ctile & ( ( 1 << lg_ncol ) - 1 ), j0 + b * jstep, v[b] );
+        }
+    }
+    __syncthreads();
+    const int col = int( threadIdx.x ) & ( ( 1 << lg_ncol ) - 1 ), tt = int( threadIdx.x ) >> lg_ncol;
+#pragma unroll 1
+    for( int g = 0; g < NSEQ; ++g )
+        middle_stages_ct<INVERSE, LOGN, FFT_LG_E, L::LG_S>( plan.twiddle, smem + g * bufp, lg_ncol, col, tt );
+#pragma unroll 1
+    for( int g = 0; g < NSEQ; ++g )
+    {
+        double2 v[L::PER][L::R];
+        stage_fetch<LOGN, L::R, false>( smem + g * bufp, lg_ncol, col, tt, v );
+#pragma unroll
+        for( int jj = 0; jj < L::PER; ++jj )
+            dft_small<INVERSE, L::R>( v[jj] );
+        const int ctile = ( g << lg_ncol ) + col;
+        if( u0 + ctile < a.n_u )
+        {
+            double2 * out = a.out + std::size_t( o ) * a.out_os + u0 + ctile;
+            if( a.opeer_planes )
+            {
+                const int q = o / a.opeer_planes, c = o - q * a.opeer_planes, r = c / a.opeer_ncl;
+                out         = a.out_peer[r] + std::size_t( q * a.opeer_ncl + ( c - r * a.opeer_ncl ) ) * a.out_os + u0 + ctile;
+            }
+#pragma unroll
+            for( int jj = 0; jj < L::PER; ++jj )
+#pragma unroll
+                for( int i = 0; i < L::R; ++i )
+                {
+                    const int j = tt + ( jj + L::PER * i ) * PER_COL;
+                    if( j < a.n_out )
+                    {
+                        const double2 w = make_double2( a.scale * v[jj][i].x, a.scale * v[jj][i].y );
+                        if( a.use_out_peer )
+                            a.out_peer[j >> lg_out_split]
+                                      [std::size_t( o ) * a.out_os + u0 + ctile + std::size_t( unsigned( j ) & ( ( 1u << lg_out_split ) - 1u ) ) * a.out_js]
+                                = w;
+                        else
+                            out[pass_offset16( j, a.out_js, lg_out_split, a.out_split_stride )] = w;
+                    }
+                }
+        }
+    }
+}
+
+// k_ddi_c_mult16 with the register-resident first / last stages described above: the first forward stage works on the loaded
+// column, the last forward stage, the tensor multiply and the first inverse stage of the three components stay in registers
+// (24 complex values per thread), the last inverse stage stores to global memory. Same launch shape, same tensor layout,
+// the same arithmetic per butterfly (only where its operands wait differs).
+template<bool REAL_D, int LOGN>
+static __global__ void __launch_bounds__( CFBounds<LOGN>::T, CFBounds<LOGN>::MINB ) k_ddi_c_mult16f(
+        const __grid_constant__ FFTPlan1D plan, const __grid_constant__ DDIDims d, double2 * __restrict__ B, const void * __restrict__ Dt_v,
+        const int lg_ncol )
+{
+    extern __shared__ double2 smem[];
+    if constexpr( FFT_E != 8 ) // (tuning builds with other radices keep k_ddi_c_mult16)
+        return;
+    using L               = LastStage<LOGN>;
+    constexpr int n       = 1 << LOGN, PER_COL = n >> FFT_LG_E;
+    const int ncol        = 1 << lg_ncol;
+    const int tile_elems  = n << lg_ncol;
+    const int bufp        = tile_elems + ( tile_elems >> 4 ) + 1;
+    const int kb = blockIdx.y, u0 = blockIdx.x << lg_ncol;
+    const int col = threadIdx.x & ( ncol - 1 ), tt = threadIdx.x >> lg_ncol; // blockDim.x = PER_COL << lg_ncol
+    const bool valid        = u0 + col < d.Ha;
+    const std::size_t plane = std::size_t( d.Pb ) * d.Ha;
+    double2 * column        = B + std::size_t( kb ) * d.Ha + u0 + col;
+    const bool mir_c = REAL_D && ( d.mirror & 1 ), mir_b = REAL_D && ( d.mirror & 2 ) && 2 * kb > d.Pb;
+    const int kbr    = mir_b ? d.Pb - kb : kb;
+    const double sgb = mir_b ? -1.0 : 1.0;
+    const int tile_d = mirror_len( n, mir_c ) << lg_ncol;
+    const std::size_t block = ( std::size_t( kbr ) * gridDim.x + blockIdx.x ) * 6 * std::size_t( tile_d );
+    {
+        const std::size_t elem  = REAL_D ? sizeof( double ) : sizeof( double2 );
+        const std::size_t bytes = 6 * std::size_t( tile_d ) * elem;
+        const char * Dblock     = static_cast<const char *>( Dt_v ) + block * elem;
+        for( std::size_t off = std::size_t( threadIdx.x ) * 128; off < bytes; off += std::size_t( blockDim.x ) * 128 )
+            asm volatile( "prefetch.global.L2 [%0];" ::"l"( Dblock + off ) );
+    }
+    auto off_c = [&]( int m ) -> std::size_t
+    {
+        const int c = tt + m * PER_COL;
+        if( d.block_stride == 0 )
+            return std::size_t( c ) * plane;
+        const int blk = c / d.c_block;
+        return std::size_t( blk ) * d.block_stride + std::size_t( c - blk * d.c_block ) * plane;
+    };
+    // forward, first stage: straight from global memory (planes c >= Nc are zero)
+#pragma unroll 1
+    for( int q = 0; q < 3; ++q )
+    {
+        const double2 * column_q = column + std::size_t( q ) * d.q_stride;
+        double2 v[1][FFT_E];
+#pragma unroll
+        for( int m = 0; m < FFT_E; ++m )
+        {
+            v[0][m] = make_double2( 0.0, 0.0 );
+            if( valid && tt + m * PER_COL < d.Nc )
+                v[0][m] = column_q[off_c( m )];
+        }
+        dft_small<false, FFT_E>( v[0] );
+        stage_emit<false, LOGN, FFT_E, 0, false>( plan.twiddle, smem + q * bufp, lg_ncol, col, tt, v );
+    }
+    __syncthreads();
+#pragma unroll 1
+    for( int q = 0; q < 3; ++q )
+        middle_stages_ct<false, LOGN, FFT_LG_E, L::LG_S>( plan.twiddle, smem + q * bufp, lg_ncol, col, tt );
+    // the tensor at the thread's point m of the column: kc = tt + m n / 8
+    auto multiply = [&]( const int m, double2 & sx, double2 & sy, double2 & sz )
+    {
+        const int kc = tt + m * PER_COL;
+        if( REAL_D )
+        {
+            const bool up     = mir_c && 2 * kc > n;
+            const int item_d  = ( ( up ? n - kc : kc ) << lg_ncol ) + col;
+            const double sgc  = up ? -1.0 : 1.0;
+            const double * Dp = static_cast<const double *>( Dt_v ) + block + item_d;
+            const double Dxx = __ldg( Dp ), Dxy = sgb * __ldg( Dp + tile_d ), Dxz = sgc * __ldg( Dp + 2 * tile_d );
+            const double Dyy = __ldg( Dp + 3 * tile_d ), Dyz = sgb * sgc * __ldg( Dp + 4 * tile_d ), Dzz = __ldg( Dp + 5 * tile_d );
+            const double2 fx = make_double2( Dxx * sx.x + Dxy * sy.x + Dxz * sz.x, Dxx * sx.y + Dxy * sy.y + Dxz * sz.y );
+            const double2 fy = make_double2( Dxy * sx.x + Dyy * sy.x + Dyz * sz.x, Dxy * sx.y + Dyy * sy.y + Dyz * sz.y );
+            const double2 fz = make_double2( Dxz * sx.x + Dyz * sy.x + Dzz * sz.x, Dxz * sx.y + Dyz * sy.y + Dzz * sz.y );
+            sx = fx, sy = fy, sz = fz;
+        }
+        else
+        {
+            const double2 * Dp = static_cast<const double2 *>( Dt_v ) + block + ( kc << lg_ncol ) + col;
+            const double2 Dxx = __ldg( Dp ), Dxy = __ldg( Dp + tile_elems ), Dxz = __ldg( Dp + 2 * tile_elems );
+            const double2 Dyy = __ldg( Dp + 3 * tile_elems ), Dyz = __ldg( Dp + 4 * tile_elems ), Dzz = __ldg( Dp + 5 * tile_elems );
+            const double2 fx = cadd( cmul( Dxx, sx ), cadd( cmul( Dxy, sy ), cmul( Dxz, sz ) ) );
+            const double2 fy = cadd( cmul( Dxy, sx ), cadd( cmul( Dyy, sy ), cmul( Dyz, sz ) ) );
+            const double2 fz = cadd( cmul( Dxz, sx ), cadd( cmul( Dyz, sy ), cmul( Dzz, sz ) ) );
+            sx = fx, sy = fy, sz = fz;
+        }
+    };
+    // forward last stage into registers, multiply, inverse first stage out of them
+    double2 V[3][L::PER][L::R];
+#pragma unroll
+    for( int q = 0; q < 3; ++q )
+    {
+        stage_fetch<LOGN, L::R, false>( smem + q * bufp, lg_ncol, col, tt, V[q] );
+#pragma unroll
+        for( int jj = 0; jj < L::PER; ++jj )
+            dft_small<false, L::R>( V[q][jj] );
+    }
+    __syncthreads(); // every thread has its inputs: the buffers may be overwritten
+#pragma unroll
+    for( int jj = 0; jj < L::PER; ++jj )
+#pragma unroll
+        for( int i = 0; i < L::R; ++i )
+            multiply( jj + L::PER * i, V[0][jj][i], V[1][jj][i], V[2][jj][i] );
+#pragma unroll
+    for( int q = 0; q < 3; ++q )
+    {
+        double2 w[1][FFT_E];
+#pragma unroll
+        for( int jj = 0; jj < L::PER; ++jj )
+#pragma unroll
+            for( int i = 0; i < L::R; ++i )
+                w[0][jj + L::PER * i] = V[q][jj][i];
+        dft_small<true, FFT_E>( w[0] );
+        stage_emit<true, LOGN, FFT_E, 0, false>( plan.twiddle, smem + q * bufp, lg_ncol, col, tt, w );
+    }
+    __syncthreads();
+#pragma unroll 1
+    for( int q = 0; q < 3; ++q )
+        middle_stages_ct<true, LOGN, FFT_LG_E, L::LG_S>( plan.twiddle, smem + q * bufp, lg_ncol, col, tt );
+    // inverse, last stage: results straight to global memory, planes c < Nc only
+#pragma unroll 1
+    for( int q = 0; q < 3; ++q )
+    {
+        double2 * column_q = column + std::size_t( q ) * d.q_stride;
+        double2 v[L::PER][L::R];
+        stage_fetch<LOGN, L::R, false>( smem + q * bufp, lg_ncol, col, tt, v );
+#pragma unroll
+        for( int jj = 0; jj < L::PER; ++jj )
+            dft_small<true, L::R>( v[jj] );
+        if( valid )
+        {
+#pragma unroll
+            for( int jj = 0; jj < L::PER; ++jj )
+#pragma unroll
+                for( int i = 0; i < L::R; ++i )
+                {
+                    const int m = jj + L::PER * i;
+                    if( tt + m * PER_COL < d.Nc )
+                        column_q[off_c( m )] = v[jj][i];
+                }
+        }
+    }
+}
+
 // D^[comp6][kc][kb][ka] -> D^t[kb][ka tile][comp6][kc][col] (setup). Columns past Ha in the last tile stay zero.
 template<bool REAL_D>
 static __global__ void k_ddi_tile_tensor( const __grid_constant__ DDIDims d, const double2 * __restrict__ Dhat, void * __restrict__ Dt_v, const int lg_ncol )
@@ -1774,16 +2110,31 @@ void launch_pass16(
         }
         return;
     }
+    // register-resident first / last stages (k_fft_pass16r; SPIRIT_B200_FFT_PASS_REG=0 / 1 forces): measured faster with one
+    // column group per CTA (256^3, length 512: 0.83 -> 0.61 ms), slower with two (length 4096: film iteration 5.5 -> 6.1 ms, the
+    // groups' halves of a sector are stored microseconds apart) -- profiles/r2ze_sweep.txt
+    const char * reg_env = std::getenv( "SPIRIT_B200_FFT_PASS_REG" );
+    const bool reg       = FFT_E == 8 && ( reg_env ? reg_env[0] != '0' : !f.lg_seq );
     switch( ilog2( plan.n ) )
     {
 #define C( L )                                                                                                         \
     case L:                                                                                                            \
         if( configure && f.lg_seq )                                                                                    \
+        {                                                                                                              \
             allow_smem( k_fft_pass16<INVERSE, L, 1>, f.smem );                                                         \
+            allow_smem( k_fft_pass16r<INVERSE, L, 1>, f.smem );                                                        \
+        }                                                                                                              \
         else if( configure )                                                                                           \
+        {                                                                                                              \
             allow_smem( k_fft_pass16<INVERSE, L, 0>, f.smem );                                                         \
+            allow_smem( k_fft_pass16r<INVERSE, L, 0>, f.smem );                                                        \
+        }                                                                                                              \
+        else if( f.lg_seq && reg )                                                                                     \
+            k_fft_pass16r<INVERSE, L, 1><<<grid, f.threads, f.smem, stream>>>( plan, a, f.lg, lg_in, lg_out );         \
         else if( f.lg_seq )                                                                                            \
             k_fft_pass16<INVERSE, L, 1><<<grid, f.threads, f.smem, stream>>>( plan, a, f.lg, lg_in, lg_out );          \
+        else if( reg )                                                                                                 \
+            k_fft_pass16r<INVERSE, L, 0><<<grid, f.threads, f.smem, stream>>>( plan, a, f.lg, lg_in, lg_out );         \
         else                                                                                                           \
             k_fft_pass16<INVERSE, L, 0><<<grid, f.threads, f.smem, stream>>>( plan, a, f.lg, lg_in, lg_out );          \
         break;
@@ -1828,12 +2179,20 @@ void launch_c_mult16(
     const DDIPlan::Fast & f, dim3 grid, cudaStream_t stream, const FFTPlan1D & plan, const DDIDims & dc, double2 * operand, const void * Dt,
     bool configure = false )
 {
+    // register-resident first / last stages (k_ddi_c_mult16f) unless SPIRIT_B200_DDI_C_FUSED=0 or the CTA is larger than the
+    // kernel was compiled for
+    const bool fused = FFT_E == 8 && !env_flag_off( "SPIRIT_B200_DDI_C_FUSED" ) && f.threads <= cf_threads( plan.n );
     switch( ilog2( plan.n ) )
     {
 #define C( L )                                                                                                         \
     case L:                                                                                                            \
         if( configure )                                                                                                \
+        {                                                                                                              \
             allow_smem( k_ddi_c_mult16<REAL_D, L>, f.smem );                                                           \
+            allow_smem( k_ddi_c_mult16f<REAL_D, L>, f.smem );                                                          \
+        }                                                                                                              \
+        else if( fused )                                                                                               \
+            k_ddi_c_mult16f<REAL_D, L><<<grid, f.threads, f.smem, stream>>>( plan, dc, operand, Dt, f.lg );            \
         else                                                                                                           \
             k_ddi_c_mult16<REAL_D, L><<<grid, f.threads, f.smem, stream>>>( plan, dc, operand, Dt, f.lg );             \
         break;
@@ -2076,7 +2435,8 @@ DDIPlan * ddi_plan_create( const Hamiltonian & ham, const StencilParams & sp, cu
                 plan->lg_split = 31 - __builtin_clz( unsigned( kbl ) );
         }
         if( allow && plan->plan[2].fast16 && d.NB == 1 )
-            shape( plan->fast_c, d.Pc, 3, "SPIRIT_B200_FFT_LG_C" );
+            shape( plan->fast_c, d.Pc, 3, "SPIRIT_B200_FFT_LG_C", // the register-resident kernel: CTAs of cf_threads( Pc )
+                   FFT_E == 8 && !env_flag_off( "SPIRIT_B200_DDI_C_FUSED" ) ? 8 * cf_threads( d.Pc ) : 2048 );
         if( allow && d.Pa % 2 == 0 && d.Pa >= 128 && ( d.Pa & ( d.Pa - 1 ) ) == 0 && !env_flag_off( "SPIRIT_B200_FFT16" ) )
         {
             make_plan_1d( plan->plan_ah, plan->twiddle_ah, d.Pa / 2 );
