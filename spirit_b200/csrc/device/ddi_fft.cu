@@ -1124,40 +1124,47 @@ static __global__ void __launch_bounds__( FFT_THREADS, SB_FFT16_MINB ) k_fft_pas
 #pragma unroll 1
     for( int g = 0; g < NSEQ; ++g )
         middle_stages_ct<INVERSE, LOGN, FFT_LG_E, L::LG_S>( plan.twiddle, smem + g * bufp, lg_ncol, col, tt );
-#pragma unroll 1
-    for( int g = 0; g < NSEQ; ++g )
+    // last stage with the thread mapping of the load phase (butterflies tt_b of the thread's own column): a warp's store
+    // instruction covers whole rows of the tile, (ncol << LG_SEQ) x 16 contiguous bytes
     {
-        double2 v[L::PER][L::R];
-        stage_fetch<LOGN, L::R, false>( smem + g * bufp, lg_ncol, col, tt, v );
-#pragma unroll
-        for( int jj = 0; jj < L::PER; ++jj )
-            dft_small<INVERSE, L::R>( v[jj] );
-        const int ctile = ( g << lg_ncol ) + col;
-        if( u0 + ctile < a.n_u )
+        const int ctile = threadIdx.x & ( ( 1 << lg_tile ) - 1 ), j0 = threadIdx.x >> lg_tile, jstep = blockDim.x >> lg_tile;
+        const double2 * mine = smem + ( ctile >> lg_ncol ) * bufp;
+        const bool valid     = u0 + ctile < a.n_u;
+        double2 * out        = a.out + std::size_t( o ) * a.out_os + u0 + ctile;
+        if( a.opeer_planes )
         {
-            double2 * out = a.out + std::size_t( o ) * a.out_os + u0 + ctile;
-            if( a.opeer_planes )
-            {
-                const int q = o / a.opeer_planes, c = o - q * a.opeer_planes, r = c / a.opeer_ncl;
-                out         = a.out_peer[r] + std::size_t( q * a.opeer_ncl + ( c - r * a.opeer_ncl ) ) * a.out_os + u0 + ctile;
-            }
+            const int q = o / a.opeer_planes, c = o - q * a.opeer_planes, r = c / a.opeer_ncl;
+            out         = a.out_peer[r] + std::size_t( q * a.opeer_ncl + ( c - r * a.opeer_ncl ) ) * a.out_os + u0 + ctile;
+        }
+#pragma unroll 1
+        for( int b = 0; b < NSEQ; ++b )
+        {
+            const int tb = j0 + b * jstep;
+            double2 v[L::PER][L::R];
+            stage_fetch<LOGN, L::R, false>( mine, lg_ncol, ctile & ( ( 1 << lg_ncol ) - 1 ), tb, v );
 #pragma unroll
             for( int jj = 0; jj < L::PER; ++jj )
+                dft_small<INVERSE, L::R>( v[jj] );
+            if( valid )
+            {
 #pragma unroll
-                for( int i = 0; i < L::R; ++i )
-                {
-                    const int j = tt + ( jj + L::PER * i ) * PER_COL;
-                    if( j < a.n_out )
+                for( int jj = 0; jj < L::PER; ++jj )
+#pragma unroll
+                    for( int i = 0; i < L::R; ++i )
                     {
-                        const double2 w = make_double2( a.scale * v[jj][i].x, a.scale * v[jj][i].y );
-                        if( a.use_out_peer )
-                            a.out_peer[j >> lg_out_split]
-                                      [std::size_t( o ) * a.out_os + u0 + ctile + std::size_t( unsigned( j ) & ( ( 1u << lg_out_split ) - 1u ) ) * a.out_js]
-                                = w;
-                        else
-                            out[pass_offset16( j, a.out_js, lg_out_split, a.out_split_stride )] = w;
+                        const int j = tb + ( jj + L::PER * i ) * PER_COL;
+                        if( j < a.n_out )
+                        {
+                            const double2 w = make_double2( a.scale * v[jj][i].x, a.scale * v[jj][i].y );
+                            if( a.use_out_peer )
+                                a.out_peer[j >> lg_out_split]
+                                          [std::size_t( o ) * a.out_os + u0 + ctile + std::size_t( unsigned( j ) & ( ( 1u << lg_out_split ) - 1u ) ) * a.out_js]
+                                    = w;
+                            else
+                                out[pass_offset16( j, a.out_js, lg_out_split, a.out_split_stride )] = w;
+                        }
                     }
-                }
+            }
         }
     }
 }
@@ -1169,7 +1176,7 @@ static __global__ void __launch_bounds__( FFT_THREADS, SB_FFT16_MINB ) k_fft_pas
 template<bool REAL_D, int LOGN>
 static __global__ void __launch_bounds__( CFBounds<LOGN>::T, CFBounds<LOGN>::MINB ) k_ddi_c_mult16f(
         const __grid_constant__ FFTPlan1D plan, const __grid_constant__ DDIDims d, double2 * __restrict__ B, const void * __restrict__ Dt_v,
-        const int lg_ncol )
+        const int lg_ncol, const int stage_tensor )
 {
     extern __shared__ double2 smem[];
     if constexpr( FFT_E != 8 ) // (tuning builds with other radices keep k_ddi_c_mult16)
@@ -2110,11 +2117,8 @@ void launch_pass16(
         }
         return;
     }
-    // register-resident first / last stages (k_fft_pass16r; SPIRIT_B200_FFT_PASS_REG=0 / 1 forces): measured faster with one
-    // column group per CTA (256^3, length 512: 0.83 -> 0.61 ms), slower with two (length 4096: film iteration 5.5 -> 6.1 ms, the
-    // groups' halves of a sector are stored microseconds apart) -- profiles/r2ze_sweep.txt
-    const char * reg_env = std::getenv( "SPIRIT_B200_FFT_PASS_REG" );
-    const bool reg       = FFT_E == 8 && ( reg_env ? reg_env[0] != '0' : !f.lg_seq );
+    // register-resident first / last stages (k_fft_pass16r) unless SPIRIT_B200_FFT_PASS_REG=0
+    const bool reg = FFT_E == 8 && !env_flag_off( "SPIRIT_B200_FFT_PASS_REG" );
     switch( ilog2( plan.n ) )
     {
 #define C( L )                                                                                                         \
