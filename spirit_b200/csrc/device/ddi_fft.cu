@@ -1176,7 +1176,7 @@ static __global__ void __launch_bounds__( FFT_THREADS, SB_FFT16_MINB ) k_fft_pas
 template<bool REAL_D, int LOGN>
 static __global__ void __launch_bounds__( CFBounds<LOGN>::T, CFBounds<LOGN>::MINB ) k_ddi_c_mult16f(
         const __grid_constant__ FFTPlan1D plan, const __grid_constant__ DDIDims d, double2 * __restrict__ B, const void * __restrict__ Dt_v,
-        const int lg_ncol, const int stage_tensor )
+        const int lg_ncol )
 {
     extern __shared__ double2 smem[];
     if constexpr( FFT_E != 8 ) // (tuning builds with other radices keep k_ddi_c_mult16)
