@@ -20,6 +20,8 @@ INCLUDE = os.path.join(ROOT, "include")
 # SPIRIT_B200_LIB selects an experimental build variant (spirit_b200/build.py); the default is the product library
 PRODUCT_LIB = os.path.join(HERE, os.environ.get("SPIRIT_B200_LIB", "libSpirit.so"))
 ORACLE_LIB = os.path.join(ROOT, "oracle", "_ref", "libSpirit_ref.so")
+# the same reference built with -DSPIRIT_ENABLE_PINNING -DSPIRIT_ENABLE_DEFECTS (`make -C oracle pd`)
+ORACLE_PD_LIB = os.path.join(ROOT, "oracle", "_ref", "libSpirit_ref_pd.so")
 
 
 class Simulation_Run_Info(ctypes.Structure):
@@ -176,3 +178,10 @@ def load_oracle():
     if "oracle" not in _cache:
         _cache["oracle"] = Library(ORACLE_LIB, "oracle")
     return _cache["oracle"]
+
+
+def load_oracle_pd():
+    """TEST INFRASTRUCTURE ONLY: the reference CPU build with pinning and defects compiled in. Never used by the product path."""
+    if "oracle_pd" not in _cache:
+        _cache["oracle_pd"] = Library(ORACLE_PD_LIB, "oracle")
+    return _cache["oracle_pd"]

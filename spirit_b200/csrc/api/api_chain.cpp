@@ -438,6 +438,8 @@ try
         }
         if( antiparallel )
             Log( Log_Level::Warning, Log_Sender::All, "For the interpolation of antiparallel spins an arbitrary rotation axis has been chosen." );
+        for( int img = idx_1 + 1; img < idx_2; ++img ) // Transitions.cpp:42
+            chain->images[img]->geometry->apply_pinning( chain->images[img]->spins.data() );
     }
     catch( ... )
     {
@@ -486,7 +488,10 @@ try
     chain->Lock();
     auto all = []( const Vec3 &, const Vec3 & ) { return true; };
     for( int img = idx_1 + 1; img <= idx_2 - 1; ++img )
+    {
         configurations::Add_Noise_Temperature( *chain->images[img], temperature, img, all );
+        chain->images[img]->geometry->apply_pinning( chain->images[img]->spins.data() ); // Transitions.cpp:107
+    }
     chain->Unlock();
 }
 catch( ... )

@@ -48,4 +48,16 @@ struct ImageLock
     }
     Spin_System & s_;
 };
+// Pinned sites are reset to their orientation after every change of a configuration through the API
+// (Geometry::Apply_Pinning at the end of each Configuration_* / Transition_* call, core/src/Spirit/Configurations.cpp:151-637).
+// Declared after the ImageLock of a call: runs before the lock is released.
+struct PinGuard
+{
+    explicit PinGuard( Spin_System & s ) : s_( s ) {}
+    ~PinGuard()
+    {
+        s_.geometry->apply_pinning( s_.spins.data() );
+    }
+    Spin_System & s_;
+};
 } // namespace sb

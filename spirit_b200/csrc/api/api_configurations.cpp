@@ -38,6 +38,7 @@ try
     const Vec3 vpos = image->geometry->center + v3( position );
     auto filter     = get_filter( vpos, r_cut_rectangular, r_cut_cylindrical, r_cut_spherical, inverted );
     ImageLock lock( *image );
+    PinGuard pin( *image );
     configurations::Insert( *image, *state->clipboard_spins, 0, filter );
 }
 SB_API_CATCH_VOID
@@ -65,6 +66,7 @@ try
     const int delta = g.n_cell_atoms * da + g.n_cell_atoms * g.n_cells[0] * db + g.n_cell_atoms * g.n_cells[0] * g.n_cells[1] * dc;
     auto filter     = get_filter( v3( position ), r_cut_rectangular, r_cut_cylindrical, r_cut_spherical, inverted );
     ImageLock lock( *image );
+    PinGuard pin( *image );
     configurations::Insert( *image, *state->clipboard_spins, delta, filter );
     return true;
 }
@@ -79,6 +81,7 @@ try
     const Vec3 vpos = image->geometry->center + v3( position );
     auto filter     = get_filter( vpos, r_cut_rectangular, r_cut_cylindrical, r_cut_spherical, inverted );
     ImageLock lock( *image );
+    PinGuard pin( *image );
     configurations::Domain( *image, v3( direction ), filter );
 }
 SB_API_CATCH_VOID
@@ -108,6 +111,7 @@ try
     const Vec3 vpos = image->geometry->center + v3( position );
     auto filter     = get_filter( vpos, r_cut_rectangular, r_cut_cylindrical, r_cut_spherical, inverted );
     ImageLock lock( *image );
+    PinGuard pin( *image );
     // `external` makes no difference in the reference either (Configurations.cpp:99-129 uses the LLG prng in both branches)
     configurations::Random( *image, filter );
 }
@@ -123,6 +127,7 @@ try
     const Vec3 vpos = image->geometry->center + v3( position );
     auto filter     = get_filter( vpos, r_cut_rectangular, r_cut_cylindrical, r_cut_spherical, inverted );
     ImageLock lock( *image );
+    PinGuard pin( *image );
     configurations::SpinSpiral( *image, direction_type ? direction_type : "", v3( q ), v3( axis ), theta, filter );
 }
 SB_API_CATCH_VOID
@@ -143,6 +148,7 @@ try
     const Vec3 vpos = image->geometry->center + v3( position );
     auto filter     = get_filter( vpos, r_cut_rectangular, r_cut_cylindrical, r_cut_spherical, inverted );
     ImageLock lock( *image );
+    PinGuard pin( *image );
     configurations::Add_Noise_Temperature( *image, temperature, 0, filter );
 }
 SB_API_CATCH_VOID
@@ -164,6 +170,7 @@ try
         r_cut_cylindrical = r;
     auto filter = get_filter( vpos, r_cut_rectangular, r_cut_cylindrical, r_cut_spherical, inverted );
     ImageLock lock( *image );
+    PinGuard pin( *image );
     configurations::Skyrmion( *image, vpos, r, order, phase, upDown, achiral, rl, filter );
 }
 SB_API_CATCH_VOID
@@ -180,6 +187,7 @@ try
         r_cut_cylindrical = std::max( 3 * dw_radius, 3 * dw_width );
     auto filter = get_filter( vpos, r_cut_rectangular, r_cut_cylindrical, r_cut_spherical, inverted );
     ImageLock lock( *image );
+    PinGuard pin( *image );
     configurations::DW_Skyrmion( *image, vpos, dw_radius, dw_width, order, phase, upDown, achiral, rl, filter );
 }
 SB_API_CATCH_VOID
@@ -195,16 +203,44 @@ try
         r_cut_spherical = r * float( constants::Pi ); // Configurations.cpp: the hopfion fills a sphere of radius pi*r
     auto filter = get_filter( vpos, r_cut_rectangular, r_cut_cylindrical, r_cut_spherical, inverted );
     ImageLock lock( *image );
+    PinGuard pin( *image );
     configurations::Hopfion( *image, vpos, r, order, v3( normal ), filter );
 }
 SB_API_CATCH_VOID
 
-void Configuration_Set_Pinned( State *, bool, const float[3], const float[3], float, float, bool, int idx_image, int idx_chain ) noexcept
+// Pinning (Configurations.cpp:697-726, Utility::Configurations::Set_Pinned): the filtered sites are (un)pinned at their current
+// orientation
+void Configuration_Set_Pinned(
+    State * state, bool pinned, const float position[3], const float r_cut_rectangular[3], float r_cut_cylindrical, float r_cut_spherical,
+    bool inverted, int idx_image, int idx_chain ) noexcept
+try
 {
-    Log( Log_Level::Warning, Log_Sender::API, "Configuration_Set_Pinned: pinning is disabled in this build (as in the reference default build)", idx_image, idx_chain );
+    auto image      = resolve( state, idx_image, idx_chain ).image;
+    const Vec3 vpos = image->geometry->center + v3( position );
+    auto filter     = get_filter( vpos, r_cut_rectangular, r_cut_cylindrical, r_cut_spherical, inverted );
+    ImageLock lock( *image );
+    const auto & positions = image->geometry->positions();
+    for( int i = 0; i < image->nos; ++i )
+        if( filter( image->spins[i], positions[i] ) )
+            image->geometry->set_pinned( i, pinned, image->spins[i] );
+    Log( Log_Level::Info, Log_Sender::API, "Set pinned spins.", idx_image, idx_chain );
 }
+SB_API_CATCH_VOID
 
-void Configuration_Set_Atom_Type( State *, int, const float[3], const float[3], float, float, bool, int idx_image, int idx_chain ) noexcept
+// Defects (Configurations.cpp:728-758, Utility::Configurations::Set_Atom_Types): type < 0 makes the filtered sites vacancies
+void Configuration_Set_Atom_Type(
+    State * state, int atom_type, const float position[3], const float r_cut_rectangular[3], float r_cut_cylindrical,
+    float r_cut_spherical, bool inverted, int idx_image, int idx_chain ) noexcept
+try
 {
-    Log( Log_Level::Warning, Log_Sender::API, "Configuration_Set_Atom_Type: defects are disabled in this build (as in the reference default build)", idx_image, idx_chain );
+    auto image      = resolve( state, idx_image, idx_chain ).image;
+    const Vec3 vpos = image->geometry->center + v3( position );
+    auto filter     = get_filter( vpos, r_cut_rectangular, r_cut_cylindrical, r_cut_spherical, inverted );
+    ImageLock lock( *image );
+    const auto & positions = image->geometry->positions();
+    for( int i = 0; i < image->nos; ++i )
+        if( filter( image->spins[i], positions[i] ) )
+            image->geometry->set_atom_type( i, atom_type );
+    Log( Log_Level::Info, Log_Sender::API, "Set atom types to " + std::to_string( atom_type ) + ".", idx_image, idx_chain );
 }
+SB_API_CATCH_VOID

@@ -124,8 +124,8 @@ const char * Spirit_Compiler() noexcept { return "nvcc+g++"; }
 const char * Spirit_Compiler_Version() noexcept { return __VERSION__; }
 const char * Spirit_Compiler_Full() noexcept { return "nvcc 12.9 + g++ " __VERSION__; }
 const char * Spirit_Scalar_Type() noexcept { return "double"; }
-const char * Spirit_Defects() noexcept { return "OFF"; }
-const char * Spirit_Pinning() noexcept { return "OFF"; }
+const char * Spirit_Defects() noexcept { return "ON"; } // (compile-time options of the reference; always built here)
+const char * Spirit_Pinning() noexcept { return "ON"; }
 const char * Spirit_Cuda() noexcept { return "ON"; }
 const char * Spirit_OpenMP() noexcept { return "OFF"; }
 int Spirit_OpenMP_Get_Num_Threads() noexcept { return 1; }

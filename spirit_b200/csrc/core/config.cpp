@@ -243,7 +243,96 @@ std::shared_ptr<Geometry> Geometry_from_Config( const std::string & config_file 
     }
 
     // The reference stores the Bravais vectors scaled by nothing and multiplies positions by the lattice constant
-    return std::make_shared<Geometry>( bravais_vectors, n_cells, cell_atoms, cell_mu_s, lattice_constant );
+    auto geometry = std::make_shared<Geometry>( bravais_vectors, n_cells, cell_atoms, cell_mu_s, lattice_constant );
+
+    // Pinning (Pinning_from_Config, Configparser.cpp:573-699) and defects (Configparser.cpp:389-441; the tables are read by
+    // Pinned_from_File / Defects_from_File, Dataparser.cpp:681-775) -- compile-time options of the reference, always built here
+    if( !config_file.empty() )
+    {
+        Pinning pinning;
+        Defects defects;
+        pinning.pinned_cell.assign( cell_atoms.size(), Vec3{ 0, 0, 1 } );
+        ConfigFile f( config_file );
+        if( f.Find( "atom_types" ) ) // (propagates: State_Setup fails, as for every Hamiltonian / lattice this library cannot build)
+            throw std::runtime_error( "spirit_b200: disordered basis cells ('atom_types' with concentrations) are not supported" );
+        try
+        {
+            int na = 0, nb = 0, nc = 0;
+            f.Read_Single( pinning.na_left, "pin_na_left" );
+            f.Read_Single( pinning.na_right, "pin_na_right" );
+            f.Read_Single( na, "pin_na " );
+            if( na > 0 && ( pinning.na_left == 0 || pinning.na_right == 0 ) )
+                pinning.na_left = pinning.na_right = na;
+            f.Read_Single( pinning.nb_left, "pin_nb_left" );
+            f.Read_Single( pinning.nb_right, "pin_nb_right" );
+            f.Read_Single( nb, "pin_nb " );
+            if( nb > 0 && ( pinning.nb_left == 0 || pinning.nb_right == 0 ) )
+                pinning.nb_left = pinning.nb_right = nb;
+            f.Read_Single( pinning.nc_left, "pin_nc_left" );
+            f.Read_Single( pinning.nc_right, "pin_nc_right" );
+            f.Read_Single( nc, "pin_nc " );
+            if( nc > 0 && ( pinning.nc_left == 0 || pinning.nc_right == 0 ) )
+                pinning.nc_left = pinning.nc_right = nc;
+            if( pinning.na_left > 0 || pinning.na_right > 0 || pinning.nb_left > 0 || pinning.nb_right > 0 || pinning.nc_left > 0
+                || pinning.nc_right > 0 )
+            {
+                if( f.Find( "pinning_cell" ) )
+                    for( std::size_t i = 0; i < cell_atoms.size(); ++i )
+                    {
+                        f.GetLine();
+                        f.iss >> pinning.pinned_cell[i][0] >> pinning.pinned_cell[i][1] >> pinning.pinned_cell[i][2];
+                    }
+                else
+                {
+                    pinning.na_left = pinning.na_right = pinning.nb_left = pinning.nb_right = pinning.nc_left = pinning.nc_right = 0;
+                    Log( Log_Level::Warning, Log_Sender::IO, "Pinning specified, but keyword 'pinning_cell' not found. Won't pin any spins!" );
+                }
+            }
+            // tables: `n_pinned N` / `n_defects N` followed by N lines in this file, or a file of such lines
+            auto read_table = [&]( const std::string & count_key, const std::string & file_key, auto && row )
+            {
+                std::string file;
+                if( f.Find( count_key ) )
+                    file = config_file;
+                else if( f.Find( file_key ) )
+                    f.iss >> file;
+                if( file.empty() )
+                    return;
+                ConfigFile t( file );
+                int n = int( 1e8 ), read = 0;
+                if( t.Find( count_key ) )
+                    t.iss >> n;
+                else
+                    t.To_Start();
+                while( read < n && t.GetLine() )
+                {
+                    row( t.iss );
+                    ++read;
+                }
+            };
+            read_table( "n_pinned", "pinned_from_file", [&]( std::istringstream & in ) {
+                LatticeSite site;
+                Vec3 o{ 0, 0, 0 };
+                in >> site.i >> site.translations[0] >> site.translations[1] >> site.translations[2] >> o[0] >> o[1] >> o[2];
+                pinning.sites.push_back( site );
+                pinning.spins.push_back( o );
+            } );
+            read_table( "n_defects", "defects_from_file", [&]( std::istringstream & in ) {
+                LatticeSite site;
+                int type = 0;
+                in >> site.i >> site.translations[0] >> site.translations[1] >> site.translations[2] >> type;
+                defects.sites.push_back( site );
+                defects.types.push_back( type );
+            } );
+        }
+        catch( const std::exception & e )
+        {
+            Log( Log_Level::Error, Log_Sender::IO,
+                 std::string( "Failed to read pinning / defects: " ) + e.what() + ". Leaving values at default." );
+        }
+        geometry->set_pinning_and_defects( pinning, defects );
+    }
+    return geometry;
 }
 
 // ---------------------------------------------------------------------------------------------

@@ -83,7 +83,7 @@ const scalarfield & Geometry::mu_s() const
     {
         _mu_s.resize( nos );
         for( std::int64_t i = 0; i < nos; ++i )
-            _mu_s[i] = cell_mu_s[i % n_cell_atoms];
+            _mu_s[i] = ( !site_flags.empty() && ( site_flags[i] & SITE_NO_MU_S ) ) ? 0.0 : cell_mu_s[i % n_cell_atoms];
     }
     return _mu_s;
 }
@@ -97,6 +97,114 @@ const intfield & Geometry::atom_types() const
             _atom_types[i] = cell_atom_types[i % n_cell_atoms];
     }
     return _atom_types;
+}
+
+// ---- pinning and defects (Geometry.cpp:50-83, 486-566, 807-832) ----
+int Geometry::site_index( const LatticeSite & site ) const
+{
+    return site.i + n_cell_atoms * ( site.translations[0] + n_cells[0] * ( site.translations[1] + n_cells[1] * site.translations[2] ) );
+}
+
+void Geometry::need_site_flags()
+{
+    if( site_flags.empty() )
+    {
+        site_flags.assign( nos, 0 );
+        mask_pinned_cells.assign( nos, Vec3{ 0, 0, 0 } );
+    }
+}
+
+void Geometry::set_pinning_and_defects( const Pinning & pinning_, const Defects & defects_ )
+{
+    pinning = pinning_;
+    defects = defects_;
+    pinning.pinned_cell.resize( n_cell_atoms, Vec3{ 0, 0, 1 } );
+    site_flags.clear();
+    mask_pinned_cells.clear();
+    _atom_types.clear();
+    _mu_s.clear();
+    nos_nonvacant = nos;
+    ++site_revision;
+    const bool boundary = pinning.na_left > 0 || pinning.na_right > 0 || pinning.nb_left > 0 || pinning.nb_right > 0 || pinning.nc_left > 0
+                          || pinning.nc_right > 0;
+    if( !boundary && pinning.sites.empty() && defects.sites.empty() )
+        return;
+    need_site_flags();
+    const std::int64_t Na = n_cells[0], Nb = n_cells[1], Nc = n_cells[2], N = n_cell_atoms;
+    if( boundary )
+        for( std::int64_t c = 0; c < Nc; ++c )
+            for( std::int64_t b = 0; b < Nb; ++b )
+                for( std::int64_t a = 0; a < Na; ++a )
+                    if( a < pinning.na_left || a >= Na - pinning.na_right || b < pinning.nb_left || b >= Nb - pinning.nb_right
+                        || c < pinning.nc_left || c >= Nc - pinning.nc_right )
+                        for( int iatom = 0; iatom < N; ++iatom )
+                        {
+                            const std::int64_t ispin = iatom + N * ( a + Na * ( b + Nb * c ) );
+                            site_flags[ispin] |= SITE_PINNED;
+                            mask_pinned_cells[ispin] = pinning.pinned_cell[iatom];
+                        }
+    for( std::size_t k = 0; k < pinning.sites.size(); ++k )
+    {
+        const int ispin = site_index( pinning.sites[k] );
+        if( ispin < 0 || ispin >= nos )
+            throw std::runtime_error( "Geometry: pinned site outside of the lattice" );
+        site_flags[ispin] |= SITE_PINNED;
+        mask_pinned_cells[ispin] = pinning.spins[k];
+    }
+    atom_types(); // per-site types: the basis cell's, then the defects'
+    for( std::size_t k = 0; k < defects.sites.size(); ++k )
+    {
+        const int ispin = site_index( defects.sites[k] );
+        if( ispin < 0 || ispin >= nos )
+            throw std::runtime_error( "Geometry: defect site outside of the lattice" );
+        _atom_types[ispin] = defects.types[k];
+        site_flags[ispin] |= SITE_NO_MU_S; // Geometry.cpp:80-81: mu_s = 0 at every defect site
+        if( defects.types[k] < 0 )
+            site_flags[ispin] |= SITE_VACANT;
+        else
+            site_flags[ispin] &= static_cast<unsigned char>( ~SITE_VACANT );
+    }
+}
+
+void Geometry::set_pinned( int ispin, bool pinned, const Vec3 & orientation )
+{
+    need_site_flags();
+    if( pinned )
+        site_flags[ispin] |= SITE_PINNED;
+    else
+        site_flags[ispin] &= static_cast<unsigned char>( ~SITE_PINNED );
+    mask_pinned_cells[ispin] = orientation;
+    ++site_revision;
+}
+
+void Geometry::set_atom_type( int ispin, int type )
+{
+    need_site_flags();
+    atom_types();
+    _atom_types[ispin] = type;
+    if( type < 0 )
+    {
+        if( !( site_flags[ispin] & SITE_VACANT ) )
+            --nos_nonvacant;
+        site_flags[ispin] |= SITE_VACANT | SITE_NO_MU_S; // Configurations.cpp:577-579: mu_s = 0 for vacancies
+    }
+    else
+    {
+        if( site_flags[ispin] & SITE_VACANT )
+            ++nos_nonvacant;
+        site_flags[ispin] &= static_cast<unsigned char>( ~SITE_VACANT ); // (mu_s stays as it is, as in the reference)
+    }
+    _mu_s.clear();
+    ++site_revision;
+}
+
+void Geometry::apply_pinning( Vec3 * spins ) const
+{
+    if( site_flags.empty() )
+        return;
+    for( std::int64_t i = 0; i < nos; ++i )
+        if( site_flags[i] & SITE_PINNED )
+            spins[i] = mask_pinned_cells[i];
 }
 
 bool Geometry::mu_s_homogeneous() const

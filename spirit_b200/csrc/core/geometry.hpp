@@ -23,6 +23,31 @@ enum class BravaisLatticeType
     FCC         = 8
 };
 
+// A lattice site named by basis atom and cell translations (Data::Site, core/include/engine/Vectormath.hpp)
+struct LatticeSite
+{
+    int i = 0;
+    int translations[3] = { 0, 0, 0 };
+};
+// Pinned boundary cells and individually pinned sites (Data::Pinning, core/include/data/Geometry.hpp:40-58)
+struct Pinning
+{
+    int na_left = 0, na_right = 0, nb_left = 0, nb_right = 0, nc_left = 0, nc_right = 0;
+    std::vector<Vec3> pinned_cell;   // orientation of the pinned boundary cells, per basis atom
+    std::vector<LatticeSite> sites;  // additional pinned sites ...
+    std::vector<Vec3> spins;         // ... and their orientations
+};
+// Defect sites (Data::Defects, core/include/data/Geometry.hpp:60-66): type < 0 is a vacancy
+struct Defects
+{
+    std::vector<LatticeSite> sites;
+    std::vector<int> types;
+};
+// per-site flags of a lattice with pinned sites or defects
+constexpr unsigned char SITE_VACANT  = 1; // atom type < 0: the site takes part in no interaction (check_atom_type, Vectormath.hpp:406-433)
+constexpr unsigned char SITE_PINNED  = 2; // mask_unpinned == 0: force and virtual force are zero (Method_LLG.cpp:122-124, 222-224)
+constexpr unsigned char SITE_NO_MU_S = 4; // mu_s == 0 (every defect site, Geometry.cpp:72-82): no Zeeman term, no dipolar moment
+
 struct Geometry
 {
     Geometry(
@@ -61,11 +86,31 @@ struct Geometry
 
     bool mu_s_homogeneous() const;
 
+    // Pinning and defects (the reference's compile-time options SPIRIT_ENABLE_PINNING / SPIRIT_ENABLE_DEFECTS, always built
+    // here). `site_flags` is empty for a lattice without either; otherwise one byte per site in the reference's site order.
+    // `mask_pinned_cells` holds the orientation pinned sites are reset to (Geometry::Apply_Pinning, Geometry.cpp:807-832).
+    // `site_revision` changes whenever the flags do (the device copy follows it).
+    void set_pinning_and_defects( const Pinning & pinning, const Defects & defects );
+    void set_pinned( int ispin, bool pinned, const Vec3 & orientation ); // Configurations::Set_Pinned, Configurations.cpp:583-599
+    void set_atom_type( int ispin, int type );                           // Configurations::Set_Atom_Types, :567-581
+    void apply_pinning( Vec3 * spins ) const;
+    bool has_site_flags() const
+    {
+        return !site_flags.empty();
+    }
+    int site_index( const LatticeSite & site ) const;
+    Pinning pinning;
+    Defects defects;
+    std::vector<unsigned char> site_flags;
+    vectorfield mask_pinned_cells;
+    std::uint64_t site_revision = 0;
+
 private:
     void calculateBounds();
     void calculateUnitCellBounds();
     void calculateDimensionality();
     void calculateGeometryType();
+    void need_site_flags();
 
     mutable vectorfield _positions;
     mutable scalarfield _mu_s;

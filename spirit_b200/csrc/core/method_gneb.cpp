@@ -65,6 +65,10 @@ Method_GNEB::Method_GNEB( std::shared_ptr<Chain> chain_, int solver_, int idx_ch
                               && h.cubic_anisotropy_magnitudes == h0.cubic_anisotropy_magnitudes && h.exchange_magnitudes == h0.exchange_magnitudes
                               && h.dmi_magnitudes == h0.dmi_magnitudes && h.ddi_method == h0.ddi_method
                               && chain->images[i]->llg_parameters->dt == chain->images[0]->llg_parameters->dt;
+            if( chain->images[i]->geometry->site_flags != chain->images[0]->geometry->site_flags )
+                throw std::runtime_error(
+                    "spirit_b200: GNEB over images with different pinned sites or defects (image " + std::to_string( i )
+                    + " differs from image 0) is not implemented: the device chain uses one set of site flags" );
             if( !same )
                 throw std::runtime_error(
                     "spirit_b200: GNEB over images with different Hamiltonian parameters or llg_dt (image " + std::to_string( i )

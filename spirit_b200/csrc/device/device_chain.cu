@@ -87,6 +87,7 @@ struct ChainView
     int moving_endpoints; // the end images feel a force too (Method_GNEB.cpp:261-355)
     int shortening;       // path shortening force on the normal images
     double * Ddi;         // dipolar gradient field of the evaluated configurations (null without dipolar interaction)
+    const unsigned char * site_flags; // pinned sites / defects of the lattice (StencilParams::site_flags), or null
 };
 // Field pointers are offset by one image, so that local index -1 / n_local address the halo images received from the
 // neighbouring ranks (images sharded over GPUs); unsharded chains have no halo and i_begin = 0.
@@ -554,6 +555,8 @@ __device__ __forceinline__ D3 chain_total_force( const ChainView & v, int img, s
     const int g = v.i_begin + img;
     if( slot( v, S_ZERO )[g] != 0.0 )
         return make_d3( 0, 0, 0 );
+    if( v.site_flags && ( __ldg( v.site_flags + idx ) & FLAG_PINNED ) ) // pinning mask on F_total (Method_GNEB.cpp:251-254)
+        return make_d3( 0, 0, 0 );
     const D3 Fg     = load3( cfield( v.Fg, v.stride, img ), idx );
     const D3 t      = load3( cfield( v.T, v.stride, img ), idx );
     const double d  = dot3( Fg, s );
@@ -869,6 +872,7 @@ DeviceChain::DeviceChain( const Geometry & geometry, int noi, int i_begin, int n
     b.view.moving_endpoints = 0;
     b.view.shortening       = 0;
     b.view.Ddi              = nullptr;
+    b.view.site_flags       = nullptr;
     b.view.P2               = nullptr;
     b.view.Acc              = nullptr;
 }
@@ -890,6 +894,7 @@ void DeviceChain::set_hamiltonian( const Hamiltonian & ham )
     // every image is evaluated with this Hamiltonian (Method_GNEB.cpp:99-100 calls each image's own; they are copies of one
     // another in a chain); with a dipolar term one convolution per image and evaluation fills the field the stencil adds
     table_->set_hamiltonian( ham );
+    buf_->view.site_flags = table_->stencil().site_flags; // (all images of the chain have image 0's pinned sites and defects)
     if( table_->stencil().has_ddi )
     {
         if( sharded_ )

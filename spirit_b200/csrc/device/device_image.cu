@@ -602,6 +602,10 @@ DeviceImage::DeviceImage( const Geometry & g )
 
 DeviceImage::~DeviceImage()
 {
+    if( site_flags_dev_ )
+        cudaFree( site_flags_dev_ );
+    if( ddi_masked_ )
+        cudaFree( ddi_masked_ );
     if( ddi_ )
         ddi_plan_destroy( ddi_ );
 }
@@ -740,11 +744,47 @@ double DeviceImage::timer_stop()
 }
 
 // Build the merged neighbour table and on-site tables from the host Hamiltonian
+// Site flags of a lattice with pinned sites or defects: one byte per storage index. With flags the nearest-neighbour
+// kernels are not used (their tables are rebuilt: sc6 = 0) and the generic kernels test the flags (stencil.cuh).
+void DeviceImage::sync_site_flags( const Geometry & g )
+{
+    if( g.site_revision == site_revision_ )
+        return;
+    site_revision_ = g.site_revision;
+    ham_revision_  = ~std::uint64_t( 0 ); // the choice of kernels depends on the flags
+    auto & b       = *buf_;
+    bool any       = false;
+    for( unsigned char f : g.site_flags )
+        any = any || f != 0;
+    if( !any )
+    {
+        if( site_flags_dev_ )
+            SB_CUDA_CHECK( cudaFree( site_flags_dev_ ) );
+        site_flags_dev_ = nullptr;
+        return;
+    }
+    if( slab_ )
+        throw std::runtime_error( "spirit_b200: pinned sites / defects are not supported on a slab decomposition" );
+    std::vector<unsigned char> h( b.n_storage, 0 );
+    const int plane_sites = stencil_.Na * stencil_.NB * stencil_.Nb;
+    for( int i = 0; i < nos_; ++i )
+    {
+        const int c = i / plane_sites;
+        h[std::size_t( i - c * plane_sites ) + std::size_t( stencil_.plane_stride ) * ( c + stencil_.halo )] = g.site_flags[i];
+    }
+    if( !site_flags_dev_ )
+        SB_CUDA_CHECK( cudaMalloc( &site_flags_dev_, b.n_storage ) );
+    SB_CUDA_CHECK( cudaMemcpyAsync( site_flags_dev_, h.data(), b.n_storage, cudaMemcpyHostToDevice, b.stream ) );
+    SB_CUDA_CHECK( cudaStreamSynchronize( b.stream ) );
+}
+
 void DeviceImage::set_hamiltonian( const Hamiltonian & ham )
 {
+    sync_site_flags( *ham.geometry );
     if( ham.revision == ham_revision_ )
         return;
     const Geometry & g = *ham.geometry;
+    stencil_.site_flags = site_flags_dev_;
     StencilParams & p  = stencil_;
     for( int d = 0; d < 3; ++d )
         p.bc[d] = ham.boundary_conditions[d];
@@ -851,7 +891,7 @@ void DeviceImage::set_hamiltonian( const Hamiltonian & ham )
             p.sc6_dflags[d] = ( plus[d]->Dx != 0 ? 1 : 0 ) | ( plus[d]->Dy != 0 ? 2 : 0 ) | ( plus[d]->Dz != 0 ? 4 : 0 );
         }
         const char * off = std::getenv( "SPIRIT_B200_GENERIC_STENCIL" ); // tests: force the generic gather kernels
-        p.sc6            = ( ok && !( off && off[0] == '1' ) ) ? 1 : 0;
+        p.sc6            = ( ok && !( off && off[0] == '1' ) && !site_flags_dev_ ) ? 1 : 0;
     }
     {
         const char * off = std::getenv( "SPIRIT_B200_NO_FUSED" ); // tests / A-B runs: force the two-pass marching kernels
@@ -1564,6 +1604,7 @@ bool DeviceImage::ddi_gradient_of( const double * configuration_base, double * o
     c.base = configuration_base;
     Field3 o;
     o.base = out_base;
+    c.base = ddi_operand( configuration_base, stream );
     launches_ += ddi_gradient( *ddi_, c, o, cudaStream_t( stream ) );
     return true;
 }
@@ -1588,7 +1629,25 @@ void DeviceImage::compute_ddi_gradient( int which )
     auto & b = *buf_;
     const DeviceField & conf = which == 0 ? b.spins : ( which == 1 ? b.pred : b.pred2 );
     DeviceField & out        = which == 0 ? b.ddi_s : b.ddi_p;
-    launches_ += ddi_gradient( *ddi_, conf.c(), out.f(), b.stream );
+    ConstField3 operand;
+    operand.base = ddi_operand( conf.base, b.stream );
+    launches_ += ddi_gradient( *ddi_, operand, out.f(), b.stream );
+}
+
+// Sites without a magnetic moment (defects: mu_s = 0, Geometry.cpp:80-81) do not enter the dipolar convolution: its operand
+// is a copy of the configuration with those sites zeroed (their own dipolar gradient is dropped in site_gradient).
+const double * DeviceImage::ddi_operand( const double * conf, void * stream_v )
+{
+    if( !site_flags_dev_ )
+        return conf;
+    auto & b            = *buf_;
+    cudaStream_t stream = cudaStream_t( stream_v );
+    if( !ddi_masked_ )
+        SB_CUDA_CHECK( cudaMalloc( &ddi_masked_, 3 * b.n_storage * sizeof( double ) ) );
+    const std::size_t n = 3 * b.n_storage;
+    k_mask_moments<<<unsigned( ( n + BLOCK_THREADS - 1 ) / BLOCK_THREADS ), BLOCK_THREADS, 0, stream>>>( conf, ddi_masked_, site_flags_dev_, n );
+    ++launches_;
+    return ddi_masked_;
 }
 
 } // namespace dev

@@ -191,6 +191,19 @@ static __global__ void __launch_bounds__( BLOCK_THREADS )
     }
 }
 
+// out = in with the sites without a magnetic moment zeroed (element e of an AoSoA-32 field belongs to storage site
+// (e / 96) * 32 + e % 32): operand of the dipolar convolution on a lattice with defects
+static __global__ void __launch_bounds__( BLOCK_THREADS )
+    k_mask_moments( const double * __restrict__ in, double * __restrict__ out, const unsigned char * __restrict__ flags, std::size_t n )
+{
+    const std::size_t e = blockIdx.x * std::size_t( BLOCK_THREADS ) + threadIdx.x;
+    if( e < n )
+    {
+        const std::size_t site = ( e / ( 3 * FIELD_BLOCK ) ) * FIELD_BLOCK + ( e % FIELD_BLOCK );
+        out[e]                 = ( flags[site] & FLAG_NO_MU_S ) ? 0.0 : in[e];
+    }
+}
+
 // ---------------------------------------------------------------------------------------------
 // Gradient (+ energy) of one configuration. Hamiltonian_Heisenberg.cpp:670-766.
 // out = sign * gradient (sign = -1 gives the effective field / force).
@@ -239,9 +252,17 @@ static __global__ void __launch_bounds__( BLOCK_THREADS ) k_energy_contributions
     const int ib  = NB_T == 1 ? 0 : site.ib;
     const D3 si   = load3( s, site.idx );
     const int lin = site.a * NB + ib + p.Na * NB * ( site.b + p.Nb * site.c ); // index without halo
+    const unsigned flags = p.site_flags ? __ldg( p.site_flags + site.idx ) : 0u;
+    if( flags & FLAG_VACANT )
+    {
+        for( int t = 0; t < 6; ++t )
+            if( out.term[t] )
+                out.term[t][lin] = 0.0;
+        return;
+    }
 
     if( out.term[0] )
-        out.term[0][lin] = -( p.zeeman[ib][0] * si.x + p.zeeman[ib][1] * si.y + p.zeeman[ib][2] * si.z );
+        out.term[0][lin] = ( flags & FLAG_NO_MU_S ) ? 0.0 : -( p.zeeman[ib][0] * si.x + p.zeeman[ib][1] * si.y + p.zeeman[ib][2] * si.z );
     if( out.term[1] )
     {
         double e = 0;
@@ -280,6 +301,8 @@ static __global__ void __launch_bounds__( BLOCK_THREADS ) k_energy_contributions
                 const int gc = p.c_begin + jc;
                 valid        = valid && ( p.bc[2] || ( gc >= 0 && gc < p.Nc ) );
             }
+            if( valid && p.site_flags && ( __ldg( p.site_flags + storage_index( p, ja * NB + nb.jb, jb, jc ) ) & FLAG_VACANT ) )
+                valid = false;
             if( valid )
             {
                 const D3 sj = load3( s, storage_index( p, ja * NB + nb.jb, jb, jc ) );
@@ -295,7 +318,7 @@ static __global__ void __launch_bounds__( BLOCK_THREADS ) k_energy_contributions
             out.term[4][lin] = e_dmi;
     }
     if( out.term[5] )
-        out.term[5][lin] = 0.5 * dot3( si, load3( ddi, site.idx ) );
+        out.term[5][lin] = ( flags & FLAG_NO_MU_S ) ? 0.0 : 0.5 * dot3( si, load3( ddi, site.idx ) );
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -347,15 +370,18 @@ static __global__ void __launch_bounds__( BLOCK_THREADS ) k_llg_stage(
         if( l.has_thermal && !l.direct_minimization )
             xi = thermal_field<NB_T>( p, l, site );
 
+        const bool frozen = site_frozen( p, site );
         D3 Fv = make_d3( 0, 0, 0 ), Fvp = make_d3( 0, 0, 0 ), spi = si;
         if( Needs::Fv_s )
         {
             const SiteGradient g = site_gradient<NB_T>( p, a.s, a.ddi_s, site, si );
             const D3 gt          = total( g );
-            const D3 F           = make_d3( -gt.x, -gt.y, -gt.z );
+            const D3 F           = frozen ? make_d3( 0, 0, 0 ) : make_d3( -gt.x, -gt.y, -gt.z );
             Fv                   = virtual_force<NB_T>( l, site, si, F, xi );
             if( l.has_stt == 2 )
                 Fv = add3( Fv, stt_gradient_term<NB_T>( p, l, a.s, site, si ) );
+            if( frozen )
+                Fv = make_d3( 0, 0, 0 );
             if( HOOK && STAGE == 1 )
             {
                 store3( a.F_out, site.idx, F );
@@ -370,6 +396,8 @@ static __global__ void __launch_bounds__( BLOCK_THREADS ) k_llg_stage(
             Fvp                  = virtual_force<NB_T>( l, site, spi, make_d3( -gt.x, -gt.y, -gt.z ), xi );
             if( l.has_stt == 2 )
                 Fvp = add3( Fvp, stt_gradient_term<NB_T>( p, l, a.sp, site, spi ) );
+            if( frozen )
+                Fvp = make_d3( 0, 0, 0 );
             if( HOOK && last_stage )
                 e = site_energy<NB_T>( p, site, spi, g );
         }
@@ -417,7 +445,7 @@ static __global__ void __launch_bounds__( BLOCK_THREADS ) k_vp_a(
         const D3 si             = load3( s, site.idx );
         const SiteGradient g    = site_gradient<NB_T>( p, s, ddi, site, si );
         const D3 gt             = total( g );
-        const D3 Fn             = make_d3( -gt.x, -gt.y, -gt.z );
+        const D3 Fn             = site_frozen( p, site ) ? make_d3( 0, 0, 0 ) : make_d3( -gt.x, -gt.y, -gt.z );
         // velocity of the last iteration = ratio_prev * (raw force of the last iteration); F_prev is the same force,
         // or its tangential projection if a post-iteration hook ran in between (SURVEY.md 8c hazard 6)
         const D3 Fr             = load3( F, site.idx );
@@ -535,11 +563,14 @@ static __global__ void __launch_bounds__( BLOCK_THREADS ) k_force_and_virtual(
             xi = thermal_field<NB_T>( p, l, site );
         const SiteGradient g = site_gradient<NB_T>( p, s, ddi, site, si );
         const D3 gt          = total( g );
-        const D3 F           = make_d3( -gt.x, -gt.y, -gt.z );
+        const bool frozen    = site_frozen( p, site );
+        const D3 F           = frozen ? make_d3( 0, 0, 0 ) : make_d3( -gt.x, -gt.y, -gt.z );
         store3( F_out, site.idx, F );
         D3 Fv = virtual_force<NB_T>( l, site, si, F, xi );
         if( l.has_stt == 2 )
             Fv = add3( Fv, stt_gradient_term<NB_T>( p, l, s, site, si ) );
+        if( frozen )
+            Fv = make_d3( 0, 0, 0 );
         store3( Fv_out, site.idx, Fv );
         e = site_energy<NB_T>( p, site, si, g );
     }
@@ -559,7 +590,9 @@ static __global__ void __launch_bounds__( BLOCK_THREADS ) k_magnetization(
     if( active )
     {
         const D3 si     = load3( s, site.idx );
-        const double mu = weighted ? p.mu_s[site.ib] : 1.0;
+        double mu       = weighted ? p.mu_s[site.ib] : 1.0;
+        if( weighted && p.site_flags && ( __ldg( p.site_flags + site.idx ) & FLAG_NO_MU_S ) )
+            mu = 0.0;
         m               = make_d3( mu * si.x, mu * si.y, mu * si.z );
     }
     double v = block_sum( m.x );

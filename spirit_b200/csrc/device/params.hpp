@@ -80,12 +80,20 @@ struct StencilParams
     double sc6_A[6];    // on-site quadratic form -2 sum_k K_k n_k n_k^T of basis atom 0: xx, yy, zz, xy, xz, yz
     double sc6_g0[3];   // -mu_s B n: start value of the gradient accumulation
 
+    // Pinned sites and defects (Geometry::site_flags; SITE_* bits below), one byte per STORAGE index; null on a lattice without
+    // either. With flags the nearest-neighbour kernels step aside (sc6 = 0) and the generic kernels test them:
+    // a vacancy takes part in no interaction (check_atom_type / idx_from_pair, Vectormath.hpp:406-528), a site without moment
+    // has no Zeeman and no dipolar term, force and virtual force of a pinned site are zero (Method_LLG.cpp:122-124, 222-224).
+    const unsigned char * site_flags;
+
     double K4[MAX_BASIS];        // cubic anisotropy per basis atom (Hamiltonian_Heisenberg.cpp:802-820)
     double zeeman[MAX_BASIS][3]; // mu_s[ib] * (B mu_B) * n_B   (Hamiltonian_Heisenberg.cpp:768-783)
     double mu_s[MAX_BASIS];
     Anisotropy aniso[MAX_ANISO];
     Neighbour neigh[MAX_NEIGH];
 };
+
+constexpr unsigned FLAG_VACANT = 1, FLAG_PINNED = 2, FLAG_NO_MU_S = 4; // = sb::SITE_* (core/geometry.hpp)
 
 // LLG virtual-force parameters (core/src/engine/Method_LLG.cpp:131-226)
 struct LLGParams

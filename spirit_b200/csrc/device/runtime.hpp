@@ -179,6 +179,12 @@ private:
     int nos_ = 0;
     StencilParams stencil_{};
     std::uint64_t ham_revision_ = ~std::uint64_t( 0 );
+    // pinned sites / defects (Geometry::site_flags) in storage order on the device; follows Geometry::site_revision
+    void sync_site_flags( const Geometry & g );
+    const double * ddi_operand( const double * conf_base, void * stream );
+    unsigned char * site_flags_dev_ = nullptr;
+    double * ddi_masked_            = nullptr; // configuration with the sites without moment zeroed: operand of the dipolar convolution
+    std::uint64_t site_revision_    = 0;
     std::unique_ptr<DeviceBuffers> buf_;
     DDIPlan * ddi_ = nullptr; // owned; created by set_hamiltonian when ddi_method == fft
     std::uint64_t launches_ = 0;

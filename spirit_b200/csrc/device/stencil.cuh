@@ -173,6 +173,8 @@ __device__ __forceinline__ D3 pair_gradient( const StencilParams & p, const Cons
         if( valid )
         {
             const int j = storage_index( p, ja * NB + nb.jb, jb, jc );
+            if( p.site_flags && ( __ldg( p.site_flags + j ) & FLAG_VACANT ) )
+                continue; // idx_from_pair: the pair does not exist
             const D3 sj = load3( s, j );
             // g -= J s_j + s_j x D
             g.x -= nb.J * sj.x + ( sj.y * nb.Dz - sj.z * nb.Dy );
@@ -189,6 +191,12 @@ site_gradient( const StencilParams & p, const ConstField3 & s, const ConstField3
 {
     SiteGradient out;
     const int ib = NB_T == 1 ? 0 : site.ib;
+    const unsigned flags = p.site_flags ? __ldg( p.site_flags + site.idx ) : 0u;
+    if( flags & FLAG_VACANT )
+    {
+        out.bilinear = out.rest = make_d3( 0, 0, 0 );
+        return out;
+    }
 
     D3 g = pair_gradient<NB_T>( p, s, site );
 
@@ -205,7 +213,7 @@ site_gradient( const StencilParams & p, const ConstField3 & s, const ConstField3
         }
     }
     // Dipole-dipole field, precomputed by the FFT convolution for this configuration
-    if( p.has_ddi )
+    if( p.has_ddi && !( flags & FLAG_NO_MU_S ) )
     {
         const D3 gd = load3( ddi, site.idx );
         g.x += gd.x;
@@ -224,7 +232,7 @@ site_gradient( const StencilParams & p, const ConstField3 & s, const ConstField3
         r.z -= k * si.z * si.z * si.z;
     }
     // Zeeman: g -= mu_s B n   (Hamiltonian_Heisenberg.cpp:768-783)
-    if( p.has_zeeman )
+    if( p.has_zeeman && !( flags & FLAG_NO_MU_S ) )
     {
         r.x -= p.zeeman[ib][0];
         r.y -= p.zeeman[ib][1];
@@ -241,15 +249,25 @@ __device__ __forceinline__ double
 site_energy( const StencilParams & p, const Site & site, const D3 & si, const SiteGradient & g )
 {
     const int ib = NB_T == 1 ? 0 : site.ib;
-    double e     = 0.5 * dot3( g.bilinear, si );
+    const unsigned flags = p.site_flags ? __ldg( p.site_flags + site.idx ) : 0u;
+    if( flags & FLAG_VACANT )
+        return 0.0;
+    double e = 0.5 * dot3( g.bilinear, si );
     if( p.has_cubic )
     {
         const double x2 = si.x * si.x, y2 = si.y * si.y, z2 = si.z * si.z;
         e -= 0.5 * p.K4[ib] * ( x2 * x2 + y2 * y2 + z2 * z2 );
     }
-    if( p.has_zeeman )
+    if( p.has_zeeman && !( flags & FLAG_NO_MU_S ) )
         e -= p.zeeman[ib][0] * si.x + p.zeeman[ib][1] * si.y + p.zeeman[ib][2] * si.z;
     return e;
+}
+
+// force and virtual force of these sites are zero: pinned ones (mask_unpinned, Method_LLG.cpp:122-124, 222-224) and vacancies
+// (their gradient is zero; the reference's dynamics divide their virtual force by mu_s = 0)
+__device__ __forceinline__ bool site_frozen( const StencilParams & p, const Site & site )
+{
+    return p.site_flags && ( __ldg( p.site_flags + site.idx ) & ( FLAG_VACANT | FLAG_PINNED ) );
 }
 
 __device__ __forceinline__ D3 total( const SiteGradient & g )

@@ -158,6 +158,17 @@ class Session:
         self.lib.Configuration_Skyrmion(
             self.state, radius, order, phase, up_down, achiral, rl, _f3(pos), _f3(self._rect0), -1, -1, False, idx_image, -1)
 
+    # ---- pinning and defects (Configurations.h:44-48, Geometry.h:42) ----------------------------------------------------
+    def set_pinned(self, pinned, pos=(0, 0, 0), rect=(-1, -1, -1), cylindrical=-1, spherical=-1, inverted=False, idx_image=-1):
+        self.lib.Configuration_Set_Pinned(self.state, bool(pinned), _f3(pos), _f3(rect), cylindrical, spherical, inverted, idx_image, -1)
+
+    def set_atom_type(self, atom_type, pos=(0, 0, 0), rect=(-1, -1, -1), cylindrical=-1, spherical=-1, inverted=False, idx_image=-1):
+        self.lib.Configuration_Set_Atom_Type(self.state, int(atom_type), _f3(pos), _f3(rect), cylindrical, spherical, inverted, idx_image, -1)
+
+    def atom_types(self, idx_image=-1):
+        ptr = self.lib.Geometry_Get_Atom_Types(self.state, idx_image, -1)
+        return np.ctypeslib.as_array(ptr, shape=(self.nos,)).copy()
+
     # ---- hamiltonian (Hamiltonian.h:65-101) --------------------------------------------------------------------------
     def set_boundary_conditions(self, bc, idx_image=-1):
         self.lib.Hamiltonian_Set_Boundary_Conditions(self.state, (ctypes.c_bool * 3)(*[bool(b) for b in bc]), idx_image, -1)

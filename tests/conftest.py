@@ -28,6 +28,15 @@ def oracle():
     return capi.load_oracle()
 
 
+@pytest.fixture(scope="session")
+def oracle_pd():
+    """TEST INFRASTRUCTURE: the reference CPU build with -DSPIRIT_ENABLE_PINNING -DSPIRIT_ENABLE_DEFECTS (`make -C oracle pd`)."""
+    from spirit_b200 import capi
+    if not os.path.exists(capi.ORACLE_PD_LIB):
+        pytest.fail("oracle/_ref/libSpirit_ref_pd.so is missing: run `make -C oracle pd` where /root/reference exists")
+    return capi.load_oracle_pd()
+
+
 @pytest.fixture
 def cfg(tmp_path):
     """Factory writing an input.cfg into the test's tmp dir: cfg('solvers', n_basis_cells='8 8 1')"""
