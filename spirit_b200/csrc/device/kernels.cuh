@@ -370,12 +370,12 @@ static __global__ void __launch_bounds__( BLOCK_THREADS ) k_llg_stage(
         if( l.has_thermal && !l.direct_minimization )
             xi = thermal_field<NB_T>( p, l, site );
 
-        const bool frozen = site_frozen( p, site );
         D3 Fv = make_d3( 0, 0, 0 ), Fvp = make_d3( 0, 0, 0 ), spi = si;
         if( Needs::Fv_s )
         {
             const SiteGradient g = site_gradient<NB_T>( p, a.s, a.ddi_s, site, si );
             const D3 gt          = total( g );
+            const bool frozen    = site_frozen( g );
             const D3 F           = frozen ? make_d3( 0, 0, 0 ) : make_d3( -gt.x, -gt.y, -gt.z );
             Fv                   = virtual_force<NB_T>( l, site, si, F, xi );
             if( l.has_stt == 2 )
@@ -396,7 +396,7 @@ static __global__ void __launch_bounds__( BLOCK_THREADS ) k_llg_stage(
             Fvp                  = virtual_force<NB_T>( l, site, spi, make_d3( -gt.x, -gt.y, -gt.z ), xi );
             if( l.has_stt == 2 )
                 Fvp = add3( Fvp, stt_gradient_term<NB_T>( p, l, a.sp, site, spi ) );
-            if( frozen )
+            if( site_frozen( g ) )
                 Fvp = make_d3( 0, 0, 0 );
             if( HOOK && last_stage )
                 e = site_energy<NB_T>( p, site, spi, g );
@@ -445,7 +445,7 @@ static __global__ void __launch_bounds__( BLOCK_THREADS ) k_vp_a(
         const D3 si             = load3( s, site.idx );
         const SiteGradient g    = site_gradient<NB_T>( p, s, ddi, site, si );
         const D3 gt             = total( g );
-        const D3 Fn             = site_frozen( p, site ) ? make_d3( 0, 0, 0 ) : make_d3( -gt.x, -gt.y, -gt.z );
+        const D3 Fn             = site_frozen( g ) ? make_d3( 0, 0, 0 ) : make_d3( -gt.x, -gt.y, -gt.z );
         // velocity of the last iteration = ratio_prev * (raw force of the last iteration); F_prev is the same force,
         // or its tangential projection if a post-iteration hook ran in between (SURVEY.md 8c hazard 6)
         const D3 Fr             = load3( F, site.idx );
@@ -563,7 +563,7 @@ static __global__ void __launch_bounds__( BLOCK_THREADS ) k_force_and_virtual(
             xi = thermal_field<NB_T>( p, l, site );
         const SiteGradient g = site_gradient<NB_T>( p, s, ddi, site, si );
         const D3 gt          = total( g );
-        const bool frozen    = site_frozen( p, site );
+        const bool frozen    = site_frozen( g );
         const D3 F           = frozen ? make_d3( 0, 0, 0 ) : make_d3( -gt.x, -gt.y, -gt.z );
         store3( F_out, site.idx, F );
         D3 Fv = virtual_force<NB_T>( l, site, si, F, xi );

@@ -111,10 +111,13 @@ struct SiteGradient
 {
     D3 bilinear; // anisotropy + exchange + DMI (+ DDI field if present)
     D3 rest;     // cubic anisotropy + Zeeman
+    unsigned flags; // FLAG_* of the site (0 on a lattice without pinned sites / defects)
 };
 
-template<int NB_T>
-__device__ __forceinline__ D3 pair_gradient( const StencilParams & p, const ConstField3 & s, const Site & site )
+// WITH_FLAGS: the lattice has vacancies to test for (a second copy of the loop, so that the loop of a plain lattice keeps its
+// independent, predicated neighbour loads: with the flag test in the one loop the film iteration went 5.3 -> 7.1 ms, profiles/r2zi)
+template<int NB_T, bool WITH_FLAGS>
+__device__ __forceinline__ D3 pair_gradient_loop( const StencilParams & p, const ConstField3 & s, const Site & site )
 {
     D3 g           = make_d3( 0, 0, 0 );
     const int NB   = NB_T > 0 ? NB_T : p.NB;
@@ -173,7 +176,7 @@ __device__ __forceinline__ D3 pair_gradient( const StencilParams & p, const Cons
         if( valid )
         {
             const int j = storage_index( p, ja * NB + nb.jb, jb, jc );
-            if( p.site_flags && ( __ldg( p.site_flags + j ) & FLAG_VACANT ) )
+            if( WITH_FLAGS && ( __ldg( p.site_flags + j ) & FLAG_VACANT ) )
                 continue; // idx_from_pair: the pair does not exist
             const D3 sj = load3( s, j );
             // g -= J s_j + s_j x D
@@ -186,17 +189,25 @@ __device__ __forceinline__ D3 pair_gradient( const StencilParams & p, const Cons
 }
 
 template<int NB_T>
+__device__ __forceinline__ D3 pair_gradient( const StencilParams & p, const ConstField3 & s, const Site & site )
+{
+    if( p.site_flags )
+        return pair_gradient_loop<NB_T, true>( p, s, site );
+    return pair_gradient_loop<NB_T, false>( p, s, site );
+}
+
+template<int NB_T>
 __device__ __forceinline__ SiteGradient
 site_gradient( const StencilParams & p, const ConstField3 & s, const ConstField3 & ddi, const Site & site, const D3 & si )
 {
     SiteGradient out;
     const int ib = NB_T == 1 ? 0 : site.ib;
+    // Site flags enter as factors, not as branches: an early return for vacancies keeps ptxas from issuing the loads of a
+    // site together (k_vp_a on the 2048 x 2048 x 4 film: 0.53 -> 2.36 ms, long-scoreboard stalls per issue 5 -> 47, profiles/r2zk)
     const unsigned flags = p.site_flags ? __ldg( p.site_flags + site.idx ) : 0u;
-    if( flags & FLAG_VACANT )
-    {
-        out.bilinear = out.rest = make_d3( 0, 0, 0 );
-        return out;
-    }
+    out.flags            = flags;
+    const double present = ( flags & FLAG_VACANT ) ? 0.0 : 1.0;                    // vacancy: every term vanishes
+    const double moment  = ( flags & ( FLAG_VACANT | FLAG_NO_MU_S ) ) ? 0.0 : 1.0; // no moment: no Zeeman, no dipolar term
 
     D3 g = pair_gradient<NB_T>( p, s, site );
 
@@ -213,13 +224,24 @@ site_gradient( const StencilParams & p, const ConstField3 & s, const ConstField3
         }
     }
     // Dipole-dipole field, precomputed by the FFT convolution for this configuration
-    if( p.has_ddi && !( flags & FLAG_NO_MU_S ) )
+    if( p.has_ddi )
     {
         const D3 gd = load3( ddi, site.idx );
-        g.x += gd.x;
-        g.y += gd.y;
-        g.z += gd.z;
+        if( p.site_flags )
+        {
+            g.x += moment * gd.x;
+            g.y += moment * gd.y;
+            g.z += moment * gd.z;
+        }
+        else
+        {
+            g.x += gd.x;
+            g.y += gd.y;
+            g.z += gd.z;
+        }
     }
+    if( p.site_flags )
+        g = make_d3( present * g.x, present * g.y, present * g.z );
     out.bilinear = g;
 
     D3 r = make_d3( 0, 0, 0 );
@@ -232,11 +254,22 @@ site_gradient( const StencilParams & p, const ConstField3 & s, const ConstField3
         r.z -= k * si.z * si.z * si.z;
     }
     // Zeeman: g -= mu_s B n   (Hamiltonian_Heisenberg.cpp:768-783)
-    if( p.has_zeeman && !( flags & FLAG_NO_MU_S ) )
+    if( p.site_flags )
+        r = make_d3( present * r.x, present * r.y, present * r.z );
+    if( p.has_zeeman )
     {
-        r.x -= p.zeeman[ib][0];
-        r.y -= p.zeeman[ib][1];
-        r.z -= p.zeeman[ib][2];
+        if( p.site_flags )
+        {
+            r.x -= moment * p.zeeman[ib][0];
+            r.y -= moment * p.zeeman[ib][1];
+            r.z -= moment * p.zeeman[ib][2];
+        }
+        else
+        {
+            r.x -= p.zeeman[ib][0];
+            r.y -= p.zeeman[ib][1];
+            r.z -= p.zeeman[ib][2];
+        }
     }
     out.rest = r;
     return out;
@@ -249,25 +282,25 @@ __device__ __forceinline__ double
 site_energy( const StencilParams & p, const Site & site, const D3 & si, const SiteGradient & g )
 {
     const int ib = NB_T == 1 ? 0 : site.ib;
-    const unsigned flags = p.site_flags ? __ldg( p.site_flags + site.idx ) : 0u;
-    if( flags & FLAG_VACANT )
-        return 0.0;
     double e = 0.5 * dot3( g.bilinear, si );
     if( p.has_cubic )
     {
         const double x2 = si.x * si.x, y2 = si.y * si.y, z2 = si.z * si.z;
         e -= 0.5 * p.K4[ib] * ( x2 * x2 + y2 * y2 + z2 * z2 );
     }
-    if( p.has_zeeman && !( flags & FLAG_NO_MU_S ) )
+    const unsigned flags = g.flags;
+    if( p.has_zeeman && !( flags & ( FLAG_VACANT | FLAG_NO_MU_S ) ) )
         e -= p.zeeman[ib][0] * si.x + p.zeeman[ib][1] * si.y + p.zeeman[ib][2] * si.z;
-    return e;
+    return ( flags & FLAG_VACANT ) ? 0.0 : e;
 }
 
 // force and virtual force of these sites are zero: pinned ones (mask_unpinned, Method_LLG.cpp:122-124, 222-224) and vacancies
-// (their gradient is zero; the reference's dynamics divide their virtual force by mu_s = 0)
-__device__ __forceinline__ bool site_frozen( const StencilParams & p, const Site & site )
+// (their gradient is zero; the reference's dynamics divide their virtual force by mu_s = 0). Taken from the flags site_gradient
+// loaded: a second look at p.site_flags after the gradient cost k_vp_a a factor 4.5 on the film (ptxas serialised the loads of
+// the site behind it; profiles/r2zk, r2zl)
+__device__ __forceinline__ bool site_frozen( const SiteGradient & g )
 {
-    return p.site_flags && ( __ldg( p.site_flags + site.idx ) & ( FLAG_VACANT | FLAG_PINNED ) );
+    return ( g.flags & ( FLAG_VACANT | FLAG_PINNED ) ) != 0u;
 }
 
 __device__ __forceinline__ D3 total( const SiteGradient & g )
