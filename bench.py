@@ -597,10 +597,14 @@ def run_b200(args):
             configs["c3"] = config_c3(product, tmp, peak)
             configs["c4"] = config_c4(product, tmp, peak)
         else:
-            parity = multi_gpu_parity(product, tmp, dist, rank, world)
+            # (the sharded chain is timed BEFORE the parity record: behind it the same 1000 iterations took 1.4 to 5 times longer
+            # in two runs on 2 GPUs, profiles/r2zm, r2zo -- something the slab / distributed-convolution sessions of the parity
+            # record leave behind costs the chain's ncclSend/Recv + all-reduces; the kernels are the same)
             if 64 % world == 0:
                 configs["c4"] = config_c4(product, tmp, peak, dist, rank, world)
         configs["c5"] = config_c5(product, tmp, peak, dist, rank, world)
+        if world > 1:
+            parity = multi_gpu_parity(product, tmp, dist, rank, world)
 
     # ---- check: the same step with the thermal variates shaped in fp64 (build variant libSpirit_xi64.so, own process) ----------
     checks = None
