@@ -108,7 +108,7 @@ try
     seg.valuedim     = 3;
     seg.valuelabels  = "position_x position_y position_z";
     seg.valueunits   = "none none none";
-    ovf::File( file ).write_segment( seg, &image->geometry->positions()[0].x, format );
+    ovf::File( file, ovf::File::ForWriting{} ).write_segment( seg, &image->geometry->positions()[0].x, format );
     Log( Log_Level::Info, Log_Sender::API, std::string( "Wrote positions to file \"" ) + file + "\"", idx_image, idx_chain );
 }
 SB_API_CATCH_VOID
@@ -142,7 +142,7 @@ try
     ImageLock lock( *image );
     check_format( format );
     warn_extension( file, idx_image, idx_chain );
-    ovf::File( file ).write_segment( spin_segment( *image, comment ), &image->spins[0].x, format );
+    ovf::File( file, ovf::File::ForWriting{} ).write_segment( spin_segment( *image, comment ), &image->spins[0].x, format );
     Log( Log_Level::Info, Log_Sender::API, std::string( "Wrote spins to file \"" ) + file + "\"", idx_image, idx_chain );
 }
 SB_API_CATCH_VOID
@@ -154,7 +154,7 @@ try
     ImageLock lock( *image );
     check_format( format );
     warn_extension( file, idx_image, idx_chain );
-    ovf::File( file ).append_segment( spin_segment( *image, comment ), &image->spins[0].x, format );
+    ovf::File( file, ovf::File::ForWriting{} ).append_segment( spin_segment( *image, comment ), &image->spins[0].x, format );
     Log( Log_Level::Info, Log_Sender::API, std::string( "Appended spins to file \"" ) + file + "\"", idx_image, idx_chain );
 }
 SB_API_CATCH_VOID
@@ -249,7 +249,7 @@ void chain_to_file( State * state, const char * file, int format, const char * c
     chain->Lock();
     try
     {
-        ovf::File f( file );
+        ovf::File f( file, ovf::File::ForWriting{} );
         for( int i = 0; i < chain->noi; ++i )
         {
             const std::string desc = "Image " + std::to_string( i + 1 ) + " of " + std::to_string( chain->noi ) + ". " + comment;
@@ -329,7 +329,7 @@ try
         seg.valueunits += " meV";
     }
     seg.valuedim = width;
-    ovf::File( file ).write_segment( seg, data.data(), format );
+    ovf::File( file, ovf::File::ForWriting{} ).write_segment( seg, data.data(), format );
     Log( Log_Level::Info, Log_Sender::API, std::string( "Wrote energies per spin to file \"" ) + file + "\"", idx_image, idx_chain );
 }
 SB_API_CATCH_VOID

@@ -356,7 +356,7 @@ void Method_LLG::Save_Current( bool initial, bool final )
             ovf::Segment seg = io::spin_segment(
                 *system, "LLG simulation (" + SolverFullName() + " solver)\n# Desc:      Iteration: " + std::to_string( iteration )
                              + "\n# Desc:      Maximum torque: " + io::shortest( max_torque ) );
-            ovf::File file( spins + suffix + ".ovf" );
+            ovf::File file( spins + suffix + ".ovf", ovf::File::ForWriting{} );
             if( append )
                 file.append_segment( seg, system->spins.scalars(), P.output_vf_filetype );
             else

@@ -171,7 +171,7 @@ void Method_GNEB::Save_Current( bool initial, bool final )
     {
         try
         {
-            ovf::File file( pre + suffix + ".ovf" );
+            ovf::File file( pre + suffix + ".ovf", ovf::File::ForWriting{} );
             for( int i = 0; i < chain->noi; ++i )
             {
                 const ovf::Segment seg = io::spin_segment(

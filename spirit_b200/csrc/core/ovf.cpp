@@ -190,6 +190,70 @@ File::File( const std::string & file_name ) : name( file_name )
     scan();
 }
 
+File::File( const std::string & file_name, ForWriting ) : name( file_name )
+{
+    scan_head();
+}
+
+// What a writer needs to know of an existing file, from its first bytes: is it there, is it empty, is it OVF 2.0, how many
+// segments does its header declare and where do the digits of that count stand. A header without a count line (or anything
+// else unexpected) falls back to the full scan.
+void File::scan_head()
+{
+    found = is_ovf = false;
+    n_segments     = 0;
+    count_pos_     = std::string::npos;
+    head_only_     = true;
+    empty_         = false;
+    segments_.clear();
+    contents_.clear();
+    std::ifstream in( name, std::ios::binary );
+    if( !in )
+    {
+        message = "file not found";
+        return;
+    }
+    found = true;
+    std::string head( 4096, '\0' );
+    in.read( &head[0], std::streamsize( head.size() ) );
+    head.resize( std::size_t( in.gcount() ) );
+    empty_ = head.empty();
+    if( empty_ )
+        return;
+    std::size_t pos = 0;
+    std::string line, key, value;
+    bool version_ok = false;
+    while( pos < head.size() )
+    {
+        pos = next_line( head, pos, line );
+        if( trim( line ).empty() )
+            continue;
+        const std::string l = lower( line );
+        version_ok          = l.find( "oommf" ) != std::string::npos && l.find( "ovf" ) != std::string::npos && l.find( "2.0" ) != std::string::npos;
+        break;
+    }
+    while( version_ok && pos < head.size() )
+    {
+        const std::size_t line_start = pos;
+        pos                          = next_line( head, pos, line );
+        if( !key_value( line, key, value ) )
+            continue;
+        if( key == "segment count" && pos < head.size() ) // (the whole line lies inside the bytes read)
+        {
+            const std::size_t c = head.find( ':', line_start );
+            count_pos_          = head.find_first_of( "0123456789", c );
+            n_segments          = std::atoi( value.c_str() );
+            is_ovf              = count_pos_ != std::string::npos;
+            contents_           = head;
+            if( is_ovf )
+                return;
+        }
+        break;
+    }
+    scan(); // not the header this library and the reference write: look at the whole file
+    head_only_ = false;
+}
+
 void File::scan()
 {
     found = is_ovf = false;
@@ -299,6 +363,8 @@ void File::scan()
 
 Segment File::read_segment_header( int index ) const
 {
+    if( head_only_ )
+        throw std::logic_error( "ovf::File opened for writing cannot be read" );
     if( !is_ovf )
         throw std::runtime_error( "file \"" + name + "\" is not in OVF format: " + message );
     if( index < 0 || index >= n_segments )
@@ -446,13 +512,25 @@ void File::write_segment( const Segment & segment, const double * data, int form
         throw std::runtime_error( "cannot open \"" + name + "\" for writing" );
     out << top_header( 1 ) << body;
     out.close();
+    if( head_only_ )
+    {
+        // what scan_head() would find, without reading the file back
+        found = is_ovf = true;
+        empty_         = false;
+        n_segments     = 1;
+        contents_      = top_header( 1 );
+        const std::size_t c = contents_.find( ':', lower( contents_ ).find( "segment count" ) );
+        count_pos_          = contents_.find_first_of( "0123456789", c );
+        return;
+    }
     scan();
 }
 
 void File::append_segment( const Segment & segment, const double * data, int format )
 {
-    scan();
-    if( !found || contents_.empty() )
+    if( !head_only_ )
+        scan();
+    if( !found || ( head_only_ ? empty_ : contents_.empty() ) )
     {
         write_segment( segment, data, format );
         return;
@@ -479,9 +557,14 @@ void File::append_segment( const Segment & segment, const double * data, int for
             std::fstream patch( name, std::ios::binary | std::ios::in | std::ios::out );
             patch.seekp( std::streamoff( count_pos_ ) );
             patch.write( buf, std::streamsize( digits ) );
+            if( head_only_ )
+                contents_.replace( count_pos_, digits, buf );
         }
     }
-    scan();
+    if( head_only_ )
+        ++n_segments; // (the next append of a chain continues from here: no pass over the file)
+    else
+        scan();
 }
 
 } // namespace ovf

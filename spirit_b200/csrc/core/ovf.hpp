@@ -40,6 +40,12 @@ class File
 {
 public:
     explicit File( const std::string & name );
+    // A file that is only going to be written or appended to: only its top header is read (version line and segment count), so
+    // that appending to an archive does not cost a pass over everything written so far. The read_* calls are not available.
+    struct ForWriting
+    {
+    };
+    File( const std::string & name, ForWriting );
     bool found = false, is_ovf = false;
     int n_segments = 0;
     std::string name, message;
@@ -61,7 +67,11 @@ private:
     std::vector<Span> segments_;
     std::size_t count_pos_ = 0; // position of the six digits of the segment count
     std::string contents_;
+    bool head_only_ = false; // ForWriting: contents_ holds the first bytes of the file only, segments_ stays empty
+    bool empty_     = false;
     void scan();
+    void scan_head();
+    void adopt_head( const std::string & head, int segments );
 };
 
 } // namespace ovf
