@@ -22,6 +22,10 @@ Reference locations (relative to /root/reference/core):
   constants                 include/utility/Constants.hpp:18-46
   topological charge        src/engine/Vectormath.cpp:462-472,504-631
   dipolar direct sum        src/engine/Hamiltonian_Heisenberg.cpp:1016-1071
+  pinning / defects         include/engine/Vectormath.hpp:406-528 (check_atom_type in idx_from_pair and in every on-site term),
+                            src/data/Geometry.cpp:72-82 (mu_s = 0 at defect sites), src/engine/Method_LLG.cpp:122-124, 222-224
+                            (mask_unpinned on gradient and virtual force) -- pinned against the reference built with
+                            -DSPIRIT_ENABLE_PINNING -DSPIRIT_ENABLE_DEFECTS (oracle/_ref/libSpirit_ref_pd.so)
 """
 import numpy as np
 
@@ -35,16 +39,24 @@ class Model:
     uniaxial K along Kn, cubic K4, field B (Tesla) along Bn, mu_s (mu_B)."""
 
     def __init__(self, n, bc, J=10.0, D=6.0, B=25.0, Bn=(0, 0, 1), mu_s=2.0, K=0.0, Kn=(0, 0, 1), K4=0.0,
-                 dt=1e-3, alpha=0.3):
+                 dt=1e-3, alpha=0.3, atom_types=None, defect_sites=None, pinned=None):
         self.n, self.bc = tuple(n), tuple(bc)
         self.J, self.D, self.B, self.Bn = J, D, B, np.asarray(Bn, float)
         self.mu_s, self.K, self.Kn, self.K4 = mu_s, K, np.asarray(Kn, float), K4
         self.dt, self.alpha = dt, alpha
+        # per-site masks in the reference's site order (a fastest): present = atom type >= 0 (check_atom_type), moment =
+        # mu_s != 0 (zero at EVERY defect site, whatever its type), free = mask_unpinned
+        nos = int(np.prod(self.n))
+        types = np.zeros(nos, int) if atom_types is None else np.asarray(atom_types, int)
+        self.present = types >= 0
+        self.moment = np.ones(nos, bool) if defect_sites is None else ~np.asarray(defect_sites, bool)
+        self.free = np.ones(nos, bool) if pinned is None else ~np.asarray(pinned, bool)
 
     # ---- Hamiltonian ----------------------------------------------------------------------------------------------
     def pair_gradient(self, S):
         """exchange + DMI, S shaped (Nc, Nb, Na, 3): g_i -= J s_j + D s_j x d_ij over the (redundant) neighbours"""
         g = np.zeros_like(S)
+        present = self.present.reshape(S.shape[:3])
         for axis, (N, per) in zip((2, 1, 0), zip(self.n, self.bc)):
             d = np.zeros(3)
             d[2 - axis] = 1.0
@@ -52,7 +64,7 @@ class Model:
                 if N == 1 and not per:
                     continue
                 Sj = np.roll(S, -sign, axis=axis)
-                mask = np.ones(S.shape[:3], bool)
+                mask = present & np.roll(present, -sign, axis=axis)  # idx_from_pair: both atoms of the pair must be there
                 if not per:
                     idx = [slice(None)] * 3
                     idx[axis] = (N - 1) if sign > 0 else 0
@@ -63,11 +75,12 @@ class Model:
     def gradient_and_energy(self, s):
         Na, Nb, Nc = self.n
         S = s.reshape(Nc, Nb, Na, 3)
+        here = self.present.reshape(Nc, Nb, Na, 1)
         gp = self.pair_gradient(S)
-        ga = -2 * self.K * (S @ self.Kn)[..., None] * self.Kn
-        gc = -2 * self.K4 * S ** 3
-        gz = -self.mu_s * mu_B * self.B * self.Bn * np.ones_like(S)
-        E = 0.5 * np.sum((gp + ga) * S) - 0.5 * self.K4 * np.sum(S ** 4) + np.sum(gz * S)
+        ga = -2 * self.K * (S @ self.Kn)[..., None] * self.Kn * here
+        gc = -2 * self.K4 * S ** 3 * here
+        gz = -self.mu_s * mu_B * self.B * self.Bn * np.ones_like(S) * (here & self.moment.reshape(Nc, Nb, Na, 1))
+        E = 0.5 * np.sum((gp + ga) * S) - 0.5 * self.K4 * np.sum(S ** 4 * here) + np.sum(gz * S)
         return (gp + ga + gc + gz).reshape(-1, 3), E
 
     def gradient(self, s):
@@ -76,11 +89,11 @@ class Model:
     # ---- LLG ------------------------------------------------------------------------------------------------------------
     def virtual_force(self, s, xi=None):
         dtg = self.dt * gamma / mu_B / (1 + self.alpha ** 2)
-        F = -self.gradient(s)
+        F = -self.gradient(s) * self.free[:, None]  # Method_LLG.cpp:122-124
         fv = (dtg * F + dtg * self.alpha * np.cross(s, F)) / self.mu_s
         if xi is not None:
             fv = fv + xi + self.alpha * np.cross(s, xi)
-        return fv
+        return fv * self.free[:, None]  # Method_LLG.cpp:222-224
 
     def thermal_amplitude(self, T):
         """epsilon * sqrt(T / mu_s), Method_LLG.cpp:74-75,105"""

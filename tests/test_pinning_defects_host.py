@@ -65,6 +65,45 @@ def test_set_pinned_and_set_atom_type(product, oracle_pd, cfg):
         x.close()
 
 
+def test_restatement_with_defects_and_pinning_matches_the_reference(oracle_pd, cfg):
+    """pins the masks of oracle/restatement.py (vacancies in the pair terms and the on-site terms, no moment at defect sites,
+    pinned sites under Depondt dynamics) to the compiled reference with both options"""
+    from oracle import restatement as R
+    from tests.test_parity_gpu import unit_random
+    n = (9, 7, 3)
+    o = S.Session(oracle_pd, cfg("cubic256", n_basis_cells="%d %d %d" % n, boundary_conditions="1 0 1", external_field_magnitude="7",
+                                 block=["n_defects 3", "0 4 4 0 -1", "0 7 2 1 -1", "0 3 5 2 2"]))
+    types = o.atom_types()
+    defect = np.zeros(o.nos, bool)
+    for a, b, c in ((4, 4, 0), (7, 2, 1), (3, 5, 2)):
+        defect[a + n[0] * (b + n[1] * c)] = True
+    m = R.Model(n, (1, 0, 1), J=10.0, D=6.0, B=7.0, mu_s=2.0, K=1.0, atom_types=types, defect_sites=defect)
+    s = unit_random(o.nos, 21)
+    go, eo = o.gradient_and_energy(s)
+    gr, er = m.gradient_and_energy(s)
+    assert np.abs(gr - go).max() <= 1e-12 * np.abs(go).max()
+    assert abs(er - eo) <= 1e-12 * abs(eo)
+    o.close()
+    # pinned boundary layers and one pinned site, three Depondt steps
+    o = S.Session(oracle_pd, cfg("cubic256", n_basis_cells="%d %d %d" % n, boundary_conditions="1 0 1", external_field_magnitude="7",
+                                 llg_temperature=0, block=["pin_na_left 2", "pin_nc_right 1", "pinning_cell", "0 0 1", "n_pinned 1", "0 5 3 1  1 0 0"]))
+    a, b, c = np.meshgrid(np.arange(n[0]), np.arange(n[1]), np.arange(n[2]), indexing="ij")
+    pinned = ((a < 2) | (c >= n[2] - 1) | ((a == 5) & (b == 3) & (c == 1))).transpose(2, 1, 0).reshape(-1)
+    f32 = lambda x: float(np.float32(x))  # the C API narrows dt and damping to float (SURVEY.md 8c hazard 5)
+    m = R.Model(n, (1, 0, 1), J=10.0, D=6.0, B=7.0, mu_s=2.0, K=1.0, dt=f32(1e-3), alpha=f32(0.3), pinned=pinned)
+    o.llg_set(temperature=0.0, damping=0.3, dt=1e-3)
+    o.set_spins(s)
+    o.llg_start(S.SOLVER_DEPONDT, single_shot=True)
+    o.n_shot(3)
+    sr = s
+    for _ in range(3):
+        sr = m.depondt(sr)
+    assert np.abs(o.spins() - s).max() > 1e-4 and np.abs(sr - o.spins()).max() < 1e-12
+    assert np.array_equal(o.spins()[pinned], s[pinned])
+    o.stop()
+    o.close()
+
+
 def test_disordered_cell_is_refused(product, cfg):
     path = cfg("default", n_basis_cells="4 4 1", block=["atom_types 1", "0 1 2.0 0.5"])
     assert not product.State_Setup(path.encode(), True)
