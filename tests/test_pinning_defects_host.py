@@ -44,6 +44,24 @@ def test_defects_from_config(product, oracle_pd, cfg):
         x.close()
 
 
+def test_tables_from_separate_files(product, oracle_pd, cfg, tmp_path):
+    """pinned_from_file / defects_from_file: tables without a count line, read from the top of their own files"""
+    pinned = tmp_path / "pinned.txt"
+    pinned.write_text("0 1 1 0   0 1 0\n0 2 3 1   -1 0 0\n0 9 7 1   0 0 -1\n")
+    defects = tmp_path / "defects.txt"
+    defects.write_text("0 0 0 0 -1\n0 5 5 1 -1\n0 6 1 0 4\n")
+    path = cfg("default", n_basis_cells="10 8 2", block=["pinned_from_file %s" % pinned, "defects_from_file %s" % defects])
+    p, o = both(product, oracle_pd, path)
+    np.testing.assert_array_equal(p.atom_types(), o.atom_types())
+    assert sorted(o.atom_types()[o.atom_types() != 0].tolist()) == [-1, -1, 4]
+    for x in (p, o):
+        x.plus_z()
+    np.testing.assert_array_equal(p.spins(), o.spins())
+    assert (np.any(o.spins() != np.array([0.0, 0.0, 1.0]), axis=1)).sum() == 3
+    for x in (p, o):
+        x.close()
+
+
 def test_set_pinned_and_set_atom_type(product, oracle_pd, cfg):
     path = cfg("default", n_basis_cells="12 12 1")
     p, o = both(product, oracle_pd, path)
