@@ -21,10 +21,14 @@
 // Every pass is a batch of shared-memory FFTs, `ncol` adjacent transforms per CTA so that strided passes still move
 // contiguous segments. Two families of kernels serve them:
 //   * power-of-two lengths 64 ... 4096 (every zero-padded power-of-two lattice): k_ddi_fwd_a16 / k_ddi_inv_a16 (real rows as
-//     complex sequences of half the length), k_fft_pass16, k_ddi_c_mult16 -- instantiated per length (block_fft_ct: stage
+//     complex sequences of half the length), k_fft_pass16r, k_ddi_c_mult16f -- instantiated per length (block_fft_ct: stage
 //     loop unrolled at compile time), radix-8 butterflies in registers, IN PLACE in one padded shared buffer, twiddles of a
 //     butterfly as powers of one table entry, tensor spectrum real (one sublattice) and stored in the c-pass's tile order;
-//     thin films (Pc <= 32) do the c-transforms in registers (k_ddi_c_mult_small);
+//     the b- and c-passes start their first stage on the loaded registers and store from their last butterflies, the c-pass
+//     multiplies with the tensor between its forward last and inverse first stage without leaving the registers
+//     (k_fft_pass16 / k_ddi_c_mult16 are the same passes with every stage through shared memory: tuning builds with other
+//     radices, SPIRIT_B200_FFT_PASS_REG=0 / SPIRIT_B200_DDI_C_FUSED=0); thin films (Pc <= 32) do the c-transforms in
+//     registers (k_ddi_c_mult_small);
 //   * any other length and any basis: k_ddi_fwd_a, k_fft_pass, k_ddi_c_mult, k_ddi_inv_a -- mixed-radix (4 / 2 / generic
 //     prime) Stockham passes between two shared buffers.
 // Slabs over several GPUs: the kb axis of B is cut into per-rank blocks, the all-to-alls travel one component at a time on
