@@ -62,7 +62,10 @@ void read_spins( const ovf::File & file, int idx_in_file, Spin_System & image, i
     {
         Vec3 & s = image.spins[i];
         if( s.norm() < 1e-5 )
+        {
             s = Vec3{ 0, 0, 1 };
+            image.geometry->set_vacancy_read_from_file( i ); // IO.cpp:268-272 (defects are always built here)
+        }
         else
             s.normalize();
     }
@@ -77,7 +80,10 @@ void read_spins_columns( const std::vector<double> & rows, int idx_in_file, Spin
     {
         Vec3 & s = image.spins[i];
         if( s.norm() < 1e-5 )
+        {
             s = Vec3{ 0, 0, 1 };
+            image.geometry->set_vacancy_read_from_file( i ); // Dataparser.cpp:39-46
+        }
         else
             s.normalize();
     }

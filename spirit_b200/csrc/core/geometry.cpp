@@ -198,6 +198,17 @@ void Geometry::set_atom_type( int ispin, int type )
     ++site_revision;
 }
 
+void Geometry::set_vacancy_read_from_file( int ispin )
+{
+    need_site_flags();
+    atom_types();
+    if( _atom_types[ispin] == -1 && ( site_flags[ispin] & SITE_VACANT ) )
+        return;
+    _atom_types[ispin] = -1;
+    site_flags[ispin] |= SITE_VACANT; // (mu_s and nos_nonvacant stay as they are: the reference sets the atom type only)
+    ++site_revision;
+}
+
 void Geometry::apply_pinning( Vec3 * spins ) const
 {
     if( site_flags.empty() )

@@ -93,6 +93,7 @@ struct Geometry
     void set_pinning_and_defects( const Pinning & pinning, const Defects & defects );
     void set_pinned( int ispin, bool pinned, const Vec3 & orientation ); // Configurations::Set_Pinned, Configurations.cpp:583-599
     void set_atom_type( int ispin, int type );                           // Configurations::Set_Atom_Types, :567-581
+    void set_vacancy_read_from_file( int ispin ); // a (near-)zero vector in a spin file: atom type -1, moment kept (IO.cpp:265-275)
     void apply_pinning( Vec3 * spins ) const;
     bool has_site_flags() const
     {

@@ -62,6 +62,29 @@ def test_tables_from_separate_files(product, oracle_pd, cfg, tmp_path):
         x.close()
 
 
+def test_zero_vectors_in_spin_files_become_vacancies(product, oracle_pd, cfg, tmp_path):
+    """IO_Image_Read of an OVF file and of a plain column file with (near-)zero vectors: +z spins, atom type -1 (IO.cpp:265-275,
+    Dataparser.cpp:39-46 of a build with defects)"""
+    from tests.test_io import HAND
+    rng = np.random.default_rng(5)
+    v = rng.standard_normal((8, 3))
+    v[2] = 0.0
+    v[6] = 1e-7
+    rows = "\n".join("%.17g %.17g %.17g" % tuple(r) for r in v)
+    ovf_file, col_file = tmp_path / "z.ovf", tmp_path / "z.txt"
+    ovf_file.write_text(HAND % (rows, rows.replace(" ", ", ")))
+    col_file.write_text(rows + "\n")
+    for f in (ovf_file, col_file):
+        p, o = both(product, oracle_pd, cfg("default", n_basis_cells="4 2 1"))
+        for x in (p, o):
+            x.image_read(f, 0)
+        np.testing.assert_array_equal(p.spins(), o.spins())
+        np.testing.assert_array_equal(p.atom_types(), o.atom_types())
+        assert (o.atom_types() == -1).sum() == 2 and np.array_equal(o.spins()[2], [0, 0, 1])
+        for x in (p, o):
+            x.close()
+
+
 def test_set_pinned_and_set_atom_type(product, oracle_pd, cfg):
     path = cfg("default", n_basis_cells="12 12 1")
     p, o = both(product, oracle_pd, path)
